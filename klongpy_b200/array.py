@@ -1,0 +1,236 @@
+"""DeviceArray — the array type of the B200 backend (what `backend.np.ndarray` names).
+
+A thin wrapper over a device-resident `torch.Tensor` used purely as the memory container (allocation, views,
+H2D/D2H copies, autograd interop).  Every arithmetic / comparison / indexing method the KlongPy verbs invoke
+directly on array objects (`x*1` in kg_truth types.py:339-340, `a - 1` adverbs.py:206,
+`.trunc()`, `==`, `.all()` dyads.py:754-755, slicing dyads.py:261, 1029-1031, `.astype(int)` base.py:203 ...)
+is routed to the CUDA library through `klongpy_b200.ops`; no torch compute op sits on that path.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+
+_NP2T = {
+    np.dtype("float64"): torch.float64,
+    np.dtype("int64"): torch.int64,
+    np.dtype("float32"): torch.float32,
+    np.dtype("int32"): torch.int32,
+    np.dtype("bool"): torch.bool,
+}
+_T2NP = {v: k for k, v in _NP2T.items()}
+_T2K = {torch.float64: _lib.F64, torch.int64: _lib.I64, torch.float32: _lib.F32, torch.int32: _lib.I32,
+        torch.bool: _lib.B8}
+_K2T = {v: k for k, v in _T2K.items()}
+
+
+def torch_dtype_of(np_dtype):
+    d = np.dtype(np_dtype)
+    if d in _NP2T:
+        return _NP2T[d]
+    if d.kind in "iu":
+        return torch.int64
+    if d.kind == "f":
+        return torch.float64
+    if d.kind == "b":
+        return torch.bool
+    raise TypeError(f"dtype {d} cannot live on the device")
+
+
+def kgb_dtype(t):
+    try:
+        return _T2K[t.dtype]
+    except KeyError:
+        raise TypeError(f"tensor dtype {t.dtype} is not supported by libkgb200") from None
+
+
+class DeviceArray:
+    """N-d array living in B200 HBM.  Immutable from the verbs' point of view (results are fresh arrays)."""
+
+    __slots__ = ("_t", "__weakref__")
+    __array_priority__ = 1000
+    __array_ufunc__ = None  # numpy scalars defer to our reflected operators
+    __hash__ = None
+
+    def __init__(self, tensor):
+        if not isinstance(tensor, torch.Tensor):
+            raise TypeError("DeviceArray wraps a torch.Tensor")
+        self._t = tensor
+
+    # ------------------------------------------------------------------ metadata (no device work)
+    @property
+    def shape(self):
+        return tuple(self._t.shape)
+
+    @property
+    def ndim(self):
+        return self._t.dim()
+
+    @property
+    def size(self):
+        return self._t.numel()
+
+    @property
+    def dtype(self):
+        return _T2NP[self._t.dtype]
+
+    @property
+    def device(self):
+        return self._t.device
+
+    @property
+    def tensor(self):
+        """The underlying torch.Tensor (autograd / DLPack interop)."""
+        return self._t
+
+    @property
+    def requires_grad(self):
+        return self._t.requires_grad
+
+    @property
+    def T(self):
+        return DeviceArray(self._t.T)
+
+    def __len__(self):
+        if self._t.dim() == 0:
+            raise TypeError("len() of unsized object")
+        return self._t.shape[0]
+
+    def __repr__(self):
+        return f"DeviceArray({self.to_numpy()!r}, device='{self._t.device}')"
+
+    # ------------------------------------------------------------------ host transfer (explicit syncs)
+    def to_numpy(self):
+        return self._t.detach().cpu().numpy()
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.to_numpy()
+        return a.astype(dtype) if dtype is not None else a
+
+    def tolist(self):
+        return self.to_numpy().tolist()
+
+    def item(self):
+        if self._t.numel() != 1:
+            raise ValueError("can only convert an array of size 1 to a Python scalar")
+        return self._t.item()
+
+    def __bool__(self):
+        if self._t.numel() != 1:
+            raise ValueError("The truth value of an array with more than one element is ambiguous. "
+                             "Use a.any() or a.all()")
+        return bool(self._t.item())
+
+    def __int__(self):
+        return int(self.item())
+
+    def __float__(self):
+        return float(self.item())
+
+    def __index__(self):
+        if self._t.dtype not in (torch.int64, torch.int32):
+            raise TypeError("only integer scalar arrays can be converted to a scalar index")
+        return int(self.item())
+
+    def __iter__(self):
+        if self._t.dim() == 0:
+            raise TypeError("iteration over a 0-d array")
+        if self._t.dim() == 1:
+            # one D2H copy, then numpy scalars like ndarray iteration
+            return iter(self.to_numpy())
+        return (DeviceArray(self._t[i]) for i in range(self._t.shape[0]))
+
+    # ------------------------------------------------------------------ views (metadata only)
+    def reshape(self, *shape):
+        if len(shape) == 1 and isinstance(shape[0], (tuple, list)):
+            shape = tuple(shape[0])
+        from . import ops
+        return DeviceArray(ops.contiguous(self)._t.reshape(*shape))
+
+    def flatten(self):
+        from . import ops
+        return DeviceArray(ops.contiguous(self)._t.reshape(-1))
+
+    ravel = flatten
+
+    def copy(self):
+        from . import ops
+        return ops.copy(self)
+
+    def astype(self, dtype, copy=True):
+        from . import ops
+        return ops.astype(self, dtype)
+
+    def __getitem__(self, key):
+        from . import ops
+        return ops.getitem(self, key)
+
+    # ------------------------------------------------------------------ arithmetic -> fused kernels
+    def _bin(self, other, op, reflected=False):
+        from . import ops
+        if isinstance(other, (list, tuple)):
+            other = ops.asarray(other, device=self._t.device)
+        if not ops.is_operand(other):
+            return NotImplemented
+        return ops.binary(op, other, self) if reflected else ops.binary(op, self, other)
+
+    def __add__(self, o): return self._bin(o, "add")
+    def __radd__(self, o): return self._bin(o, "add", True)
+    def __sub__(self, o): return self._bin(o, "sub")
+    def __rsub__(self, o): return self._bin(o, "sub", True)
+    def __mul__(self, o): return self._bin(o, "mul")
+    def __rmul__(self, o): return self._bin(o, "mul", True)
+    def __truediv__(self, o): return self._bin(o, "div")
+    def __rtruediv__(self, o): return self._bin(o, "div", True)
+    def __pow__(self, o): return self._bin(o, "pow")
+    def __rpow__(self, o): return self._bin(o, "pow", True)
+    def __mod__(self, o): return self._bin(o, "fmod")
+    def __lt__(self, o): return self._bin(o, "lt_b")
+    def __gt__(self, o): return self._bin(o, "gt_b")
+    def __le__(self, o): return self._bin(o, "le_b")
+    def __ge__(self, o): return self._bin(o, "ge_b")
+    def __eq__(self, o): return self._bin(o, "eq_b")
+    def __ne__(self, o): return self._bin(o, "ne_b")
+
+    def __neg__(self):
+        from . import ops
+        return ops.unary("neg", self)
+
+    def __pos__(self):
+        return self
+
+    def __abs__(self):
+        from . import ops
+        return ops.unary("abs", self)
+
+    def __invert__(self):
+        from . import ops
+        return ops.unary("not_b", self)
+
+    def trunc(self):
+        from . import ops
+        return ops.unary("trunc", self)
+
+    def all(self):
+        from . import ops
+        return ops.all_(self)
+
+    def any(self):
+        from . import ops
+        return ops.any_(self)
+
+    def sum(self, axis=None):
+        from . import ops
+        return ops.reduce("add", self)
+
+    def max(self, axis=None):
+        from . import ops
+        return ops.reduce("max", self)
+
+    def min(self, axis=None):
+        from . import ops
+        return ops.reduce("min", self)
+
+    def argsort(self, kind=None):
+        from . import ops
+        return ops.argsort(self)

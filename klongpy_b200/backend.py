@@ -1,0 +1,351 @@
+"""B200BackendProvider — the drop-in for KlongPy's backend seam.
+
+Implements the `BackendProvider` interface of `klongpy/backends/base.py:27-506` (15 abstract methods + the
+overridable defaults that matter: `compile_expr_ir`, `power`, `floor_to_int`, `to_int_array`, `safe_equal`,
+`array_equal`, autograd hooks).  Registration: `klongpy_b200.register()` calls
+`klongpy.backends.register_backend('b200', B200BackendProvider)` (`registry.py:23-25`), after which
+`KlongInterpreter(backend='b200', device='cuda:0')` constructs it (`interpreter.py:249`).
+
+When klongpy is importable the class derives from the reference's own ABC; on a box without klongpy (the GPU
+test box) it derives from a local mirror with the same method set, so parity tests can drive the provider
+with IR tuples captured from the real compiler (tests/golden/).
+"""
+import numpy as np
+import torch
+
+from . import _lib, lowering, ops
+from .array import DeviceArray
+from .npshim import B200Numpy
+
+try:  # the reference's own ABC when it is installed
+    from klongpy.backends.base import BackendProvider as _Base, UnsupportedDtypeError, is_jagged_array
+    HAVE_KLONGPY = True
+except Exception:  # pragma: no cover - exercised on the GPU box
+    HAVE_KLONGPY = False
+
+    class UnsupportedDtypeError(Exception):
+        """Raised when an operation requires a dtype the backend cannot hold (base.py:509-511)."""
+
+    def is_jagged_array(x):
+        if isinstance(x, list) and len(x) > 0:
+            if all(isinstance(item, (list, tuple)) for item in x):
+                return len(set(map(len, x))) > 1
+        return False
+
+    class _Base:
+        """Mirror of the non-abstract defaults of klongpy.backends.base.BackendProvider the hot path uses."""
+
+        def to_display(self, x):
+            if self.is_backend_array(x):
+                x = self.to_numpy(x)
+            if hasattr(x, "item") and hasattr(x, "ndim") and x.ndim == 0:
+                return x.item()
+            return x
+
+        def scalar_to_python(self, x):
+            return x.item() if hasattr(x, "item") else x
+
+        def is_integer(self, x):
+            if issubclass(type(x), (int, np.integer)):
+                return True
+            return self.is_scalar_integer(x)
+
+        def is_float(self, x):
+            if issubclass(type(x), (float, np.floating, int)):
+                return True
+            return self.is_scalar_float(x) or self.is_scalar_integer(x)
+
+        def is_number(self, a):
+            return self.is_float(a) or self.is_integer(a)
+
+        def str_to_chr_arr(self, s):
+            return self.str_to_char_array(s)
+
+        def vec_fn(self, a, f):
+            if self.np.isarray(a) and a.dtype == "O":
+                result = [self.vec_fn(x, f) if self._is_list(x) else f(x) for x in a]
+                return np.asarray(result, dtype=object)
+            return f(a)
+
+        def vec_fn2(self, a, b, f):
+            if self.np.isarray(a):
+                if a.dtype == "O":
+                    if self.np.isarray(b):
+                        assert len(a) == len(b)
+                        return self.kg_asarray([self.vec_fn2(x, y, f) for x, y in zip(a, b)])
+                    return self.kg_asarray([self.vec_fn2(x, b, f) for x in a])
+                elif self.np.isarray(b) and b.dtype == "O":
+                    assert len(a) == len(b)
+                    return self.kg_asarray([self.vec_fn2(x, y, f) for x, y in zip(a, b)])
+            elif self.np.isarray(b) and b.dtype == "O":
+                return self.kg_asarray([self.vec_fn2(a, x, f) for x in b])
+            return f(a, b)
+
+        def rec_fn(self, a, f):
+            return self.kg_asarray([self.rec_fn(x, f) for x in a]) if self._is_list(a) else f(a)
+
+        def get_info(self):
+            return {
+                "name": self.name, "device": self.device, "devices": self.list_devices(),
+                "supports_float64": self.supports_float64(), "supports_strings": self.supports_strings(),
+                "supports_object_dtype": self.supports_object_dtype(),
+                "supports_autograd": self.supports_autograd(),
+            }
+
+
+class KGChar(str):
+    """Character type (numpy_backend.py:16-18); the reference's class is used when available."""
+
+
+try:
+    from klongpy.backends.numpy_backend import KGChar  # noqa: F811
+except Exception:  # pragma: no cover
+    pass
+
+
+class B200BackendProvider(_Base):
+    """Array backend whose arrays live in B200 HBM and whose primitives are libkgb200 kernels."""
+
+    def __init__(self, device=None):
+        if device is None:
+            device = ops.default_device()
+        device = torch.device(device)
+        if device.type == "cuda" and device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        if device.type != "cuda" and _lib._host_double is None:
+            raise ValueError(f"Backend 'b200' needs a CUDA device, got '{device}' (there is no CPU fallback)")
+        self._device = device
+        if device.type == "cuda":
+            _lib.bind_device(device.index)  # fails loudly if the .so is missing or the GPU is not sm_100
+        ops.set_default_device(device)
+        self._np = B200Numpy(device)
+        self._compiled = {}
+
+    # ------------------------------------------------------------------ identity / capabilities
+    @property
+    def name(self):
+        return "b200"
+
+    @property
+    def np(self):
+        return self._np
+
+    @property
+    def device(self):
+        return str(self._device)
+
+    def list_devices(self):
+        return [f"cuda:{i}" for i in range(torch.cuda.device_count())]
+
+    def supports_object_dtype(self):
+        return False
+
+    def supports_strings(self):
+        return False
+
+    def supports_float64(self):
+        return True
+
+    def supports_autograd(self):
+        return True
+
+    # ------------------------------------------------------------------ array typing
+    def is_array(self, x):
+        return isinstance(x, (np.ndarray, DeviceArray))
+
+    def is_backend_array(self, x):
+        return isinstance(x, DeviceArray)
+
+    def _is_list(self, x):
+        if isinstance(x, DeviceArray):
+            return x.ndim > 0 and x.size > 0
+        if isinstance(x, np.ndarray):
+            return x.size > 0
+        if isinstance(x, (list, tuple)):
+            return len(x) > 0
+        return False
+
+    def get_dtype_kind(self, arr):
+        if hasattr(arr, "dtype") and hasattr(arr.dtype, "kind"):
+            return arr.dtype.kind
+        return None
+
+    def to_numpy(self, x):
+        return x.to_numpy() if isinstance(x, DeviceArray) else x
+
+    def is_scalar_integer(self, x):
+        if isinstance(x, DeviceArray) and x.ndim == 0:
+            return x.dtype.kind in "iu"
+        if isinstance(x, np.ndarray) and x.ndim == 0:
+            return np.issubdtype(x.dtype, np.integer)
+        return False
+
+    def is_scalar_float(self, x):
+        if isinstance(x, DeviceArray) and x.ndim == 0:
+            return x.dtype.kind == "f"
+        if isinstance(x, np.ndarray) and x.ndim == 0:
+            return np.issubdtype(x.dtype, np.floating)
+        return False
+
+    def array_size(self, a):
+        if isinstance(a, DeviceArray):
+            return a.size
+        if hasattr(a, "size"):
+            s = a.size
+            return s if isinstance(s, (int, np.integer)) else s()
+        return len(a) if hasattr(a, "__len__") else 1
+
+    def str_to_char_array(self, s):
+        # strings are host data (torch precedent torch_backend.py:802-806)
+        return np.asarray([KGChar(x) for x in s], dtype=object)
+
+    def kg_asarray(self, a):
+        """Literal lists -> device arrays (int -> int64, float -> float64: numpy_backend.py:180-198 typing, not
+        the torch backend's float32 demotion); strings / jagged / mixed data stay host object arrays like the
+        torch precedent (torch_backend.py:1086-1128)."""
+        if isinstance(a, DeviceArray):
+            return a
+        if isinstance(a, str):
+            return self.str_to_char_array(a)
+        if isinstance(a, np.ndarray):
+            if a.dtype.kind in "ifb":
+                return ops.asarray(a, device=self._device)
+            if a.dtype != object:
+                return a
+        try:
+            if is_jagged_array(a):
+                raise ValueError
+            if isinstance(a, (list, tuple)) and len(a) and all(isinstance(x, DeviceArray) for x in a):
+                shapes = {x.shape for x in a}
+                kinds = {x.dtype.kind for x in a}
+                if len(shapes) == 1 and kinds <= {"i", "f"}:
+                    return self._np.stack(a)
+                raise ValueError
+            conv = [x.to_numpy() if isinstance(x, DeviceArray) else x for x in a] \
+                if isinstance(a, (list, tuple)) else a
+            arr = np.asarray(conv)
+            if arr.dtype.kind not in "if":
+                raise ValueError
+            return ops.asarray(arr, device=self._device)
+        except (ValueError, TypeError):
+            try:
+                arr = np.empty(len(a), dtype=object)
+                for i, x in enumerate(a):
+                    arr[i] = self.kg_asarray(x) if isinstance(x, (list, tuple)) else x
+                return arr
+            except TypeError:
+                return a
+
+    # ------------------------------------------------------------------ primitives
+    def argsort(self, a, descending=False):
+        """Stable grade (writer.py:114-117 fast path)."""
+        if not isinstance(a, DeviceArray):
+            a = ops.asarray(a, device=self._device)
+        return ops.argsort(a, descending=descending)
+
+    def safe_equal(self, x, y):
+        if isinstance(x, DeviceArray) or isinstance(y, DeviceArray):
+            if isinstance(x, DeviceArray) and x.ndim == 0 and not isinstance(y, DeviceArray):
+                x = x.item()
+            if isinstance(y, DeviceArray) and y.ndim == 0 and not isinstance(x, DeviceArray):
+                y = y.item()
+            if isinstance(x, DeviceArray) or isinstance(y, DeviceArray):
+                if ops.is_operand(x) and ops.is_operand(y):
+                    return ops.binary("eq_b", x, y)
+                return False
+            return x == y
+        return np.asarray(x, dtype=object) == np.asarray(y, dtype=object)
+
+    def array_equal(self, a, b):
+        if isinstance(a, DeviceArray) and isinstance(b, DeviceArray):
+            return ops.array_equal(a, b)
+        return bool(np.array_equal(self.to_numpy(a), self.to_numpy(b)))
+
+    def kg_equal(self, a, b):
+        if a is b:
+            return True
+        if isinstance(a, DeviceArray) and isinstance(b, DeviceArray) and a.ndim > 0 and b.ndim > 0:
+            return self.array_equal(a, b)
+        if isinstance(a, DeviceArray):
+            a = a.to_numpy()
+        if isinstance(b, DeviceArray):
+            b = b.to_numpy()
+        if HAVE_KLONGPY:
+            return super().kg_equal(a, b)
+        return _np_kg_equal(self, a, b)
+
+    def detach_if_needed(self, x):
+        if isinstance(x, DeviceArray) and x.requires_grad:
+            return DeviceArray(x._t.detach())
+        return x
+
+    def has_gradient(self, x):
+        return isinstance(x, DeviceArray) and x.requires_grad
+
+    def to_int_array(self, a):
+        if isinstance(a, DeviceArray):
+            return ops.astype(a, np.int64)
+        return np.asarray(a, dtype=int) if isinstance(a, np.ndarray) else int(a)
+
+    def floor_to_int(self, a):
+        if isinstance(a, DeviceArray):
+            return ops.unary("floor_i64", a)
+        result = np.floor(np.asarray(a, dtype=float))
+        return result.astype(int) if hasattr(result, "astype") else int(result)
+
+    def power(self, a, b):
+        if isinstance(a, DeviceArray) or isinstance(b, DeviceArray):
+            if isinstance(a, (int, np.integer)):
+                a = float(a)  # base.py:205-212: python-int bases are promoted
+            return ops.binary("pow", a, b)
+        return np.power(float(a) if isinstance(a, (int, np.integer)) else a, b)
+
+    # ------------------------------------------------------------------ expression compiler hook
+    def compile_expr_ir(self, ir, var_syms):
+        """IR tree -> (callable, var_syms) running fused CUDA kernels (base.py:324-342 contract)."""
+        try:
+            key = repr(ir)
+            fn = self._compiled.get(key)
+            if fn is None:
+                fn = lowering.make_callable(ir)
+                self._compiled[key] = fn
+        except (ValueError, TypeError, KeyError):
+            return None
+        return (fn, var_syms)
+
+    # ------------------------------------------------------------------ autograd (torch interop)
+    def create_grad_tensor(self, x):
+        from . import autograd
+        return autograd.create_grad_tensor(self, x)
+
+    def compute_autograd(self, func, x):
+        from . import autograd
+        return autograd.compute_autograd(self, func, x)
+
+    def compute_multi_autograd(self, func, params):
+        from . import autograd
+        return autograd.compute_multi_autograd(self, func, params)
+
+    def compute_jacobian(self, func, x):
+        from . import autograd
+        return autograd.compute_jacobian(self, func, x)
+
+
+def _np_kg_equal(backend, a, b):
+    """Restatement of base.py:367-433 for host values (used only when klongpy is not importable)."""
+    if isinstance(a, np.ndarray) and isinstance(b, np.ndarray) and a.dtype != object and b.dtype != object:
+        return bool(np.array_equal(a, b))
+    if isinstance(a, np.ndarray) and a.ndim == 0:
+        a = a.item()
+    if isinstance(b, np.ndarray) and b.ndim == 0:
+        b = b.item()
+    a_seq = isinstance(a, (list, tuple)) or (isinstance(a, np.ndarray) and a.ndim > 0)
+    b_seq = isinstance(b, (list, tuple)) or (isinstance(b, np.ndarray) and b.ndim > 0)
+    if a_seq or b_seq:
+        if not (a_seq and b_seq) or len(a) != len(b):
+            return False
+        return all(backend.kg_equal(x, y) for x, y in zip(a, b))
+    if backend.is_number(a) and backend.is_number(b):
+        return bool(np.isclose(a, b))
+    r = a == b
+    return bool(r.all()) if hasattr(r, "all") else bool(r)

@@ -1,0 +1,570 @@
+// kgb200 JIT skeleton — the hand-written part of every fused expression kernel (sm_100a).
+//
+// expr_codegen.cpp prepends a block of macros describing ONE expression tree:
+//   KGB_MODE            0 map / 1 reduce / 2 scan / 3 scan+epilogue+reduce
+//   KGB_VEC             elements per 128-bit (or narrower) vector group
+//   KGB_OUT_T, KGB_ACC_T  C types of the stored result / the fold accumulator
+//   KGB_SCALARS         loads of by-value and 0-d device scalars into locals s<i>
+//   KGB_DECL_REGS(N)    register arrays a<i>[N] for each ARRAY argument
+//   KGB_LOAD_VEC(V,off,idx)   a<i>[off..off+V) <- V elements at element index idx (vector load)
+//   KGB_EVAL(j)         the expression value for register slot j
+//   KGB_RED(a,b), KGB_RED_IDENT           fold operator + identity (modes 1,2,3)
+//   KGB_EVAL2(j,sv), KGB_RED2(a,b), KGB_RED2_IDENT, KGB_ACC2_T   (mode 3 epilogue)
+// and this file supplies the memory movement: 128-bit streaming loads/stores, grid-stride unrolling
+// for bytes-in-flight, warp-shuffle + block folds with a fixed-order last-block combine
+// (deterministic), and the single-pass decoupled-lookback scan.
+// Compiled by NVRTC with --fmad=false so a*b+c rounds twice like NumPy.
+
+typedef long long i64;
+typedef unsigned long long u64;
+typedef unsigned int u32;
+typedef unsigned char u8;
+
+#define KGB_MAX_ARGS 12
+#define KGB_BLOCK 256
+#define KGB_UNROLL 4
+
+struct KgbParams {
+    const void* ptr[KGB_MAX_ARGS];
+    double sf[KGB_MAX_ARGS];
+    i64 si[KGB_MAX_ARGS];
+    void* out;
+    void* ws;
+    i64 n;
+};
+
+// ------------------------------------------------------------------ scalar helpers
+__device__ __forceinline__ double kgb_inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+__device__ __forceinline__ float kgb_inff() { return __int_as_float(0x7f800000); }
+
+template <typename T> struct kgb_lim;
+template <> struct kgb_lim<double> {
+    static __device__ __forceinline__ double lo() { return -kgb_inf(); }
+    static __device__ __forceinline__ double hi() { return kgb_inf(); }
+};
+template <> struct kgb_lim<float> {
+    static __device__ __forceinline__ float lo() { return -kgb_inff(); }
+    static __device__ __forceinline__ float hi() { return kgb_inff(); }
+};
+template <> struct kgb_lim<i64> {
+    static __device__ __forceinline__ i64 lo() { return (i64)0x8000000000000000LL; }
+    static __device__ __forceinline__ i64 hi() { return 0x7fffffffffffffffLL; }
+};
+template <> struct kgb_lim<int> {
+    static __device__ __forceinline__ int lo() { return (int)0x80000000; }
+    static __device__ __forceinline__ int hi() { return 0x7fffffff; }
+};
+template <> struct kgb_lim<u8> {
+    static __device__ __forceinline__ u8 lo() { return 0; }
+    static __device__ __forceinline__ u8 hi() { return 1; }
+};
+
+// np.maximum / np.minimum: NaN-propagating for floats
+__device__ __forceinline__ double kgb_max(double a, double b) { return (a != a) ? a : ((b != b) ? b : (a > b ? a : b)); }
+__device__ __forceinline__ double kgb_min(double a, double b) { return (a != a) ? a : ((b != b) ? b : (a < b ? a : b)); }
+__device__ __forceinline__ float kgb_max(float a, float b) { return (a != a) ? a : ((b != b) ? b : (a > b ? a : b)); }
+__device__ __forceinline__ float kgb_min(float a, float b) { return (a != a) ? a : ((b != b) ? b : (a < b ? a : b)); }
+__device__ __forceinline__ i64 kgb_max(i64 a, i64 b) { return a > b ? a : b; }
+__device__ __forceinline__ i64 kgb_min(i64 a, i64 b) { return a < b ? a : b; }
+__device__ __forceinline__ int kgb_max(int a, int b) { return a > b ? a : b; }
+__device__ __forceinline__ int kgb_min(int a, int b) { return a < b ? a : b; }
+__device__ __forceinline__ u8 kgb_max(u8 a, u8 b) { return a > b ? a : b; }
+__device__ __forceinline__ u8 kgb_min(u8 a, u8 b) { return a < b ? a : b; }
+
+// numpy ** : exponent 2 is an exact square (NumPy's scalar fast path; also what a correctly rounded
+// pow returns), 0.5 is sqrt; everything else goes to pow().
+__device__ __forceinline__ double kgb_pow(double a, double b) {
+    if (b == 2.0) return a * a;
+    if (b == 0.5) return sqrt(a);
+    if (b == 1.0) return a;
+    if (b == -1.0) return 1.0 / a;
+    return pow(a, b);
+}
+__device__ __forceinline__ float kgb_pow(float a, float b) {
+    if (b == 2.0f) return a * a;
+    if (b == 0.5f) return sqrtf(a);
+    if (b == 1.0f) return a;
+    return powf(a, b);
+}
+// integer power by squaring, wrapping like numpy int64.  Negative exponents (a ValueError in numpy)
+// follow the mathematical truncation: 1 -> 1, -1 -> +-1, otherwise 0.
+__device__ __forceinline__ i64 kgb_pow(i64 a, i64 b) {
+    if (b < 0) {
+        if (a == 1) return 1;
+        if (a == -1) return (b & 1) ? -1 : 1;
+        return 0;
+    }
+    u64 r = 1, x = (u64)a;
+    while (b) {
+        if (b & 1) r *= x;
+        x *= x;
+        b >>= 1;
+    }
+    return (i64)r;
+}
+__device__ __forceinline__ int kgb_pow(int a, int b) { return (int)kgb_pow((i64)a, (i64)b); }
+
+// np.fmod: C truncated remainder; integer x % 0 -> 0 (numpy warns and returns 0)
+__device__ __forceinline__ double kgb_fmod(double a, double b) { return fmod(a, b); }
+__device__ __forceinline__ float kgb_fmod(float a, float b) { return fmodf(a, b); }
+__device__ __forceinline__ i64 kgb_fmod(i64 a, i64 b) { return b == 0 ? 0 : (b == -1 ? 0 : a % b); }
+__device__ __forceinline__ int kgb_fmod(int a, int b) { return b == 0 ? 0 : (b == -1 ? 0 : a % b); }
+
+__device__ __forceinline__ double kgb_abs(double a) { return fabs(a); }
+__device__ __forceinline__ float kgb_abs(float a) { return fabsf(a); }
+__device__ __forceinline__ i64 kgb_abs(i64 a) { return a < 0 ? -a : a; }
+__device__ __forceinline__ int kgb_abs(int a) { return a < 0 ? -a : a; }
+__device__ __forceinline__ u8 kgb_abs(u8 a) { return a; }
+
+__device__ __forceinline__ double kgb_sign(double a) { return (a != a) ? a : (double)((a > 0.0) - (a < 0.0)); }
+__device__ __forceinline__ float kgb_sign(float a) { return (a != a) ? a : (float)((a > 0.0f) - (a < 0.0f)); }
+__device__ __forceinline__ i64 kgb_sign(i64 a) { return (i64)((a > 0) - (a < 0)); }
+__device__ __forceinline__ int kgb_sign(int a) { return (a > 0) - (a < 0); }
+
+__device__ __forceinline__ bool kgb_isclose(double a, double b) {
+    if (a == b) return true;
+    if (isinf(a) || isinf(b)) return false;
+    return fabs(a - b) <= 1e-08 + 1e-05 * fabs(b);
+}
+
+// ------------------------------------------------------------------ vector load / store
+template <int BYTES> struct kgb_raw;
+template <> struct kgb_raw<1> { typedef unsigned char type; };
+template <> struct kgb_raw<2> { typedef unsigned short type; };
+template <> struct kgb_raw<4> { typedef unsigned int type; };
+template <> struct kgb_raw<8> { typedef uint2 type; };
+template <> struct kgb_raw<16> { typedef uint4 type; };
+
+// streaming (evict-first) load of V contiguous elements into registers dst[0..V)
+template <typename T, int V> __device__ __forceinline__ void kgb_ldv(T* dst, const T* src) {
+    typedef typename kgb_raw<sizeof(T) * V>::type R;
+    union {
+        R r;
+        T t[V];
+    } u;
+    u.r = __ldcs(reinterpret_cast<const R*>(src));
+#pragma unroll
+    for (int j = 0; j < V; j++) dst[j] = u.t[j];
+}
+template <typename T, int V> __device__ __forceinline__ void kgb_stv(T* dst, const T* src) {
+    typedef typename kgb_raw<sizeof(T) * V>::type R;
+    union {
+        R r;
+        T t[V];
+    } u;
+#pragma unroll
+    for (int j = 0; j < V; j++) u.t[j] = src[j];
+    __stcs(reinterpret_cast<R*>(dst), u.r);
+}
+
+// ------------------------------------------------------------------ warp / block folds
+template <typename T> __device__ __forceinline__ T kgb_shfl_xor(T v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+template <> __device__ __forceinline__ u8 kgb_shfl_xor<u8>(u8 v, int m) { return (u8)__shfl_xor_sync(0xffffffffu, (int)v, m); }
+template <typename T> __device__ __forceinline__ T kgb_shfl_up(T v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+template <> __device__ __forceinline__ u8 kgb_shfl_up<u8>(u8 v, int d) { return (u8)__shfl_up_sync(0xffffffffu, (int)v, d); }
+template <typename T> __device__ __forceinline__ T kgb_shfl(T v, int l) { return __shfl_sync(0xffffffffu, v, l); }
+template <> __device__ __forceinline__ u8 kgb_shfl<u8>(u8 v, int l) { return (u8)__shfl_sync(0xffffffffu, (int)v, l); }
+
+// =====================================================================================================
+#if KGB_MODE == 0
+// ------------------------------------------------------------------ MAP: out[i] = f(args[i])
+// Grid-stride over vector groups, KGB_UNROLL independent 128-bit loads per array in flight per thread.
+template <int V> __device__ __forceinline__ void kgb_map_body(const KgbParams& p) {
+    KGB_SCALARS
+    KGB_OUT_T* __restrict__ out = (KGB_OUT_T*)p.out;
+    const i64 n = p.n;
+    const i64 ngroups = n / V;
+    const i64 stride = (i64)gridDim.x * KGB_BLOCK;
+    const i64 tid = (i64)blockIdx.x * KGB_BLOCK + threadIdx.x;
+    for (i64 g0 = tid; g0 < ngroups; g0 += stride * KGB_UNROLL) {
+        KGB_DECL_REGS(V * KGB_UNROLL)
+#pragma unroll
+        for (int u = 0; u < KGB_UNROLL; u++) {
+            const i64 g = g0 + u * stride;
+            if (g < ngroups) { KGB_LOAD_VEC(V, u * V, g * V) }
+        }
+#pragma unroll
+        for (int u = 0; u < KGB_UNROLL; u++) {
+            const i64 g = g0 + u * stride;
+            if (g < ngroups) {
+                KGB_OUT_T o[V];
+#pragma unroll
+                for (int j = 0; j < V; j++) o[j] = (KGB_OUT_T)(KGB_EVAL(u * V + j));
+                kgb_stv<KGB_OUT_T, V>(out + g * V, o);
+            }
+        }
+    }
+    // scalar tail (n % V elements)
+    const i64 t = ngroups * V + tid;
+    if (t < n) {
+        KGB_DECL_REGS(1)
+        KGB_LOAD_VEC(1, 0, t)
+        out[t] = (KGB_OUT_T)(KGB_EVAL(0));
+    }
+}
+extern "C" __global__ void __launch_bounds__(KGB_BLOCK) KGB_KERNEL_NAME_V(const __grid_constant__ KgbParams p) { kgb_map_body<KGB_VEC>(p); }
+extern "C" __global__ void __launch_bounds__(KGB_BLOCK) KGB_KERNEL_NAME_S(const __grid_constant__ KgbParams p) { kgb_map_body<1>(p); }
+#endif
+
+// =====================================================================================================
+#if KGB_MODE == 1
+// ------------------------------------------------------------------ REDUCE: out[0] = fold f(args[i])
+// Per-thread V*UNROLL independent accumulators -> fixed tree -> warp shuffle -> block smem -> one
+// partial per block in ws -> the last block to finish folds the partials in index order.  The shape of
+// the tree depends only on (n, grid), so results are bit-reproducible run to run.
+// ws layout: [0,4) ticket (zeroed by the host wrapper), [64, 64+grid*sizeof(ACC)) partials.
+__device__ __forceinline__ KGB_ACC_T kgb_block_fold(KGB_ACC_T v, KGB_ACC_T* sh) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        KGB_ACC_T o = kgb_shfl_xor<KGB_ACC_T>(v, m);
+        v = KGB_RED(v, o);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        v = (lane < KGB_BLOCK / 32) ? sh[lane] : (KGB_ACC_T)(KGB_RED_IDENT);
+#pragma unroll
+        for (int m = (KGB_BLOCK / 64); m >= 1; m >>= 1) {
+            KGB_ACC_T o = kgb_shfl_xor<KGB_ACC_T>(v, m);
+            v = KGB_RED(v, o);
+        }
+    }
+    return v;  // valid in thread 0
+}
+
+template <int V> __device__ __forceinline__ void kgb_reduce_body(const KgbParams& p) {
+    KGB_SCALARS
+    __shared__ KGB_ACC_T sh[KGB_BLOCK / 32];
+    __shared__ bool is_last;
+    const i64 n = p.n;
+    const i64 ngroups = n / V;
+    const i64 stride = (i64)gridDim.x * KGB_BLOCK;
+    const i64 tid = (i64)blockIdx.x * KGB_BLOCK + threadIdx.x;
+    KGB_ACC_T acc[V * KGB_UNROLL];
+#pragma unroll
+    for (int k = 0; k < V * KGB_UNROLL; k++) acc[k] = (KGB_ACC_T)(KGB_RED_IDENT);
+    for (i64 g0 = tid; g0 < ngroups; g0 += stride * KGB_UNROLL) {
+        KGB_DECL_REGS(V * KGB_UNROLL)
+#pragma unroll
+        for (int u = 0; u < KGB_UNROLL; u++) {
+            const i64 g = g0 + u * stride;
+            if (g < ngroups) { KGB_LOAD_VEC(V, u * V, g * V) }
+        }
+#pragma unroll
+        for (int u = 0; u < KGB_UNROLL; u++) {
+            const i64 g = g0 + u * stride;
+            if (g < ngroups) {
+#pragma unroll
+                for (int j = 0; j < V; j++) {
+                    KGB_ACC_T e = (KGB_ACC_T)(KGB_EVAL(u * V + j));
+                    acc[u * V + j] = KGB_RED(acc[u * V + j], e);
+                }
+            }
+        }
+    }
+    const i64 t = ngroups * V + tid;
+    if (t < n) {
+        KGB_DECL_REGS(1)
+        KGB_LOAD_VEC(1, 0, t)
+        KGB_ACC_T e = (KGB_ACC_T)(KGB_EVAL(0));
+        acc[0] = KGB_RED(acc[0], e);
+    }
+#pragma unroll
+    for (int w = (V * KGB_UNROLL) / 2; w >= 1; w >>= 1) {
+#pragma unroll
+        for (int k = 0; k < w; k++) acc[k] = KGB_RED(acc[k], acc[k + w]);
+    }
+    KGB_ACC_T v = kgb_block_fold(acc[0], sh);
+
+    u32* ticket = (u32*)p.ws;
+    volatile KGB_ACC_T* partial = (volatile KGB_ACC_T*)((char*)p.ws + 64);
+    if (threadIdx.x == 0) {
+        partial[blockIdx.x] = v;
+        __threadfence();
+        const u32 tk = atomicAdd(ticket, 1u);
+        is_last = (tk == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        KGB_ACC_T a = (KGB_ACC_T)(KGB_RED_IDENT);
+        for (u32 b = threadIdx.x; b < gridDim.x; b += KGB_BLOCK) {
+            KGB_ACC_T o = partial[b];
+            a = KGB_RED(a, o);
+        }
+        __syncthreads();
+        a = kgb_block_fold(a, sh);
+        if (threadIdx.x == 0) {
+            *(KGB_OUT_T*)p.out = (KGB_OUT_T)a;
+            *ticket = 0u;
+        }
+    }
+}
+extern "C" __global__ void __launch_bounds__(KGB_BLOCK) KGB_KERNEL_NAME_V(const __grid_constant__ KgbParams p) { kgb_reduce_body<KGB_VEC>(p); }
+extern "C" __global__ void __launch_bounds__(KGB_BLOCK) KGB_KERNEL_NAME_S(const __grid_constant__ KgbParams p) { kgb_reduce_body<1>(p); }
+#endif
+
+// =====================================================================================================
+#if KGB_MODE == 2 || KGB_MODE == 3
+// ------------------------------------------------------------------ SCAN: out[i] = fold_{j<=i} f(args[j])
+// Single-pass chained scan with decoupled look-back.  One tile = 256 threads x ITEMS (128 B) elements.
+//   1. coalesced 128-bit striped loads, expression evaluated, values parked in padded smem
+//   2. each thread re-reads its 128 B chunk (bank-conflict-free thanks to the 16 B pad per chunk),
+//      scans it in registers; warp-shuffle + cross-warp scan of thread totals
+//   3. tile aggregate published; warp 0 looks back over predecessor tiles (32 at a time)
+//   4. results go back through smem and leave as coalesced 128-bit streaming stores
+// Tiles take their index from an atomic ticket so a tile's predecessors are always already running.
+// ws layout: [0,4) ticket, [4,8) done-count (mode 3), [64,...) flags u32[T], then agg ACC[T], incl ACC[T]
+// (mode 3: then partial ACC2[T]).  The host wrapper zeroes ticket+flags before each launch.
+#define KGB_ITEMS (128 / (int)sizeof(KGB_ACC_T))
+#define KGB_PADE (16 / (int)sizeof(KGB_ACC_T))
+#define KGB_TILE (KGB_BLOCK * KGB_ITEMS)
+#define KGB_SMEM_ELEMS (KGB_BLOCK * (KGB_ITEMS + KGB_PADE))
+#define KGB_FLAG_EMPTY 0u
+#define KGB_FLAG_AGG 1u
+#define KGB_FLAG_PREFIX 2u
+
+__device__ __forceinline__ int kgb_pad(int e) { return e + (e / KGB_ITEMS) * KGB_PADE; }
+
+__device__ __forceinline__ u32 kgb_ld_acquire(const u32* p) {
+    u32 v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void kgb_st_release(u32* p, u32 v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <int V> __device__ __forceinline__ void kgb_scan_body(const KgbParams& p) {
+    KGB_SCALARS
+    __shared__ __align__(16) KGB_ACC_T sbuf[KGB_SMEM_ELEMS];
+    __shared__ KGB_ACC_T swarp[KGB_BLOCK / 32];
+    __shared__ KGB_ACC_T s_excl;
+    __shared__ u32 s_tile;
+    const i64 n = p.n;
+    const u32 ntiles = (u32)((n + KGB_TILE - 1) / KGB_TILE);
+    u32* ticket = (u32*)p.ws;
+    u32* flags = (u32*)((char*)p.ws + 64);
+    const size_t flags_bytes = (((size_t)ntiles * 4 + 63) / 64) * 64;
+    KGB_ACC_T* aggs = (KGB_ACC_T*)((char*)p.ws + 64 + flags_bytes);
+    KGB_ACC_T* incls = aggs + ntiles;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const u32 tile = s_tile;
+    const i64 base = (i64)tile * KGB_TILE;
+    const bool full = (base + KGB_TILE <= n);
+
+    // ---- 1. striped load + evaluate -> padded smem
+    if (full) {
+#pragma unroll
+        for (int h = 0; h < KGB_ITEMS / V; h += KGB_UNROLL) {
+            KGB_DECL_REGS(V * KGB_UNROLL)
+#pragma unroll
+            for (int u = 0; u < KGB_UNROLL; u++) {
+                const int e = ((h + u) * KGB_BLOCK + tid) * V;
+                KGB_LOAD_VEC(V, u * V, base + e)
+            }
+#pragma unroll
+            for (int u = 0; u < KGB_UNROLL; u++) {
+                const int e = ((h + u) * KGB_BLOCK + tid) * V;
+                KGB_ACC_T o[V];
+#pragma unroll
+                for (int j = 0; j < V; j++) o[j] = (KGB_ACC_T)(KGB_EVAL(u * V + j));
+                if (V * sizeof(KGB_ACC_T) == 16) {
+                    *reinterpret_cast<uint4*>(&sbuf[kgb_pad(e)]) = *reinterpret_cast<uint4*>(o);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < V; j++) sbuf[kgb_pad(e + j)] = o[j];
+                }
+            }
+        }
+    } else {
+        for (int k = 0; k < KGB_ITEMS; k++) {
+            const int e = k * KGB_BLOCK + tid;
+            KGB_ACC_T o = (KGB_ACC_T)(KGB_RED_IDENT);
+            if (base + e < n) {
+                KGB_DECL_REGS(1)
+                KGB_LOAD_VEC(1, 0, base + e)
+                o = (KGB_ACC_T)(KGB_EVAL(0));
+            }
+            sbuf[kgb_pad(e)] = o;
+        }
+    }
+    __syncthreads();
+
+    // ---- 2. blocked read + in-register scan
+    KGB_ACC_T x[KGB_ITEMS];
+    {
+        const KGB_ACC_T* src = &sbuf[tid * (KGB_ITEMS + KGB_PADE)];
+#pragma unroll
+        for (int q = 0; q < KGB_ITEMS * (int)sizeof(KGB_ACC_T) / 16; q++) {
+            uint4 r = reinterpret_cast<const uint4*>(src)[q];
+            *reinterpret_cast<uint4*>(&x[q * (16 / (int)sizeof(KGB_ACC_T))]) = r;
+        }
+    }
+#pragma unroll
+    for (int k = 1; k < KGB_ITEMS; k++) x[k] = KGB_RED(x[k - 1], x[k]);
+    // inclusive warp scan of the thread totals
+    KGB_ACC_T tot = x[KGB_ITEMS - 1];
+    KGB_ACC_T inc = tot;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        KGB_ACC_T o = kgb_shfl_up<KGB_ACC_T>(inc, d);
+        if (lane >= d) inc = KGB_RED(o, inc);
+    }
+    if (lane == 31) swarp[warp] = inc;
+    KGB_ACC_T lane_excl = kgb_shfl_up<KGB_ACC_T>(inc, 1);
+    __syncthreads();
+    // fixed-order prefix over the warp totals
+    KGB_ACC_T wpre = (KGB_ACC_T)(KGB_RED_IDENT);
+    KGB_ACC_T tile_agg = (KGB_ACC_T)(KGB_RED_IDENT);
+#pragma unroll
+    for (int w = 0; w < KGB_BLOCK / 32; w++) {
+        const KGB_ACC_T sw = swarp[w];
+        if (w == warp) wpre = tile_agg;
+        tile_agg = (w == 0) ? sw : KGB_RED(tile_agg, sw);
+    }
+    // identities are exact for every fold operator (0, 1, -+inf / INT_MIN / INT_MAX), so no validity
+    // tracking is needed when a prefix is still empty
+    KGB_ACC_T thread_excl = (lane == 0) ? wpre : KGB_RED(wpre, lane_excl);
+
+    // ---- 3. publish aggregate, look back
+    if (tid == 0) {
+        if (tile == 0) {
+            incls[0] = tile_agg;
+            __threadfence();
+            kgb_st_release(&flags[0], KGB_FLAG_PREFIX);
+        } else {
+            aggs[tile] = tile_agg;
+            __threadfence();
+            kgb_st_release(&flags[tile], KGB_FLAG_AGG);
+        }
+    }
+    if (warp == 0 && tile > 0) {
+        KGB_ACC_T excl = (KGB_ACC_T)(KGB_RED_IDENT);
+        i64 look = (i64)tile - 1;
+        while (true) {
+            const i64 idx = look - lane;
+            u32 f = KGB_FLAG_PREFIX;  // virtual tiles before 0: an identity prefix
+            if (idx >= 0) f = kgb_ld_acquire(&flags[idx]);
+            // every lane of the warp takes part in the vote (lanes past tile 0 hold the virtual prefix)
+            u32 spins = 0;
+            while (__any_sync(0xffffffffu, f == KGB_FLAG_EMPTY)) {
+                if (f == KGB_FLAG_EMPTY) f = kgb_ld_acquire(&flags[idx]);
+                if (++spins > (1u << 26)) __trap();  // a predecessor never published: fail, do not hang
+            }
+            const u32 pmask = __ballot_sync(0xffffffffu, f == KGB_FLAG_PREFIX);
+            const int first = __ffs(pmask) - 1;  // nearest tile holding an inclusive prefix
+            KGB_ACC_T c = (KGB_ACC_T)(KGB_RED_IDENT);
+            if ((pmask == 0 || lane <= first) && idx >= 0)
+                c = (lane == first) ? __ldcg(&incls[idx]) : __ldcg(&aggs[idx]);
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) {
+                KGB_ACC_T o = kgb_shfl_xor<KGB_ACC_T>(c, d);
+                c = KGB_RED(c, o);
+            }
+            excl = KGB_RED(c, excl);
+            if (pmask != 0) break;
+            look -= 32;
+        }
+        if (lane == 0) {
+            s_excl = excl;
+            incls[tile] = KGB_RED(excl, tile_agg);
+            __threadfence();
+            kgb_st_release(&flags[tile], KGB_FLAG_PREFIX);
+        }
+    }
+    __syncthreads();
+    if (tile > 0) thread_excl = KGB_RED(s_excl, thread_excl);
+#pragma unroll
+    for (int k = 0; k < KGB_ITEMS; k++) x[k] = KGB_RED(thread_excl, x[k]);
+
+#if KGB_MODE == 2
+    // ---- 4. blocked -> smem -> striped coalesced stores
+    {
+        KGB_ACC_T* dst = &sbuf[tid * (KGB_ITEMS + KGB_PADE)];
+#pragma unroll
+        for (int q = 0; q < KGB_ITEMS * (int)sizeof(KGB_ACC_T) / 16; q++)
+            reinterpret_cast<uint4*>(dst)[q] = *reinterpret_cast<uint4*>(&x[q * (16 / (int)sizeof(KGB_ACC_T))]);
+    }
+    __syncthreads();
+    KGB_OUT_T* __restrict__ out = (KGB_OUT_T*)p.out;
+    if (full) {
+#pragma unroll
+        for (int h = 0; h < KGB_ITEMS / V; h++) {
+            const int e = (h * KGB_BLOCK + tid) * V;
+            KGB_OUT_T o[V];
+#pragma unroll
+            for (int j = 0; j < V; j++) o[j] = (KGB_OUT_T)sbuf[kgb_pad(e + j)];
+            kgb_stv<KGB_OUT_T, V>(out + base + e, o);
+        }
+    } else {
+        for (int k = 0; k < KGB_ITEMS; k++) {
+            const int e = k * KGB_BLOCK + tid;
+            if (base + e < n) out[base + e] = (KGB_OUT_T)sbuf[kgb_pad(e)];
+        }
+    }
+#else
+    // ---- 4'. epilogue g(scan value, args[i]) folded with RED2; args re-read in the blocked layout
+    // (the tile was just streamed, so these hit L2) -> per-tile partial -> last tile folds in order.
+    KGB_ACC2_T r2 = (KGB_ACC2_T)(KGB_RED2_IDENT);
+#pragma unroll
+    for (int k = 0; k < KGB_ITEMS; k++) {
+        const i64 gi = base + (i64)tid * KGB_ITEMS + k;
+        if (gi < n) {
+            KGB_DECL_REGS(1)
+            KGB_LOAD_VEC(1, 0, gi)
+            KGB_ACC2_T e2 = (KGB_ACC2_T)(KGB_EVAL2(0, x[k]));
+            r2 = KGB_RED2(r2, e2);
+        }
+    }
+    __shared__ KGB_ACC2_T sh2[KGB_BLOCK / 32];
+    __shared__ bool is_last;
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        KGB_ACC2_T o = kgb_shfl_xor<KGB_ACC2_T>(r2, m);
+        r2 = KGB_RED2(r2, o);
+    }
+    if (lane == 0) sh2[warp] = r2;
+    __syncthreads();
+    KGB_ACC2_T* part2 = (KGB_ACC2_T*)(incls + ntiles);
+    u32* done = ticket + 1;
+    if (tid == 0) {
+        KGB_ACC2_T a = sh2[0];
+#pragma unroll
+        for (int w = 1; w < KGB_BLOCK / 32; w++) a = KGB_RED2(a, sh2[w]);
+        ((volatile KGB_ACC2_T*)part2)[tile] = a;
+        __threadfence();
+        is_last = (atomicAdd(done, 1u) == ntiles - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        KGB_ACC2_T a = (KGB_ACC2_T)(KGB_RED2_IDENT);
+        for (u32 b = tid; b < ntiles; b += KGB_BLOCK) {
+            KGB_ACC2_T o = ((volatile KGB_ACC2_T*)part2)[b];
+            a = KGB_RED2(a, o);
+        }
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            KGB_ACC2_T o = kgb_shfl_xor<KGB_ACC2_T>(a, m);
+            a = KGB_RED2(a, o);
+        }
+        __syncthreads();
+        if (lane == 0) sh2[warp] = a;
+        __syncthreads();
+        if (tid == 0) {
+            a = sh2[0];
+#pragma unroll
+            for (int w = 1; w < KGB_BLOCK / 32; w++) a = KGB_RED2(a, sh2[w]);
+            *(KGB_OUT_T*)p.out = (KGB_OUT_T)a;
+        }
+    }
+#endif
+}
+extern "C" __global__ void __launch_bounds__(KGB_BLOCK) KGB_KERNEL_NAME_V(const __grid_constant__ KgbParams p) { kgb_scan_body<KGB_VEC>(p); }
+extern "C" __global__ void __launch_bounds__(KGB_BLOCK) KGB_KERNEL_NAME_S(const __grid_constant__ KgbParams p) { kgb_scan_body<1>(p); }
+#endif

@@ -1,0 +1,174 @@
+// Grouped min / max / sum / count over (int64 key, float64 value) rows — the 1brc-style aggregation of
+// examples/1brc/worker.kg:3-5 (collect = [min max sum count], merge = (&, |, +, +)).
+//
+// v1: streaming 128-bit loads of both columns; the G x 4 table lives in L2-resident global memory.
+// min/max use order-encoded 64-bit integers with a read-before-update filter (after the first few rows of a
+// station almost no row improves its extremes, so the RED is rarely issued); sum/count are RED.ADD.
+#include "kgb_device.cuh"
+#include "kgb_internal.h"
+
+namespace kgb {
+
+struct AggWs {
+    u64* tmin;  // order-encoded, NaN = 0
+    u64* tmax;  // order-encoded, NaN = ~0, empty = 0
+    double* tsum;
+    u64* tcnt;
+    int* err;
+    size_t total;
+};
+static AggWs carve_agg(void* ws, i64 G) {
+    AggWs a;
+    char* p = (char*)ws;
+    const size_t gb = align_up((size_t)G * 8, 256);
+    a.tmin = (u64*)p;
+    a.tmax = (u64*)(p + gb);
+    a.tsum = (double*)(p + 2 * gb);
+    a.tcnt = (u64*)(p + 3 * gb);
+    a.err = (int*)(p + 4 * gb);
+    a.total = 4 * gb + 256;
+    return a;
+}
+
+__device__ __forceinline__ u64 enc_for_min(double v) { return (v != v) ? 0ull : key_from_f64(v); }
+__device__ __forceinline__ u64 enc_for_max(double v) { return key_from_f64(v); }  // NaN -> ~0
+
+__device__ __forceinline__ void agg_row(i64 k, double v, i64 G, const AggWs& a) {
+    if ((u64)k >= (u64)G) {
+        *a.err = 1;
+        return;
+    }
+    const u64 emin = enc_for_min(v), emax = enc_for_max(v);
+    if (emin < ld_relaxed_u64(&a.tmin[k])) atomicMin(&a.tmin[k], emin);
+    if (emax > ld_relaxed_u64(&a.tmax[k])) atomicMax(&a.tmax[k], emax);
+    atomicAdd(&a.tsum[k], v);
+    atomicAdd(&a.tcnt[k], 1ull);
+}
+
+__global__ void __launch_bounds__(256) groupagg_kernel(const i64* __restrict__ keys, const double* __restrict__ vals,
+                                                        i64 n, i64 G, AggWs a) {
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    const i64 tid = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool vec = ((reinterpret_cast<uintptr_t>(keys) | reinterpret_cast<uintptr_t>(vals)) & 15) == 0;
+    constexpr int U = 4;
+    if (vec) {
+        const i64 n2 = n / 2;
+        for (i64 g0 = tid; g0 < n2; g0 += stride * U) {
+            longlong2 k[U];
+            double2 v[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const i64 g = g0 + u * stride;
+                if (g < n2) {
+                    k[u] = __ldcs(reinterpret_cast<const longlong2*>(keys) + g);
+                    v[u] = __ldcs(reinterpret_cast<const double2*>(vals) + g);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const i64 g = g0 + u * stride;
+                if (g < n2) {
+                    agg_row(k[u].x, v[u].x, G, a);
+                    agg_row(k[u].y, v[u].y, G, a);
+                }
+            }
+        }
+        if ((n & 1) && tid == 0) agg_row(keys[n - 1], vals[n - 1], G, a);
+    } else {
+        for (i64 i = tid; i < n; i += stride) agg_row(keys[i], vals[i], G, a);
+    }
+}
+
+__device__ __forceinline__ double nanpropagating_min(double a, double b) { return (a != a) ? a : ((b != b) ? b : (a < b ? a : b)); }
+__device__ __forceinline__ double nanpropagating_max(double a, double b) { return (a != a) ? a : ((b != b) ? b : (a > b ? a : b)); }
+
+__global__ void __launch_bounds__(256) groupagg_finalize(AggWs a, i64 G, double* __restrict__ mn, double* __restrict__ mx,
+                                                          double* __restrict__ sm, i64* __restrict__ ct, int accumulate) {
+    const i64 g = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    const u64 c = a.tcnt[g];
+    double vmin = __longlong_as_double(0x7ff0000000000000ll), vmax = -vmin, vsum = 0.0;
+    if (c) {
+        const u64 emin = a.tmin[g], emax = a.tmax[g];
+        vmin = (emin == 0ull) ? __longlong_as_double(0x7ff8000000000000ll) : key_to_f64(emin);
+        vmax = key_to_f64(emax);
+        vsum = a.tsum[g];
+    }
+    if (accumulate) {
+        mn[g] = nanpropagating_min(mn[g], vmin);
+        mx[g] = nanpropagating_max(mx[g], vmax);
+        sm[g] = sm[g] + vsum;
+        ct[g] = ct[g] + (i64)c;
+    } else {
+        mn[g] = vmin;
+        mx[g] = vmax;
+        sm[g] = vsum;
+        ct[g] = (i64)c;
+    }
+}
+
+__global__ void __launch_bounds__(256) groupagg_merge_kernel(double* mn, double* mx, double* sm, i64* ct,
+                                                              const double* __restrict__ mn2, const double* __restrict__ mx2,
+                                                              const double* __restrict__ sm2, const i64* __restrict__ ct2, i64 G) {
+    const i64 g = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    mn[g] = nanpropagating_min(mn[g], mn2[g]);
+    mx[g] = nanpropagating_max(mx[g], mx2[g]);
+    sm[g] = sm[g] + sm2[g];
+    ct[g] = ct[g] + ct2[g];
+}
+
+}  // namespace kgb
+
+using namespace kgb;
+
+extern "C" int kgb_groupagg_workspace_bytes(int64_t n, int64_t n_groups, size_t* out_bytes) {
+    (void)n;
+    KGB_REQUIRE(out_bytes && n_groups >= 0, "kgb_groupagg_workspace_bytes: bad arguments");
+    *out_bytes = carve_agg(nullptr, n_groups).total;
+    return KGB_OK;
+}
+
+extern "C" int kgb_groupagg_f64(const int64_t* keys, const double* vals, int64_t n, int64_t n_groups, double* min_out,
+                                double* max_out, double* sum_out, int64_t* count_out, int32_t accumulate,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+    KGB_REQUIRE(current_device() >= 0, "kgb_init() has not been called on this thread");
+    KGB_REQUIRE(n >= 0 && n_groups >= 0, "kgb_groupagg_f64: negative size");
+    if (n_groups == 0) return KGB_OK;
+    KGB_REQUIRE(min_out && max_out && sum_out && count_out && workspace &&
+                    workspace_bytes >= carve_agg(nullptr, n_groups).total && (n == 0 || (keys && vals)),
+                "kgb_groupagg_f64: null pointer or workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    AggWs a = carve_agg(workspace, n_groups);
+    const size_t gb = align_up((size_t)n_groups * 8, 256);
+    KGB_CUDA_CHECK(cudaMemsetAsync(a.tmin, 0xff, gb, st));
+    KGB_CUDA_CHECK(cudaMemsetAsync(a.tmax, 0, 3 * gb + 256, st));
+    if (n > 0) {
+        long long blocks = (n / 2 + 256 * 4 - 1) / (256 * 4);
+        const long long cap = (long long)sm_count() * 8;
+        if (blocks > cap) blocks = cap;
+        if (blocks < 1) blocks = 1;
+        groupagg_kernel<<<(unsigned)blocks, 256, 0, st>>>((const i64*)keys, vals, n, n_groups, a);
+    }
+    groupagg_finalize<<<(unsigned)((n_groups + 255) / 256), 256, 0, st>>>(a, n_groups, min_out, max_out, sum_out,
+                                                                         (i64*)count_out, accumulate);
+    KGB_CUDA_CHECK(cudaGetLastError());
+    int err = 0;
+    // out-of-range keys are a caller bug: report it (one 4-byte read after the kernels)
+    KGB_CUDA_CHECK(cudaMemcpyAsync(&err, a.err, 4, cudaMemcpyDeviceToHost, st));
+    KGB_CUDA_CHECK(cudaStreamSynchronize(st));
+    KGB_REQUIRE(err == 0, "kgb_groupagg_f64: key outside [0, n_groups)");
+    return KGB_OK;
+}
+
+extern "C" int kgb_groupagg_merge(double* min_io, double* max_io, double* sum_io, int64_t* count_io, const double* min_in,
+                                  const double* max_in, const double* sum_in, const int64_t* count_in, int64_t n_groups,
+                                  void* stream) {
+    KGB_REQUIRE(current_device() >= 0, "kgb_init() has not been called on this thread");
+    KGB_REQUIRE(n_groups >= 0, "kgb_groupagg_merge: negative size");
+    if (n_groups == 0) return KGB_OK;
+    groupagg_merge_kernel<<<(unsigned)((n_groups + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        min_io, max_io, sum_io, (i64*)count_io, min_in, max_in, sum_in, (const i64*)count_in, n_groups);
+    KGB_CUDA_CHECK(cudaGetLastError());
+    return KGB_OK;
+}

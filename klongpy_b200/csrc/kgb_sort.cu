@@ -1,0 +1,389 @@
+// Grade-up / grade-down: stable LSD radix sort of (key, position) in the onesweep style.
+//
+//   hist   : ONE read of the keys builds the 8 x 256-bin digit histograms (privatised in smem; warps whose
+//            lanes agree on a digit issue one aggregated atomic, which is what the constant high digits of
+//            small-range int64 keys always do).
+//   plan   : exclusive digit offsets; digits on which every key agrees are SKIPPED (their pass returns at
+//            once), the ping-pong schedule and first/last roles are decided on the device (no host sync).
+//   pass   : per 8-bit digit, one kernel: warp-level multisplit ranking (match_any), per-tile digit counts
+//            published for chained decoupled look-back, keys/positions staged through shared memory so the
+//            global scatter leaves as digit-contiguous (coalesced) runs.  The first pass reads the caller's
+//            keys directly (order-encoding them on the fly; positions are implicit) and the last pass writes
+//            int64 positions straight into idx_out (reversed for grade-down), so no extra copy pass exists.
+//
+// Replaces np.argsort (klongpy/backends/numpy_backend.py:75-80) behind kg_argsort (klongpy/writer.py:97-122).
+// Stability is the language contract (ties by position; grade-down = reversed stable ascending).
+#include "kgb_sort.cuh"
+
+namespace kgb {
+
+constexpr int RADIX = 256;
+constexpr int NPASS = 8;
+constexpr int ST = 256;            // threads per CTA
+constexpr int SI = 16;             // keys per thread
+constexpr int STILE = ST * SI;     // 4096 keys per tile
+constexpr int SWARPS = ST / 32;
+
+struct SortPlan {
+    int active[NPASS], src[NPASS], dst[NPASS], first[NPASS], last[NPASS];
+    int n_active;
+    int pad[7];
+    u64 digit_base[NPASS][RADIX];
+};
+
+struct SortWs {
+    SortPlan* plan;
+    u64* hist;      // [NPASS][RADIX]
+    u32* tickets;   // [NPASS] (+pad)
+    u64* states;    // [tiles][RADIX]
+    u64* keys[2];
+    u32* idx[2];
+    size_t zero_bytes;  // hist + tickets + states are contiguous from `hist`
+    size_t total;
+};
+
+static SortWs carve(void* ws, i64 n) {
+    SortWs w;
+    const size_t tiles = (size_t)((n + STILE - 1) / STILE);
+    char* p = (char*)ws;
+    size_t o = 0;
+    w.plan = (SortPlan*)(p + o);
+    o += align_up(sizeof(SortPlan), 256);
+    const size_t z0 = o;
+    w.hist = (u64*)(p + o);
+    o += (size_t)NPASS * RADIX * 8;
+    w.tickets = (u32*)(p + o);
+    o += 64;
+    w.states = (u64*)(p + o);
+    o += align_up(tiles * RADIX * 8, 256);
+    w.zero_bytes = o - z0;
+    for (int b = 0; b < 2; b++) {
+        w.keys[b] = (u64*)(p + o);
+        o += align_up((size_t)n * 8, 256);
+    }
+    for (int b = 0; b < 2; b++) {
+        w.idx[b] = (u32*)(p + o);
+        o += align_up((size_t)n * 4, 256);
+    }
+    w.total = o;
+    return w;
+}
+
+size_t sort_ws_bytes(i64 n) { return carve(nullptr, n).total; }
+
+// ------------------------------------------------------------------------------------------- histogram
+template <int DT>
+__global__ void __launch_bounds__(256) hist_kernel(const typename KeyCodec<DT>::T* __restrict__ keys, i64 n,
+                                                    u64* __restrict__ ghist) {
+    __shared__ u32 sh[NPASS][RADIX];
+    for (int i = threadIdx.x; i < NPASS * RADIX; i += 256) (&sh[0][0])[i] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    constexpr int U = 4;
+    const i64 chunk = 256 * U;
+    for (i64 base = (i64)blockIdx.x * chunk; base < n; base += (i64)gridDim.x * chunk) {
+        u64 k[U];
+        bool valid[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const i64 i = base + u * 256 + threadIdx.x;
+            valid[u] = i < n;
+            k[u] = valid[u] ? KeyCodec<DT>::enc(__ldcs(&keys[i])) : 0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const u32 act = __ballot_sync(0xffffffffu, valid[u]);
+            if (valid[u]) {
+#pragma unroll
+                for (int p = 0; p < NPASS; p++) {
+                    const u32 d = (u32)(k[u] >> (8 * p)) & 255u;
+                    int same;
+                    __match_all_sync(act, d, &same);
+                    if (same) {
+                        if (lane == __ffs(act) - 1) atomicAdd(&sh[p][d], (u32)__popc(act));
+                    } else {
+                        atomicAdd(&sh[p][d], 1u);
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NPASS * RADIX; i += 256) {
+        const u32 c = (&sh[0][0])[i];
+        if (c) atomicAdd(&ghist[i], (u64)c);
+    }
+}
+
+// ------------------------------------------------------------------------------------------- plan
+__global__ void __launch_bounds__(RADIX) plan_kernel(const u64* __restrict__ ghist, i64 n, SortPlan* plan) {
+    __shared__ u64 sc[RADIX];
+    __shared__ int trivial[NPASS];
+    const int d = threadIdx.x;
+    for (int p = 0; p < NPASS; p++) {
+        const u64 c = ghist[p * RADIX + d];
+        sc[d] = c;
+        const int t = __syncthreads_or(c == (u64)n);
+        if (d == 0) trivial[p] = t;
+        u64 ex = 0;
+        for (int j = 0; j < d; j++) ex += sc[j];
+        plan->digit_base[p][d] = ex;
+        __syncthreads();
+    }
+    if (d == 0) {
+        int na = 0, last = -1;
+        for (int p = 0; p < NPASS; p++)
+            if (!trivial[p]) last = p;
+        for (int p = 0; p < NPASS; p++) {
+            const int a = !trivial[p];
+            plan->active[p] = a;
+            plan->first[p] = a && (na == 0);
+            plan->last[p] = a && (p == last);
+            plan->src[p] = (na + 1) & 1;  // previous pass's destination
+            plan->dst[p] = na & 1;
+            if (a) na++;
+        }
+        plan->n_active = na;
+    }
+}
+
+// ------------------------------------------------------------------------------------------- onesweep pass
+struct PassSmem {
+    u64 keys[STILE];
+    u32 idx[STILE];
+    u32 whist[SWARPS][RADIX];
+    u32 dstart[RADIX];   // exclusive digit offsets inside the tile
+    i64 gbase[RADIX];    // global position of tile-sorted slot p with digit d is gbase[d] + p
+    u32 wsum[SWARPS];
+    u32 tile;
+};
+
+template <int DT>
+__global__ void __launch_bounds__(ST) onesweep_pass(const typename KeyCodec<DT>::T* __restrict__ in_keys,
+                                                     u64* keysA, u64* keysB, u32* idxA, u32* idxB,
+                                                     i64* __restrict__ idx_out,
+                                                     typename KeyCodec<DT>::T* __restrict__ keys_sorted_out,
+                                                     u64* __restrict__ enc_sorted_out, const SortPlan* __restrict__ plan,
+                                                     int pass, u64* states, u32* tickets, i64 n, int descending) {
+    if (!plan->active[pass]) return;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PassSmem& s = *reinterpret_cast<PassSmem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool first = plan->first[pass] != 0, last = plan->last[pass] != 0;
+    const u64* src_keys = plan->src[pass] ? keysB : keysA;
+    const u32* src_idx = plan->src[pass] ? idxB : idxA;
+    u64* dst_keys = plan->dst[pass] ? keysB : keysA;
+    u32* dst_idx = plan->dst[pass] ? idxB : idxA;
+    const u32 epoch = (u32)pass + 1;
+    const int shift = 8 * pass;
+
+    for (int i = tid; i < SWARPS * RADIX; i += ST) (&s.whist[0][0])[i] = 0;
+    if (tid == 0) s.tile = atomicAdd(&tickets[pass], 1u);
+    __syncthreads();
+    const i64 tile = s.tile;
+    const i64 base = tile * STILE;
+    const int tile_n = (int)((n - base) < (i64)STILE ? (n - base) : (i64)STILE);
+
+    // ---- load: warp w owns tile slots [w*512, (w+1)*512), item k of lane l is slot w*512 + k*32 + l
+    u64 key[SI];
+    u32 idx[SI];
+    const int wslot = warp * (SI * 32);
+#pragma unroll
+    for (int k = 0; k < SI; k++) {
+        const int slot = wslot + k * 32 + lane;
+        const i64 g = base + slot;
+        if (slot < tile_n) {
+            if (first) {
+                key[k] = KeyCodec<DT>::enc(__ldcs(&in_keys[g]));
+                idx[k] = (u32)g;
+            } else {
+                key[k] = __ldcs(&src_keys[g]);
+                idx[k] = __ldcs(&src_idx[g]);
+            }
+        } else {
+            key[k] = ~0ull;
+            idx[k] = 0;
+        }
+    }
+    // ---- warp-level multisplit: rank of each key among the warp's keys with the same digit
+    u32 rank[SI];
+    const u32 lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int k = 0; k < SI; k++) {
+        const bool valid = (wslot + k * 32 + lane) < tile_n;
+        const u32 d = (u32)(key[k] >> shift) & 255u;
+        const u32 peers = __match_any_sync(0xffffffffu, valid ? d : 256u);
+        const int leader = __ffs(peers) - 1;
+        u32 old = 0;
+        if (valid && lane == leader) {
+            old = s.whist[warp][d];
+            s.whist[warp][d] = old + __popc(peers);
+        }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        rank[k] = old + __popc(peers & lt);
+        __syncwarp();
+    }
+    __syncthreads();
+    // ---- per digit (thread d): exclusive offsets across warps, tile count, publish, look back
+    {
+        const int d = tid;
+        u32 run = 0;
+#pragma unroll
+        for (int w = 0; w < SWARPS; w++) {
+            const u32 c = s.whist[w][d];
+            s.whist[w][d] = run;
+            run += c;
+        }
+        const u32 cnt = run;
+        u64* my_state = &states[(size_t)tile * RADIX + d];
+        st_relaxed_u64(my_state, lb_pack(tile == 0 ? KGB_LB_PREFIX : KGB_LB_AGG, epoch, cnt));
+        // exclusive scan of cnt over the 256 digits -> dstart
+        u32 inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u32 v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+        }
+        if (lane == 31) s.wsum[warp] = inc;
+        __syncthreads();
+        u32 wpre = 0;
+#pragma unroll
+        for (int w = 0; w < SWARPS; w++)
+            if (w < warp) wpre += s.wsum[w];
+        const u32 dstart = wpre + inc - cnt;
+        s.dstart[d] = dstart;
+        u64 excl = 0;
+        if (tile > 0) {
+            i64 t = tile - 1;
+            u32 spins = 0;
+            while (true) {
+                const u64 w = ld_relaxed_u64(&states[(size_t)t * RADIX + d]);
+                const u64 f = lb_flag(w, epoch);
+                if (f == 0) {
+                    if (++spins > (1u << 26)) __trap();  // a predecessor never published: fail, do not hang
+                    continue;
+                }
+                excl += lb_count(w);
+                if (f == KGB_LB_PREFIX) break;
+                t--;
+            }
+            st_relaxed_u64(my_state, lb_pack(KGB_LB_PREFIX, epoch, excl + cnt));
+        }
+        s.gbase[d] = (i64)(plan->digit_base[pass][d] + excl) - (i64)dstart;
+    }
+    __syncthreads();
+    // ---- scatter into tile-sorted order in shared memory
+#pragma unroll
+    for (int k = 0; k < SI; k++) {
+        if ((wslot + k * 32 + lane) < tile_n) {
+            const u32 d = (u32)(key[k] >> shift) & 255u;
+            const u32 p = s.dstart[d] + s.whist[warp][d] + rank[k];
+            s.keys[p] = key[k];
+            s.idx[p] = idx[k];
+        }
+    }
+    __syncthreads();
+    // ---- coalesced runs out to global
+#pragma unroll
+    for (int j = 0; j < SI; j++) {
+        const int p = j * ST + tid;
+        if (p < tile_n) {
+            const u64 kk = s.keys[p];
+            const u32 d = (u32)(kk >> shift) & 255u;
+            const i64 gp = s.gbase[d] + p;
+            if (last) {
+                const i64 op = descending ? (n - 1 - gp) : gp;
+                idx_out[op] = (i64)s.idx[p];
+                if (keys_sorted_out) keys_sorted_out[op] = KeyCodec<DT>::dec(kk);
+                if (enc_sorted_out) enc_sorted_out[op] = kk;
+            } else {
+                dst_keys[gp] = kk;
+                dst_idx[gp] = s.idx[p];
+            }
+        }
+    }
+}
+
+// all keys equal on every digit (or n == 1): the stable permutation is the identity
+template <int DT>
+__global__ void __launch_bounds__(256) sort_identity_kernel(const typename KeyCodec<DT>::T* __restrict__ in_keys,
+                                                             i64* __restrict__ idx_out,
+                                                             typename KeyCodec<DT>::T* __restrict__ keys_sorted_out,
+                                                             u64* __restrict__ enc_sorted_out,
+                                                             const SortPlan* __restrict__ plan, i64 n, int descending) {
+    if (plan->n_active != 0) return;
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const i64 op = descending ? (n - 1 - i) : i;
+        idx_out[op] = i;
+        if (keys_sorted_out) keys_sorted_out[op] = KeyCodec<DT>::dec(KeyCodec<DT>::enc(in_keys[i]));
+        if (enc_sorted_out) enc_sorted_out[op] = KeyCodec<DT>::enc(in_keys[i]);
+    }
+}
+
+template <int DT>
+static int sort_impl(const void* keys, i64 n, int descending, i64* idx_out, void* keys_sorted_out, u64* enc_sorted_out,
+                     void* ws, cudaStream_t st) {
+    typedef typename KeyCodec<DT>::T T;
+    SortWs w = carve(ws, n);
+    const unsigned tiles = (unsigned)((n + STILE - 1) / STILE);
+    static bool attr_set[64] = {false};
+    const int dev = current_device();
+    if (!attr_set[dev]) {
+        KGB_CUDA_CHECK(cudaFuncSetAttribute(onesweep_pass<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)sizeof(PassSmem)));
+        attr_set[dev] = true;
+    }
+    KGB_CUDA_CHECK(cudaMemsetAsync(w.hist, 0, w.zero_bytes, st));
+    long long hb = (n + 1023) / 1024;
+    const long long cap = (long long)sm_count() * 8;
+    if (hb > cap) hb = cap;
+    hist_kernel<DT><<<(unsigned)hb, 256, 0, st>>>((const T*)keys, n, w.hist);
+    plan_kernel<<<1, RADIX, 0, st>>>(w.hist, n, w.plan);
+    for (int p = 0; p < NPASS; p++) {
+        if ((DT == KGB_F32 || DT == KGB_I32 || DT == KGB_F32_RAW) && p >= 4) break;  // 32-bit keys: upper digits are zero
+        onesweep_pass<DT><<<tiles, ST, sizeof(PassSmem), st>>>((const T*)keys, w.keys[0], w.keys[1], w.idx[0], w.idx[1],
+                                                               idx_out, (T*)keys_sorted_out, enc_sorted_out, w.plan, p,
+                                                               w.states, w.tickets, n, descending);
+    }
+    long long ib = (n + 255) / 256;
+    if (ib > cap) ib = cap;
+    sort_identity_kernel<DT><<<(unsigned)ib, 256, 0, st>>>((const T*)keys, idx_out, (T*)keys_sorted_out, enc_sorted_out,
+                                                           w.plan, n, descending);
+    KGB_CUDA_CHECK(cudaGetLastError());
+    return KGB_OK;
+}
+
+int sort_pairs(const void* keys, int dtype, i64 n, int descending, i64* idx_out, void* keys_sorted_out,
+               u64* enc_sorted_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+    KGB_REQUIRE(current_device() >= 0, "kgb_init() has not been called on this thread");
+    KGB_REQUIRE(n >= 0 && n < 0xffffffffll, "argsort: n must be below 2^32");
+    if (n == 0) return KGB_OK;
+    KGB_REQUIRE(keys && idx_out && ws && ws_bytes >= sort_ws_bytes(n), "argsort: null pointer or workspace too small");
+    switch (dtype) {
+        case KGB_F64: return sort_impl<KGB_F64>(keys, n, descending, idx_out, keys_sorted_out, enc_sorted_out, ws, st);
+        case KGB_I64: return sort_impl<KGB_I64>(keys, n, descending, idx_out, keys_sorted_out, enc_sorted_out, ws, st);
+        case KGB_F32: return sort_impl<KGB_F32>(keys, n, descending, idx_out, keys_sorted_out, enc_sorted_out, ws, st);
+        case KGB_I32: return sort_impl<KGB_I32>(keys, n, descending, idx_out, keys_sorted_out, enc_sorted_out, ws, st);
+        case KGB_F64_RAW: return sort_impl<KGB_F64_RAW>(keys, n, descending, idx_out, keys_sorted_out, enc_sorted_out, ws, st);
+        case KGB_F32_RAW: return sort_impl<KGB_F32_RAW>(keys, n, descending, idx_out, keys_sorted_out, enc_sorted_out, ws, st);
+    }
+    set_error("argsort: unsupported dtype %d", dtype);
+    return KGB_EINVAL;
+}
+
+}  // namespace kgb
+
+using namespace kgb;
+
+extern "C" int kgb_argsort_workspace_bytes(int32_t dtype, int64_t n, size_t* out_bytes) {
+    KGB_REQUIRE(out_bytes && n >= 0 && dtype_size(dtype) >= 4, "kgb_argsort_workspace_bytes: bad arguments");
+    *out_bytes = sort_ws_bytes(n);
+    return KGB_OK;
+}
+
+extern "C" int kgb_argsort(const void* keys, int32_t dtype, int64_t n, int32_t descending, int64_t* idx_out,
+                           void* keys_sorted_out, void* workspace, size_t workspace_bytes, void* stream) {
+    return sort_pairs(keys, dtype, n, descending, (i64*)idx_out, keys_sorted_out, nullptr, workspace, workspace_bytes,
+                      (cudaStream_t)stream);
+}

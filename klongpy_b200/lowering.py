@@ -1,0 +1,234 @@
+"""Compiler-IR -> fused kernel stages  (the backend half of klongpy/compiler.py).
+
+The reference lowers the tuple IR of `compiler.py:37-113` to a Python source string of unfused NumPy calls
+(`numpy_backend.py:105-178`): every node is a pass over memory with a temporary.  Here the tree becomes a small
+DAG of *stages* (SURVEY.md Appendix C scheduling rule):
+
+  * every `reduce` / `scan` node is one kernel whose argument sub-tree is its fused prologue,
+  * a `reduce` whose argument contains exactly one `scan` (max-drawdown, `|/(|\\ts)-ts`) becomes ONE
+    scan+epilogue+reduce kernel (8 B/elem instead of 8+16+16),
+  * the enclosing elementwise tree is one more fused MAP kernel that reads stage results as 0-d device
+    scalars (never synced to the host) or arrays.
+
+Parameter order = first reference order = `BackendProvider._collect_params` (base.py:345-365) = var_syms.
+Anything the kernels do not support RAISES, so the interpreter's silent fallback
+(interpreter.py:697-701) takes the eager path instead of mis-computing.
+"""
+import numpy as np
+
+from . import _lib, ops
+from .array import DeviceArray
+
+_BIN = {"+": "add", "-": "sub", "*": "mul", "%": "div", "^": "pow"}
+_CMP = {"=": "eq", ">": "gt", "<": "lt"}
+
+
+def collect_params(ir):
+    params, seen = [], set()
+
+    def walk(node):
+        t = node[0]
+        if t == "var":
+            if node[1] not in seen:
+                seen.add(node[1])
+                params.append(node[1])
+        elif t in ("binop", "cmp"):
+            walk(node[2])
+            walk(node[3])
+        elif t == "negate":
+            walk(node[1])
+        elif t in ("reduce", "scan"):
+            walk(node[2])
+    walk(ir)
+    return params
+
+
+def _count(node, kinds):
+    t = node[0]
+    c = 1 if t in kinds else 0
+    if t in ("binop", "cmp"):
+        return c + _count(node[2], kinds) + _count(node[3], kinds)
+    if t == "negate":
+        return c + _count(node[1], kinds)
+    if t in ("reduce", "scan"):
+        return c + _count(node[2], kinds)
+    return c
+
+
+def _validate(node):
+    t = node[0]
+    if t == "literal":
+        if type(node[1]) not in (int, float, bool):
+            raise TypeError("literal must be int or float")
+    elif t == "var":
+        pass
+    elif t == "binop":
+        if node[1] not in _BIN:
+            raise ValueError(f"unsupported binop {node[1]!r}")
+        _validate(node[2])
+        _validate(node[3])
+    elif t == "cmp":
+        if node[1] not in _CMP:
+            raise ValueError(f"unsupported cmp {node[1]!r}")
+        _validate(node[2])
+        _validate(node[3])
+    elif t == "negate":
+        _validate(node[1])
+    elif t in ("reduce", "scan"):
+        if node[1] not in ops.RED:
+            raise ValueError(f"unsupported fold op {node[1]!r}")
+        _validate(node[2])
+    else:
+        raise ValueError(f"unknown IR node {t!r}")
+
+
+class _Emitter:
+    """Builds one stage's postfix code; maps global value slots to the stage's local argument indices."""
+
+    def __init__(self):
+        self.code = []
+        self.slots = []  # global slot ids in local-arg order
+
+    def arg(self, slot):
+        if slot not in self.slots:
+            self.slots.append(slot)
+        self.code += [ops.OP_ARG, self.slots.index(slot)]
+
+
+class Stage:
+    __slots__ = ("mode", "red", "red2", "code", "code2", "slots", "out_slot")
+
+    def __init__(self, mode, red, red2, code, code2, slots, out_slot):
+        self.mode, self.red, self.red2 = mode, red, red2
+        self.code, self.code2, self.slots, self.out_slot = tuple(code), tuple(code2) if code2 else None, slots, out_slot
+
+
+class Plan:
+    """Stage list for one IR tree.  Slots 0..n_params-1 are the call arguments; each stage adds one slot."""
+
+    def __init__(self, ir):
+        _validate(ir)
+        self.params = collect_params(ir)
+        self.n_slots = len(self.params)
+        self.stages = []
+        em = _Emitter()
+        self._emit(ir, em, None)
+        if len(em.code) == 2 and em.code[0] == ops.OP_ARG and em.slots[0] >= len(self.params):
+            self.result_slot = em.slots[0]  # the tree's root was itself a stage
+        else:
+            self.result_slot = self._add_stage(_lib.MODE_MAP, 0, 0, em.code, None, em.slots)
+
+    def _add_stage(self, mode, red, red2, code, code2, slots):
+        slot = self.n_slots
+        self.n_slots += 1
+        self.stages.append(Stage(mode, red, red2, code, code2, list(slots), slot))
+        return slot
+
+    def _emit(self, node, em, scan_hole):
+        t = node[0]
+        if t == "literal":
+            em.code += ops.lit(node[1])
+        elif t == "var":
+            em.arg(self.params.index(node[1]))
+        elif t == "binop":
+            self._emit(node[2], em, scan_hole)
+            self._emit(node[3], em, scan_hole)
+            em.code.append(ops.OPC[_BIN[node[1]]])
+        elif t == "cmp":
+            self._emit(node[2], em, scan_hole)
+            self._emit(node[3], em, scan_hole)
+            em.code.append(ops.OPC[_CMP[node[1]]])
+        elif t == "negate":
+            self._emit(node[1], em, scan_hole)
+            em.code.append(ops.OPC["neg"])
+        elif t == "scan" and scan_hole is not None and node is scan_hole:
+            em.code.append(ops.OP_SCANVAL)
+        elif t == "reduce":
+            arg = node[2]
+            if _count(arg, ("scan",)) == 1 and _count(arg, ("reduce",)) == 0:
+                scan_node = _find(arg, "scan")
+                if _count(scan_node[2], ("scan", "reduce")) == 0:
+                    # fused scan -> epilogue -> reduce
+                    sub = _Emitter()
+                    self._emit(scan_node[2], sub, None)
+                    epi = _Emitter()
+                    epi.slots = sub.slots  # shared argument table
+                    self._emit(arg, epi, scan_node)
+                    slot = self._add_stage(_lib.MODE_SCANRED, ops.RED[scan_node[1]], ops.RED[node[1]], sub.code,
+                                           epi.code, epi.slots)
+                    em.arg(slot)
+                    return
+            sub = _Emitter()
+            self._emit(arg, sub, None)
+            slot = self._add_stage(_lib.MODE_REDUCE, ops.RED[node[1]], 0, sub.code, None, sub.slots)
+            em.arg(slot)
+        elif t == "scan":
+            sub = _Emitter()
+            self._emit(node[2], sub, None)
+            slot = self._add_stage(_lib.MODE_SCAN, ops.RED[node[1]], 0, sub.code, None, sub.slots)
+            em.arg(slot)
+        else:
+            raise ValueError(f"unknown IR node {t!r}")
+
+
+def _find(node, kind):
+    if node[0] == kind:
+        return node
+    t = node[0]
+    kids = (node[2], node[3]) if t in ("binop", "cmp") else (node[1],) if t == "negate" else \
+        (node[2],) if t in ("reduce", "scan") else ()
+    for k in kids:
+        r = _find(k, kind)
+        if r is not None:
+            return r
+    return None
+
+
+def _is_arraylike(v):
+    return isinstance(v, DeviceArray) and v._t.dim() > 0
+
+
+def make_callable(ir):
+    """Return fn(*args) executing the plan on device arrays.  Raises on unsupported argument kinds."""
+    plan = Plan(ir)
+    n_params = len(plan.params)
+
+    def fn(*args):
+        if len(args) != n_params:
+            raise TypeError(f"compiled expression takes {n_params} arguments ({len(args)} given)")
+        vals = list(args) + [None] * (plan.n_slots - n_params)
+        any_dev = False
+        for v in args:
+            if isinstance(v, DeviceArray):
+                any_dev = True
+                if v._t.dim() > 1:
+                    raise NotImplementedError("compiled kernels take 1-d arrays; N-d goes through the eager verbs")
+                if v._t.requires_grad:
+                    raise NotImplementedError("autograd operands take the eager (differentiable) path")
+            elif type(v) in (int, float) or isinstance(v, (np.integer, np.floating)):
+                pass
+            else:
+                raise TypeError(f"unsupported compiled-expression operand {type(v).__name__}")
+        if not any_dev:
+            raise NotImplementedError("no device operand: scalar expressions stay in the interpreter")
+        for st in plan.stages:
+            sargs = [vals[s] for s in st.slots]
+            has_array = any(_is_arraylike(a) for a in sargs)
+            if st.mode != _lib.MODE_MAP and not has_array:
+                raise NotImplementedError("fold over a scalar: interpreter semantics apply")
+            if st.mode in (_lib.MODE_REDUCE, _lib.MODE_SCANRED):
+                n = next(a for a in sargs if _is_arraylike(a))._t.numel()
+                if n == 0:
+                    # np.add.reduce([]) -> 0.0 and np.multiply.reduce([]) -> 1.0 in the result dtype;
+                    # np.maximum.reduce([]) raises (numpy_backend.py:163) -> interpreter fallback
+                    if st.mode == _lib.MODE_REDUCE and st.red in (_lib.RED_ADD, _lib.RED_MUL):
+                        vals[st.out_slot] = ops.empty_fold(st.code, sargs, st.red)
+                        continue
+                    raise ValueError("zero-size array to reduction operation which has no identity")
+            if not any(isinstance(a, DeviceArray) for a in sargs):
+                raise NotImplementedError("stage without device operands")
+            vals[st.out_slot] = ops.run(st.code, sargs, mode=st.mode, red=st.red, code2=st.code2, red2=st.red2)
+        return vals[plan.result_slot]
+
+    fn.plan = plan
+    return fn

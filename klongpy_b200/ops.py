@@ -1,0 +1,652 @@
+"""Host-side bridge from Python operands to libkgb200 launches.
+
+Everything here is argument marshalling: classify operands (device array / 0-d device scalar / host scalar),
+build or look up the postfix program, allocate the result with torch (memory container only) and launch on
+torch's current stream.  Host scalars combined with host scalars stay on the host (they are interpreter
+control flow) — no device value ever falls back to NumPy.
+"""
+import ctypes
+import struct
+
+import numpy as np
+import torch
+
+from . import _lib
+from .array import DeviceArray, _K2T, kgb_dtype, torch_dtype_of
+
+# ---------------------------------------------------------------------------------------- opcodes
+OP_ARG, OP_LIT_I64, OP_LIT_F64, OP_SCANVAL = 1, 2, 3, 4
+OPC = {
+    "add": 16, "sub": 17, "mul": 18, "div": 19, "pow": 20, "eq": 21, "gt": 22, "lt": 23,
+    "max": 24, "min": 25, "fmod": 26, "eq_b": 27, "gt_b": 28, "lt_b": 29, "ne_b": 30, "ge_b": 31, "le_b": 32,
+    "isclose": 33,
+    "neg": 48, "abs": 49, "floor": 50, "floor_i64": 51, "trunc": 52, "recip": 53, "not_b": 54,
+    "to_f64": 55, "to_i64": 56, "to_f32": 57, "to_b8": 58, "to_i32": 59,
+    "sqrt": 64, "exp": 65, "log": 66, "sin": 67, "cos": 68, "tan": 69, "tanh": 70, "ceil": 71, "sign": 72,
+    "isnan_b": 73, "isinf_b": 74, "log2": 75, "log10": 76, "sinh": 77, "cosh": 78, "asin": 79, "acos": 80,
+    "atan": 81, "expm1": 82, "log1p": 83, "square": 84,
+    "where": 96,
+}
+RED = {"add": _lib.RED_ADD, "mul": _lib.RED_MUL, "max": _lib.RED_MAX, "min": _lib.RED_MIN,
+       "+": _lib.RED_ADD, "*": _lib.RED_MUL, "|": _lib.RED_MAX, "&": _lib.RED_MIN}
+
+# numpy equivalents for host-scalar (control-flow) arithmetic
+_HOST = {
+    "add": np.add, "sub": np.subtract, "mul": np.multiply, "div": np.divide, "pow": np.power,
+    "max": np.maximum, "min": np.minimum, "fmod": np.fmod, "eq_b": np.equal, "gt_b": np.greater,
+    "lt_b": np.less, "ne_b": np.not_equal, "ge_b": np.greater_equal, "le_b": np.less_equal,
+    "isclose": np.isclose,
+    "neg": np.negative, "abs": np.abs, "floor": np.floor, "trunc": np.trunc, "ceil": np.ceil,
+    "recip": lambda x: np.reciprocal(np.asarray(x, dtype=float))[()], "not_b": np.logical_not,
+    "sqrt": np.sqrt, "exp": np.exp, "log": np.log, "sin": np.sin, "cos": np.cos, "tan": np.tan,
+    "tanh": np.tanh, "sign": np.sign, "isnan_b": np.isnan, "isinf_b": np.isinf, "log2": np.log2,
+    "log10": np.log10, "sinh": np.sinh, "cosh": np.cosh, "asin": np.arcsin, "acos": np.arccos,
+    "atan": np.arctan, "expm1": np.expm1, "log1p": np.log1p, "square": np.square,
+    "floor_i64": lambda x: int(np.floor(x)),
+}
+
+
+def lit(v):
+    """Inline literal words for a postfix program."""
+    if isinstance(v, (bool, np.bool_)):
+        v = int(v)
+    if isinstance(v, (int, np.integer)):
+        lo, hi = struct.unpack("<ii", struct.pack("<q", int(v)))
+        return [OP_LIT_I64, lo, hi]
+    lo, hi = struct.unpack("<ii", struct.pack("<d", float(v)))
+    return [OP_LIT_F64, lo, hi]
+
+
+# ---------------------------------------------------------------------------------------- device state
+_default_device = None
+
+
+def set_default_device(device):
+    global _default_device
+    _default_device = torch.device(device)
+
+
+def default_device():
+    global _default_device
+    if _default_device is None:
+        if not torch.cuda.is_available():
+            raise _lib.KgbError("klongpy_b200 needs an NVIDIA B200 (sm_100) GPU; there is no CPU fallback")
+        _default_device = torch.device("cuda", torch.cuda.current_device())
+    return _default_device
+
+
+def _lib_for(device):
+    """Library bound to `device` on this thread (and the raw stream to launch on)."""
+    if device.type != "cuda":
+        lib = _lib.load_for_host_device(device)  # only a test double registers itself here
+        return lib, None
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    lib = _lib.bind_device(idx)
+    return lib, ctypes.c_void_p(torch.cuda.current_stream(idx).cuda_stream)
+
+
+# ---------------------------------------------------------------------------------------- operands
+_SCALARS = (int, float, bool, np.integer, np.floating, np.bool_)
+
+
+def is_host_scalar(x):
+    return isinstance(x, _SCALARS) or (isinstance(x, np.ndarray) and x.ndim == 0 and x.dtype.kind in "ifub")
+
+
+def is_operand(x):
+    return isinstance(x, DeviceArray) or is_host_scalar(x) or \
+        (isinstance(x, np.ndarray) and x.dtype.kind in "ifub")
+
+
+def asarray(a, device=None, dtype=None):
+    """Host data -> DeviceArray (one H2D copy).  DeviceArrays pass through unchanged
+    (same-object contract, tests/test_torch_backend.py:112-118)."""
+    if isinstance(a, DeviceArray):
+        return a if dtype is None else astype(a, dtype)
+    device = torch.device(device) if device is not None else default_device()
+    if isinstance(a, torch.Tensor):
+        t = a if a.device == device else a.to(device)
+        return DeviceArray(t)
+    arr = np.asarray(a, dtype=dtype)
+    if arr.dtype == object or arr.dtype.kind not in "ifub":
+        raise TypeError(f"cannot place dtype {arr.dtype} on the device")
+    td = torch_dtype_of(arr.dtype)
+    arr = np.ascontiguousarray(arr)
+    t = torch.from_numpy(arr) if arr.dtype in (np.float64, np.int64, np.float32, np.int32, np.bool_) \
+        else torch.from_numpy(arr.astype(np.int64 if arr.dtype.kind in "iu" else np.float64))
+    return DeviceArray(t.to(device=device, dtype=td))
+
+
+def contiguous(x):
+    return x if x._t.is_contiguous() else DeviceArray(x._t.contiguous())
+
+
+def empty(shape, kdt, device):
+    return DeviceArray(torch.empty(shape, dtype=_K2T[kdt], device=device))
+
+
+# ---------------------------------------------------------------------------------------- program runner
+_handles = {}
+
+
+def _classify(x, device):
+    """-> (kind, kgb dtype, keepalive object, raw pointer)"""
+    if isinstance(x, DeviceArray):
+        if x._t.device != device:
+            raise ValueError(f"operand on {x._t.device}, expected {device}")
+        x = contiguous(x)
+        kind = _lib.ARG_DEVSCALAR if x._t.numel() == 1 and x._t.dim() == 0 else _lib.ARG_ARRAY
+        return kind, kgb_dtype(x._t), x, x._t.data_ptr()
+    if isinstance(x, (bool, np.bool_)):
+        x = int(x)
+    if isinstance(x, np.ndarray) and x.ndim == 0:
+        x = x[()]
+    if isinstance(x, (int, np.integer)):
+        c = ctypes.c_int64(int(x))
+        return _lib.ARG_SCALAR, _lib.I64, c, ctypes.addressof(c)
+    if isinstance(x, (float, np.floating)):
+        c = ctypes.c_double(float(x))
+        return _lib.ARG_SCALAR, _lib.F64, c, ctypes.addressof(c)
+    raise TypeError(f"unsupported operand type {type(x).__name__}")
+
+
+def run(code, args, mode=_lib.MODE_MAP, red=0, code2=None, red2=0, out_shape=None, device=None):
+    """Compile (cached) and launch one expression program.  Returns a DeviceArray."""
+    shape = None
+    for a in args:
+        if isinstance(a, DeviceArray):
+            device = a._t.device
+            if a._t.dim() > 0:
+                if shape is None:
+                    shape = tuple(a._t.shape)
+                elif tuple(a._t.shape) != shape:
+                    raise ValueError(f"operands could not be broadcast together with shapes {shape} {tuple(a._t.shape)}")
+    if device is None:
+        raise TypeError("run() needs at least one device operand")
+    if shape is None and out_shape is not None:
+        shape = tuple(out_shape)
+    lib, stream = _lib_for(device)
+    cls = [_classify(a, device) for a in args]
+    kinds = tuple(c[0] for c in cls)
+    dts = tuple(c[1] for c in cls)
+    code_t = tuple(code)
+    code2_t = tuple(code2) if code2 else ()
+    key = (device.index, code_t, code2_t, kinds, dts, mode, red, red2)
+    ent = _handles.get(key)
+    if ent is None:
+        n_args = len(args)
+        c_code = (ctypes.c_int32 * len(code_t))(*code_t)
+        c_code2 = (ctypes.c_int32 * len(code2_t))(*code2_t) if code2_t else None
+        c_k = (ctypes.c_int32 * max(n_args, 1))(*kinds)
+        c_d = (ctypes.c_int32 * max(n_args, 1))(*dts)
+        h = ctypes.c_void_p()
+        od = ctypes.c_int32()
+        _lib.check(lib.kgb_expr_compile(c_code, len(code_t), c_code2, len(code2_t), c_k, c_d, n_args, mode, red,
+                                        red2, ctypes.byref(h), ctypes.byref(od)), "kgb_expr_compile")
+        ent = (h, od.value)
+        _handles[key] = ent
+    h, od = ent
+    n = 1
+    if shape is not None:
+        for s in shape:
+            n *= s
+    if mode in (_lib.MODE_REDUCE, _lib.MODE_SCANRED):
+        oshape = ()
+        if n == 0:
+            raise ValueError("zero-size array to reduction operation which has no identity")
+    else:
+        oshape = shape if shape is not None else ()
+    if out_shape is not None:
+        oshape = out_shape
+    out = empty(oshape, od, device)
+    wsb = ctypes.c_size_t()
+    ws = None
+    ws_ptr = None
+    if mode != _lib.MODE_MAP:
+        _lib.check(lib.kgb_expr_workspace_bytes(h, n, ctypes.byref(wsb)), "kgb_expr_workspace_bytes")
+        ws = torch.empty(max(wsb.value, 64), dtype=torch.uint8, device=device)
+        ws_ptr = ws.data_ptr()
+    if n == 0:
+        return out  # empty MAP / SCAN: nothing to launch
+    argv = (ctypes.c_void_p * max(len(args), 1))(*[c[3] for c in cls])
+    _lib.check(lib.kgb_expr_launch(h, argv, n, out._t.data_ptr(), ws_ptr, wsb.value, stream), "kgb_expr_launch")
+    return out
+
+
+def empty_fold(code, args, red):
+    """Identity of an add / multiply fold over zero elements, in the dtype the expression would produce."""
+    m = run(code, args)  # zero-length MAP launch: compiles, allocates, launches nothing
+    t = m._t
+    dt = torch.int64 if t.dtype in (torch.bool, torch.int32) else t.dtype
+    fill = torch.zeros if red == _lib.RED_ADD else torch.ones
+    return DeviceArray(fill((), dtype=dt, device=t.device))
+
+
+# ---------------------------------------------------------------------------------------- eager ops
+def _device_of(*xs):
+    for x in xs:
+        if isinstance(x, DeviceArray):
+            return x._t.device
+    return None
+
+
+def _lift(x, device):
+    """Host numeric ndarrays (ndim>0) become device arrays; everything else is passed through."""
+    if isinstance(x, np.ndarray) and x.ndim > 0:
+        return asarray(x, device=device)
+    if isinstance(x, (list, tuple)):
+        return asarray(x, device=device)
+    return x
+
+
+def binary(op, a, b):
+    """Eager dyad: one-node program (dyads.py:6-21, 214-232, 588-803 call sites)."""
+    dev = _device_of(a, b)
+    if dev is None:
+        if is_host_scalar(a) and is_host_scalar(b):
+            return _HOST[op](a, b)
+        dev = default_device()
+    a, b = _lift(a, dev), _lift(b, dev)
+    if op == "pow":
+        a, b = _pow_operands(a, b)
+    return run([OP_ARG, 0, OP_ARG, 1, OPC[op]], [a, b])
+
+
+def _pow_operands(a, b):
+    # int ** negative int is a ValueError in numpy; like the reference's other non-numpy backends
+    # (tests/custom_backend.py:121-138, torch_backend.py:667-682) compute it in floating point.
+    def _is_int(x):
+        return (isinstance(x, DeviceArray) and x.dtype.kind in "iub") or isinstance(x, (int, np.integer))
+    if _is_int(a) and _is_int(b):
+        neg = (b < 0) if not isinstance(b, DeviceArray) else bool(any_(binary("lt_b", b, 0)))
+        if neg:
+            a = astype(a, np.float64) if isinstance(a, DeviceArray) else float(a)
+    return a, b
+
+
+def unary(op, a):
+    dev = _device_of(a)
+    if dev is None:
+        if is_host_scalar(a):
+            return _HOST[op](a)
+        a = _lift(a, default_device())
+    return run([OP_ARG, 0, OPC[op]], [a])
+
+
+def full(shape, value, dtype=None, device=None):
+    """np.full on the device: a MAP program over scalars only."""
+    dev = torch.device(device) if device is not None else default_device()
+    shape = (int(shape),) if isinstance(shape, (int, np.integer)) else tuple(int(s) for s in shape)
+    if isinstance(value, DeviceArray):
+        value = value.item()
+    if dtype is None:
+        dtype = np.int64 if isinstance(value, (int, np.integer, bool, np.bool_)) else np.float64
+    d = np.dtype(dtype)
+    if isinstance(value, (bool, np.bool_)):
+        value = int(value)
+    return run([OP_ARG, 0, OPC[_CAST[d]]], [value], out_shape=shape, device=dev)
+
+
+def where3(c, a, b):
+    dev = _device_of(c, a, b) or default_device()
+    c, a, b = _lift(c, dev), _lift(a, dev), _lift(b, dev)
+    return run([OP_ARG, 0, OP_ARG, 1, OP_ARG, 2, OPC["where"]], [c, a, b])
+
+
+_CAST = {np.dtype("float64"): "to_f64", np.dtype("int64"): "to_i64", np.dtype("float32"): "to_f32",
+         np.dtype("int32"): "to_i32", np.dtype("bool"): "to_b8"}
+
+
+def astype(a, dtype):
+    if dtype in (int, "int"):
+        dtype = np.int64
+    elif dtype in (float, "float"):
+        dtype = np.float64
+    elif dtype in (bool, "bool"):
+        dtype = np.bool_
+    d = np.dtype(dtype)
+    if d not in _CAST:
+        d = np.dtype(np.int64) if d.kind in "iu" else np.dtype(np.float64) if d.kind == "f" else d
+    if d not in _CAST:
+        raise TypeError(f"cannot cast device array to {dtype}")
+    if not isinstance(a, DeviceArray):
+        return np.asarray(a).astype(d)[()]
+    if a.dtype == d:
+        return copy(a)
+    return run([OP_ARG, 0, OPC[_CAST[d]]], [a])
+
+
+def copy(a):
+    if a._t.numel() == 0:
+        return DeviceArray(a._t.clone())
+    return run([OP_ARG, 0], [a])
+
+
+def reduce(op, a, code=None, args=None):
+    """op-fold over a 1-d device array (adverbs.py:232-243); N-d folds along axis 0 like numpy ufunc.reduce."""
+    if a._t.dim() == 0:
+        return a
+    if a._t.dim() > 1:
+        acc = DeviceArray(a._t[0])
+        for i in range(1, a._t.shape[0]):
+            acc = binary(op, acc, DeviceArray(a._t[i]))
+        return acc
+    if a._t.numel() == 0:
+        if op == "add":
+            return DeviceArray(torch.zeros((), dtype=a._t.dtype if a._t.dtype != torch.bool else torch.int64,
+                                           device=a._t.device))
+        if op == "mul":
+            return DeviceArray(torch.ones((), dtype=a._t.dtype if a._t.dtype != torch.bool else torch.int64,
+                                          device=a._t.device))
+        raise ValueError("zero-size array to reduction operation which has no identity")
+    return run([OP_ARG, 0], [a], mode=_lib.MODE_REDUCE, red=RED[op])
+
+
+def scan(op, a):
+    """inclusive op-scan (adverbs.py:325-332); N-d scans along axis 0."""
+    if a._t.dim() == 0:
+        return a
+    if a._t.dim() > 1:
+        rows = [DeviceArray(a._t[0])]
+        for i in range(1, a._t.shape[0]):
+            rows.append(binary(op, rows[-1], DeviceArray(a._t[i])))
+        out = torch.empty_like(a._t if a._t.dtype == rows[-1]._t.dtype else a._t.to(rows[-1]._t.dtype))
+        for i, r in enumerate(rows):
+            out[i].copy_(r._t)
+        return DeviceArray(out)
+    if a._t.numel() == 0:
+        return DeviceArray(a._t.clone())
+    return run([OP_ARG, 0], [a], mode=_lib.MODE_SCAN, red=RED[op])
+
+
+def all_(a):
+    if a._t.numel() == 0:
+        return True
+    flat = a.flatten()
+    return run([OP_ARG, 0, OPC["to_b8"]], [flat], mode=_lib.MODE_REDUCE, red=_lib.RED_MIN)
+
+
+def any_(a):
+    if a._t.numel() == 0:
+        return False
+    flat = a.flatten()
+    return run([OP_ARG, 0, OPC["to_b8"]], [flat], mode=_lib.MODE_REDUCE, red=_lib.RED_MAX)
+
+
+# ---------------------------------------------------------------------------------------- AOT kernels
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 64), dtype=torch.uint8, device=device)
+
+
+def argsort(a, descending=False, return_sorted=False):
+    """Stable grade (writer.py:97-122 -> numpy_backend.py:75-80)."""
+    a = contiguous(a)
+    if a._t.dim() != 1:
+        raise NotImplementedError("argsort: 1-d arrays only")
+    dev = a._t.device
+    lib, stream = _lib_for(dev)
+    if a._t.dtype == torch.bool:
+        a = astype(a, np.int64)
+    kdt = kgb_dtype(a._t)
+    n = a._t.numel()
+    idx = torch.empty(n, dtype=torch.int64, device=dev)
+    ks = torch.empty_like(a._t) if return_sorted else None
+    if n:
+        wsb = ctypes.c_size_t()
+        _lib.check(lib.kgb_argsort_workspace_bytes(kdt, n, ctypes.byref(wsb)))
+        ws = _ws(wsb.value, dev)
+        _lib.check(lib.kgb_argsort(a._t.data_ptr(), kdt, n, 1 if descending else 0, idx.data_ptr(),
+                                   ks.data_ptr() if ks is not None else None, ws.data_ptr(), wsb.value, stream),
+                   "kgb_argsort")
+    if return_sorted:
+        return DeviceArray(idx), DeviceArray(ks)
+    return DeviceArray(idx)
+
+
+def group(a):
+    """`=a` (monads.py:182-204): -> (order int64[n], starts int64[G+1]) with one D2H read of G."""
+    a = contiguous(a)
+    dev = a._t.device
+    lib, stream = _lib_for(dev)
+    if a._t.dtype == torch.bool:
+        a = astype(a, np.int64)
+    kdt = kgb_dtype(a._t)
+    n = a._t.numel()
+    order = torch.empty(n, dtype=torch.int64, device=dev)
+    starts = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    ng = torch.zeros(1, dtype=torch.int64, device=dev)
+    wsb = ctypes.c_size_t()
+    _lib.check(lib.kgb_group_workspace_bytes(kdt, n, ctypes.byref(wsb)))
+    ws = _ws(wsb.value, dev)
+    _lib.check(lib.kgb_group(a._t.data_ptr(), kdt, n, order.data_ptr(), starts.data_ptr(), ng.data_ptr(),
+                             ws.data_ptr(), wsb.value, stream), "kgb_group")
+    g = int(ng.item())
+    return DeviceArray(order), DeviceArray(starts[: g + 1]), g
+
+
+def _select(fn_name, a, needle=None):
+    a = contiguous(a)
+    dev = a._t.device
+    lib, stream = _lib_for(dev)
+    kdt = kgb_dtype(a._t)
+    n = a._t.numel()
+    pos = torch.empty(n, dtype=torch.int64, device=dev)
+    cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+    if n:
+        wsb = ctypes.c_size_t()
+        _lib.check(lib.kgb_select_workspace_bytes(n, ctypes.byref(wsb)))
+        ws = _ws(wsb.value, dev)
+        if fn_name == "find":
+            _lib.check(lib.kgb_find_equal(a._t.data_ptr(), kdt, n, ctypes.addressof(needle), pos.data_ptr(),
+                                          cnt.data_ptr(), ws.data_ptr(), wsb.value, stream), "kgb_find_equal")
+        else:
+            _lib.check(lib.kgb_nonzero(a._t.data_ptr(), kdt, n, pos.data_ptr(), cnt.data_ptr(), ws.data_ptr(),
+                                       wsb.value, stream), "kgb_nonzero")
+    c = int(cnt.item()) if n else 0
+    return DeviceArray(pos[:c])
+
+
+def find_equal(a, b):
+    """`a?b` for an atom b (dyads.py:342): ascending positions where a == b."""
+    a = a.flatten() if a._t.dim() != 1 else a
+    if a._t.dtype == torch.bool:
+        a = astype(a, np.int64)
+    if isinstance(b, DeviceArray):
+        b = b.item()
+    k = a.dtype.kind
+    if k == "f":
+        if a._t.dtype == torch.float32:
+            needle = ctypes.c_float(float(b))
+        else:
+            needle = ctypes.c_double(float(b))
+    else:
+        if isinstance(b, (float, np.floating)) and float(b) != int(b):
+            return DeviceArray(torch.empty(0, dtype=torch.int64, device=a._t.device))
+        needle = ctypes.c_int64(int(b)) if a._t.dtype == torch.int64 else ctypes.c_int32(int(b))
+    return _select("find", a, needle)
+
+
+def nonzero(a):
+    """np.where(flags)[0]"""
+    a = a.flatten() if a._t.dim() != 1 else a
+    return _select("nonzero", a)
+
+
+def unique_first(a):
+    """`?a` (monads.py:260-295): unique values in first-appearance order."""
+    a = contiguous(a)
+    dev = a._t.device
+    lib, stream = _lib_for(dev)
+    was_bool = a._t.dtype == torch.bool
+    if was_bool:
+        a = astype(a, np.int64)
+    kdt = kgb_dtype(a._t)
+    n = a._t.numel()
+    if n == 0:
+        return a
+    out = torch.empty_like(a._t)
+    first = torch.empty(n, dtype=torch.int64, device=dev)
+    cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+    wsb = ctypes.c_size_t()
+    _lib.check(lib.kgb_unique_first_workspace_bytes(kdt, n, ctypes.byref(wsb)))
+    ws = _ws(wsb.value, dev)
+    _lib.check(lib.kgb_unique_first(a._t.data_ptr(), kdt, n, out.data_ptr(), first.data_ptr(), cnt.data_ptr(),
+                                    ws.data_ptr(), wsb.value, stream), "kgb_unique_first")
+    c = int(cnt.item())
+    return DeviceArray(out[:c])
+
+
+def iota(n, device=None, start=0, step=1):
+    """`!n` (monads.py:52)."""
+    dev = torch.device(device) if device is not None else default_device()
+    lib, stream = _lib_for(dev)
+    out = torch.empty(int(n), dtype=torch.int64, device=dev)
+    if n:
+        _lib.check(lib.kgb_iota_i64(out.data_ptr(), int(n), int(start), int(step), stream), "kgb_iota_i64")
+    return DeviceArray(out)
+
+
+def gather(a, idx):
+    """`a@b` for an integer index list (dyads.py:176-181)."""
+    a = contiguous(a)
+    idx = contiguous(idx)
+    dev = a._t.device
+    lib, stream = _lib_for(dev)
+    if idx._t.dtype != torch.int64:
+        idx = astype(idx, np.int64)
+    n_idx = idx._t.numel()
+    if a._t.dim() == 0:
+        raise IndexError("too many indices for array")
+    row = 1
+    for s in a._t.shape[1:]:
+        row *= s
+    out = torch.empty(tuple(idx._t.shape) + tuple(a._t.shape[1:]), dtype=a._t.dtype, device=dev)
+    if n_idx and row:
+        err = torch.zeros(1, dtype=torch.int32, device=dev)
+        _lib.check(lib.kgb_gather(a._t.data_ptr(), a._t.element_size() * row, a._t.shape[0], idx._t.data_ptr(),
+                                  n_idx, out.data_ptr(), err.data_ptr(), stream), "kgb_gather")
+        if int(err.item()):
+            raise IndexError(f"index out of bounds for axis 0 with size {a._t.shape[0]}")
+    return DeviceArray(out)
+
+
+def reverse(a):
+    a = contiguous(a)
+    dev = a._t.device
+    lib, stream = _lib_for(dev)
+    out = torch.empty_like(a._t)
+    n = a._t.shape[0] if a._t.dim() else 1
+    row = a._t.numel() // n if n else 0
+    if n and row:
+        _lib.check(lib.kgb_reverse(a._t.data_ptr(), a._t.element_size() * row, n, out.data_ptr(), stream),
+                   "kgb_reverse")
+    return DeviceArray(out)
+
+
+def expand(counts):
+    """`&a` (monads.py:79): np.repeat(np.arange(len(a)), a)."""
+    counts = contiguous(counts)
+    if counts._t.dtype != torch.int64:
+        counts = astype(counts, np.int64)
+    dev = counts._t.device
+    n = counts._t.numel()
+    if n == 0:
+        return DeviceArray(torch.empty(0, dtype=torch.int64, device=dev))
+    if bool(any_(binary("lt_b", counts, 0))):
+        raise ValueError("repeats may not contain negative values.")
+    incl = scan("add", counts)
+    total = int(DeviceArray(incl._t[-1]).item())
+    lib, stream = _lib_for(dev)
+    out = torch.empty(total, dtype=torch.int64, device=dev)
+    if total:
+        _lib.check(lib.kgb_expand(counts._t.data_ptr(), incl._t.data_ptr(), n, total, out.data_ptr(), stream),
+                   "kgb_expand")
+    return DeviceArray(out)
+
+
+def array_equal(a, b):
+    """backend.array_equal (base.py:222-224): exact elementwise equality, one 4-byte D2H read."""
+    if tuple(a._t.shape) != tuple(b._t.shape):
+        return False
+    if a._t.numel() == 0:
+        return True
+    if a._t.dtype != b._t.dtype:
+        d = np.result_type(a.dtype, b.dtype)
+        a, b = astype(a, d), astype(b, d)
+    a, b = contiguous(a), contiguous(b)
+    dev = a._t.device
+    lib, stream = _lib_for(dev)
+    flag = torch.empty(1, dtype=torch.int32, device=dev)
+    _lib.check(lib.kgb_array_equal(a._t.data_ptr(), b._t.data_ptr(), kgb_dtype(a._t), a._t.numel(),
+                                   flag.data_ptr(), stream), "kgb_array_equal")
+    return bool(flag.item())
+
+
+def groupagg(keys, vals, n_groups, tables=None):
+    """1brc-style grouped (min, max, sum, count) (examples/1brc/worker.kg:3-5)."""
+    keys, vals = contiguous(keys), contiguous(vals)
+    dev = keys._t.device
+    lib, stream = _lib_for(dev)
+    if keys._t.dtype != torch.int64:
+        keys = astype(keys, np.int64)
+    if vals._t.dtype != torch.float64:
+        vals = astype(vals, np.float64)
+    n = keys._t.numel()
+    if vals._t.numel() != n:
+        raise ValueError("groupagg: keys and values differ in length")
+    G = int(n_groups)
+    acc = tables is not None
+    if not acc:
+        tables = (torch.empty(G, dtype=torch.float64, device=dev), torch.empty(G, dtype=torch.float64, device=dev),
+                  torch.empty(G, dtype=torch.float64, device=dev), torch.empty(G, dtype=torch.int64, device=dev))
+    else:
+        tables = tuple(t._t if isinstance(t, DeviceArray) else t for t in tables)
+    wsb = ctypes.c_size_t()
+    _lib.check(lib.kgb_groupagg_workspace_bytes(n, G, ctypes.byref(wsb)))
+    ws = _ws(wsb.value, dev)
+    _lib.check(lib.kgb_groupagg_f64(keys._t.data_ptr(), vals._t.data_ptr(), n, G, tables[0].data_ptr(),
+                                    tables[1].data_ptr(), tables[2].data_ptr(), tables[3].data_ptr(),
+                                    1 if acc else 0, ws.data_ptr(), wsb.value, stream), "kgb_groupagg_f64")
+    return tuple(DeviceArray(t) for t in tables)
+
+
+# ---------------------------------------------------------------------------------------- indexing
+def getitem(a, key):
+    t = a._t
+    if isinstance(key, DeviceArray):
+        if key._t.dim() == 0:
+            key = key.item()
+        elif key._t.dtype == torch.bool:
+            return gather(a, nonzero(key))
+        else:
+            return gather(a, key)
+    if isinstance(key, (bool, np.bool_)):
+        raise IndexError("boolean scalar index")
+    if isinstance(key, (int, np.integer)):
+        return DeviceArray(t[int(key)])
+    if isinstance(key, float) and float(key).is_integer():
+        return DeviceArray(t[int(key)])
+    if isinstance(key, slice):
+        if key.step is not None and key.step < 0:
+            n = t.shape[0]
+            start, stop, step = key.indices(n)
+            if step == -1 and key.start is None and key.stop is None:
+                return reverse(a)
+            count = len(range(start, stop, step))
+            return gather(a, iota(count, t.device, start, step))
+        return DeviceArray(t[key])
+    if isinstance(key, (list, np.ndarray)):
+        k = np.asarray(key)
+        if k.dtype == bool:
+            return gather(a, nonzero(asarray(k, device=t.device)))
+        if k.size == 0:
+            return DeviceArray(t[:0])
+        return gather(a, asarray(k.astype(np.int64), device=t.device))
+    if isinstance(key, tuple):
+        if all(isinstance(k, (int, np.integer, slice)) or k is None or k is Ellipsis for k in key) and \
+                not any(isinstance(k, slice) and k.step is not None and k.step < 0 for k in key):
+            return DeviceArray(t[tuple(int(k) if isinstance(k, np.integer) else k for k in key)])
+        raise NotImplementedError("advanced tuple indexing on device arrays")
+    if key is None or key is Ellipsis:
+        return DeviceArray(t[key])
+    raise IndexError(f"unsupported index type {type(key).__name__}")

@@ -1,0 +1,170 @@
+"""Op-table overrides for the verbs that bypass the backend seam.
+
+`= ? ! & ~ % + ^` (monads) and `? @ , :+` (dyads) call the *global* NumPy module or Python loops directly
+(`bknp.unique/where/arange/repeat/...`, SURVEY.md §8b "leaks": monads.py:52,79,202-203,256,275-281,316,442,
+dyads.py:176-181,336-342,563-585).  A provider cannot intercept those, so after constructing an interpreter
+on the b200 backend `install(klong)` replaces the affected entries of `klong._vm` / `klong._vd` (plain dicts
+built at interpreter.py:252-253) with device-aware versions.  Every override handles ONLY device arrays and
+defers to the reference implementation for everything else (strings, dicts, host object arrays).
+"""
+import numpy as np
+
+from . import ops
+from .array import DeviceArray
+
+
+def _is_dev(x):
+    return isinstance(x, DeviceArray)
+
+
+def _is_num(x):
+    return isinstance(x, (int, float, np.integer, np.floating)) and not isinstance(x, bool)
+
+
+def group_indices(a):
+    """`=a` on a device array: groups in ascending key order, indices ascending inside each group —
+    the contract of monads.py:182-204 (np.unique + one np.where per group) in one sort + one compaction."""
+    if a.size == 0:
+        return a
+    order, starts, g = ops.group(a.flatten() if a.ndim != 1 else a)
+    st = starts.to_numpy()
+    sizes = np.diff(st)
+    if g > 0 and (sizes == sizes[0]).all():
+        return order.reshape(g, int(sizes[0]))  # numpy would build a 2-d int64 array here too
+    out = np.empty(g, dtype=object)
+    t = order._t
+    for i in range(g):
+        out[i] = DeviceArray(t[int(st[i]):int(st[i + 1])])
+    return out
+
+
+def install(klong):
+    """Replace the leaking verbs of `klong` (a KlongInterpreter on the b200 backend).  Returns klong."""
+    backend = klong._backend
+    shim = backend.np
+    dev = shim.device
+    vm, vd = klong._vm, klong._vd
+    ref_m = dict(vm)
+    ref_d = dict(vd)
+
+    # ---------------------------------------------------------------- monads
+    def enumerate_(a):  # !a  (monads.py:38-52)
+        if not backend.is_integer(a):
+            raise RuntimeError(f"enumerate: invalid type error: {a}")
+        return ops.iota(int(a), dev)
+
+    def expand_where(a):  # &a  (monads.py:55-79)
+        if _is_dev(a):
+            if a.ndim == 0:
+                a = a.reshape(1)
+            return ops.expand(a)
+        if _is_num(a):
+            return ops.full(int(a), 0, np.int64, dev)
+        if isinstance(a, (list, np.ndarray)) and not (isinstance(a, np.ndarray) and a.dtype == object):
+            return ops.expand(ops.asarray(np.asarray(a, dtype=np.int64), device=dev))
+        return ref_m["&"](a)
+
+    def groupby(a):  # =a  (monads.py:182-204)
+        if _is_dev(a) and a.dtype.kind in "ifb":
+            return group_indices(a)
+        return ref_m["="](a)
+
+    def range_(a):  # ?a  (monads.py:260-295)
+        if _is_dev(a) and a.ndim == 1 and a.dtype.kind in "ifb":
+            return ops.unique_first(a)
+        return ref_m["?"](a)
+
+    def not_(a):  # ~a  (monads.py:240-257): 1 for 0, else 0, as int64
+        if _is_dev(a) and a.size > 0:
+            return ops.run([ops.OP_ARG, 0, ops.OPC["not_b"], ops.OPC["to_i64"]], [a])
+        return ref_m["~"](a)
+
+    def reciprocal(a):  # %a  (monads.py:298-316)
+        if _is_dev(a) and a.ndim > 0:
+            return ops.unary("recip", a)
+        return ref_m["%"](a)
+
+    def transpose(a):  # +a  (monads.py:430-442)
+        if _is_dev(a):
+            return shim.transpose(a) if a.ndim > 1 else a
+        return ref_m["+"](a)
+
+    def shape(a):  # ^a  (monads.py:372-405): metadata only, no D2H of the payload
+        if _is_dev(a):
+            return 0 if a.ndim == 0 else np.asarray(a.shape)
+        return ref_m["^"](a)
+
+    def reverse(a):  # |a  (monads.py:319-340)
+        if _is_dev(a):
+            return ops.reverse(a) if a.ndim > 0 else a
+        return ref_m["|"](a)
+
+    vm.update({"!": enumerate_, "&": expand_where, "=": groupby, "?": range_, "~": not_, "%": reciprocal,
+               "+": transpose, "^": shape, "|": reverse})
+
+    # ---------------------------------------------------------------- dyads
+    def find(a, b):  # a?b  (dyads.py:307-342)
+        if _is_dev(a) and (_is_num(b) or (_is_dev(b) and b.ndim == 0)):
+            return ops.find_equal(a, b)
+        return ref_d["?"](a, b)
+
+    def at_index(a, b):  # a@b  (dyads.py:140-191)
+        if _is_dev(a):
+            if _is_dev(b):
+                return a[b] if b.ndim == 0 else (ops.gather(a, b) if b.size else DeviceArray(a._t[:0]))
+            if isinstance(b, (int, np.integer)) and not isinstance(b, bool):
+                return a[int(b)]
+            if isinstance(b, (list, np.ndarray)):
+                bb = np.asarray(b)
+                if bb.size == 0:
+                    return DeviceArray(a._t[:0])
+                if bb.dtype.kind in "iu":
+                    return ops.gather(a, ops.asarray(bb.astype(np.int64), device=dev))
+        elif _is_dev(b) and isinstance(a, (np.ndarray, str, list)):
+            b = b.to_numpy() if b.ndim > 0 else b.item()
+        return ref_d["@"](a, b)
+
+    def join(a, b):  # a,b  (dyads.py:512-585)
+        if _is_dev(a) or _is_dev(b):
+            da = a if _is_dev(a) else None
+            db = b if _is_dev(b) else None
+            if da is not None and db is not None and da.ndim >= 1 and db.ndim >= 1:
+                if da.shape[0] == 0:
+                    return db
+                if da.ndim == db.ndim and da.shape[1:] == db.shape[1:]:
+                    return shim.concatenate((da, db))
+            elif da is not None and da.ndim == 1 and (_is_num(b) or (db is not None and db.ndim == 0)):
+                return shim.concatenate((da, _atom_array(b, da)))
+            elif db is not None and db.ndim == 1 and (_is_num(a) or (da is not None and da.ndim == 0)):
+                return shim.concatenate((_atom_array(a, db), db))
+            elif da is not None and db is not None and da.ndim == 0 and db.ndim == 0:
+                return shim.concatenate((da.reshape(1), db.reshape(1)))
+        return ref_d[","](a, b)
+
+    def _atom_array(x, like):
+        if _is_dev(x):
+            return x.reshape(1)
+        d = np.result_type(like.dtype, np.float64 if isinstance(x, (float, np.floating)) else np.int64)
+        return ops.full(1, x, d, dev)
+
+    def rotate(a, b):  # a:+b  (dyads.py:897-923): np.roll
+        if _is_dev(b) and b.ndim >= 1 and b.shape[0] > 0:
+            a = int(a)
+            n = b.shape[0]
+            s = a % n
+            if s == 0:
+                return b
+            idx = ops.run([ops.OP_ARG, 0, ops.OP_ARG, 1, ops.OPC["add"], ops.OP_ARG, 2, ops.OPC["fmod"]],
+                          [ops.iota(n, dev), n - s, n])
+            return ops.gather(b, idx)
+        return ref_d[":+"](a, b)
+
+    vd.update({"?": find, "@": at_index, ",": join, ":+": rotate})
+    klong._b200_installed = True
+    return klong
+
+
+def grouped_stats(keys, vals, n_groups):
+    """Grouped min/mean/max — the `stats`/`collect`/`merge` pipeline of examples/1brc/worker.kg:3-5 as one
+    kernel pass.  Returns device arrays (min, max, sum, count) ordered by ascending station id."""
+    return ops.groupagg(keys, vals, n_groups)

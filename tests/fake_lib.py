@@ -1,0 +1,373 @@
+"""Test double for libkgb200 on a box WITHOUT a GPU — test infrastructure only.
+
+Implements the C-ABI entry points `klongpy_b200.ops` calls, over HOST memory, by interpreting expression
+programs with NumPy and delegating the other primitives to the oracle.  It exists so that the host-side logic
+(provider, np-shim, IR lowering / stage scheduling, verb overrides, dtype rules) can be driven through the REAL
+KlongPy interpreter in the CPU-only container; it is registered explicitly by tests via
+`klongpy_b200._lib._host_double` and is never importable from the product package.
+"""
+import ctypes
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+from oracle import kg_oracle as O  # noqa: E402
+
+F64, I64, F32, I32, B8 = 0, 1, 2, 3, 4
+_NP = {F64: np.float64, I64: np.int64, F32: np.float32, I32: np.int32, B8: np.bool_}
+_CT = {F64: ctypes.c_double, I64: ctypes.c_int64, F32: ctypes.c_float, I32: ctypes.c_int32, B8: ctypes.c_bool}
+_CODE = {np.dtype(v): k for k, v in _NP.items()}
+
+
+def _addr(p):
+    if p is None:
+        return 0
+    if isinstance(p, int):
+        return p
+    if hasattr(p, "value"):
+        return p.value or 0
+    return ctypes.cast(p, ctypes.c_void_p).value or 0
+
+
+def view(p, n, dt):
+    a = _addr(p)
+    if n == 0 or a == 0:
+        return np.zeros(0, dtype=_NP[dt])
+    buf = (_CT[dt] * n).from_address(a)
+    return np.frombuffer(buf, dtype=_NP[dt], count=n)
+
+
+def view_bytes(p, nbytes):
+    return np.frombuffer((ctypes.c_uint8 * nbytes).from_address(_addr(p)), dtype=np.uint8, count=nbytes)
+
+
+_UN = {48: np.negative, 49: np.abs, 50: np.floor, 52: np.trunc, 64: np.sqrt, 65: np.exp, 66: np.log, 67: np.sin,
+       68: np.cos, 69: np.tan, 70: np.tanh, 71: np.ceil, 72: np.sign, 75: np.log2, 76: np.log10, 77: np.sinh,
+       78: np.cosh, 79: np.arcsin, 80: np.arccos, 81: np.arctan, 82: np.expm1, 83: np.log1p, 84: np.square}
+_RED = {0: np.add, 1: np.multiply, 2: np.maximum, 3: np.minimum}
+
+
+def _b2i(x):
+    """the kernels treat bool arithmetic as int64 (kgb_expr.cpp promote rules)"""
+    if isinstance(x, np.ndarray) and x.dtype == np.bool_:
+        return x.astype(np.int64)
+    if isinstance(x, (bool, np.bool_)):
+        return int(x)
+    return x
+
+
+def run_program(code, args, scanval=None):
+    st = []
+    pc = 0
+    with np.errstate(all="ignore"):
+        while pc < len(code):
+            op = code[pc]
+            if op == 1:
+                st.append(args[code[pc + 1]])
+                pc += 2
+                continue
+            if op in (2, 3):
+                raw = (code[pc + 1] & 0xFFFFFFFF) | ((code[pc + 2] & 0xFFFFFFFF) << 32)
+                if op == 2:
+                    st.append(int(np.array(raw, dtype=np.uint64).astype(np.int64)))
+                else:
+                    st.append(float(np.array(raw, dtype=np.uint64).view(np.float64)))
+                pc += 3
+                continue
+            if op == 4:
+                st.append(scanval)
+                pc += 1
+                continue
+            pc += 1
+            if 16 <= op <= 33:
+                b = st.pop()
+                a = st.pop()
+                if op in (16, 17, 18, 19, 20, 26):
+                    a, b = _b2i(a), _b2i(b)
+                if op == 16:
+                    r = a + b
+                elif op == 17:
+                    r = a - b
+                elif op == 18:
+                    r = a * b
+                elif op == 19:
+                    r = np.divide(a, b)
+                elif op == 20:
+                    r = np.power(a, b)
+                elif op == 21:
+                    r = np.equal(a, b) * 1
+                elif op == 22:
+                    r = np.greater(a, b) * 1
+                elif op == 23:
+                    r = np.less(a, b) * 1
+                elif op == 24:
+                    r = np.maximum(a, b)
+                elif op == 25:
+                    r = np.minimum(a, b)
+                elif op == 26:
+                    r = np.fmod(a, b)
+                elif op == 27:
+                    r = np.equal(a, b)
+                elif op == 28:
+                    r = np.greater(a, b)
+                elif op == 29:
+                    r = np.less(a, b)
+                elif op == 30:
+                    r = np.not_equal(a, b)
+                elif op == 31:
+                    r = np.greater_equal(a, b)
+                elif op == 32:
+                    r = np.less_equal(a, b)
+                else:
+                    r = np.isclose(a, b)
+                st.append(r)
+            elif op == 96:
+                b = st.pop()
+                a = st.pop()
+                c = st.pop()
+                st.append(np.where(np.asarray(c) != 0, a, b))
+            else:
+                a = st.pop()
+                if op in _UN:
+                    if op >= 64 and op != 84 and op != 71 and op != 72:
+                        a = np.asarray(a)
+                        if a.dtype.kind != "f":
+                            a = a.astype(np.float64)
+                    r = _UN[op](_b2i(a) if op in (48, 84, 72) else a)
+                elif op == 51:
+                    r = np.floor(np.asarray(a, dtype=float)).astype(np.int64)
+                elif op == 53:
+                    r = np.reciprocal(np.asarray(a, dtype=float))
+                elif op == 54:
+                    r = np.logical_not(a)
+                elif op == 73:
+                    r = np.isnan(np.asarray(a, dtype=float)) if np.asarray(a).dtype.kind == "f" else np.zeros(np.shape(a), bool)
+                elif op == 74:
+                    r = np.isinf(np.asarray(a, dtype=float)) if np.asarray(a).dtype.kind == "f" else np.zeros(np.shape(a), bool)
+                elif op == 55:
+                    r = np.asarray(a).astype(np.float64)
+                elif op == 56:
+                    r = np.asarray(a).astype(np.int64)
+                elif op == 57:
+                    r = np.asarray(a).astype(np.float32)
+                elif op == 58:
+                    r = np.asarray(a) != 0
+                elif op == 59:
+                    r = np.asarray(a).astype(np.int32)
+                else:
+                    raise ValueError(f"fake_lib: unknown opcode {op}")
+                st.append(r)
+    assert len(st) == 1
+    return st[0]
+
+
+def _fold_dtype(dt, red):
+    if red in (0, 1) and dt in (np.dtype(np.bool_), np.dtype(np.int32)):
+        return np.dtype(np.int64)
+    return dt
+
+
+class _Expr:
+    def __init__(self, code, code2, kinds, dtypes, mode, red, red2):
+        self.code, self.code2, self.kinds, self.dtypes = code, code2, kinds, dtypes
+        self.mode, self.red, self.red2 = mode, red, red2
+        # infer the result dtype on 1-element dummies with numpy's own promotion rules
+        dummy = []
+        for k, d in zip(kinds, dtypes):
+            if k == 1:
+                dummy.append(1 if d == I64 else 1.5)
+            elif k == 2:
+                dummy.append(np.ones((), dtype=_NP[d]))
+            else:
+                dummy.append(np.ones(1, dtype=_NP[d]))
+        r = np.asarray(run_program(code, dummy))
+        dt = r.dtype
+        if mode != 0:
+            dt = _fold_dtype(dt, red)
+        self.acc = dt
+        if mode == 3:
+            r2 = np.asarray(run_program(code2, dummy, scanval=np.ones(1, dtype=dt)))
+            dt = _fold_dtype(r2.dtype, red2)
+        if dt not in _CODE:
+            dt = np.dtype(np.int64) if dt.kind in "iu" else np.dtype(np.float64)
+        self.out = dt
+
+
+class FakeLib:
+    def __init__(self):
+        self.exprs = []
+        self.err = b""
+
+    # -- library
+    def kgb_last_error(self):
+        return self.err
+
+    def kgb_abi_version(self):
+        return 1
+
+    def kgb_init(self, d):
+        return 0
+
+    # -- expressions
+    def kgb_expr_compile(self, code, n_code, code2, n_code2, kinds, dtypes, n_args, mode, red, red2, h, od):
+        try:
+            e = _Expr(list(code[:n_code]), list(code2[:n_code2]) if code2 is not None else None, list(kinds[:n_args]),
+                      list(dtypes[:n_args]), mode, red, red2)
+        except Exception as ex:  # noqa: BLE001
+            self.err = f"fake compile: {ex}".encode()
+            return -1
+        self.exprs.append(e)
+        h._obj.value = len(self.exprs)
+        od._obj.value = _CODE[e.out]
+        return 0
+
+    def kgb_expr_workspace_bytes(self, h, n, out):
+        out._obj.value = 64
+        return 0
+
+    def kgb_expr_launch(self, h, argv, n, out, ws, wsb, stream):
+        e = self.exprs[_addr(h) - 1]
+        args = []
+        for i, (k, d) in enumerate(zip(e.kinds, e.dtypes)):
+            p = argv[i]
+            if k == 0:
+                args.append(view(p, n, d))
+            elif k == 2:
+                args.append(view(p, 1, d)[0])
+            else:
+                args.append(int(view(p, 1, I64)[0]) if d == I64 else float(view(p, 1, F64)[0]))
+        try:
+            with np.errstate(all="ignore"):
+                v = run_program(e.code, args)
+                if e.mode == 0:
+                    res = np.broadcast_to(np.asarray(v), (n,))
+                    view(out, n, _CODE[e.out])[:] = res.astype(e.out)
+                    return 0
+                v = np.broadcast_to(np.asarray(v), (n,)).astype(e.acc)
+                if e.mode == 1:
+                    view(out, 1, _CODE[e.out])[0] = _RED[e.red].reduce(v)
+                elif e.mode == 2:
+                    view(out, n, _CODE[e.out])[:] = _RED[e.red].accumulate(v)
+                else:
+                    sv = _RED[e.red].accumulate(v)
+                    v2 = np.broadcast_to(np.asarray(run_program(e.code2, args, scanval=sv)), (n,)).astype(e.out)
+                    view(out, 1, _CODE[e.out])[0] = _RED[e.red2].reduce(v2)
+        except Exception as ex:  # noqa: BLE001
+            self.err = f"fake launch: {type(ex).__name__}: {ex}".encode()
+            return -1
+        return 0
+
+    # -- sort / group / select
+    def kgb_argsort_workspace_bytes(self, dt, n, out):
+        out._obj.value = 64
+        return 0
+
+    kgb_group_workspace_bytes = kgb_argsort_workspace_bytes
+    kgb_unique_first_workspace_bytes = kgb_argsort_workspace_bytes
+
+    def kgb_select_workspace_bytes(self, n, out):
+        out._obj.value = 64
+        return 0
+
+    def kgb_groupagg_workspace_bytes(self, n, g, out):
+        out._obj.value = 64
+        return 0
+
+    def kgb_argsort(self, keys, dt, n, desc, idx_out, ks_out, ws, wsb, stream):
+        k = view(keys, n, dt)
+        o = O.grade_down(k) if desc else O.grade_up(k)
+        view(idx_out, n, I64)[:] = o
+        if _addr(ks_out):
+            view(ks_out, n, dt)[:] = k[o]
+        return 0
+
+    def kgb_group(self, keys, dt, n, order_out, starts_out, ng_out, ws, wsb, stream):
+        k = view(keys, n, dt)
+        order, starts = O.group_csr(k)
+        view(order_out, n, I64)[:] = order
+        view(starts_out, len(starts), I64)[:] = starts
+        view(ng_out, 1, I64)[0] = len(starts) - 1
+        return 0
+
+    def kgb_find_equal(self, a, dt, n, needle, pos_out, cnt_out, ws, wsb, stream):
+        nd = view(needle, 1, dt)[0]
+        r = O.find(view(a, n, dt), nd)
+        view(pos_out, len(r), I64)[:] = r
+        view(cnt_out, 1, I64)[0] = len(r)
+        return 0
+
+    def kgb_nonzero(self, a, dt, n, pos_out, cnt_out, ws, wsb, stream):
+        r = np.flatnonzero(view(a, n, dt))
+        view(pos_out, len(r), I64)[:] = r
+        view(cnt_out, 1, I64)[0] = len(r)
+        return 0
+
+    def kgb_unique_first(self, a, dt, n, out, first_out, cnt_out, ws, wsb, stream):
+        arr = view(a, n, dt)
+        _, idx = np.unique(arr, return_index=True)
+        idx = np.sort(idx)
+        view(out, len(idx), dt)[:] = arr[idx]
+        view(first_out, len(idx), I64)[:] = idx
+        view(cnt_out, 1, I64)[0] = len(idx)
+        return 0
+
+    # -- support verbs
+    def kgb_iota_i64(self, out, n, start, step, stream):
+        view(out, n, I64)[:] = start + step * np.arange(n)
+        return 0
+
+    def kgb_gather(self, a, eb, n_a, idx, n_idx, out, err, stream):
+        src = view_bytes(a, eb * n_a).reshape(n_a, eb)
+        ix = view(idx, n_idx, I64).copy()
+        ix[ix < 0] += n_a
+        bad = (ix < 0) | (ix >= n_a)
+        dst = view_bytes(out, eb * n_idx).reshape(n_idx, eb)
+        if bad.any():
+            view(err, 1, I32)[0] = 1
+            ix[bad] = 0
+        dst[:] = src[ix]
+        return 0
+
+    def kgb_expand(self, counts, incl, n, total, out, stream):
+        view(out, total, I64)[:] = np.repeat(np.arange(n), view(counts, n, I64))
+        return 0
+
+    def kgb_reverse(self, a, eb, n, out, stream):
+        view_bytes(out, eb * n).reshape(n, eb)[:] = view_bytes(a, eb * n).reshape(n, eb)[::-1]
+        return 0
+
+    def kgb_array_equal(self, a, b, dt, n, flag, stream):
+        view(flag, 1, I32)[0] = int(np.array_equal(view(a, n, dt), view(b, n, dt)))
+        return 0
+
+    def kgb_groupagg_f64(self, keys, vals, n, G, mn, mx, sm, ct, acc, ws, wsb, stream):
+        r = O.grouped_stats(view(keys, n, I64), view(vals, n, F64), G)
+        outs = (view(mn, G, F64), view(mx, G, F64), view(sm, G, F64), view(ct, G, I64))
+        if acc:
+            outs[0][:] = np.minimum(outs[0], r[0])
+            outs[1][:] = np.maximum(outs[1], r[1])
+            outs[2][:] += r[2]
+            outs[3][:] += r[3]
+        else:
+            for o, v in zip(outs, r):
+                o[:] = v
+        return 0
+
+    def kgb_groupagg_merge(self, mn, mx, sm, ct, mn2, mx2, sm2, ct2, G, stream):
+        a = (view(mn, G, F64), view(mx, G, F64), view(sm, G, F64), view(ct, G, I64))
+        b = (view(mn2, G, F64), view(mx2, G, F64), view(sm2, G, F64), view(ct2, G, I64))
+        a[0][:] = np.minimum(a[0], b[0])
+        a[1][:] = np.maximum(a[1], b[1])
+        a[2][:] += b[2]
+        a[3][:] += b[3]
+        return 0
+
+
+def install():
+    """Register the double and return a CPU device string for the provider."""
+    from klongpy_b200 import _lib
+    if not isinstance(_lib._host_double, FakeLib):
+        _lib._host_double = FakeLib()
+    return "cpu"
