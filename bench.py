@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py — the headline measurement (BASELINE.json config 2) plus a per-primitive table.
+
+    python bench.py --gpus N --steps K --warmup W            # this framework (one rank per GPU under torchrun)
+    python bench.py --impl reference --gpus N ...            # the reference's CPU path (NumPy oracle port), rank 0 only
+
+A *step* is one pass of the hot path over one resident batch: the fused reduce `{+/((x*2)+1)^2}` followed by the
+running sum `+\\x` over a float64 vector of --n elements per GPU (default 1e9 = 8 GB, so every pass streams from
+HBM: inputs are 60x larger than L2).  value = elements processed per second = 2*n*N / step time (each primitive
+sweeps the n-element shard once; weak scaling: per-GPU work is fixed, the global vector is N*n).  Timed with
+CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.
+
+Extra keys: `roofline` (dominant kernel = the scan, algorithmic 16 B/elem), `cpu_baseline` (oracle port timed on
+the host, bounded sample), `e2e` (same step with HOST buffers: pinned H2D of x and D2H of both results inside
+the timed region), `primitives` (grade / group / find / range / grouped aggregation / elementwise at their
+BASELINE sizes), `clocks`, `gpu_launches`.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "elements_per_sec"
+UNIT = "elements/s"
+WORKLOAD = "config2: fused reduce {+/((x*2)+1)^2} + running sum +\\x over float64"
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+            "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown," \
+            "clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for nm, v in zip(names, r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    """The reference's own CPU implementation of the path = its NumPy backend calls, restated in oracle/."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import kg_oracle as O
+    n = int(args.ref_n)
+    rng = np.random.default_rng(0)
+    x = rng.integers(0, 256, n) / 256.0
+    ir = ("reduce", "+", ("binop", "^", ("binop", "+", ("binop", "*", ("var", "_v0"), ("literal", 2)), ("literal", 1)), ("literal", 2)))
+    sc = ("scan", "+", ("var", "_v0"))
+
+    def step():
+        O.eval_ir(ir, {"_v0": x})
+        O.eval_ir(sc, {"_v0": x})
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    value = 2 * n / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "n_per_step": n, "note": "bounded sample of the 1e9-element workload; "
+                   "NumPy executes these primitives single-threaded"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": f"{n} float64 elements per step (oracle/kg_oracle.eval_ir = numpy_backend.py:116-178)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "host_cpus": os.cpu_count(),
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=float, default=1e9, help="float64 elements per GPU")
+    ap.add_argument("--ref-n", type=float, default=1e8, help="elements per step of the CPU reference arm")
+    ap.add_argument("--cpu-n", type=float, default=1e8, help="elements of the cpu_baseline sample")
+    ap.add_argument("--no-primitives", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as td
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        td.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import klongpy_b200
+    from klongpy_b200 import DeviceArray, _lib, dist, ops
+    be = klongpy_b200.B200BackendProvider(device=f"cuda:{local}")
+    dev = torch.device("cuda", local)
+    n = int(args.n)
+    peak, peak_src = measured_peak()
+
+    # synthetic shard: dyadic float64 (k/256) so the parity assertion below is bit-exact
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    ki = torch.randint(0, 256, (n,), dtype=torch.int64, device=dev, generator=g)
+    X = DeviceArray(ki) / 256
+    isum = int(ops.reduce("add", DeviceArray(ki)).item())
+    del ki
+    RED_CODE = [ops.OP_ARG, 0] + ops.lit(2) + [ops.OPC["mul"]] + ops.lit(1) + [ops.OPC["add"]] + ops.lit(2) + [ops.OPC["pow"]]
+    ID_CODE = [ops.OP_ARG, 0]
+
+    launches = {"n": 0}
+
+    def step():
+        r = dist.sharded_reduce(RED_CODE, [X], "+")
+        s = dist.sharded_scan(ID_CODE, [X], "+")
+        return r, s
+
+    per_step_launches = 2 if world == 1 else (2 + 1 + (2 if rank > 0 else 1) + 1)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            td.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        r, s = step()
+    sync_all()
+    # parity inside the bench: the carried scan offset and the fold are exact on dyadic data
+    tot = DeviceArray(s.tensor[-1]).item()
+    if world == 1:
+        assert tot == isum / 256.0, (tot, isum / 256.0)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    for _ in range(args.steps):
+        r, s = step()
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    del r, s
+
+    # dominant kernel (the scan) and the fused reduce timed alone, on the launching stream
+    def time_kernel(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    scan_ms = time_kernel(lambda: ops.run(ID_CODE, [X], mode=_lib.MODE_SCAN, red=_lib.RED_ADD), max(3, args.steps))
+    red_ms = time_kernel(lambda: ops.run(RED_CODE, [X], mode=_lib.MODE_REDUCE, red=_lib.RED_ADD), max(3, args.steps))
+
+    tms = torch.tensor([ms, scan_ms, red_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        td.all_reduce(tms, op=td.ReduceOp.MAX)
+    ms, scan_ms, red_ms = (float(v) for v in tms.tolist())
+    value = 2.0 * n * world / (ms * 1e-3)
+
+    # ---- e2e: host buffers, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        try:
+            hx = torch.empty(n, dtype=torch.float64).pin_memory()
+            hx.copy_(X.tensor)
+            hs = torch.empty(n, dtype=torch.float64).pin_memory()
+            hr = torch.empty(1, dtype=torch.float64).pin_memory()
+            tmp = X
+            del X
+            torch.cuda.empty_cache()
+
+            def e2e_step():
+                dx = ops.asarray(hx.to(dev, non_blocking=True))
+                rr = dist.sharded_reduce(RED_CODE, [dx], "+")
+                ss = dist.sharded_scan(ID_CODE, [dx], "+")
+                hs.copy_(ss.tensor, non_blocking=True)
+                hr.copy_(rr.tensor.reshape(1), non_blocking=True)
+
+            X = tmp
+            e2e_step()
+            sync_all()
+            k = max(1, min(3, args.steps))
+            e0.record()
+            for _ in range(k):
+                e2e_step()
+            e1.record()
+            sync_all()
+            e_ms = torch.tensor([e0.elapsed_time(e1) / k], dtype=torch.float64, device=dev)
+            if world > 1:
+                td.all_reduce(e_ms, op=td.ReduceOp.MAX)
+            e2e = {"value": 2.0 * n * world / (float(e_ms.item()) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * n,
+                   "d2h_bytes_per_step": 8 * n + 8, "ms_per_step": float(e_ms.item()), "steps": k,
+                   "path": "pinned host float64 -> B200BackendProvider device array -> fused kernels -> pinned host"}
+            del hx, hs, hr
+        except Exception as ex:  # noqa: BLE001
+            e2e = {"value": None, "unit": UNIT, "error": f"{type(ex).__name__}: {ex}"}
+
+    # ---- per-primitive table (N=1 sizes from BASELINE.json configs 1/3/4)
+    prims = {}
+    if not args.no_primitives:
+        prims["fused_reduce"] = prim_row(n, red_ms, 8, peak)
+        prims["running_sum"] = prim_row(n, scan_ms, 16, peak)
+        try:
+            prims.update(primitive_table(be, ops, dist, time_kernel, dev, peak, world, rank))
+        except Exception as ex:  # noqa: BLE001
+            prims["error"] = f"{type(ex).__name__}: {ex}"
+
+    # ---- CPU baseline (oracle port), rank 0, bounded sample
+    cpu = None
+    if rank == 0:
+        from oracle import kg_oracle as O
+        m = int(args.cpu_n)
+        hxs = np.random.default_rng(0).integers(0, 256, m) / 256.0
+        ir = ("reduce", "+", ("binop", "^", ("binop", "+", ("binop", "*", ("var", "_v0"), ("literal", 2)), ("literal", 1)), ("literal", 2)))
+        best = 1e30
+        for _ in range(3):
+            t0 = time.perf_counter()
+            O.eval_ir(ir, {"_v0": hxs})
+            O.eval_ir(("scan", "+", ("var", "_v0")), {"_v0": hxs})
+            best = min(best, time.perf_counter() - t0)
+        cpu = {"value": 2 * m / best, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"{m} float64 elements, best of 3 (NumPy runs these ops on one core; host has {os.cpu_count()} cpus)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "n_per_gpu": n, "global_n": n * world, "sharding": f"block x{world}",
+                       "l2": "inputs (8 GB/GPU) are larger than L2; no flush needed",
+                       "exchange": "none" if world == 1 else "all_gather of per-rank partials (reduce) and totals (scan carry)"},
+            "roofline": {"bound": "hbm", "achieved": 16.0 * n / (scan_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": 16.0 * n / (scan_ms * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "kgb_scan_* (running sum +\\x)",
+                         "algorithmic_bytes_per_launch": 16 * n, "ms_per_launch": scan_ms, "peak_source": peak_src},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": per_step_launches * args.steps, "clocks": clocks,
+            "primitives": prims,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        td.barrier()
+        td.destroy_process_group()
+
+
+def prim_row(n, ms, bytes_per_elem, peak, **extra):
+    gbs = bytes_per_elem * n / (ms * 1e-3) / 1e9
+    row = {"n": n, "ms": ms, "elements_per_sec": n / (ms * 1e-3), "algorithmic_bytes_per_elem": bytes_per_elem,
+           "achieved_gbs": gbs, "roofline_frac": gbs / peak}
+    row.update(extra)
+    return row
+
+
+def primitive_table(be, ops, dist, time_kernel, dev, peak, world, rank):
+    """Per-primitive elements/s and roofline fraction at the BASELINE.json sizes (1 GPU each rank)."""
+    import torch
+    from klongpy_b200 import DeviceArray
+    out = {}
+    g = torch.Generator(device=dev).manual_seed(99 + rank)
+    n = 100_000_000
+    a = DeviceArray(torch.rand(n, dtype=torch.float64, device=dev, generator=g))
+    b = DeviceArray(torch.rand(n, dtype=torch.float64, device=dev, generator=g))
+    out["a+b"] = prim_row(n, time_kernel(lambda: ops.binary("add", a, b), 5), 24, peak)
+    c = DeviceArray(torch.rand(n, dtype=torch.float64, device=dev, generator=g))
+    fn, _ = be.compile_expr_ir(("binop", "%", ("binop", "*", ("var", "_v0"), ("binop", "+", ("literal", 2), ("binop", "*", ("var", "_v1"), ("literal", 3)))),
+                                ("binop", "-", ("binop", "+", ("var", "_v0"), ("literal", 1)), ("binop", "*", ("var", "_v1"), ("var", "_v2")))), ["a", "b", "c"])
+    out["(a*2+b*3)%(a+1)-(b*c)"] = prim_row(n, time_kernel(lambda: fn(a, b, c), 5), 32, peak)
+    fn2, _ = be.compile_expr_ir(("reduce", "|", ("binop", "-", ("scan", "|", ("var", "_v0")), ("var", "_v0"))), ["a"])
+    out["|/(|\\ts)-ts"] = prim_row(n, time_kernel(lambda: fn2(a), 5), 8, peak)
+    del b, c
+    keys_perm = DeviceArray(torch.randperm(n, device=dev, generator=g))
+    out["grade_up_perm_1e8"] = prim_row(n, time_kernel(lambda: ops.argsort(keys_perm), 3), 16, peak,
+                                        model_bytes_per_elem=8 + 24 * 4 - 4 + 4, passes=4)
+    del keys_perm
+    keys_10k = DeviceArray(torch.randint(0, 10_000, (n,), dtype=torch.int64, device=dev, generator=g))
+    out["grade_up_10k_1e8"] = prim_row(n, time_kernel(lambda: ops.argsort(keys_10k), 3), 16, peak,
+                                       model_bytes_per_elem=8 + 24 * 2 - 4 + 4, passes=2)
+    out["group_10k_1e8"] = prim_row(n, time_kernel(lambda: ops.group(keys_10k), 3), 16, peak)
+    out["find_1e8"] = prim_row(n, time_kernel(lambda: ops.find_equal(keys_10k, 77), 3), 8, peak)
+    out["range_10k_1e8"] = prim_row(n, time_kernel(lambda: ops.unique_first(keys_10k), 3), 16, peak)
+    temp = DeviceArray(torch.randn(n, dtype=torch.float64, device=dev, generator=g))
+    out["grouped_min_mean_max_10k_1e8"] = prim_row(n, time_kernel(lambda: dist.sharded_groupagg(keys_10k, temp, 10_000), 3),
+                                                  16, peak, n_gpus=world)
+    del temp, a
+    keys_full = DeviceArray(torch.randint(-2**62, 2**62, (n,), dtype=torch.int64, device=dev, generator=g))
+    out["grade_up_full64_1e8"] = prim_row(n, time_kernel(lambda: ops.argsort(keys_full), 3), 16, peak,
+                                          model_bytes_per_elem=8 + 24 * 8 - 4 + 4, passes=8)
+    return out
+
+
+if __name__ == "__main__":
+    main()

@@ -136,11 +136,18 @@ int kgb_device_sm_count(int device, int* out);
    single-pass kernel per IR tree instead of one NumPy call (and temporary) per node.  Also the engine
    behind every eager dyad/monad (one-node programs).
    code/n_code: postfix program.  For KGB_MODE_SCANRED, code2/n_code2 is the epilogue program evaluated
-   at each element with KGB_OP_SCANVAL available, folded with red_op2; otherwise pass NULL/0.
+   at each element with KGB_OP_SCANVAL available, folded with red_op2.  For KGB_MODE_SCAN an optional
+   code2 over scalar arguments only is the SEED folded in front of element 0 (the exclusive offset a shard
+   carries in a multi-GPU scan).  Otherwise pass NULL/0.
    out_dtype receives the result element type. */
 int kgb_expr_compile(const int32_t* code, int32_t n_code, const int32_t* code2, int32_t n_code2,
                      const int32_t* arg_kinds, const int32_t* arg_dtypes, int32_t n_args, int32_t mode,
                      int32_t red_op, int32_t red_op2, kgb_expr** out_handle, int32_t* out_dtype);
+/* Same code generation + NVRTC compile to an sm_100a cubin, but WITHOUT loading it: works on a box with
+   no GPU (build check, host-logic tests).  *source_out stays valid until the next call on the thread. */
+int kgb_expr_check(const int32_t* code, int32_t n_code, const int32_t* code2, int32_t n_code2,
+                   const int32_t* arg_kinds, const int32_t* arg_dtypes, int32_t n_args, int32_t mode,
+                   int32_t red_op, int32_t red_op2, int32_t* out_dtype, const char** source_out);
 /* bytes of zero-initialisable scratch a launch over n elements needs (0 for MAP) */
 int kgb_expr_workspace_bytes(const kgb_expr* h, int64_t n, size_t* out_bytes);
 /* args[i]: device pointer (ARRAY, DEVSCALAR) or host pointer to 8 bytes (SCALAR).  out: device.

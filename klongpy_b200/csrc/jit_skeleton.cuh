@@ -10,6 +10,7 @@
 //   KGB_EVAL(j)         the expression value for register slot j
 //   KGB_RED(a,b), KGB_RED_IDENT           fold operator + identity (modes 1,2,3)
 //   KGB_EVAL2(j,sv), KGB_RED2(a,b), KGB_RED2_IDENT, KGB_ACC2_T   (mode 3 epilogue)
+//   KGB_HAS_CARRY, KGB_CARRY   (mode 2, optional) scalar seed folded in front of element 0
 // and this file supplies the memory movement: 128-bit streaming loads/stores, grid-stride unrolling
 // for bytes-in-flight, warp-shuffle + block folds with a fixed-order last-block combine
 // (deterministic), and the single-pass decoupled-lookback scan.
@@ -432,6 +433,14 @@ template <int V> __device__ __forceinline__ void kgb_scan_body(const KgbParams& 
     KGB_ACC_T thread_excl = (lane == 0) ? wpre : KGB_RED(wpre, lane_excl);
 
     // ---- 3. publish aggregate, look back
+#ifdef KGB_HAS_CARRY
+    // seed of the whole scan (the exclusive offset of this shard in a multi-GPU scan)
+    const KGB_ACC_T carry = (KGB_ACC_T)(KGB_CARRY);
+    if (tile == 0) {
+        thread_excl = KGB_RED(carry, thread_excl);
+        tile_agg = KGB_RED(carry, tile_agg);
+    }
+#endif
     if (tid == 0) {
         if (tile == 0) {
             incls[0] = tile_agg;

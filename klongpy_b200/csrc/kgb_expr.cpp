@@ -524,6 +524,13 @@ static int build_source(kgb_expr* h, const int32_t* code, int n_code, const int3
     if (h->mode != KGB_MODE_MAP) {
         m << fold_macro("KGB_RED", h->red_op) << fold_ident("KGB_RED_IDENT", h->red_op, h->acc_dtype);
     }
+    if (h->mode == KGB_MODE_SCAN && code2 && n_code2 > 0) {
+        // optional seed program over scalar arguments only (multi-GPU scans pass the shard's exclusive offset)
+        Val vc;
+        if (!gen_expr(code2, n_code2, h->args, false, 0, &vc)) return KGB_EINVAL;
+        if (vc.s.find("[(j)]") != std::string::npos) return set_error("scan seed program must not read arrays"), KGB_EINVAL;
+        m << "#define KGB_HAS_CARRY 1\n#define KGB_CARRY (" << cast(vc, h->acc_dtype) << ")\n";
+    }
     if (h->mode == KGB_MODE_SCANRED) {
         m << "#define KGB_ACC2_T " << ctype(h->acc2_dtype) << "\n";
         m << "#define KGB_EVAL2(j, sv) (" << cast(v2, h->acc2_dtype) << ")\n";

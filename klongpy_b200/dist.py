@@ -1,0 +1,119 @@
+"""Multi-GPU sharding of the hot path: one process per GPU, `torch.distributed` (NCCL over NVLink/NVSwitch)
+for the plumbing.
+
+A long vector is block-sharded: rank r holds the contiguous slice [r*n_local, (r+1)*n_local).  Elementwise
+expressions need no exchange.  The primitives with a real exchange step:
+
+  * reduce  `+/ */ |/ &/` : per-rank fused fold -> all_gather of `world` scalars (8 B each) -> the SAME
+    fixed-order combine kernel on every rank (bit-identical results everywhere; all_reduce's association is
+    NCCL's choice, so it is not used for float sums).
+  * scan    `+\\ *\\ |\\ &\\` : per-rank fold -> all_gather of totals -> exclusive prefix over lower ranks = the
+    shard's carried offset -> ONE local decoupled-look-back scan seeded with that offset (24 B/elem/rank).
+  * grouped min/mean/max : per-rank partial G x 4 tables -> all_to_all of the per-owner table slices
+    (station block s // B owned by rank s // B) -> merge -> all_gather of the final slices.
+
+Messages are tiny (8 B .. 320 KB): they are latency-, not bandwidth-bound, so each primitive does exactly one
+or two collectives.
+"""
+import numpy as np
+import torch
+import torch.distributed as td
+
+from . import _lib, ops
+from .array import DeviceArray
+
+_IDENT = {_lib.RED_ADD: 0, _lib.RED_MUL: 1}
+
+
+def world():
+    return td.get_world_size() if td.is_available() and td.is_initialized() else 1
+
+
+def rank():
+    return td.get_rank() if td.is_available() and td.is_initialized() else 0
+
+
+def _gather_scalars(x):
+    """all_gather of one 0-d device value per rank -> 1-d DeviceArray of length world (same on every rank)."""
+    w = world()
+    t = x._t.reshape(1)
+    out = torch.empty(w, dtype=t.dtype, device=t.device)
+    td.all_gather_into_tensor(out, t.contiguous())
+    return DeviceArray(out)
+
+
+def sharded_reduce(code, args, red):
+    """Fold of an expression over a block-sharded vector.  Returns a 0-d DeviceArray replicated on all ranks."""
+    red = ops.RED[red] if not isinstance(red, int) else red
+    part = ops.run(code, args, mode=_lib.MODE_REDUCE, red=red)
+    if world() == 1:
+        return part
+    allp = _gather_scalars(part)
+    return ops.run([ops.OP_ARG, 0], [allp], mode=_lib.MODE_REDUCE, red=red)
+
+
+def shard_offset(code, args, red):
+    """Exclusive fold over all lower ranks of the per-rank totals: the offset this shard's scan carries.
+    Returns (offset 0-d DeviceArray or None on rank 0, totals)."""
+    red = ops.RED[red] if not isinstance(red, int) else red
+    total = ops.run(code, args, mode=_lib.MODE_REDUCE, red=red)
+    totals = _gather_scalars(total)
+    r = rank()
+    if r == 0:
+        return None, totals
+    return ops.run([ops.OP_ARG, 0], [DeviceArray(totals._t[:r])], mode=_lib.MODE_REDUCE, red=red), totals
+
+
+def sharded_scan(code, args, red):
+    """Inclusive scan of an expression over a block-sharded vector; returns this rank's slice of the result."""
+    red = ops.RED[red] if not isinstance(red, int) else red
+    if world() == 1:
+        return ops.run(code, args, mode=_lib.MODE_SCAN, red=red)
+    off, _ = shard_offset(code, args, red)
+    if off is None:
+        return ops.run(code, args, mode=_lib.MODE_SCAN, red=red)
+    seed = [ops.OP_ARG, len(args)]
+    return ops.run(code, list(args) + [off], mode=_lib.MODE_SCAN, red=red, code2=seed)
+
+
+def sharded_groupagg(keys, vals, n_groups):
+    """Grouped (min, max, sum, count) over block-sharded rows.  Every rank returns the full G-entry tables."""
+    w = world()
+    mn, mx, sm, ct = ops.groupagg(keys, vals, n_groups)
+    if w == 1:
+        return mn, mx, sm, ct
+    G = int(n_groups)
+    B = (G + w - 1) // w  # stations [r*B, (r+1)*B) are owned by rank r
+    dev = mn._t.device
+    lib, stream = ops._lib_for(dev)
+
+    def padded(t, fill):
+        p = torch.full((w * B,), fill, dtype=t.dtype, device=dev)
+        p[:G].copy_(t)
+        return p
+
+    send = [padded(mn._t, float("inf")), padded(mx._t, float("-inf")), padded(sm._t, 0.0), padded(ct._t, 0)]
+    recv = [torch.empty_like(s) for s in send]
+    for s, r in zip(send, recv):  # owner slices: rank r receives block r of every rank's partial table
+        td.all_to_all_single(r, s)
+    acc = [r[:B].clone() for r in recv]
+    for k in range(1, w):
+        sl = [r[k * B:(k + 1) * B] for r in recv]
+        _lib.check(lib.kgb_groupagg_merge(acc[0].data_ptr(), acc[1].data_ptr(), acc[2].data_ptr(), acc[3].data_ptr(),
+                                          sl[0].data_ptr(), sl[1].data_ptr(), sl[2].data_ptr(), sl[3].data_ptr(), B,
+                                          stream), "kgb_groupagg_merge")
+    outs = []
+    for a in acc:
+        full = torch.empty(w * B, dtype=a.dtype, device=dev)
+        td.all_gather_into_tensor(full, a.contiguous())
+        outs.append(DeviceArray(full[:G]))
+    return tuple(outs)
+
+
+def shard_bounds(n_global, r=None, w=None):
+    """Contiguous block partition of a global index range."""
+    r = rank() if r is None else r
+    w = world() if w is None else w
+    per = (n_global + w - 1) // w
+    lo = min(r * per, n_global)
+    return lo, min(lo + per, n_global)

@@ -249,6 +249,9 @@ class FakeLib:
                 if e.mode == 1:
                     view(out, 1, _CODE[e.out])[0] = _RED[e.red].reduce(v)
                 elif e.mode == 2:
+                    if e.code2:
+                        v = v.copy()
+                        v[0] = _RED[e.red](np.asarray(run_program(e.code2, args)).astype(e.acc), v[0])
                     view(out, n, _CODE[e.out])[:] = _RED[e.red].accumulate(v)
                 else:
                     sv = _RED[e.red].accumulate(v)
@@ -306,7 +309,12 @@ class FakeLib:
 
     def kgb_unique_first(self, a, dt, n, out, first_out, cnt_out, ws, wsb, stream):
         arr = view(a, n, dt)
-        _, idx = np.unique(arr, return_index=True)
+        keys = arr
+        if arr.dtype.kind == "f":  # -0.0 and 0.0 are distinct for `?a`, NaNs collapse (oracle.range_unique)
+            b = arr.astype(np.float64, copy=True)
+            b[np.isnan(b)] = np.nan
+            keys = b.view(np.int64)
+        _, idx = np.unique(keys, return_index=True)
         idx = np.sort(idx)
         view(out, len(idx), dt)[:] = arr[idx]
         view(first_out, len(idx), I64)[:] = idx

@@ -1,0 +1,88 @@
+"""Multi-process path on CPU: world_size 2 over gloo, device library replaced by the NumPy test double.
+Checks the exchange logic of klongpy_b200/dist.py (all_gather of partials, carried scan offset, all_to_all of
+per-owner table slices)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    try:
+        sys.path.insert(0, ROOT)
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        import torch.distributed as td
+        td.init_process_group("gloo", rank=rank, world_size=world)
+        import fake_lib
+        dev = fake_lib.install()
+        from klongpy_b200 import B200BackendProvider, dist, ops
+        be = B200BackendProvider(device=dev)
+        rng = np.random.default_rng(123)
+        n = 20_001
+        x = rng.integers(0, 256, n) / 256.0
+        i = rng.integers(-100, 100, n)
+        lo, hi = dist.shard_bounds(n)
+        X, I = be.kg_asarray(x[lo:hi]), be.kg_asarray(i[lo:hi])
+        code = [ops.OP_ARG, 0] + ops.lit(2) + [ops.OPC["mul"]] + ops.lit(1) + [ops.OPC["add"]] + ops.lit(2) + [ops.OPC["pow"]]
+        r = dist.sharded_reduce(code, [X], "+").item()
+        assert r == np.add.reduce(((x * 2) + 1) ** 2), (r, rank)
+        assert dist.sharded_reduce([ops.OP_ARG, 0], [I], "|").item() == i.max()
+        s = dist.sharded_scan([ops.OP_ARG, 0], [X], "+").to_numpy()
+        assert np.array_equal(s, np.cumsum(x)[lo:hi]), rank
+        s = dist.sharded_scan([ops.OP_ARG, 0], [I], "|").to_numpy()
+        assert np.array_equal(s, np.maximum.accumulate(i)[lo:hi]), rank
+        s = dist.sharded_scan([ops.OP_ARG, 0], [I], "+").to_numpy()
+        assert np.array_equal(s, np.cumsum(i)[lo:hi]), rank
+        G = 37
+        k = rng.integers(0, G, n)
+        v = np.round(rng.normal(10, 15, n), 1)
+        mn, mx, sm, ct = (t.to_numpy() for t in dist.sharded_groupagg(be.kg_asarray(k[lo:hi]), be.kg_asarray(v[lo:hi]), G))
+        from oracle import kg_oracle as O
+        rmn, rmx, rsm, rct = O.grouped_stats(k, v, G)
+        assert np.array_equal(mn, rmn) and np.array_equal(mx, rmx) and np.array_equal(ct, rct)
+        assert np.allclose(sm, rsm, rtol=1e-12, atol=1e-9)
+        td.barrier()
+        td.destroy_process_group()
+        q.put((rank, "ok"))
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        q.put((rank, "FAIL " + traceback.format_exc()))
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_primitives_gloo(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for r, status in res:
+        assert status == "ok", f"rank {r}: {status}"
+
+
+def test_shard_bounds_cover_range():
+    from klongpy_b200 import dist
+    for n in (0, 1, 7, 1000, 10**9):
+        for w in (1, 2, 3, 8):
+            spans = [dist.shard_bounds(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for a, b in zip(spans, spans[1:]):
+                assert a[1] == b[0]

@@ -1,0 +1,174 @@
+"""Host-side logic through the REAL KlongPy interpreter (CPU container only: needs /root/reference).
+
+The provider, np-shim, IR lowering and verb overrides run unchanged; only the device library is replaced by
+the NumPy test double (tests/fake_lib.py).  Results must equal the reference NumPy backend's.  The GPU box has
+no klongpy, so these tests skip there; the kernels themselves are covered by tests/test_gpu_parity.py.
+"""
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import REFERENCE, have_reference
+
+pytestmark = pytest.mark.skipif(not have_reference(), reason="reference klongpy not available on this box")
+
+
+@pytest.fixture(scope="module")
+def interp():
+    sys.path.insert(0, REFERENCE)
+    sys.dont_write_bytecode = True
+    import fake_lib
+    dev = fake_lib.install()
+    import klongpy_b200
+    from klongpy import KlongInterpreter
+    return klongpy_b200.interpreter(device=dev), KlongInterpreter(backend="numpy"), klongpy_b200
+
+
+def norm(x, mod):
+    if isinstance(x, mod.DeviceArray):
+        return x.to_numpy()
+    if isinstance(x, np.ndarray) and x.dtype == object:
+        out = np.empty(len(x), dtype=object)
+        for i, y in enumerate(x):
+            out[i] = norm(y, mod)
+        return out
+    return x
+
+
+PROGRAMS = [
+    "1+2", "[1 2 3]+1", "a::[1.0 2.0 3.0];{+/((x*2)+1)^2}(a)", "+\\[1 2 3 4]", "<[3 1 2 1]", ">[3 1 2 1]",
+    "=[1 2 1 3 2]", "?[1 1 2 3 3]", "[1 2 3 1]?1", "!5", "&[0 1 0 1]", "[1 2 3]@[0 2]", "|[1 2 3]",
+    "[1 2 3],[4 5]", "[1 2 3],4", "2^[1 2 3]", "[1 2 3]^2", "[1.5 2.5]^2", "-[1 2 3]", "_[1.5 2.5]", "%[1 2 4]",
+    "#[1 2 3]", "[1 2 3]%2", "[1 2 3]:%2", "[5 6 7]!3", "|/[1 5 2]", "&/[4 2 8]", "|\\[1 5 2 7]",
+    "a::!10;+/a*a", "3#[1 2 3 4 5]", "7#[1 2 3]", "2_[1 2 3 4]", "1:+[1 2 3 4]", "[1 2 3]=[1 5 3]",
+    "[1 2 3]<[2 2 2]", "[1 2 3]~[1 2 3]", "*[4 5 6]", "^[1 2 3]", "[[1 2] [3 4]]+1", "+[[1 2] [3 4]]",
+    "+/[[1 2] [3 4]]", "a::[1 2 3];b::[4 5 6];(a*2)+b", "ts::[3.0 1.0 4.0 1.0 5.0];|/(|\\ts)-ts",
+    "{x*2}'[1 2 3]", "10{x+1}:*0", "[1 2 3]|2", "[1 2 3]&2", "+/[]", "#[]", '"abc","def"', "=[1 1 2 2]",
+    "[1 [2 3] 4]+1", "(+/[1.0 2.0 3.0])%#[1 2 3]", "p::[1.0 2.0 3.0];s::[4 5 6];(+/p*s)%+/s",
+    "a::[1.0 2.0 3.0];a-(+/a)%#a", "-\\[10 1 2 3]", "-/[10 1 2 3]", "*/[1 2 3 4]", "%/[8.0 2.0 2.0]",
+    "a::[3 1 2];a@<a", "a::[3 1 2];a@>a", "&5", "&0", "[1 2 3]?4", "(-2)#[1 2 3 4]", "(-1)_[1 2 3 4]",
+    "[1.0 2.0]=[1.0 3.0]", "~[1 0 2]", "a::[1 2 3];+/a>1", "x::[0.5 0.25 0.125];+\\(x*2)+1",
+]
+
+
+@pytest.mark.parametrize("src", PROGRAMS)
+def test_program_matches_numpy_backend(interp, src):
+    kb, kn, mod = interp
+    got = norm(kb(src), mod)
+    ref = kn(src)
+    assert kn._backend.kg_equal(got, ref), (src, got, ref)
+    if isinstance(ref, np.ndarray) and ref.dtype != object and isinstance(got, np.ndarray):
+        assert got.dtype == ref.dtype, (src, got.dtype, ref.dtype)
+
+
+def test_arrays_stay_on_the_backend(interp):
+    """tests/test_backend_abstraction.py:12-31 pattern: literals and `+` results are backend arrays."""
+    kb, _, mod = interp
+    assert isinstance(kb("[1 2 3]"), mod.DeviceArray)
+    assert isinstance(kb("[1 2 3]+[4 5 6]"), mod.DeviceArray)
+    assert isinstance(kb("!4"), mod.DeviceArray)
+    assert isinstance(kb("<[3 1 2]"), mod.DeviceArray)
+
+
+def test_compiled_path_is_taken_and_fused(interp):
+    """`compile_expr` hands our provider the IR; the headline tree lowers to ONE reduce stage and
+    max-drawdown to ONE scan+reduce stage."""
+    kb, _, mod = interp
+    from klongpy.compiler import compile_expr
+    from klongpy_b200 import _lib
+    kb("a::[1.0 2.0 3.0 4.0]")
+    _, ast = kb.prog("+/((a*2)+1)^2")
+    fn, syms = compile_expr(ast[0], kb)
+    assert [s.mode for s in fn.plan.stages] == [_lib.MODE_REDUCE]
+    r = fn(kb["a"])
+    assert isinstance(r, mod.DeviceArray) and r.ndim == 0 and r.item() == 164.0
+    _, ast = kb.prog("|/(|\\a)-a")
+    fn, _ = compile_expr(ast[0], kb)
+    assert [s.mode for s in fn.plan.stages] == [_lib.MODE_SCANRED]
+    kb("p::[1.0 2.0];s::[3 4]")
+    _, ast = kb.prog("(+/p*s)%+/s")
+    fn, _ = compile_expr(ast[0], kb)
+    assert [s.mode for s in fn.plan.stages] == [_lib.MODE_REDUCE, _lib.MODE_REDUCE, _lib.MODE_MAP]
+
+
+def test_compiled_callable_raises_on_unsupported(interp):
+    """interpreter.py:697-701 falls back silently on any exception: host arrays / scalars-only must RAISE."""
+    kb, _, mod = interp
+    from klongpy_b200 import lowering
+    fn = lowering.make_callable(("binop", "+", ("var", "_v0"), ("literal", 1)))
+    with pytest.raises(Exception):
+        fn(np.arange(3))
+    with pytest.raises(Exception):
+        fn(3)
+    with pytest.raises(Exception):
+        fn(kb("[[1 2] [3 4]]"))
+
+
+def test_host_numpy_symbols_are_not_compiled(interp):
+    """tests/test_compiler.py:42-52: a host ndarray symbol makes compile_expr return None on a device backend."""
+    kb, _, _ = interp
+    from klongpy.compiler import compile_expr
+    kb["h"] = np.arange(4.0)
+    _, ast = kb.prog("h+1")
+    assert compile_expr(ast[0], kb) is None
+
+
+def test_golden_programs_through_interpreter(interp, golden):
+    kb, kn, mod = interp
+    arrays = golden["compiled_arrays"]
+    for name, v in arrays.items():
+        if name.startswith("in_"):
+            kb[name[3:]] = kb._backend.kg_asarray(v)
+    kb["k"] = 3
+    kb["f"] = 2.5
+    for case in golden["compiled"]:
+        if case["src"] in ("+/e", "*/e"):
+            continue  # empty folds: the eager interpreter returns [] (adverbs.py:225), compiled returns 0.0/1.0
+        got = norm(kb(case["src"]), mod)
+        ref = arrays[case["out"]]
+        got = np.asarray(got)
+        assert got.shape == ref.shape, case["src"]
+        assert got.dtype == ref.dtype, (case["src"], got.dtype, ref.dtype)
+        assert np.allclose(got, ref, rtol=1e-12, atol=0, equal_nan=True), case["src"]
+
+
+def test_golden_verbs_through_interpreter(interp, golden):
+    kb, kn, mod = interp
+    arrays = golden["verb_arrays"]
+    for name, v in arrays.items():
+        if name.startswith("in_"):
+            kb[name[3:]] = kb._backend.kg_asarray(v)
+    for case in golden["verbs"]:
+        got = norm(kb(case["src"]), mod)
+        key = case["out"]
+        if case["ragged"]:
+            flat = np.concatenate([np.asarray(x) for x in got])
+            starts = np.concatenate([[0], np.cumsum([len(x) for x in got])])
+            assert np.array_equal(flat, arrays[key + "_flat"]), case["src"]
+            assert np.array_equal(starts, arrays[key + "_starts"]), case["src"]
+            continue
+        ref = arrays[key]
+        got = np.asarray(got)
+        assert got.shape == ref.shape, (case["src"], got.shape, ref.shape)
+        if not case.get("object_scalars"):
+            assert got.dtype == ref.dtype, (case["src"], got.dtype, ref.dtype)
+        assert np.allclose(got, ref, rtol=1e-12, atol=0, equal_nan=True), case["src"]
+
+
+def test_bench_compiler_example_runs(interp):
+    """examples/bench_compiler.kg (config 1) expressions on device-resident inputs, vs the NumPy backend."""
+    kb, kn, mod = interp
+    rng = np.random.default_rng(0)
+    n = 1000
+    data = {"a": rng.random(n), "b": rng.random(n), "c": rng.random(n), "ts": 100 + rng.standard_normal(n) * 0.5,
+            "p": 50 + rng.standard_normal(n) * 10, "s": (np.floor(rng.random(n) * 9900) + 100).astype(np.int64)}
+    for k, v in data.items():
+        kb[k] = kb._backend.kg_asarray(v)
+        kn[k] = v
+    exprs = ["a+b", "a*2+b", "(a+b)*(a-b)", "(a*2+b)%(a+1)", "(a*2+b*3)%(a+1)-(b*c)", "{x+y}(a;b)",
+             "{(x+y)*(x-y)}(a;b)", "{+/x*y}(a;b)", "+/a", "+/a*b", "|/a-b", "+/a*b+c", "+\\ts", "|\\ts",
+             "(|\\ts)-ts", "|/(|\\ts)-ts", "(+/p*s)%+/s", "a-(+/a)%#a", "3{x;a+b;x+1}:*0"]
+    for e in exprs:
+        got, ref = np.asarray(norm(kb(e), mod)), np.asarray(kn(e))
+        assert got.shape == ref.shape and np.allclose(got, ref, rtol=1e-12, atol=0), e
