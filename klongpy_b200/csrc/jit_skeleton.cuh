@@ -309,47 +309,77 @@ extern "C" __global__ void __launch_bounds__(KGB_BLOCK) KGB_KERNEL_NAME_S(const 
 // =====================================================================================================
 #if KGB_MODE == 2 || KGB_MODE == 3
 // ------------------------------------------------------------------ SCAN: out[i] = fold_{j<=i} f(args[j])
-// Single-pass chained scan with decoupled look-back.  One tile = 256 threads x ITEMS (128 B) elements.
+// Single-pass chained scan with decoupled look-back.  One tile = KGB_SBLOCK threads x KGB_ITEMS elements
+// (KGB_SBLOCK / KGB_ITEMS are chosen by the host per accumulator width; DESIGN.md "scan").
 //   1. coalesced 128-bit striped loads, expression evaluated, values parked in padded smem
-//   2. each thread re-reads its 128 B chunk (bank-conflict-free thanks to the 16 B pad per chunk),
+//   2. each thread re-reads its contiguous chunk (bank-conflict-free thanks to the 16 B pad per chunk),
 //      scans it in registers; warp-shuffle + cross-warp scan of thread totals
-//   3. tile aggregate published; warp 0 looks back over predecessor tiles (32 at a time)
+//   3. tile aggregate published; warp 0 looks back over predecessor tiles (32 per round)
 //   4. results go back through smem and leave as coalesced 128-bit streaming stores
 // Tiles take their index from an atomic ticket so a tile's predecessors are always already running.
-// ws layout: [0,4) ticket, [4,8) done-count (mode 3), [64,...) flags u32[T], then agg ACC[T], incl ACC[T]
-// (mode 3: then partial ACC2[T]).  The host wrapper zeroes ticket+flags before each launch.
+//
+// Tile state = ONE 16-byte record {w0, w1} read and written with a single 128-bit access and no fence: each
+// 64-bit half carries the status in its upper 32 bits and half of the value's bit pattern in its lower 32, so a
+// reader accepts a record only when both halves show the same status — correct with nothing more than
+// 64-bit single-copy atomicity.  The look-back throughput of the whole scan is (window / round-trip) tiles per
+// unit time, which is why the value travels inside the polled word instead of behind a second
+// dependent load + __threadfence.
+// ws layout: [0,4) ticket, [4,8) done-count (mode 3), [64,...) state uint4[T] (mode 3: then partial ACC2[T]).
+// The host wrapper zeroes ticket + states before each launch.
+#ifndef KGB_SBLOCK
+#define KGB_SBLOCK 256
+#endif
+#ifndef KGB_ITEMS
 #define KGB_ITEMS (128 / (int)sizeof(KGB_ACC_T))
+#endif
 #define KGB_PADE (16 / (int)sizeof(KGB_ACC_T))
-#define KGB_TILE (KGB_BLOCK * KGB_ITEMS)
-#define KGB_SMEM_ELEMS (KGB_BLOCK * (KGB_ITEMS + KGB_PADE))
-#define KGB_FLAG_EMPTY 0u
-#define KGB_FLAG_AGG 1u
-#define KGB_FLAG_PREFIX 2u
+#define KGB_TILE (KGB_SBLOCK * KGB_ITEMS)
+#define KGB_SMEM_ELEMS (KGB_SBLOCK * (KGB_ITEMS + KGB_PADE))
+#define KGB_ST_EMPTY 0u
+#define KGB_ST_AGG 1u
+#define KGB_ST_PREFIX 2u
 
 __device__ __forceinline__ int kgb_pad(int e) { return e + (e / KGB_ITEMS) * KGB_PADE; }
 
-__device__ __forceinline__ u32 kgb_ld_acquire(const u32* p) {
-    u32 v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
+template <typename T, int BYTES = sizeof(T)> struct kgb_bits;
+template <typename T> struct kgb_bits<T, 8> {
+    static __device__ __forceinline__ u64 to(T v) { return *reinterpret_cast<u64*>(&v); }
+    static __device__ __forceinline__ T from(u64 b) { return *reinterpret_cast<T*>(&b); }
+};
+template <typename T> struct kgb_bits<T, 4> {
+    static __device__ __forceinline__ u64 to(T v) { return (u64)(*reinterpret_cast<u32*>(&v)); }
+    static __device__ __forceinline__ T from(u64 b) { u32 x = (u32)b; return *reinterpret_cast<T*>(&x); }
+};
+template <typename T> struct kgb_bits<T, 1> {
+    static __device__ __forceinline__ u64 to(T v) { return (u64)v; }
+    static __device__ __forceinline__ T from(u64 b) { return (T)b; }
+};
+
+__device__ __forceinline__ void kgb_state_store(uint4* p, u32 status, KGB_ACC_T v) {
+    const u64 b = kgb_bits<KGB_ACC_T>::to(v);
+    const u64 w0 = ((u64)status << 32) | (b >> 32), w1 = ((u64)status << 32) | (b & 0xffffffffull);
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(w0), "l"(w1) : "memory");
 }
-__device__ __forceinline__ void kgb_st_release(u32* p, u32 v) {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+// returns the status (EMPTY when the two halves disagree, i.e. a write is still landing)
+__device__ __forceinline__ u32 kgb_state_load(const uint4* p, KGB_ACC_T& v) {
+    u64 w0, w1;
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(p) : "memory");
+    const u32 s0 = (u32)(w0 >> 32), s1 = (u32)(w1 >> 32);
+    v = kgb_bits<KGB_ACC_T>::from((w0 << 32) | (w1 & 0xffffffffull));
+    return (s0 == s1) ? s0 : KGB_ST_EMPTY;
 }
 
 template <int V> __device__ __forceinline__ void kgb_scan_body(const KgbParams& p) {
     KGB_SCALARS
-    __shared__ __align__(16) KGB_ACC_T sbuf[KGB_SMEM_ELEMS];
-    __shared__ KGB_ACC_T swarp[KGB_BLOCK / 32];
+    extern __shared__ __align__(16) unsigned char kgb_dyn_smem[];
+    KGB_ACC_T* sbuf = reinterpret_cast<KGB_ACC_T*>(kgb_dyn_smem);  // KGB_SMEM_ELEMS accumulators
+    __shared__ KGB_ACC_T swarp[KGB_SBLOCK / 32];
     __shared__ KGB_ACC_T s_excl;
     __shared__ u32 s_tile;
     const i64 n = p.n;
     const u32 ntiles = (u32)((n + KGB_TILE - 1) / KGB_TILE);
     u32* ticket = (u32*)p.ws;
-    u32* flags = (u32*)((char*)p.ws + 64);
-    const size_t flags_bytes = (((size_t)ntiles * 4 + 63) / 64) * 64;
-    KGB_ACC_T* aggs = (KGB_ACC_T*)((char*)p.ws + 64 + flags_bytes);
-    KGB_ACC_T* incls = aggs + ntiles;
+    uint4* states = (uint4*)((char*)p.ws + 64);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     if (tid == 0) s_tile = atomicAdd(ticket, 1u);
@@ -365,12 +395,12 @@ template <int V> __device__ __forceinline__ void kgb_scan_body(const KgbParams& 
             KGB_DECL_REGS(V * KGB_UNROLL)
 #pragma unroll
             for (int u = 0; u < KGB_UNROLL; u++) {
-                const int e = ((h + u) * KGB_BLOCK + tid) * V;
+                const int e = ((h + u) * KGB_SBLOCK + tid) * V;
                 KGB_LOAD_VEC(V, u * V, base + e)
             }
 #pragma unroll
             for (int u = 0; u < KGB_UNROLL; u++) {
-                const int e = ((h + u) * KGB_BLOCK + tid) * V;
+                const int e = ((h + u) * KGB_SBLOCK + tid) * V;
                 KGB_ACC_T o[V];
 #pragma unroll
                 for (int j = 0; j < V; j++) o[j] = (KGB_ACC_T)(KGB_EVAL(u * V + j));
@@ -384,7 +414,7 @@ template <int V> __device__ __forceinline__ void kgb_scan_body(const KgbParams& 
         }
     } else {
         for (int k = 0; k < KGB_ITEMS; k++) {
-            const int e = k * KGB_BLOCK + tid;
+            const int e = k * KGB_SBLOCK + tid;
             KGB_ACC_T o = (KGB_ACC_T)(KGB_RED_IDENT);
             if (base + e < n) {
                 KGB_DECL_REGS(1)
@@ -423,7 +453,7 @@ template <int V> __device__ __forceinline__ void kgb_scan_body(const KgbParams& 
     KGB_ACC_T wpre = (KGB_ACC_T)(KGB_RED_IDENT);
     KGB_ACC_T tile_agg = (KGB_ACC_T)(KGB_RED_IDENT);
 #pragma unroll
-    for (int w = 0; w < KGB_BLOCK / 32; w++) {
+    for (int w = 0; w < KGB_SBLOCK / 32; w++) {
         const KGB_ACC_T sw = swarp[w];
         if (w == warp) wpre = tile_agg;
         tile_agg = (w == 0) ? sw : KGB_RED(tile_agg, sw);
@@ -441,35 +471,24 @@ template <int V> __device__ __forceinline__ void kgb_scan_body(const KgbParams& 
         tile_agg = KGB_RED(carry, tile_agg);
     }
 #endif
-    if (tid == 0) {
-        if (tile == 0) {
-            incls[0] = tile_agg;
-            __threadfence();
-            kgb_st_release(&flags[0], KGB_FLAG_PREFIX);
-        } else {
-            aggs[tile] = tile_agg;
-            __threadfence();
-            kgb_st_release(&flags[tile], KGB_FLAG_AGG);
-        }
-    }
+    if (tid == 0) kgb_state_store(&states[tile], tile == 0 ? KGB_ST_PREFIX : KGB_ST_AGG, tile_agg);
     if (warp == 0 && tile > 0) {
         KGB_ACC_T excl = (KGB_ACC_T)(KGB_RED_IDENT);
         i64 look = (i64)tile - 1;
         while (true) {
             const i64 idx = look - lane;
-            u32 f = KGB_FLAG_PREFIX;  // virtual tiles before 0: an identity prefix
-            if (idx >= 0) f = kgb_ld_acquire(&flags[idx]);
+            u32 f = KGB_ST_PREFIX;  // virtual tiles before 0: an identity prefix
+            KGB_ACC_T c = (KGB_ACC_T)(KGB_RED_IDENT);
+            if (idx >= 0) f = kgb_state_load(&states[idx], c);
             // every lane of the warp takes part in the vote (lanes past tile 0 hold the virtual prefix)
             u32 spins = 0;
-            while (__any_sync(0xffffffffu, f == KGB_FLAG_EMPTY)) {
-                if (f == KGB_FLAG_EMPTY) f = kgb_ld_acquire(&flags[idx]);
+            while (__any_sync(0xffffffffu, f == KGB_ST_EMPTY)) {
+                if (f == KGB_ST_EMPTY) f = kgb_state_load(&states[idx], c);
                 if (++spins > (1u << 26)) __trap();  // a predecessor never published: fail, do not hang
             }
-            const u32 pmask = __ballot_sync(0xffffffffu, f == KGB_FLAG_PREFIX);
+            const u32 pmask = __ballot_sync(0xffffffffu, f == KGB_ST_PREFIX);
             const int first = __ffs(pmask) - 1;  // nearest tile holding an inclusive prefix
-            KGB_ACC_T c = (KGB_ACC_T)(KGB_RED_IDENT);
-            if ((pmask == 0 || lane <= first) && idx >= 0)
-                c = (lane == first) ? __ldcg(&incls[idx]) : __ldcg(&aggs[idx]);
+            if (!((pmask == 0 || lane <= first) && idx >= 0)) c = (KGB_ACC_T)(KGB_RED_IDENT);
 #pragma unroll
             for (int d = 16; d >= 1; d >>= 1) {
                 KGB_ACC_T o = kgb_shfl_xor<KGB_ACC_T>(c, d);
@@ -481,9 +500,7 @@ template <int V> __device__ __forceinline__ void kgb_scan_body(const KgbParams& 
         }
         if (lane == 0) {
             s_excl = excl;
-            incls[tile] = KGB_RED(excl, tile_agg);
-            __threadfence();
-            kgb_st_release(&flags[tile], KGB_FLAG_PREFIX);
+            kgb_state_store(&states[tile], KGB_ST_PREFIX, KGB_RED(excl, tile_agg));
         }
     }
     __syncthreads();
@@ -504,7 +521,7 @@ template <int V> __device__ __forceinline__ void kgb_scan_body(const KgbParams& 
     if (full) {
 #pragma unroll
         for (int h = 0; h < KGB_ITEMS / V; h++) {
-            const int e = (h * KGB_BLOCK + tid) * V;
+            const int e = (h * KGB_SBLOCK + tid) * V;
             KGB_OUT_T o[V];
 #pragma unroll
             for (int j = 0; j < V; j++) o[j] = (KGB_OUT_T)sbuf[kgb_pad(e + j)];
@@ -512,7 +529,7 @@ template <int V> __device__ __forceinline__ void kgb_scan_body(const KgbParams& 
         }
     } else {
         for (int k = 0; k < KGB_ITEMS; k++) {
-            const int e = k * KGB_BLOCK + tid;
+            const int e = k * KGB_SBLOCK + tid;
             if (base + e < n) out[base + e] = (KGB_OUT_T)sbuf[kgb_pad(e)];
         }
     }
@@ -530,7 +547,7 @@ template <int V> __device__ __forceinline__ void kgb_scan_body(const KgbParams& 
             r2 = KGB_RED2(r2, e2);
         }
     }
-    __shared__ KGB_ACC2_T sh2[KGB_BLOCK / 32];
+    __shared__ KGB_ACC2_T sh2[KGB_SBLOCK / 32];
     __shared__ bool is_last;
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) {
@@ -539,12 +556,12 @@ template <int V> __device__ __forceinline__ void kgb_scan_body(const KgbParams& 
     }
     if (lane == 0) sh2[warp] = r2;
     __syncthreads();
-    KGB_ACC2_T* part2 = (KGB_ACC2_T*)(incls + ntiles);
+    KGB_ACC2_T* part2 = (KGB_ACC2_T*)(states + ntiles);
     u32* done = ticket + 1;
     if (tid == 0) {
         KGB_ACC2_T a = sh2[0];
 #pragma unroll
-        for (int w = 1; w < KGB_BLOCK / 32; w++) a = KGB_RED2(a, sh2[w]);
+        for (int w = 1; w < KGB_SBLOCK / 32; w++) a = KGB_RED2(a, sh2[w]);
         ((volatile KGB_ACC2_T*)part2)[tile] = a;
         __threadfence();
         is_last = (atomicAdd(done, 1u) == ntiles - 1);
@@ -553,7 +570,7 @@ template <int V> __device__ __forceinline__ void kgb_scan_body(const KgbParams& 
     if (is_last) {
         __threadfence();
         KGB_ACC2_T a = (KGB_ACC2_T)(KGB_RED2_IDENT);
-        for (u32 b = tid; b < ntiles; b += KGB_BLOCK) {
+        for (u32 b = tid; b < ntiles; b += KGB_SBLOCK) {
             KGB_ACC2_T o = ((volatile KGB_ACC2_T*)part2)[b];
             a = KGB_RED2(a, o);
         }
@@ -568,12 +585,12 @@ template <int V> __device__ __forceinline__ void kgb_scan_body(const KgbParams& 
         if (tid == 0) {
             a = sh2[0];
 #pragma unroll
-            for (int w = 1; w < KGB_BLOCK / 32; w++) a = KGB_RED2(a, sh2[w]);
+            for (int w = 1; w < KGB_SBLOCK / 32; w++) a = KGB_RED2(a, sh2[w]);
             *(KGB_OUT_T*)p.out = (KGB_OUT_T)a;
         }
     }
 #endif
 }
-extern "C" __global__ void __launch_bounds__(KGB_BLOCK) KGB_KERNEL_NAME_V(const __grid_constant__ KgbParams p) { kgb_scan_body<KGB_VEC>(p); }
-extern "C" __global__ void __launch_bounds__(KGB_BLOCK) KGB_KERNEL_NAME_S(const __grid_constant__ KgbParams p) { kgb_scan_body<1>(p); }
+extern "C" __global__ void __launch_bounds__(KGB_SBLOCK) KGB_KERNEL_NAME_V(const __grid_constant__ KgbParams p) { kgb_scan_body<KGB_VEC>(p); }
+extern "C" __global__ void __launch_bounds__(KGB_SBLOCK) KGB_KERNEL_NAME_S(const __grid_constant__ KgbParams p) { kgb_scan_body<1>(p); }
 #endif

@@ -50,11 +50,11 @@ __device__ __forceinline__ u64 lb_warp_lookback(const u64* states, i64 tile, u32
     while (look >= 0) {
         const i64 idx = look - lane;
         u64 w = lb_pack(KGB_LB_PREFIX, epoch, 0);  // virtual tiles before 0
-        if (idx >= 0) w = ld_acquire_u64(&states[idx]);
+        if (idx >= 0) w = ld_relaxed_u64(&states[idx]);  // the count travels inside the polled word: no acquire
         // all 32 lanes vote (lanes past tile 0 hold the virtual prefix and never spin)
         u32 spins = 0;
         while (__any_sync(0xffffffffu, lb_flag(w, epoch) == 0)) {
-            if (lb_flag(w, epoch) == 0) w = ld_acquire_u64(&states[idx]);
+            if (lb_flag(w, epoch) == 0) w = ld_relaxed_u64(&states[idx]);
             if (++spins > (1u << 26)) __trap();  // a predecessor never published: fail, do not hang
         }
         const u32 pmask = __ballot_sync(0xffffffffu, lb_flag(w, epoch) == KGB_LB_PREFIX);

@@ -25,6 +25,7 @@ struct Driver {
                              CUstream, void**, void**) = nullptr;
     CUresult (*OccupancyMaxActiveBlocksPerMultiprocessor)(int*, CUfunction, int, size_t) = nullptr;
     CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
+    CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
     bool ok = false;
 };
 
@@ -44,6 +45,7 @@ static Driver& driver() {
         ok &= get("cuOccupancyMaxActiveBlocksPerMultiprocessor",
                   (void**)&d.OccupancyMaxActiveBlocksPerMultiprocessor);
         ok &= get("cuGetErrorString", (void**)&d.GetErrorString);
+        ok &= get("cuFuncSetAttribute", (void**)&d.FuncSetAttribute);
         d.ok = ok;
     });
     return d;
@@ -451,6 +453,7 @@ struct kgb_expr {
     CUmodule module = nullptr;
     CUfunction fn_v = nullptr, fn_s = nullptr;
     int occ_v = 1, occ_s = 1;
+    int sblock = 256, sitems = 16;  // scan tile geometry (threads, elements per thread)
 };
 
 namespace kgb {
@@ -466,6 +469,29 @@ struct KgbParamsHost {
 
 static std::mutex g_cache_mu;
 static std::unordered_map<std::string, kgb_expr*> g_cache;
+
+// Scan tile geometry.  The chained look-back moves (32-tile window / state round-trip) tiles per unit time, so
+// the tile must carry enough bytes for that rate to exceed HBM bandwidth (DESIGN.md "scan"); the tile also has
+// to fit shared memory several times per SM.  Overridable for tuning: KGB200_SCAN_BLOCK / KGB200_SCAN_ITEMS.
+static void scan_geometry(kgb_expr* h) {
+    const int sz = (int)dtype_size(h->acc_dtype);
+    h->sblock = 512;
+    h->sitems = 128 / sz;  // 128 B per thread
+    if (const char* e = getenv("KGB200_SCAN_BLOCK")) {
+        const int v = atoi(e);
+        if (v >= 32 && v <= 1024 && (v & (v - 1)) == 0) h->sblock = v;
+    }
+    if (const char* e = getenv("KGB200_SCAN_ITEMS")) {
+        const int v = atoi(e) / sz;  // given in bytes per thread
+        if (v >= 16 / sz && v * sz <= 512 && (v * sz) % 64 == 0) h->sitems = v;
+    }
+}
+
+// dynamic shared memory of a scan tile: KGB_SBLOCK * (KGB_ITEMS + 16 B pad) accumulators (jit_skeleton.cuh)
+static size_t scan_smem_bytes(const kgb_expr* h) {
+    const size_t sz = dtype_size(h->acc_dtype);
+    return (size_t)h->sblock * ((size_t)h->sitems * sz + 16);
+}
 
 static int build_source(kgb_expr* h, const int32_t* code, int n_code, const int32_t* code2, int n_code2) {
     Val v;
@@ -498,6 +524,10 @@ static int build_source(kgb_expr* h, const int32_t* code, int n_code, const int3
     m << "#define KGB_VEC " << h->vec << "\n";
     m << "#define KGB_OUT_T " << ctype(h->out_dtype) << "\n";
     m << "#define KGB_ACC_T " << ctype(h->acc_dtype) << "\n";
+    if (h->mode == KGB_MODE_SCAN || h->mode == KGB_MODE_SCANRED) {
+        scan_geometry(h);
+        m << "#define KGB_SBLOCK " << h->sblock << "\n#define KGB_ITEMS " << h->sitems << "\n";
+    }
     // scalars
     m << "#define KGB_SCALARS";
     for (size_t i = 0; i < h->args.size(); i++) {
@@ -592,8 +622,15 @@ static int jit_compile(kgb_expr* h, bool load) {
     if (cr != CUDA_SUCCESS) return set_error("cuModuleGetFunction(%s): %s", h->name_v.c_str(), cu_err(cr)), KGB_ECUDA;
     cr = d.ModuleGetFunction(&h->fn_s, h->module, h->name_s.c_str());
     if (cr != CUDA_SUCCESS) return set_error("cuModuleGetFunction(%s): %s", h->name_s.c_str(), cu_err(cr)), KGB_ECUDA;
-    d.OccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_v, h->fn_v, 256, 0);
-    d.OccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_s, h->fn_s, 256, 0);
+    const bool is_scan = h->mode == KGB_MODE_SCAN || h->mode == KGB_MODE_SCANRED;
+    const size_t dyn = is_scan ? scan_smem_bytes(h) : 0;
+    if (dyn) {
+        cr = d.FuncSetAttribute(h->fn_v, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)dyn);
+        if (cr == CUDA_SUCCESS) cr = d.FuncSetAttribute(h->fn_s, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)dyn);
+        if (cr != CUDA_SUCCESS) return set_error("cuFuncSetAttribute(max dynamic smem %zu): %s", dyn, cu_err(cr)), KGB_ECUDA;
+    }
+    d.OccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_v, h->fn_v, is_scan ? h->sblock : 256, dyn);
+    d.OccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_s, h->fn_s, is_scan ? h->sblock : 256, dyn);
     if (h->occ_v < 1) h->occ_v = 1;
     if (h->occ_s < 1) h->occ_s = 1;
     return KGB_OK;
@@ -601,7 +638,7 @@ static int jit_compile(kgb_expr* h, bool load) {
 
 static const int kBlock = 256, kUnroll = 4;
 
-static long long scan_tile(const kgb_expr* h) { return (long long)kBlock * (128 / (long long)dtype_size(h->acc_dtype)); }
+static long long scan_tile(const kgb_expr* h) { return (long long)h->sblock * h->sitems; }
 
 static unsigned fold_grid(const kgb_expr* h, long long n, bool vec) {
     const long long V = vec ? h->vec : 1;
@@ -695,7 +732,7 @@ extern "C" int kgb_expr_workspace_bytes(const kgb_expr* h, int64_t n, size_t* ou
         b = 64 + (size_t)sm_count() * std::max(h->occ_v, h->occ_s) * dtype_size(h->acc_dtype);
     } else if (h->mode == KGB_MODE_SCAN || h->mode == KGB_MODE_SCANRED) {
         const size_t tiles = (size_t)((n + scan_tile(h) - 1) / scan_tile(h));
-        b = 64 + align_up(tiles * 4, 64) + 2 * tiles * dtype_size(h->acc_dtype);
+        b = 64 + tiles * 16;
         if (h->mode == KGB_MODE_SCANRED) b += tiles * dtype_size(h->acc2_dtype);
     }
     *out_bytes = align_up(b, 64);
@@ -746,10 +783,12 @@ extern "C" int kgb_expr_launch(kgb_expr* h, const void* const* args, int64_t n, 
         const size_t tiles = (size_t)((n + scan_tile(h) - 1) / scan_tile(h));
         KGB_REQUIRE(tiles < 0xffffffffull, "kgb_expr_launch: too many scan tiles");
         grid = (unsigned)tiles;
-        KGB_CUDA_CHECK(cudaMemsetAsync(workspace, 0, 64 + align_up(tiles * 4, 64), st));
+        KGB_CUDA_CHECK(cudaMemsetAsync(workspace, 0, 64 + tiles * 16, st));
     }
     void* params[] = {&P};
-    CUresult cr = driver().LaunchKernel(aligned ? h->fn_v : h->fn_s, grid, 1, 1, kBlock, 1, 1, 0, (CUstream)stream,
+    const unsigned block = (h->mode == KGB_MODE_SCAN || h->mode == KGB_MODE_SCANRED) ? (unsigned)h->sblock : (unsigned)kBlock;
+    const unsigned dyn_smem = (h->mode == KGB_MODE_SCAN || h->mode == KGB_MODE_SCANRED) ? (unsigned)scan_smem_bytes(h) : 0u;
+    CUresult cr = driver().LaunchKernel(aligned ? h->fn_v : h->fn_s, grid, 1, 1, block, 1, 1, dyn_smem, (CUstream)stream,
                                         params, nullptr);
     if (cr != CUDA_SUCCESS) return set_error("cuLaunchKernel(%s): %s", h->name_v.c_str(), cu_err(cr)), KGB_ECUDA;
     return KGB_OK;

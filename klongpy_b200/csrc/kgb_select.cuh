@@ -1,13 +1,15 @@
 // Single-pass stream compaction (decoupled look-back on the running count), shared by find / where /
-// group-boundaries / unique.  Tile = 8 warps x 16 rows x 32 lanes = 4096 elements; each warp ballots its
-// rows so every lane knows the whole warp's masks without shuffles.
+// group-boundaries / unique.  Tile = 16 warps x 16 rows x 32 lanes = 8192 elements (64 KB of 8-byte input):
+// the chained look-back advances about (32-tile window / state round trip) tiles per unit time, so a tile must
+// carry enough bytes for that rate to exceed HBM bandwidth (4096-element tiles measured 16 % of roofline).
+// Each warp ballots its rows so every lane knows the whole warp's masks without shuffles.
 #pragma once
 #include "kgb_device.cuh"
 #include "kgb_internal.h"
 
 namespace kgb {
 
-constexpr int SEL_THREADS = 256;
+constexpr int SEL_THREADS = 512;
 constexpr int SEL_ROWS = 16;
 constexpr int SEL_TILE = SEL_THREADS * SEL_ROWS;
 
@@ -32,11 +34,19 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(Pred pred, i64 n, i
     const i64 ntiles = (n + SEL_TILE - 1) / SEL_TILE;
     const i64 wbase = tile * SEL_TILE + (i64)warp * (SEL_ROWS * 32);
 
+    // all of a thread's loads are issued before the first test: a fused load+compare per row lets the compiler
+    // recycle one destination register, which serialises the loads (measured: 16 % of HBM roofline)
+    typename Pred::V val[SEL_ROWS];
+#pragma unroll
+    for (int r = 0; r < SEL_ROWS; r++) {
+        const i64 i = wbase + r * 32 + lane;
+        val[r] = pred.load(i < n ? i : (n - 1));
+    }
     bool hit[SEL_ROWS];
 #pragma unroll
     for (int r = 0; r < SEL_ROWS; r++) {
         const i64 i = wbase + r * 32 + lane;
-        hit[r] = (i < n) && pred(i);
+        hit[r] = (i < n) && pred.test(i, val[r]);
     }
     u32 masks[SEL_ROWS];
     u32 wtotal = 0;
@@ -78,18 +88,24 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(Pred pred, i64 n, i
 }
 
 template <typename T> struct NonzeroPred {
+    typedef T V;
     const T* a;
-    __device__ __forceinline__ bool operator()(i64 i) const { return __ldcs(&a[i]) != T(0); }
+    __device__ __forceinline__ V load(i64 i) const { return __ldcs(&a[i]); }
+    __device__ __forceinline__ bool test(i64, V v) const { return v != T(0); }
 };
 template <typename T> struct EqualPred {
+    typedef T V;
     const T* a;
     T needle;
-    __device__ __forceinline__ bool operator()(i64 i) const { return __ldcs(&a[i]) == needle; }
+    __device__ __forceinline__ V load(i64 i) const { return __ldcs(&a[i]); }
+    __device__ __forceinline__ bool test(i64, V v) const { return v == needle; }
 };
 // run heads of a sorted, order-encoded key array
 struct BoundaryPred {
+    typedef ulonglong2 V;
     const u64* k;
-    __device__ __forceinline__ bool operator()(i64 i) const { return i == 0 || k[i] != k[i - 1]; }
+    __device__ __forceinline__ V load(i64 i) const { return make_ulonglong2(k[i], k[i > 0 ? i - 1 : 0]); }
+    __device__ __forceinline__ bool test(i64 i, V v) const { return i == 0 || v.x != v.y; }
 };
 
 template <typename Pred>

@@ -19,8 +19,10 @@ namespace kgb {
 
 constexpr int RADIX = 256;
 constexpr int NPASS = 8;
-constexpr int ST = 256;            // threads per CTA
-constexpr int SI = 16;             // keys per thread
+constexpr int ST = 512;            // threads per CTA
+constexpr int SI = 8;              // keys per thread (8 x (u64 key + u32 pos + u32 rank) = 32 payload registers, so
+                                   // two 512-thread CTAs fit an SM's register file; 16/thread ran at 25 % occupancy)
+constexpr int LB = 4;              // look-back states fetched per round (independent loads, one L2 round trip)
 constexpr int STILE = ST * SI;     // 4096 keys per tile
 constexpr int SWARPS = ST / 32;
 
@@ -154,12 +156,12 @@ struct PassSmem {
     u32 whist[SWARPS][RADIX];
     u32 dstart[RADIX];   // exclusive digit offsets inside the tile
     i64 gbase[RADIX];    // global position of tile-sorted slot p with digit d is gbase[d] + p
-    u32 wsum[SWARPS];
+    u32 wsum[RADIX / 32];
     u32 tile;
 };
 
 template <int DT>
-__global__ void __launch_bounds__(ST) onesweep_pass(const typename KeyCodec<DT>::T* __restrict__ in_keys,
+__global__ void __launch_bounds__(ST, 2) onesweep_pass(const typename KeyCodec<DT>::T* __restrict__ in_keys,
                                                      u64* keysA, u64* keysB, u32* idxA, u32* idxB,
                                                      i64* __restrict__ idx_out,
                                                      typename KeyCodec<DT>::T* __restrict__ keys_sorted_out,
@@ -224,8 +226,9 @@ __global__ void __launch_bounds__(ST) onesweep_pass(const typename KeyCodec<DT>:
         __syncwarp();
     }
     __syncthreads();
-    // ---- per digit (thread d): exclusive offsets across warps, tile count, publish, look back
-    {
+    // ---- per digit (threads 0..255): exclusive offsets across warps, tile count, publish, look back
+    u32 cnt = 0, inc = 0;
+    if (tid < RADIX) {
         const int d = tid;
         u32 run = 0;
 #pragma unroll
@@ -234,40 +237,56 @@ __global__ void __launch_bounds__(ST) onesweep_pass(const typename KeyCodec<DT>:
             s.whist[w][d] = run;
             run += c;
         }
-        const u32 cnt = run;
-        u64* my_state = &states[(size_t)tile * RADIX + d];
-        st_relaxed_u64(my_state, lb_pack(tile == 0 ? KGB_LB_PREFIX : KGB_LB_AGG, epoch, cnt));
+        cnt = run;
+        st_relaxed_u64(&states[(size_t)tile * RADIX + d], lb_pack(tile == 0 ? KGB_LB_PREFIX : KGB_LB_AGG, epoch, cnt));
         // exclusive scan of cnt over the 256 digits -> dstart
-        u32 inc = cnt;
+        inc = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const u32 v = __shfl_up_sync(0xffffffffu, inc, o);
             if (lane >= o) inc += v;
         }
         if (lane == 31) s.wsum[warp] = inc;
-        __syncthreads();
+    }
+    __syncthreads();
+    if (tid < RADIX) {
+        const int d = tid;
         u32 wpre = 0;
 #pragma unroll
-        for (int w = 0; w < SWARPS; w++)
+        for (int w = 0; w < RADIX / 32; w++)
             if (w < warp) wpre += s.wsum[w];
         const u32 dstart = wpre + inc - cnt;
         s.dstart[d] = dstart;
         u64 excl = 0;
         if (tile > 0) {
+            // chained look-back, LB predecessor states per round: the loads are independent, so a round costs
+            // one L2 round trip instead of LB of them
             i64 t = tile - 1;
             u32 spins = 0;
-            while (true) {
-                const u64 w = ld_relaxed_u64(&states[(size_t)t * RADIX + d]);
-                const u64 f = lb_flag(w, epoch);
-                if (f == 0) {
-                    if (++spins > (1u << 26)) __trap();  // a predecessor never published: fail, do not hang
-                    continue;
+            bool done = false;
+            while (!done) {
+                u64 w[LB];
+#pragma unroll
+                for (int j = 0; j < LB; j++) {
+                    const i64 tj = t - j;
+                    w[j] = (tj >= 0) ? ld_relaxed_u64(&states[(size_t)tj * RADIX + d]) : lb_pack(KGB_LB_PREFIX, epoch, 0);
                 }
-                excl += lb_count(w);
-                if (f == KGB_LB_PREFIX) break;
-                t--;
+                int used = 0;
+#pragma unroll
+                for (int j = 0; j < LB; j++) {
+                    if (!done && used == j) {
+                        const u64 f = lb_flag(w[j], epoch);
+                        if (f != 0) {
+                            excl += lb_count(w[j]);
+                            used = j + 1;
+                            done = (f == KGB_LB_PREFIX);
+                        }
+                    }
+                }
+                t -= used;
+                if (used == 0 && ++spins > (1u << 24)) __trap();  // a predecessor never published: fail, do not hang
             }
-            st_relaxed_u64(my_state, lb_pack(KGB_LB_PREFIX, epoch, excl + cnt));
+            st_relaxed_u64(&states[(size_t)tile * RADIX + d], lb_pack(KGB_LB_PREFIX, epoch, excl + cnt));
         }
         s.gbase[d] = (i64)(plan->digit_base[pass][d] + excl) - (i64)dstart;
     }

@@ -1,0 +1,47 @@
+"""Time the running-sum / fused scan-reduce kernels for one tile geometry (KGB200_SCAN_BLOCK / KGB200_SCAN_ITEMS
+are read at JIT time, so each geometry is its own process)."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, ".")
+from klongpy_b200 import _lib, ops  # noqa: E402
+from klongpy_b200.ops import OPC, OP_ARG  # noqa: E402
+
+dev = torch.device("cuda:0")
+ops.set_default_device(dev)
+n = int(float(sys.argv[1])) if len(sys.argv) > 1 else 1 << 28
+peak = 6546.2
+
+
+def timeit(fn, reps=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(reps):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / reps
+
+
+ki = torch.randint(0, 256, (n,), dtype=torch.int64, device=dev)
+x = ops.asarray(ki.to(torch.float64) / 256)
+r = ops.scan("add", x)
+chk = torch.cumsum(x._t[: 1 << 22], 0)
+assert torch.equal(r._t[: 1 << 22], chk), "scan mismatch"
+assert r._t[-1].item() == ki.sum().item() / 256.0, "scan total mismatch"
+del r, chk, ki
+ms = timeit(lambda: ops.scan("add", x))
+ms2 = timeit(lambda: ops.run([OP_ARG, 0], [x], mode=_lib.MODE_SCANRED, red=_lib.RED_MAX, code2=[4, OP_ARG, 0, OPC["sub"]],
+                             red2=_lib.RED_MAX))
+xi = ops.asarray(torch.randint(-1000, 1000, (n,), dtype=torch.int64, device=dev))
+ms3 = timeit(lambda: ops.scan("add", xi))
+print(f"block={os.environ.get('KGB200_SCAN_BLOCK', 'dflt')} bytes/thr={os.environ.get('KGB200_SCAN_ITEMS', 'dflt')} n={n}: "
+      f"scan f64 {ms:.3f} ms {16 * n / ms / 1e6:.0f} GB/s frac {16 * n / ms / 1e6 / peak:.3f} | "
+      f"scanred {ms2:.3f} ms {8 * n / ms2 / 1e6:.0f} GB/s frac {8 * n / ms2 / 1e6 / peak:.3f} | "
+      f"scan i64 {ms3:.3f} ms frac {16 * n / ms3 / 1e6 / peak:.3f}", flush=True)

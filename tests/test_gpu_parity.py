@@ -425,7 +425,15 @@ def test_grouped_min_mean_max(be, K, n, G):
     rmn, rmx, rsm, rct = O.grouped_stats(k, v, G)
     assert np.array_equal(mn, rmn) and np.array_equal(mx, rmx) and np.array_equal(ct, rct)   # bit-exact / exact
     assert np.allclose(sm, rsm, rtol=RTOL, atol=1e-9)
-    assert O.report_1brc(mn, mx, sm, ct) == O.report_1brc(rmn, rmx, rsm, rct)                 # the 1brc report lines
+    # the 1brc report lines (par.kg:4-6).  The mean is sum%count printed with one decimal; a sum that differs in its
+    # last bits (association order) may flip the print only when the mean sits on an x.x5 rounding boundary.
+    rep, ref = O.report_1brc(mn, mx, sm, ct), O.report_1brc(rmn, rmx, rsm, rct)
+    assert rep.keys() == ref.keys()
+    for s in rep:
+        if rep[s] != ref[s]:
+            m10 = rsm[s] / rct[s] * 10
+            assert abs(abs(m10 - np.floor(m10)) - 0.5) < 1e-9, (s, rep[s], ref[s])
+            assert rep[s].split("/")[0::2] == ref[s].split("/")[0::2]
     with pytest.raises(Exception):
         K.groupagg(dev(be, [0, G]), dev(be, [1.0, 2.0]), G)
 
