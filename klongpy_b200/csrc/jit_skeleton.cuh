@@ -594,3 +594,305 @@ template <int V> __device__ __forceinline__ void kgb_scan_body(const KgbParams& 
 extern "C" __global__ void __launch_bounds__(KGB_SBLOCK) KGB_KERNEL_NAME_V(const __grid_constant__ KgbParams p) { kgb_scan_body<KGB_VEC>(p); }
 extern "C" __global__ void __launch_bounds__(KGB_SBLOCK) KGB_KERNEL_NAME_S(const __grid_constant__ KgbParams p) { kgb_scan_body<1>(p); }
 #endif
+
+// =====================================================================================================
+#if KGB_MODE == 2 && defined(KGB_PIPE)
+// ------------------------------------------------------------------ SCAN, persistent pipelined variant
+// Used when the expression reads exactly ONE 8-byte array (running sum / max / min / product of x, of x*2, ...).
+// The generic kernel above spends ~45 % of its warp time at the barrier behind the look-back (ncu, r1c): a
+// look-back is 2-4 dependent L2 round trips at ~1 us each under a saturated memory system, and nothing else
+// in the CTA can run meanwhile.  Here ONE persistent CTA per SM takes the look-back off the critical path:
+//
+//   cp.async ring  : KGB_PS stages of 32 KB (4096 elements).  Raw input of tile i+P streams into its stage with
+//                    16-byte cp.async (no registers held) while tiles i .. i-D are being worked on.
+//   phase A (i)    : each compute thread reads its 128-byte row from the stage (XOR-swizzled 16-byte chunks:
+//                    conflict-free both row-wise and stripe-wise), evaluates the expression, scans in registers,
+//                    adds the CTA-local prefix and writes the row back IN PLACE; thread 0 publishes the tile
+//                    aggregate and hands the tile to a look-back warp through an mbarrier.
+//   look-back warps: KGB_PLW dedicated warps; warp (i mod KGB_PLW) resolves tile i's exclusive prefix with a
+//                    128-tile window per round (4 independent state loads per lane) and signals an mbarrier.
+//   phase B (i-D)  : D tiles later the prefix is (almost always) already there: stripe-wise read of the parked
+//                    tile, add the prefix, coalesced 128-bit streaming stores.  No transposition on the way out —
+//                    adding a scalar does not care about layout.
+// Tiles come from the same atomic ticket as the generic kernel, so no co-residency assumption is made.
+#define KGB_PT 256
+#define KGB_PS 7
+#define KGB_PP 2
+#define KGB_PD 4
+#define KGB_PLW 4
+#define KGB_PITEMS 16
+#define KGB_PTILE (KGB_PT * KGB_PITEMS)
+#define KGB_PSTAGE_BYTES (KGB_PTILE * 8)
+#define KGB_PRING 16
+
+struct KgbPipeCtl {
+    u64 agg_bar[KGB_PS];
+    u64 pre_bar[KGB_PS];
+    KGB_ACC_T agg[KGB_PS];
+    KGB_ACC_T excl[KGB_PS];
+    u32 aggtile[KGB_PS + 1];
+    u32 tile_ring[KGB_PRING];
+    KGB_ACC_T swarp[KGB_PT / 32];
+};
+
+__device__ __forceinline__ u32 kgb_smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void kgb_mbar_init(u64* bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(kgb_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void kgb_mbar_arrive(u64* bar) {
+    asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" ::"r"(kgb_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void kgb_mbar_wait(u64* bar, u32 parity) {
+    const u32 a = kgb_smem_u32(bar);
+    u32 done = 0, spins = 0;
+    while (!done) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
+        if (!done && ++spins > (1u << 24)) __trap();  // fail, do not hang
+    }
+}
+__device__ __forceinline__ void kgb_cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(kgb_smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void kgb_bar_compute() { asm volatile("bar.sync 1, %0;" ::"n"(KGB_PT) : "memory"); }
+
+// physical byte offset of 16-byte chunk `c` (0..7) of row `row` inside a stage
+__device__ __forceinline__ int kgb_swz(int row, int c) { return row * 128 + ((c ^ (row & 7)) << 4); }
+
+extern "C" __global__ void __launch_bounds__(KGB_PT + 32 * KGB_PLW, 1) KGB_KERNEL_NAME_P(const __grid_constant__ KgbParams p) {
+    KGB_SCALARS
+    extern __shared__ __align__(128) unsigned char kgb_dyn_smem[];
+    unsigned char* stages = kgb_dyn_smem;
+    KgbPipeCtl& ctl = *reinterpret_cast<KgbPipeCtl*>(kgb_dyn_smem + KGB_PS * KGB_PSTAGE_BYTES);
+    const i64 n = p.n;
+    const u32 ntiles = (u32)((n + KGB_PTILE - 1) / KGB_PTILE);
+    u32* ticket = (u32*)p.ws;
+    uint4* states = (uint4*)((char*)p.ws + 64);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const KGB_PIPE_T* __restrict__ src = (const KGB_PIPE_T*)KGB_PIPE_PTR;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < KGB_PS; s++) {
+            kgb_mbar_init(&ctl.agg_bar[s], 1);
+            kgb_mbar_init(&ctl.pre_bar[s], 1);
+        }
+        for (int j = 0; j < KGB_PP + 2; j++) ctl.tile_ring[j] = atomicAdd(ticket, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp >= KGB_PT / 32) {
+        // ================================================================ look-back warps
+        const u32 lw = (u32)warp - KGB_PT / 32;
+        for (u32 i = lw;; i += KGB_PLW) {
+            const u32 s = i % KGB_PS;
+            kgb_mbar_wait(&ctl.agg_bar[s], (i / KGB_PS) & 1u);
+            const u32 tile = ctl.aggtile[s];
+            if (tile == 0xffffffffu) break;
+            KGB_ACC_T excl = (KGB_ACC_T)(KGB_RED_IDENT);
+            if (tile == 0) {
+#ifdef KGB_HAS_CARRY
+                excl = (KGB_ACC_T)(KGB_CARRY);
+#endif
+            } else {
+                const KGB_ACC_T agg = ctl.agg[s];
+                i64 look = (i64)tile - 1;
+                bool done = false;
+                while (!done) {
+                    KGB_ACC_T c[4];
+                    u32 f[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const i64 idx = look - (j * 32 + lane);
+                        f[j] = KGB_ST_PREFIX;  // virtual tiles before 0: an identity prefix
+                        c[j] = (KGB_ACC_T)(KGB_RED_IDENT);
+                        if (idx >= 0) f[j] = kgb_state_load(&states[idx], c[j]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        if (!done) {
+                            const i64 idx = look - (j * 32 + lane);
+                            u32 spins = 0;
+                            while (__any_sync(0xffffffffu, f[j] == KGB_ST_EMPTY)) {
+                                if (f[j] == KGB_ST_EMPTY) f[j] = kgb_state_load(&states[idx], c[j]);
+                                if (++spins > (1u << 24)) __trap();  // a predecessor never published: fail, do not hang
+                            }
+                            const u32 pmask = __ballot_sync(0xffffffffu, f[j] == KGB_ST_PREFIX);
+                            const int first = __ffs(pmask) - 1;  // nearest tile holding an inclusive prefix
+                            KGB_ACC_T v = ((pmask == 0 || lane <= first) && idx >= 0) ? c[j] : (KGB_ACC_T)(KGB_RED_IDENT);
+#pragma unroll
+                            for (int d = 16; d >= 1; d >>= 1) {
+                                KGB_ACC_T o = kgb_shfl_xor<KGB_ACC_T>(v, d);
+                                v = KGB_RED(v, o);
+                            }
+                            excl = KGB_RED(v, excl);
+                            done = (pmask != 0);
+                        }
+                    }
+                    look -= 128;
+                }
+                if (lane == 0) kgb_state_store(&states[tile], KGB_ST_PREFIX, KGB_RED(excl, agg));
+            }
+            if (lane == 0) {
+                ctl.excl[s] = excl;
+                kgb_mbar_arrive(&ctl.pre_bar[s]);
+            }
+            __syncwarp();
+        }
+        return;
+    }
+
+    // ==================================================================== compute warps (tid < KGB_PT)
+    KGB_OUT_T* __restrict__ out = (KGB_OUT_T*)p.out;
+
+    // stream one tile into its stage: 8 x 16-byte cp.async per thread, stripe-wise (coalesced)
+    auto issue_load = [&](u32 li) {
+        const u32 t = ctl.tile_ring[li % KGB_PRING];
+        if (t < ntiles) {
+            unsigned char* sb = stages + (size_t)(li % KGB_PS) * KGB_PSTAGE_BYTES;
+            const i64 base = (i64)t * KGB_PTILE;
+            if (base + KGB_PTILE <= n) {
+#pragma unroll
+                for (int h = 0; h < 8; h++) {
+                    const int cf = h * KGB_PT + tid;
+                    kgb_cp_async16(sb + kgb_swz(cf >> 3, cf & 7), src + base + cf * 2);
+                }
+            } else {  // the last, partial tile: guarded element loads (zero-filled beyond n, masked in phase A)
+#pragma unroll
+                for (int h = 0; h < 8; h++) {
+                    const int cf = h * KGB_PT + tid;
+                    KGB_PIPE_T v0 = 0, v1 = 0;
+                    if (base + cf * 2 < n) v0 = src[base + cf * 2];
+                    if (base + cf * 2 + 1 < n) v1 = src[base + cf * 2 + 1];
+                    KGB_PIPE_T* d = reinterpret_cast<KGB_PIPE_T*>(sb + kgb_swz(cf >> 3, cf & 7));
+                    d[0] = v0;
+                    d[1] = v1;
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    // phase B: parked tile + exclusive prefix -> global, stripe-wise
+    auto phase_b = [&](u32 li, u32 t) {
+        const u32 s = li % KGB_PS;
+        kgb_mbar_wait(&ctl.pre_bar[s], (li / KGB_PS) & 1u);
+        const KGB_ACC_T excl = ctl.excl[s];
+        const unsigned char* sb = stages + (size_t)s * KGB_PSTAGE_BYTES;
+        const i64 base = (i64)t * KGB_PTILE;
+        const bool full = (base + KGB_PTILE <= n);
+#pragma unroll
+        for (int h = 0; h < 8; h++) {
+            const int cf = h * KGB_PT + tid;
+            KGB_ACC_T v[2];
+            *reinterpret_cast<uint4*>(v) = *reinterpret_cast<const uint4*>(sb + kgb_swz(cf >> 3, cf & 7));
+            KGB_OUT_T o[2];
+            o[0] = (KGB_OUT_T)(KGB_RED(excl, v[0]));
+            o[1] = (KGB_OUT_T)(KGB_RED(excl, v[1]));
+            if (full) {
+                kgb_stv<KGB_OUT_T, 2>(out + base + cf * 2, o);
+            } else {
+                if (base + cf * 2 < n) out[base + cf * 2] = o[0];
+                if (base + cf * 2 + 1 < n) out[base + cf * 2 + 1] = o[1];
+            }
+        }
+    };
+
+#pragma unroll
+    for (int j = 0; j < KGB_PP; j++) issue_load((u32)j);
+
+    u32 tq[KGB_PD];  // tiles parked in shared memory, oldest first
+#pragma unroll
+    for (int j = 0; j < KGB_PD; j++) tq[j] = 0xffffffffu;
+    u32 tk = 0;
+    u32 i = 0;
+    for (;; i++) {
+        const u32 s = i % KGB_PS;
+        if (tid == 0) {
+            if (i > 0) ctl.tile_ring[(i + KGB_PP + 1) % KGB_PRING] = tk;  // ticket taken one iteration ago
+            tk = atomicAdd(ticket, 1u);                                    // for local tile i + P + 2
+        }
+        const u32 tile = ctl.tile_ring[i % KGB_PRING];
+        if (tile >= ntiles) break;
+        issue_load(i + KGB_PP);
+        asm volatile("cp.async.wait_group %0;" ::"n"(KGB_PP) : "memory");
+        kgb_bar_compute();
+
+        // ---- phase A
+        unsigned char* sb = stages + (size_t)s * KGB_PSTAGE_BYTES;
+        const i64 base = (i64)tile * KGB_PTILE;
+        const bool full = (base + KGB_PTILE <= n);
+        KGB_ACC_T x[KGB_PITEMS];
+        {
+            KGB_DECL_REGS(KGB_PITEMS)
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+                *reinterpret_cast<uint4*>(&KGB_PIPE_ARG[q * 2]) = *reinterpret_cast<const uint4*>(sb + kgb_swz(tid, q));
+#pragma unroll
+            for (int k = 0; k < KGB_PITEMS; k++) {
+                x[k] = (KGB_ACC_T)(KGB_EVAL(k));
+                if (!full && base + tid * KGB_PITEMS + k >= n) x[k] = (KGB_ACC_T)(KGB_RED_IDENT);
+            }
+        }
+#pragma unroll
+        for (int k = 1; k < KGB_PITEMS; k++) x[k] = KGB_RED(x[k - 1], x[k]);
+        KGB_ACC_T inc = x[KGB_PITEMS - 1];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            KGB_ACC_T o = kgb_shfl_up<KGB_ACC_T>(inc, d);
+            if (lane >= d) inc = KGB_RED(o, inc);
+        }
+        if (lane == 31) ctl.swarp[warp] = inc;
+        KGB_ACC_T lane_excl = kgb_shfl_up<KGB_ACC_T>(inc, 1);
+        kgb_bar_compute();
+        KGB_ACC_T wpre = (KGB_ACC_T)(KGB_RED_IDENT);
+        KGB_ACC_T tile_agg = (KGB_ACC_T)(KGB_RED_IDENT);
+#pragma unroll
+        for (int w = 0; w < KGB_PT / 32; w++) {
+            const KGB_ACC_T sw = ctl.swarp[w];
+            if (w == warp) wpre = tile_agg;
+            tile_agg = (w == 0) ? sw : KGB_RED(tile_agg, sw);
+        }
+        const KGB_ACC_T thread_excl = (lane == 0) ? wpre : KGB_RED(wpre, lane_excl);
+        if (tid == 0) {
+            KGB_ACC_T pub = tile_agg;
+#ifdef KGB_HAS_CARRY
+            if (tile == 0) pub = KGB_RED((KGB_ACC_T)(KGB_CARRY), tile_agg);
+#endif
+            kgb_state_store(&states[tile], tile == 0 ? KGB_ST_PREFIX : KGB_ST_AGG, pub);
+            ctl.agg[s] = tile_agg;
+            ctl.aggtile[s] = tile;
+            kgb_mbar_arrive(&ctl.agg_bar[s]);
+        }
+#pragma unroll
+        for (int k = 0; k < KGB_PITEMS; k++) x[k] = KGB_RED(thread_excl, x[k]);
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+            *reinterpret_cast<uint4*>(sb + kgb_swz(tid, q)) = *reinterpret_cast<uint4*>(&x[q * 2]);
+        // the row-wise write-back must be visible to the stripe-wise readers of phase B: the barrier at the top of
+        // a later iteration orders it (phase B of this tile runs D >= 1 iterations from now)
+
+        // ---- phase B of the tile parked D iterations ago
+        if (tq[0] != 0xffffffffu) phase_b(i - KGB_PD, tq[0]);
+#pragma unroll
+        for (int j = 0; j < KGB_PD - 1; j++) tq[j] = tq[j + 1];
+        tq[KGB_PD - 1] = tile;
+    }
+    // ---- drain: remaining parked tiles (i is the first local index without a tile)
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    kgb_bar_compute();
+#pragma unroll
+    for (int j = 0; j < KGB_PD; j++)
+        if (tq[j] != 0xffffffffu) phase_b(i - KGB_PD + j, tq[j]);
+    kgb_bar_compute();
+    if (tid == 0) {
+        // release the look-back warps: one sentinel per warp, on the stages of the next KGB_PLW local indices
+        for (u32 k = 0; k < KGB_PLW; k++) {
+            const u32 s = (i + k) % KGB_PS;
+            ctl.aggtile[s] = 0xffffffffu;
+            kgb_mbar_arrive(&ctl.agg_bar[s]);
+        }
+    }
+}
+#endif

@@ -454,6 +454,9 @@ struct kgb_expr {
     CUfunction fn_v = nullptr, fn_s = nullptr;
     int occ_v = 1, occ_s = 1;
     int sblock = 256, sitems = 16;  // scan tile geometry (threads, elements per thread)
+    int pipe_arg = -1;              // >= 0: the persistent pipelined scan kernel exists (index of its one array argument)
+    std::string name_p;
+    CUfunction fn_p = nullptr;
 };
 
 namespace kgb {
@@ -475,7 +478,7 @@ static std::unordered_map<std::string, kgb_expr*> g_cache;
 // to fit shared memory several times per SM.  Overridable for tuning: KGB200_SCAN_BLOCK / KGB200_SCAN_ITEMS.
 static void scan_geometry(kgb_expr* h) {
     const int sz = (int)dtype_size(h->acc_dtype);
-    h->sblock = 512;
+    h->sblock = 256;
     h->sitems = 128 / sz;  // 128 B per thread
     if (const char* e = getenv("KGB200_SCAN_BLOCK")) {
         const int v = atoi(e);
@@ -486,6 +489,11 @@ static void scan_geometry(kgb_expr* h) {
         if (v >= 16 / sz && v * sz <= 512 && (v * sz) % 64 == 0) h->sitems = v;
     }
 }
+
+// persistent pipelined scan (jit_skeleton.cuh KGB_PIPE): 7 stages of 4096 x 8 B + control block, 256 + 4*32 threads
+static const size_t kPipeSmem = 7 * 32768 + 512;
+static const long long kPipeTile = 4096;
+static const unsigned kPipeThreads = 256 + 4 * 32;
 
 // dynamic shared memory of a scan tile: KGB_SBLOCK * (KGB_ITEMS + 16 B pad) accumulators (jit_skeleton.cuh)
 static size_t scan_smem_bytes(const kgb_expr* h) {
@@ -561,6 +569,20 @@ static int build_source(kgb_expr* h, const int32_t* code, int n_code, const int3
         if (vc.s.find("[(j)]") != std::string::npos) return set_error("scan seed program must not read arrays"), KGB_EINVAL;
         m << "#define KGB_HAS_CARRY 1\n#define KGB_CARRY (" << cast(vc, h->acc_dtype) << ")\n";
     }
+    if (h->mode == KGB_MODE_SCAN && dtype_size(h->acc_dtype) == 8 && dtype_size(h->out_dtype) == 8 && !getenv("KGB200_NO_PIPE")) {
+        // persistent pipelined variant (jit_skeleton.cuh, KGB_PIPE): exactly one array argument, 8-byte elements
+        int n_arr = 0, idx = -1;
+        for (size_t i = 0; i < h->args.size(); i++)
+            if (h->args[i].kind == KGB_ARG_ARRAY) {
+                n_arr++;
+                idx = (int)i;
+            }
+        if (n_arr == 1 && dtype_size(h->args[idx].dtype) == 8) {
+            h->pipe_arg = idx;
+            m << "#define KGB_PIPE 1\n#define KGB_PIPE_T " << ctype(h->args[idx].dtype) << "\n#define KGB_PIPE_ARG a" << idx
+              << "\n#define KGB_PIPE_PTR p.ptr[" << idx << "]\n";
+        }
+    }
     if (h->mode == KGB_MODE_SCANRED) {
         m << "#define KGB_ACC2_T " << ctype(h->acc2_dtype) << "\n";
         m << "#define KGB_EVAL2(j, sv) (" << cast(v2, h->acc2_dtype) << ")\n";
@@ -573,8 +595,10 @@ static int build_source(kgb_expr* h, const int32_t* code, int n_code, const int3
     std::string stem = std::string("kgb_") + mode_names[h->mode] + "_" + hx;
     h->name_v = stem + "_v";
     h->name_s = stem + "_s";
+    h->name_p = stem + "_p";
     h->source = "// generated by libkgb200 (kgb_expr.cpp)\n#define KGB_KERNEL_NAME_V " + h->name_v +
-                "\n#define KGB_KERNEL_NAME_S " + h->name_s + "\n" + macros + kgb_jit_skeleton_src;
+                "\n#define KGB_KERNEL_NAME_S " + h->name_s + "\n#define KGB_KERNEL_NAME_P " + h->name_p + "\n" + macros +
+                kgb_jit_skeleton_src;
     return KGB_OK;
 }
 
@@ -622,6 +646,12 @@ static int jit_compile(kgb_expr* h, bool load) {
     if (cr != CUDA_SUCCESS) return set_error("cuModuleGetFunction(%s): %s", h->name_v.c_str(), cu_err(cr)), KGB_ECUDA;
     cr = d.ModuleGetFunction(&h->fn_s, h->module, h->name_s.c_str());
     if (cr != CUDA_SUCCESS) return set_error("cuModuleGetFunction(%s): %s", h->name_s.c_str(), cu_err(cr)), KGB_ECUDA;
+    if (h->pipe_arg >= 0) {
+        cr = d.ModuleGetFunction(&h->fn_p, h->module, h->name_p.c_str());
+        if (cr != CUDA_SUCCESS) return set_error("cuModuleGetFunction(%s): %s", h->name_p.c_str(), cu_err(cr)), KGB_ECUDA;
+        cr = d.FuncSetAttribute(h->fn_p, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)kPipeSmem);
+        if (cr != CUDA_SUCCESS) return set_error("cuFuncSetAttribute(%s, %zu B): %s", h->name_p.c_str(), kPipeSmem, cu_err(cr)), KGB_ECUDA;
+    }
     const bool is_scan = h->mode == KGB_MODE_SCAN || h->mode == KGB_MODE_SCANRED;
     const size_t dyn = is_scan ? scan_smem_bytes(h) : 0;
     if (dyn) {
@@ -731,7 +761,8 @@ extern "C" int kgb_expr_workspace_bytes(const kgb_expr* h, int64_t n, size_t* ou
     if (h->mode == KGB_MODE_REDUCE) {
         b = 64 + (size_t)sm_count() * std::max(h->occ_v, h->occ_s) * dtype_size(h->acc_dtype);
     } else if (h->mode == KGB_MODE_SCAN || h->mode == KGB_MODE_SCANRED) {
-        const size_t tiles = (size_t)((n + scan_tile(h) - 1) / scan_tile(h));
+        const long long tl = std::min(scan_tile(h), kPipeTile);
+        const size_t tiles = (size_t)((n + tl - 1) / tl);
         b = 64 + tiles * 16;
         if (h->mode == KGB_MODE_SCANRED) b += tiles * dtype_size(h->acc2_dtype);
     }
@@ -773,6 +804,7 @@ extern "C" int kgb_expr_launch(kgb_expr* h, const void* const* args, int64_t n, 
     KGB_REQUIRE(workspace_bytes >= need && (need == 0 || workspace), "kgb_expr_launch: workspace %zu < %zu bytes",
                 workspace_bytes, need);
     unsigned grid = 1;
+    bool use_pipe = false;
     cudaStream_t st = (cudaStream_t)stream;
     if (h->mode == KGB_MODE_MAP) {
         grid = fold_grid(h, n, aligned);
@@ -783,7 +815,17 @@ extern "C" int kgb_expr_launch(kgb_expr* h, const void* const* args, int64_t n, 
         const size_t tiles = (size_t)((n + scan_tile(h) - 1) / scan_tile(h));
         KGB_REQUIRE(tiles < 0xffffffffull, "kgb_expr_launch: too many scan tiles");
         grid = (unsigned)tiles;
-        KGB_CUDA_CHECK(cudaMemsetAsync(workspace, 0, 64 + tiles * 16, st));
+        const size_t ptiles = (size_t)((n + kPipeTile - 1) / kPipeTile);
+        // the persistent variant pays a pipeline fill per CTA: worth it once every SM has a few tiles
+        use_pipe = h->fn_p && aligned && ptiles >= (size_t)sm_count() * 4;
+        if (use_pipe) grid = (unsigned)std::min<size_t>(ptiles, (size_t)sm_count());
+        KGB_CUDA_CHECK(cudaMemsetAsync(workspace, 0, 64 + std::max(tiles, ptiles) * 16, st));
+    }
+    if (use_pipe) {
+        void* pp[] = {&P};
+        CUresult pr = driver().LaunchKernel(h->fn_p, grid, 1, 1, kPipeThreads, 1, 1, (unsigned)kPipeSmem, (CUstream)stream, pp, nullptr);
+        if (pr != CUDA_SUCCESS) return set_error("cuLaunchKernel(%s): %s", h->name_p.c_str(), cu_err(pr)), KGB_ECUDA;
+        return KGB_OK;
     }
     void* params[] = {&P};
     const unsigned block = (h->mode == KGB_MODE_SCAN || h->mode == KGB_MODE_SCANRED) ? (unsigned)h->sblock : (unsigned)kBlock;

@@ -4,6 +4,8 @@
 // v1: streaming 128-bit loads of both columns; the G x 4 table lives in L2-resident global memory.
 // min/max use order-encoded 64-bit integers with a read-before-update filter (after the first few rows of a
 // station almost no row improves its extremes, so the RED is rarely issued); sum/count are RED.ADD.
+#include <cstdlib>
+
 #include "kgb_device.cuh"
 #include "kgb_internal.h"
 
@@ -79,6 +81,87 @@ __global__ void __launch_bounds__(256) groupagg_kernel(const i64* __restrict__ k
     }
 }
 
+// v2: per-CTA shared-memory state for everything that does not need a 64-bit float atomic.
+//   cnt[k]        u32 row count of this CTA (native ATOMS.ADD), flushed to the global table at the end
+//   minhi/maxhi   upper 32 bits of the order-encoded running extremes seen by this CTA: a row whose upper half
+//                 cannot beat them is filtered with two LDS and touches no atomic unit; the exact 64-bit
+//                 extreme lives in the L2-resident global table and is updated (read-check + RED) only by
+//                 rows that pass the filter — O(log rows) per station per CTA on unordered data
+//   sum           RED.ADD.F64 on the global table (shared-memory f64 add is a CAS loop, ATOMS.CAST.SPIN)
+// One persistent CTA per SM, 12 B of shared memory per station.
+template <int COUNT_IN_SMEM>
+__global__ void __launch_bounds__(1024, 1) groupagg_kernel_v2(const i64* __restrict__ keys, const double* __restrict__ vals,
+                                                              i64 n, i64 G, AggWs a) {
+    extern __shared__ __align__(16) unsigned char agg_smem[];
+    u32* s_cnt = reinterpret_cast<u32*>(agg_smem);
+    u32* s_minhi = s_cnt + G;
+    u32* s_maxhi = s_minhi + G;
+    for (i64 i = threadIdx.x; i < G; i += blockDim.x) {
+        s_cnt[i] = 0u;
+        s_minhi[i] = 0xffffffffu;
+        s_maxhi[i] = 0u;
+    }
+    __syncthreads();
+    auto row = [&](i64 k, double v) {
+        if ((u64)k >= (u64)G) {
+            *a.err = 1;
+            return;
+        }
+        const u64 emin = enc_for_min(v), emax = enc_for_max(v);
+        const u32 lo = (u32)(emin >> 32), hi = (u32)(emax >> 32);
+        if (lo <= s_minhi[k]) {
+            if (lo < s_minhi[k]) atomicMin(&s_minhi[k], lo);
+            if (emin < ld_relaxed_u64(&a.tmin[k])) atomicMin(&a.tmin[k], emin);
+        }
+        if (hi >= s_maxhi[k]) {
+            if (hi > s_maxhi[k]) atomicMax(&s_maxhi[k], hi);
+            if (emax > ld_relaxed_u64(&a.tmax[k])) atomicMax(&a.tmax[k], emax);
+        }
+        atomicAdd(&a.tsum[k], v);
+        if (COUNT_IN_SMEM)
+            atomicAdd(&s_cnt[k], 1u);
+        else
+            atomicAdd(&a.tcnt[k], 1ull);
+    };
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    const i64 tid = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool vec = ((reinterpret_cast<uintptr_t>(keys) | reinterpret_cast<uintptr_t>(vals)) & 15) == 0;
+    constexpr int U = 4;
+    if (vec) {
+        const i64 n2 = n / 2;
+        for (i64 g0 = tid; g0 < n2; g0 += stride * U) {
+            longlong2 k[U];
+            double2 v[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const i64 g = g0 + u * stride;
+                if (g < n2) {
+                    k[u] = __ldcs(reinterpret_cast<const longlong2*>(keys) + g);
+                    v[u] = __ldcs(reinterpret_cast<const double2*>(vals) + g);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const i64 g = g0 + u * stride;
+                if (g < n2) {
+                    row(k[u].x, v[u].x);
+                    row(k[u].y, v[u].y);
+                }
+            }
+        }
+        if ((n & 1) && tid == 0) row(keys[n - 1], vals[n - 1]);
+    } else {
+        for (i64 i = tid; i < n; i += stride) row(keys[i], vals[i]);
+    }
+    if (COUNT_IN_SMEM) {
+        __syncthreads();
+        for (i64 i = threadIdx.x; i < G; i += blockDim.x) {
+            const u32 c = s_cnt[i];
+            if (c) atomicAdd(&a.tcnt[i], (u64)c);
+        }
+    }
+}
+
 __device__ __forceinline__ double nanpropagating_min(double a, double b) { return (a != a) ? a : ((b != b) ? b : (a < b ? a : b)); }
 __device__ __forceinline__ double nanpropagating_max(double a, double b) { return (a != a) ? a : ((b != b) ? b : (a > b ? a : b)); }
 
@@ -148,7 +231,33 @@ extern "C" int kgb_groupagg_f64(const int64_t* keys, const double* vals, int64_t
         const long long cap = (long long)sm_count() * 8;
         if (blocks > cap) blocks = cap;
         if (blocks < 1) blocks = 1;
-        groupagg_kernel<<<(unsigned)blocks, 256, 0, st>>>((const i64*)keys, vals, n, n_groups, a);
+        // variant: 1 = shared-memory filters + shared count (default when the table fits), 2 = filters only,
+        // 0 = v1 (all four updates on the global table).  KGB200_AGG_VARIANT overrides for measurements.
+        int variant = 1;
+        if (const char* e = getenv("KGB200_AGG_VARIANT")) variant = atoi(e);
+        const size_t smem = (size_t)n_groups * 12;
+        if (smem > 200 * 1024) variant = 0;
+        if (variant == 0) {
+            groupagg_kernel<<<(unsigned)blocks, 256, 0, st>>>((const i64*)keys, vals, n, n_groups, a);
+        } else {
+            static bool attr_set[64][2] = {{false}};
+            const int dev = current_device();
+            const int vi = variant == 1 ? 1 : 0;
+            if (!attr_set[dev][vi]) {
+                if (vi)
+                    KGB_CUDA_CHECK(cudaFuncSetAttribute(groupagg_kernel_v2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                else
+                    KGB_CUDA_CHECK(cudaFuncSetAttribute(groupagg_kernel_v2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                attr_set[dev][vi] = true;
+            }
+            long long pb = (n / 2 + 1024 * 4 - 1) / (1024 * 4);
+            if (pb > sm_count()) pb = sm_count();
+            if (pb < 1) pb = 1;
+            if (vi)
+                groupagg_kernel_v2<1><<<(unsigned)pb, 1024, smem, st>>>((const i64*)keys, vals, n, n_groups, a);
+            else
+                groupagg_kernel_v2<0><<<(unsigned)pb, 1024, smem, st>>>((const i64*)keys, vals, n, n_groups, a);
+        }
     }
     groupagg_finalize<<<(unsigned)((n_groups + 255) / 256), 256, 0, st>>>(a, n_groups, min_out, max_out, sum_out,
                                                                          (i64*)count_out, accumulate);

@@ -32,10 +32,18 @@ def timeit(fn, reps=10):
 ki = torch.randint(0, 256, (n,), dtype=torch.int64, device=dev)
 x = ops.asarray(ki.to(torch.float64) / 256)
 r = ops.scan("add", x)
-chk = torch.cumsum(x._t[: 1 << 22], 0)
-assert torch.equal(r._t[: 1 << 22], chk), "scan mismatch"
-assert r._t[-1].item() == ki.sum().item() / 256.0, "scan total mismatch"
-del r, chk, ki
+chk = torch.cumsum(ki, 0).to(torch.float64) / 256  # exact: every partial sum of k/256 is representable
+bad = (r._t != chk).nonzero()
+assert bad.numel() == 0, f"scan mismatch at {bad[:4].flatten().tolist()} of {n}"
+del r, chk, ki, bad
+for m in (n - 1, n - 4097, 4096 * 148 * 4 + 5):  # ragged tails through the same path
+    xs = ops.asarray(x._t[:m])
+    rs = ops.scan("add", xs)
+    assert torch.equal(rs._t, torch.cumsum(xs._t, 0)), f"scan mismatch at n={m}"
+    del xs, rs
+mx = ops.scan("max", x)
+assert torch.equal(mx._t, torch.cummax(x._t, 0).values), "running max mismatch"
+del mx
 ms = timeit(lambda: ops.scan("add", x))
 ms2 = timeit(lambda: ops.run([OP_ARG, 0], [x], mode=_lib.MODE_SCANRED, red=_lib.RED_MAX, code2=[4, OP_ARG, 0, OPC["sub"]],
                              red2=_lib.RED_MAX))
