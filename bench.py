@@ -300,7 +300,7 @@ def main():
                        "l2": "inputs (8 GB/GPU) are larger than L2; no flush needed",
                        "exchange": "none" if world == 1 else "all_gather of per-rank partials (reduce) and totals (scan carry)"},
             "roofline": {"bound": "hbm", "achieved": 16.0 * n / (scan_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": 16.0 * n / (scan_ms * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "kgb_scan_* (running sum +\\x)",
+                         "frac": 16.0 * n / (scan_ms * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "kgb_scan_*_p (running sum +\\x, persistent pipelined scan)",
                          "algorithmic_bytes_per_launch": 16 * n, "ms_per_launch": scan_ms, "peak_source": peak_src},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": per_step_launches * args.steps, "clocks": clocks,
             "primitives": prims,
@@ -350,6 +350,28 @@ def primitive_table(be, ops, dist, time_kernel, dev, peak, world, rank):
     out["grouped_min_mean_max_10k_1e8"] = prim_row(n, time_kernel(lambda: dist.sharded_groupagg(keys_10k, temp, 10_000), 3),
                                                   16, peak, n_gpus=world)
     del temp, a
+    # config 5: autograd at a 1e7-element batch (fused forward + fused backward kernels, float64)
+    m = 10_000_000
+    X = DeviceArray(torch.rand(m, dtype=torch.float64, device=dev, generator=g) * 2)
+    Y = DeviceArray(torch.rand(m, dtype=torch.float64, device=dev, generator=g))
+
+    def nn_loss(params):
+        w, b = params
+        s = 1 / (1 + ops.unary("exp", 0 - ((w * X) + b)))
+        return ops.reduce("add", (s - Y) ** 2)
+
+    out["autograd_sigmoid_nn_1e7"] = prim_row(m, time_kernel(lambda: be.compute_multi_autograd(nn_loss, [0.1, 0.1]), 3), 32, peak,
+                                              note="operator-by-operator tape, as the interpreter evaluates the Klong source")
+    R = DeviceArray(torch.rand(m, dtype=torch.float64, device=dev, generator=g) * 0.14 + 0.01)
+    V = DeviceArray(torch.rand(m, dtype=torch.float64, device=dev, generator=g) * 0.35 + 0.05)
+    W = DeviceArray(torch.full((m,), 1.0 / m, dtype=torch.float64, device=dev))
+    sharpe_ir = ("binop", "%", ("reduce", "+", ("binop", "*", ("var", "_v0"), ("var", "_v1"))),
+                 ("binop", "^", ("reduce", "+", ("binop", "*", ("binop", "^", ("var", "_v0"), ("literal", 2)),
+                                                 ("binop", "^", ("var", "_v2"), ("literal", 2)))), ("literal", 0.5)))
+    sharpe, _ = be.compile_expr_ir(sharpe_ir, ["x", "returns", "vols"])
+    out["autograd_sharpe_grad_1e7"] = prim_row(m, time_kernel(lambda: be.compute_autograd(lambda x: sharpe(x, R, V), W), 3), 56, peak,
+                                               note="compiled IR tree: fused forward and fused backward kernels")
+    del X, Y, R, V, W
     keys_full = DeviceArray(torch.randint(-2**62, 2**62, (n,), dtype=torch.int64, device=dev, generator=g))
     out["grade_up_full64_1e8"] = prim_row(n, time_kernel(lambda: ops.argsort(keys_full), 3), 16, peak,
                                           model_bytes_per_elem=8 + 24 * 8 - 4 + 4, passes=8)

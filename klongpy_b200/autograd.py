@@ -1,13 +1,212 @@
-"""Autograd interop — placeholder until the differentiable wrappers land.
+"""Autograd interop (BASELINE config 5).
 
-The reference's torch backend differentiates by running the interpreter on `requires_grad` tensors
-(`torch_backend.py:692-782`).  The B200 path will wrap the fused kernels in `torch.autograd.Function`s; until
-then the hooks raise, so `:>` reports a clear error instead of silently computing on the CPU.
+The reference's torch backend differentiates by running the interpreter on `requires_grad` tensors and letting
+ATen record one node per operator (`torch_backend.py:692-782`; inputs are cast to float32, `:692-699`).  Here
+torch's tape is only the *bookkeeping*: every libkgb200 expression launch whose operands require grad is recorded
+as ONE `torch.autograd.Function` node whose backward launches the fused gradient programs derived symbolically
+by `autodiff.py` (one fused kernel per differentiated operand, recomputing from the inputs — no intermediate
+is saved).  Compiled IR trees therefore stay fused under `:>`: `loss::{+/(sigmoid((w1*X)+b1)-Y)^2}` is one
+reduce kernel forward and one reduce kernel per scalar parameter backward.  float64 throughout.
+
+Provider hooks mirror `BackendProvider.create_grad_tensor / compute_autograd / compute_multi_autograd /
+compute_jacobian` (`base.py:226-258`) with the reference's error types (`autograd.py:10-32`).
 """
+import numpy as np
+import torch
+
+from . import _lib, autodiff, ops
+from .array import DeviceArray
+
+try:
+    from klongpy.autograd import AutogradChainBrokenError, NonScalarLossError
+except Exception:  # pragma: no cover - GPU box without klongpy
+    class AutogradChainBrokenError(Exception):
+        def __init__(self, context, expected, actual, suggestion=None):
+            msg = f"Autograd chain broken at {context}: expected {expected}, got {actual}."
+            if suggestion:
+                msg += f" {suggestion}"
+            super().__init__(msg)
+
+    class NonScalarLossError(Exception):
+        def __init__(self, shape):
+            self.shape = shape
+            super().__init__(f"Loss function must return a scalar, got shape {shape}. "
+                             "Use sum (+/) or mean (%#) to reduce to a scalar.")
+
+NotDifferentiable = autodiff.NotDifferentiable
 
 
-def _todo(*_a, **_k):
-    raise NotImplementedError("klongpy_b200: autograd interop is not implemented yet (SURVEY.md §8 row a14)")
+def wants_grad(args):
+    return torch.is_grad_enabled() and any(isinstance(a, DeviceArray) and a._t.requires_grad for a in args)
 
 
-create_grad_tensor = compute_autograd = compute_multi_autograd = compute_jacobian = _todo
+class _Spec:
+    """Static description of one launch: program, mode and where the tensor operands sit among the arguments."""
+    __slots__ = ("code", "mode", "red", "template", "out_shape", "device")
+
+    def __init__(self, code, mode, red, template, out_shape, device):
+        self.code, self.mode, self.red = tuple(code), mode, red
+        self.template, self.out_shape, self.device = template, out_shape, device
+
+    def rebuild(self, tensors):
+        """argument list with detached DeviceArrays in the tensor slots"""
+        it = iter(tensors)
+        return [DeviceArray(next(it).detach()) if slot is _TENSOR else slot for slot in self.template]
+
+
+_TENSOR = object()
+
+
+def run_differentiable(code, args, mode, red, code2, red2, out_shape, device):
+    """ops.run for operands that require grad: same launch, recorded as one autograd node."""
+    if code2 or mode == _lib.MODE_SCANRED:
+        raise NotDifferentiable("fused scan+reduce programs take the eager path under autograd")
+    if mode == _lib.MODE_REDUCE and red == _lib.RED_MUL:
+        raise NotDifferentiable("*/ has no gradient rule here")
+    if mode == _lib.MODE_SCAN and red != _lib.RED_ADD:
+        raise NotDifferentiable("only +\\ is differentiable")
+    autodiff.parse(code)  # unknown operators fail before anything runs
+    tensors = [a._t for a in args if isinstance(a, DeviceArray)]
+    template = [_TENSOR if isinstance(a, DeviceArray) else a for a in args]
+    out = _Launch.apply(_Spec(code, mode, red, template, out_shape, device), *tensors)
+    return DeviceArray(out)
+
+
+def _sum_to(x, shape):
+    """gradient of a broadcast scalar operand: fold the elementwise gradient"""
+    if x.ndim == 0:
+        return x._t.reshape(shape)
+    return ops.reduce("add", x.flatten())._t.reshape(shape)
+
+
+_prog_cache = {}
+
+
+def _grad_prog(code, pos, n_args, gated):
+    """Postfix program of  g * d f/d(arg pos)  [* the arg-extreme gate]  over (args..., g[, out, count]); cached —
+    the symbolic work happens once per (program, operand), not once per backward pass."""
+    key = (code, pos, n_args, gated)
+    if key not in _prog_cache:
+        tan = autodiff.tangent(autodiff.parse(code), pos)
+        if autodiff._is(tan, 0.0):
+            _prog_cache[key] = None
+        else:
+            tree = autodiff.op("mul", ("arg", n_args), tan)
+            if gated:
+                hit = autodiff.op("eq_b", autodiff.parse(code), ("arg", n_args + 1))
+                tree = autodiff.op("mul", tree, autodiff.op("where", hit, autodiff.op("div", autodiff.ONE, ("arg", n_args + 2)),
+                                                            autodiff.ZERO))
+            _prog_cache[key] = tuple(autodiff.emit(("op", "to_f64", tree)))
+    return _prog_cache[key]
+
+
+class _Launch(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, spec, *tensors):
+        with torch.no_grad():
+            out = ops.run(spec.code, spec.rebuild(tensors), mode=spec.mode, red=spec.red, out_shape=spec.out_shape,
+                          device=spec.device)
+        ctx.spec = spec
+        ctx.save_for_backward(*tensors, out._t)
+        if not out._t.dtype.is_floating_point:
+            ctx.mark_non_differentiable(out._t)
+        return out._t
+
+    @staticmethod
+    def backward(ctx, g):
+        spec = ctx.spec
+        *tensors, out = ctx.saved_tensors
+        with torch.no_grad():
+            args = spec.rebuild(tensors)
+            n_args = len(args)
+            G = DeviceArray(g.contiguous())
+            extra = [G]
+            gate = None  # tree multiplied into the tangent (max/min folds route the gradient to the arg-extremes)
+            if spec.mode == _lib.MODE_SCAN:
+                # out_j = sum_{k<=j} f_k  =>  dL/df_k = sum_{j>=k} g_j : a reversed running sum
+                extra = [ops.reverse(ops.scan("add", ops.reverse(G)))]
+            elif spec.mode == _lib.MODE_REDUCE and spec.red in (_lib.RED_MAX, _lib.RED_MIN):
+                f = autodiff.parse(spec.code)
+                hit = autodiff.op("eq_b", f, ("arg", n_args + 1))
+                cnt = ops.run(autodiff.emit(("op", "to_f64", hit)), args + [G, DeviceArray(out)], mode=_lib.MODE_REDUCE,
+                              red=_lib.RED_ADD)
+                extra = [G, DeviceArray(out), cnt]  # ties share the gradient evenly, like torch.amax
+                gate = True
+            grads = [None]
+            slots = [k for k, s in enumerate(spec.template) if s is _TENSOR]
+            for j, pos in enumerate(slots):
+                t = tensors[j]
+                if not ctx.needs_input_grad[j + 1] or not t.dtype.is_floating_point:
+                    grads.append(None)
+                    continue
+                prog = _grad_prog(spec.code, pos, n_args, gate is not None)
+                if prog is None:
+                    grads.append(torch.zeros_like(t))
+                    continue
+                full = args + extra
+                elementwise = t.dim() > 0
+                if elementwise:
+                    r = ops.run(prog, full, out_shape=tuple(t.shape) if t.numel() == 0 else None)
+                    grads.append(r._t.to(t.dtype) if r._t.shape == t.shape else _sum_to(r, t.shape).to(t.dtype))
+                else:
+                    # a 0-d operand broadcast against arrays: its gradient is the FOLD of the elementwise gradient —
+                    # one fused reduce kernel, nothing materialised
+                    if any(isinstance(a, DeviceArray) and a.ndim > 0 for a in full):
+                        r = ops.run(prog, full, mode=_lib.MODE_REDUCE, red=_lib.RED_ADD)
+                    else:
+                        r = ops.run(prog, full, out_shape=())
+                    grads.append(r._t.reshape(t.shape).to(t.dtype))
+        return tuple(grads)
+
+
+# ------------------------------------------------------------------------------------------- provider hooks
+def create_grad_tensor(backend, x):
+    """A float64 leaf that tracks gradients (the reference casts to float32, torch_backend.py:692-699)."""
+    if isinstance(x, DeviceArray):
+        t = x._t.detach().clone().to(torch.float64)
+    elif isinstance(x, torch.Tensor):
+        t = x.detach().clone().to(device=backend._device, dtype=torch.float64)
+    else:
+        t = torch.as_tensor(np.asarray(x, dtype=np.float64)).to(backend._device)
+    return DeviceArray(t.requires_grad_(True))
+
+
+def _check_loss(y, what):
+    if not isinstance(y, DeviceArray):
+        kind = "numpy.ndarray" if isinstance(y, np.ndarray) else type(y).__name__
+        raise AutogradChainBrokenError(what, "device array", kind, "Keep the computation on b200 device arrays.")
+    if y.size != 1:
+        raise NonScalarLossError(tuple(y.shape))
+    if not y._t.requires_grad:
+        raise AutogradChainBrokenError("gradient computation", "requires_grad=True", "requires_grad=False",
+                                       "Output lost gradient tracking (integer result, .item(), or a host round trip).")
+
+
+def compute_autograd(backend, func, x):
+    xt = create_grad_tensor(backend, x)
+    y = func(xt)
+    _check_loss(y, "function output")
+    y._t.backward()
+    return DeviceArray(xt._t.grad)
+
+
+def compute_multi_autograd(backend, func, params):
+    leaves = [create_grad_tensor(backend, p) for p in params]
+    y = func(leaves)
+    _check_loss(y, "loss computation")
+    grads = torch.autograd.grad(y._t, [p._t for p in leaves], create_graph=False)
+    return [DeviceArray(g) for g in grads]
+
+
+def compute_jacobian(backend, func, x):
+    xt = create_grad_tensor(backend, x)
+    y = func(xt)
+    if not isinstance(y, DeviceArray):
+        raise AutogradChainBrokenError("function output", "device array", type(y).__name__)
+    flat = y._t.reshape(-1)
+    rows = []
+    for i in range(flat.numel()):
+        (gi,) = torch.autograd.grad(flat[i], xt._t, retain_graph=True, allow_unused=True)
+        rows.append(torch.zeros_like(xt._t) if gi is None else gi)
+    jac = torch.stack(rows).reshape(tuple(y.shape) + tuple(xt.shape)) if rows else torch.zeros(0, device=xt._t.device)
+    return DeviceArray(jac)

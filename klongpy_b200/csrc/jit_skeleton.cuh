@@ -61,10 +61,11 @@ template <> struct kgb_lim<u8> {
 };
 
 // np.maximum / np.minimum: NaN-propagating for floats
-__device__ __forceinline__ double kgb_max(double a, double b) { return (a != a) ? a : ((b != b) ? b : (a > b ? a : b)); }
-__device__ __forceinline__ double kgb_min(double a, double b) { return (a != a) ? a : ((b != b) ? b : (a < b ? a : b)); }
-__device__ __forceinline__ float kgb_max(float a, float b) { return (a != a) ? a : ((b != b) ? b : (a > b ? a : b)); }
-__device__ __forceinline__ float kgb_min(float a, float b) { return (a != a) ? a : ((b != b) ? b : (a < b ? a : b)); }
+// (a NaN -> a; b NaN -> b because a > NaN is false: two compares instead of three)
+__device__ __forceinline__ double kgb_max(double a, double b) { return (a != a || a > b) ? a : b; }
+__device__ __forceinline__ double kgb_min(double a, double b) { return (a != a || a < b) ? a : b; }
+__device__ __forceinline__ float kgb_max(float a, float b) { return (a != a || a > b) ? a : b; }
+__device__ __forceinline__ float kgb_min(float a, float b) { return (a != a || a < b) ? a : b; }
 __device__ __forceinline__ i64 kgb_max(i64 a, i64 b) { return a > b ? a : b; }
 __device__ __forceinline__ i64 kgb_min(i64 a, i64 b) { return a < b ? a : b; }
 __device__ __forceinline__ int kgb_max(int a, int b) { return a > b ? a : b; }
@@ -508,8 +509,7 @@ template <int V> __device__ __forceinline__ void kgb_scan_body(const KgbParams& 
 #pragma unroll
     for (int k = 0; k < KGB_ITEMS; k++) x[k] = KGB_RED(thread_excl, x[k]);
 
-#if KGB_MODE == 2
-    // ---- 4. blocked -> smem -> striped coalesced stores
+    // ---- 4. blocked -> smem -> striped (coalesced) epilogue
     {
         KGB_ACC_T* dst = &sbuf[tid * (KGB_ITEMS + KGB_PADE)];
 #pragma unroll
@@ -517,6 +517,7 @@ template <int V> __device__ __forceinline__ void kgb_scan_body(const KgbParams& 
             reinterpret_cast<uint4*>(dst)[q] = *reinterpret_cast<uint4*>(&x[q * (16 / (int)sizeof(KGB_ACC_T))]);
     }
     __syncthreads();
+#if KGB_MODE == 2
     KGB_OUT_T* __restrict__ out = (KGB_OUT_T*)p.out;
     if (full) {
 #pragma unroll
@@ -534,17 +535,38 @@ template <int V> __device__ __forceinline__ void kgb_scan_body(const KgbParams& 
         }
     }
 #else
-    // ---- 4'. epilogue g(scan value, args[i]) folded with RED2; args re-read in the blocked layout
-    // (the tile was just streamed, so these hit L2) -> per-tile partial -> last tile folds in order.
+    // ---- 4'. epilogue g(scan value, args[i]) folded with RED2.  The arguments are re-read stripe-wise with the
+    // same 128-bit coalesced loads as step 1 (the tile was streamed moments ago, so these hit L2); a row-wise
+    // re-read (one element per lane at a 128-byte stride) measured 19 % of roofline.
     KGB_ACC2_T r2 = (KGB_ACC2_T)(KGB_RED2_IDENT);
+    if (full) {
 #pragma unroll
-    for (int k = 0; k < KGB_ITEMS; k++) {
-        const i64 gi = base + (i64)tid * KGB_ITEMS + k;
-        if (gi < n) {
-            KGB_DECL_REGS(1)
-            KGB_LOAD_VEC(1, 0, gi)
-            KGB_ACC2_T e2 = (KGB_ACC2_T)(KGB_EVAL2(0, x[k]));
-            r2 = KGB_RED2(r2, e2);
+        for (int h = 0; h < KGB_ITEMS / V; h += KGB_UNROLL) {
+            KGB_DECL_REGS(V * KGB_UNROLL)
+#pragma unroll
+            for (int u = 0; u < KGB_UNROLL; u++) {
+                const int e = ((h + u) * KGB_SBLOCK + tid) * V;
+                KGB_LOAD_VEC(V, u * V, base + e)
+            }
+#pragma unroll
+            for (int u = 0; u < KGB_UNROLL; u++) {
+                const int e = ((h + u) * KGB_SBLOCK + tid) * V;
+#pragma unroll
+                for (int j = 0; j < V; j++) {
+                    KGB_ACC2_T e2 = (KGB_ACC2_T)(KGB_EVAL2(u * V + j, sbuf[kgb_pad(e + j)]));
+                    r2 = KGB_RED2(r2, e2);
+                }
+            }
+        }
+    } else {
+        for (int k = 0; k < KGB_ITEMS; k++) {
+            const int e = k * KGB_SBLOCK + tid;
+            if (base + e < n) {
+                KGB_DECL_REGS(1)
+                KGB_LOAD_VEC(1, 0, base + e)
+                KGB_ACC2_T e2 = (KGB_ACC2_T)(KGB_EVAL2(0, sbuf[kgb_pad(e)]));
+                r2 = KGB_RED2(r2, e2);
+            }
         }
     }
     __shared__ KGB_ACC2_T sh2[KGB_SBLOCK / 32];
@@ -596,7 +618,7 @@ extern "C" __global__ void __launch_bounds__(KGB_SBLOCK) KGB_KERNEL_NAME_S(const
 #endif
 
 // =====================================================================================================
-#if KGB_MODE == 2 && defined(KGB_PIPE)
+#if (KGB_MODE == 2 || KGB_MODE == 3) && defined(KGB_PIPE)
 // ------------------------------------------------------------------ SCAN, persistent pipelined variant
 // Used when the expression reads exactly ONE 8-byte array (running sum / max / min / product of x, of x*2, ...).
 // The generic kernel above spends ~45 % of its warp time at the barrier behind the look-back (ncu, r1c): a
@@ -615,13 +637,22 @@ extern "C" __global__ void __launch_bounds__(KGB_SBLOCK) KGB_KERNEL_NAME_S(const
 //                    tile, add the prefix, coalesced 128-bit streaming stores.  No transposition on the way out —
 //                    adding a scalar does not care about layout.
 // Tiles come from the same atomic ticket as the generic kernel, so no co-residency assumption is made.
-#define KGB_PT 256
-#define KGB_PS 7
-#define KGB_PP 2
-#define KGB_PD 4
-#define KGB_PLW 4
-#define KGB_PITEMS 16
-#define KGB_PTILE (KGB_PT * KGB_PITEMS)
+#ifndef KGB_PT
+#define KGB_PT 256   // compute threads (256 or 512); a tile is always 4096 elements
+#endif
+#ifndef KGB_PS
+#define KGB_PS 7     // stages
+#define KGB_PP 2     // tiles in flight from global memory
+#define KGB_PD 4     // tiles parked while their look-back runs
+#define KGB_PLW 4    // look-back warps
+#endif
+#ifndef KGB_PMINB
+#define KGB_PMINB 1  // CTAs per SM
+#endif
+#define KGB_PTILE 4096
+#define KGB_PITEMS (KGB_PTILE / KGB_PT)   // elements per thread row: 16 or 8
+#define KGB_PCR (KGB_PITEMS / 2)          // 16-byte chunks per row: 8 or 4
+#define KGB_PCT (KGB_PTILE / 2 / KGB_PT)  // chunks per thread: 8 or 4
 #define KGB_PSTAGE_BYTES (KGB_PTILE * 8)
 #define KGB_PRING 16
 
@@ -633,6 +664,9 @@ struct KgbPipeCtl {
     u32 aggtile[KGB_PS + 1];
     u32 tile_ring[KGB_PRING];
     KGB_ACC_T swarp[KGB_PT / 32];
+#if KGB_MODE == 3
+    KGB_ACC2_T sh2[KGB_PT / 32];
+#endif
 };
 
 __device__ __forceinline__ u32 kgb_smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
@@ -657,9 +691,13 @@ __device__ __forceinline__ void kgb_cp_async16(void* smem_dst, const void* gsrc)
 __device__ __forceinline__ void kgb_bar_compute() { asm volatile("bar.sync 1, %0;" ::"n"(KGB_PT) : "memory"); }
 
 // physical byte offset of 16-byte chunk `c` (0..7) of row `row` inside a stage
-__device__ __forceinline__ int kgb_swz(int row, int c) { return row * 128 + ((c ^ (row & 7)) << 4); }
+// (rows of 128 B: chunk ^ (row & 7); rows of 64 B: chunk ^ ((row >> 1) & 3) — either way the 8 threads of a
+// quarter-warp hit 8 different 16-byte bank groups whether they walk down rows or along them)
+__device__ __forceinline__ int kgb_swz(int row, int c) {
+    return KGB_PCR == 8 ? row * 128 + ((c ^ (row & 7)) << 4) : row * 64 + ((c ^ ((row >> 1) & 3)) << 4);
+}
 
-extern "C" __global__ void __launch_bounds__(KGB_PT + 32 * KGB_PLW, 1) KGB_KERNEL_NAME_P(const __grid_constant__ KgbParams p) {
+extern "C" __global__ void __launch_bounds__(KGB_PT + 32 * KGB_PLW, KGB_PMINB) KGB_KERNEL_NAME_P(const __grid_constant__ KgbParams p) {
     KGB_SCALARS
     extern __shared__ __align__(128) unsigned char kgb_dyn_smem[];
     unsigned char* stages = kgb_dyn_smem;
@@ -744,7 +782,14 @@ extern "C" __global__ void __launch_bounds__(KGB_PT + 32 * KGB_PLW, 1) KGB_KERNE
     }
 
     // ==================================================================== compute warps (tid < KGB_PT)
+#if KGB_MODE == 2
     KGB_OUT_T* __restrict__ out = (KGB_OUT_T*)p.out;
+#else
+    // mode 3: the epilogue g(scan value, args[i]) is folded into one accumulator per thread across all of the
+    // CTA's tiles; one partial per CTA at the end (max/min/int folds are order-independent; a float sum here is
+    // already association-dependent through the look-back window, like the scan itself)
+    KGB_ACC2_T r2 = (KGB_ACC2_T)(KGB_RED2_IDENT);
+#endif
 
     // stream one tile into its stage: 8 x 16-byte cp.async per thread, stripe-wise (coalesced)
     auto issue_load = [&](u32 li) {
@@ -754,18 +799,18 @@ extern "C" __global__ void __launch_bounds__(KGB_PT + 32 * KGB_PLW, 1) KGB_KERNE
             const i64 base = (i64)t * KGB_PTILE;
             if (base + KGB_PTILE <= n) {
 #pragma unroll
-                for (int h = 0; h < 8; h++) {
+                for (int h = 0; h < KGB_PCT; h++) {
                     const int cf = h * KGB_PT + tid;
-                    kgb_cp_async16(sb + kgb_swz(cf >> 3, cf & 7), src + base + cf * 2);
+                    kgb_cp_async16(sb + kgb_swz(cf / KGB_PCR, cf % KGB_PCR), src + base + cf * 2);
                 }
             } else {  // the last, partial tile: guarded element loads (zero-filled beyond n, masked in phase A)
 #pragma unroll
-                for (int h = 0; h < 8; h++) {
+                for (int h = 0; h < KGB_PCT; h++) {
                     const int cf = h * KGB_PT + tid;
                     KGB_PIPE_T v0 = 0, v1 = 0;
                     if (base + cf * 2 < n) v0 = src[base + cf * 2];
                     if (base + cf * 2 + 1 < n) v1 = src[base + cf * 2 + 1];
-                    KGB_PIPE_T* d = reinterpret_cast<KGB_PIPE_T*>(sb + kgb_swz(cf >> 3, cf & 7));
+                    KGB_PIPE_T* d = reinterpret_cast<KGB_PIPE_T*>(sb + kgb_swz(cf / KGB_PCR, cf % KGB_PCR));
                     d[0] = v0;
                     d[1] = v1;
                 }
@@ -782,11 +827,12 @@ extern "C" __global__ void __launch_bounds__(KGB_PT + 32 * KGB_PLW, 1) KGB_KERNE
         const unsigned char* sb = stages + (size_t)s * KGB_PSTAGE_BYTES;
         const i64 base = (i64)t * KGB_PTILE;
         const bool full = (base + KGB_PTILE <= n);
+#if KGB_MODE == 2
 #pragma unroll
-        for (int h = 0; h < 8; h++) {
+        for (int h = 0; h < KGB_PCT; h++) {
             const int cf = h * KGB_PT + tid;
             KGB_ACC_T v[2];
-            *reinterpret_cast<uint4*>(v) = *reinterpret_cast<const uint4*>(sb + kgb_swz(cf >> 3, cf & 7));
+            *reinterpret_cast<uint4*>(v) = *reinterpret_cast<const uint4*>(sb + kgb_swz(cf / KGB_PCR, cf % KGB_PCR));
             KGB_OUT_T o[2];
             o[0] = (KGB_OUT_T)(KGB_RED(excl, v[0]));
             o[1] = (KGB_OUT_T)(KGB_RED(excl, v[1]));
@@ -797,6 +843,42 @@ extern "C" __global__ void __launch_bounds__(KGB_PT + 32 * KGB_PLW, 1) KGB_KERNE
                 if (base + cf * 2 + 1 < n) out[base + cf * 2 + 1] = o[1];
             }
         }
+#else
+        // arguments re-read stripe-wise from global memory (L2: the tile streamed through a few microseconds ago)
+        if (full) {
+            KGB_DECL_REGS(2 * KGB_PCT)
+#pragma unroll
+            for (int h = 0; h < KGB_PCT; h++) {
+                const int cf = h * KGB_PT + tid;
+                KGB_LOAD_VEC(2, h * 2, base + cf * 2)
+            }
+#pragma unroll
+            for (int h = 0; h < KGB_PCT; h++) {
+                const int cf = h * KGB_PT + tid;
+                KGB_ACC_T v[2];
+                *reinterpret_cast<uint4*>(v) = *reinterpret_cast<const uint4*>(sb + kgb_swz(cf / KGB_PCR, cf % KGB_PCR));
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    KGB_ACC2_T e2 = (KGB_ACC2_T)(KGB_EVAL2(h * 2 + j, KGB_RED(excl, v[j])));
+                    r2 = KGB_RED2(r2, e2);
+                }
+            }
+        } else {
+            for (int h = 0; h < KGB_PCT; h++) {
+                const int cf = h * KGB_PT + tid;
+                KGB_ACC_T v[2];
+                *reinterpret_cast<uint4*>(v) = *reinterpret_cast<const uint4*>(sb + kgb_swz(cf / KGB_PCR, cf % KGB_PCR));
+                for (int j = 0; j < 2; j++) {
+                    if (base + cf * 2 + j < n) {
+                        KGB_DECL_REGS(1)
+                        KGB_LOAD_VEC(1, 0, base + cf * 2 + j)
+                        KGB_ACC2_T e2 = (KGB_ACC2_T)(KGB_EVAL2(0, KGB_RED(excl, v[j])));
+                        r2 = KGB_RED2(r2, e2);
+                    }
+                }
+            }
+        }
+#endif
     };
 
 #pragma unroll
@@ -827,7 +909,7 @@ extern "C" __global__ void __launch_bounds__(KGB_PT + 32 * KGB_PLW, 1) KGB_KERNE
         {
             KGB_DECL_REGS(KGB_PITEMS)
 #pragma unroll
-            for (int q = 0; q < 8; q++)
+            for (int q = 0; q < KGB_PCR; q++)
                 *reinterpret_cast<uint4*>(&KGB_PIPE_ARG[q * 2]) = *reinterpret_cast<const uint4*>(sb + kgb_swz(tid, q));
 #pragma unroll
             for (int k = 0; k < KGB_PITEMS; k++) {
@@ -868,7 +950,7 @@ extern "C" __global__ void __launch_bounds__(KGB_PT + 32 * KGB_PLW, 1) KGB_KERNE
 #pragma unroll
         for (int k = 0; k < KGB_PITEMS; k++) x[k] = KGB_RED(thread_excl, x[k]);
 #pragma unroll
-        for (int q = 0; q < 8; q++)
+        for (int q = 0; q < KGB_PCR; q++)
             *reinterpret_cast<uint4*>(sb + kgb_swz(tid, q)) = *reinterpret_cast<uint4*>(&x[q * 2]);
         // the row-wise write-back must be visible to the stripe-wise readers of phase B: the barrier at the top of
         // a later iteration orders it (phase B of this tile runs D >= 1 iterations from now)
@@ -894,5 +976,43 @@ extern "C" __global__ void __launch_bounds__(KGB_PT + 32 * KGB_PLW, 1) KGB_KERNE
             kgb_mbar_arrive(&ctl.agg_bar[s]);
         }
     }
+#if KGB_MODE == 3
+    // one partial per CTA -> the last CTA to finish folds them in CTA order
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        KGB_ACC2_T o = kgb_shfl_xor<KGB_ACC2_T>(r2, m);
+        r2 = KGB_RED2(r2, o);
+    }
+    if (lane == 0) ctl.sh2[warp] = r2;
+    kgb_bar_compute();
+    if (warp == 0) {
+        KGB_ACC2_T* part2 = (KGB_ACC2_T*)(states + ntiles);
+        u32* done = ticket + 1;
+        u32 last = 0;
+        if (lane == 0) {
+            KGB_ACC2_T a = ctl.sh2[0];
+#pragma unroll
+            for (int w = 1; w < KGB_PT / 32; w++) a = KGB_RED2(a, ctl.sh2[w]);
+            ((volatile KGB_ACC2_T*)part2)[blockIdx.x] = a;
+            __threadfence();
+            last = (atomicAdd(done, 1u) == gridDim.x - 1) ? 1u : 0u;
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {
+            __threadfence();
+            KGB_ACC2_T a = (KGB_ACC2_T)(KGB_RED2_IDENT);
+            for (u32 b = lane; b < gridDim.x; b += 32) {
+                KGB_ACC2_T o = ((volatile KGB_ACC2_T*)part2)[b];
+                a = KGB_RED2(a, o);
+            }
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) {
+                KGB_ACC2_T o = kgb_shfl_xor<KGB_ACC2_T>(a, m);
+                a = KGB_RED2(a, o);
+            }
+            if (lane == 0) *(KGB_OUT_T*)p.out = (KGB_OUT_T)a;
+        }
+    }
+#endif
 }
 #endif

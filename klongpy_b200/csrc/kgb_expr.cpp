@@ -457,6 +457,8 @@ struct kgb_expr {
     int pipe_arg = -1;              // >= 0: the persistent pipelined scan kernel exists (index of its one array argument)
     std::string name_p;
     CUfunction fn_p = nullptr;
+    int pipe_threads = 256, pipe_stages = 7, pipe_load = 2, pipe_park = 4, pipe_lw = 4;
+    int pipe_ctas_per_sm = 1;
 };
 
 namespace kgb {
@@ -490,10 +492,20 @@ static void scan_geometry(kgb_expr* h) {
     }
 }
 
-// persistent pipelined scan (jit_skeleton.cuh KGB_PIPE): 7 stages of 4096 x 8 B + control block, 256 + 4*32 threads
-static const size_t kPipeSmem = 7 * 32768 + 512;
+// persistent pipelined scan (jit_skeleton.cuh KGB_PIPE): `stages` x 32 KB + control block; compute threads + look-back warps
 static const long long kPipeTile = 4096;
-static const unsigned kPipeThreads = 256 + 4 * 32;
+static size_t pipe_smem(const kgb_expr* h) { return (size_t)h->pipe_stages * 32768 + 1024; }
+static unsigned pipe_block(const kgb_expr* h) { return (unsigned)(h->pipe_threads + 32 * h->pipe_lw); }
+// Geometry: KGB200_PIPE="threads,stages,load,park,lookback_warps,ctas_per_sm" overrides the default for tuning.
+static void pipe_geometry(kgb_expr* h) {
+    if (const char* e = getenv("KGB200_PIPE")) {
+        int t, s, l, d, w, c;
+        if (sscanf(e, "%d,%d,%d,%d,%d,%d", &t, &s, &l, &d, &w, &c) == 6 && (t == 256 || t == 512) && s >= l + d + 1 && s <= 7 &&
+            l >= 1 && d >= 1 && w >= 1 && w <= 8 && c >= 1 && c <= 2) {
+            h->pipe_threads = t, h->pipe_stages = s, h->pipe_load = l, h->pipe_park = d, h->pipe_lw = w, h->pipe_ctas_per_sm = c;
+        }
+    }
+}
 
 // dynamic shared memory of a scan tile: KGB_SBLOCK * (KGB_ITEMS + 16 B pad) accumulators (jit_skeleton.cuh)
 static size_t scan_smem_bytes(const kgb_expr* h) {
@@ -569,7 +581,8 @@ static int build_source(kgb_expr* h, const int32_t* code, int n_code, const int3
         if (vc.s.find("[(j)]") != std::string::npos) return set_error("scan seed program must not read arrays"), KGB_EINVAL;
         m << "#define KGB_HAS_CARRY 1\n#define KGB_CARRY (" << cast(vc, h->acc_dtype) << ")\n";
     }
-    if (h->mode == KGB_MODE_SCAN && dtype_size(h->acc_dtype) == 8 && dtype_size(h->out_dtype) == 8 && !getenv("KGB200_NO_PIPE")) {
+    if ((h->mode == KGB_MODE_SCAN || h->mode == KGB_MODE_SCANRED) && dtype_size(h->acc_dtype) == 8 &&
+        (h->mode == KGB_MODE_SCANRED || dtype_size(h->out_dtype) == 8) && !getenv("KGB200_NO_PIPE")) {
         // persistent pipelined variant (jit_skeleton.cuh, KGB_PIPE): exactly one array argument, 8-byte elements
         int n_arr = 0, idx = -1;
         for (size_t i = 0; i < h->args.size(); i++)
@@ -579,6 +592,9 @@ static int build_source(kgb_expr* h, const int32_t* code, int n_code, const int3
             }
         if (n_arr == 1 && dtype_size(h->args[idx].dtype) == 8) {
             h->pipe_arg = idx;
+            pipe_geometry(h);
+            m << "#define KGB_PT " << h->pipe_threads << "\n#define KGB_PS " << h->pipe_stages << "\n#define KGB_PP " << h->pipe_load
+              << "\n#define KGB_PD " << h->pipe_park << "\n#define KGB_PLW " << h->pipe_lw << "\n#define KGB_PMINB " << h->pipe_ctas_per_sm << "\n";
             m << "#define KGB_PIPE 1\n#define KGB_PIPE_T " << ctype(h->args[idx].dtype) << "\n#define KGB_PIPE_ARG a" << idx
               << "\n#define KGB_PIPE_PTR p.ptr[" << idx << "]\n";
         }
@@ -649,8 +665,8 @@ static int jit_compile(kgb_expr* h, bool load) {
     if (h->pipe_arg >= 0) {
         cr = d.ModuleGetFunction(&h->fn_p, h->module, h->name_p.c_str());
         if (cr != CUDA_SUCCESS) return set_error("cuModuleGetFunction(%s): %s", h->name_p.c_str(), cu_err(cr)), KGB_ECUDA;
-        cr = d.FuncSetAttribute(h->fn_p, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)kPipeSmem);
-        if (cr != CUDA_SUCCESS) return set_error("cuFuncSetAttribute(%s, %zu B): %s", h->name_p.c_str(), kPipeSmem, cu_err(cr)), KGB_ECUDA;
+        cr = d.FuncSetAttribute(h->fn_p, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)pipe_smem(h));
+        if (cr != CUDA_SUCCESS) return set_error("cuFuncSetAttribute(%s, %zu B): %s", h->name_p.c_str(), pipe_smem(h), cu_err(cr)), KGB_ECUDA;
     }
     const bool is_scan = h->mode == KGB_MODE_SCAN || h->mode == KGB_MODE_SCANRED;
     const size_t dyn = is_scan ? scan_smem_bytes(h) : 0;
@@ -818,12 +834,12 @@ extern "C" int kgb_expr_launch(kgb_expr* h, const void* const* args, int64_t n, 
         const size_t ptiles = (size_t)((n + kPipeTile - 1) / kPipeTile);
         // the persistent variant pays a pipeline fill per CTA: worth it once every SM has a few tiles
         use_pipe = h->fn_p && aligned && ptiles >= (size_t)sm_count() * 4;
-        if (use_pipe) grid = (unsigned)std::min<size_t>(ptiles, (size_t)sm_count());
+        if (use_pipe) grid = (unsigned)std::min<size_t>(ptiles, (size_t)sm_count() * h->pipe_ctas_per_sm);
         KGB_CUDA_CHECK(cudaMemsetAsync(workspace, 0, 64 + std::max(tiles, ptiles) * 16, st));
     }
     if (use_pipe) {
         void* pp[] = {&P};
-        CUresult pr = driver().LaunchKernel(h->fn_p, grid, 1, 1, kPipeThreads, 1, 1, (unsigned)kPipeSmem, (CUstream)stream, pp, nullptr);
+        CUresult pr = driver().LaunchKernel(h->fn_p, grid, 1, 1, pipe_block(h), 1, 1, (unsigned)pipe_smem(h), (CUstream)stream, pp, nullptr);
         if (pr != CUDA_SUCCESS) return set_error("cuLaunchKernel(%s): %s", h->name_p.c_str(), cu_err(pr)), KGB_ECUDA;
         return KGB_OK;
     }

@@ -89,17 +89,21 @@ __global__ void __launch_bounds__(256) groupagg_kernel(const i64* __restrict__ k
 //                 rows that pass the filter — O(log rows) per station per CTA on unordered data
 //   sum           RED.ADD.F64 on the global table (shared-memory f64 add is a CAS loop, ATOMS.CAST.SPIN)
 // One persistent CTA per SM, 12 B of shared memory per station.
-template <int COUNT_IN_SMEM>
+template <int VARIANT>
 __global__ void __launch_bounds__(1024, 1) groupagg_kernel_v2(const i64* __restrict__ keys, const double* __restrict__ vals,
                                                               i64 n, i64 G, AggWs a) {
     extern __shared__ __align__(16) unsigned char agg_smem[];
-    u32* s_cnt = reinterpret_cast<u32*>(agg_smem);
+    constexpr bool COUNT_IN_SMEM = VARIANT == 1 || VARIANT == 3;
+    constexpr bool SUM_IN_SMEM = VARIANT == 3;
+    double* s_sum = reinterpret_cast<double*>(agg_smem);  // VARIANT 3 only (G doubles first, keeps 8-byte alignment)
+    u32* s_cnt = reinterpret_cast<u32*>(agg_smem + (SUM_IN_SMEM ? (size_t)G * 8 : 0));
     u32* s_minhi = s_cnt + G;
     u32* s_maxhi = s_minhi + G;
     for (i64 i = threadIdx.x; i < G; i += blockDim.x) {
         s_cnt[i] = 0u;
         s_minhi[i] = 0xffffffffu;
         s_maxhi[i] = 0u;
+        if (SUM_IN_SMEM) s_sum[i] = 0.0;
     }
     __syncthreads();
     auto row = [&](i64 k, double v) {
@@ -117,7 +121,10 @@ __global__ void __launch_bounds__(1024, 1) groupagg_kernel_v2(const i64* __restr
             if (hi > s_maxhi[k]) atomicMax(&s_maxhi[k], hi);
             if (emax > ld_relaxed_u64(&a.tmax[k])) atomicMax(&a.tmax[k], emax);
         }
-        atomicAdd(&a.tsum[k], v);
+        if (SUM_IN_SMEM)
+            atomicAdd(&s_sum[k], v);  // ATOMS.CAST.SPIN.64: a CAS loop, but on the SM's own atomic unit
+        else
+            atomicAdd(&a.tsum[k], v);
         if (COUNT_IN_SMEM)
             atomicAdd(&s_cnt[k], 1u);
         else
@@ -157,7 +164,10 @@ __global__ void __launch_bounds__(1024, 1) groupagg_kernel_v2(const i64* __restr
         __syncthreads();
         for (i64 i = threadIdx.x; i < G; i += blockDim.x) {
             const u32 c = s_cnt[i];
-            if (c) atomicAdd(&a.tcnt[i], (u64)c);
+            if (c) {
+                atomicAdd(&a.tcnt[i], (u64)c);
+                if (SUM_IN_SMEM) atomicAdd(&a.tsum[i], s_sum[i]);
+            }
         }
     }
 }
@@ -231,32 +241,36 @@ extern "C" int kgb_groupagg_f64(const int64_t* keys, const double* vals, int64_t
         const long long cap = (long long)sm_count() * 8;
         if (blocks > cap) blocks = cap;
         if (blocks < 1) blocks = 1;
-        // variant: 1 = shared-memory filters + shared count (default when the table fits), 2 = filters only,
-        // 0 = v1 (all four updates on the global table).  KGB200_AGG_VARIANT overrides for measurements.
-        int variant = 1;
+        // variant: 3 = everything in shared memory (default when 20 B/station fit), 1 = filters + count in shared
+        // memory and RED.ADD.F64 sums on the global table, 2 = filters only, 0 = v1 (all four updates on the
+        // global table).  KGB200_AGG_VARIANT overrides for measurements.
+        int variant = 3;
         if (const char* e = getenv("KGB200_AGG_VARIANT")) variant = atoi(e);
-        const size_t smem = (size_t)n_groups * 12;
-        if (smem > 200 * 1024) variant = 0;
+        if (variant < 0 || variant > 3) variant = 3;
+        const size_t limit = 200 * 1024;
+        if (variant == 3 && (size_t)n_groups * 20 > limit) variant = 1;
+        if (variant != 0 && (size_t)n_groups * 12 > limit) variant = 0;
         if (variant == 0) {
             groupagg_kernel<<<(unsigned)blocks, 256, 0, st>>>((const i64*)keys, vals, n, n_groups, a);
         } else {
-            static bool attr_set[64][2] = {{false}};
+            const size_t smem = (size_t)n_groups * (variant == 3 ? 20 : 12);
+            static bool attr_set[64] = {false};
             const int dev = current_device();
-            const int vi = variant == 1 ? 1 : 0;
-            if (!attr_set[dev][vi]) {
-                if (vi)
-                    KGB_CUDA_CHECK(cudaFuncSetAttribute(groupagg_kernel_v2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                else
-                    KGB_CUDA_CHECK(cudaFuncSetAttribute(groupagg_kernel_v2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                attr_set[dev][vi] = true;
+            if (!attr_set[dev]) {
+                KGB_CUDA_CHECK(cudaFuncSetAttribute(groupagg_kernel_v2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
+                KGB_CUDA_CHECK(cudaFuncSetAttribute(groupagg_kernel_v2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
+                KGB_CUDA_CHECK(cudaFuncSetAttribute(groupagg_kernel_v2<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
+                attr_set[dev] = true;
             }
             long long pb = (n / 2 + 1024 * 4 - 1) / (1024 * 4);
             if (pb > sm_count()) pb = sm_count();
             if (pb < 1) pb = 1;
-            if (vi)
+            if (variant == 1)
                 groupagg_kernel_v2<1><<<(unsigned)pb, 1024, smem, st>>>((const i64*)keys, vals, n, n_groups, a);
+            else if (variant == 2)
+                groupagg_kernel_v2<2><<<(unsigned)pb, 1024, smem, st>>>((const i64*)keys, vals, n, n_groups, a);
             else
-                groupagg_kernel_v2<0><<<(unsigned)pb, 1024, smem, st>>>((const i64*)keys, vals, n, n_groups, a);
+                groupagg_kernel_v2<3><<<(unsigned)pb, 1024, smem, st>>>((const i64*)keys, vals, n, n_groups, a);
         }
     }
     groupagg_finalize<<<(unsigned)((n_groups + 255) / 256), 256, 0, st>>>(a, n_groups, min_out, max_out, sum_out,

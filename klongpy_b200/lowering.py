@@ -203,8 +203,6 @@ def make_callable(ir):
                 any_dev = True
                 if v._t.dim() > 1:
                     raise NotImplementedError("compiled kernels take 1-d arrays; N-d goes through the eager verbs")
-                if v._t.requires_grad:
-                    raise NotImplementedError("autograd operands take the eager (differentiable) path")
             elif type(v) in (int, float) or isinstance(v, (np.integer, np.floating)):
                 pass
             else:

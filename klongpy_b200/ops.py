@@ -152,6 +152,9 @@ def _classify(x, device):
 
 def run(code, args, mode=_lib.MODE_MAP, red=0, code2=None, red2=0, out_shape=None, device=None):
     """Compile (cached) and launch one expression program.  Returns a DeviceArray."""
+    if torch.is_grad_enabled() and any(isinstance(a, DeviceArray) and a._t.requires_grad for a in args):
+        from . import autograd  # operands on the autograd tape: same launch, recorded as one node
+        return autograd.run_differentiable(code, args, mode, red, code2, red2, out_shape, device)
     shape = None
     for a in args:
         if isinstance(a, DeviceArray):
@@ -508,6 +511,9 @@ def iota(n, device=None, start=0, step=1):
 
 def gather(a, idx):
     """`a@b` for an integer index list (dyads.py:176-181)."""
+    if torch.is_grad_enabled() and a._t.requires_grad:
+        # autograd interop only: the backward of a gather is a scatter-add torch already knows
+        return DeviceArray(a._t[idx._t.to(torch.int64)])
     a = contiguous(a)
     idx = contiguous(idx)
     dev = a._t.device

@@ -44,12 +44,23 @@ for m in (n - 1, n - 4097, 4096 * 148 * 4 + 5):  # ragged tails through the same
 mx = ops.scan("max", x)
 assert torch.equal(mx._t, torch.cummax(x._t, 0).values), "running max mismatch"
 del mx
+SR = dict(mode=_lib.MODE_SCANRED, red=_lib.RED_MAX, code2=[4, OP_ARG, 0, OPC["sub"]], red2=_lib.RED_MAX)
+for m in (n, n - 4097, 4096 * 148 * 4 + 5, 100_003):
+    xs = ops.asarray(x._t[:m])
+    got = ops.run([OP_ARG, 0], [xs], **SR).item()
+    ref = (torch.cummax(xs._t, 0).values - xs._t).max().item()
+    assert got == ref, f"max-drawdown mismatch at n={m}: {got} vs {ref}"
+    got = ops.run([OP_ARG, 0], [xs], mode=_lib.MODE_SCANRED, red=_lib.RED_ADD, code2=[4, OP_ARG, 0, OPC["mul"]], red2=_lib.RED_ADD).item()
+    ref = (torch.cumsum(xs._t[: min(m, 1 << 20)], 0) * xs._t[: min(m, 1 << 20)]).sum().item() if m <= (1 << 20) else None
+    if ref is not None:
+        assert abs(got - ref) <= 1e-12 * abs(ref), f"sum(cumsum*x) mismatch at n={m}: {got} vs {ref}"
+    del xs
 ms = timeit(lambda: ops.scan("add", x))
 ms2 = timeit(lambda: ops.run([OP_ARG, 0], [x], mode=_lib.MODE_SCANRED, red=_lib.RED_MAX, code2=[4, OP_ARG, 0, OPC["sub"]],
                              red2=_lib.RED_MAX))
 xi = ops.asarray(torch.randint(-1000, 1000, (n,), dtype=torch.int64, device=dev))
 ms3 = timeit(lambda: ops.scan("add", xi))
-print(f"block={os.environ.get('KGB200_SCAN_BLOCK', 'dflt')} bytes/thr={os.environ.get('KGB200_SCAN_ITEMS', 'dflt')} n={n}: "
+print(f"pipe={os.environ.get('KGB200_PIPE', 'dflt')} nopipe={os.environ.get('KGB200_NO_PIPE', '0')} n={n}: "
       f"scan f64 {ms:.3f} ms {16 * n / ms / 1e6:.0f} GB/s frac {16 * n / ms / 1e6 / peak:.3f} | "
       f"scanred {ms2:.3f} ms {8 * n / ms2 / 1e6:.0f} GB/s frac {8 * n / ms2 / 1e6 / peak:.3f} | "
       f"scan i64 {ms3:.3f} ms frac {16 * n / ms3 / 1e6 / peak:.3f}", flush=True)
