@@ -1,27 +1,81 @@
-// Single-pass stream compaction (decoupled look-back on the running count), shared by find / where /
-// group-boundaries / unique.  Tile = 16 warps x 16 rows x 32 lanes = 8192 elements (64 KB of 8-byte input):
-// the chained look-back advances about (32-tile window / state round trip) tiles per unit time, so a tile must
-// carry enough bytes for that rate to exceed HBM bandwidth (4096-element tiles measured 16 % of roofline).
-// Each warp ballots its rows so every lane knows the whole warp's masks without shuffles.
+// Stream compaction for find / where / group boundaries / unique, in two kernels with a bitmask in between:
+//
+//   select_mask_kernel   : pure streaming pass over the input (no inter-CTA dependency at all).  A warp takes 32
+//                          rows of 32 elements, every lane issues its 32 loads before the first test, each row is
+//                          balloted, and lane r keeps row r's mask — so a warp leaves ONE coalesced 128-byte store
+//                          per 1024 elements.  Traffic: the input once + n/8 bytes.
+//   select_compact_kernel: turns the mask words into ascending positions: per-thread popcounts, block scan,
+//                          decoupled look-back over tiles of 65536 elements (2048 words), then every thread
+//                          expands its own words.  It reads n/8 bytes and writes 8 bytes per hit.
+//
+// History: a single-pass kernel with the look-back in the streaming loop measured 0.16 -> 0.33 of
+// the HBM roofline and no better when made persistent with prefetch (0.27): with ~150 tiles in flight in lock-step
+// every look-back walks 2-5 dependent L2 round trips while the CTA's other warps idle (60 % of the samples at that
+// barrier, ncu r01h).  Moving the dependency chain onto the 64x smaller mask stream takes it off the critical path.
 #pragma once
 #include "kgb_device.cuh"
 #include "kgb_internal.h"
 
 namespace kgb {
 
-constexpr int SEL_THREADS = 512;
-constexpr int SEL_ROWS = 16;
-constexpr int SEL_TILE = SEL_THREADS * SEL_ROWS;
+constexpr int SEL_MASK_THREADS = 256;             // 8 warps; a warp step covers 32 x 32 = 1024 elements
+constexpr int SEL_WARP_ELEMS = 1024;
+constexpr int SEL_THREADS = 512;                  // compaction kernel
+constexpr int SEL_WPT = 4;                        // mask words per thread
+constexpr int SEL_TILE_WORDS = SEL_THREADS * SEL_WPT;
+constexpr i64 SEL_TILE = (i64)SEL_TILE_WORDS * 32;  // elements per compaction tile
 
-inline size_t select_ws_bytes(i64 n) {
-    const size_t tiles = (size_t)((n + SEL_TILE - 1) / SEL_TILE);
-    return 64 + align_up(tiles * 8, 64);
+inline size_t select_mask_words(i64 n) { return (size_t)((n + SEL_WARP_ELEMS - 1) / SEL_WARP_ELEMS) * 32; }
+inline size_t select_tiles(i64 n) { return (select_mask_words(n) + SEL_TILE_WORDS - 1) / SEL_TILE_WORDS; }
+// ws: [0,4) ticket | [64, ...) u64 look-back state per tile (both zero on entry) | mask words
+inline size_t select_state_bytes(i64 n) { return 64 + align_up(select_tiles(n) * 8, 64); }
+inline size_t select_ws_bytes(i64 n) { return select_state_bytes(n) + align_up(select_mask_words(n) * 4, 64); }
+
+template <typename Pred>
+__global__ void __launch_bounds__(SEL_MASK_THREADS) select_mask_kernel(Pred pred, i64 n, u32* __restrict__ masks) {
+    const int lane = threadIdx.x & 31;
+    const i64 nsteps = (n + SEL_WARP_ELEMS - 1) / SEL_WARP_ELEMS;
+    const i64 wstride = (i64)gridDim.x * (SEL_MASK_THREADS / 32);
+    for (i64 step = (i64)blockIdx.x * (SEL_MASK_THREADS / 32) + (threadIdx.x >> 5); step < nsteps; step += wstride) {
+        const i64 wbase = step * SEL_WARP_ELEMS;
+        // all of a thread's loads are issued before the first test: a fused load+compare per row lets the compiler
+        // recycle one destination register, which serialises the loads (measured: 16 % of HBM roofline)
+        typename Pred::V val[32];
+#pragma unroll
+        for (int r = 0; r < 32; r++) {
+            const i64 i = wbase + r * 32 + lane;
+            val[r] = pred.load(i < n ? i : (n - 1));
+        }
+        u32 mine = 0;
+        if (Pred::NEEDS_PREV) {
+            // element i-1 comes from the neighbouring lane (or the previous row's lane 31); only lane 0 of row 0
+            // loads it — one extra load per 1024 elements instead of a second value per element
+            typename Pred::V prev0 = val[0];
+            if (lane == 0 && wbase > 0) prev0 = pred.load(wbase - 1);
+#pragma unroll
+            for (int r = 0; r < 32; r++) {
+                const i64 i = wbase + r * 32 + lane;
+                typename Pred::V up = __shfl_up_sync(0xffffffffu, val[r], 1);
+                typename Pred::V last = __shfl_sync(0xffffffffu, val[r > 0 ? r - 1 : 0], 31);
+                const typename Pred::V prev = lane > 0 ? up : (r > 0 ? last : prev0);
+                const u32 m = __ballot_sync(0xffffffffu, (i < n) && pred.test2(i, val[r], prev));
+                if (lane == r) mine = m;
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 32; r++) {
+                const i64 i = wbase + r * 32 + lane;
+                const u32 m = __ballot_sync(0xffffffffu, (i < n) && pred.test(i, val[r]));
+                if (lane == r) mine = m;
+            }
+        }
+        masks[step * 32 + lane] = mine;
+    }
 }
 
-// ws: [0,4) ticket | [64, ...) u64 state per tile — all zero on entry.
-template <typename Pred>
-__global__ void __launch_bounds__(SEL_THREADS) select_kernel(Pred pred, i64 n, i64* __restrict__ pos_out,
-                                                              i64* __restrict__ count_out, void* ws) {
+__global__ void __launch_bounds__(SEL_THREADS) select_compact_kernel(const u32* __restrict__ masks, i64 nwords,
+                                                                      i64* __restrict__ pos_out,
+                                                                      i64* __restrict__ count_out, void* ws) {
     __shared__ u32 s_tile;
     __shared__ u32 s_wcnt[SEL_THREADS / 32];
     __shared__ u64 s_base;
@@ -31,31 +85,26 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(Pred pred, i64 n, i
     if (tid == 0) s_tile = atomicAdd(ticket, 1u);
     __syncthreads();
     const i64 tile = s_tile;
-    const i64 ntiles = (n + SEL_TILE - 1) / SEL_TILE;
-    const i64 wbase = tile * SEL_TILE + (i64)warp * (SEL_ROWS * 32);
-
-    // all of a thread's loads are issued before the first test: a fused load+compare per row lets the compiler
-    // recycle one destination register, which serialises the loads (measured: 16 % of HBM roofline)
-    typename Pred::V val[SEL_ROWS];
+    const i64 ntiles = (nwords + SEL_TILE_WORDS - 1) / SEL_TILE_WORDS;
+    const i64 w0 = tile * SEL_TILE_WORDS + (i64)tid * SEL_WPT;
+    u32 m[SEL_WPT];
+    if (w0 + SEL_WPT <= nwords) {
+        const uint4 q = *reinterpret_cast<const uint4*>(masks + w0);  // nwords is a multiple of 32, w0 of 4
+        m[0] = q.x, m[1] = q.y, m[2] = q.z, m[3] = q.w;
+    } else {
 #pragma unroll
-    for (int r = 0; r < SEL_ROWS; r++) {
-        const i64 i = wbase + r * 32 + lane;
-        val[r] = pred.load(i < n ? i : (n - 1));
+        for (int j = 0; j < SEL_WPT; j++) m[j] = (w0 + j < nwords) ? masks[w0 + j] : 0u;
     }
-    bool hit[SEL_ROWS];
+    u32 cnt = 0;
 #pragma unroll
-    for (int r = 0; r < SEL_ROWS; r++) {
-        const i64 i = wbase + r * 32 + lane;
-        hit[r] = (i < n) && pred.test(i, val[r]);
-    }
-    u32 masks[SEL_ROWS];
-    u32 wtotal = 0;
+    for (int j = 0; j < SEL_WPT; j++) cnt += __popc(m[j]);
+    u32 inc = cnt;
 #pragma unroll
-    for (int r = 0; r < SEL_ROWS; r++) {
-        masks[r] = __ballot_sync(0xffffffffu, hit[r]);
-        wtotal += __popc(masks[r]);
+    for (int d = 1; d < 32; d <<= 1) {
+        const u32 v = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += v;
     }
-    if (lane == 0) s_wcnt[warp] = wtotal;
+    if (lane == 31) s_wcnt[warp] = inc;
     __syncthreads();
     u32 woff = 0, ttotal = 0;
 #pragma unroll
@@ -65,8 +114,7 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(Pred pred, i64 n, i
         ttotal += c;
     }
     if (warp == 0) {
-        if (lane == 0)
-            st_relaxed_u64(&states[tile], lb_pack(tile == 0 ? KGB_LB_PREFIX : KGB_LB_AGG, 1, ttotal));
+        if (lane == 0) st_relaxed_u64(&states[tile], lb_pack(tile == 0 ? KGB_LB_PREFIX : KGB_LB_AGG, 1, ttotal));
         u64 excl = 0;
         if (tile > 0) {
             excl = lb_warp_lookback(states, tile, 1);
@@ -77,47 +125,64 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(Pred pred, i64 n, i
             if (tile == ntiles - 1) *count_out = (i64)(excl + ttotal);
         }
     }
+    if (ttotal == 0) return;  // nothing to write (uniform across the CTA)
     __syncthreads();
-    u64 o = s_base + woff;
-    const u32 lt = (1u << lane) - 1u;
+    u64 o = s_base + woff + (inc - cnt);
 #pragma unroll
-    for (int r = 0; r < SEL_ROWS; r++) {
-        if (hit[r]) pos_out[o + __popc(masks[r] & lt)] = wbase + r * 32 + lane;
-        o += __popc(masks[r]);
+    for (int j = 0; j < SEL_WPT; j++) {
+        u32 mm = m[j];
+        const i64 ebase = (w0 + j) * 32;
+        while (mm) {
+            const int b = __ffs(mm) - 1;
+            pos_out[o++] = ebase + b;
+            mm &= mm - 1;
+        }
     }
 }
 
 template <typename T> struct NonzeroPred {
     typedef T V;
+    static constexpr bool NEEDS_PREV = false;
     const T* a;
     __device__ __forceinline__ V load(i64 i) const { return __ldcs(&a[i]); }
     __device__ __forceinline__ bool test(i64, V v) const { return v != T(0); }
+    __device__ __forceinline__ bool test2(i64, V, V) const { return false; }
 };
 template <typename T> struct EqualPred {
     typedef T V;
+    static constexpr bool NEEDS_PREV = false;
     const T* a;
     T needle;
     __device__ __forceinline__ V load(i64 i) const { return __ldcs(&a[i]); }
     __device__ __forceinline__ bool test(i64, V v) const { return v == needle; }
+    __device__ __forceinline__ bool test2(i64, V, V) const { return false; }
 };
-// run heads of a sorted, order-encoded key array
+// run heads of a sorted, order-encoded key array: k[i] != k[i-1]
 struct BoundaryPred {
-    typedef ulonglong2 V;
+    typedef u64 V;
+    static constexpr bool NEEDS_PREV = true;
     const u64* k;
-    __device__ __forceinline__ V load(i64 i) const { return make_ulonglong2(k[i], k[i > 0 ? i - 1 : 0]); }
-    __device__ __forceinline__ bool test(i64 i, V v) const { return i == 0 || v.x != v.y; }
+    __device__ __forceinline__ V load(i64 i) const { return k[i]; }
+    __device__ __forceinline__ bool test(i64, V) const { return false; }
+    __device__ __forceinline__ bool test2(i64 i, V v, V prev) const { return i == 0 || v != prev; }
 };
 
 template <typename Pred>
 inline int launch_select(Pred pred, i64 n, i64* pos_out, i64* count_out, void* ws, size_t ws_bytes, cudaStream_t st) {
     KGB_REQUIRE(ws && ws_bytes >= select_ws_bytes(n), "select: workspace too small");
-    const size_t tiles = (size_t)((n + SEL_TILE - 1) / SEL_TILE);
-    KGB_CUDA_CHECK(cudaMemsetAsync(ws, 0, select_ws_bytes(n), st));
-    if (tiles == 0) {
+    if (n == 0) {
         KGB_CUDA_CHECK(cudaMemsetAsync(count_out, 0, 8, st));
         return KGB_OK;
     }
-    select_kernel<Pred><<<(unsigned)tiles, SEL_THREADS, 0, st>>>(pred, n, pos_out, count_out, ws);
+    KGB_CUDA_CHECK(cudaMemsetAsync(ws, 0, select_state_bytes(n), st));
+    u32* masks = (u32*)((char*)ws + select_state_bytes(n));
+    const size_t nwords = select_mask_words(n);
+    const long long steps = (long long)(nwords / 32);
+    long long mb = (steps + (SEL_MASK_THREADS / 32) - 1) / (SEL_MASK_THREADS / 32);
+    const long long cap = (long long)sm_count() * 8;
+    if (mb > cap) mb = cap;
+    select_mask_kernel<Pred><<<(unsigned)mb, SEL_MASK_THREADS, 0, st>>>(pred, n, masks);
+    select_compact_kernel<<<(unsigned)select_tiles(n), SEL_THREADS, 0, st>>>(masks, (i64)nwords, pos_out, count_out, ws);
     KGB_CUDA_CHECK(cudaGetLastError());
     return KGB_OK;
 }
