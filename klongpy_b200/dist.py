@@ -52,6 +52,14 @@ def sharded_reduce(code, args, red):
     return ops.run([ops.OP_ARG, 0], [allp], mode=_lib.MODE_REDUCE, red=red)
 
 
+def combine_partials(part, red):
+    """All ranks' 0-d partial folds -> the global fold (same fixed-order combine on every rank)."""
+    red = ops.RED[red] if not isinstance(red, int) else red
+    if world() == 1:
+        return part
+    return ops.run([ops.OP_ARG, 0], [_gather_scalars(part)], mode=_lib.MODE_REDUCE, red=red)
+
+
 def shard_offset(code, args, red):
     """Exclusive fold over all lower ranks of the per-rank totals: the offset this shard's scan carries.
     Returns (offset 0-d DeviceArray or None on rank 0, totals)."""

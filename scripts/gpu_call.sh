@@ -9,7 +9,7 @@ for step in "$@"; do
       timeout 900 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest_gpu.log 2>&1; echo "pytest exit=$?" | tee -a $out/${tag}_pytest_gpu.log
       grep -E "^(FAILED|ERROR)|passed|failed" $out/${tag}_pytest_gpu.log | tail -5 ;;
     bench)
-      timeout 900 python bench.py --steps 5 --warmup 3 > $out/${tag}_bench.json 2> $out/${tag}_bench.err; echo "bench exit=$?"
+      timeout 900 python bench.py --steps ${BENCH_STEPS:-5} --warmup 3 > $out/${tag}_bench.json 2> $out/${tag}_bench.err; echo "bench exit=$?"
       tail -c 400 $out/${tag}_bench.err; head -c 1500 $out/${tag}_bench.json ;;
     ref)
       timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > $out/${tag}_bench_ref.json 2> $out/${tag}_bench_ref.err; echo "ref exit=$?" ;;
