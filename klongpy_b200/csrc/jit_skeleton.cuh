@@ -679,10 +679,16 @@ __device__ __forceinline__ void kgb_mbar_arrive(u64* bar) {
 __device__ __forceinline__ void kgb_mbar_wait(u64* bar, u32 parity) {
     const u32 a = kgb_smem_u32(bar);
     u32 done = 0, spins = 0;
+    unsigned long long t0 = 0;
     while (!done) {
         asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
                      : "=r"(done) : "r"(a), "r"(parity) : "memory");
-        if (!done && ++spins > (1u << 24)) __trap();  // fail, do not hang
+        if (!done && (++spins & 1023u) == 0) {  // a partner that never arrives: fail after ~4 s, do not hang
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            if (now - t0 > 4000000000ull) __trap();
+        }
     }
 }
 __device__ __forceinline__ void kgb_cp_async16(void* smem_dst, const void* gsrc) {

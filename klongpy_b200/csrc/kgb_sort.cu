@@ -13,6 +13,8 @@
 //
 // Replaces np.argsort (klongpy/backends/numpy_backend.py:75-80) behind kg_argsort (klongpy/writer.py:97-122).
 // Stability is the language contract (ties by position; grade-down = reversed stable ascending).
+#include <cstdlib>
+
 #include "kgb_sort.cuh"
 
 namespace kgb {
@@ -322,6 +324,325 @@ __global__ void __launch_bounds__(ST, 2) onesweep_pass(const typename KeyCodec<D
     }
 }
 
+// ------------------------------------------------------------------------------------------- persistent pipelined pass
+// Same algorithm as onesweep_pass, re-staged the way the scan was because the profile had the
+// same shape: 21 % of the samples waiting for the tile's global loads, 18 % at barriers behind the per-digit
+// look-back (ncu r01h).  One persistent CTA per SM:
+//   * 4 shared-memory stages of 48 KB (keys + positions).  The raw keys of tile i+1 stream in with cp.async while
+//     tile i is ranked; after ranking, the SAME stage receives the tile in digit-sorted order (the keys are in
+//     registers by then) and stays parked until its global offsets are known.
+//   * 512 compute threads: rank (3-sweep warp multisplit) -> per-digit totals, publish counts -> scatter into the
+//     stage -> write out the tile that was parked 2 iterations ago.
+//   * 256 look-back threads (one per digit): wait on an mbarrier for a tile's counts, walk the predecessor states
+//     (4 per round) and hand back the global digit bases through a second mbarrier — off the compute threads'
+//     critical path, with two tile periods of slack.
+// Tiles come from the per-pass atomic ticket (no co-residency assumption).  64-bit key types only; the first pass
+// needs 16-byte aligned caller keys (else the one-tile-per-CTA kernel above runs).
+constexpr int PT = 512, PLT = 256, PNS = 4, PP = 1, PD = 2, PRING = 8;
+constexpr u32 NO_TILE = 0xffffffffu;
+static_assert(PNS == PP + PD + 1, "stage count");
+
+struct PipeSmem {
+    u64 keys[PNS][STILE];
+    u32 idx[PNS][STILE];
+    u32 whist[PT / 32][RADIX];
+    uint2 cntd[PNS][RADIX];  // {tile count of the digit, exclusive digit offset inside the tile}
+    i64 gbase[PNS][RADIX];   // global position of tile-sorted slot p with digit d is gbase[d] + p
+    u32 wsum[RADIX / 32];
+    u64 cnt_bar[PNS], gb_bar[PNS];
+    u32 tile_of[PNS];
+    u32 tile_ring[PRING];
+};
+
+static_assert(sizeof(PipeSmem) <= 227 * 1024, "PipeSmem must fit one SM");
+
+__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64* bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(u64* bar) {
+    asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
+    const u32 a = smem_u32(bar);
+    u32 done = 0, spins = 0;
+    unsigned long long t0 = 0;
+    while (!done) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
+        if (!done && (++spins & 1023u) == 0) {  // a partner that never arrives: fail after ~4 s, do not hang
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            if (now - t0 > 4000000000ull) __trap();
+        }
+    }
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, %0;" ::"n"(PT) : "memory"); }
+
+template <int DT>
+__global__ void __launch_bounds__(PT + PLT, 1) onesweep_pass_p(const typename KeyCodec<DT>::T* __restrict__ in_keys,
+                                                                u64* keysA, u64* keysB, u32* idxA, u32* idxB,
+                                                                i64* __restrict__ idx_out,
+                                                                typename KeyCodec<DT>::T* __restrict__ keys_sorted_out,
+                                                                u64* __restrict__ enc_sorted_out,
+                                                                const SortPlan* __restrict__ plan, int pass, u64* states,
+                                                                u32* tickets, i64 n, int descending) {
+    typedef typename KeyCodec<DT>::T T;
+    static_assert(sizeof(T) == 8, "pipelined pass: 64-bit keys");
+    if (!plan->active[pass]) return;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PipeSmem& sm = *reinterpret_cast<PipeSmem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool first = plan->first[pass] != 0, last = plan->last[pass] != 0;
+    const u64* src_keys = first ? reinterpret_cast<const u64*>(in_keys) : (plan->src[pass] ? keysB : keysA);
+    const u32* src_idx = plan->src[pass] ? idxB : idxA;
+    u64* dst_keys = plan->dst[pass] ? keysB : keysA;
+    u32* dst_idx = plan->dst[pass] ? idxB : idxA;
+    const u32 epoch = (u32)pass + 1;
+    const int shift = 8 * pass;
+    const u32 ntiles = (u32)((n + STILE - 1) / STILE);
+    u32* ticket = &tickets[pass];
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < PNS; s++) {
+            mbar_init(&sm.cnt_bar[s], 1);
+            mbar_init(&sm.gb_bar[s], PLT);
+        }
+        for (int j = 0; j < PP + 2; j++) sm.tile_ring[j] = atomicAdd(ticket, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < (PT / 32) * RADIX; i += PT + PLT) (&sm.whist[0][0])[i] = 0;
+    __syncthreads();
+
+    if (tid >= PT) {
+        // ============================================================ look-back group: thread d owns digit d
+        const int d = tid - PT;
+        const u64 dbase = plan->digit_base[pass][d];
+        for (u32 i = 0;; i++) {
+            const u32 s = i % PNS;
+            mbar_wait(&sm.cnt_bar[s], (i / PNS) & 1u);
+            const u32 tile = sm.tile_of[s];
+            if (tile == NO_TILE) break;
+            const uint2 cd = sm.cntd[s][d];
+            u64 excl = 0;
+            if (tile > 0) {
+                const u64* sp = states + (size_t)(tile - 1) * RADIX + d;  // walks back one tile (RADIX words) at a time
+                u32 left = tile;                                         // predecessors not yet visited
+                u32 spins = 0;
+                bool done = false;
+                while (!done) {
+                    u64 w[LB];
+#pragma unroll
+                    for (int j = 0; j < LB; j++)
+                        w[j] = ((u32)j < left) ? ld_relaxed_u64(sp - (size_t)j * RADIX) : lb_pack(KGB_LB_PREFIX, epoch, 0);
+                    int used = 0;
+#pragma unroll
+                    for (int j = 0; j < LB; j++) {
+                        if (!done && used == j) {
+                            const u64 f = lb_flag(w[j], epoch);
+                            if (f != 0) {
+                                excl += lb_count(w[j]);
+                                used = j + 1;
+                                done = (f == KGB_LB_PREFIX);
+                            }
+                        }
+                    }
+                    sp -= (size_t)used * RADIX;
+                    left = left > (u32)used ? left - (u32)used : 0u;
+                    if (used == 0 && ++spins > (1u << 24)) __trap();  // a predecessor never published: fail, do not hang
+                }
+                st_relaxed_u64(&states[(size_t)tile * RADIX + d], lb_pack(KGB_LB_PREFIX, epoch, excl + cd.x));
+            }
+            sm.gbase[s][d] = (i64)(dbase + excl) - (i64)cd.y;
+            mbar_arrive(&sm.gb_bar[s]);
+        }
+        return;
+    }
+
+    // ================================================================ compute threads
+    const bool src_aligned = (reinterpret_cast<uintptr_t>(src_keys) & 15) == 0;
+    auto issue_load = [&](u32 li) {
+        const u32 t = sm.tile_ring[li % PRING];
+        if (t < ntiles) {
+            const u32 st = li % PNS;
+            const i64 base = (i64)t * STILE;
+            if (base + STILE <= n && src_aligned) {
+#pragma unroll
+                for (int h = 0; h < STILE / 2 / PT; h++) {
+                    const int cf = h * PT + tid;
+                    cp_async16(&sm.keys[st][cf * 2], src_keys + base + cf * 2);
+                }
+                if (!first) {
+#pragma unroll
+                    for (int h = 0; h < STILE / 4 / PT; h++) {
+                        const int cf = h * PT + tid;
+                        cp_async16(&sm.idx[st][cf * 4], src_idx + base + cf * 4);
+                    }
+                }
+            } else {  // ragged last tile (or unaligned caller keys): guarded loads
+#pragma unroll
+                for (int k = 0; k < SI; k++) {
+                    const int slot = k * PT + tid;
+                    if (base + slot < n) {
+                        sm.keys[st][slot] = src_keys[base + slot];
+                        if (!first) sm.idx[st][slot] = src_idx[base + slot];
+                    }
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // tile parked in stage `st` -> global, as digit-contiguous runs
+    auto write_out = [&](u32 li, u32 t) {
+        const u32 st = li % PNS;
+        mbar_wait(&sm.gb_bar[st], (li / PNS) & 1u);
+        const i64 base = (i64)t * STILE;
+        const int tile_n = (int)((n - base) < (i64)STILE ? (n - base) : (i64)STILE);
+#pragma unroll
+        for (int j = 0; j < SI; j++) {
+            const int p = j * PT + tid;
+            if (p < tile_n) {
+                const u64 kk = sm.keys[st][p];
+                const u32 d = (u32)(kk >> shift) & 255u;
+                const i64 gp = sm.gbase[st][d] + p;
+                if (last) {
+                    const i64 op = descending ? (n - 1 - gp) : gp;
+                    idx_out[op] = (i64)sm.idx[st][p];
+                    if (keys_sorted_out) keys_sorted_out[op] = KeyCodec<DT>::dec(kk);
+                    if (enc_sorted_out) enc_sorted_out[op] = kk;
+                } else {
+                    dst_keys[gp] = kk;
+                    dst_idx[gp] = sm.idx[st][p];
+                }
+            }
+        }
+    };
+
+#pragma unroll
+    for (int j = 0; j < PP; j++) issue_load((u32)j);
+    u32 tq[PD];
+#pragma unroll
+    for (int j = 0; j < PD; j++) tq[j] = NO_TILE;
+    u32 tk = 0, i = 0;
+    for (;; i++) {
+        const u32 st = i % PNS;
+        if (tid == 0) {
+            if (i > 0) sm.tile_ring[(i + PP + 1) % PRING] = tk;  // ticket taken one iteration ago
+            tk = atomicAdd(ticket, 1u);                           // for local tile i + PP + 2
+        }
+        const u32 tile = sm.tile_ring[i % PRING];
+        if (tile >= ntiles) break;
+        asm volatile("cp.async.wait_group %0;" ::"n"(PP - 1) : "memory");
+        bar_compute();              // A: tile i is in its stage; everybody is past last iteration's write_out
+        issue_load(i + PP);         // into the stage the previous iteration's write_out released
+        const i64 base = (i64)tile * STILE;
+        const int tile_n = (int)((n - base) < (i64)STILE ? (n - base) : (i64)STILE);
+
+        // ---- rank: warp w owns slots [w*256, (w+1)*256), item k of lane l is slot w*256 + k*32 + l
+        u64 key[SI];
+        u32 idx[SI], rank[SI];
+        const int wslot = warp * (SI * 32);
+#pragma unroll
+        for (int k = 0; k < SI; k++) {
+            const int slot = wslot + k * 32 + lane;
+            if (slot < tile_n) {
+                const u64 raw = sm.keys[st][slot];
+                key[k] = first ? KeyCodec<DT>::enc(*reinterpret_cast<const T*>(&raw)) : raw;
+                idx[k] = first ? (u32)(base + slot) : sm.idx[st][slot];
+            } else {
+                key[k] = ~0ull;
+                idx[k] = 0;
+            }
+        }
+        {
+            const u32 lt = (1u << lane) - 1u;
+            u32 peers[SI];
+#pragma unroll
+            for (int k = 0; k < SI; k++) {
+                const bool valid = (wslot + k * 32 + lane) < tile_n;
+                const u32 d = (u32)(key[k] >> shift) & 255u;
+                peers[k] = __match_any_sync(0xffffffffu, valid ? d : 256u);
+            }
+#pragma unroll
+            for (int k = 0; k < SI; k++) {
+                const bool valid = (wslot + k * 32 + lane) < tile_n;
+                const u32 d = (u32)(key[k] >> shift) & 255u;
+                rank[k] = 0;
+                if (valid && lane == __ffs(peers[k]) - 1) rank[k] = atomicAdd(&sm.whist[warp][d], (u32)__popc(peers[k]));
+            }
+#pragma unroll
+            for (int k = 0; k < SI; k++)
+                rank[k] = __shfl_sync(0xffffffffu, rank[k], __ffs(peers[k]) - 1) + __popc(peers[k] & lt);
+        }
+        bar_compute();              // B: warp histograms complete; every raw key of the stage has been read
+        // ---- per digit (threads 0..255): exclusive offsets across warps, tile count, publish
+        u32 cnt = 0, inc = 0;
+        if (tid < RADIX) {
+            const int d = tid;
+            u32 run = 0;
+#pragma unroll
+            for (int w = 0; w < PT / 32; w++) {
+                const u32 c = sm.whist[w][d];
+                sm.whist[w][d] = run;
+                run += c;
+            }
+            cnt = run;
+            st_relaxed_u64(&states[(size_t)tile * RADIX + d], lb_pack(tile == 0 ? KGB_LB_PREFIX : KGB_LB_AGG, epoch, cnt));
+            inc = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const u32 v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += v;
+            }
+            if (lane == 31) sm.wsum[warp] = inc;
+        }
+        bar_compute();              // C'
+        if (tid < RADIX) {
+            u32 wpre = 0;
+#pragma unroll
+            for (int w = 0; w < RADIX / 32; w++)
+                if (w < warp) wpre += sm.wsum[w];
+            sm.cntd[st][tid] = make_uint2(cnt, wpre + inc - cnt);
+        }
+        bar_compute();              // C: counts + digit offsets of the tile are in the ring
+        if (tid == 0) {
+            sm.tile_of[st] = tile;
+            mbar_arrive(&sm.cnt_bar[st]);  // hand the tile to the look-back group
+        }
+        // ---- scatter into tile-sorted order, into the stage the raw keys came from
+#pragma unroll
+        for (int k = 0; k < SI; k++) {
+            if ((wslot + k * 32 + lane) < tile_n) {
+                const u32 d = (u32)(key[k] >> shift) & 255u;
+                const u32 p = sm.cntd[st][d].y + sm.whist[warp][d] + rank[k];
+                sm.keys[st][p] = key[k];
+                sm.idx[st][p] = idx[k];
+            }
+        }
+        bar_compute();              // D: the sorted tile is parked; whist is free again
+        for (int q = tid; q < (PT / 32) * RADIX; q += PT) (&sm.whist[0][0])[q] = 0;
+        // ---- write out the tile parked PD iterations ago
+        if (tq[0] != NO_TILE) write_out(i - PD, tq[0]);
+#pragma unroll
+        for (int j = 0; j < PD - 1; j++) tq[j] = tq[j + 1];
+        tq[PD - 1] = tile;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < PD; j++)
+        if (tq[j] != NO_TILE) write_out(i - PD + j, tq[j]);
+    bar_compute();
+    if (tid == 0) {
+        sm.tile_of[i % PNS] = NO_TILE;  // release the look-back group
+        mbar_arrive(&sm.cnt_bar[i % PNS]);
+    }
+}
+
 // all keys equal on every digit (or n == 1): the stable permutation is the identity
 template <int DT>
 __global__ void __launch_bounds__(256) sort_identity_kernel(const typename KeyCodec<DT>::T* __restrict__ in_keys,
@@ -337,6 +658,31 @@ __global__ void __launch_bounds__(256) sort_identity_kernel(const typename KeyCo
         if (keys_sorted_out) keys_sorted_out[op] = KeyCodec<DT>::dec(KeyCodec<DT>::enc(in_keys[i]));
         if (enc_sorted_out) enc_sorted_out[op] = KeyCodec<DT>::enc(in_keys[i]);
     }
+}
+
+template <int DT, bool WIDE = sizeof(typename KeyCodec<DT>::T) == 8> struct PipeLauncher {
+    static void go(const void*, const SortWs&, i64*, void*, u64*, int, i64, int, unsigned, cudaStream_t) {}
+};
+template <int DT> struct PipeLauncher<DT, true> {
+    static void go(const void* keys, const SortWs& w, i64* idx_out, void* keys_sorted_out, u64* enc_sorted_out, int p, i64 n,
+                   int descending, unsigned tiles, cudaStream_t st) {
+        typedef typename KeyCodec<DT>::T T;
+        static bool attr_set[64] = {false};
+        const int dev = current_device();
+        if (!attr_set[dev]) {
+            cudaFuncSetAttribute(onesweep_pass_p<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PipeSmem));
+            attr_set[dev] = true;
+        }
+        const unsigned grid = tiles < (unsigned)sm_count() ? tiles : (unsigned)sm_count();
+        onesweep_pass_p<DT><<<grid, PT + PLT, sizeof(PipeSmem), st>>>((const T*)keys, w.keys[0], w.keys[1], w.idx[0], w.idx[1],
+                                                                      idx_out, (T*)keys_sorted_out, enc_sorted_out, w.plan, p,
+                                                                      w.states, w.tickets, n, descending);
+    }
+};
+template <int DT>
+static void launch_pipe(const void* keys, const SortWs& w, i64* idx_out, void* keys_sorted_out, u64* enc_sorted_out, int p, i64 n,
+                        int descending, unsigned tiles, cudaStream_t st) {
+    PipeLauncher<DT>::go(keys, w, idx_out, keys_sorted_out, enc_sorted_out, p, n, descending, tiles, st);
 }
 
 template <int DT>
@@ -358,11 +704,17 @@ static int sort_impl(const void* keys, i64 n, int descending, i64* idx_out, void
     if (hb > cap) hb = cap;
     hist_kernel<DT><<<(unsigned)hb, 256, 0, st>>>((const T*)keys, n, w.hist);
     plan_kernel<<<1, RADIX, 0, st>>>(w.hist, n, w.plan);
+    // persistent pipelined pass for 64-bit keys once every SM has a few tiles (KGB200_SORT_PIPE=0 disables it)
+    bool pipe = sizeof(T) == 8 && tiles >= (unsigned)sm_count() * 4;
+    if (const char* e = getenv("KGB200_SORT_PIPE")) pipe = pipe && atoi(e) != 0;
     for (int p = 0; p < NPASS; p++) {
         if ((DT == KGB_F32 || DT == KGB_I32 || DT == KGB_F32_RAW) && p >= 4) break;  // 32-bit keys: upper digits are zero
-        onesweep_pass<DT><<<tiles, ST, sizeof(PassSmem), st>>>((const T*)keys, w.keys[0], w.keys[1], w.idx[0], w.idx[1],
-                                                               idx_out, (T*)keys_sorted_out, enc_sorted_out, w.plan, p,
-                                                               w.states, w.tickets, n, descending);
+        if (pipe)
+            launch_pipe<DT>(keys, w, idx_out, keys_sorted_out, enc_sorted_out, p, n, descending, tiles, st);
+        else
+            onesweep_pass<DT><<<tiles, ST, sizeof(PassSmem), st>>>((const T*)keys, w.keys[0], w.keys[1], w.idx[0], w.idx[1],
+                                                                   idx_out, (T*)keys_sorted_out, enc_sorted_out, w.plan, p,
+                                                                   w.states, w.tickets, n, descending);
     }
     long long ib = (n + 255) / 256;
     if (ib > cap) ib = cap;

@@ -1,0 +1,48 @@
+"""Multi-GPU parity under torchrun (NCCL): sharded reduce / scan / grouped aggregation vs the oracle on the full data.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 scripts/dist_check.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as td
+
+sys.path.insert(0, ".")
+rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(local)
+td.init_process_group("nccl", device_id=torch.device("cuda", local))
+import klongpy_b200  # noqa: E402
+from klongpy_b200 import dist, ops  # noqa: E402
+from oracle import kg_oracle as O  # noqa: E402
+
+be = klongpy_b200.B200BackendProvider(device=f"cuda:{local}")
+ok = True
+for n in (1000, 1_000_003, 40_000_001):
+    rng = np.random.default_rng(n)           # same data on every rank
+    x = rng.integers(0, 256, n) / 256.0
+    lo, hi = dist.shard_bounds(n)
+    X = be.kg_asarray(x[lo:hi])
+    red = [ops.OP_ARG, 0] + ops.lit(2) + [ops.OPC["mul"]] + ops.lit(1) + [ops.OPC["add"]] + ops.lit(2) + [ops.OPC["pow"]]
+    r = dist.sharded_reduce(red, [X], "+").item()
+    ref = O.eval_ir(("reduce", "+", ("binop", "^", ("binop", "+", ("binop", "*", ("var", "_v0"), ("literal", 2)), ("literal", 1)),
+                                    ("literal", 2))), {"_v0": x})
+    s = dist.sharded_scan([ops.OP_ARG, 0], [X], "+").to_numpy()
+    sref = np.cumsum(x)[lo:hi]
+    mx = dist.sharded_scan([ops.OP_ARG, 0], [X], "|").to_numpy()
+    G = 1000
+    k = rng.integers(0, G, n)
+    v = np.round(rng.normal(10, 15, n), 1)
+    mn, mxg, sm, ct = (t.to_numpy() for t in dist.sharded_groupagg(be.kg_asarray(k[lo:hi]), be.kg_asarray(v[lo:hi]), G))
+    rmn, rmx, rsm, rct = O.grouped_stats(k, v, G)
+    good = (r == ref and np.array_equal(s, sref) and np.array_equal(mx, np.maximum.accumulate(x)[lo:hi]) and
+            np.array_equal(mn, rmn) and np.array_equal(mxg, rmx) and np.array_equal(ct, rct) and
+            np.allclose(sm, rsm, rtol=1e-12, atol=1e-9))
+    print(f"rank {rank}/{world} n={n}: {'ok' if good else 'MISMATCH'}", flush=True)
+    ok &= good
+flag = torch.tensor([1 if ok else 0], device=f"cuda:{local}")
+td.all_reduce(flag, op=td.ReduceOp.MIN)
+td.barrier()
+td.destroy_process_group()
+sys.exit(0 if flag.item() == 1 else 1)
