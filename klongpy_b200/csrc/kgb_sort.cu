@@ -142,6 +142,26 @@ __global__ void __launch_bounds__(RADIX) plan_kernel(const u64* __restrict__ ghi
     }
 }
 
+// peers of a lane = lanes of the warp holding the same 8-bit digit.  Two implementations: MATCH.ANY (one
+// instruction, but a slow unit) or eight ballots folded with LOP3 (CUB's choice); picked by measurement.
+#ifndef KGB_SORT_BALLOT
+#define KGB_SORT_BALLOT 1
+#endif
+__device__ __forceinline__ u32 digit_peers(u32 d, bool valid) {
+#if KGB_SORT_BALLOT
+    u32 peers = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+        const u32 bit = (d >> b) & 1u;
+        const u32 m = __ballot_sync(0xffffffffu, bit != 0u);
+        peers &= m ^ (bit - 1u);  // bit ? m : ~m
+    }
+    return valid ? peers : 0x80000000u;  // invalid lanes: a harmless singleton (their rank is never used)
+#else
+    return __match_any_sync(0xffffffffu, valid ? d : 256u);
+#endif
+}
+
 // ------------------------------------------------------------------------------------------- onesweep pass
 struct PassSmem {
     u64 keys[STILE];
@@ -213,7 +233,7 @@ __global__ void __launch_bounds__(ST, 2) onesweep_pass(const typename KeyCodec<D
         for (int k = 0; k < SI; k++) {
             const bool valid = (wslot + k * 32 + lane) < tile_n;
             const u32 d = (u32)(key[k] >> shift) & 255u;
-            peers[k] = __match_any_sync(0xffffffffu, valid ? d : 256u);
+            peers[k] = digit_peers(d, valid);
         }
 #pragma unroll
         for (int k = 0; k < SI; k++) {
@@ -566,7 +586,7 @@ __global__ void __launch_bounds__(PT + PLT, 1) onesweep_pass_p(const typename Ke
             for (int k = 0; k < SI; k++) {
                 const bool valid = (wslot + k * 32 + lane) < tile_n;
                 const u32 d = (u32)(key[k] >> shift) & 255u;
-                peers[k] = __match_any_sync(0xffffffffu, valid ? d : 256u);
+                peers[k] = digit_peers(d, valid);
             }
 #pragma unroll
             for (int k = 0; k < SI; k++) {
