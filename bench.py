@@ -282,8 +282,11 @@ def main():
     # ---- per-primitive table (N=1 sizes from BASELINE.json configs 1/3/4)
     prims = {}
     if not args.no_primitives:
-        prims["fused_reduce"] = prim_row(n, red_ms, 8, peak)
-        prims["running_sum"] = prim_row(n, scan_ms, 16, peak)
+        xt = X.tensor
+        prims["fused_reduce"] = prim_row(n, red_ms, 8, peak,
+                                         torch_eager_ms=time_kernel(lambda: (((xt * 2) + 1) ** 2).sum(0), 3))
+        prims["running_sum"] = prim_row(n, scan_ms, 16, peak, torch_eager_ms=time_kernel(lambda: xt.cumsum(0), 3))
+        del xt
         try:
             prims.update(primitive_table(be, ops, dist, time_kernel, dev, peak, world, rank))
         except Exception as ex:  # noqa: BLE001
@@ -342,24 +345,35 @@ def primitive_table(be, ops, dist, time_kernel, dev, peak, world, rank):
     n = 100_000_000
     a = DeviceArray(torch.rand(n, dtype=torch.float64, device=dev, generator=g))
     b = DeviceArray(torch.rand(n, dtype=torch.float64, device=dev, generator=g))
-    out["a+b"] = prim_row(n, time_kernel(lambda: ops.binary("add", a, b), 5), 24, peak)
+    # `torch_eager_ms`: the same primitive through the ATen calls the reference's torch backend issues
+    # (torch_backend.py:413-459, 612-616, 1058-1082) on the same GPU in the same run — the prior-art GPU path.
+    out["a+b"] = prim_row(n, time_kernel(lambda: ops.binary("add", a, b), 5), 24, peak,
+                          torch_eager_ms=time_kernel(lambda: torch.add(a.tensor, b.tensor), 5))
     c = DeviceArray(torch.rand(n, dtype=torch.float64, device=dev, generator=g))
     fn, _ = be.compile_expr_ir(("binop", "%", ("binop", "*", ("var", "_v0"), ("binop", "+", ("literal", 2), ("binop", "*", ("var", "_v1"), ("literal", 3)))),
                                 ("binop", "-", ("binop", "+", ("var", "_v0"), ("literal", 1)), ("binop", "*", ("var", "_v1"), ("var", "_v2")))), ["a", "b", "c"])
-    out["(a*2+b*3)%(a+1)-(b*c)"] = prim_row(n, time_kernel(lambda: fn(a, b, c), 5), 32, peak)
+    ta, tb, tc = a.tensor, b.tensor, c.tensor
+    out["(a*2+b*3)%(a+1)-(b*c)"] = prim_row(n, time_kernel(lambda: fn(a, b, c), 5), 32, peak,
+                                            torch_eager_ms=time_kernel(lambda: (ta * (2 + (tb * 3))) / ((ta + 1) - (tb * tc)), 5))
     fn2, _ = be.compile_expr_ir(("reduce", "|", ("binop", "-", ("scan", "|", ("var", "_v0")), ("var", "_v0"))), ["a"])
-    out["|/(|\\ts)-ts"] = prim_row(n, time_kernel(lambda: fn2(a), 5), 8, peak)
+    out["|/(|\\ts)-ts"] = prim_row(n, time_kernel(lambda: fn2(a), 5), 8, peak,
+                                  torch_eager_ms=time_kernel(lambda: (ta.cummax(0).values - ta).amax(0), 5))
     del b, c
     keys_perm = DeviceArray(torch.randperm(n, device=dev, generator=g))
     out["grade_up_perm_1e8"] = prim_row(n, time_kernel(lambda: ops.argsort(keys_perm), 3), 16, peak,
-                                        model_bytes_per_elem=8 + 24 * 4 - 4 + 4, passes=4)
+                                        model_bytes_per_elem=8 + 24 * 4 - 4 + 4, passes=4,
+                                        torch_eager_ms=time_kernel(lambda: torch.argsort(keys_perm.tensor, stable=True), 3))
     del keys_perm
     keys_10k = DeviceArray(torch.randint(0, 10_000, (n,), dtype=torch.int64, device=dev, generator=g))
     out["grade_up_10k_1e8"] = prim_row(n, time_kernel(lambda: ops.argsort(keys_10k), 3), 16, peak,
-                                       model_bytes_per_elem=8 + 24 * 2 - 4 + 4, passes=2)
+                                       model_bytes_per_elem=8 + 24 * 2 - 4 + 4, passes=2,
+                                       torch_eager_ms=time_kernel(lambda: torch.argsort(keys_10k.tensor, stable=True), 3))
     out["group_10k_1e8"] = prim_row(n, time_kernel(lambda: ops.group(keys_10k), 3), 16, peak)
-    out["find_1e8"] = prim_row(n, time_kernel(lambda: ops.find_equal(keys_10k, 77), 3), 8, peak)
-    out["range_10k_1e8"] = prim_row(n, time_kernel(lambda: ops.unique_first(keys_10k), 3), 16, peak)
+    out["find_1e8"] = prim_row(n, time_kernel(lambda: ops.find_equal(keys_10k, 77), 3), 8, peak,
+                               torch_eager_ms=time_kernel(lambda: torch.nonzero(keys_10k.tensor == 77), 3))
+    out["range_10k_1e8"] = prim_row(n, time_kernel(lambda: ops.unique_first(keys_10k), 3), 16, peak,
+                                    torch_eager_ms=time_kernel(lambda: torch.unique(keys_10k.tensor), 3),
+                                    note="torch.unique returns sorted values, not first-appearance order")
     temp = DeviceArray(torch.randn(n, dtype=torch.float64, device=dev, generator=g))
     out["grouped_min_mean_max_10k_1e8"] = prim_row(n, time_kernel(lambda: dist.sharded_groupagg(keys_10k, temp, 10_000), 3),
                                                   16, peak, n_gpus=world)

@@ -23,7 +23,9 @@ typedef unsigned char u8;
 
 #define KGB_MAX_ARGS 12
 #define KGB_BLOCK 256
+#ifndef KGB_UNROLL
 #define KGB_UNROLL 4
+#endif
 
 struct KgbParams {
     const void* ptr[KGB_MAX_ARGS];
@@ -137,26 +139,49 @@ template <> struct kgb_raw<4> { typedef unsigned int type; };
 template <> struct kgb_raw<8> { typedef uint2 type; };
 template <> struct kgb_raw<16> { typedef uint4 type; };
 
-// streaming (evict-first) load of V contiguous elements into registers dst[0..V)
+// streaming (evict-first) load of V contiguous elements into registers dst[0..V).  32-byte groups use the 256-bit
+// global accesses of sm_100 (LDG.E.256 / STG.E.256): half the memory instructions per byte moved.
 template <typename T, int V> __device__ __forceinline__ void kgb_ldv(T* dst, const T* src) {
-    typedef typename kgb_raw<sizeof(T) * V>::type R;
-    union {
-        R r;
-        T t[V];
-    } u;
-    u.r = __ldcs(reinterpret_cast<const R*>(src));
+    if constexpr (sizeof(T) * V == 32) {
+        union {
+            u64 r[4];
+            T t[V];
+        } u;
+        asm volatile("ld.global.cs.v4.u64 {%0, %1, %2, %3}, [%4];"
+                     : "=l"(u.r[0]), "=l"(u.r[1]), "=l"(u.r[2]), "=l"(u.r[3]) : "l"(src));
 #pragma unroll
-    for (int j = 0; j < V; j++) dst[j] = u.t[j];
+        for (int j = 0; j < V; j++) dst[j] = u.t[j];
+    } else {
+        typedef typename kgb_raw<sizeof(T) * V>::type R;
+        union {
+            R r;
+            T t[V];
+        } u;
+        u.r = __ldcs(reinterpret_cast<const R*>(src));
+#pragma unroll
+        for (int j = 0; j < V; j++) dst[j] = u.t[j];
+    }
 }
 template <typename T, int V> __device__ __forceinline__ void kgb_stv(T* dst, const T* src) {
-    typedef typename kgb_raw<sizeof(T) * V>::type R;
-    union {
-        R r;
-        T t[V];
-    } u;
+    if constexpr (sizeof(T) * V == 32) {
+        union {
+            u64 r[4];
+            T t[V];
+        } u;
 #pragma unroll
-    for (int j = 0; j < V; j++) u.t[j] = src[j];
-    __stcs(reinterpret_cast<R*>(dst), u.r);
+        for (int j = 0; j < V; j++) u.t[j] = src[j];
+        asm volatile("st.global.cs.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "l"(u.r[0]), "l"(u.r[1]), "l"(u.r[2]), "l"(u.r[3])
+                     : "memory");
+    } else {
+        typedef typename kgb_raw<sizeof(T) * V>::type R;
+        union {
+            R r;
+            T t[V];
+        } u;
+#pragma unroll
+        for (int j = 0; j < V; j++) u.t[j] = src[j];
+        __stcs(reinterpret_cast<R*>(dst), u.r);
+    }
 }
 
 // ------------------------------------------------------------------ warp / block folds
@@ -683,6 +708,7 @@ __device__ __forceinline__ void kgb_mbar_wait(u64* bar, u32 parity) {
     while (!done) {
         asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
                      : "=r"(done) : "r"(a), "r"(parity) : "memory");
+        if (!done) __nanosleep(64);  // idle partners should not eat the issue slots of the working warps
         if (!done && (++spins & 1023u) == 0) {  // a partner that never arrives: fail after ~4 s, do not hang
             unsigned long long now;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));

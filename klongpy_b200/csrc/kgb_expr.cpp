@@ -447,7 +447,7 @@ struct kgb_expr {
     int device = -1;
     int mode = 0, red_op = 0, red_op2 = 0;
     int out_dtype = 0, acc_dtype = 0, acc2_dtype = 0;
-    int vec = 1;
+    int vec = 1, align = 16, unroll = 4;
     std::vector<kgb::ArgInfo> args;
     std::string source, name_v, name_s;
     CUmodule module = nullptr;
@@ -539,9 +539,14 @@ static int build_source(kgb_expr* h, const int32_t* code, int n_code, const int3
     }
     maxsz = std::max(maxsz, (int)dtype_size(h->out_dtype));
     maxsz = std::max(maxsz, (int)dtype_size(h->acc_dtype));
-    h->vec = 16 / maxsz;
+    // MAP / REDUCE move 32-byte groups (256-bit LDG/STG, two groups in flight per array per thread); the scan
+    // kernels keep 16-byte groups (their shared-memory transposes are built around uint4)
+    const bool wide = (h->mode == KGB_MODE_MAP || h->mode == KGB_MODE_REDUCE) && !getenv("KGB200_NO_WIDE");
+    h->vec = (wide ? 32 : 16) / maxsz;
+    h->align = wide ? 32 : 16;
+    h->unroll = wide ? 2 : 4;
 
-    m << "#define KGB_VEC " << h->vec << "\n";
+    m << "#define KGB_VEC " << h->vec << "\n#define KGB_UNROLL " << h->unroll << "\n";
     m << "#define KGB_OUT_T " << ctype(h->out_dtype) << "\n";
     m << "#define KGB_ACC_T " << ctype(h->acc_dtype) << "\n";
     if (h->mode == KGB_MODE_SCAN || h->mode == KGB_MODE_SCANRED) {
@@ -682,14 +687,14 @@ static int jit_compile(kgb_expr* h, bool load) {
     return KGB_OK;
 }
 
-static const int kBlock = 256, kUnroll = 4;
+static const int kBlock = 256;
 
 static long long scan_tile(const kgb_expr* h) { return (long long)h->sblock * h->sitems; }
 
 static unsigned fold_grid(const kgb_expr* h, long long n, bool vec) {
     const long long V = vec ? h->vec : 1;
     const long long groups = (n + V - 1) / V;
-    long long need = (groups + (long long)kBlock * kUnroll - 1) / ((long long)kBlock * kUnroll);
+    long long need = (groups + (long long)kBlock * h->unroll - 1) / ((long long)kBlock * h->unroll);
     long long cap = (long long)sm_count() * (vec ? h->occ_v : h->occ_s);
     if (need < 1) need = 1;
     return (unsigned)std::min(need, cap);
@@ -798,7 +803,8 @@ extern "C" int kgb_expr_launch(kgb_expr* h, const void* const* args, int64_t n, 
     }
     KgbParamsHost P;
     memset(&P, 0, sizeof P);
-    bool aligned = ((uintptr_t)out % 16) == 0;
+    const uintptr_t amask = (uintptr_t)h->align - 1;
+    bool aligned = ((uintptr_t)out & amask) == 0;
     for (size_t i = 0; i < h->args.size(); i++) {
         const ArgInfo& a = h->args[i];
         KGB_REQUIRE(args && args[i], "kgb_expr_launch: argument %zu is null", i);
@@ -809,7 +815,7 @@ extern "C" int kgb_expr_launch(kgb_expr* h, const void* const* args, int64_t n, 
                 memcpy(&P.si[i], args[i], 8);
         } else {
             P.ptr[i] = args[i];
-            if (a.kind == KGB_ARG_ARRAY) aligned &= ((uintptr_t)args[i] % 16) == 0;
+            if (a.kind == KGB_ARG_ARRAY) aligned &= ((uintptr_t)args[i] & amask) == 0;
         }
     }
     P.out = out;

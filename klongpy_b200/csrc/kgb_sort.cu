@@ -390,6 +390,7 @@ __device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
     while (!done) {
         asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
                      : "=r"(done) : "r"(a), "r"(parity) : "memory");
+        if (!done) __nanosleep(64);  // idle partners should not eat the issue slots of the working warps
         if (!done && (++spins & 1023u) == 0) {  // a partner that never arrives: fail after ~4 s, do not hang
             unsigned long long now;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
