@@ -457,7 +457,7 @@ struct kgb_expr {
     int pipe_arg = -1;              // >= 0: the persistent pipelined scan kernel exists (index of its one array argument)
     std::string name_p;
     CUfunction fn_p = nullptr;
-    int pipe_threads = 256, pipe_stages = 7, pipe_load = 2, pipe_park = 4, pipe_lw = 4;
+    int pipe_threads = 256, pipe_stages = 7, pipe_load = 2, pipe_park = 4, pipe_lw = 2, pipe_lbw = 1;
     int pipe_ctas_per_sm = 1;
 };
 
@@ -498,6 +498,10 @@ static size_t pipe_smem(const kgb_expr* h) { return (size_t)h->pipe_stages * 327
 static unsigned pipe_block(const kgb_expr* h) { return (unsigned)(h->pipe_threads + 32 * h->pipe_lw); }
 // Geometry: KGB200_PIPE="threads,stages,load,park,lookback_warps,ctas_per_sm" overrides the default for tuning.
 static void pipe_geometry(kgb_expr* h) {
+    if (const char* e = getenv("KGB200_PIPE_LBW")) {
+        const int v = atoi(e);
+        if (v == 1 || v == 2 || v == 4 || v == 8) h->pipe_lbw = v;
+    }
     if (const char* e = getenv("KGB200_PIPE")) {
         int t, s, l, d, w, c;
         if (sscanf(e, "%d,%d,%d,%d,%d,%d", &t, &s, &l, &d, &w, &c) == 6 && (t == 256 || t == 512) && s >= l + d + 1 && s <= 7 &&
@@ -599,7 +603,7 @@ static int build_source(kgb_expr* h, const int32_t* code, int n_code, const int3
             h->pipe_arg = idx;
             pipe_geometry(h);
             m << "#define KGB_PT " << h->pipe_threads << "\n#define KGB_PS " << h->pipe_stages << "\n#define KGB_PP " << h->pipe_load
-              << "\n#define KGB_PD " << h->pipe_park << "\n#define KGB_PLW " << h->pipe_lw << "\n#define KGB_PMINB " << h->pipe_ctas_per_sm << "\n";
+              << "\n#define KGB_PD " << h->pipe_park << "\n#define KGB_PLW " << h->pipe_lw << "\n#define KGB_PMINB " << h->pipe_ctas_per_sm << "\n#define KGB_PLBW " << h->pipe_lbw << "\n";
             m << "#define KGB_PIPE 1\n#define KGB_PIPE_T " << ctype(h->args[idx].dtype) << "\n#define KGB_PIPE_ARG a" << idx
               << "\n#define KGB_PIPE_PTR p.ptr[" << idx << "]\n";
         }
