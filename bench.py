@@ -378,6 +378,13 @@ def primitive_table(be, ops, dist, time_kernel, dev, peak, world, rank):
     out["grouped_min_mean_max_10k_1e8"] = prim_row(n, time_kernel(lambda: dist.sharded_groupagg(keys_10k, temp, 10_000), 3),
                                                   16, peak, n_gpus=world)
     del temp, a
+    if world == 1:
+        # config 4 at its full size: 1e9 synthetic rows, 10k stations (16 GB of input)
+        nb = 1_000_000_000
+        st_b = DeviceArray(torch.randint(0, 10_000, (nb,), dtype=torch.int64, device=dev, generator=g))
+        tp_b = DeviceArray(torch.randn(nb, dtype=torch.float64, device=dev, generator=g))
+        out["grouped_min_mean_max_10k_1e9"] = prim_row(nb, time_kernel(lambda: ops.groupagg(st_b, tp_b, 10_000), 3), 16, peak)
+        del st_b, tp_b
     # config 5: autograd at a 1e7-element batch (fused forward + fused backward kernels, float64)
     m = 10_000_000
     X = DeviceArray(torch.rand(m, dtype=torch.float64, device=dev, generator=g) * 2)

@@ -17,8 +17,11 @@ struct AggWs {
     double* tsum;
     u64* tcnt;
     int* err;
+    double* psum;  // [parts][G] per-CTA partial sums   (all-shared-memory variant: plain stores, folded in CTA order)
+    u32* pcnt;     // [parts][G] per-CTA partial counts
     size_t total;
 };
+constexpr int AGG_MAX_PARTS = 160;  // >= SM count: one persistent CTA per SM
 static AggWs carve_agg(void* ws, i64 G) {
     AggWs a;
     char* p = (char*)ws;
@@ -28,7 +31,9 @@ static AggWs carve_agg(void* ws, i64 G) {
     a.tsum = (double*)(p + 2 * gb);
     a.tcnt = (u64*)(p + 3 * gb);
     a.err = (int*)(p + 4 * gb);
-    a.total = 4 * gb + 256;
+    a.psum = (double*)(p + 4 * gb + 256);
+    a.pcnt = (u32*)(p + 4 * gb + 256 + (size_t)AGG_MAX_PARTS * gb);
+    a.total = 4 * gb + 256 + (size_t)AGG_MAX_PARTS * gb + (size_t)AGG_MAX_PARTS * align_up((size_t)G * 4, 256);
     return a;
 }
 
@@ -91,8 +96,9 @@ __global__ void __launch_bounds__(256) groupagg_kernel(const i64* __restrict__ k
 // One persistent CTA per SM, 12 B of shared memory per station.
 template <int VARIANT>
 __global__ void __launch_bounds__(1024, 1) groupagg_kernel_v2(const i64* __restrict__ keys, const double* __restrict__ vals,
-                                                              i64 n, i64 G, AggWs a) {
+                                                              i64 n, i64 G, AggWs a, int l2_every) {
     extern __shared__ __align__(16) unsigned char agg_smem[];
+    const bool sum_to_l2 = l2_every > 0 && ((threadIdx.x >> 5) % l2_every) == l2_every - 1;
     constexpr bool COUNT_IN_SMEM = VARIANT == 1 || VARIANT == 3;
     constexpr bool SUM_IN_SMEM = VARIANT == 3;
     double* s_sum = reinterpret_cast<double*>(agg_smem);  // VARIANT 3 only (G doubles first, keeps 8-byte alignment)
@@ -121,8 +127,11 @@ __global__ void __launch_bounds__(1024, 1) groupagg_kernel_v2(const i64* __restr
             if (hi > s_maxhi[k]) atomicMax(&s_maxhi[k], hi);
             if (emax > ld_relaxed_u64(&a.tmax[k])) atomicMax(&a.tmax[k], emax);
         }
-        if (SUM_IN_SMEM)
-            atomicAdd(&s_sum[k], v);  // ATOMS.CAST.SPIN.64: a CAS loop, but on the SM's own atomic unit
+        // the float64 add is the expensive step: a CAS loop (ATOMS.CAST.SPIN.64) on the SM's own atomic unit, or a
+        // RED.ADD.F64 on the L2 atomic units.  Both units work at the same time when one warp in `l2_every` sends
+        // its sums to L2 (groupagg_finalize adds the global table and the per-CTA partials).
+        if (SUM_IN_SMEM && !sum_to_l2)
+            atomicAdd(&s_sum[k], v);
         else
             atomicAdd(&a.tsum[k], v);
         if (COUNT_IN_SMEM)
@@ -160,15 +169,115 @@ __global__ void __launch_bounds__(1024, 1) groupagg_kernel_v2(const i64* __restr
     } else {
         for (i64 i = tid; i < n; i += stride) row(keys[i], vals[i]);
     }
-    if (COUNT_IN_SMEM) {
+    if (SUM_IN_SMEM) {
+        // per-CTA partial tables leave as plain coalesced stores; groupagg_finalize folds them in CTA order
+        // (3 M global atomics for the flush cost ~0.1 ms at 1e8 rows)
+        __syncthreads();
+        double* ps = a.psum + (size_t)blockIdx.x * G;
+        u32* pc = a.pcnt + (size_t)blockIdx.x * G;
+        for (i64 i = threadIdx.x; i < G; i += blockDim.x) {
+            ps[i] = s_sum[i];
+            pc[i] = s_cnt[i];
+        }
+    } else if (COUNT_IN_SMEM) {
         __syncthreads();
         for (i64 i = threadIdx.x; i < G; i += blockDim.x) {
             const u32 c = s_cnt[i];
-            if (c) {
-                atomicAdd(&a.tcnt[i], (u64)c);
-                if (SUM_IN_SMEM) atomicAdd(&a.tsum[i], s_sum[i]);
+            if (c) atomicAdd(&a.tcnt[i], (u64)c);
+        }
+    }
+}
+
+// v4 (kept for the record, not the default: ATOMS.CAS.128 measured 1.7x slower than v3's CAS.64 + POPC.INC):
+// one 16-byte shared-memory record per station {sum f64 | count u32 | min filter u16 | max filter u16}, updated
+// with ONE 128-bit CAS per row (ATOMS.CAS.128): the record load, the float64 add, the count and both filters share a
+// single shared-memory read-modify-write instead of five separate operations.  The filters are the top 16 bits of the
+// order-encoded value (sign, exponent, 4 mantissa bits); rows that land in the extreme's bucket take the exact
+// read-check + RED on the L2-resident global table, like v2.  16 B of shared memory per station (G <= 12 800).
+struct __align__(16) AggRec {
+    u64 sum_bits;
+    u64 meta;  // [31:0] count  [47:32] min filter  [63:48] max filter
+};
+__device__ __forceinline__ AggRec cas128_shared(AggRec* addr, AggRec cmp, AggRec val) {
+    AggRec old;
+    asm volatile(
+        "{\n .reg .b128 c, v, o;\n mov.b128 c, {%2, %3};\n mov.b128 v, {%4, %5};\n"
+        " atom.shared.cas.b128 o, [%6], c, v;\n mov.b128 {%0, %1}, o;\n}\n"
+        : "=l"(old.sum_bits), "=l"(old.meta)
+        : "l"(cmp.sum_bits), "l"(cmp.meta), "l"(val.sum_bits), "l"(val.meta), "r"((u32)__cvta_generic_to_shared(addr))
+        : "memory");
+    return old;
+}
+
+__global__ void __launch_bounds__(1024, 1) groupagg_kernel_v4(const i64* __restrict__ keys, const double* __restrict__ vals,
+                                                              i64 n, i64 G, AggWs a) {
+    extern __shared__ __align__(16) unsigned char agg_smem[];
+    AggRec* tab = reinterpret_cast<AggRec*>(agg_smem);
+    for (i64 i = threadIdx.x; i < G; i += blockDim.x) {
+        tab[i].sum_bits = 0ull;
+        tab[i].meta = 0x0000ffff00000000ull;  // count 0, min filter 0xffff, max filter 0
+    }
+    __syncthreads();
+    auto row = [&](i64 k, double v) {
+        if ((u64)k >= (u64)G) {
+            *a.err = 1;
+            return;
+        }
+        const u64 emin = enc_for_min(v), emax = enc_for_max(v);
+        const u32 lo16 = (u32)(emin >> 48), hi16 = (u32)(emax >> 48);
+        AggRec* p = &tab[k];
+        AggRec cur = *p;
+        bool slow_min, slow_max;
+        while (true) {
+            const u32 mn = (u32)(cur.meta >> 32) & 0xffffu, mx = (u32)(cur.meta >> 48);
+            slow_min = lo16 <= mn;
+            slow_max = hi16 >= mx;
+            AggRec nw;
+            nw.sum_bits = (u64)__double_as_longlong(__longlong_as_double((i64)cur.sum_bits) + v);
+            nw.meta = (u64)((u32)cur.meta + 1u) | ((u64)(lo16 < mn ? lo16 : mn) << 32) | ((u64)(hi16 > mx ? hi16 : mx) << 48);
+            const AggRec got = cas128_shared(p, cur, nw);
+            if (got.sum_bits == cur.sum_bits && got.meta == cur.meta) break;
+            cur = got;
+        }
+        if (slow_min && emin < ld_relaxed_u64(&a.tmin[k])) atomicMin(&a.tmin[k], emin);
+        if (slow_max && emax > ld_relaxed_u64(&a.tmax[k])) atomicMax(&a.tmax[k], emax);
+    };
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    const i64 tid = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool vec = ((reinterpret_cast<uintptr_t>(keys) | reinterpret_cast<uintptr_t>(vals)) & 15) == 0;
+    constexpr int U = 4;
+    if (vec) {
+        const i64 n2 = n / 2;
+        for (i64 g0 = tid; g0 < n2; g0 += stride * U) {
+            longlong2 k[U];
+            double2 v[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const i64 g = g0 + u * stride;
+                if (g < n2) {
+                    k[u] = __ldcs(reinterpret_cast<const longlong2*>(keys) + g);
+                    v[u] = __ldcs(reinterpret_cast<const double2*>(vals) + g);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const i64 g = g0 + u * stride;
+                if (g < n2) {
+                    row(k[u].x, v[u].x);
+                    row(k[u].y, v[u].y);
+                }
             }
         }
+        if ((n & 1) && tid == 0) row(keys[n - 1], vals[n - 1]);
+    } else {
+        for (i64 i = tid; i < n; i += stride) row(keys[i], vals[i]);
+    }
+    __syncthreads();
+    double* ps = a.psum + (size_t)blockIdx.x * G;
+    u32* pc = a.pcnt + (size_t)blockIdx.x * G;
+    for (i64 i = threadIdx.x; i < G; i += blockDim.x) {
+        ps[i] = __longlong_as_double((i64)tab[i].sum_bits);
+        pc[i] = (u32)tab[i].meta;
     }
 }
 
@@ -176,16 +285,21 @@ __device__ __forceinline__ double nanpropagating_min(double a, double b) { retur
 __device__ __forceinline__ double nanpropagating_max(double a, double b) { return (a != a) ? a : ((b != b) ? b : (a > b ? a : b)); }
 
 __global__ void __launch_bounds__(256) groupagg_finalize(AggWs a, i64 G, double* __restrict__ mn, double* __restrict__ mx,
-                                                          double* __restrict__ sm, i64* __restrict__ ct, int accumulate) {
+                                                          double* __restrict__ sm, i64* __restrict__ ct, int accumulate, int nparts) {
     const i64 g = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= G) return;
-    const u64 c = a.tcnt[g];
+    u64 c = a.tcnt[g];
+    double psum = 0.0;
+    for (int part = 0; part < nparts; part++) {  // fixed order: the cross-CTA combine is bit-reproducible
+        psum += a.psum[(size_t)part * G + g];
+        c += a.pcnt[(size_t)part * G + g];
+    }
     double vmin = __longlong_as_double(0x7ff0000000000000ll), vmax = -vmin, vsum = 0.0;
     if (c) {
         const u64 emin = a.tmin[g], emax = a.tmax[g];
         vmin = (emin == 0ull) ? __longlong_as_double(0x7ff8000000000000ll) : key_to_f64(emin);
         vmax = key_to_f64(emax);
-        vsum = a.tsum[g];
+        vsum = a.tsum[g] + psum;
     }
     if (accumulate) {
         mn[g] = nanpropagating_min(mn[g], vmin);
@@ -236,22 +350,38 @@ extern "C" int kgb_groupagg_f64(const int64_t* keys, const double* vals, int64_t
     const size_t gb = align_up((size_t)n_groups * 8, 256);
     KGB_CUDA_CHECK(cudaMemsetAsync(a.tmin, 0xff, gb, st));
     KGB_CUDA_CHECK(cudaMemsetAsync(a.tmax, 0, 3 * gb + 256, st));
+    int nparts = 0;
     if (n > 0) {
         long long blocks = (n / 2 + 256 * 4 - 1) / (256 * 4);
         const long long cap = (long long)sm_count() * 8;
         if (blocks > cap) blocks = cap;
         if (blocks < 1) blocks = 1;
-        // variant: 3 = everything in shared memory (default when 20 B/station fit), 1 = filters + count in shared
+        // variant: 3 = sum / count / filters in separate shared-memory arrays (default when 20 B/station fit),
+        // 4 = one 128-bit CAS per row on a 16-byte record (ATOMS.CAS.128 turned out slower than CAS.64 + POPC.INC), 1 = filters + count in shared
         // memory and RED.ADD.F64 sums on the global table, 2 = filters only, 0 = v1 (all four updates on the
         // global table).  KGB200_AGG_VARIANT overrides for measurements.
-        int variant = 3;
+        int variant = 3;  // measured at 1e9 rows / 10k stations: v3 4.2 ms (0.58 of roofline), v4 7.1 ms, v1 ~14 ms, v0 ~23 ms
         if (const char* e = getenv("KGB200_AGG_VARIANT")) variant = atoi(e);
-        if (variant < 0 || variant > 3) variant = 3;
+        if (variant < 0 || variant > 4) variant = 3;
         const size_t limit = 200 * 1024;
+        if (variant == 4 && (size_t)n_groups * 16 > limit) variant = 1;
         if (variant == 3 && (size_t)n_groups * 20 > limit) variant = 1;
         if (variant != 0 && (size_t)n_groups * 12 > limit) variant = 0;
         if (variant == 0) {
             groupagg_kernel<<<(unsigned)blocks, 256, 0, st>>>((const i64*)keys, vals, n, n_groups, a);
+        } else if (variant == 4) {
+            static bool attr4[64] = {false};
+            const int dev = current_device();
+            if (!attr4[dev]) {
+                KGB_CUDA_CHECK(cudaFuncSetAttribute(groupagg_kernel_v4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
+                attr4[dev] = true;
+            }
+            long long pb = (n / 2 + 1024 * 4 - 1) / (1024 * 4);
+            if (pb > sm_count()) pb = sm_count();
+            if (pb > AGG_MAX_PARTS) pb = AGG_MAX_PARTS;
+            if (pb < 1) pb = 1;
+            groupagg_kernel_v4<<<(unsigned)pb, 1024, (size_t)n_groups * 16, st>>>((const i64*)keys, vals, n, n_groups, a);
+            nparts = (int)pb;
         } else {
             const size_t smem = (size_t)n_groups * (variant == 3 ? 20 : 12);
             static bool attr_set[64] = {false};
@@ -262,19 +392,24 @@ extern "C" int kgb_groupagg_f64(const int64_t* keys, const double* vals, int64_t
                 KGB_CUDA_CHECK(cudaFuncSetAttribute(groupagg_kernel_v2<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
                 attr_set[dev] = true;
             }
+            int l2_every = 0;
+            if (const char* e = getenv("KGB200_AGG_L2_EVERY")) l2_every = atoi(e);
             long long pb = (n / 2 + 1024 * 4 - 1) / (1024 * 4);
             if (pb > sm_count()) pb = sm_count();
+            if (pb > AGG_MAX_PARTS) pb = AGG_MAX_PARTS;
             if (pb < 1) pb = 1;
             if (variant == 1)
-                groupagg_kernel_v2<1><<<(unsigned)pb, 1024, smem, st>>>((const i64*)keys, vals, n, n_groups, a);
+                groupagg_kernel_v2<1><<<(unsigned)pb, 1024, smem, st>>>((const i64*)keys, vals, n, n_groups, a, l2_every);
             else if (variant == 2)
-                groupagg_kernel_v2<2><<<(unsigned)pb, 1024, smem, st>>>((const i64*)keys, vals, n, n_groups, a);
-            else
-                groupagg_kernel_v2<3><<<(unsigned)pb, 1024, smem, st>>>((const i64*)keys, vals, n, n_groups, a);
+                groupagg_kernel_v2<2><<<(unsigned)pb, 1024, smem, st>>>((const i64*)keys, vals, n, n_groups, a, l2_every);
+            else {
+                groupagg_kernel_v2<3><<<(unsigned)pb, 1024, smem, st>>>((const i64*)keys, vals, n, n_groups, a, l2_every);
+                nparts = (int)pb;
+            }
         }
     }
     groupagg_finalize<<<(unsigned)((n_groups + 255) / 256), 256, 0, st>>>(a, n_groups, min_out, max_out, sum_out,
-                                                                         (i64*)count_out, accumulate);
+                                                                         (i64*)count_out, accumulate, nparts);
     KGB_CUDA_CHECK(cudaGetLastError());
     int err = 0;
     // out-of-range keys are a caller bug: report it (one 4-byte read after the kernels)

@@ -24,7 +24,7 @@ constexpr int NPASS = 8;
 constexpr int ST = 512;            // threads per CTA
 constexpr int SI = 8;              // keys per thread (8 x (u64 key + u32 pos + u32 rank) = 32 payload registers, so
                                    // two 512-thread CTAs fit an SM's register file; 16/thread ran at 25 % occupancy)
-constexpr int LB = 4;              // look-back states fetched per round (independent loads, one L2 round trip)
+constexpr int LB = 2;              // look-back states fetched per round (independent loads, one L2 round trip)
 constexpr int STILE = ST * SI;     // 4096 keys per tile
 constexpr int SWARPS = ST / 32;
 
