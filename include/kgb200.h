@@ -135,7 +135,10 @@ int kgb_device_sm_count(int device, int* out);
 /* Replaces NumpyBackendProvider.compile_expr_ir / _ir_to_source (numpy_backend.py:105-178): one
    single-pass kernel per IR tree instead of one NumPy call (and temporary) per node.  Also the engine
    behind every eager dyad/monad (one-node programs).
-   code/n_code: postfix program.  For KGB_MODE_SCANRED, code2/n_code2 is the epilogue program evaluated
+   code/n_code: postfix program.  For KGB_MODE_REDUCE an optional code2 is a SECOND expression over the same
+   arguments folded with red_op2 in the same pass (both accumulators 8 bytes wide): out[0] receives the first
+   result, the next 8-byte slot the second — `(+/p*s)%+/s` (examples/bench_compiler.kg VWAP) reads p and s once.
+   For KGB_MODE_SCANRED, code2/n_code2 is the epilogue program evaluated
    at each element with KGB_OP_SCANVAL available, folded with red_op2.  For KGB_MODE_SCAN an optional
    code2 over scalar arguments only is the SEED folded in front of element 0 (the exclusive offset a shard
    carries in a multi-GPU scan).  Otherwise pass NULL/0.
@@ -154,6 +157,8 @@ int kgb_expr_workspace_bytes(const kgb_expr* h, int64_t n, size_t* out_bytes);
    REDUCE over n == 0 is rejected (the host mirrors numpy's identity / ValueError rules). */
 int kgb_expr_launch(kgb_expr* h, const void* const* args, int64_t n, void* out, void* workspace,
                     size_t workspace_bytes, void* stream);
+/* element type of the second result of a two-output reduce, -1 if the handle has none */
+int kgb_expr_out_dtype2(const kgb_expr* h);
 /* generated CUDA source of a compiled expression (for tests, DESIGN.md and ncu --import-source) */
 const char* kgb_expr_source(const kgb_expr* h);
 /* name of the dominant kernel in the compiled module (shows up in ncu) */

@@ -260,6 +260,30 @@ __device__ __forceinline__ KGB_ACC_T kgb_block_fold(KGB_ACC_T v, KGB_ACC_T* sh) 
     return v;  // valid in thread 0
 }
 
+#ifdef KGB_HAS_RED2
+// second fold of a two-output reduce (KGB_EVALB / KGB_RED2): `(+/p*s)%+/s` reads p and s ONCE for both sums, and a
+// sharded scan gets its shard total from the same pass as another reduction over the same vector
+__device__ __forceinline__ KGB_ACC2_T kgb_block_fold2(KGB_ACC2_T v, KGB_ACC2_T* sh) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        KGB_ACC2_T o = kgb_shfl_xor<KGB_ACC2_T>(v, m);
+        v = KGB_RED2(v, o);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        v = (lane < KGB_BLOCK / 32) ? sh[lane] : (KGB_ACC2_T)(KGB_RED2_IDENT);
+#pragma unroll
+        for (int m = (KGB_BLOCK / 64); m >= 1; m >>= 1) {
+            KGB_ACC2_T o = kgb_shfl_xor<KGB_ACC2_T>(v, m);
+            v = KGB_RED2(v, o);
+        }
+    }
+    return v;  // valid in thread 0
+}
+#endif
+
 template <int V> __device__ __forceinline__ void kgb_reduce_body(const KgbParams& p) {
     KGB_SCALARS
     __shared__ KGB_ACC_T sh[KGB_BLOCK / 32];
@@ -271,6 +295,12 @@ template <int V> __device__ __forceinline__ void kgb_reduce_body(const KgbParams
     KGB_ACC_T acc[V * KGB_UNROLL];
 #pragma unroll
     for (int k = 0; k < V * KGB_UNROLL; k++) acc[k] = (KGB_ACC_T)(KGB_RED_IDENT);
+#ifdef KGB_HAS_RED2
+    __shared__ KGB_ACC2_T sh2[KGB_BLOCK / 32];
+    KGB_ACC2_T acc2[V * KGB_UNROLL];
+#pragma unroll
+    for (int k = 0; k < V * KGB_UNROLL; k++) acc2[k] = (KGB_ACC2_T)(KGB_RED2_IDENT);
+#endif
     for (i64 g0 = tid; g0 < ngroups; g0 += stride * KGB_UNROLL) {
         KGB_DECL_REGS(V * KGB_UNROLL)
 #pragma unroll
@@ -286,6 +316,10 @@ template <int V> __device__ __forceinline__ void kgb_reduce_body(const KgbParams
                 for (int j = 0; j < V; j++) {
                     KGB_ACC_T e = (KGB_ACC_T)(KGB_EVAL(u * V + j));
                     acc[u * V + j] = KGB_RED(acc[u * V + j], e);
+#ifdef KGB_HAS_RED2
+                    KGB_ACC2_T e2 = (KGB_ACC2_T)(KGB_EVALB(u * V + j));
+                    acc2[u * V + j] = KGB_RED2(acc2[u * V + j], e2);
+#endif
                 }
             }
         }
@@ -296,18 +330,35 @@ template <int V> __device__ __forceinline__ void kgb_reduce_body(const KgbParams
         KGB_LOAD_VEC(1, 0, t)
         KGB_ACC_T e = (KGB_ACC_T)(KGB_EVAL(0));
         acc[0] = KGB_RED(acc[0], e);
+#ifdef KGB_HAS_RED2
+        KGB_ACC2_T e2 = (KGB_ACC2_T)(KGB_EVALB(0));
+        acc2[0] = KGB_RED2(acc2[0], e2);
+#endif
     }
 #pragma unroll
     for (int w = (V * KGB_UNROLL) / 2; w >= 1; w >>= 1) {
 #pragma unroll
-        for (int k = 0; k < w; k++) acc[k] = KGB_RED(acc[k], acc[k + w]);
+        for (int k = 0; k < w; k++) {
+            acc[k] = KGB_RED(acc[k], acc[k + w]);
+#ifdef KGB_HAS_RED2
+            acc2[k] = KGB_RED2(acc2[k], acc2[k + w]);
+#endif
+        }
     }
     KGB_ACC_T v = kgb_block_fold(acc[0], sh);
 
     u32* ticket = (u32*)p.ws;
     volatile KGB_ACC_T* partial = (volatile KGB_ACC_T*)((char*)p.ws + 64);
+#ifdef KGB_HAS_RED2
+    KGB_ACC2_T v2 = kgb_block_fold2(acc2[0], sh2);
+    // second partial array sits behind the first one (the host sizes the workspace for both)
+    volatile KGB_ACC2_T* partial2 = (volatile KGB_ACC2_T*)((char*)p.ws + 64 + (((size_t)gridDim.x * sizeof(KGB_ACC_T) + 63) / 64) * 64);
+#endif
     if (threadIdx.x == 0) {
         partial[blockIdx.x] = v;
+#ifdef KGB_HAS_RED2
+        partial2[blockIdx.x] = v2;
+#endif
         __threadfence();
         const u32 tk = atomicAdd(ticket, 1u);
         is_last = (tk == gridDim.x - 1);
@@ -322,8 +373,20 @@ template <int V> __device__ __forceinline__ void kgb_reduce_body(const KgbParams
         }
         __syncthreads();
         a = kgb_block_fold(a, sh);
+#ifdef KGB_HAS_RED2
+        KGB_ACC2_T a2 = (KGB_ACC2_T)(KGB_RED2_IDENT);
+        for (u32 b = threadIdx.x; b < gridDim.x; b += KGB_BLOCK) {
+            KGB_ACC2_T o = partial2[b];
+            a2 = KGB_RED2(a2, o);
+        }
+        __syncthreads();
+        a2 = kgb_block_fold2(a2, sh2);
+#endif
         if (threadIdx.x == 0) {
             *(KGB_OUT_T*)p.out = (KGB_OUT_T)a;
+#ifdef KGB_HAS_RED2
+            *(KGB_ACC2_T*)((char*)p.out + 8) = a2;  // second result in the next 8-byte slot
+#endif
             *ticket = 0u;
         }
     }

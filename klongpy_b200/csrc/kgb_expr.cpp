@@ -459,6 +459,7 @@ struct kgb_expr {
     CUfunction fn_p = nullptr;
     int pipe_threads = 256, pipe_stages = 7, pipe_load = 2, pipe_park = 4, pipe_lw = 2, pipe_lbw = 1;
     int pipe_ctas_per_sm = 1;
+    bool has_red2 = false;          // two-output reduce (second result at out + 8 bytes)
 };
 
 namespace kgb {
@@ -582,6 +583,18 @@ static int build_source(kgb_expr* h, const int32_t* code, int n_code, const int3
     m << "\n#define KGB_EVAL(j) (" << cast(v, h->mode == KGB_MODE_MAP ? h->out_dtype : h->acc_dtype) << ")\n";
     if (h->mode != KGB_MODE_MAP) {
         m << fold_macro("KGB_RED", h->red_op) << fold_ident("KGB_RED_IDENT", h->red_op, h->acc_dtype);
+    }
+    if (h->mode == KGB_MODE_REDUCE && code2 && n_code2 > 0) {
+        // two-output reduce: a second expression over the same arguments folded with red_op2 in the same pass
+        Val vb;
+        if (!gen_expr(code2, n_code2, h->args, false, 0, &vb)) return KGB_EINVAL;
+        h->acc2_dtype = fold_acc_type(vb.t.dt, h->red_op2);
+        if (dtype_size(h->acc_dtype) != 8 || dtype_size(h->acc2_dtype) != 8)
+            return set_error("two-output reduce needs 8-byte accumulators"), KGB_EINVAL;
+        h->has_red2 = true;
+        m << "#define KGB_HAS_RED2 1\n#define KGB_ACC2_T " << ctype(h->acc2_dtype) << "\n";
+        m << "#define KGB_EVALB(j) (" << cast(vb, h->acc2_dtype) << ")\n";
+        m << fold_macro("KGB_RED2", h->red_op2) << fold_ident("KGB_RED2_IDENT", h->red_op2, h->acc2_dtype);
     }
     if (h->mode == KGB_MODE_SCAN && code2 && n_code2 > 0) {
         // optional seed program over scalar arguments only (multi-GPU scans pass the shard's exclusive offset)
@@ -784,7 +797,9 @@ extern "C" int kgb_expr_workspace_bytes(const kgb_expr* h, int64_t n, size_t* ou
     KGB_REQUIRE(h && out_bytes && n >= 0, "kgb_expr_workspace_bytes: bad arguments");
     size_t b = 0;
     if (h->mode == KGB_MODE_REDUCE) {
-        b = 64 + (size_t)sm_count() * std::max(h->occ_v, h->occ_s) * dtype_size(h->acc_dtype);
+        const size_t parts = (size_t)sm_count() * std::max(h->occ_v, h->occ_s);
+        b = 64 + align_up(parts * dtype_size(h->acc_dtype), 64);
+        if (h->has_red2) b += align_up(parts * dtype_size(h->acc2_dtype), 64);
     } else if (h->mode == KGB_MODE_SCAN || h->mode == KGB_MODE_SCANRED) {
         const long long tl = std::min(scan_tile(h), kPipeTile);
         const size_t tiles = (size_t)((n + tl - 1) / tl);
@@ -862,5 +877,6 @@ extern "C" int kgb_expr_launch(kgb_expr* h, const void* const* args, int64_t n, 
     return KGB_OK;
 }
 
+extern "C" int kgb_expr_out_dtype2(const kgb_expr* h) { return (h && h->has_red2) ? h->acc2_dtype : -1; }
 extern "C" const char* kgb_expr_source(const kgb_expr* h) { return h ? h->source.c_str() : ""; }
 extern "C" const char* kgb_expr_kernel_name(const kgb_expr* h) { return h ? h->name_v.c_str() : ""; }

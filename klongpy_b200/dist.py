@@ -60,6 +60,38 @@ def combine_partials(part, red):
     return ops.run([ops.OP_ARG, 0], [_gather_scalars(part)], mode=_lib.MODE_REDUCE, red=red)
 
 
+def sharded_reduce_with_total(code, red, args, scan_code, scan_red):
+    """One pass over the shard for BOTH the fold of `code` and the shard total of `scan_code` (what a following
+    sharded_scan needs for its carried offset): returns (global fold replicated on every rank, this rank's exclusive
+    scan offset or None on rank 0).  Saves the separate 8 B/elem reduce pass of `shard_offset`, so a reduce + scan
+    step stays at 24 B/elem per rank for any number of ranks."""
+    red = ops.RED[red] if not isinstance(red, int) else red
+    scan_red = ops.RED[scan_red] if not isinstance(scan_red, int) else scan_red
+    part, total = ops.reduce2(code, red, scan_code, scan_red, args)
+    if world() == 1:
+        return part, None
+    w = world()
+    # one all_gather of the 16-byte pair {partial fold, shard total} (raw bytes: the two may differ in dtype)
+    pair = torch.cat([part._t.reshape(1).view(torch.uint8), total._t.reshape(1).view(torch.uint8)])
+    allp = torch.empty(16 * w, dtype=torch.uint8, device=pair.device)
+    td.all_gather_into_tensor(allp, pair)
+    allp = allp.reshape(w, 16)
+    parts = DeviceArray(allp[:, :8].contiguous().view(part._t.dtype).reshape(w))
+    totals = DeviceArray(allp[:, 8:].contiguous().view(total._t.dtype).reshape(w))
+    fold = ops.run([ops.OP_ARG, 0], [parts], mode=_lib.MODE_REDUCE, red=red)
+    r = rank()
+    off = None if r == 0 else ops.run([ops.OP_ARG, 0], [DeviceArray(totals._t[:r])], mode=_lib.MODE_REDUCE, red=scan_red)
+    return fold, off
+
+
+def sharded_scan_with_offset(code, args, red, off):
+    """Local scan seeded with a precomputed exclusive offset (from sharded_reduce_with_total)."""
+    red = ops.RED[red] if not isinstance(red, int) else red
+    if off is None:
+        return ops.run(code, args, mode=_lib.MODE_SCAN, red=red)
+    return ops.run(code, list(args) + [off], mode=_lib.MODE_SCAN, red=red, code2=[ops.OP_ARG, len(args)])
+
+
 def shard_offset(code, args, red):
     """Exclusive fold over all lower ranks of the per-rank totals: the offset this shard's scan carries.
     Returns (offset 0-d DeviceArray or None on rank 0, totals)."""

@@ -96,11 +96,13 @@ class _Emitter:
 
 
 class Stage:
-    __slots__ = ("mode", "red", "red2", "code", "code2", "slots", "out_slot")
+    __slots__ = ("mode", "red", "red2", "code", "code2", "slots", "out_slot", "pair", "paired_with")
 
     def __init__(self, mode, red, red2, code, code2, slots, out_slot):
         self.mode, self.red, self.red2 = mode, red, red2
         self.code, self.code2, self.slots, self.out_slot = tuple(code), tuple(code2) if code2 else None, slots, out_slot
+        self.pair = None         # (second stage, its code re-indexed onto the merged slot list, merged slots)
+        self.paired_with = None  # set on the second stage of a pair
 
 
 class Plan:
@@ -117,6 +119,37 @@ class Plan:
             self.result_slot = em.slots[0]  # the tree's root was itself a stage
         else:
             self.result_slot = self._add_stage(_lib.MODE_MAP, 0, 0, em.code, None, em.slots)
+        self._pair_reductions()
+
+    def _pair_reductions(self):
+        """Two reductions that read only call arguments (`(+/p*s)%+/s`, VWAP) become ONE two-output reduce kernel:
+        the shared operands stream from HBM once.  The pairing is undone at call time if the operands turn out to
+        have different lengths or a narrow accumulator (make_callable)."""
+        n_params = len(self.params)
+        reds = [st for st in self.stages if st.mode == _lib.MODE_REDUCE and st.pair is None and
+                all(sl < n_params for sl in st.slots)]
+        for a, b in zip(reds[0::2], reds[1::2]):
+            slots = list(a.slots)
+            remap = {}
+            for j, sl in enumerate(b.slots):
+                if sl not in slots:
+                    slots.append(sl)
+                remap[j] = slots.index(sl)
+            code_b, i = [], 0
+            cb = list(b.code)
+            while i < len(cb):
+                w = cb[i]
+                if w == ops.OP_ARG:
+                    code_b += [ops.OP_ARG, remap[cb[i + 1]]]
+                    i += 2
+                elif w in (ops.OP_LIT_I64, ops.OP_LIT_F64):
+                    code_b += cb[i:i + 3]
+                    i += 3
+                else:
+                    code_b.append(w)
+                    i += 1
+            a.pair = (b, tuple(code_b), slots)
+            b.paired_with = a
 
     def _add_stage(self, mode, red, red2, code, code2, slots):
         slot = self.n_slots
@@ -210,6 +243,19 @@ def make_callable(ir):
         if not any_dev:
             raise NotImplementedError("no device operand: scalar expressions stay in the interpreter")
         for st in plan.stages:
+            if vals[st.out_slot] is not None:
+                continue  # second half of a pair, already produced by the two-output kernel
+            if st.pair is not None:
+                other, code_b, slots = st.pair
+                pargs = [vals[s] for s in slots]
+                lens = {a._t.numel() for a in pargs if _is_arraylike(a)}
+                grad = any(isinstance(a, DeviceArray) and a._t.requires_grad for a in pargs)
+                if len(lens) == 1 and 0 not in lens and not grad:
+                    try:
+                        vals[st.out_slot], vals[other.out_slot] = ops.reduce2(st.code, st.red, code_b, other.red, pargs)
+                        continue
+                    except _lib.KgbError:
+                        pass  # e.g. a narrow accumulator: run the two reductions separately
             sargs = [vals[s] for s in st.slots]
             has_array = any(_is_arraylike(a) for a in sargs)
             if st.mode != _lib.MODE_MAP and not has_array:

@@ -216,6 +216,55 @@ def run(code, args, mode=_lib.MODE_MAP, red=0, code2=None, red2=0, out_shape=Non
     return out
 
 
+def reduce2(code, red, code2, red2, args):
+    """Two folds over the same arguments in ONE pass (kgb200.h: KGB_MODE_REDUCE with a second program).
+    Returns two 0-d DeviceArrays.  Both accumulators must be 8 bytes wide (float64 / int64)."""
+    device = None
+    n = None
+    for a in args:
+        if isinstance(a, DeviceArray):
+            if a._t.requires_grad and torch.is_grad_enabled():
+                raise NotImplementedError("two-output reduce is not on the autograd tape")
+            device = a._t.device
+            if a._t.dim() > 0:
+                m = a._t.numel()
+                if a._t.dim() != 1 or (n is not None and m != n):
+                    raise ValueError("reduce2: operands must be 1-d arrays of one length")
+                n = m
+    if device is None or n is None or n == 0:
+        raise ValueError("reduce2 needs a non-empty device array operand")
+    red = RED[red] if not isinstance(red, int) else red
+    red2 = RED[red2] if not isinstance(red2, int) else red2
+    lib, stream = _lib_for(device)
+    cls = [_classify(a, device) for a in args]
+    kinds, dts = tuple(c[0] for c in cls), tuple(c[1] for c in cls)
+    code_t, code2_t = tuple(code), tuple(code2)
+    key = (device.index, code_t, code2_t, kinds, dts, _lib.MODE_REDUCE, red, red2, "reduce2")
+    ent = _handles.get(key)
+    if ent is None:
+        n_args = len(args)
+        h = ctypes.c_void_p()
+        od = ctypes.c_int32()
+        _lib.check(lib.kgb_expr_compile((ctypes.c_int32 * len(code_t))(*code_t), len(code_t),
+                                        (ctypes.c_int32 * len(code2_t))(*code2_t), len(code2_t),
+                                        (ctypes.c_int32 * max(n_args, 1))(*kinds), (ctypes.c_int32 * max(n_args, 1))(*dts),
+                                        n_args, _lib.MODE_REDUCE, red, red2, ctypes.byref(h), ctypes.byref(od)),
+                   "kgb_expr_compile")
+        od2 = lib.kgb_expr_out_dtype2(h)
+        if od2 < 0:
+            raise _lib.KgbError("kgb_expr_compile did not produce a two-output reduce")
+        ent = (h, od.value, od2)
+        _handles[key] = ent
+    h, od, od2 = ent
+    buf = torch.empty(16, dtype=torch.uint8, device=device)
+    wsb = ctypes.c_size_t()
+    _lib.check(lib.kgb_expr_workspace_bytes(h, n, ctypes.byref(wsb)), "kgb_expr_workspace_bytes")
+    ws = torch.empty(max(wsb.value, 64), dtype=torch.uint8, device=device)
+    argv = (ctypes.c_void_p * max(len(args), 1))(*[c[3] for c in cls])
+    _lib.check(lib.kgb_expr_launch(h, argv, n, buf.data_ptr(), ws.data_ptr(), wsb.value, stream), "kgb_expr_launch")
+    return DeviceArray(buf[:8].view(_K2T[od]).reshape(())), DeviceArray(buf[8:].view(_K2T[od2]).reshape(()))
+
+
 def empty_fold(code, args, red):
     """Identity of an add / multiply fold over zero elements, in the dtype the expression would produce."""
     m = run(code, args)  # zero-length MAP launch: compiles, allocates, launches nothing

@@ -187,6 +187,11 @@ class _Expr:
         if mode != 0:
             dt = _fold_dtype(dt, red)
         self.acc = dt
+        self.out2 = None
+        if mode == 1 and code2:
+            r2 = np.asarray(run_program(code2, dummy))
+            d2 = _fold_dtype(r2.dtype, red2)
+            self.out2 = d2 if d2 in _CODE else (np.dtype(np.int64) if d2.kind in "iu" else np.dtype(np.float64))
         if mode == 3:
             r2 = np.asarray(run_program(code2, dummy, scanval=np.ones(1, dtype=dt)))
             dt = _fold_dtype(r2.dtype, red2)
@@ -223,6 +228,10 @@ class FakeLib:
         od._obj.value = _CODE[e.out]
         return 0
 
+    def kgb_expr_out_dtype2(self, h):
+        e = self.exprs[_addr(h) - 1]
+        return -1 if e.out2 is None else _CODE[e.out2]
+
     def kgb_expr_workspace_bytes(self, h, n, out):
         out._obj.value = 64
         return 0
@@ -248,6 +257,9 @@ class FakeLib:
                 v = np.broadcast_to(np.asarray(v), (n,)).astype(e.acc)
                 if e.mode == 1:
                     view(out, 1, _CODE[e.out])[0] = _RED[e.red].reduce(v)
+                    if e.out2 is not None:
+                        vb = np.broadcast_to(np.asarray(run_program(e.code2, args)), (n,)).astype(e.out2)
+                        view(_addr(out) + 8, 1, _CODE[e.out2])[0] = _RED[e.red2].reduce(vb)
                 elif e.mode == 2:
                     if e.code2:
                         v = v.copy()

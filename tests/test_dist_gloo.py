@@ -47,6 +47,11 @@ def _worker(rank, world, port, q):
         assert np.array_equal(s, np.maximum.accumulate(i)[lo:hi]), rank
         s = dist.sharded_scan([ops.OP_ARG, 0], [I], "+").to_numpy()
         assert np.array_equal(s, np.cumsum(i)[lo:hi]), rank
+        # fused pass: global fold of one expression + this shard's scan offset from the SAME read of the shard
+        fold, off = dist.sharded_reduce_with_total(code, "+", [X], [ops.OP_ARG, 0], "+")
+        assert fold.item() == np.add.reduce(((x * 2) + 1) ** 2), rank
+        s = dist.sharded_scan_with_offset([ops.OP_ARG, 0], [X], "+", off).to_numpy()
+        assert np.array_equal(s, np.cumsum(x)[lo:hi]), rank
         G = 37
         k = rng.integers(0, G, n)
         v = np.round(rng.normal(10, 15, n), 1)

@@ -504,3 +504,23 @@ def test_full_size_grade_group_1e8(be, K):
     assert K.array_equal(heads, K.iota(10_000))                                                      # ascending key order
     sizes = DeviceArray(starts.tensor[1:]) - DeviceArray(starts.tensor[:-1])
     assert K.reduce("add", sizes).item() == n and K.reduce("min", sizes).item() > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [1, 1000, 100_003, 3_000_001])
+def test_two_output_reduce_and_vwap(be, K, n):
+    """`(+/p*s)%+/s` (examples/bench_compiler.kg VWAP): both sums from ONE pass over p and s, through the compiled IR
+    and through ops.reduce2 directly; exact on dyadic prices and integer sizes."""
+    rng = np.random.default_rng(n + 77)
+    p = rng.integers(0, 4096, n) / 64.0
+    s = rng.integers(100, 10_000, n)
+    P, S = dev(be, p), dev(be, s)
+    a, b = K.reduce2([K.OP_ARG, 0, K.OP_ARG, 1, K.OPC["mul"]], "+", [K.OP_ARG, 1], "+", [P, S])
+    assert a.item() == np.add.reduce(p * s) and b.item() == np.add.reduce(s)
+    assert host(a).dtype == np.float64 and host(b).dtype == np.int64
+    ir = ("binop", "%", ("reduce", "+", ("binop", "*", ("var", "_v0"), ("var", "_v1"))), ("reduce", "+", ("var", "_v1")))
+    fn, _ = be.compile_expr_ir(ir, ["p", "s"])
+    assert any(st.pair is not None for st in fn.plan.stages)  # the two reductions were paired
+    assert fn(P, S).item() == O.eval_ir(ir, {"_v0": p, "_v1": s})
+    mx, mn = K.reduce2([K.OP_ARG, 0], "|", [K.OP_ARG, 0], "&", [P])
+    assert mx.item() == p.max() and mn.item() == p.min()
