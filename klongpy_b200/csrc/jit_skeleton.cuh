@@ -882,7 +882,6 @@ extern "C" __global__ void __launch_bounds__(KGB_PT + 32 * KGB_PLW, KGB_PMINB) K
     // ==================================================================== compute warps (tid < KGB_PT)
 #if KGB_MODE == 2
     KGB_OUT_T* __restrict__ out = (KGB_OUT_T*)p.out;
-    const bool out_al32 = (reinterpret_cast<unsigned long long>(p.out) & 31ull) == 0;
 #else
     // mode 3: the epilogue g(scan value, args[i]) is folded into one accumulator per thread across all of the
     // CTA's tiles; one partial per CTA at the end (max/min/int folds are order-independent; a float sum here is
@@ -927,35 +926,23 @@ extern "C" __global__ void __launch_bounds__(KGB_PT + 32 * KGB_PLW, KGB_PMINB) K
         const i64 base = (i64)t * KGB_PTILE;
         const bool full = (base + KGB_PTILE <= n);
 #if KGB_MODE == 2
-        if (full && out_al32) {
-            // two adjacent 16-byte chunks per step -> one 256-bit streaming store (the chunk pairs of a quarter-warp
-            // cover an (even, odd) row pair, whose swizzled bank groups are disjoint: still conflict-free)
+        // NOTE the chunk a thread reads here is exactly the chunk the same thread's cp.async overwrites when the stage
+        // is reused (issue_load uses the same h * KGB_PT + tid mapping): that is what makes the stage hand-over safe
+        // without another barrier.  A 256-bit store variant (two adjacent chunks per thread) broke this invariant
+        // and raced with the prefetch; it bought no bandwidth either, so stores stay 128-bit.
 #pragma unroll
-            for (int h = 0; h < KGB_PCT / 2; h++) {
-                const int cf = (h * KGB_PT + tid) * 2;
-                KGB_ACC_T v[4];
-                *reinterpret_cast<uint4*>(&v[0]) = *reinterpret_cast<const uint4*>(sb + kgb_swz(cf / KGB_PCR, cf % KGB_PCR));
-                *reinterpret_cast<uint4*>(&v[2]) = *reinterpret_cast<const uint4*>(sb + kgb_swz((cf + 1) / KGB_PCR, (cf + 1) % KGB_PCR));
-                KGB_OUT_T o[4];
-#pragma unroll
-                for (int j = 0; j < 4; j++) o[j] = (KGB_OUT_T)(KGB_RED(excl, v[j]));
-                kgb_stv<KGB_OUT_T, 4>(out + base + cf * 2, o);
-            }
-        } else {
-#pragma unroll
-            for (int h = 0; h < KGB_PCT; h++) {
-                const int cf = h * KGB_PT + tid;
-                KGB_ACC_T v[2];
-                *reinterpret_cast<uint4*>(v) = *reinterpret_cast<const uint4*>(sb + kgb_swz(cf / KGB_PCR, cf % KGB_PCR));
-                KGB_OUT_T o[2];
-                o[0] = (KGB_OUT_T)(KGB_RED(excl, v[0]));
-                o[1] = (KGB_OUT_T)(KGB_RED(excl, v[1]));
-                if (full) {
-                    kgb_stv<KGB_OUT_T, 2>(out + base + cf * 2, o);
-                } else {
-                    if (base + cf * 2 < n) out[base + cf * 2] = o[0];
-                    if (base + cf * 2 + 1 < n) out[base + cf * 2 + 1] = o[1];
-                }
+        for (int h = 0; h < KGB_PCT; h++) {
+            const int cf = h * KGB_PT + tid;
+            KGB_ACC_T v[2];
+            *reinterpret_cast<uint4*>(v) = *reinterpret_cast<const uint4*>(sb + kgb_swz(cf / KGB_PCR, cf % KGB_PCR));
+            KGB_OUT_T o[2];
+            o[0] = (KGB_OUT_T)(KGB_RED(excl, v[0]));
+            o[1] = (KGB_OUT_T)(KGB_RED(excl, v[1]));
+            if (full) {
+                kgb_stv<KGB_OUT_T, 2>(out + base + cf * 2, o);
+            } else {
+                if (base + cf * 2 < n) out[base + cf * 2] = o[0];
+                if (base + cf * 2 + 1 < n) out[base + cf * 2 + 1] = o[1];
             }
         }
 #else

@@ -31,6 +31,9 @@ for n in (1000, 1_000_003, 40_000_001):
     s = dist.sharded_scan([ops.OP_ARG, 0], [X], "+").to_numpy()
     sref = np.cumsum(x)[lo:hi]
     mx = dist.sharded_scan([ops.OP_ARG, 0], [X], "|").to_numpy()
+    fold, off = dist.sharded_reduce_with_total(red, "+", [X], [ops.OP_ARG, 0], "+")   # fused pass (two-output reduce)
+    s2 = dist.sharded_scan_with_offset([ops.OP_ARG, 0], [X], "+", off).to_numpy()
+    assert fold.item() == ref and np.array_equal(s2, sref), "fused reduce+total path"
     G = 1000
     k = rng.integers(0, G, n)
     v = np.round(rng.normal(10, 15, n), 1)

@@ -524,3 +524,25 @@ def test_two_output_reduce_and_vwap(be, K, n):
     assert fn(P, S).item() == O.eval_ir(ir, {"_v0": p, "_v1": s})
     mx, mn = K.reduce2([K.OP_ARG, 0], "|", [K.OP_ARG, 0], "&", [P])
     assert mx.item() == p.max() and mn.item() == p.min()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [2_500_000, 20_000_001])
+def test_pipelined_scan_with_carried_seed(be, K, n):
+    """The persistent pipelined scan (>= 4 tiles per SM) with the exclusive offset a shard / chunk carries
+    (dist.sharded_scan, stream.HostStream): bit-exact on dyadic data, repeated to give a race a chance to show."""
+    import torch
+    from klongpy_b200 import _lib
+    rng = np.random.default_rng(n)
+    k = rng.integers(0, 256, n)
+    x = dev(be, k / 256.0)
+    from klongpy_b200 import DeviceArray
+    seed = DeviceArray(torch.tensor(12345.5, dtype=torch.float64, device="cuda:0"))  # 0-d device scalar
+    ref = np.cumsum(k) / 256.0 + 12345.5
+    for _ in range(5):
+        s = K.run([K.OP_ARG, 0], [x, seed], mode=_lib.MODE_SCAN, red=_lib.RED_ADD, code2=[K.OP_ARG, 1])
+        assert np.array_equal(host(s), ref)
+    i = dev(be, k)
+    for _ in range(3):
+        assert np.array_equal(host(K.scan("add", i)), np.cumsum(k))
+        assert np.array_equal(host(K.scan("max", x)), np.maximum.accumulate(k / 256.0))
