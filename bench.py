@@ -33,6 +33,17 @@ UNIT = "elements/s"
 WORKLOAD = "config2: fused reduce {+/((x*2)+1)^2} + running sum +\\x over float64"
 
 
+def scan_traffic(n):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu --set full capture
+    (profiles/r01_scan_traffic.json), per launch; only quoted when it was captured at this problem size."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_scan_traffic.json")) as f:
+            d = json.load(f)
+        return float(d["traffic_bytes"]) if int(d["n_elements"]) == int(n) else None
+    except Exception:
+        return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -324,7 +335,7 @@ def main():
                        "l2": "inputs (8 GB/GPU) are larger than L2; no flush needed",
                        "exchange": "none" if world == 1 else "one all_gather of 16 B per rank: {partial fold, shard total}; the scan carries the exclusive offset"},
             "roofline": {"bound": "hbm", "achieved": 16.0 * n / (scan_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": 16.0 * n / (scan_ms * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "kgb_scan_*_p (running sum +\\x, persistent pipelined scan)",
+                         "frac": 16.0 * n / (scan_ms * 1e-3) / 1e9 / peak, "traffic": scan_traffic(n), "kernel": "kgb_scan_*_p (running sum +\\x, persistent pipelined scan)",
                          "algorithmic_bytes_per_launch": 16 * n, "ms_per_launch": scan_ms, "peak_source": peak_src},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": per_step_launches * args.steps, "clocks": clocks,
             "primitives": prims,

@@ -29,6 +29,17 @@ for step in "$@"; do
         ncu -i $rep --page source --csv > $out/${tag}_source_$only.csv 2>/dev/null; gzip -f $out/${tag}_source_$only.csv
         sz=$(du -m $rep | cut -f1); if [ "$sz" -gt 12 ]; then rm -f $rep; fi
       fi ;;
+    traffic)
+      # DRAM bytes of the dominant kernel (the 1e9-element running sum of bench.py) from one ncu --set full capture
+      python bench.py --steps 2 --warmup 3 --no-e2e --no-primitives > $out/${tag}_traffic_plain.log 2>&1 && \
+      ncu --set full --clock-control none --import-source on -k regex:kgb_scan -s 3 -c 1 -o $out/${tag}_prof_bench_scan \
+        python bench.py --steps 2 --warmup 3 --no-e2e --no-primitives > $out/${tag}_traffic_ncu.log 2>&1; echo "traffic exit=$?"
+      rep=$out/${tag}_prof_bench_scan.ncu-rep
+      if [ -f $rep ]; then
+        ncu -i $rep --page raw --csv > $out/${tag}_raw_bench_scan.csv 2>/dev/null
+        ncu -i $rep --page source --csv > $out/${tag}_source_bench_scan.csv 2>/dev/null; gzip -f $out/${tag}_source_bench_scan.csv
+        sz=$(du -m $rep | cut -f1); if [ "$sz" -gt 12 ]; then rm -f $rep; fi
+      fi ;;
     firstlight)
       timeout 900 python scripts/gpu_first_light.py --perf > $out/${tag}_first_light.log 2>&1; echo "firstlight exit=$?"; grep -E "perf|FAIL" $out/${tag}_first_light.log ;;
     *) echo "unknown step $step" ;;
