@@ -403,6 +403,44 @@ def primitive_table(be, ops, dist, time_kernel, dev, peak, world, rank):
         tp_b = DeviceArray(torch.randn(nb, dtype=torch.float64, device=dev, generator=g))
         out["grouped_min_mean_max_10k_1e9"] = prim_row(nb, time_kernel(lambda: ops.groupagg(st_b, tp_b, 10_000), 3), 16, peak)
         del st_b, tp_b
+    # config 1: examples/bench_compiler.kg expressions at the file's own size (100 K float64): µs per call through the
+    # compiled callable (1000 back-to-back calls, one sync), next to the reference's NumPy codegen on this box's CPU
+    import time as _time
+    from oracle import kg_oracle as O
+    rngc = np.random.default_rng(0)
+    hc = {k: rngc.random(100_000) for k in ("a", "b", "c")}
+    dc = {k: be.kg_asarray(v) for k, v in hc.items()}
+    V = lambda k: ("var", k)  # noqa: E731
+    exprs = {
+        "a+b": (("binop", "+", V("_v0"), V("_v1")), ["a", "b"]),
+        "a*2+b": (("binop", "*", V("_v0"), ("binop", "+", ("literal", 2), V("_v1"))), ["a", "b"]),
+        "(a+b)*(a-b)": (("binop", "*", ("binop", "+", V("_v0"), V("_v1")), ("binop", "-", V("_v0"), V("_v1"))), ["a", "b"]),
+        "+/a": (("reduce", "+", V("_v0")), ["a"]),
+        "+/a*b": (("reduce", "+", ("binop", "*", V("_v0"), V("_v1"))), ["a", "b"]),
+        "+\\a": (("scan", "+", V("_v0")), ["a"]),
+        "|/(|\\a)-a": (("reduce", "|", ("binop", "-", ("scan", "|", V("_v0")), V("_v0"))), ["a"]),
+        "(+/a*b)%+/b": (("binop", "%", ("reduce", "+", ("binop", "*", V("_v0"), V("_v1"))), ("reduce", "+", V("_v1"))), ["a", "b"]),
+    }
+    cfg1 = {}
+    for name, (ir, params) in exprs.items():
+        fnc, _ = be.compile_expr_ir(ir, params)
+        dargs = [dc[k] for k in params]
+        for _ in range(20):
+            fnc(*dargs)
+        torch.cuda.synchronize()
+        t0 = _time.perf_counter()
+        for _ in range(1000):
+            fnc(*dargs)
+        torch.cuda.synchronize()
+        us = (_time.perf_counter() - t0) * 1e3
+        env = {f"_v{i}": hc[k] for i, k in enumerate(params)}
+        O.eval_ir(ir, env)
+        t0 = _time.perf_counter()
+        for _ in range(50):
+            O.eval_ir(ir, env)
+        cfg1[name] = {"us_per_call": us, "numpy_us_per_call": (_time.perf_counter() - t0) / 50 * 1e6}
+    out["config1_bench_compiler_100k"] = cfg1
+    del dc
     # config 5: autograd at a 1e7-element batch (fused forward + fused backward kernels, float64)
     m = 10_000_000
     X = DeviceArray(torch.rand(m, dtype=torch.float64, device=dev, generator=g) * 2)
