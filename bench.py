@@ -402,7 +402,14 @@ def primitive_table(be, ops, dist, time_kernel, dev, peak, world, rank):
         st_b = DeviceArray(torch.randint(0, 10_000, (nb,), dtype=torch.int64, device=dev, generator=g))
         tp_b = DeviceArray(torch.randn(nb, dtype=torch.float64, device=dev, generator=g))
         out["grouped_min_mean_max_10k_1e9"] = prim_row(nb, time_kernel(lambda: ops.groupagg(st_b, tp_b, 10_000), 3), 16, peak)
-        del st_b, tp_b
+        del tp_b
+        # config 3 at its upper size: 1e9 int64 keys
+        out["group_10k_1e9"] = prim_row(nb, time_kernel(lambda: ops.group(st_b), 2), 16, peak)
+        del st_b
+        kp = DeviceArray(torch.randperm(nb, device=dev, generator=g))
+        out["grade_up_perm_1e9"] = prim_row(nb, time_kernel(lambda: ops.argsort(kp), 2), 16, peak,
+                                            model_bytes_per_elem=8 + 24 * 4 - 4 + 4, passes=4)
+        del kp
     # config 1: examples/bench_compiler.kg expressions at the file's own size (100 K float64): µs per call through the
     # compiled callable (1000 back-to-back calls, one sync), next to the reference's NumPy codegen on this box's CPU
     import time as _time

@@ -358,13 +358,21 @@ __global__ void __launch_bounds__(ST, 2) onesweep_pass(const typename KeyCodec<D
 //     critical path, with two tile periods of slack.
 // Tiles come from the per-pass atomic ticket (no co-residency assumption).  64-bit key types only; the first pass
 // needs 16-byte aligned caller keys (else the one-tile-per-CTA kernel above runs).
-constexpr int PT = 512, PLT = 256, PNS = 4, PP = 1, PD = 2, PRING = 8;
+#ifndef KGB_SORT_PT
+#define KGB_SORT_PT 512   // compute threads
+#define KGB_SORT_PSI 8    // keys per compute thread (even)
+#define KGB_SORT_PD 2     // tiles parked while their look-back runs
+#endif
+constexpr int PT = KGB_SORT_PT, PLT = 256, PP = 1, PD = KGB_SORT_PD, PNS = PP + PD + 1, PRING = 8;
+constexpr int PSI = KGB_SORT_PSI;
+constexpr int PTILE = PT * PSI;  // keys per tile of the pipelined pass
+static_assert(PT + PLT <= 1024 && PSI % 2 == 0, "pipelined pass geometry");
 constexpr u32 NO_TILE = 0xffffffffu;
 static_assert(PNS == PP + PD + 1, "stage count");
 
 struct PipeSmem {
-    u64 keys[PNS][STILE];
-    u32 idx[PNS][STILE];
+    u64 keys[PNS][PTILE];
+    u32 idx[PNS][PTILE];
     u32 whist[PT / 32][RADIX];
     uint2 cntd[PNS][RADIX];  // {tile count of the digit, exclusive digit offset inside the tile}
     i64 gbase[PNS][RADIX];   // global position of tile-sorted slot p with digit d is gbase[d] + p
@@ -402,6 +410,9 @@ __device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, %0;" ::"n"(PT) : "memory"); }
 
 template <int DT>
@@ -425,7 +436,7 @@ __global__ void __launch_bounds__(PT + PLT, 1) onesweep_pass_p(const typename Ke
     u32* dst_idx = plan->dst[pass] ? idxB : idxA;
     const u32 epoch = (u32)pass + 1;
     const int shift = 8 * pass;
-    const u32 ntiles = (u32)((n + STILE - 1) / STILE);
+    const u32 ntiles = (u32)((n + PTILE - 1) / PTILE);
     u32* ticket = &tickets[pass];
 
     if (tid == 0) {
@@ -491,23 +502,23 @@ __global__ void __launch_bounds__(PT + PLT, 1) onesweep_pass_p(const typename Ke
         const u32 t = sm.tile_ring[li % PRING];
         if (t < ntiles) {
             const u32 st = li % PNS;
-            const i64 base = (i64)t * STILE;
-            if (base + STILE <= n && src_aligned) {
+            const i64 base = (i64)t * PTILE;
+            if (base + PTILE <= n && src_aligned) {
 #pragma unroll
-                for (int h = 0; h < STILE / 2 / PT; h++) {
+                for (int h = 0; h < PTILE / 2 / PT; h++) {
                     const int cf = h * PT + tid;
                     cp_async16(&sm.keys[st][cf * 2], src_keys + base + cf * 2);
                 }
                 if (!first) {
 #pragma unroll
-                    for (int h = 0; h < STILE / 4 / PT; h++) {
+                    for (int h = 0; h < PTILE / 2 / PT; h++) {
                         const int cf = h * PT + tid;
-                        cp_async16(&sm.idx[st][cf * 4], src_idx + base + cf * 4);
+                        cp_async8(&sm.idx[st][cf * 2], src_idx + base + cf * 2);
                     }
                 }
             } else {  // ragged last tile (or unaligned caller keys): guarded loads
 #pragma unroll
-                for (int k = 0; k < SI; k++) {
+                for (int k = 0; k < PSI; k++) {
                     const int slot = k * PT + tid;
                     if (base + slot < n) {
                         sm.keys[st][slot] = src_keys[base + slot];
@@ -522,10 +533,10 @@ __global__ void __launch_bounds__(PT + PLT, 1) onesweep_pass_p(const typename Ke
     auto write_out = [&](u32 li, u32 t) {
         const u32 st = li % PNS;
         mbar_wait(&sm.gb_bar[st], (li / PNS) & 1u);
-        const i64 base = (i64)t * STILE;
-        const int tile_n = (int)((n - base) < (i64)STILE ? (n - base) : (i64)STILE);
+        const i64 base = (i64)t * PTILE;
+        const int tile_n = (int)((n - base) < (i64)PTILE ? (n - base) : (i64)PTILE);
 #pragma unroll
-        for (int j = 0; j < SI; j++) {
+        for (int j = 0; j < PSI; j++) {
             const int p = j * PT + tid;
             if (p < tile_n) {
                 const u64 kk = sm.keys[st][p];
@@ -561,15 +572,15 @@ __global__ void __launch_bounds__(PT + PLT, 1) onesweep_pass_p(const typename Ke
         asm volatile("cp.async.wait_group %0;" ::"n"(PP - 1) : "memory");
         bar_compute();              // A: tile i is in its stage; everybody is past last iteration's write_out
         issue_load(i + PP);         // into the stage the previous iteration's write_out released
-        const i64 base = (i64)tile * STILE;
-        const int tile_n = (int)((n - base) < (i64)STILE ? (n - base) : (i64)STILE);
+        const i64 base = (i64)tile * PTILE;
+        const int tile_n = (int)((n - base) < (i64)PTILE ? (n - base) : (i64)PTILE);
 
         // ---- rank: warp w owns slots [w*256, (w+1)*256), item k of lane l is slot w*256 + k*32 + l
-        u64 key[SI];
-        u32 idx[SI], rank[SI];
-        const int wslot = warp * (SI * 32);
+        u64 key[PSI];
+        u32 idx[PSI], rank[PSI];
+        const int wslot = warp * (PSI * 32);
 #pragma unroll
-        for (int k = 0; k < SI; k++) {
+        for (int k = 0; k < PSI; k++) {
             const int slot = wslot + k * 32 + lane;
             if (slot < tile_n) {
                 const u64 raw = sm.keys[st][slot];
@@ -582,22 +593,22 @@ __global__ void __launch_bounds__(PT + PLT, 1) onesweep_pass_p(const typename Ke
         }
         {
             const u32 lt = (1u << lane) - 1u;
-            u32 peers[SI];
+            u32 peers[PSI];
 #pragma unroll
-            for (int k = 0; k < SI; k++) {
+            for (int k = 0; k < PSI; k++) {
                 const bool valid = (wslot + k * 32 + lane) < tile_n;
                 const u32 d = (u32)(key[k] >> shift) & 255u;
                 peers[k] = digit_peers(d, valid);
             }
 #pragma unroll
-            for (int k = 0; k < SI; k++) {
+            for (int k = 0; k < PSI; k++) {
                 const bool valid = (wslot + k * 32 + lane) < tile_n;
                 const u32 d = (u32)(key[k] >> shift) & 255u;
                 rank[k] = 0;
                 if (valid && lane == __ffs(peers[k]) - 1) rank[k] = atomicAdd(&sm.whist[warp][d], (u32)__popc(peers[k]));
             }
 #pragma unroll
-            for (int k = 0; k < SI; k++)
+            for (int k = 0; k < PSI; k++)
                 rank[k] = __shfl_sync(0xffffffffu, rank[k], __ffs(peers[k]) - 1) + __popc(peers[k] & lt);
         }
         bar_compute();              // B: warp histograms complete; every raw key of the stage has been read
@@ -637,7 +648,7 @@ __global__ void __launch_bounds__(PT + PLT, 1) onesweep_pass_p(const typename Ke
         }
         // ---- scatter into tile-sorted order, into the stage the raw keys came from
 #pragma unroll
-        for (int k = 0; k < SI; k++) {
+        for (int k = 0; k < PSI; k++) {
             if ((wslot + k * 32 + lane) < tile_n) {
                 const u32 d = (u32)(key[k] >> shift) & 255u;
                 const u32 p = sm.cntd[st][d].y + sm.whist[warp][d] + rank[k];
@@ -694,7 +705,9 @@ template <int DT> struct PipeLauncher<DT, true> {
             cudaFuncSetAttribute(onesweep_pass_p<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PipeSmem));
             attr_set[dev] = true;
         }
-        const unsigned grid = tiles < (unsigned)sm_count() ? tiles : (unsigned)sm_count();
+        const unsigned ptiles = (unsigned)((n + PTILE - 1) / PTILE);
+        const unsigned grid = ptiles < (unsigned)sm_count() ? ptiles : (unsigned)sm_count();
+        (void)tiles;
         onesweep_pass_p<DT><<<grid, PT + PLT, sizeof(PipeSmem), st>>>((const T*)keys, w.keys[0], w.keys[1], w.idx[0], w.idx[1],
                                                                       idx_out, (T*)keys_sorted_out, enc_sorted_out, w.plan, p,
                                                                       w.states, w.tickets, n, descending);
