@@ -4,6 +4,7 @@
 // v1: streaming 128-bit loads of both columns; the G x 4 table lives in L2-resident global memory.
 // min/max use order-encoded 64-bit integers with a read-before-update filter (after the first few rows of a
 // station almost no row improves its extremes, so the RED is rarely issued); sum/count are RED.ADD.
+#include <algorithm>
 #include <cstdlib>
 
 #include "kgb_device.cuh"
@@ -86,6 +87,23 @@ __global__ void __launch_bounds__(256) groupagg_kernel(const i64* __restrict__ k
     }
 }
 
+// Filter seeding: the exact extremes of a SAMPLE of the rows (the first `m`) go into the global table before the
+// main kernel starts, and every CTA initialises its shared-memory filters from that table.  Without it each CTA
+// re-learns every station's extremes from scratch — ~ln(rows per station per CTA) record-breaking rows per station
+// per CTA take the exact path (14 % of all rows at 1e8 rows / 10 k stations / 148 CTAs).
+__global__ void __launch_bounds__(256) groupagg_seed_kernel(const i64* __restrict__ keys, const double* __restrict__ vals,
+                                                             i64 m, i64 G, AggWs a) {
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
+        const i64 k = keys[i];
+        if ((u64)k >= (u64)G) continue;  // reported by the main kernel
+        const double v = vals[i];
+        const u64 emin = enc_for_min(v), emax = enc_for_max(v);
+        if (emin < ld_relaxed_u64(&a.tmin[k])) atomicMin(&a.tmin[k], emin);
+        if (emax > ld_relaxed_u64(&a.tmax[k])) atomicMax(&a.tmax[k], emax);
+    }
+}
+
 // v2: per-CTA shared-memory state for everything that does not need a 64-bit float atomic.
 //   cnt[k]        u32 row count of this CTA (native ATOMS.ADD), flushed to the global table at the end
 //   minhi/maxhi   upper 32 bits of the order-encoded running extremes seen by this CTA: a row whose upper half
@@ -107,8 +125,8 @@ __global__ void __launch_bounds__(1024, 1) groupagg_kernel_v2(const i64* __restr
     u32* s_maxhi = s_minhi + G;
     for (i64 i = threadIdx.x; i < G; i += blockDim.x) {
         s_cnt[i] = 0u;
-        s_minhi[i] = 0xffffffffu;
-        s_maxhi[i] = 0u;
+        s_minhi[i] = (u32)(a.tmin[i] >> 32);  // seeded extremes (0xffffffff / 0 where the sample had no row)
+        s_maxhi[i] = (u32)(a.tmax[i] >> 32);
         if (SUM_IN_SMEM) s_sum[i] = 0.0;
     }
     __syncthreads();
@@ -398,6 +416,13 @@ extern "C" int kgb_groupagg_f64(const int64_t* keys, const double* vals, int64_t
             if (pb > sm_count()) pb = sm_count();
             if (pb > AGG_MAX_PARTS) pb = AGG_MAX_PARTS;
             if (pb < 1) pb = 1;
+            // seed the filters from a sample: ~64 rows per station, and only when the run is long enough to pay for it
+            long long seed_rows = 64 * n_groups;
+            if (const char* e = getenv("KGB200_AGG_SEED")) seed_rows = atoll(e);
+            if (seed_rows > 0 && n >= 32 * seed_rows) {
+                const long long sb = std::min<long long>((seed_rows + 255) / 256, (long long)sm_count() * 8);
+                groupagg_seed_kernel<<<(unsigned)sb, 256, 0, st>>>((const i64*)keys, vals, seed_rows, n_groups, a);
+            }
             if (variant == 1)
                 groupagg_kernel_v2<1><<<(unsigned)pb, 1024, smem, st>>>((const i64*)keys, vals, n, n_groups, a, l2_every);
             else if (variant == 2)
