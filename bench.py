@@ -376,11 +376,16 @@ def primitive_table(be, ops, dist, time_kernel, dev, peak, world, rank):
     fn2, _ = be.compile_expr_ir(("reduce", "|", ("binop", "-", ("scan", "|", ("var", "_v0")), ("var", "_v0"))), ["a"])
     out["|/(|\\ts)-ts"] = prim_row(n, time_kernel(lambda: fn2(a), 5), 8, peak,
                                   torch_eager_ms=time_kernel(lambda: (ta.cummax(0).values - ta).amax(0), 5))
-    del b, c
+    del c
     keys_perm = DeviceArray(torch.randperm(n, device=dev, generator=g))
     out["grade_up_perm_1e8"] = prim_row(n, time_kernel(lambda: ops.argsort(keys_perm), 3), 16, peak,
                                         model_bytes_per_elem=8 + 24 * 4 - 4 + 4, passes=4,
                                         torch_eager_ms=time_kernel(lambda: torch.argsort(keys_perm.tensor, stable=True), 3))
+    # (f) rank 1 of SURVEY.md §8f: gather `a@b` and join `a,b` on device arrays (what `x@<x` spends its time in once
+    # the sort is fast).  A random 8-byte read moves a 32-byte sector: algorithmic 24 B/elem, sector traffic 48 B/elem.
+    out["gather_perm_1e8"] = prim_row(n, time_kernel(lambda: ops.gather(a, keys_perm), 3), 24, peak, sector_bytes_per_elem=48,
+                                      torch_eager_ms=time_kernel(lambda: a.tensor[keys_perm.tensor], 3))
+    out["join_1e8+1e8"] = prim_row(2 * n, time_kernel(lambda: be.np.concatenate((a, b)), 3), 16, peak)
     del keys_perm
     keys_10k = DeviceArray(torch.randint(0, 10_000, (n,), dtype=torch.int64, device=dev, generator=g))
     out["grade_up_10k_1e8"] = prim_row(n, time_kernel(lambda: ops.argsort(keys_10k), 3), 16, peak,
@@ -395,7 +400,7 @@ def primitive_table(be, ops, dist, time_kernel, dev, peak, world, rank):
     temp = DeviceArray(torch.randn(n, dtype=torch.float64, device=dev, generator=g))
     out["grouped_min_mean_max_10k_1e8"] = prim_row(n, time_kernel(lambda: dist.sharded_groupagg(keys_10k, temp, 10_000), 3),
                                                   16, peak, n_gpus=world)
-    del temp, a
+    del temp, a, b
     if world == 1:
         # config 4 at its full size: 1e9 synthetic rows, 10k stations (16 GB of input)
         nb = 1_000_000_000

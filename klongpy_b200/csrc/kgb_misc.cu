@@ -106,10 +106,44 @@ __global__ void __launch_bounds__(256) array_equal_kernel(const T* __restrict__ 
     }
 }
 
+// gather of single elements (`x@<x`, the common case): four independent index loads, then four independent
+// random loads in flight per thread — a random 8-byte read costs a whole 32-byte sector, so the only lever is
+// memory-level parallelism
+template <typename W>
+__global__ void __launch_bounds__(256) gather1_kernel(const W* __restrict__ a, i64 n_a, const i64* __restrict__ idx,
+                                                       i64 n_idx, W* __restrict__ out, int* err) {
+    constexpr int U = 4;
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 g0 = (i64)blockIdx.x * blockDim.x + threadIdx.x; g0 < n_idx; g0 += stride * U) {
+        i64 j[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const i64 g = g0 + u * stride;
+            j[u] = g < n_idx ? __ldcs(&idx[g]) : 0;
+            if (j[u] < 0) j[u] += n_a;
+        }
+        W v[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const bool ok = j[u] >= 0 && j[u] < n_a;
+            v[u] = ok ? __ldg(&a[j[u]]) : W(0);
+            if (!ok && g0 + u * stride < n_idx) *err = 1;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const i64 g = g0 + u * stride;
+            if (g < n_idx) __stcs(&out[g], v[u]);
+        }
+    }
+}
+
 template <typename W>
 static int launch_gather(const void* a, i64 n_a, const i64* idx, i64 n_idx, i64 units, void* out, int* err,
                          cudaStream_t st) {
-    gather_kernel<W><<<grid_for(n_idx * units, 256, 2), 256, 0, st>>>((const W*)a, n_a, idx, n_idx, units, (W*)out, err);
+    if (units == 1)
+        gather1_kernel<W><<<grid_for((n_idx + 3) / 4, 256, 8), 256, 0, st>>>((const W*)a, n_a, idx, n_idx, (W*)out, err);
+    else
+        gather_kernel<W><<<grid_for(n_idx * units, 256, 2), 256, 0, st>>>((const W*)a, n_a, idx, n_idx, units, (W*)out, err);
     KGB_CUDA_CHECK(cudaGetLastError());
     return KGB_OK;
 }
