@@ -465,6 +465,13 @@ def primitive_table(be, ops, dist, time_kernel, dev, peak, world, rank):
 
     out["autograd_sigmoid_nn_1e7"] = prim_row(m, time_kernel(lambda: be.compute_multi_autograd(nn_loss, [0.1, 0.1]), 3), 32, peak,
                                               note="operator-by-operator tape, as the interpreter evaluates the Klong source")
+    from klongpy_b200 import lazy
+    lazy.enable(True)   # opt-in deferred elementwise expressions: the same Python, fused forward + fused backward
+    try:
+        out["autograd_sigmoid_nn_1e7_lazy"] = prim_row(m, time_kernel(lambda: be.compute_multi_autograd(nn_loss, [0.1, 0.1]), 3), 32, peak,
+                                                       note="KGB200_LAZY: eager operators deferred and fused (klongpy_b200/lazy.py)")
+    finally:
+        lazy.enable(False)
     R = DeviceArray(torch.rand(m, dtype=torch.float64, device=dev, generator=g) * 0.14 + 0.01)
     V = DeviceArray(torch.rand(m, dtype=torch.float64, device=dev, generator=g) * 0.35 + 0.05)
     W = DeviceArray(torch.full((m,), 1.0 / m, dtype=torch.float64, device=dev))

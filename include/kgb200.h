@@ -157,6 +157,11 @@ int kgb_expr_workspace_bytes(const kgb_expr* h, int64_t n, size_t* out_bytes);
    REDUCE over n == 0 is rejected (the host mirrors numpy's identity / ValueError rules). */
 int kgb_expr_launch(kgb_expr* h, const void* const* args, int64_t n, void* out, void* workspace,
                     size_t workspace_bytes, void* stream);
+/* Host-only type inference: the element type a MAP program would produce for these argument kinds / dtypes (the
+   NumPy promotion rules of numpy_backend.py's generated source).  No NVRTC, no GPU: lets the host answer `.dtype`
+   for a deferred (not yet launched) elementwise expression. */
+int kgb_expr_infer(const int32_t* code, int32_t n_code, const int32_t* arg_kinds, const int32_t* arg_dtypes,
+                   int32_t n_args, int32_t* out_dtype);
 /* element type of the second result of a two-output reduce, -1 if the handle has none */
 int kgb_expr_out_dtype2(const kgb_expr* h);
 /* generated CUDA source of a compiled expression (for tests, DESIGN.md and ncu --import-source) */

@@ -37,6 +37,7 @@ SIGNATURES = {
                               _c.POINTER(_c.c_char_p)]),
     "kgb_expr_workspace_bytes": (_i32, [_vp, _i64, _psz]),
     "kgb_expr_launch": (_i32, [_vp, _c.POINTER(_vp), _i64, _vp, _vp, _sz, _vp]),
+    "kgb_expr_infer": (_i32, [_pi32, _i32, _pi32, _pi32, _i32, _pi32]),
     "kgb_expr_out_dtype2": (_i32, [_vp]),
     "kgb_expr_source": (_c.c_char_p, [_vp]),
     "kgb_expr_kernel_name": (_c.c_char_p, [_vp]),

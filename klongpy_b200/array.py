@@ -47,7 +47,7 @@ def kgb_dtype(t):
 class DeviceArray:
     """N-d array living in B200 HBM.  Immutable from the verbs' point of view (results are fresh arrays)."""
 
-    __slots__ = ("_t", "__weakref__")
+    __slots__ = ("_tensor", "_node", "__weakref__")
     __array_priority__ = 1000
     __array_ufunc__ = None  # numpy scalars defer to our reflected operators
     __hash__ = None
@@ -55,28 +55,51 @@ class DeviceArray:
     def __init__(self, tensor):
         if not isinstance(tensor, torch.Tensor):
             raise TypeError("DeviceArray wraps a torch.Tensor")
-        self._t = tensor
+        self._tensor = tensor
+        self._node = None
+
+    @classmethod
+    def _deferred(cls, node):
+        """An elementwise expression that has not been launched yet (klongpy_b200.lazy, opt-in)."""
+        obj = cls.__new__(cls)
+        obj._tensor = None
+        obj._node = node
+        return obj
+
+    @property
+    def _t(self):
+        """The backing tensor.  Touching it materialises a deferred expression (one fused kernel)."""
+        if self._tensor is None:
+            from . import lazy
+            self._tensor = lazy.materialize(self._node)
+            self._node = None
+        return self._tensor
 
     # ------------------------------------------------------------------ metadata (no device work)
     @property
     def shape(self):
-        return tuple(self._t.shape)
+        return self._node.shape if self._tensor is None else tuple(self._tensor.shape)
 
     @property
     def ndim(self):
-        return self._t.dim()
+        return len(self._node.shape) if self._tensor is None else self._tensor.dim()
 
     @property
     def size(self):
-        return self._t.numel()
+        if self._tensor is None:
+            n = 1
+            for d in self._node.shape:
+                n *= d
+            return n
+        return self._tensor.numel()
 
     @property
     def dtype(self):
-        return _T2NP[self._t.dtype]
+        return _T2NP[_K2T[self._node.kdt]] if self._tensor is None else _T2NP[self._tensor.dtype]
 
     @property
     def device(self):
-        return self._t.device
+        return self._node.device if self._tensor is None else self._tensor.device
 
     @property
     def tensor(self):
@@ -85,7 +108,9 @@ class DeviceArray:
 
     @property
     def requires_grad(self):
-        return self._t.requires_grad
+        if self._tensor is None:
+            return any(isinstance(a, DeviceArray) and a.requires_grad for a in self._node.args)
+        return self._tensor.requires_grad
 
     @property
     def T(self):
@@ -169,7 +194,7 @@ class DeviceArray:
     def _bin(self, other, op, reflected=False):
         from . import ops
         if isinstance(other, (list, tuple)):
-            other = ops.asarray(other, device=self._t.device)
+            other = ops.asarray(other, device=self.device)
         if not ops.is_operand(other):
             return NotImplemented
         return ops.binary(op, other, self) if reflected else ops.binary(op, self, other)

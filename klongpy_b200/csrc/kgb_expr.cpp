@@ -877,6 +877,21 @@ extern "C" int kgb_expr_launch(kgb_expr* h, const void* const* args, int64_t n, 
     return KGB_OK;
 }
 
+// Result element type of a MAP program for the given argument kinds / dtypes: host-only type inference with the
+// same promotion rules the code generator applies (no NVRTC, no GPU) — what a lazy host layer needs to answer
+// `.dtype` without launching anything.
+extern "C" int kgb_expr_infer(const int32_t* code, int32_t n_code, const int32_t* arg_kinds, const int32_t* arg_dtypes,
+                              int32_t n_args, int32_t* out_dtype) {
+    KGB_REQUIRE(code && n_code > 0 && out_dtype, "kgb_expr_infer: null program");
+    KGB_REQUIRE(n_args >= 0 && n_args <= KGB_MAX_ARGS, "kgb_expr_infer: %d arguments (max %d)", n_args, KGB_MAX_ARGS);
+    std::vector<ArgInfo> args;
+    for (int i = 0; i < n_args; i++) args.push_back(ArgInfo{arg_kinds[i], arg_dtypes[i]});
+    Val v;
+    if (!gen_expr(code, n_code, args, false, 0, &v)) return KGB_EINVAL;
+    *out_dtype = v.t.dt;
+    return KGB_OK;
+}
+
 extern "C" int kgb_expr_out_dtype2(const kgb_expr* h) { return (h && h->has_red2) ? h->acc2_dtype : -1; }
 extern "C" const char* kgb_expr_source(const kgb_expr* h) { return h ? h->source.c_str() : ""; }
 extern "C" const char* kgb_expr_kernel_name(const kgb_expr* h) { return h ? h->name_v.c_str() : ""; }

@@ -1,0 +1,152 @@
+"""Deferred elementwise expressions — SURVEY.md §8f rank 2 ("compiler coverage"), OPT-IN (KGB200_LAZY=1 or
+`lazy.enable()`).
+
+The reference's compiler IR covers `+ - * % ^ = < > -x +/ +\\` only (`compiler.py:77-90`); everything else — `& | !
+_`, `%x`, and the `.bkf` unary math the autograd examples live on (`exp tanh sqrt ...`, `sys_fn.py:715-723`) — reaches
+the backend one operator at a time, so `sigmoid((w1*X)+b1)` is five kernels and four temporaries.  With the lazy
+layer an eager elementwise op returns a `DeviceArray` that only *describes* its result (postfix program + leaf
+operands + inferred shape/dtype via `kgb_expr_infer`); consumers that are themselves elementwise, reductions or
+scans inline that description into their own program, and anything that touches the data (`to_numpy`, indexing,
+sort, an operand used a second time) materialises it with ONE fused kernel.  Under autograd a fused program is a
+single tape node whose backward is derived symbolically (autodiff.py), so the backward fuses too.
+
+Rules that keep it safe:
+  * shapes are checked and dtypes inferred when the node is built — errors are raised at the operator, not later;
+  * a node inlines into at most ONE consumer; a second consumer materialises it first (no exponential recompute);
+  * programs are capped (arguments <= KGB_MAX_ARGS, code <= 96 words); beyond that operands are materialised.
+"""
+import ctypes
+import os
+
+import torch
+
+from . import _lib
+
+ENABLED = os.environ.get("KGB200_LAZY", "0") == "1"
+MAX_ARGS = 12
+MAX_CODE = 96
+_infer_cache = {}
+
+
+def enable(flag=True):
+    global ENABLED
+    ENABLED = bool(flag)
+
+
+class Node:
+    __slots__ = ("code", "args", "shape", "kdt", "device", "uses")
+
+    def __init__(self, code, args, shape, kdt, device):
+        self.code, self.args, self.shape, self.kdt, self.device = tuple(code), list(args), tuple(shape), kdt, device
+        self.uses = 0
+
+
+def _is_lazy(a):
+    from .array import DeviceArray
+    return isinstance(a, DeviceArray) and a._tensor is None
+
+
+def inline(code, args):
+    """Expand deferred operands into `code` (postfix over `args`).  Returns (code, args) over leaf operands only."""
+    if not any(_is_lazy(a) for a in args):
+        return list(code), list(args)
+    from . import ops
+    new_args, index_of = [], {}
+
+    def leaf(a):
+        k = id(a)
+        if k not in index_of:
+            index_of[k] = len(new_args)
+            new_args.append(a)
+        return index_of[k]
+
+    # decide which deferred operands can be inlined (first consumer, and the result must stay within the caps)
+    budget_args = MAX_ARGS - sum(1 for a in args if not _is_lazy(a))
+    budget_code = MAX_CODE - len(code)
+    plan = []
+    for a in args:
+        if _is_lazy(a):
+            nd = a._node
+            ok = nd.uses == 0 and len(nd.args) <= budget_args and len(nd.code) <= budget_code
+            if ok:
+                budget_args -= len(nd.args)
+                budget_code -= len(nd.code)
+            plan.append(ok)
+        else:
+            plan.append(False)
+    out, i = [], 0
+    code = list(code)
+    while i < len(code):
+        w = code[i]
+        if w == ops.OP_ARG:
+            a = args[code[i + 1]]
+            if _is_lazy(a) and plan[code[i + 1]]:
+                nd = a._node
+                nd.uses += 1
+                sub, j = list(nd.code), 0
+                while j < len(sub):
+                    v = sub[j]
+                    if v == ops.OP_ARG:
+                        out += [ops.OP_ARG, leaf(nd.args[sub[j + 1]])]
+                        j += 2
+                    elif v in (ops.OP_LIT_I64, ops.OP_LIT_F64):
+                        out += sub[j:j + 3]
+                        j += 3
+                    else:
+                        out.append(v)
+                        j += 1
+            else:
+                if _is_lazy(a):
+                    a._t  # noqa: B018 - materialise: used twice, or the fused program would get too large
+                out += [ops.OP_ARG, leaf(a)]
+            i += 2
+        elif w in (ops.OP_LIT_I64, ops.OP_LIT_F64):
+            out += code[i:i + 3]
+            i += 3
+        else:
+            out.append(w)
+            i += 1
+    return out, new_args
+
+
+def _infer(code, args, device):
+    from . import ops
+    lib, _ = ops._lib_for(device)
+    cls = [ops._classify_meta(a) for a in args]
+    key = (tuple(code), tuple(cls))
+    kdt = _infer_cache.get(key)
+    if kdt is None:
+        n = len(args)
+        od = ctypes.c_int32()
+        _lib.check(lib.kgb_expr_infer((ctypes.c_int32 * len(code))(*code), len(code),
+                                      (ctypes.c_int32 * max(n, 1))(*[c[0] for c in cls]),
+                                      (ctypes.c_int32 * max(n, 1))(*[c[1] for c in cls]), n, ctypes.byref(od)),
+                   "kgb_expr_infer")
+        kdt = od.value
+        _infer_cache[key] = kdt
+    return kdt
+
+
+def defer(code, args):
+    """A deferred DeviceArray for the MAP program `code` over leaf operands `args`, or None when it cannot be
+    deferred (no device operand, too many arguments)."""
+    from .array import DeviceArray
+    device, shape = None, None
+    for a in args:
+        if isinstance(a, DeviceArray):
+            device = a.device
+            if a.ndim > 0:
+                if shape is None:
+                    shape = a.shape
+                elif a.shape != shape:
+                    raise ValueError(f"operands could not be broadcast together with shapes {shape} {a.shape}")
+    if device is None or len(args) > MAX_ARGS or len(code) > MAX_CODE:
+        return None
+    kdt = _infer(code, args, device)
+    return DeviceArray._deferred(Node(code, args, shape if shape is not None else (), kdt, device))
+
+
+def materialize(node):
+    """Launch the deferred program: one fused kernel (and one autograd node when an operand is on the tape)."""
+    from . import ops
+    return ops.run(node.code, node.args, _no_defer=True)._t

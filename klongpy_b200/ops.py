@@ -150,9 +150,32 @@ def _classify(x, device):
     raise TypeError(f"unsupported operand type {type(x).__name__}")
 
 
-def run(code, args, mode=_lib.MODE_MAP, red=0, code2=None, red2=0, out_shape=None, device=None):
+def _classify_meta(x):
+    """(kind, kgb dtype) of an operand from metadata only (never materialises a deferred array)."""
+    if isinstance(x, DeviceArray):
+        kind = _lib.ARG_DEVSCALAR if x.ndim == 0 else _lib.ARG_ARRAY
+        return kind, {"float64": _lib.F64, "int64": _lib.I64, "float32": _lib.F32, "int32": _lib.I32, "bool": _lib.B8}[x.dtype.name]
+    if isinstance(x, (bool, np.bool_, int, np.integer)):
+        return _lib.ARG_SCALAR, _lib.I64
+    if isinstance(x, np.ndarray) and x.ndim == 0:
+        return _lib.ARG_SCALAR, (_lib.I64 if x.dtype.kind in "iub" else _lib.F64)
+    if isinstance(x, (float, np.floating)):
+        return _lib.ARG_SCALAR, _lib.F64
+    raise TypeError(f"unsupported operand type {type(x).__name__}")
+
+
+def run(code, args, mode=_lib.MODE_MAP, red=0, code2=None, red2=0, out_shape=None, device=None, _no_defer=False):
     """Compile (cached) and launch one expression program.  Returns a DeviceArray."""
-    if torch.is_grad_enabled() and any(isinstance(a, DeviceArray) and a._t.requires_grad for a in args):
+    from . import lazy
+    if lazy.ENABLED and not _no_defer:
+        # deferred operands are inlined into this program (elementwise chains, reduce / scan prologues fuse);
+        # a MAP result is itself deferred until something needs the data
+        code, args = lazy.inline(code, args)
+        if mode == _lib.MODE_MAP and out_shape is None and not code2:
+            r = lazy.defer(code, args)
+            if r is not None:
+                return r
+    if torch.is_grad_enabled() and any(isinstance(a, DeviceArray) and a.requires_grad for a in args):
         from . import autograd  # operands on the autograd tape: same launch, recorded as one node
         return autograd.run_differentiable(code, args, mode, red, code2, red2, out_shape, device)
     shape = None
@@ -278,7 +301,7 @@ def empty_fold(code, args, red):
 def _device_of(*xs):
     for x in xs:
         if isinstance(x, DeviceArray):
-            return x._t.device
+            return x.device  # metadata only: never materialises a deferred operand
     return None
 
 
@@ -369,24 +392,24 @@ def astype(a, dtype):
 
 
 def copy(a):
-    if a._t.numel() == 0:
+    if a.size == 0:
         return DeviceArray(a._t.clone())
     return run([OP_ARG, 0], [a])
 
 
 def reduce(op, a, code=None, args=None):
     """op-fold over a 1-d device array (adverbs.py:232-243); N-d folds along axis 0 like numpy ufunc.reduce."""
-    if a._t.dim() == 0:
+    if a.ndim == 0:
         return a
-    if a._t.dim() > 1:
+    if a.ndim > 1:
         acc = DeviceArray(a._t[0])
         for i in range(1, a._t.shape[0]):
             acc = binary(op, acc, DeviceArray(a._t[i]))
         return acc
-    if a._t.numel() == 0:
+    if a.size == 0:
         if op == "add":
             return DeviceArray(torch.zeros((), dtype=a._t.dtype if a._t.dtype != torch.bool else torch.int64,
-                                           device=a._t.device))
+                                           device=a.device))
         if op == "mul":
             return DeviceArray(torch.ones((), dtype=a._t.dtype if a._t.dtype != torch.bool else torch.int64,
                                           device=a._t.device))
@@ -396,9 +419,9 @@ def reduce(op, a, code=None, args=None):
 
 def scan(op, a):
     """inclusive op-scan (adverbs.py:325-332); N-d scans along axis 0."""
-    if a._t.dim() == 0:
+    if a.ndim == 0:
         return a
-    if a._t.dim() > 1:
+    if a.ndim > 1:
         rows = [DeviceArray(a._t[0])]
         for i in range(1, a._t.shape[0]):
             rows.append(binary(op, rows[-1], DeviceArray(a._t[i])))
@@ -406,20 +429,20 @@ def scan(op, a):
         for i, r in enumerate(rows):
             out[i].copy_(r._t)
         return DeviceArray(out)
-    if a._t.numel() == 0:
+    if a.size == 0:
         return DeviceArray(a._t.clone())
     return run([OP_ARG, 0], [a], mode=_lib.MODE_SCAN, red=RED[op])
 
 
 def all_(a):
-    if a._t.numel() == 0:
+    if a.size == 0:
         return True
     flat = a.flatten()
     return run([OP_ARG, 0, OPC["to_b8"]], [flat], mode=_lib.MODE_REDUCE, red=_lib.RED_MIN)
 
 
 def any_(a):
-    if a._t.numel() == 0:
+    if a.size == 0:
         return False
     flat = a.flatten()
     return run([OP_ARG, 0, OPC["to_b8"]], [flat], mode=_lib.MODE_REDUCE, red=_lib.RED_MAX)

@@ -228,6 +228,15 @@ class FakeLib:
         od._obj.value = _CODE[e.out]
         return 0
 
+    def kgb_expr_infer(self, code, n_code, kinds, dtypes, n_args, od):
+        try:
+            e = _Expr(list(code[:n_code]), None, list(kinds[:n_args]), list(dtypes[:n_args]), 0, 0, 0)
+        except Exception as ex:  # noqa: BLE001
+            self.err = f"fake infer: {ex}".encode()
+            return -1
+        od._obj.value = _CODE[e.out]
+        return 0
+
     def kgb_expr_out_dtype2(self, h):
         e = self.exprs[_addr(h) - 1]
         return -1 if e.out2 is None else _CODE[e.out2]
