@@ -218,7 +218,7 @@ def _find(node, kind):
 
 
 def _is_arraylike(v):
-    return isinstance(v, DeviceArray) and v._t.dim() > 0
+    return isinstance(v, DeviceArray) and v.ndim > 0
 
 
 def make_callable(ir):
@@ -234,7 +234,7 @@ def make_callable(ir):
         for v in args:
             if isinstance(v, DeviceArray):
                 any_dev = True
-                if v._t.dim() > 1:
+                if v.ndim > 1:
                     raise NotImplementedError("compiled kernels take 1-d arrays; N-d goes through the eager verbs")
             elif type(v) in (int, float) or isinstance(v, (np.integer, np.floating)):
                 pass
@@ -248,8 +248,8 @@ def make_callable(ir):
             if st.pair is not None:
                 other, code_b, slots = st.pair
                 pargs = [vals[s] for s in slots]
-                lens = {a._t.numel() for a in pargs if _is_arraylike(a)}
-                grad = any(isinstance(a, DeviceArray) and a._t.requires_grad for a in pargs)
+                lens = {a.size for a in pargs if _is_arraylike(a)}
+                grad = any(isinstance(a, DeviceArray) and a.requires_grad for a in pargs)
                 if len(lens) == 1 and 0 not in lens and not grad:
                     try:
                         vals[st.out_slot], vals[other.out_slot] = ops.reduce2(st.code, st.red, code_b, other.red, pargs)
@@ -261,7 +261,7 @@ def make_callable(ir):
             if st.mode != _lib.MODE_MAP and not has_array:
                 raise NotImplementedError("fold over a scalar: interpreter semantics apply")
             if st.mode in (_lib.MODE_REDUCE, _lib.MODE_SCANRED):
-                n = next(a for a in sargs if _is_arraylike(a))._t.numel()
+                n = next(a for a in sargs if _is_arraylike(a)).size
                 if n == 0:
                     # np.add.reduce([]) -> 0.0 and np.multiply.reduce([]) -> 1.0 in the result dtype;
                     # np.maximum.reduce([]) raises (numpy_backend.py:163) -> interpreter fallback
