@@ -141,13 +141,17 @@ template <> struct kgb_raw<16> { typedef uint4 type; };
 
 // streaming (evict-first) load of V contiguous elements into registers dst[0..V).  32-byte groups use the 256-bit
 // global accesses of sm_100 (LDG.E.256 / STG.E.256): half the memory instructions per byte moved.
+#ifndef KGB_LDHINT
+#define KGB_LDHINT ".cs"   // streaming (evict-first) by default; tuning: "" = default policy, ".cg", ".lu"
+#define KGB_STHINT ".cs"
+#endif
 template <typename T, int V> __device__ __forceinline__ void kgb_ldv(T* dst, const T* src) {
     if constexpr (sizeof(T) * V == 32) {
         union {
             u64 r[4];
             T t[V];
         } u;
-        asm volatile("ld.global.cs.v4.u64 {%0, %1, %2, %3}, [%4];"
+        asm volatile("ld.global" KGB_LDHINT ".v4.u64 {%0, %1, %2, %3}, [%4];"
                      : "=l"(u.r[0]), "=l"(u.r[1]), "=l"(u.r[2]), "=l"(u.r[3]) : "l"(src));
 #pragma unroll
         for (int j = 0; j < V; j++) dst[j] = u.t[j];
@@ -170,7 +174,7 @@ template <typename T, int V> __device__ __forceinline__ void kgb_stv(T* dst, con
         } u;
 #pragma unroll
         for (int j = 0; j < V; j++) u.t[j] = src[j];
-        asm volatile("st.global.cs.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "l"(u.r[0]), "l"(u.r[1]), "l"(u.r[2]), "l"(u.r[3])
+        asm volatile("st.global" KGB_STHINT ".v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "l"(u.r[0]), "l"(u.r[1]), "l"(u.r[2]), "l"(u.r[3])
                      : "memory");
     } else {
         typedef typename kgb_raw<sizeof(T) * V>::type R;

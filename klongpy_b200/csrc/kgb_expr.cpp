@@ -552,6 +552,7 @@ static int build_source(kgb_expr* h, const int32_t* code, int n_code, const int3
     h->unroll = wide ? 2 : 4;
 
     m << "#define KGB_VEC " << h->vec << "\n#define KGB_UNROLL " << h->unroll << "\n";
+    if (const char* e = getenv("KGB200_LDHINT")) m << "#define KGB_LDHINT \"" << e << "\"\n#define KGB_STHINT \"" << (getenv("KGB200_STHINT") ? getenv("KGB200_STHINT") : e) << "\"\n";
     m << "#define KGB_OUT_T " << ctype(h->out_dtype) << "\n";
     m << "#define KGB_ACC_T " << ctype(h->acc_dtype) << "\n";
     if (h->mode == KGB_MODE_SCAN || h->mode == KGB_MODE_SCANRED) {
@@ -713,6 +714,13 @@ static unsigned fold_grid(const kgb_expr* h, long long n, bool vec) {
     const long long groups = (n + V - 1) / V;
     long long need = (groups + (long long)kBlock * h->unroll - 1) / ((long long)kBlock * h->unroll);
     long long cap = (long long)sm_count() * (vec ? h->occ_v : h->occ_s);
+    // MAP: many waves of CTAs instead of one persistent wave — SMs do not all stream at the same speed, and the
+    // hardware CTA scheduler balances them (measured at 2^28 f64: a+b 0.998 -> 1.06 of the copy peak, -a 0.92 -> 1.05;
+    // the fold kernels keep one wave: their partial count grows with the grid and they lose 7 % at x64)
+    int mult = h->mode == KGB_MODE_MAP ? 32 : 1;
+    if (const char* e = getenv("KGB200_GRID_MULT"))
+        if (h->mode == KGB_MODE_MAP) mult = std::max(1, atoi(e));  // (the fold workspace is sized for one wave)
+    cap *= mult;
     if (need < 1) need = 1;
     return (unsigned)std::min(need, cap);
 }
