@@ -1,3 +1,5 @@
+"""Pipelined scan with a carried seed and the two-output reduce at sizes that take the persistent kernels, against torch
+(the check that exposed the stage hand-over race of round 1; kept as a quick standalone probe)."""
 import sys
 import numpy as np
 import torch
