@@ -258,7 +258,7 @@ def main():
             torch.cuda.empty_cache()
 
             from klongpy_b200 import stream
-            hs_stream = stream.HostStream(dev, chunk=1 << 26) if world == 1 else None
+            hs_stream = stream.HostStream(dev, chunk=1 << 24) if world == 1 else None
 
             def e2e_step():
                 if world == 1:
@@ -290,7 +290,7 @@ def main():
                 td.all_reduce(e_ms, op=td.ReduceOp.MAX)
             e2e = {"value": 2.0 * n * world / (float(e_ms.item()) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * n,
                    "d2h_bytes_per_step": 8 * n + 8, "ms_per_step": float(e_ms.item()), "steps": k,
-                   "path": ("pinned host float64 -> klongpy_b200.stream.HostStream (64 Mi-element chunks: H2D | fused reduce + "
+                   "path": ("pinned host float64 -> klongpy_b200.stream.HostStream (16 Mi-element chunks: H2D | fused reduce + "
                             "carried scan | D2H overlapped on three streams) -> pinned host") if world == 1 else
                    "pinned host shard -> device -> dist.sharded_reduce / sharded_scan -> pinned host", "check": e2e_check}
             del hx, hs, hr
