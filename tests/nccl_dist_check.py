@@ -1,6 +1,6 @@
 """Multi-GPU parity under torchrun (NCCL): sharded reduce / scan / grouped aggregation vs the oracle on the full data.
 
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 scripts/dist_check.py
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tests/nccl_dist_check.py
 """
 import os
 import sys
