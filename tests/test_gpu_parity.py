@@ -546,3 +546,36 @@ def test_pipelined_scan_with_carried_seed(be, K, n):
     for _ in range(3):
         assert np.array_equal(host(K.scan("add", i)), np.cumsum(k))
         assert np.array_equal(host(K.scan("max", x)), np.maximum.accumulate(k / 256.0))
+
+
+@pytest.mark.gpu
+def test_grade_large_float_keys_with_nan_inf_and_signed_zero(be, K):
+    """The persistent pipelined sort pass on float64 keys with every special value mixed in: NaN sorts last, -0.0 and
+    +0.0 tie (stable by position), +-inf at the ends — np.argsort(kind='stable') is the contract (writer.py:97-108)."""
+    rng = np.random.default_rng(99)
+    n = 3_000_017
+    k = np.round(rng.standard_normal(n), 2)
+    special = rng.integers(0, n, 60_000)
+    k[special[:10_000]] = np.nan
+    k[special[10_000:20_000]] = np.inf
+    k[special[20_000:30_000]] = -np.inf
+    k[special[30_000:45_000]] = -0.0
+    k[special[45_000:]] = 0.0
+    d = dev(be, k)
+    ref = np.argsort(k, kind="stable")
+    assert np.array_equal(host(K.argsort(d)), ref)
+    assert np.array_equal(host(K.argsort(d, descending=True)), ref[::-1])
+    order, starts, g = K.group(d)
+    assert np.array_equal(host(order), ref)
+    u = host(K.unique_first(dev(be, k[:200_000])))
+    kk = k[:200_000]
+    # first-appearance order; NaNs collapse to one entry, -0.0 and 0.0 stay distinct (the reference keys on str(x))
+    seen, want = set(), []
+    for x in kk:
+        key = "nan" if x != x else repr(float(x))
+        if key not in seen:
+            seen.add(key)
+            want.append(x)
+    want = np.array(want)
+    assert len(u) == len(want) and np.array_equal(np.isnan(u), np.isnan(want))
+    assert np.array_equal(u[~np.isnan(u)], want[~np.isnan(want)]) and np.array_equal(np.signbit(u), np.signbit(want))
