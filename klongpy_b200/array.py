@@ -49,8 +49,6 @@ class DeviceArray:
 
     __slots__ = ("_tensor", "_node", "__weakref__")
     __array_priority__ = 1000
-    __array_ufunc__ = None  # numpy scalars defer to our reflected operators
-    __hash__ = None
 
     def __init__(self, tensor):
         if not isinstance(tensor, torch.Tensor):
@@ -244,15 +242,62 @@ class DeviceArray:
         from . import ops
         return ops.any_(self)
 
-    def sum(self, axis=None):
+    # numpy ufuncs applied to device arrays (np.float64(2) * a, np.equal(a, b), np.add.reduce(a) ...) run on the device
+    # when the ufunc has a kernel opcode, and on host copies otherwise — global-NumPy call sites of the reference
+    # (SURVEY.md §8b "leaks") and user code keep working instead of raising
+    _UFUNC = {"add": "add", "subtract": "sub", "multiply": "mul", "divide": "div", "true_divide": "div", "power": "pow",
+              "maximum": "max", "minimum": "min", "fmod": "fmod", "equal": "eq_b", "not_equal": "ne_b", "less": "lt_b",
+              "greater": "gt_b", "less_equal": "le_b", "greater_equal": "ge_b", "negative": "neg", "absolute": "abs",
+              "floor": "floor", "ceil": "ceil", "trunc": "trunc", "reciprocal": "recip", "logical_not": "not_b",
+              "sqrt": "sqrt", "exp": "exp", "log": "log", "sin": "sin", "cos": "cos", "tan": "tan", "tanh": "tanh",
+              "sign": "sign", "isnan": "isnan_b", "isinf": "isinf_b", "log2": "log2", "log10": "log10", "square": "square",
+              "expm1": "expm1", "log1p": "log1p", "sinh": "sinh", "cosh": "cosh", "arcsin": "asin", "arccos": "acos",
+              "arctan": "atan"}
+
+    def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
+        from . import ops
+        name = self._UFUNC.get(ufunc.__name__)
+        if name is not None and not kwargs:
+            if method == "__call__" and all(ops.is_operand(x) for x in inputs):
+                if len(inputs) == 2:
+                    return ops.binary(name, inputs[0], inputs[1])
+                if len(inputs) == 1:
+                    return ops.unary(name, inputs[0])
+            if method in ("reduce", "accumulate") and name in ("add", "mul", "max", "min") and len(inputs) == 1:
+                return ops.reduce(name, inputs[0]) if method == "reduce" else ops.scan(name, inputs[0])
+        host = [x.to_numpy() if isinstance(x, DeviceArray) else x for x in inputs]
+        return getattr(ufunc, method)(*host, **kwargs)
+
+    def __hash__(self):
+        # 0-d device values appear as dictionary keys (`:{[k v]}` builds `a[b[0]] = b[1]`, dyads dictionary code):
+        # hash like the host scalar they stand for; arrays stay unhashable like numpy's
+        if self.ndim == 0:
+            return hash(self.item())
+        raise TypeError("unhashable type: 'DeviceArray'")
+
+    def __floordiv__(self, other):
+        from . import ops
+        if self.ndim == 0 and ops.is_host_scalar(other):
+            return self.item() // other
+        return ops.unary("floor_i64", ops.binary("div", self, other)) if self.dtype.kind in "iub" else \
+            ops.unary("floor", ops.binary("div", self, other))
+
+    def __rfloordiv__(self, other):
+        from . import ops
+        if self.ndim == 0 and ops.is_host_scalar(other):
+            return other // self.item()
+        return ops.unary("floor_i64", ops.binary("div", other, self)) if self.dtype.kind in "iub" else \
+            ops.unary("floor", ops.binary("div", other, self))
+
+    def sum(self, axis=None, out=None, **_kw):
         from . import ops
         return ops.reduce("add", self)
 
-    def max(self, axis=None):
+    def max(self, axis=None, out=None, **_kw):
         from . import ops
         return ops.reduce("max", self)
 
-    def min(self, axis=None):
+    def min(self, axis=None, out=None, **_kw):
         from . import ops
         return ops.reduce("min", self)
 

@@ -205,6 +205,8 @@ class B200BackendProvider(_Base):
         torch precedent (torch_backend.py:1086-1128)."""
         if isinstance(a, DeviceArray):
             return a
+        if isinstance(a, (int, float, np.integer, np.floating)) and not isinstance(a, bool):
+            return np.asarray(a)  # scalars are interpreter control flow: 0-d HOST arrays, like numpy_backend.py:185
         if isinstance(a, str):
             return self.str_to_char_array(a)
         if isinstance(a, np.ndarray):

@@ -139,7 +139,7 @@ def defer(code, args):
                 if shape is None:
                     shape = a.shape
                 elif a.shape != shape:
-                    raise ValueError(f"operands could not be broadcast together with shapes {shape} {a.shape}")
+                    return None  # NumPy broadcasting between different shapes: the eager path expands (or raises)
     if device is None or len(args) > MAX_ARGS or len(code) > MAX_CODE:
         return None
     kdt = _infer(code, args, device)

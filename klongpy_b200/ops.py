@@ -111,7 +111,8 @@ def asarray(a, device=None, dtype=None):
     if arr.dtype == object or arr.dtype.kind not in "ifub":
         raise TypeError(f"cannot place dtype {arr.dtype} on the device")
     td = torch_dtype_of(arr.dtype)
-    arr = np.ascontiguousarray(arr)
+    if arr.ndim > 0:  # (np.ascontiguousarray would turn a 0-d array into shape (1,))
+        arr = np.ascontiguousarray(arr)
     t = torch.from_numpy(arr) if arr.dtype in (np.float64, np.int64, np.float32, np.int32, np.bool_) \
         else torch.from_numpy(arr.astype(np.int64 if arr.dtype.kind in "iu" else np.float64))
     return DeviceArray(t.to(device=device, dtype=td))
@@ -179,6 +180,7 @@ def run(code, args, mode=_lib.MODE_MAP, red=0, code2=None, red2=0, out_shape=Non
         from . import autograd  # operands on the autograd tape: same launch, recorded as one node
         return autograd.run_differentiable(code, args, mode, red, code2, red2, out_shape, device)
     shape = None
+    mixed = False
     for a in args:
         if isinstance(a, DeviceArray):
             device = a._t.device
@@ -186,7 +188,17 @@ def run(code, args, mode=_lib.MODE_MAP, red=0, code2=None, red2=0, out_shape=Non
                 if shape is None:
                     shape = tuple(a._t.shape)
                 elif tuple(a._t.shape) != shape:
-                    raise ValueError(f"operands could not be broadcast together with shapes {shape} {tuple(a._t.shape)}")
+                    mixed = True
+    if mixed:
+        # NumPy broadcasting between arrays of different shapes (`[[1]]&[2]`, tests/kgtests/language/test_broadcasting.kg):
+        # rare and small in Klong programs, so the operands are expanded to the common shape first (one copy each)
+        shapes = [tuple(a._t.shape) for a in args if isinstance(a, DeviceArray) and a._t.dim() > 0]
+        try:
+            shape = tuple(np.broadcast_shapes(*shapes))
+        except ValueError:
+            raise ValueError("operands could not be broadcast together with shapes " + " ".join(map(str, shapes))) from None
+        args = [DeviceArray(a._t.expand(shape).contiguous()) if isinstance(a, DeviceArray) and a._t.dim() > 0 and
+                tuple(a._t.shape) != shape else a for a in args]
     if device is None:
         raise TypeError("run() needs at least one device operand")
     if shape is None and out_shape is not None:

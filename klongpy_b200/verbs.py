@@ -91,7 +91,9 @@ def install(klong):
 
     def shape(a):  # ^a  (monads.py:372-405): metadata only, no D2H of the payload
         if _is_dev(a):
-            return 0 if a.ndim == 0 else np.asarray(a.shape)
+            if a.ndim == 0 or (a.ndim == 1 and a.size == 0):
+                return 0  # `^[]` is 0 (monads.py:372-405: the empty list is an atom); `^[[]]` is [1 0]
+            return np.asarray(a.shape)
         return ref_m["^"](a)
 
     def reverse(a):  # |a  (monads.py:319-340)
@@ -159,9 +161,65 @@ def install(klong):
             return ops.gather(b, idx)
         return ref_d[":+"](a, b)
 
+    # ---------------------------------------------------------------- structural verbs: host round trip
+    # `:= :- :_ :^ :#` (amend, amend-in-depth, cut, reshape, split) and monadic `,` build their results with global
+    # NumPy calls that need real ndarrays (`numpy.put`, `bknp.array_split`, item assignment on the shape list:
+    # dyads.py:24-135, 806-895, 926-973).  They restructure small arrays and are not on the data-parallel path, so device
+    # operands make one round trip: to host, through the REFERENCE implementation, numeric results back to the device.
+    def _to_host(x):
+        if _is_dev(x):
+            return x.to_numpy() if x.ndim > 0 else x.item()
+        if isinstance(x, np.ndarray) and x.dtype == object:
+            out = np.empty(len(x), dtype=object)
+            for i, y in enumerate(x):
+                out[i] = _to_host(y)
+            return out
+        if isinstance(x, list):
+            return [_to_host(y) for y in x]
+        return x
+
+    def _via_host(fn):
+        def wrapped(a, b):
+            if not (_has_dev(a) or _has_dev(b)):
+                return fn(a, b)
+            r = fn(_to_host(a), _to_host(b))
+            return backend.kg_asarray(r) if isinstance(r, (np.ndarray, list)) else r
+        return wrapped
+
+    def _has_dev(x):
+        if _is_dev(x):
+            return True
+        if isinstance(x, np.ndarray) and x.dtype == object or isinstance(x, list):
+            return any(_has_dev(y) for y in x)
+        return False
+
+    # the reference implementations of these verbs call `backend.np.*` internally, so the host twin must be the op
+    # table of an interpreter on the reference's own NumPy backend (one shared instance)
+    host_vd = _host_twin()._vd
+    for sym in (":=", ":-", ":_", ":^", ":#", "$", ":$"):  # `$` / `:$` format to / from strings: host data either way
+        if sym in host_vd:
+            vd[sym] = _via_host(host_vd[sym])
+
     vd.update({"?": find, "@": at_index, ",": join, ":+": rotate})
     klong._b200_installed = True
     return klong
+
+
+_HOST_TWIN = None
+BUILDING_HOST_TWIN = False
+
+
+def _host_twin():
+    """A KlongInterpreter on the reference's NumPy backend whose op table serves the host-round-trip verbs."""
+    global _HOST_TWIN, BUILDING_HOST_TWIN
+    if _HOST_TWIN is None:
+        from klongpy import KlongInterpreter
+        BUILDING_HOST_TWIN = True  # lets test harnesses that re-route every interpreter to 'b200' leave this one alone
+        try:
+            _HOST_TWIN = KlongInterpreter(backend="numpy")
+        finally:
+            BUILDING_HOST_TWIN = False
+    return _HOST_TWIN
 
 
 def grouped_stats(keys, vals, n_groups):
