@@ -17,8 +17,10 @@ def pytest_configure(config):
     import sys
     # appended (not prepended): the reference tests do `from conftest import ...` and must get their own conftest
     sys.path.append(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    import fake_lib
-    dev = fake_lib.install()
+    dev = os.environ.get("REF_SUITE_DEVICE")  # e.g. cuda:0 on a GPU box: the REAL library instead of the CPU double
+    if not dev:
+        import fake_lib
+        dev = fake_lib.install()
     import klongpy
     import klongpy_b200
     from klongpy_b200 import verbs
