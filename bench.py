@@ -351,6 +351,8 @@ def prim_row(n, ms, bytes_per_elem, peak, **extra):
     row = {"n": n, "ms": ms, "elements_per_sec": n / (ms * 1e-3), "algorithmic_bytes_per_elem": bytes_per_elem,
            "achieved_gbs": gbs, "roofline_frac": gbs / peak}
     row.update(extra)
+    if "model_bytes_per_elem" in extra:  # multi-pass algorithms: fraction of the roofline of the pass model's bytes
+        row["model_roofline_frac"] = extra["model_bytes_per_elem"] * n / (ms * 1e-3) / 1e9 / peak
     return row
 
 
@@ -398,16 +400,28 @@ def primitive_table(be, ops, dist, time_kernel, dev, peak, world, rank):
                                     torch_eager_ms=time_kernel(lambda: torch.unique(keys_10k.tensor), 3),
                                     note="torch.unique returns sorted values, not first-appearance order")
     temp = DeviceArray(torch.randn(n, dtype=torch.float64, device=dev, generator=g))
-    out["grouped_min_mean_max_10k_1e8"] = prim_row(n, time_kernel(lambda: dist.sharded_groupagg(keys_10k, temp, 10_000), 3),
-                                                  16, peak, n_gpus=world)
+    def over_ranks(ms):  # a sharded primitive is as slow as its slowest rank
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return float(t.item())
+
+    # rows block-sharded over the ranks (n rows PER GPU, weak scaling); at N>1 the per-rank partial tables meet in one
+    # owner-partitioned all-to-all + merge + all-gather (dist.sharded_groupagg); totals and peak are whole-job
+    out["grouped_min_mean_max_10k_1e8"] = prim_row(
+        n * world, over_ranks(time_kernel(lambda: dist.sharded_groupagg(keys_10k, temp, 10_000), 3)), 16, peak * world,
+        n_gpus=world, rows_per_gpu=n)
     del temp, a, b
+    # config 4 at its full size: 1e9 synthetic rows PER GPU, 10k stations (16 GB of input per GPU)
+    nb = 1_000_000_000
+    st_b = DeviceArray(torch.randint(0, 10_000, (nb,), dtype=torch.int64, device=dev, generator=g))
+    tp_b = DeviceArray(torch.randn(nb, dtype=torch.float64, device=dev, generator=g))
+    out["grouped_min_mean_max_10k_1e9"] = prim_row(
+        nb * world, over_ranks(time_kernel(lambda: dist.sharded_groupagg(st_b, tp_b, 10_000), 3)), 16, peak * world,
+        n_gpus=world, rows_per_gpu=nb)
+    del tp_b
     if world == 1:
-        # config 4 at its full size: 1e9 synthetic rows, 10k stations (16 GB of input)
-        nb = 1_000_000_000
-        st_b = DeviceArray(torch.randint(0, 10_000, (nb,), dtype=torch.int64, device=dev, generator=g))
-        tp_b = DeviceArray(torch.randn(nb, dtype=torch.float64, device=dev, generator=g))
-        out["grouped_min_mean_max_10k_1e9"] = prim_row(nb, time_kernel(lambda: ops.groupagg(st_b, tp_b, 10_000), 3), 16, peak)
-        del tp_b
         # config 3 at its upper size: 1e9 int64 keys
         out["group_10k_1e9"] = prim_row(nb, time_kernel(lambda: ops.group(st_b), 2), 16, peak)
         del st_b
@@ -415,6 +429,8 @@ def primitive_table(be, ops, dist, time_kernel, dev, peak, world, rank):
         out["grade_up_perm_1e9"] = prim_row(nb, time_kernel(lambda: ops.argsort(kp), 2), 16, peak,
                                             model_bytes_per_elem=8 + 24 * 4 - 4 + 4, passes=4)
         del kp
+    else:
+        del st_b
     # config 1: examples/bench_compiler.kg expressions at the file's own size (100 K float64): µs per call through the
     # compiled callable (1000 back-to-back calls, one sync), next to the reference's NumPy codegen on this box's CPU
     import time as _time

@@ -126,28 +126,31 @@ def sharded_groupagg(keys, vals, n_groups):
     B = (G + w - 1) // w  # stations [r*B, (r+1)*B) are owned by rank r
     dev = mn._t.device
     lib, stream = ops._lib_for(dev)
-
-    def padded(t, fill):
-        p = torch.full((w * B,), fill, dtype=t.dtype, device=dev)
-        p[:G].copy_(t)
-        return p
-
-    send = [padded(mn._t, float("inf")), padded(mx._t, float("-inf")), padded(sm._t, 0.0), padded(ct._t, 0)]
-    recv = [torch.empty_like(s) for s in send]
-    for s, r in zip(send, recv):  # owner slices: rank r receives block r of every rank's partial table
-        td.all_to_all_single(r, s)
-    acc = [r[:B].clone() for r in recv]
-    for k in range(1, w):
-        sl = [r[k * B:(k + 1) * B] for r in recv]
+    # One exchange buffer for the four tables (all 8-byte lanes; float64 travels as its bit pattern):
+    # send[r, j, :] = table j of this rank's partials for the stations rank r owns.
+    i64 = torch.int64
+    pad = torch.empty((4, w * B), dtype=i64, device=dev)
+    if w * B > G:
+        pad[0, G:] = torch.tensor(float("inf"), dtype=torch.float64).view(i64).item()
+        pad[1, G:] = torch.tensor(float("-inf"), dtype=torch.float64).view(i64).item()
+        pad[2:, G:] = 0
+    for j, t in enumerate((mn._t, mx._t, sm._t, ct._t)):
+        pad[j, :G].copy_(t.view(i64) if t.dtype != i64 else t)
+    send = pad.view(4, w, B).permute(1, 0, 2).contiguous()
+    recv = torch.empty_like(send)
+    td.all_to_all_single(recv, send)  # recv[k] = rank k's partial tables for MY stations
+    acc = recv[0]
+    f64 = torch.float64
+    for k in range(1, w):  # fixed rank order: identical results on every run
+        sl = recv[k]
         _lib.check(lib.kgb_groupagg_merge(acc[0].data_ptr(), acc[1].data_ptr(), acc[2].data_ptr(), acc[3].data_ptr(),
                                           sl[0].data_ptr(), sl[1].data_ptr(), sl[2].data_ptr(), sl[3].data_ptr(), B,
                                           stream), "kgb_groupagg_merge")
-    outs = []
-    for a in acc:
-        full = torch.empty(w * B, dtype=a.dtype, device=dev)
-        td.all_gather_into_tensor(full, a.contiguous())
-        outs.append(DeviceArray(full[:G]))
-    return tuple(outs)
+    full = torch.empty(w * 4 * B, dtype=i64, device=dev)
+    td.all_gather_into_tensor(full, acc.contiguous().view(-1))
+    tabs = full.view(w, 4, B).permute(1, 0, 2).reshape(4, w * B)[:, :G].contiguous()
+    return (DeviceArray(tabs[0].view(f64)), DeviceArray(tabs[1].view(f64)), DeviceArray(tabs[2].view(f64)),
+            DeviceArray(tabs[3] if ct._t.dtype == i64 else tabs[3].view(ct._t.dtype)))
 
 
 def shard_bounds(n_global, r=None, w=None):
