@@ -1,17 +1,20 @@
-// Stream compaction for find / where / group boundaries / unique, in two kernels with a bitmask in between:
+// Stream compaction for find / where / group boundaries / unique, in three kernels with a bitmask in between:
 //
 //   select_mask_kernel   : pure streaming pass over the input (no inter-CTA dependency at all).  A warp takes 32
 //                          rows of 32 elements, every lane issues its 32 loads before the first test, each row is
 //                          balloted, and lane r keeps row r's mask — so a warp leaves ONE coalesced 128-byte store
-//                          per 1024 elements.  Traffic: the input once + n/8 bytes.
-//   select_compact_kernel: turns the mask words into ascending positions: per-thread popcounts, block scan,
-//                          decoupled look-back over tiles of 65536 elements (2048 words), then every thread
-//                          expands its own words.  It reads n/8 bytes and writes 8 bytes per hit.
+//                          per 1024 elements, plus (only when it found something) one RED of its hit count into
+//                          the counter of its 65536-element tile.  Traffic: the input once + n/8 bytes.
+//   select_offsets_kernel: one CTA turns the tile counters into exclusive offsets in place and writes the total.
+//   select_emit_kernel   : every tile with hits expands its 2048 mask words into ascending positions (per-thread
+//                          popcounts, block scan, tile offset from the table); empty tiles return without reading.
 //
 // History: a single-pass kernel with the look-back in the streaming loop measured 0.16 -> 0.33 of
 // the HBM roofline and no better when made persistent with prefetch (0.27): with ~150 tiles in flight in lock-step
 // every look-back walks 2-5 dependent L2 round trips while the CTA's other warps idle (60 % of the samples at that
-// barrier, ncu r01h).  Moving the dependency chain onto the 64x smaller mask stream takes it off the critical path.
+// barrier, ncu r01h).  Moving the dependency chain onto the 64x smaller mask stream (mask kernel + a compaction
+// kernel with decoupled look-back over the mask words) gave 0.59 at 1e8 / 0.79 at 1e9 — the chain was still there,
+// ~20 ns per 8 KB tile, 0.3 ms at 1e9.  Counting hits per tile in the mask pass removes the chain altogether.
 #pragma once
 #include "kgb_device.cuh"
 #include "kgb_internal.h"
@@ -27,12 +30,14 @@ constexpr i64 SEL_TILE = (i64)SEL_TILE_WORDS * 32;  // elements per compaction t
 
 inline size_t select_mask_words(i64 n) { return (size_t)((n + SEL_WARP_ELEMS - 1) / SEL_WARP_ELEMS) * 32; }
 inline size_t select_tiles(i64 n) { return (select_mask_words(n) + SEL_TILE_WORDS - 1) / SEL_TILE_WORDS; }
-// ws: [0,4) ticket | [64, ...) u64 look-back state per tile (both zero on entry) | mask words
-inline size_t select_state_bytes(i64 n) { return 64 + align_up(select_tiles(n) * 8, 64); }
+constexpr int SEL_TILE_STEPS = SEL_TILE_WORDS / 32;  // mask-kernel warp steps per tile
+// ws: [0,64) unused | [64, ...) u64 hit counter per tile (+1 slot for the total; zero on entry) | mask words
+inline size_t select_state_bytes(i64 n) { return 64 + align_up((select_tiles(n) + 1) * 8, 64); }
 inline size_t select_ws_bytes(i64 n) { return select_state_bytes(n) + align_up(select_mask_words(n) * 4, 64); }
 
 template <typename Pred>
-__global__ void __launch_bounds__(SEL_MASK_THREADS) select_mask_kernel(Pred pred, i64 n, u32* __restrict__ masks) {
+__global__ void __launch_bounds__(SEL_MASK_THREADS) select_mask_kernel(Pred pred, i64 n, u32* __restrict__ masks,
+                                                                        unsigned long long* __restrict__ tilecnt) {
     const int lane = threadIdx.x & 31;
     const i64 nsteps = (n + SEL_WARP_ELEMS - 1) / SEL_WARP_ELEMS;
     const i64 wstride = (i64)gridDim.x * (SEL_MASK_THREADS / 32);
@@ -70,22 +75,60 @@ __global__ void __launch_bounds__(SEL_MASK_THREADS) select_mask_kernel(Pred pred
             }
         }
         masks[step * 32 + lane] = mine;
+        const u32 hits = __reduce_add_sync(0xffffffffu, (u32)__popc(mine));
+        if (lane == 0 && hits) atomicAdd(&tilecnt[step / SEL_TILE_STEPS], (unsigned long long)hits);
     }
 }
 
-__global__ void __launch_bounds__(SEL_THREADS) select_compact_kernel(const u32* __restrict__ masks, i64 nwords,
-                                                                      i64* __restrict__ pos_out,
-                                                                      i64* __restrict__ count_out, void* ws) {
-    __shared__ u32 s_tile;
-    __shared__ u32 s_wcnt[SEL_THREADS / 32];
-    __shared__ u64 s_base;
-    u32* ticket = (u32*)ws;
-    u64* states = (u64*)((char*)ws + 64);
+// counters -> exclusive offsets, in place; cnt[ntiles] and *count_out receive the total
+__global__ void __launch_bounds__(1024) select_offsets_kernel(unsigned long long* __restrict__ cnt, i64 ntiles,
+                                                              i64* __restrict__ count_out) {
+    __shared__ unsigned long long s_w[32];
+    __shared__ unsigned long long s_carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    if (tid == 0) s_carry = 0;
     __syncthreads();
-    const i64 tile = s_tile;
-    const i64 ntiles = (nwords + SEL_TILE_WORDS - 1) / SEL_TILE_WORDS;
+    for (i64 base = 0; base < ntiles; base += 1024) {
+        const i64 i = base + tid;
+        const unsigned long long c = i < ntiles ? cnt[i] : 0ull;
+        unsigned long long inc = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long v = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += v;
+        }
+        if (lane == 31) s_w[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long w = s_w[lane], wi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned long long v = __shfl_up_sync(0xffffffffu, wi, d);
+                if (lane >= d) wi += v;
+            }
+            s_w[lane] = wi - w;  // exclusive over warps
+        }
+        __syncthreads();
+        const unsigned long long carry = s_carry;
+        if (i < ntiles) cnt[i] = carry + s_w[warp] + (inc - c);
+        __syncthreads();
+        if (tid == 1023) s_carry = carry + s_w[warp] + inc;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        cnt[ntiles] = s_carry;
+        *count_out = (i64)s_carry;
+    }
+}
+
+__global__ void __launch_bounds__(SEL_THREADS) select_emit_kernel(const u32* __restrict__ masks, i64 nwords,
+                                                                   i64* __restrict__ pos_out,
+                                                                   const unsigned long long* __restrict__ offs) {
+    __shared__ u32 s_wcnt[SEL_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const i64 tile = blockIdx.x;
+    const unsigned long long base = offs[tile];
+    if (offs[tile + 1] == base) return;  // no hit in this tile (uniform across the CTA): nothing to read or write
     const i64 w0 = tile * SEL_TILE_WORDS + (i64)tid * SEL_WPT;
     u32 m[SEL_WPT];
     if (w0 + SEL_WPT <= nwords) {
@@ -106,28 +149,13 @@ __global__ void __launch_bounds__(SEL_THREADS) select_compact_kernel(const u32* 
     }
     if (lane == 31) s_wcnt[warp] = inc;
     __syncthreads();
-    u32 woff = 0, ttotal = 0;
+    u32 woff = 0;
 #pragma unroll
     for (int w = 0; w < SEL_THREADS / 32; w++) {
         const u32 c = s_wcnt[w];
         if (w < warp) woff += c;
-        ttotal += c;
     }
-    if (warp == 0) {
-        if (lane == 0) st_relaxed_u64(&states[tile], lb_pack(tile == 0 ? KGB_LB_PREFIX : KGB_LB_AGG, 1, ttotal));
-        u64 excl = 0;
-        if (tile > 0) {
-            excl = lb_warp_lookback(states, tile, 1);
-            if (lane == 0) st_relaxed_u64(&states[tile], lb_pack(KGB_LB_PREFIX, 1, excl + ttotal));
-        }
-        if (lane == 0) {
-            s_base = excl;
-            if (tile == ntiles - 1) *count_out = (i64)(excl + ttotal);
-        }
-    }
-    if (ttotal == 0) return;  // nothing to write (uniform across the CTA)
-    __syncthreads();
-    u64 o = s_base + woff + (inc - cnt);
+    u64 o = base + woff + (inc - cnt);
 #pragma unroll
     for (int j = 0; j < SEL_WPT; j++) {
         u32 mm = m[j];
@@ -181,8 +209,11 @@ inline int launch_select(Pred pred, i64 n, i64* pos_out, i64* count_out, void* w
     long long mb = (steps + (SEL_MASK_THREADS / 32) - 1) / (SEL_MASK_THREADS / 32);
     const long long cap = (long long)sm_count() * 8;
     if (mb > cap) mb = cap;
-    select_mask_kernel<Pred><<<(unsigned)mb, SEL_MASK_THREADS, 0, st>>>(pred, n, masks);
-    select_compact_kernel<<<(unsigned)select_tiles(n), SEL_THREADS, 0, st>>>(masks, (i64)nwords, pos_out, count_out, ws);
+    unsigned long long* tilecnt = (unsigned long long*)((char*)ws + 64);
+    const i64 ntiles = (i64)select_tiles(n);
+    select_mask_kernel<Pred><<<(unsigned)mb, SEL_MASK_THREADS, 0, st>>>(pred, n, masks, tilecnt);
+    select_offsets_kernel<<<1, 1024, 0, st>>>(tilecnt, ntiles, count_out);
+    select_emit_kernel<<<(unsigned)ntiles, SEL_THREADS, 0, st>>>(masks, (i64)nwords, pos_out, tilecnt);
     KGB_CUDA_CHECK(cudaGetLastError());
     return KGB_OK;
 }

@@ -7,6 +7,7 @@ control flow) — no device value ever falls back to NumPy
 """
 import ctypes
 import struct
+import threading
 
 import numpy as np
 import torch
@@ -511,14 +512,32 @@ def group(a):
     return DeviceArray(order), DeviceArray(starts[: g + 1]), g
 
 
+_slots = threading.local()
+
+
+def _count_slot(dev):
+    """One 8-byte result slot per (thread, device): pinned host memory on a GPU, plain memory on the test double."""
+    d = getattr(_slots, "d", None)
+    if d is None:
+        d = _slots.d = {}
+    t = d.get(dev)
+    if t is None:
+        t = d[dev] = torch.zeros(1, dtype=torch.int64, pin_memory=(dev.type == "cuda"))
+    return t
+
+
 def _select(fn_name, a, needle=None):
     a = contiguous(a)
     dev = a._t.device
     lib, stream = _lib_for(dev)
     kdt = kgb_dtype(a._t)
     n = a._t.numel()
+    if not n:
+        return DeviceArray(torch.empty(0, dtype=torch.int64, device=dev))
     pos = torch.empty(n, dtype=torch.int64, device=dev)
-    cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+    # the match count is the one value the host needs: the kernel writes it straight into pinned (device-visible) host
+    # memory, so the read-back is a stream synchronise and no copy
+    cnt = _count_slot(dev)
     if n:
         wsb = ctypes.c_size_t()
         _lib.check(lib.kgb_select_workspace_bytes(n, ctypes.byref(wsb)))
@@ -529,8 +548,11 @@ def _select(fn_name, a, needle=None):
         else:
             _lib.check(lib.kgb_nonzero(a._t.data_ptr(), kdt, n, pos.data_ptr(), cnt.data_ptr(), ws.data_ptr(),
                                        wsb.value, stream), "kgb_nonzero")
-    c = int(cnt.item()) if n else 0
-    return DeviceArray(pos[:c])
+    if dev.type == "cuda":
+        torch.cuda.current_stream(dev).synchronize()
+    c = int(cnt[0])
+    res = pos[:c]
+    return DeviceArray(res.clone() if 2 * c < n else res)  # do not pin n words of storage under a short result
 
 
 def find_equal(a, b):
