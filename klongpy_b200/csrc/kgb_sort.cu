@@ -29,6 +29,16 @@ constexpr int SI = 8;              // keys per thread (8 x (u64 key + u32 pos + 
                                    // two 512-thread CTAs fit an SM's register file; 16/thread ran at 25 % occupancy)
 constexpr int LB = 2;              // look-back states fetched per round (independent loads, one L2 round trip)
 constexpr int STILE = ST * SI;     // 4096 keys per tile
+// geometry of the persistent pipelined pass (see onesweep_pass_p)
+#ifndef KGB_SORT_PT
+#define KGB_SORT_PT 512   // compute threads
+#define KGB_SORT_PSI 8    // keys per compute thread (even)
+#define KGB_SORT_PD 2     // tiles parked while their look-back runs
+#endif
+#ifndef KGB_SORT_OCC
+#define KGB_SORT_OCC 1    // persistent CTAs per SM
+#endif
+constexpr int MIN_TILE = (KGB_SORT_PT * KGB_SORT_PSI < STILE) ? KGB_SORT_PT * KGB_SORT_PSI : STILE;  // sizes the look-back states
 constexpr int SWARPS = ST / 32;
 
 struct SortPlan {
@@ -51,7 +61,7 @@ struct SortWs {
 
 static SortWs carve(void* ws, i64 n) {
     SortWs w;
-    const size_t tiles = (size_t)((n + STILE - 1) / STILE);
+    const size_t tiles = (size_t)((n + MIN_TILE - 1) / MIN_TILE);
     char* p = (char*)ws;
     size_t o = 0;
     w.plan = (SortPlan*)(p + o);
@@ -361,11 +371,6 @@ __global__ void __launch_bounds__(ST, 2) onesweep_pass(const typename KeyCodec<D
 //     critical path, with two tile periods of slack.
 // Tiles come from the per-pass atomic ticket (no co-residency assumption).  64-bit key types only; the first pass
 // needs 16-byte aligned caller keys (else the one-tile-per-CTA kernel above runs).
-#ifndef KGB_SORT_PT
-#define KGB_SORT_PT 512   // compute threads
-#define KGB_SORT_PSI 8    // keys per compute thread (even)
-#define KGB_SORT_PD 2     // tiles parked while their look-back runs
-#endif
 constexpr int PT = KGB_SORT_PT, PLT = 256, PP = 1, PD = KGB_SORT_PD, PNS = PP + PD + 1, PRING = 8;
 constexpr int PSI = KGB_SORT_PSI;
 constexpr int PTILE = PT * PSI;  // keys per tile of the pipelined pass
@@ -419,7 +424,7 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, %0;" ::"n"(PT) : "memory"); }
 
 template <int DT>
-__global__ void __launch_bounds__(PT + PLT, 1) onesweep_pass_p(const typename KeyCodec<DT>::T* __restrict__ in_keys,
+__global__ void __launch_bounds__(PT + PLT, KGB_SORT_OCC) onesweep_pass_p(const typename KeyCodec<DT>::T* __restrict__ in_keys,
                                                                 u64* keysA, u64* keysB, u32* idxA, u32* idxB,
                                                                 i64* __restrict__ idx_out,
                                                                 typename KeyCodec<DT>::T* __restrict__ keys_sorted_out,
@@ -709,7 +714,8 @@ template <int DT> struct PipeLauncher<DT, true> {
             attr_set[dev] = true;
         }
         const unsigned ptiles = (unsigned)((n + PTILE - 1) / PTILE);
-        const unsigned grid = ptiles < (unsigned)sm_count() ? ptiles : (unsigned)sm_count();
+        const unsigned cap = (unsigned)sm_count() * KGB_SORT_OCC;
+        const unsigned grid = ptiles < cap ? ptiles : cap;
         (void)tiles;
         onesweep_pass_p<DT><<<grid, PT + PLT, sizeof(PipeSmem), st>>>((const T*)keys, w.keys[0], w.keys[1], w.idx[0], w.idx[1],
                                                                       idx_out, (T*)keys_sorted_out, enc_sorted_out, w.plan, p,
