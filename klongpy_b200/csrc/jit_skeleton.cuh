@@ -64,8 +64,22 @@ template <> struct kgb_lim<u8> {
 
 // np.maximum / np.minimum: NaN-propagating for floats
 // (a NaN -> a; b NaN -> b because a > NaN is false: two compares instead of three)
-__device__ __forceinline__ double kgb_max(double a, double b) { return (a != a || a > b) ? a : b; }
-__device__ __forceinline__ double kgb_min(double a, double b) { return (a != a || a < b) ? a : b; }
+// NaN-propagating float64 max / min (np.maximum / np.minimum): `(a != a || a > b) ? a : b`, spelled in PTX so that it
+// is two DSETP (the second OR-ed with the first) and one 64-bit select.  The C++ form compiles to two DSETP + four
+// FSEL and, inside the unrolled scan loops, to divergent branches (BSSY/BRA/BSYNC): 56 instructions per element in
+// `|/(|\x)-x` (ncu r01v), 26 of them selects and compares, 6.5 branch bookkeeping.
+__device__ __forceinline__ double kgb_max(double a, double b) {
+    double r;
+    asm("{ .reg .pred p, q; setp.nan.f64 p, %1, %1; setp.gt.or.f64 q, %1, %2, p; selp.f64 %0, %1, %2, q; }"
+        : "=d"(r) : "d"(a), "d"(b));
+    return r;
+}
+__device__ __forceinline__ double kgb_min(double a, double b) {
+    double r;
+    asm("{ .reg .pred p, q; setp.nan.f64 p, %1, %1; setp.lt.or.f64 q, %1, %2, p; selp.f64 %0, %1, %2, q; }"
+        : "=d"(r) : "d"(a), "d"(b));
+    return r;
+}
 __device__ __forceinline__ float kgb_max(float a, float b) { return (a != a || a > b) ? a : b; }
 __device__ __forceinline__ float kgb_min(float a, float b) { return (a != a || a < b) ? a : b; }
 __device__ __forceinline__ i64 kgb_max(i64 a, i64 b) { return a > b ? a : b; }
@@ -922,7 +936,11 @@ extern "C" __global__ void __launch_bounds__(KGB_PT + 32 * KGB_PLW, KGB_PMINB) K
     };
 
     // phase B: parked tile + exclusive prefix -> global, stripe-wise
+#if KGB_MODE == 2
     auto phase_b = [&](u32 li, u32 t) {
+#else
+    auto phase_b = [&](u32 li, u32 t, KGB_ACC_T te) {
+#endif
         const u32 s = li % KGB_PS;
         kgb_mbar_wait(&ctl.pre_bar[s], (li / KGB_PS) & 1u);
         const KGB_ACC_T excl = ctl.excl[s];
@@ -950,35 +968,29 @@ extern "C" __global__ void __launch_bounds__(KGB_PT + 32 * KGB_PLW, KGB_PMINB) K
             }
         }
 #else
-        // arguments re-read stripe-wise from global memory (L2: the tile streamed through a few microseconds ago)
-        if (full) {
-            KGB_DECL_REGS(2 * KGB_PCT)
+        // Mode 3 never stores the scan: phase A only REDUCES the thread's row (nothing is written back to the stage), and
+        // here the same thread re-reads its raw row, re-runs the serial scan from (tile prefix (+) its exclusive prefix
+        // inside the tile, kept in a register since phase A) and folds the epilogue g(scan value, x) on the fly.  The
+        // pipelined kernel exists only for programs with ONE array argument, so g's operand is the staged row itself:
+        // no global re-read (the stripe-wise L2 re-read stalled the 8 compute warps: ncu r01v, DADD behind LDG).
+        {
+            KGB_ACC_T run = KGB_RED(excl, te);
+            KGB_DECL_REGS(KGB_PITEMS)
 #pragma unroll
-            for (int h = 0; h < KGB_PCT; h++) {
-                const int cf = h * KGB_PT + tid;
-                KGB_LOAD_VEC(2, h * 2, base + cf * 2)
-            }
+            for (int q = 0; q < KGB_PCR; q++)
+                *reinterpret_cast<uint4*>(&KGB_PIPE_ARG[q * 2]) = *reinterpret_cast<const uint4*>(sb + kgb_swz(tid, q));
+            if (full) {
 #pragma unroll
-            for (int h = 0; h < KGB_PCT; h++) {
-                const int cf = h * KGB_PT + tid;
-                KGB_ACC_T v[2];
-                *reinterpret_cast<uint4*>(v) = *reinterpret_cast<const uint4*>(sb + kgb_swz(cf / KGB_PCR, cf % KGB_PCR));
-#pragma unroll
-                for (int j = 0; j < 2; j++) {
-                    KGB_ACC2_T e2 = (KGB_ACC2_T)(KGB_EVAL2(h * 2 + j, KGB_RED(excl, v[j])));
+                for (int k = 0; k < KGB_PITEMS; k++) {
+                    run = KGB_RED(run, (KGB_ACC_T)(KGB_EVAL(k)));
+                    KGB_ACC2_T e2 = (KGB_ACC2_T)(KGB_EVAL2(k, run));
                     r2 = KGB_RED2(r2, e2);
                 }
-            }
-        } else {
-            for (int h = 0; h < KGB_PCT; h++) {
-                const int cf = h * KGB_PT + tid;
-                KGB_ACC_T v[2];
-                *reinterpret_cast<uint4*>(v) = *reinterpret_cast<const uint4*>(sb + kgb_swz(cf / KGB_PCR, cf % KGB_PCR));
-                for (int j = 0; j < 2; j++) {
-                    if (base + cf * 2 + j < n) {
-                        KGB_DECL_REGS(1)
-                        KGB_LOAD_VEC(1, 0, base + cf * 2 + j)
-                        KGB_ACC2_T e2 = (KGB_ACC2_T)(KGB_EVAL2(0, KGB_RED(excl, v[j])));
+            } else {
+                for (int k = 0; k < KGB_PITEMS; k++) {
+                    if (base + tid * KGB_PITEMS + k < n) {
+                        run = KGB_RED(run, (KGB_ACC_T)(KGB_EVAL(k)));
+                        KGB_ACC2_T e2 = (KGB_ACC2_T)(KGB_EVAL2(k, run));
                         r2 = KGB_RED2(r2, e2);
                     }
                 }
@@ -991,6 +1003,11 @@ extern "C" __global__ void __launch_bounds__(KGB_PT + 32 * KGB_PLW, KGB_PMINB) K
     for (int j = 0; j < KGB_PP; j++) issue_load((u32)j);
 
     u32 tq[KGB_PD];  // tiles parked in shared memory, oldest first
+#if KGB_MODE == 3
+    KGB_ACC_T teq[KGB_PD];  // this thread's exclusive prefix inside each parked tile
+#pragma unroll
+    for (int j = 0; j < KGB_PD; j++) teq[j] = (KGB_ACC_T)(KGB_RED_IDENT);
+#endif
 #pragma unroll
     for (int j = 0; j < KGB_PD; j++) tq[j] = 0xffffffffu;
     u32 tk = 0;
@@ -1003,9 +1020,17 @@ extern "C" __global__ void __launch_bounds__(KGB_PT + 32 * KGB_PLW, KGB_PMINB) K
         }
         const u32 tile = ctl.tile_ring[i % KGB_PRING];
         if (tile >= ntiles) break;
+#if KGB_MODE == 2
         issue_load(i + KGB_PP);
         asm volatile("cp.async.wait_group %0;" ::"n"(KGB_PP) : "memory");
         kgb_bar_compute();
+#else
+        // mode 3 reads the parked stage row-wise in phase B (not with the cp.async mapping), so the load that recycles
+        // a stage is issued only after the barrier that puts every thread past that stage's phase B
+        asm volatile("cp.async.wait_group %0;" ::"n"(KGB_PP - 1) : "memory");
+        kgb_bar_compute();
+        issue_load(i + KGB_PP);
+#endif
 
         // ---- phase A
         unsigned char* sb = stages + (size_t)s * KGB_PSTAGE_BYTES;
@@ -1053,6 +1078,7 @@ extern "C" __global__ void __launch_bounds__(KGB_PT + 32 * KGB_PLW, KGB_PMINB) K
             ctl.aggtile[s] = tile;
             kgb_mbar_arrive(&ctl.agg_bar[s]);
         }
+#if KGB_MODE == 2
 #pragma unroll
         for (int k = 0; k < KGB_PITEMS; k++) x[k] = KGB_RED(thread_excl, x[k]);
 #pragma unroll
@@ -1063,6 +1089,12 @@ extern "C" __global__ void __launch_bounds__(KGB_PT + 32 * KGB_PLW, KGB_PMINB) K
 
         // ---- phase B of the tile parked D iterations ago
         if (tq[0] != 0xffffffffu) phase_b(i - KGB_PD, tq[0]);
+#else
+        if (tq[0] != 0xffffffffu) phase_b(i - KGB_PD, tq[0], teq[0]);
+#pragma unroll
+        for (int j = 0; j < KGB_PD - 1; j++) teq[j] = teq[j + 1];
+        teq[KGB_PD - 1] = thread_excl;
+#endif
 #pragma unroll
         for (int j = 0; j < KGB_PD - 1; j++) tq[j] = tq[j + 1];
         tq[KGB_PD - 1] = tile;
@@ -1071,8 +1103,13 @@ extern "C" __global__ void __launch_bounds__(KGB_PT + 32 * KGB_PLW, KGB_PMINB) K
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     kgb_bar_compute();
 #pragma unroll
-    for (int j = 0; j < KGB_PD; j++)
+    for (int j = 0; j < KGB_PD; j++) {
+#if KGB_MODE == 2
         if (tq[j] != 0xffffffffu) phase_b(i - KGB_PD + j, tq[j]);
+#else
+        if (tq[j] != 0xffffffffu) phase_b(i - KGB_PD + j, tq[j], teq[j]);
+#endif
+    }
     kgb_bar_compute();
     if (tid == 0) {
         // release the look-back warps: one sentinel per warp, on the stages of the next KGB_PLW local indices

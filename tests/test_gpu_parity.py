@@ -279,6 +279,35 @@ def test_reduce_nan_and_overflow(be, K):
     assert K.reduce("add", dev(be, np.zeros(0))).item() == 0.0
 
 
+@pytest.mark.parametrize("n", [257, 70_001, 6_000_011])
+def test_max_min_with_nan_inf_and_signed_zero(be, K, n):
+    """np.maximum / np.minimum semantics (NaN from either side propagates and sticks; +-inf; +-0) through every kernel
+    family that folds with max/min: elementwise, reduce, scan (generic and pipelined) and scan+reduce."""
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal(n)
+    y = rng.standard_normal(n)
+    sp = rng.choice(n, size=min(64, n // 4), replace=False)
+    x[sp[0::4]] = np.inf
+    x[sp[1::4]] = -np.inf
+    x[sp[2::4]] = 0.0
+    y[sp[2::4]] = -0.0
+    y[sp[3::4]] = np.nan
+    X, Y = dev(be, x), dev(be, y)
+    for name, f in (("max", np.maximum), ("min", np.minimum)):
+        assert np.array_equal(host(K.binary(name, X, Y)), f(x, y), equal_nan=True), name
+        assert np.array_equal(host(K.binary(name, Y, X)), f(y, x), equal_nan=True), name
+        assert np.array_equal(host(K.scan(name, X)), f.accumulate(x), equal_nan=True), name     # no NaN: +-inf stick
+        assert np.array_equal(host(K.scan(name, Y)), f.accumulate(y), equal_nan=True), name     # NaN from its first index on
+        assert np.array_equal(host(K.reduce(name, X)), f.reduce(x), equal_nan=True), name
+        assert np.isnan(K.reduce(name, Y).item()), name
+    # drawdown |/(|\x)-x before the first NaN-free prefix ends, and with a clean vector
+    ir = ("reduce", "|", ("binop", "-", ("scan", "|", ("var", "_v0")), ("var", "_v0")))
+    fn, _ = be.compile_expr_ir(ir, ["x"])
+    z = rng.standard_normal(n)
+    assert fn(dev(be, z)).item() == float(np.max(np.maximum.accumulate(z) - z))
+    assert np.isnan(fn(Y).item())
+
+
 @pytest.mark.parametrize("n", [1, 2, 4095, 4096, 4097, 8193, 100_003, 10_000_019])
 def test_scan_parity(be, K, n):
     rng = np.random.default_rng(n + 2)
