@@ -742,6 +742,9 @@ extern "C" __global__ void __launch_bounds__(KGB_SBLOCK) KGB_KERNEL_NAME_S(const
 //   phase B (i-D)  : D tiles later the prefix is (almost always) already there: stripe-wise read of the parked
 //                    tile, add the prefix, coalesced 128-bit streaming stores.  No transposition on the way out —
 //                    adding a scalar does not care about layout.
+// Mode 3 (scan + reduce epilogue) stores nothing: phase A only reduces the row (no write-back), phase B re-reads the
+// raw row, re-scans it from (tile prefix (+) the thread's exclusive prefix, kept in a register) and folds the epilogue;
+// because that read is row-wise, the load that recycles a stage is issued after the barrier (mode 2 issues it before).
 // Tiles come from the same atomic ticket as the generic kernel, so no co-residency assumption is made.
 #ifndef KGB_PT
 #define KGB_PT 256   // compute threads (256 or 512); a tile is always 4096 elements
@@ -980,12 +983,29 @@ extern "C" __global__ void __launch_bounds__(KGB_PT + 32 * KGB_PLW, KGB_PMINB) K
             for (int q = 0; q < KGB_PCR; q++)
                 *reinterpret_cast<uint4*>(&KGB_PIPE_ARG[q * 2]) = *reinterpret_cast<const uint4*>(sb + kgb_swz(tid, q));
             if (full) {
+                // two half-rows scanned independently (the second from its own first element), then the first half's
+                // total is folded into the second: 7 more folds, but dependent chains of 8 + 1 instead of 16; the
+                // epilogue folds into four accumulators for the same reason
+                constexpr int H = KGB_PITEMS / 2;
+                KGB_ACC_T sv[KGB_PITEMS];
+                sv[0] = KGB_RED(run, (KGB_ACC_T)(KGB_EVAL(0)));
+                sv[H] = (KGB_ACC_T)(KGB_EVAL(H));
 #pragma unroll
-                for (int k = 0; k < KGB_PITEMS; k++) {
-                    run = KGB_RED(run, (KGB_ACC_T)(KGB_EVAL(k)));
-                    KGB_ACC2_T e2 = (KGB_ACC2_T)(KGB_EVAL2(k, run));
-                    r2 = KGB_RED2(r2, e2);
+                for (int k = 1; k < H; k++) {
+                    sv[k] = KGB_RED(sv[k - 1], (KGB_ACC_T)(KGB_EVAL(k)));
+                    sv[H + k] = KGB_RED(sv[H + k - 1], (KGB_ACC_T)(KGB_EVAL(H + k)));
                 }
+#pragma unroll
+                for (int k = H; k < KGB_PITEMS; k++) sv[k] = KGB_RED(sv[H - 1], sv[k]);
+                KGB_ACC2_T q2[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) q2[k] = (KGB_ACC2_T)(KGB_EVAL2(k, sv[k]));
+#pragma unroll
+                for (int k = 4; k < KGB_PITEMS; k++) {
+                    KGB_ACC2_T e2 = (KGB_ACC2_T)(KGB_EVAL2(k, sv[k]));
+                    q2[k & 3] = KGB_RED2(q2[k & 3], e2);
+                }
+                r2 = KGB_RED2(r2, KGB_RED2(KGB_RED2(q2[0], q2[1]), KGB_RED2(q2[2], q2[3])));
             } else {
                 for (int k = 0; k < KGB_PITEMS; k++) {
                     if (base + tid * KGB_PITEMS + k < n) {
@@ -1048,9 +1068,20 @@ extern "C" __global__ void __launch_bounds__(KGB_PT + 32 * KGB_PLW, KGB_PMINB) K
                 if (!full && base + tid * KGB_PITEMS + k >= n) x[k] = (KGB_ACC_T)(KGB_RED_IDENT);
             }
         }
+#if KGB_MODE == 2
 #pragma unroll
         for (int k = 1; k < KGB_PITEMS; k++) x[k] = KGB_RED(x[k - 1], x[k]);
         KGB_ACC_T inc = x[KGB_PITEMS - 1];
+#else
+        // only the row total is needed here: a pairwise tree (depth log2 instead of a 15-long dependent chain; with 8
+        // compute warps per SM the float64 compare/select latency is what the kernel waits for)
+#pragma unroll
+        for (int w = 1; w < KGB_PITEMS; w <<= 1) {
+#pragma unroll
+            for (int k = 0; k + w < KGB_PITEMS; k += 2 * w) x[k] = KGB_RED(x[k], x[k + w]);
+        }
+        KGB_ACC_T inc = x[0];
+#endif
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             KGB_ACC_T o = kgb_shfl_up<KGB_ACC_T>(inc, d);
