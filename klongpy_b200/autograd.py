@@ -72,6 +72,20 @@ def run_differentiable(code, args, mode, red, code2, red2, out_shape, device):
     return DeviceArray(out)
 
 
+def run_differentiable2(code, red, code2, red2, args, device):
+    """ops.reduce2 (two folds in one pass) for operands that require grad: ONE autograd node with two outputs; its
+    backward is one fused kernel per differentiated operand for BOTH incoming gradients."""
+    if red != _lib.RED_ADD or red2 != _lib.RED_ADD:
+        raise NotDifferentiable("paired reductions are differentiated for +/ only")
+    autodiff.parse(code)
+    autodiff.parse(code2)
+    tensors = [a._t for a in args if isinstance(a, DeviceArray)]
+    template = [_TENSOR if isinstance(a, DeviceArray) else a for a in args]
+    spec = _Spec(code, _lib.MODE_REDUCE, red, template, None, device)
+    o1, o2 = _Launch2.apply(spec, tuple(code2), *tensors)
+    return DeviceArray(o1), DeviceArray(o2)
+
+
 def _sum_to(x, shape):
     """gradient of a broadcast scalar operand: fold the elementwise gradient"""
     if x.ndim == 0:
@@ -98,6 +112,96 @@ def _grad_prog(code, pos, n_args, gated):
                                                             autodiff.ZERO))
             _prog_cache[key] = tuple(autodiff.emit(("op", "to_f64", tree)))
     return _prog_cache[key]
+
+
+def _grad_prog2(code, code2, pos, n_args):
+    """g1 * d f1/d(arg pos) + g2 * d f2/d(arg pos) over (args..., g1, g2) as one postfix program (None if both vanish)."""
+    key = (code, code2, pos, n_args, "pair")
+    if key not in _prog_cache:
+        t1 = autodiff.tangent(autodiff.parse(code), pos)
+        t2 = autodiff.tangent(autodiff.parse(code2), pos)
+        terms = []
+        if not autodiff._is(t1, 0.0):
+            terms.append(autodiff.op("mul", ("arg", n_args), t1))
+        if not autodiff._is(t2, 0.0):
+            terms.append(autodiff.op("mul", ("arg", n_args + 1), t2))
+        if not terms:
+            _prog_cache[key] = None
+        else:
+            tree = terms[0] if len(terms) == 1 else autodiff.op("add", terms[0], terms[1])
+            _prog_cache[key] = tuple(autodiff.emit(("op", "to_f64", tree)))
+    return _prog_cache[key]
+
+
+def _fold_scalars(pending, grads):
+    """Gradients of 0-d operands are folds of an elementwise program over the same arguments: two at a time share one
+    pass (two-output reduce), e.g. dL/dw and dL/db of a dense layer."""
+    k = 0
+    while k < len(pending):
+        if k + 1 < len(pending) and pending[k][2] is pending[k + 1][2]:
+            (ia, pa, full, ta), (ib, pb, _, tb) = pending[k], pending[k + 1]
+            try:
+                ra, rb = ops.reduce2(pa, _lib.RED_ADD, pb, _lib.RED_ADD, full)
+                grads[ia] = ra._t.reshape(ta.shape).to(ta.dtype)
+                grads[ib] = rb._t.reshape(tb.shape).to(tb.dtype)
+                k += 2
+                continue
+            except (ValueError, _lib.KgbError):
+                pass
+        i, prog, full, t = pending[k]
+        r = ops.run(prog, full, mode=_lib.MODE_REDUCE, red=_lib.RED_ADD)
+        grads[i] = r._t.reshape(t.shape).to(t.dtype)
+        k += 1
+
+
+class _Launch2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, spec, code2, *tensors):
+        with torch.no_grad():
+            o1, o2 = ops.reduce2(spec.code, spec.red, code2, _lib.RED_ADD, spec.rebuild(tensors))
+        ctx.spec, ctx.code2 = spec, code2
+        ctx.save_for_backward(*tensors)
+        for o in (o1, o2):
+            if not o._t.dtype.is_floating_point:
+                ctx.mark_non_differentiable(o._t)
+        return o1._t, o2._t
+
+    @staticmethod
+    def backward(ctx, g1, g2):
+        spec = ctx.spec
+        tensors = ctx.saved_tensors
+        with torch.no_grad():
+            args = spec.rebuild(tensors)
+            n_args = len(args)
+            dev = tensors[0].device
+            z = None
+
+            def scalar(g):
+                nonlocal z
+                if g is None:
+                    if z is None:
+                        z = torch.zeros((), dtype=torch.float64, device=dev)
+                    return DeviceArray(z)
+                return DeviceArray(g.contiguous().to(torch.float64))
+
+            full = args + [scalar(g1), scalar(g2)]
+            grads = [None, None] + [None] * len(tensors)
+            pending = []
+            slots = [k for k, s in enumerate(spec.template) if s is _TENSOR]
+            for j, pos in enumerate(slots):
+                t = tensors[j]
+                if not ctx.needs_input_grad[j + 2] or not t.dtype.is_floating_point:
+                    continue
+                prog = _grad_prog2(spec.code, ctx.code2, pos, n_args)
+                if prog is None:
+                    grads[j + 2] = torch.zeros_like(t)
+                elif t.dim() > 0:
+                    r = ops.run(prog, full)
+                    grads[j + 2] = r._t.to(t.dtype) if r._t.shape == t.shape else _sum_to(r, t.shape).to(t.dtype)
+                else:
+                    pending.append((j + 2, prog, full, t))
+            _fold_scalars(pending, grads)
+        return tuple(grads)
 
 
 class _Launch(torch.autograd.Function):
@@ -133,6 +237,8 @@ class _Launch(torch.autograd.Function):
                 extra = [G, DeviceArray(out), cnt]  # ties share the gradient evenly, like torch.amax
                 gate = True
             grads = [None]
+            pending = []
+            full = args + extra
             slots = [k for k, s in enumerate(spec.template) if s is _TENSOR]
             for j, pos in enumerate(slots):
                 t = tensors[j]
@@ -143,19 +249,20 @@ class _Launch(torch.autograd.Function):
                 if prog is None:
                     grads.append(torch.zeros_like(t))
                     continue
-                full = args + extra
                 elementwise = t.dim() > 0
                 if elementwise:
                     r = ops.run(prog, full, out_shape=tuple(t.shape) if t.numel() == 0 else None)
                     grads.append(r._t.to(t.dtype) if r._t.shape == t.shape else _sum_to(r, t.shape).to(t.dtype))
                 else:
                     # a 0-d operand broadcast against arrays: its gradient is the FOLD of the elementwise gradient —
-                    # one fused reduce kernel, nothing materialised
+                    # one fused reduce kernel, nothing materialised (two such operands share one pass)
                     if any(isinstance(a, DeviceArray) and a.ndim > 0 for a in full):
-                        r = ops.run(prog, full, mode=_lib.MODE_REDUCE, red=_lib.RED_ADD)
+                        grads.append(None)
+                        pending.append((len(grads) - 1, prog, full, t))
                     else:
                         r = ops.run(prog, full, out_shape=())
-                    grads.append(r._t.reshape(t.shape).to(t.dtype))
+                        grads.append(r._t.reshape(t.shape).to(t.dtype))
+            _fold_scalars(pending, grads)
         return tuple(grads)
 
 
@@ -163,7 +270,10 @@ class _Launch(torch.autograd.Function):
 def create_grad_tensor(backend, x):
     """A float64 leaf that tracks gradients (the reference casts to float32, torch_backend.py:692-699)."""
     if isinstance(x, DeviceArray):
-        t = x._t.detach().clone().to(torch.float64)
+        # a detached alias, not a copy: device arrays are never modified in place (amend builds a new array), and a
+        # clone of a 1e7-element parameter vector costs as much as the fused forward kernel
+        t = x._t.detach()
+        t = t.to(torch.float64) if t.dtype != torch.float64 else t
     elif isinstance(x, torch.Tensor):
         t = x.detach().clone().to(device=backend._device, dtype=torch.float64)
     else:

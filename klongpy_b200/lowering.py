@@ -16,7 +16,7 @@ Anything the kernels do not support RAISES, so the interpreter's silent fallback
 """
 import numpy as np
 
-from . import _lib, ops
+from . import _lib, autodiff, ops
 from .array import DeviceArray
 
 _BIN = {"+": "add", "-": "sub", "*": "mul", "%": "div", "^": "pow"}
@@ -249,13 +249,12 @@ def make_callable(ir):
                 other, code_b, slots = st.pair
                 pargs = [vals[s] for s in slots]
                 lens = {a.size for a in pargs if _is_arraylike(a)}
-                grad = any(isinstance(a, DeviceArray) and a.requires_grad for a in pargs)
-                if len(lens) == 1 and 0 not in lens and not grad:
+                if len(lens) == 1 and 0 not in lens:
                     try:
                         vals[st.out_slot], vals[other.out_slot] = ops.reduce2(st.code, st.red, code_b, other.red, pargs)
                         continue
-                    except _lib.KgbError:
-                        pass  # e.g. a narrow accumulator: run the two reductions separately
+                    except (_lib.KgbError, autodiff.NotDifferentiable):
+                        pass  # a narrow accumulator, or a fold without a gradient rule: two separate reductions
             sargs = [vals[s] for s in st.slots]
             has_array = any(_is_arraylike(a) for a in sargs)
             if st.mode != _lib.MODE_MAP and not has_array:

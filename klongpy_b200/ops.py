@@ -259,8 +259,6 @@ def reduce2(code, red, code2, red2, args):
     n = None
     for a in args:
         if isinstance(a, DeviceArray):
-            if a._t.requires_grad and torch.is_grad_enabled():
-                raise NotImplementedError("two-output reduce is not on the autograd tape")
             device = a._t.device
             if a._t.dim() > 0:
                 m = a._t.numel()
@@ -271,6 +269,9 @@ def reduce2(code, red, code2, red2, args):
         raise ValueError("reduce2 needs a non-empty device array operand")
     red = RED[red] if not isinstance(red, int) else red
     red2 = RED[red2] if not isinstance(red2, int) else red2
+    if torch.is_grad_enabled() and any(isinstance(a, DeviceArray) and a._t.requires_grad for a in args):
+        from . import autograd  # one two-output node on the tape (raises NotDifferentiable for folds other than +/)
+        return autograd.run_differentiable2(code, red, code2, red2, args, device)
     lib, stream = _lib_for(device)
     cls = [_classify(a, device) for a in args]
     kinds, dts = tuple(c[0] for c in cls), tuple(c[1] for c in cls)

@@ -137,6 +137,55 @@ def test_non_scalar_loss_raises(interp):
         klong("{x*2}:>[1.0 2.0]")
 
 
+def test_paired_reductions_stay_paired_under_autograd(monkeypatch):
+    """Compiled trees with two +/ over the same operands (Sharpe, VWAP) run as ONE two-output reduce forward and ONE
+    fused gradient kernel backward; two scalar parameters of one node share one two-output fold.  Checked against
+    closed forms, with the launches counted."""
+    import fake_lib
+    dev = fake_lib.install()
+    import klongpy_b200 as kb
+    from klongpy_b200 import ops
+    be = kb.B200BackendProvider(device=dev)
+    rng = np.random.default_rng(8)
+    n = 4099
+    r, v, w = rng.uniform(0.01, 0.15, n), rng.uniform(0.05, 0.4, n), np.full(n, 1.0 / n)
+    sharpe_ir = ("binop", "%", ("reduce", "+", ("binop", "*", ("var", "_v0"), ("var", "_v1"))),
+                 ("binop", "^", ("reduce", "+", ("binop", "*", ("binop", "^", ("var", "_v0"), ("literal", 2)),
+                                                 ("binop", "^", ("var", "_v2"), ("literal", 2)))), ("literal", 0.5)))
+    sharpe, _ = be.compile_expr_ir(sharpe_ir, ["x", "returns", "vols"])
+    R, V, W = be.kg_asarray(r), be.kg_asarray(v), be.kg_asarray(w)
+    calls = {"run": 0, "reduce2": 0}
+    real_run, real_r2 = ops.run, ops.reduce2
+
+    def run(*a, **k):
+        calls["run"] += 1
+        return real_run(*a, **k)
+
+    def reduce2(*a, **k):
+        calls["reduce2"] += 1
+        return real_r2(*a, **k)
+
+    monkeypatch.setattr(ops, "run", run)
+    monkeypatch.setattr(ops, "reduce2", reduce2)
+    got = be.compute_autograd(lambda x: sharpe(x, R, V), W).to_numpy()
+    A, B = np.sum(w * r), np.sum(w * w * v * v)
+    assert np.allclose(got, r / np.sqrt(B) - A * w * v * v / B ** 1.5, rtol=1e-10)
+    assert calls["reduce2"] >= 1                       # forward: one two-output kernel, not two reductions
+    big = calls["run"]
+    # dense layer: two scalar parameters inside ONE compiled tree -> their folds share a pass
+    X, Y = rng.random(n), rng.random(n)
+    ir = ("reduce", "+", ("binop", "^", ("binop", "-", ("binop", "+", ("binop", "*", ("var", "_v0"), ("var", "_v1")), ("var", "_v2")),
+                                         ("var", "_v3")), ("literal", 2)))   # variables are numbered in first-reference order
+    fn, _ = be.compile_expr_ir(ir, ["w", "X", "b", "Y"])
+    DX, DY = be.kg_asarray(X), be.kg_asarray(Y)
+    calls["reduce2"] = 0
+    gw, gb = be.compute_multi_autograd(lambda p: fn(p[0], DX, p[1], DY), [0.3, -0.2])
+    d = 2 * (0.3 * X - 0.2 - Y)
+    assert np.allclose([float(gw.to_numpy()), float(gb.to_numpy())], [np.sum(d * X), np.sum(d)], rtol=1e-10)
+    assert calls["reduce2"] == 1, calls                # dL/dw and dL/db: one pass over X, Y
+    assert big <= 8, calls
+
+
 # ------------------------------------------------------------------------------------------- GPU: fused kernels vs torch f64
 @pytest.mark.gpu
 def test_gpu_sigmoid_and_sharpe_vs_torch(cuda_backend):
