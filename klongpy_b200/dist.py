@@ -12,6 +12,10 @@ expressions need no exchange.  The primitives with a real exchange step:
   * grouped min/mean/max : per-rank partial G x 4 tables -> all_to_all of the per-owner table slices
     (station block s // B owned by rank s // B) -> merge -> all_gather of the final slices.
 
+  * find `a?b` : local compaction -> all_gather of (shard length, hit count) -> global positions (sharded_find).
+  * autograd : the loss `+/` is a sharded reduce whose tape holds only the local fused node (sharded_loss_sum);
+    vector gradients stay sharded, scalar-parameter gradients are summed rank-ordered (combine_param_grads).
+
 Messages are tiny (8 B .. 320 KB): they are latency-, not bandwidth-bound, so each primitive does exactly one
 or two collectives.
 """
@@ -151,6 +155,58 @@ def sharded_groupagg(keys, vals, n_groups):
     tabs = full.view(w, 4, B).permute(1, 0, 2).reshape(4, w * B)[:, :G].contiguous()
     return (DeviceArray(tabs[0].view(f64)), DeviceArray(tabs[1].view(f64)), DeviceArray(tabs[2].view(f64)),
             DeviceArray(tabs[3] if ct._t.dtype == i64 else tabs[3].view(ct._t.dtype)))
+
+
+def sharded_find(a, needle, n_global=None):
+    """`a?b` over a block-sharded vector: this rank's hits as GLOBAL positions (ascending), plus every rank's hit
+    count (1-d host array), so the caller knows where its slice sits in the concatenated answer.  One all_gather
+    of `world` counts; no data moves."""
+    pos = ops.find_equal(a, needle)
+    w = world()
+    if w == 1:
+        return pos, np.array([pos.size], dtype=np.int64)
+    n_local = a.size
+    sizes = torch.empty(2 * w, dtype=torch.int64, device=a._t.device)
+    mine = torch.tensor([n_local, pos.size], dtype=torch.int64, device=a._t.device)
+    td.all_gather_into_tensor(sizes, mine)
+    sizes = sizes.reshape(w, 2).cpu().numpy()
+    start = int(sizes[:rank(), 0].sum())  # block start from the actual shard lengths (ragged last block included)
+    if start:
+        pos = ops.binary("add", pos, start)
+    return pos, sizes[:, 1].copy()
+
+
+def sharded_loss_sum(code, args):
+    """Differentiable `+/` of an expression over block-sharded operands (autograd row): the scalar loss
+    is replicated on every rank, the tape holds only this rank's fused reduce node, so gradients of sharded vectors
+    stay sharded and need no exchange.  Gradients of replicated (scalar) parameters are per-rank partial sums:
+    finish them with `combine_param_grads`."""
+    part = ops.run(code, args, mode=_lib.MODE_REDUCE, red=_lib.RED_ADD)
+    if world() == 1:
+        return part
+    with torch.no_grad():
+        allp = _gather_scalars(DeviceArray(part._t.detach()))
+        total = ops.run([ops.OP_ARG, 0], [allp], mode=_lib.MODE_REDUCE, red=_lib.RED_ADD)
+        rest = total._t - part._t.detach()
+    # value = the fixed-order global sum (bit-identical on every rank); d value / d part = 1
+    return DeviceArray(part._t - part._t.detach() + (rest + part._t.detach()))
+
+
+def combine_param_grads(grads):
+    """Per-rank partial gradients of replicated scalar parameters -> their global sums, in ONE all_gather and with the
+    same rank-ordered summation on every rank."""
+    w = world()
+    if w == 1:
+        return list(grads)
+    dev = grads[0]._t.device
+    mine = torch.stack([g._t.reshape(()).to(torch.float64) for g in grads])
+    allg = torch.empty(w * len(grads), dtype=torch.float64, device=dev)
+    td.all_gather_into_tensor(allg, mine.contiguous())
+    allg = allg.reshape(w, len(grads))
+    out = allg[0].clone()
+    for r in range(1, w):
+        out = out + allg[r]
+    return [DeviceArray(out[i].reshape(())) for i in range(len(grads))]
 
 
 def shard_bounds(n_global, r=None, w=None):

@@ -39,7 +39,17 @@ for n in (1000, 1_000_003, 40_000_001):
     v = np.round(rng.normal(10, 15, n), 1)
     mn, mxg, sm, ct = (t.to_numpy() for t in dist.sharded_groupagg(be.kg_asarray(k[lo:hi]), be.kg_asarray(v[lo:hi]), G))
     rmn, rmx, rsm, rct = O.grouped_stats(k, v, G)
-    good = (r == ref and np.array_equal(s, sref) and np.array_equal(mx, np.maximum.accumulate(x)[lo:hi]) and
+    pos, counts = dist.sharded_find(be.kg_asarray(k[lo:hi]), 7)
+    want = np.nonzero(k == 7)[0]
+    find_ok = counts.sum() == len(want) and np.array_equal(pos.to_numpy(), want[(want >= lo) & (want < hi)])
+    y = rng.random(n)
+    Y = be.kg_asarray(y[lo:hi])
+    lcode = [ops.OP_ARG, 0, ops.OP_ARG, 1, ops.OPC["mul"], ops.OP_ARG, 2, ops.OPC["add"], ops.OP_ARG, 3, ops.OPC["sub"], ops.OPC["square"]]
+    gw, gb = dist.combine_param_grads(be.compute_multi_autograd(
+        lambda p: dist.sharded_loss_sum(lcode, [p[0], X, p[1], Y]), [0.3, -0.2]))
+    d = 2 * (0.3 * x - 0.2 - y)
+    grad_ok = np.allclose([gw.item(), gb.item()], [np.sum(d * x), np.sum(d)], rtol=1e-10)
+    good = (find_ok and grad_ok and r == ref and np.array_equal(s, sref) and np.array_equal(mx, np.maximum.accumulate(x)[lo:hi]) and
             np.array_equal(mn, rmn) and np.array_equal(mxg, rmx) and np.array_equal(ct, rct) and
             np.allclose(sm, rsm, rtol=1e-12, atol=1e-9))
     print(f"rank {rank}/{world} n={n}: {'ok' if good else 'MISMATCH'}", flush=True)

@@ -60,6 +60,26 @@ def _worker(rank, world, port, q):
         rmn, rmx, rsm, rct = O.grouped_stats(k, v, G)
         assert np.array_equal(mn, rmn) and np.array_equal(mx, rmx) and np.array_equal(ct, rct)
         assert np.allclose(sm, rsm, rtol=1e-12, atol=1e-9)
+        # find: global positions of this rank's hits + every rank's count
+        pos, counts = dist.sharded_find(I, 7)
+        want = np.nonzero(i == 7)[0]
+        assert counts.sum() == len(want) and counts[rank] == pos.size
+        assert np.array_equal(pos.to_numpy(), want[(want >= lo) & (want < hi)]), rank
+        # autograd over shards: loss = +/(w*x + b - y)^2 with replicated scalars w, b and a sharded weight vector u
+        y = rng.random(n)
+        Y = be.kg_asarray(y[lo:hi])
+        lcode = [ops.OP_ARG, 0, ops.OP_ARG, 1, ops.OPC["mul"], ops.OP_ARG, 2, ops.OPC["add"], ops.OP_ARG, 3, ops.OPC["sub"],
+                 ops.OPC["square"]]
+        def loss(params):
+            return dist.sharded_loss_sum(lcode, [params[0], X, params[1], Y])
+        gw, gb = dist.combine_param_grads(be.compute_multi_autograd(loss, [0.3, -0.2]))
+        d = 2 * (0.3 * x - 0.2 - y)
+        assert np.allclose([float(gw.to_numpy()), float(gb.to_numpy())], [np.sum(d * x), np.sum(d)], rtol=1e-10), rank
+        gu = be.compute_autograd(lambda u: dist.sharded_loss_sum([ops.OP_ARG, 0, ops.OP_ARG, 1, ops.OPC["mul"], ops.OPC["square"]],
+                                                                 [u, X]), Y).to_numpy()
+        assert np.allclose(gu, 2 * y[lo:hi] * x[lo:hi] ** 2, rtol=1e-12), rank   # a sharded vector's gradient stays sharded
+        lv = dist.sharded_loss_sum([ops.OP_ARG, 0, ops.OPC["square"]], [X]).item()
+        assert lv == np.add.reduce(x * x) or abs(lv - np.sum(x * x)) <= 1e-12 * np.sum(x * x)
         td.barrier()
         td.destroy_process_group()
         q.put((rank, "ok"))
