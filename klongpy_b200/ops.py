@@ -134,11 +134,13 @@ _handles = {}
 def _classify(x, device):
     """-> (kind, kgb dtype, keepalive object, raw pointer)"""
     if isinstance(x, DeviceArray):
-        if x._t.device != device:
-            raise ValueError(f"operand on {x._t.device}, expected {device}")
-        x = contiguous(x)
-        kind = _lib.ARG_DEVSCALAR if x._t.numel() == 1 and x._t.dim() == 0 else _lib.ARG_ARRAY
-        return kind, kgb_dtype(x._t), x, x._t.data_ptr()
+        t = x._t
+        if t.device != device:
+            raise ValueError(f"operand on {t.device}, expected {device}")
+        if not t.is_contiguous():
+            t = t.contiguous()
+            x = DeviceArray(t)
+        return (_lib.ARG_DEVSCALAR if t.dim() == 0 else _lib.ARG_ARRAY), kgb_dtype(t), x, t.data_ptr()
     if isinstance(x, (bool, np.bool_)):
         x = int(x)
     if isinstance(x, np.ndarray) and x.ndim == 0:
@@ -166,30 +168,42 @@ def _classify_meta(x):
     raise TypeError(f"unsupported operand type {type(x).__name__}")
 
 
+_ARGV = [ctypes.c_void_p * max(k, 1) for k in range(17)]  # argument-pointer array types, by argument count
+_lazy = None  # klongpy_b200.lazy, imported on first use (it imports this module)
+
+
 def run(code, args, mode=_lib.MODE_MAP, red=0, code2=None, red2=0, out_shape=None, device=None, _no_defer=False):
     """Compile (cached) and launch one expression program.  Returns a DeviceArray."""
-    from . import lazy
-    if lazy.ENABLED and not _no_defer:
+    global _lazy
+    if _lazy is None:
+        from . import lazy as _lazy_mod
+        _lazy = _lazy_mod
+    if _lazy.ENABLED and not _no_defer:
         # deferred operands are inlined into this program (elementwise chains, reduce / scan prologues fuse);
         # a MAP result is itself deferred until something needs the data
-        code, args = lazy.inline(code, args)
+        code, args = _lazy.inline(code, args)
         if mode == _lib.MODE_MAP and out_shape is None and not code2:
-            r = lazy.defer(code, args)
+            r = _lazy.defer(code, args)
             if r is not None:
                 return r
-    if torch.is_grad_enabled() and any(isinstance(a, DeviceArray) and a.requires_grad for a in args):
-        from . import autograd  # operands on the autograd tape: same launch, recorded as one node
-        return autograd.run_differentiable(code, args, mode, red, code2, red2, out_shape, device)
     shape = None
     mixed = False
+    grad = False
+    dev_param = device
     for a in args:
         if isinstance(a, DeviceArray):
-            device = a._t.device
-            if a._t.dim() > 0:
+            t = a._t
+            device = t.device
+            if t.requires_grad:
+                grad = True
+            if t.dim() > 0:
                 if shape is None:
-                    shape = tuple(a._t.shape)
-                elif tuple(a._t.shape) != shape:
+                    shape = tuple(t.shape)
+                elif tuple(t.shape) != shape:
                     mixed = True
+    if grad and torch.is_grad_enabled():
+        from . import autograd  # operands on the autograd tape: same launch, recorded as one node
+        return autograd.run_differentiable(code, args, mode, red, code2, red2, out_shape, dev_param)
     if mixed:
         # NumPy broadcasting between arrays of different shapes (`[[1]]&[2]`, tests/kgtests/language/test_broadcasting.kg):
         # rare and small in Klong programs, so the operands are expanded to the common shape first (one copy each)
@@ -247,8 +261,10 @@ def run(code, args, mode=_lib.MODE_MAP, red=0, code2=None, red2=0, out_shape=Non
         ws_ptr = ws.data_ptr()
     if n == 0:
         return out  # empty MAP / SCAN: nothing to launch
-    argv = (ctypes.c_void_p * max(len(args), 1))(*[c[3] for c in cls])
-    _lib.check(lib.kgb_expr_launch(h, argv, n, out._t.data_ptr(), ws_ptr, wsb.value, stream), "kgb_expr_launch")
+    argv = _ARGV[len(cls)](*[c[3] for c in cls]) if len(cls) < len(_ARGV) else (ctypes.c_void_p * len(cls))(*[c[3] for c in cls])
+    rc = lib.kgb_expr_launch(h, argv, n, out._t.data_ptr(), ws_ptr, wsb.value, stream)
+    if rc:
+        _lib.check(rc, "kgb_expr_launch")
     return out
 
 
