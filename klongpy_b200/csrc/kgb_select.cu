@@ -1,4 +1,6 @@
 // find (a?b), where / nonzero, group (=a) and range (?a): compaction- and sort-based kernels.
+#include <cstdlib>
+
 #include "kgb_select.cuh"
 #include "kgb_sort.cuh"
 
@@ -63,6 +65,142 @@ static GroupWs carve_group(void* ws, i64 n) {
     o += g.sort_bytes;
     g.total = o;
     return g;
+}
+
+
+// ------------------------------------------------------------------------------------------- range (?a) by hashing
+// Low-cardinality inputs (10 k stations in 1e8 rows) do not need a sort: an L2-resident open-addressing table keyed by
+// the raw bits keeps, per distinct key, the smallest position that holds it.  A row whose key is already present
+// with a smaller position costs one 16-byte L2 read and no atomic — which is every row but the first few of each key —
+// so the pass runs near the streaming rate.  The table has 2^20 slots (16 MB); when more than half fill up the kernel
+// raises a flag, every CTA stops at its next iteration and the caller falls back to the sort-based path, so the
+// attempt costs a high-cardinality input a few tens of microseconds.
+struct __align__(16) UniqSlot {
+    u64 key;    // raw bits; UNIQ_EMPTY while free
+    u64 first;  // smallest position seen so far
+};
+constexpr u64 UNIQ_EMPTY = ~0ull;
+constexpr int UNIQ_LOG2_SLOTS = 20;
+constexpr u64 UNIQ_SLOTS = 1ull << UNIQ_LOG2_SLOTS;
+constexpr u64 UNIQ_LIMIT = UNIQ_SLOTS / 2;
+struct UniqCtl {
+    unsigned long long distinct;       // keys inserted so far
+    unsigned long long special_first;  // first position of the key whose bits equal UNIQ_EMPTY (all ones)
+    unsigned long long out_count;      // collect kernel's cursor
+    int overflow;
+};
+
+__device__ __forceinline__ u64 uniq_hash(u64 k) {
+    k ^= k >> 33;
+    k *= 0xff51afd7ed558ccdull;
+    k ^= k >> 33;
+    k *= 0xc4ceb9fe1a85ec53ull;
+    k ^= k >> 33;
+    return k;
+}
+
+template <typename T> __device__ __forceinline__ u64 uniq_bits(T v);
+template <> __device__ __forceinline__ u64 uniq_bits<u64>(u64 v) { return v; }
+template <> __device__ __forceinline__ u64 uniq_bits<u32>(u32 v) { return (u64)v; }
+
+template <typename T>
+__global__ void __launch_bounds__(256) uniq_insert_kernel(const T* __restrict__ a, i64 m, i64 step, UniqSlot* __restrict__ tab,
+                                                           UniqCtl* __restrict__ ctl) {
+    // visits rows j * step for j < m: step 1 is the full pass, a larger step the cardinality probe on a strided sample
+    constexpr int U = 4;
+    const i64 stride = (i64)gridDim.x * 256 * U;
+    u32 fresh = 0;
+    for (i64 base = (i64)blockIdx.x * 256 * U; base < m; base += stride) {
+        if (__any_sync(0xffffffffu, *(volatile int*)&ctl->overflow != 0)) return;  // warp-uniform exit
+        bool bail = false;
+        T v[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const i64 j = base + u * 256 + threadIdx.x;
+            v[u] = a[(j < m ? j : m - 1) * step];
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const i64 j = base + u * 256 + threadIdx.x;
+            if (j >= m || bail) continue;
+            const i64 i = j * step;
+            const u64 k = uniq_bits<T>(v[u]);
+            if (k == UNIQ_EMPTY) {
+                if ((u64)i < *(volatile unsigned long long*)&ctl->special_first) atomicMin(&ctl->special_first, (unsigned long long)i);
+                continue;
+            }
+            u64 slot = uniq_hash(k) & (UNIQ_SLOTS - 1);
+            for (u64 probe = 0; probe < UNIQ_SLOTS; probe++) {
+                ulonglong2 e;  // one 16-byte relaxed load of {key, first}; either half may be stale, both only move one way
+                asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(e.x), "=l"(e.y) : "l"(&tab[slot]) : "memory");
+                if (e.x == k) {
+                    if ((u64)i < e.y) atomicMin((unsigned long long*)&tab[slot].first, (unsigned long long)i);
+                    break;
+                }
+                if (e.x == UNIQ_EMPTY) {
+                    // no new keys once the table is over its limit: the rows in flight when the flag goes up would
+                    // otherwise fill it completely and turn every probe sequence into a scan of the whole table
+                    if (*(volatile int*)&ctl->overflow) {
+                        bail = true;
+                        break;
+                    }
+                    const u64 prev = atomicCAS((unsigned long long*)&tab[slot].key, (unsigned long long)UNIQ_EMPTY, (unsigned long long)k);
+                    if (prev == UNIQ_EMPTY) {
+                        fresh++;
+                        atomicMin((unsigned long long*)&tab[slot].first, (unsigned long long)i);
+                        break;
+                    }
+                    if (prev == k) {
+                        atomicMin((unsigned long long*)&tab[slot].first, (unsigned long long)i);
+                        break;
+                    }
+                }
+                slot = (slot + 1) & (UNIQ_SLOTS - 1);
+                if ((probe & 15) == 15) {
+                    // a probe sequence this long means the table is far past half full (the counter below lags by
+                    // one iteration of every thread): give up, the caller sorts instead
+                    if (probe >= 255) ctl->overflow = 1;
+                    if (*(volatile int*)&ctl->overflow) {
+                        bail = true;
+                        break;
+                    }
+                }
+            }
+        }
+        // new keys are counted once per warp and iteration, not once per insertion: a permutation would otherwise
+        // serialise half a million atomics on this one word (measured: 1 ms)
+        fresh = __reduce_add_sync(0xffffffffu, fresh);
+        if ((threadIdx.x & 31) == 0 && fresh) {
+            if (atomicAdd(&ctl->distinct, (unsigned long long)fresh) + fresh > UNIQ_LIMIT) ctl->overflow = 1;
+        }
+        fresh = 0;
+        if (__any_sync(0xffffffffu, bail)) return;
+    }
+}
+
+// first positions of all occupied slots, in no particular order (they are sorted afterwards)
+__global__ void __launch_bounds__(256) uniq_collect_kernel(const UniqSlot* __restrict__ tab, UniqCtl* __restrict__ ctl,
+                                                            i64* __restrict__ first, i64* __restrict__ count_out) {
+    const u64 slot = (u64)blockIdx.x * 256 + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    bool occ = false;
+    u64 f = 0;
+    if (slot < UNIQ_SLOTS) {
+        const UniqSlot e = tab[slot];
+        occ = e.key != UNIQ_EMPTY;
+        f = e.first;
+    } else if (slot == UNIQ_SLOTS) {
+        f = ctl->special_first;
+        occ = f != ~0ull;
+    }
+    const u32 m = __ballot_sync(0xffffffffu, occ);
+    if (m) {
+        unsigned long long b = 0;
+        if (lane == __ffs(m) - 1) b = atomicAdd(&ctl->out_count, (unsigned long long)__popc(m));
+        b = __shfl_sync(0xffffffffu, b, __ffs(m) - 1);
+        if (occ) first[b + __popc(m & ((1u << lane) - 1u))] = (i64)f;
+    }
+    (void)count_out;
 }
 
 }  // namespace kgb
@@ -155,20 +293,60 @@ extern "C" int kgb_unique_first(const void* a, int32_t dtype, int64_t n, void* o
     i64* first = (i64*)(p + 2 * nb);
     i64* tmpidx = (i64*)(p + 3 * nb);
     GroupWs g = carve_group(p + 4 * nb, n);
-    // 1. stable sort -> runs of equal keys, smallest position first inside each run
-    const int sort_dt = dtype == KGB_F64 ? KGB_F64_RAW : dtype == KGB_F32 ? KGB_F32_RAW : dtype;
-    int rc = sort_pairs(a, sort_dt, n, 0, idx1, nullptr, g.enc, g.sort, g.sort_bytes, st);
-    if (rc != KGB_OK) return rc;
-    // 2. run heads
-    rc = launch_select(BoundaryPred{g.enc}, n, heads, (i64*)count_out, g.sel, g.sel_bytes, st);
-    if (rc != KGB_OK) return rc;
-    // 3. first occurrence position of every distinct key
-    gather_counted_i64<<<cap_grid(n), 256, 0, st>>>(idx1, heads, (const i64*)count_out, first);
-    KGB_CUDA_CHECK(cudaGetLastError());
-    // the number of distinct keys sizes the second sort: one 8-byte D2H read (the caller needs it anyway)
-    i64 c = 0;
-    KGB_CUDA_CHECK(cudaMemcpyAsync(&c, count_out, 8, cudaMemcpyDeviceToHost, st));
-    KGB_CUDA_CHECK(cudaStreamSynchronize(st));
+    int rc;
+    i64 c = -1;
+    // 0. low-cardinality fast path: first positions through an L2-resident hash table (no sort of the n rows)
+    static const bool hash_on = !(getenv("KGB200_UNIQUE_HASH") && atoi(getenv("KGB200_UNIQUE_HASH")) == 0);
+    const size_t tab_bytes = (size_t)UNIQ_SLOTS * sizeof(UniqSlot);
+    if (hash_on && nb >= tab_bytes && nb >= 256 + sizeof(UniqCtl)) {
+        UniqSlot* tab = (UniqSlot*)idx1;          // the table borrows the sort path's index buffer
+        UniqCtl* ctl = (UniqCtl*)heads;
+        KGB_CUDA_CHECK(cudaMemsetAsync(tab, 0xff, tab_bytes, st));
+        KGB_CUDA_CHECK(cudaMemsetAsync(ctl, 0, sizeof(UniqCtl), st));
+        KGB_CUDA_CHECK(cudaMemsetAsync(&ctl->special_first, 0xff, 8, st));
+        auto insert = [&](i64 m, i64 step) {
+            long long ib = (m + 1023) / 1024;
+            const long long icap = (long long)sm_count() * 8;
+            if (ib > icap) ib = icap;
+            if (dtype_size(dtype) == 8)
+                uniq_insert_kernel<u64><<<(unsigned)ib, 256, 0, st>>>((const u64*)a, m, step, tab, ctl);
+            else
+                uniq_insert_kernel<u32><<<(unsigned)ib, 256, 0, st>>>((const u32*)a, m, step, tab, ctl);
+        };
+        UniqCtl h;
+        // cardinality probe: 512k rows spread over the whole input go in first (they are real rows, nothing is wasted);
+        // if they alone bring in more than 300k distinct keys the table would overflow — go straight to the sort
+        const i64 sample = n < (1ll << 19) ? n : (1ll << 19);
+        insert(sample, n / sample);
+        KGB_CUDA_CHECK(cudaMemcpyAsync(&h, ctl, sizeof(UniqCtl), cudaMemcpyDeviceToHost, st));
+        KGB_CUDA_CHECK(cudaStreamSynchronize(st));
+        if (!h.overflow && h.distinct <= 300000ull) {
+            insert(n, 1);
+            uniq_collect_kernel<<<(unsigned)(UNIQ_SLOTS / 256 + 1), 256, 0, st>>>(tab, ctl, first, (i64*)count_out);
+            KGB_CUDA_CHECK(cudaGetLastError());
+            KGB_CUDA_CHECK(cudaMemcpyAsync(&h, ctl, sizeof(UniqCtl), cudaMemcpyDeviceToHost, st));
+            KGB_CUDA_CHECK(cudaStreamSynchronize(st));
+            if (!h.overflow) {
+                c = (i64)h.out_count;
+                KGB_CUDA_CHECK(cudaMemcpyAsync(count_out, &ctl->out_count, 8, cudaMemcpyDeviceToDevice, st));
+            }
+        }
+    }
+    if (c < 0) {
+        // 1. stable sort -> runs of equal keys, smallest position first inside each run
+        const int sort_dt = dtype == KGB_F64 ? KGB_F64_RAW : dtype == KGB_F32 ? KGB_F32_RAW : dtype;
+        rc = sort_pairs(a, sort_dt, n, 0, idx1, nullptr, g.enc, g.sort, g.sort_bytes, st);
+        if (rc != KGB_OK) return rc;
+        // 2. run heads
+        rc = launch_select(BoundaryPred{g.enc}, n, heads, (i64*)count_out, g.sel, g.sel_bytes, st);
+        if (rc != KGB_OK) return rc;
+        // 3. first occurrence position of every distinct key
+        gather_counted_i64<<<cap_grid(n), 256, 0, st>>>(idx1, heads, (const i64*)count_out, first);
+        KGB_CUDA_CHECK(cudaGetLastError());
+        // the number of distinct keys sizes the second sort: one 8-byte D2H read (the caller needs it anyway)
+        KGB_CUDA_CHECK(cudaMemcpyAsync(&c, count_out, 8, cudaMemcpyDeviceToHost, st));
+        KGB_CUDA_CHECK(cudaStreamSynchronize(st));
+    }
     // 4. order of first appearance = ascending first positions
     rc = sort_pairs(first, KGB_I64, c, 0, tmpidx, first_idx_out, nullptr, g.sort, g.sort_bytes, st);
     if (rc != KGB_OK) return rc;

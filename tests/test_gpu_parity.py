@@ -421,6 +421,45 @@ def test_range_and_find_bit_exact(be, K, n, G):
     assert np.array_equal(host(K.nonzero(dev(be, flags) > 1)), np.flatnonzero(flags > 1))
 
 
+def _first_appearance(a):
+    """np.unique on the raw bits + first index: the oracle's `?a` without its Python loop (large inputs)."""
+    bits = a.view(np.int64) if a.dtype == np.float64 else a
+    _, first = np.unique(bits, return_index=True)
+    return a[np.sort(first)]
+
+
+@pytest.mark.parametrize("case", ["10k", "minus_one", "float_special", "near_limit", "over_limit", "all_distinct", "int32"])
+def test_range_hash_path_and_fallback(be, K, case):
+    """`?a` at sizes where the L2-resident hash table is tried (n >= 2^21): low cardinality stays on it, the key whose
+    bits are all ones (-1) takes its side slot, NaN / -0.0 / +0.0 are distinct raw-bit keys, and more than 2^19 distinct
+    keys overflow into the sort-based path — every variant bit-exact against first-appearance order."""
+    rng = np.random.default_rng(len(case))
+    n = 3_000_001
+    if case == "10k":
+        a = rng.integers(0, 10_000, n)
+    elif case == "minus_one":
+        a = rng.integers(-3, 40, n)
+    elif case == "float_special":
+        a = rng.integers(0, 500, n) / 8.0
+        a[::1001] = np.nan
+        a[5::997] = -0.0
+        a[7::991] = 0.0
+    elif case == "near_limit":
+        a = rng.integers(0, 250_000, n)
+    elif case == "over_limit":
+        a = rng.integers(0, 900_000, n)
+    elif case == "all_distinct":
+        a = rng.permutation(n)
+    else:
+        a = rng.integers(-5, 3000, n).astype(np.int32)
+    got = host(K.unique_first(dev(be, a)))
+    want = _first_appearance(a)
+    assert got.dtype == want.dtype and got.shape == want.shape
+    gb = got.view(np.int64) if got.dtype == np.float64 else got
+    wb = want.view(np.int64) if want.dtype == np.float64 else want
+    assert np.array_equal(gb, wb), case
+
+
 def test_support_verbs(be, K):
     rng = np.random.default_rng(5)
     assert np.array_equal(host(K.iota(0)), O.enumerate_(0)) and np.array_equal(host(K.iota(100_001)), O.enumerate_(100_001))
