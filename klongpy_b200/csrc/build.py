@@ -21,7 +21,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-fmad=false", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function",
           "-I", os.path.join(ROOT, "include"), "-I", HERE] + os.environ.get("KGB200_NVCC_DEFS", "").split()  # tuning: extra -D flags
 
-SOURCES = ["kgb_core.cpp", "kgb_expr.cpp", "kgb_sort.cu", "kgb_select.cu", "kgb_misc.cu", "kgb_groupagg.cu"]
+SOURCES = ["kgb_core.cpp", "kgb_expr.cpp", "kgb_sort.cu", "kgb_select.cu", "kgb_misc.cu", "kgb_groupagg.cu", "kgb_ingest.cu"]
 
 
 def _embed_skeleton():

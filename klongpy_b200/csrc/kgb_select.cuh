@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(SEL_MASK_THREADS) select_mask_kernel(Pred pred
 }
 
 // counters -> exclusive offsets, in place; cnt[ntiles] and *count_out receive the total
-__global__ void __launch_bounds__(1024) select_offsets_kernel(unsigned long long* __restrict__ cnt, i64 ntiles,
+static __global__ void __launch_bounds__(1024) select_offsets_kernel(unsigned long long* __restrict__ cnt, i64 ntiles,
                                                               i64* __restrict__ count_out) {
     __shared__ unsigned long long s_w[32];
     __shared__ unsigned long long s_carry;
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(1024) select_offsets_kernel(unsigned long long
     }
 }
 
-__global__ void __launch_bounds__(SEL_THREADS) select_emit_kernel(const u32* __restrict__ masks, i64 nwords,
+static __global__ void __launch_bounds__(SEL_THREADS) select_emit_kernel(const u32* __restrict__ masks, i64 nwords,
                                                                    i64* __restrict__ pos_out,
                                                                    const unsigned long long* __restrict__ offs) {
     __shared__ u32 s_wcnt[SEL_THREADS / 32];

@@ -291,6 +291,26 @@ def grouped_stats_fast(keys, vals, n_groups):
     return mn, mx, sm, ct
 
 
+def parse_1brc(text):
+    """examples/1brc/par.py:57-88: `for line in f: location, measurement = line.split(";")`, stations kept as
+    strings, `np.asarray(temps, dtype=float)`; worker.kg:5 then groups by station name (`=s`) and par.kg:4 sorts the
+    names.  Restated for a whole buffer: returns (names sorted ascending, station id per row as an index into that
+    list, float64 temperature per row).  `float()` is Python's correctly rounded decimal conversion."""
+    if isinstance(text, (bytes, bytearray, memoryview)):
+        text = bytes(text).decode("utf-8")
+    stations, temps = [], []
+    for line in text.split("\n"):
+        if not line:
+            continue
+        location, measurement = line.split(";")
+        stations.append(location)
+        temps.append(float(measurement))
+    names = sorted(set(stations), key=lambda s: s.encode("utf-8"))
+    index = {s: i for i, s in enumerate(names)}
+    ids = np.fromiter((index[s] for s in stations), dtype=np.int64, count=len(stations))
+    return names, ids, np.asarray(temps, dtype=float)
+
+
 def report_1brc(mn, mx, sm, ct):
     """examples/1brc/par.kg:4-6: 'min/mean/max' with one decimal, stations ascending, mean = sum % count."""
     out = {}

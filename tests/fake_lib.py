@@ -384,6 +384,41 @@ class FakeLib:
                 o[:] = v
         return 0
 
+    def kgb_brc_workspace_bytes(self, n, out):
+        out._obj.value = 64
+        return 0
+
+    def kgb_brc_scan(self, text, n, rows_out, ws, wsb, stream):
+        t = view_bytes(text, n) if n else np.zeros(0, np.uint8)
+        if n and t[-1] != 10:
+            self.err = b"kgb_brc_scan: the text must end with a newline"
+            return 1
+        rows_out._obj.value = int(np.count_nonzero(t == 10))
+        return 0
+
+    def kgb_brc_parse(self, text, n, rows, ids, temps, doff, dlen, cap, n_names_out, ws, wsb, stream):
+        raw = bytes(view_bytes(text, n)) if n else b""
+        seen, pos, r = {}, 0, 0
+        ido, tmo = view(ids, rows, I64), view(temps, rows, F64)
+        dof, dln = view(doff, cap, I64), view(dlen, cap, I32)
+        for line in raw.split(b"\n")[:-1]:
+            name, _, meas = line.rpartition(b";")
+            ok = len(name) > 0 and len(meas) in (3, 4, 5) and meas[-2:-1] == b"." and meas.lstrip(b"-").replace(b".", b"").isdigit()
+            if not ok:
+                self.err = b"kgb_brc_parse: malformed row (expected name;[-]d[d].d)"
+                return 1
+            if name not in seen:
+                if len(seen) >= cap:
+                    self.err = b"kgb_brc_parse: more than %d distinct names" % cap
+                    return 1
+                dof[len(seen)], dln[len(seen)] = pos, len(name)
+                seen[name] = len(seen)
+            ido[r], tmo[r] = seen[name], float(meas)
+            pos += len(line) + 1
+            r += 1
+        n_names_out._obj.value = len(seen)
+        return 0
+
     def kgb_groupagg_merge(self, mn, mx, sm, ct, mn2, mx2, sm2, ct2, G, stream):
         a = (view(mn, G, F64), view(mx, G, F64), view(sm, G, F64), view(ct, G, I64))
         b = (view(mn2, G, F64), view(mx2, G, F64), view(sm2, G, F64), view(ct2, G, I64))

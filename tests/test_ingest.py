@@ -1,0 +1,107 @@
+"""1brc text ingest: the oracle's `parse_1brc` against the fixture produced by the REAL
+reference example (tests/golden/make_golden_1brc.py), the b200 pipeline on the CPU test double, and — on the GPU —
+the kernels against the oracle on synthetic files with the edge cases of the format."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import kg_oracle as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return json.load(open(os.path.join(HERE, "golden", "golden_1brc.json"), encoding="utf-8"))
+
+
+def _table(names, ids, temps):
+    mn, mx, sm, ct = O.grouped_stats(ids, temps, len(names))
+    return {s: [mn[i], mx[i], sm[i], int(ct[i])] for i, s in enumerate(names)}
+
+
+def _check_table(got, want):
+    assert sorted(got) == sorted(want)
+    for s, (mn, mx, sm, ct) in want.items():
+        g = got[s]
+        assert g[0] == mn and g[1] == mx and g[3] == ct, s
+        assert abs(g[2] - sm) <= 1e-12 * max(1.0, abs(sm)), s
+
+
+def test_oracle_matches_reference_example(golden):
+    names, ids, temps = O.parse_1brc(golden["text"].encode("utf-8"))
+    assert names == sorted(names, key=lambda s: s.encode("utf-8")) and len(ids) == golden["text"].count("\n")
+    _check_table(_table(names, ids, temps), golden["table_min_max_sum_count"])
+    assert np.signbit(temps[list(golden["text"].split("\n")).index("a;-0.0")])  # float("-0.0") keeps its sign
+
+
+def test_b200_pipeline_on_cpu_double(golden):
+    import fake_lib
+    dev = fake_lib.install()
+    from klongpy_b200 import ingest
+    text = golden["text"].encode("utf-8")
+    ids, temps, names = ingest.parse(text, device=dev)
+    rn, ri, rt = O.parse_1brc(text)
+    assert names == rn and np.array_equal(ids.to_numpy(), ri) and np.array_equal(temps.to_numpy(), rt)
+    names, mn, mean, mx, ct = ingest.aggregate(text, device=dev)
+    want = golden["table_min_max_sum_count"]
+    for i, s in enumerate(names):
+        assert mn[i] == want[s][0] and mx[i] == want[s][1] and ct[i] == want[s][3]
+        assert abs(mean[i] - want[s][2] / want[s][3]) <= 1e-12 * max(1.0, abs(mean[i]))
+    assert ingest.parse(text[:-1], device=dev)[2] == rn          # a missing final newline is tolerated by the wrapper
+    from klongpy_b200 import _lib
+    with pytest.raises(_lib.KgbError):
+        ingest.parse(b"Abha;12.34\n", device=dev)                # not the 1brc format
+
+
+def _synthetic(rng, rows, n_names):
+    alphabet = list("abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ éüñ'-.,")
+    names = set()
+    while len(names) < n_names:
+        k = int(rng.integers(1, 27))
+        names.add("".join(rng.choice(alphabet, k)).strip() or "q")
+    names = sorted(names)
+    ids = rng.integers(0, len(names), rows)
+    tenths = np.clip(np.round(rng.normal(100, 250, rows)), -999, 999).astype(np.int64)
+    parts = []
+    for i, t in zip(ids, tenths):
+        a = abs(int(t))
+        parts.append(f"{names[i]};{'-' if t < 0 else ''}{a // 10}.{a % 10}\n")
+    return "".join(parts).encode("utf-8")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows,n_names", [(1, 1), (7, 3), (70_001, 413), (600_000, 10_000)])
+def test_gpu_ingest_vs_oracle(rows, n_names):
+    import torch
+    from klongpy_b200 import ingest
+    rng = np.random.default_rng(rows)
+    text = _synthetic(rng, rows, n_names)
+    ids, temps, names = ingest.parse(text, device="cuda:0")
+    rn, ri, rt = O.parse_1brc(text)
+    assert names == rn
+    assert np.array_equal(ids.to_numpy(), ri)
+    t = temps.to_numpy()
+    assert np.array_equal(t, rt) and np.array_equal(np.signbit(t), np.signbit(rt))
+    rep = ingest.report(text, device="cuda:0")
+    mn, mx, sm, ct = O.grouped_stats(ri, rt, len(rn))
+    ref = {rn[i]: v for i, v in O.report_1brc(mn, mx, sm, ct).items()}
+    bad = [s for s in ref if rep[s] != ref[s]]
+    for s in bad:  # a mean that sits on a rounding boundary may print one digit apart when sums differ in the last ulp
+        a, b = rep[s].split("/"), ref[s].split("/")
+        assert a[0] == b[0] and a[2] == b[2] and abs(float(a[1]) - float(b[1])) <= 0.1 + 1e-9, s
+    assert torch.cuda.is_available()
+
+
+@pytest.mark.gpu
+def test_gpu_ingest_fixture_and_errors(golden):
+    from klongpy_b200 import _lib, ingest
+    text = golden["text"].encode("utf-8")
+    ids, temps, names = ingest.parse(text, device="cuda:0")
+    _check_table(_table(names, ids.to_numpy(), temps.to_numpy()), golden["table_min_max_sum_count"])
+    for bad in (b"Abha;12.34\n", b"Abha 12.3\n", b";1.0\n", b"Abha;1,0\n"):
+        with pytest.raises(_lib.KgbError):
+            ingest.parse(b"ok;1.0\n" + bad, device="cuda:0")
+    assert ingest.parse(b"", device="cuda:0")[2] == []
