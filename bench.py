@@ -356,6 +356,21 @@ def prim_row(n, ms, bytes_per_elem, peak, **extra):
     return row
 
 
+def synthetic_1brc_block(rows=1_000_000, n_names=10_000, seed=5):
+    """`name;[-]d[d].d\n` lines in the shape of examples/1brc: n_names distinct stations of 3-19 bytes, temperatures
+    N(10, 25) clipped to +-99.9.  -> (bytes, names list, station index per row, tenths per row)"""
+    rng = np.random.default_rng(seed)
+    letters = list("abcdefghijklmnopqrstuvwxyz ABCDEFGHIJK")
+    names = set()
+    while len(names) < n_names:
+        names.add("".join(rng.choice(letters, int(rng.integers(3, 20)))).strip() or "q")
+    names = sorted(names)
+    ids = rng.integers(0, n_names, rows)
+    tenths = np.clip(np.round(rng.normal(100, 250, rows)), -999, 999).astype(np.int64)
+    block = "".join(f"{names[i]};{'-' if t < 0 else ''}{abs(int(t)) // 10}.{abs(int(t)) % 10}\n" for i, t in zip(ids, tenths)).encode()
+    return block, names, ids, tenths
+
+
 def primitive_table(be, ops, dist, time_kernel, dev, peak, world, rank):
     """Per-primitive elements/s and roofline fraction at the BASELINE.json sizes (1 GPU each rank)."""
     import torch
@@ -502,6 +517,27 @@ def primitive_table(be, ops, dist, time_kernel, dev, peak, world, rank):
     keys_full = DeviceArray(torch.randint(-2**62, 2**62, (n,), dtype=torch.int64, device=dev, generator=g))
     out["grade_up_full64_1e8"] = prim_row(n, time_kernel(lambda: ops.argsort(keys_full), 3), 16, peak,
                                           model_bytes_per_elem=8 + 24 * 8 - 4 + 4, passes=8)
+    del keys_full
+    if world == 1:
+        # 1brc text -> (station id, float64 temperature) columns + dictionary on the device.  A
+        # 1e6-row block tiled 100x (1e8 rows, ~1.7 GB of text); algorithmic bytes per row = its text + 16 B of output.
+        from klongpy_b200 import ingest
+        block, names, _, _ = synthetic_1brc_block()
+        reps = 100
+        text = torch.from_numpy(np.frombuffer(block, dtype=np.uint8).copy()).to(dev).repeat(reps)
+        rows = 1_000_000 * reps
+        bpr = text.numel() / rows + 16
+        got = ingest.parse(text)
+        assert got[0].size == rows and got[2] == sorted(names, key=lambda s: s.encode())
+        del got
+        ms_kernels = time_kernel(lambda: ingest._parse_arrival(text, dev, fetch_names=False), 5)
+        out["ingest_1brc_parse_1e8"] = prim_row(rows, time_kernel(lambda: ingest.parse(text), 3), bpr, peak,
+                                                device_ms=ms_kernels, device_roofline_frac=bpr * rows / (ms_kernels * 1e-3) / 1e9 / peak,
+                                                note="ms: ingest.parse() incl. the host-side dictionary (10k names fetched, sorted, decoded) "
+                                                     "and the id remap gather; device_ms: kgb_brc_scan + kgb_brc_parse only")
+        out["ingest_1brc_aggregate_1e8"] = prim_row(rows, time_kernel(lambda: ingest.aggregate(text), 3), bpr, peak,
+                                                    note="text -> min/mean/max per station, names ascending (examples/1brc end to end)")
+        del text
     return out
 
 

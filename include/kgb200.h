@@ -238,18 +238,19 @@ int kgb_groupagg_merge(double* min_io, double* max_io, double* sum_io, int64_t* 
    Two phases, because the row count sizes the outputs:
      kgb_brc_scan   newline bitmask + per-tile counts; writes the number of rows to *rows_out_host (one
                     synchronising 8-byte read).  The text must end with '\n'.
-     kgb_brc_parse  per row: name span, FNV-1a hash, insert / look up in an open-addressing table (names are
+     kgb_brc_parse  per row: name span, 64-bit hash, insert / look up in an open-addressing table (names are
                     compared byte for byte on a hash match), fixed-point parse of the measurement (exactly
-                    float("[-]d[d].d")).  id_out[r] in [0, *n_names) in first-arrival order; dict_off_out /
-                    dict_len_out (capacity dict_capacity) give one occurrence of every name as a byte span of
-                    `text`.  *n_names_out_host receives the dictionary size (synchronising read).  Returns
-                    KGB_EINVAL for a malformed row or more than dict_capacity distinct names.
+                    float("[-]d[d].d")).  id_out[r] in [0, *n_names) in first-arrival order; row i of
+                    dict_names_out (dict_capacity rows of 256 bytes, 4-byte aligned) holds the dict_len_out[i] <= 255
+                    bytes of name i, zero-filled up to the next multiple of 16.  *n_names_out_host receives the
+                    dictionary size (synchronising read).  Returns KGB_EINVAL for a malformed row, a name longer
+                    than 255 bytes or more than dict_capacity distinct names.
    `workspace` must be the one kgb_brc_scan filled (same text, same n_bytes). */
 int kgb_brc_workspace_bytes(int64_t n_bytes, size_t* out_bytes);
 int kgb_brc_scan(const uint8_t* text, int64_t n_bytes, int64_t* rows_out_host, void* workspace,
                  size_t workspace_bytes, void* stream);
 int kgb_brc_parse(const uint8_t* text, int64_t n_bytes, int64_t rows, int64_t* id_out, double* temp_out,
-                  int64_t* dict_off_out, int32_t* dict_len_out, int64_t dict_capacity,
+                  uint8_t* dict_names_out, int32_t* dict_len_out, int64_t dict_capacity,
                   int64_t* n_names_out_host, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus

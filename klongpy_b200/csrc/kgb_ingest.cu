@@ -7,14 +7,16 @@
 //                     warp saw a newline) one RED of its count into the counter of its 65536-byte tile — the same
 //                     mask / tile-counter layout as the stream compaction in kgb_select.cuh, whose offsets kernel
 //                     is reused.  Traffic: the text once + n/8 bytes.
-//   brc_parse_kernel  one CTA per 65536-byte tile with newlines: block scan of the per-thread newline counts gives
-//                     every line its row number; the thread owning a line's '\n' finds the line start through the
-//                     mask (no byte search), parses the measurement backwards from the newline in fixed point,
-//                     hashes the name (FNV-1a, 64 bit) and resolves it in an L2-resident open-addressing table.
-//                     A name already present costs one 32-byte slot read and a byte compare against the stored
-//                     occurrence; a new name takes the slot with one CAS, draws the next dense id and publishes
-//                     {span, id}.  Traffic: the text a second time (L2/L1 friendly: neighbouring threads share
-//                     sectors) + 16 bytes of output per row.
+//   brc_parse_kernel  one CTA per 65536-byte tile with newlines: the tile's mask words are expanded into a list of
+//                     newline positions in shared memory (block scan of popcounts = row numbers), then line i goes
+//                     to thread i mod 512, so a warp reads ~5 consecutive 128-byte lines of text and writes its 16
+//                     bytes per row coalesced.  Per line: the measurement is parsed backwards from the newline in
+//                     fixed point; the name is hashed four bytes at a time (aligned loads, funnel shift) and
+//                     resolved in an L2-resident open-addressing table of 16-byte slots {hash, id<<8|len}.  A known
+//                     name costs one slot read plus a word-wise compare against the dictionary row of its id; a
+//                     new name takes the slot with one CAS, draws the next dense id, stores its bytes into the
+//                     dictionary row and publishes {id, len}.  Traffic: the text a second time + 16 B per row.
+//   v1 (one thread per 128-byte segment, byte-wise FNV-1a and compare): 1e8 rows in 18.8 ms end to end.
 #include <cstdlib>
 
 #include "kgb_select.cuh"
@@ -24,15 +26,29 @@ namespace kgb {
 constexpr int BRC_LOG2_SLOTS = 18;
 constexpr u64 BRC_SLOTS = 1ull << BRC_LOG2_SLOTS;
 constexpr u64 BRC_UNSET = ~0ull;
-struct __align__(32) BrcSlot {
-    u64 hash;  // 0 = free
-    u64 span;  // (byte offset << 8) | length of one occurrence of the name; BRC_UNSET until published
-    u64 id;    // dense id in first-arrival order; BRC_UNSET until published
-    u64 pad;
+constexpr int BRC_NAME_BYTES = 256;                 // dictionary row: a name of <= 255 bytes as zero-extended 32-bit words
+constexpr int BRC_NAME_WORDS = BRC_NAME_BYTES / 4;
+constexpr int BRC_THREADS = 512;
+constexpr int BRC_MAX_LINES = (int)(SEL_TILE / 6) + 1;  // the shortest valid line, "a;0.0\n", is 6 bytes
+struct __align__(32) BrcSlot {  // one 32-byte sector: a lookup is ONE 256-bit load
+    u64 hash;   // 0 = free; set once by the claimant's CAS
+    u64 idlen;  // (dense id in first-arrival order << 8) | name length; BRC_UNSET until the name is published
+    u64 n0, n1; // the name's first 16 bytes (zero-extended): names of <= 16 bytes never touch the dictionary rows
 };
+struct Slot4 {
+    u64 hash, idlen, n0, n1;
+};
+__device__ __forceinline__ Slot4 ld_slot(const BrcSlot* p) {
+    Slot4 v;
+    asm volatile("ld.relaxed.gpu.global.v4.u64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(v.hash), "=l"(v.idlen), "=l"(v.n0), "=l"(v.n1)
+                 : "l"(p)
+                 : "memory");
+    return v;
+}
 struct BrcCtl {
     unsigned long long n_names;
-    int err;  // 1 malformed row, 2 dictionary full, 3 a slot was never published
+    int err;  // 1 malformed row, 2 dictionary full / name too long, 3 a slot was never published
 };
 
 // workspace: [select state (tile counters)] [mask words] [BrcCtl 256 B] [table]
@@ -65,37 +81,57 @@ __device__ __forceinline__ u32 nl4(u32 x) {
     return ((m >> 7) | (m >> 14) | (m >> 21) | (m >> 28)) & 0xfu;
 }
 
+// 16 bytes -> 16 mask bits
+__device__ __forceinline__ u32 nl16(uint4 q) { return nl4(q.x) | (nl4(q.y) << 4) | (nl4(q.z) << 8) | (nl4(q.w) << 12); }
+
+constexpr int BRC_MASK_ROWS = 8;                         // 512-byte rows per warp step: 8 x 128-bit loads in flight per lane
+constexpr int BRC_MASK_STEP = BRC_MASK_ROWS * 512;       // bytes per warp step (divides the 65536-byte tile)
+
 __global__ void __launch_bounds__(256) brc_mask_kernel(const unsigned char* __restrict__ text, i64 n, u32* __restrict__ masks,
                                                         unsigned long long* __restrict__ tilecnt) {
     const int lane = threadIdx.x & 31;
-    const i64 nsteps = (n + SEL_WARP_ELEMS - 1) / SEL_WARP_ELEMS;
+    const i64 nsteps = (n + BRC_MASK_STEP - 1) / BRC_MASK_STEP;
     const i64 wstride = (i64)gridDim.x * 8;
     const bool aligned = (reinterpret_cast<uintptr_t>(text) & 15) == 0;
     for (i64 step = (i64)blockIdx.x * 8 + (threadIdx.x >> 5); step < nsteps; step += wstride) {
-        const i64 b0 = step * SEL_WARP_ELEMS + lane * 32;  // this lane's 32 bytes -> mask word `lane` of the step
-        u32 word = 0;
-        if (aligned && b0 + 32 <= n) {
-            const uint4 q0 = __ldcs(reinterpret_cast<const uint4*>(text + b0));
-            const uint4 q1 = __ldcs(reinterpret_cast<const uint4*>(text + b0 + 16));
-            word = nl4(q0.x) | (nl4(q0.y) << 4) | (nl4(q0.z) << 8) | (nl4(q0.w) << 12) | (nl4(q1.x) << 16) |
-                   (nl4(q1.y) << 20) | (nl4(q1.z) << 24) | (nl4(q1.w) << 28);
+        const i64 s0 = step * BRC_MASK_STEP;
+        u32 h[BRC_MASK_ROWS];  // row r: 16 mask bits for bytes s0 + 512 r + 16 lane ..
+        if (aligned && s0 + BRC_MASK_STEP <= n) {
+            uint4 q[BRC_MASK_ROWS];
+#pragma unroll
+            for (int r = 0; r < BRC_MASK_ROWS; r++)  // volatile: all eight loads are issued before the first compare
+                asm volatile("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(q[r].x), "=r"(q[r].y), "=r"(q[r].z), "=r"(q[r].w)
+                             : "l"(text + s0 + r * 512 + lane * 16));
+#pragma unroll
+            for (int r = 0; r < BRC_MASK_ROWS; r++) h[r] = nl16(q[r]);
         } else {
-            for (int j = 0; j < 32; j++)
-                if (b0 + j < n && text[b0 + j] == '\n') word |= 1u << j;
+#pragma unroll 1
+            for (int r = 0; r < BRC_MASK_ROWS; r++) {
+                const i64 b0 = s0 + r * 512 + lane * 16;
+                u32 w = 0;
+                for (int j = 0; j < 16; j++)
+                    if (b0 + j < n && text[b0 + j] == '\n') w |= 1u << j;
+                h[r] = w;
+            }
         }
-        masks[step * 32 + lane] = word;
-        const u32 hits = __reduce_add_sync(0xffffffffu, (u32)__popc(word));
-        if (lane == 0 && hits) atomicAdd(&tilecnt[step / SEL_TILE_STEPS], (unsigned long long)hits);
+        // a mask word covers 32 bytes = the halves of lanes 2k and 2k+1 of one row.  Rows are paired so that one
+        // exchange serves both: the even lane assembles word k of row r, the odd lane word k of row r + 1.
+        u32 hits = 0;
+        const i64 wbase = s0 / 32;
+        const i64 nwords = (n + SEL_WARP_ELEMS - 1) / SEL_WARP_ELEMS * 32;  // select_mask_words(n)
+#pragma unroll
+        for (int r = 0; r < BRC_MASK_ROWS; r += 2) {
+            const u32 send = (lane & 1) ? h[r] : h[r + 1];
+            const u32 recv = __shfl_xor_sync(0xffffffffu, send, 1);
+            const u32 word = (lane & 1) ? (recv | (h[r + 1] << 16)) : (h[r] | (recv << 16));
+            const i64 wi = wbase + (r + (lane & 1)) * 16 + (lane >> 1);
+            if (wi < nwords) masks[wi] = word;
+            hits += __popc(word);
+        }
+        hits = __reduce_add_sync(0xffffffffu, hits);
+        if (lane == 0 && hits) atomicAdd(&tilecnt[s0 / SEL_TILE], (unsigned long long)hits);
     }
-}
-
-__device__ __forceinline__ u64 fnv1a(const unsigned char* __restrict__ p, int len) {
-    u64 h = 0xcbf29ce484222325ull;
-    for (int j = 0; j < len; j++) {
-        h ^= (u64)p[j];
-        h *= 0x100000001b3ull;
-    }
-    return h ? h : 1ull;  // 0 marks a free slot
 }
 
 // position of the newest '\n' strictly before byte position p (or -1): the line containing p starts right after it
@@ -110,25 +146,73 @@ __device__ __forceinline__ i64 prev_newline(const u32* __restrict__ masks, i64 p
     return w * 32 + (31 - __clz(m));
 }
 
-__global__ void __launch_bounds__(SEL_THREADS) brc_parse_kernel(const unsigned char* __restrict__ text, i64 n,
-                                                                 const u32* __restrict__ masks, i64 nwords,
-                                                                 const unsigned long long* __restrict__ offs,
-                                                                 BrcSlot* __restrict__ tab, BrcCtl* __restrict__ ctl,
-                                                                 i64* __restrict__ id_out, double* __restrict__ temp_out,
-                                                                 i64* __restrict__ dict_off, int* __restrict__ dict_len,
-                                                                 i64 dict_capacity) {
-    __shared__ u32 s_wcnt[SEL_THREADS / 32];
+// Bytes [0, 16) at `p` (any alignment) as two little-endian 64-bit words, zero from byte `len` on.  The text is read
+// through ALIGNED 32-bit loads — five words cover 16 bytes at any alignment, neighbours are funnel-shifted — and never
+// past the word that holds the buffer's last byte.
+__device__ __forceinline__ void load16(const unsigned char* p, int len, const unsigned char* text_end, u64& lo, u64& hi) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const u32* aw = reinterpret_cast<const u32*>(a & ~(uintptr_t)3);
+    const u32 sh = (u32)(a & 3) * 8;
+    u32 a0, a1, a2, a3, a4;
+    if (p + 24 <= text_end) {  // one bounds test for all five
+        a0 = __ldg(aw), a1 = __ldg(aw + 1), a2 = __ldg(aw + 2), a3 = __ldg(aw + 3), a4 = __ldg(aw + 4);
+    } else {
+        const u32* we = reinterpret_cast<const u32*>((reinterpret_cast<uintptr_t>(text_end) + 3) & ~(uintptr_t)3);
+        a0 = __ldg(aw);
+        a1 = aw + 1 < we ? __ldg(aw + 1) : 0u, a2 = aw + 2 < we ? __ldg(aw + 2) : 0u;
+        a3 = aw + 3 < we ? __ldg(aw + 3) : 0u, a4 = aw + 4 < we ? __ldg(aw + 4) : 0u;
+    }
+    lo = (u64)__funnelshift_r(a0, a1, sh) | ((u64)__funnelshift_r(a1, a2, sh) << 32);
+    hi = (u64)__funnelshift_r(a2, a3, sh) | ((u64)__funnelshift_r(a3, a4, sh) << 32);
+    if (len < 8) lo &= (1ull << (8 * len)) - 1ull;
+    if (len < 16) hi = len <= 8 ? 0ull : hi & ((1ull << (8 * (len - 8))) - 1ull);
+}
+constexpr u64 BRC_MIX = 0xd6e8feb86659fd93ull;
+
+// One CTA per 65536-byte tile.  The tile's newline positions are expanded from the mask words into shared memory, then
+// LINE i of the tile goes to thread i mod 512: neighbouring lanes parse neighbouring lines, so a warp's text loads fall
+// in ~5 consecutive 128-byte lines (L1 serves the re-reads) and its 16 bytes of output per row are coalesced stores.
+__global__ void __launch_bounds__(256) brc_init_kernel(BrcSlot* __restrict__ tab, BrcCtl* __restrict__ ctl) {
+    const u64 i = (u64)blockIdx.x * 256 + threadIdx.x;
+    if (i < BRC_SLOTS) *reinterpret_cast<uint4*>(&tab[i]) = make_uint4(0u, 0u, 0xffffffffu, 0xffffffffu);  // {hash 0, idlen UNSET}
+    if (i == 0) {
+        ctl->n_names = 0;
+        ctl->err = 0;
+    }
+}
+
+// 3 CTAs/SM (40 registers); a 4-CTA build (32 registers, small spills) measured slower: 1.94 vs 1.83 ms at 1e8 rows
+__global__ void __launch_bounds__(BRC_THREADS, 3) brc_parse_kernel(const unsigned char* __restrict__ text, i64 n,
+                                                                    const u32* __restrict__ masks, i64 nwords,
+                                                                    const unsigned long long* __restrict__ offs,
+                                                                    BrcSlot* __restrict__ tab, BrcCtl* __restrict__ ctl,
+                                                                    i64* __restrict__ id_out, double* __restrict__ temp_out,
+                                                                    u32* __restrict__ dict_names, int* __restrict__ dict_len,
+                                                                    i64 dict_capacity) {
+    __shared__ unsigned short s_pos[BRC_MAX_LINES];
+    __shared__ u32 s_wcnt[BRC_THREADS / 32];
+    __shared__ i64 s_start0;
+    __shared__ double s_tenth[1000];  // tenths -> tenths / 10.0, correctly rounded (one LDS instead of a division per row)
+    constexpr int WPT = SEL_TILE_WORDS / BRC_THREADS;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const i64 tile = blockIdx.x;
     const unsigned long long base = offs[tile];
-    if (offs[tile + 1] == base) return;  // no line ends in this tile
-    const i64 w0 = tile * SEL_TILE_WORDS + (i64)tid * SEL_WPT;
-    u32 m[SEL_WPT];
+    const u32 nlines = (u32)(offs[tile + 1] - base);
+    if (nlines == 0) return;  // no line ends in this tile
+    if (nlines > (u32)BRC_MAX_LINES) {  // lines shorter than 6 bytes: malformed
+        if (tid == 0) ctl->err = 1;
+        return;
+    }
+    const i64 byte0 = tile * SEL_TILE;
+    if (tid == 0) s_start0 = prev_newline(masks, byte0) + 1;  // start of the line that ends first in this tile
+    for (int t = tid; t < 1000; t += BRC_THREADS) s_tenth[t] = (double)t / 10.0;
+    const i64 w0 = tile * SEL_TILE_WORDS + (i64)tid * WPT;
+    u32 m[WPT];
 #pragma unroll
-    for (int j = 0; j < SEL_WPT; j++) m[j] = (w0 + j < nwords) ? masks[w0 + j] : 0u;
+    for (int j = 0; j < WPT; j++) m[j] = (w0 + j < nwords) ? masks[w0 + j] : 0u;
     u32 cnt = 0;
 #pragma unroll
-    for (int j = 0; j < SEL_WPT; j++) cnt += __popc(m[j]);
+    for (int j = 0; j < WPT; j++) cnt += __popc(m[j]);
     u32 inc = cnt;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -137,103 +221,133 @@ __global__ void __launch_bounds__(SEL_THREADS) brc_parse_kernel(const unsigned c
     }
     if (lane == 31) s_wcnt[warp] = inc;
     __syncthreads();
-    u32 woff = 0;
+    u32 k = inc - cnt;
 #pragma unroll
-    for (int w = 0; w < SEL_THREADS / 32; w++)
-        if (w < warp) woff += s_wcnt[w];
-    u64 row = base + woff + (inc - cnt);
-    i64 start = -2;  // start of the next line this thread handles; -2 = not known yet
-#pragma unroll 1
-    for (int j = 0; j < SEL_WPT; j++) {
+    for (int w = 0; w < BRC_THREADS / 32; w++)
+        if (w < warp) k += s_wcnt[w];
+#pragma unroll
+    for (int j = 0; j < WPT; j++) {
         u32 mm = m[j];
         while (mm) {
             const int b = __ffs(mm) - 1;
             mm &= mm - 1;
-            const i64 p = (w0 + j) * 32 + b;  // this line's '\n'
-            if (start == -2) start = prev_newline(masks, p) + 1;
-            // ---- measurement, backwards from the newline: [-]d[d].d
-            bool bad = p - start < 5;  // shortest line: "a;0.0"
-            int tenths = 0;
-            i64 semi = start;
-            bool neg = false;
-            if (!bad) {
-                const int f = text[p - 1] - '0', dot = text[p - 2], d1 = text[p - 3] - '0';
-                i64 q = p - 4;
-                int d2 = 0;
-                int c = text[q];
-                if (c >= '0' && c <= '9') {
-                    d2 = c - '0';
-                    q--;
-                    c = q >= start ? text[q] : 0;
-                }
-                if (c == '-') {
-                    neg = true;
-                    q--;
-                    c = q >= start ? text[q] : 0;
-                }
-                bad = (unsigned)f > 9u || (unsigned)d1 > 9u || dot != '.' || c != ';' || q <= start;
-                tenths = (d2 * 10 + d1) * 10 + f;
-                semi = q;
-            }
-            if (bad) {
-                ctl->err = 1;
-            } else {
-                double v = (double)tenths / 10.0;  // correctly rounded quotient of two exact integers == float("d.d")
-                temp_out[row] = neg ? -v : v;
-                // ---- station: hash the name, find or claim its slot
-                const int len = (int)(semi - start);
-                const unsigned char* name = text + start;
-                const u64 h = fnv1a(name, len);
-                const u64 span = ((u64)start << 8) | (u64)(len & 255);
-                u64 slot = (h ^ (h >> 29)) & (BRC_SLOTS - 1);
-                u64 id = BRC_UNSET;
-                for (u64 probe = 0; probe < BRC_SLOTS && id == BRC_UNSET; probe++) {
-                    u64 cur = ld_relaxed_u64(&tab[slot].hash);
-                    if (cur == 0) {
-                        cur = atomicCAS((unsigned long long*)&tab[slot].hash, 0ull, (unsigned long long)h);
-                        if (cur == 0) {  // ours: draw the next dense id and publish {span, id}
-                            const u64 nid = atomicAdd(&ctl->n_names, 1ull);
-                            if ((i64)nid < dict_capacity && len <= 255) {
-                                dict_off[nid] = start;
-                                dict_len[nid] = len;
-                            } else {
-                                ctl->err = 2;
-                            }
-                            st_relaxed_u64(&tab[slot].span, span);
-                            __threadfence();
-                            st_relaxed_u64(&tab[slot].id, nid);
-                            id = nid;
-                            break;
-                        }
-                    }
-                    if (cur == h) {
-                        u64 sid = ld_relaxed_u64(&tab[slot].id);
-                        for (u32 spins = 0; sid == BRC_UNSET; spins++) {  // the claimant publishes right after its CAS
-                            __nanosleep(32);
-                            sid = ld_relaxed_u64(&tab[slot].id);
-                            if (spins > (1u << 22)) {
-                                ctl->err = 3;
-                                break;
-                            }
-                        }
-                        if (sid == BRC_UNSET) break;
-                        __threadfence();
-                        const u64 sp = ld_relaxed_u64(&tab[slot].span);
-                        if ((int)(sp & 255) == len) {
-                            const unsigned char* other = text + (sp >> 8);
-                            bool same = true;
-                            for (int t = 0; t < len; t++) same &= other[t] == name[t];
-                            if (same) id = sid;
-                        }
-                    }
-                    slot = (slot + 1) & (BRC_SLOTS - 1);
-                }
-                if (id == BRC_UNSET && ctl->err == 0) ctl->err = 2;
-                id_out[row] = (i64)id;
-            }
-            row++;
-            start = p + 1;
+            s_pos[k++] = (unsigned short)((tid * WPT + j) * 32 + b);
         }
+    }
+    __syncthreads();
+    const unsigned char* text_end = text + n;
+#pragma unroll 1
+    for (u32 i = tid; i < nlines; i += BRC_THREADS) {
+        const i64 p = byte0 + s_pos[i];                              // this line's '\n'
+        const i64 start = i ? byte0 + s_pos[i - 1] + 1 : s_start0;
+        // ---- measurement, backwards from the newline: [-]d[d].d
+        if (p - start < 5) {  // shortest line: "a;0.0"
+            ctl->err = 1;
+            continue;
+        }
+        const int f = __ldg(text + p - 1) - '0', dot = __ldg(text + p - 2), d1 = __ldg(text + p - 3) - '0';
+        const int c4 = __ldg(text + p - 4), c5 = __ldg(text + p - 5), c6 = p - 6 >= start ? __ldg(text + p - 6) : 0;
+        int d2 = 0, back = 4;  // `back`: distance from the newline to the ';'
+        int c = c4;
+        if (c >= '0' && c <= '9') {
+            d2 = c - '0';
+            back = 5;
+            c = c5;
+        }
+        bool neg = false;
+        if (c == '-') {
+            neg = true;
+            back++;
+            c = back == 5 ? c5 : c6;
+        }
+        const int len = (int)(p - back - start);
+        if ((unsigned)f > 9u || (unsigned)d1 > 9u || dot != '.' || c != ';' || len <= 0) {
+            ctl->err = 1;
+            continue;
+        }
+        const int tenths = (d2 * 10 + d1) * 10 + f;
+        const double v = s_tenth[tenths];  // correctly rounded quotient of two exact integers == float("d.d")
+        temp_out[base + i] = neg ? -v : v;
+        if (len > BRC_NAME_BYTES - 1) {
+            ctl->err = 2;
+            continue;
+        }
+        // ---- station: the first 16 bytes travel in two registers, the hash takes four bytes at a time beyond them
+        const unsigned char* name = text + start;
+        u64 n0, n1;
+        load16(name, len, text_end, n0, n1);
+        u64 h = 0x9e3779b97f4a7c15ull ^ (u64)len;
+        h = (h ^ n0) * BRC_MIX;
+        h = (h ^ (h >> 32) ^ n1) * BRC_MIX;
+        for (int c = 16; c < len; c += 16) {  // rare for station names
+            u64 lo, hi;
+            load16(name + c, len - c, text_end, lo, hi);
+            h = (h ^ (h >> 32) ^ lo) * BRC_MIX;
+            h = (h ^ (h >> 32) ^ hi) * BRC_MIX;
+        }
+        h ^= h >> 32;
+        h *= BRC_MIX;
+        h ^= h >> 29;
+        if (h == 0) h = 1;  // 0 marks a free slot
+        u64 slot = h >> (64 - BRC_LOG2_SLOTS);
+        u64 id = BRC_UNSET;
+        for (u64 probe = 0; probe < BRC_SLOTS && id == BRC_UNSET; probe++) {
+            Slot4 sv = ld_slot(&tab[slot]);
+            if (sv.hash == 0) {
+                sv.hash = atomicCAS((unsigned long long*)&tab[slot].hash, 0ull, (unsigned long long)h);
+                if (sv.hash == 0) {  // ours: draw the next dense id, store the name, then publish {id, len}
+                    const u64 nid = atomicAdd(&ctl->n_names, 1ull);
+                    st_relaxed_u64(&tab[slot].n0, n0);
+                    st_relaxed_u64(&tab[slot].n1, n1);
+                    if ((i64)nid < dict_capacity) {
+                        uint4* row = reinterpret_cast<uint4*>(dict_names + nid * BRC_NAME_WORDS);
+                        for (int c = 0; c < len; c += 16) {  // zero-filled to the next multiple of 16 bytes
+                            u64 lo, hi;
+                            load16(name + c, len - c, text_end, lo, hi);
+                            __stcg(row + (c >> 4), make_uint4((u32)lo, (u32)(lo >> 32), (u32)hi, (u32)(hi >> 32)));
+                        }
+                        dict_len[nid] = len;
+                    } else {
+                        ctl->err = 2;
+                    }
+                    __threadfence();
+                    st_relaxed_u64(&tab[slot].idlen, (nid << 8) | (u64)len);
+                    id = nid;
+                    break;
+                }
+                sv.idlen = BRC_UNSET;  // somebody else's claim: if it is our hash, read the slot again below
+            }
+            if (sv.hash == h) {
+                for (u32 spins = 0; sv.idlen == BRC_UNSET; spins++) {  // the claimant publishes right after its CAS
+                    if (spins) __nanosleep(32);
+                    sv = ld_slot(&tab[slot]);
+                    if (spins > (1u << 22)) {
+                        ctl->err = 3;
+                        break;
+                    }
+                }
+                if (sv.idlen == BRC_UNSET) break;
+                if (sv.n0 != n0 || sv.n1 != n1) sv = ld_slot(&tab[slot]);  // published slots are final: rules out a torn first read
+                if ((int)(sv.idlen & 255) == len && sv.n0 == n0 && sv.n1 == n1 && (i64)(sv.idlen >> 8) < dict_capacity) {
+                    u64 diff = 0;
+                    if (len > 16) {  // the rest of the name against the dictionary row, 16 bytes per load
+                        // no fence on this side: the row's address is computed from the id just read, the loads go to
+                        // L2 (the point of coherence) and the writer fenced between the row and the id
+                        const uint4* row = reinterpret_cast<const uint4*>(dict_names + (sv.idlen >> 8) * BRC_NAME_WORDS);
+                        for (int c = 16; c < len; c += 16) {
+                            const uint4 r = __ldcg(row + (c >> 4));
+                            u64 lo, hi;
+                            load16(name + c, len - c, text_end, lo, hi);
+                            diff |= (lo ^ ((u64)r.x | ((u64)r.y << 32))) | (hi ^ ((u64)r.z | ((u64)r.w << 32)));
+                        }
+                    }
+                    if (diff == 0) id = sv.idlen >> 8;
+                }
+            }
+            slot = (slot + 1) & (BRC_SLOTS - 1);
+        }
+        if (id == BRC_UNSET && ctl->err == 0) ctl->err = 2;
+        id_out[base + i] = (i64)id;
     }
 }
 
@@ -258,7 +372,7 @@ extern "C" int kgb_brc_scan(const uint8_t* text, int64_t n_bytes, int64_t* rows_
     cudaStream_t st = (cudaStream_t)stream;
     BrcWs w = carve_brc(workspace, n_bytes);
     KGB_CUDA_CHECK(cudaMemsetAsync(workspace, 0, select_state_bytes(n_bytes), st));
-    const long long steps = (long long)((n_bytes + SEL_WARP_ELEMS - 1) / SEL_WARP_ELEMS);
+    const long long steps = (long long)((n_bytes + BRC_MASK_STEP - 1) / BRC_MASK_STEP);
     long long mb = (steps + 7) / 8;
     const long long cap = (long long)sm_count() * 8;
     if (mb > cap) mb = cap;
@@ -277,27 +391,24 @@ extern "C" int kgb_brc_scan(const uint8_t* text, int64_t n_bytes, int64_t* rows_
 }
 
 extern "C" int kgb_brc_parse(const uint8_t* text, int64_t n_bytes, int64_t rows, int64_t* id_out, double* temp_out,
-                             int64_t* dict_off_out, int32_t* dict_len_out, int64_t dict_capacity,
+                             uint8_t* dict_names_out, int32_t* dict_len_out, int64_t dict_capacity,
                              int64_t* n_names_out_host, void* workspace, size_t workspace_bytes, void* stream) {
     KGB_REQUIRE(current_device() >= 0, "kgb_init() has not been called on this thread");
     KGB_REQUIRE(n_names_out_host && n_bytes >= 0 && rows >= 0 && dict_capacity >= 0, "kgb_brc_parse: bad arguments");
     *n_names_out_host = 0;
     if (n_bytes == 0 || rows == 0) return KGB_OK;
-    KGB_REQUIRE(text && id_out && temp_out && dict_off_out && dict_len_out && workspace &&
+    KGB_REQUIRE(text && id_out && temp_out && dict_names_out && dict_len_out && workspace &&
                     workspace_bytes >= carve_brc(nullptr, n_bytes).total,
                 "kgb_brc_parse: null pointer or workspace too small");
     KGB_REQUIRE(dict_capacity <= (int64_t)(BRC_SLOTS / 2), "kgb_brc_parse: dictionary capacity above %lld",
                 (long long)(BRC_SLOTS / 2));
     cudaStream_t st = (cudaStream_t)stream;
     BrcWs w = carve_brc(workspace, n_bytes);
-    KGB_CUDA_CHECK(cudaMemsetAsync(w.ctl, 0, 128, st));
-    KGB_CUDA_CHECK(cudaMemsetAsync(w.tab, 0, (size_t)BRC_SLOTS * sizeof(BrcSlot), st));
-    // span / id words start as BRC_UNSET: one strided memset would do, a second full one is simpler and 8 MB is 2 us
-    KGB_CUDA_CHECK(cudaMemset2DAsync((char*)w.tab + 8, sizeof(BrcSlot), 0xff, 16, (size_t)BRC_SLOTS, st));
+    brc_init_kernel<<<(unsigned)(BRC_SLOTS / 256), 256, 0, st>>>(w.tab, w.ctl);
     const i64 ntiles = (i64)select_tiles(n_bytes);
-    brc_parse_kernel<<<(unsigned)ntiles, SEL_THREADS, 0, st>>>(text, n_bytes, w.masks, (i64)select_mask_words(n_bytes),
+    brc_parse_kernel<<<(unsigned)ntiles, BRC_THREADS, 0, st>>>(text, n_bytes, w.masks, (i64)select_mask_words(n_bytes),
                                                              w.tilecnt, w.tab, w.ctl, (i64*)id_out, temp_out,
-                                                             (i64*)dict_off_out, dict_len_out, dict_capacity);
+                                                             (u32*)dict_names_out, dict_len_out, dict_capacity);
     KGB_CUDA_CHECK(cudaGetLastError());
     BrcCtl h;
     KGB_CUDA_CHECK(cudaMemcpyAsync(&h, w.ctl, sizeof(BrcCtl), cudaMemcpyDeviceToHost, st));

@@ -35,10 +35,12 @@ def _as_device_text(text, device):
     return torch.from_numpy(arr.copy()).to(device)
 
 
-def parse(text, device=None):
-    """-> (ids int64 DeviceArray [rows], temps float64 DeviceArray [rows], names list[str] sorted ascending).
-    ids index `names`.  `text` is bytes / str / a uint8 array or tensor (host or device) of complete lines."""
-    device = torch.device(device) if device is not None else ops.default_device()
+NAME_BYTES = 256  # one dictionary row (include/kgb200.h: kgb_brc_parse)
+
+
+def _parse_arrival(text, device, fetch_names=True):
+    """-> (ids in first-arrival order (torch int64), temps (torch float64), (names list[bytes] by arrival id, the same
+    as a fixed-width numpy bytes array or None)).  fetch_names=False stops after the two C-ABI calls."""
     t = _as_device_text(text, device)
     n = t.numel()
     lib, stream = ops._lib_for(device)
@@ -50,26 +52,49 @@ def parse(text, device=None):
     r = rows.value
     ids = torch.empty(r, dtype=torch.int64, device=device)
     temps = torch.empty(r, dtype=torch.float64, device=device)
-    doff = torch.empty(DICT_CAPACITY, dtype=torch.int64, device=device)
+    dnames = torch.zeros(DICT_CAPACITY * NAME_BYTES, dtype=torch.uint8, device=device)
     dlen = torch.empty(DICT_CAPACITY, dtype=torch.int32, device=device)
     n_names = ctypes.c_int64()
-    _lib.check(lib.kgb_brc_parse(t.data_ptr(), n, r, ids.data_ptr(), temps.data_ptr(), doff.data_ptr(), dlen.data_ptr(),
+    _lib.check(lib.kgb_brc_parse(t.data_ptr(), n, r, ids.data_ptr(), temps.data_ptr(), dnames.data_ptr(), dlen.data_ptr(),
                                  DICT_CAPACITY, ctypes.byref(n_names), ws.data_ptr(), wsb.value, stream), "kgb_brc_parse")
     d = n_names.value
-    if d == 0:
-        return DeviceArray(ids), DeviceArray(temps), []
-    # the dictionary: D names of <= 255 bytes, fetched as one padded [D, L] block (a gather on the device, one copy)
-    off = doff[:d]
-    ln = dlen[:d].to(torch.int64)
-    L = int(ln.max().item())
-    cols = torch.arange(L, device=device, dtype=torch.int64)
-    idx = (off[:, None] + cols[None, :]).clamp_(max=n - 1)
-    block = t[idx.reshape(-1)].reshape(d, L).cpu().numpy()
-    lens = ln.cpu().numpy()
-    raw = [bytes(block[i, :lens[i]]) for i in range(d)]
-    order = sorted(range(d), key=lambda i: raw[i])           # par.kg:4 `s@<s`: ascending names
+    if d == 0 or not fetch_names:
+        return ids, temps, ([], None)
+    # the dictionary comes back as one [D, 256] block of zero-padded names: two small copies, no per-row work
+    block = dnames[:d * NAME_BYTES].cpu().numpy().reshape(d, NAME_BYTES)
+    lens = dlen[:d].cpu().numpy()
+    L = int(lens.max())
+    fixed = None
+    if (block[:, :L] == 0).sum() == int((L - lens).sum()):   # no NUL inside a name: fixed-width bytes strip exactly the padding
+        fixed = np.ascontiguousarray(block[:, :L]).view(f"S{L}").reshape(d)
+        raw = fixed.tolist()
+    else:
+        raw = [bytes(block[i, :lens[i]]) for i in range(d)]
+    return ids, temps, (raw, fixed)
+
+
+def _name_order(names):
+    """par.kg:4 `s@<s`: ascending names (bytewise).  -> (order: sorted position -> arrival id, rank: the inverse)"""
+    raw, fixed = names
+    d = len(raw)
+    if fixed is not None:
+        order = np.argsort(fixed, kind="stable").astype(np.int64)   # unsigned bytewise, as Python compares bytes
+    else:
+        order = np.asarray(sorted(range(d), key=raw.__getitem__), dtype=np.int64)
     rank = np.empty(d, dtype=np.int64)
-    rank[np.asarray(order, dtype=np.int64)] = np.arange(d, dtype=np.int64)
+    rank[order] = np.arange(d, dtype=np.int64)
+    return order, rank
+
+
+def parse(text, device=None):
+    """-> (ids int64 DeviceArray [rows], temps float64 DeviceArray [rows], names list[str] sorted ascending).
+    ids index `names`.  `text` is bytes / str / a uint8 array or tensor (host or device) of complete lines."""
+    device = torch.device(device) if device is not None else ops.default_device()
+    ids, temps, names = _parse_arrival(text, device)
+    raw = names[0]
+    if not raw:
+        return DeviceArray(ids), DeviceArray(temps), []
+    order, rank = _name_order(names)
     # arrival-order ids -> name-order ids: a D-entry lookup gathered over the rows (8 B/row in, 8 B/row out)
     lut = ops.asarray(rank, device=device)
     ids = ops.gather(lut, DeviceArray(ids))
@@ -77,14 +102,19 @@ def parse(text, device=None):
 
 
 def aggregate(text, device=None):
-    """-> (names sorted, min, mean, max as host float64 arrays, count int64): examples/1brc end to end."""
-    ids, temps, names = parse(text, device)
-    if not names:
+    """-> (names sorted, min, mean, max as host float64 arrays, count int64): examples/1brc end to end.
+    The rows are aggregated under their arrival-order ids and only the D results are put in name order."""
+    device = torch.device(device) if device is not None else ops.default_device()
+    ids, temps, names = _parse_arrival(text, device)
+    raw = names[0]
+    if not raw:
         z = np.zeros(0)
         return [], z, z, z, np.zeros(0, dtype=np.int64)
-    mn, mx, sm, ct = ops.groupagg(ids, temps, len(names))
-    ctn = ct.to_numpy()
-    return names, mn.to_numpy(), sm.to_numpy() / ctn, mx.to_numpy(), ctn
+    order, _ = _name_order(names)
+    mn, mx, sm, ct = ops.groupagg(DeviceArray(ids), DeviceArray(temps), len(raw))
+    ctn = ct.to_numpy()[order]
+    return ([raw[i].decode("utf-8") for i in order], mn.to_numpy()[order], sm.to_numpy()[order] / ctn,
+            mx.to_numpy()[order], ctn)
 
 
 def report(text, device=None):

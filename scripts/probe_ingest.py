@@ -8,14 +8,10 @@ from klongpy_b200 import ingest, ops  # noqa: E402
 
 dev = torch.device("cuda:0")
 ops.set_default_device(dev)
-rng = np.random.default_rng(5)
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 100
-names = sorted({"".join(rng.choice(list("abcdefghijklmnopqrstuvwxyz ABCDEFGHIJK"), int(rng.integers(3, 20)))).strip() or "q"
-                for _ in range(12_000)})[:10_000]
-ids = rng.integers(0, len(names), 1_000_000)
-tenths = np.clip(np.round(rng.normal(100, 250, ids.size)), -999, 999).astype(np.int64)
 t0 = time.perf_counter()
-block = "".join(f"{names[i]};{'-' if t < 0 else ''}{abs(int(t)) // 10}.{abs(int(t)) % 10}\n" for i, t in zip(ids, tenths)).encode()
+from bench import synthetic_1brc_block  # noqa: E402
+block, names, ids, tenths = synthetic_1brc_block()
 print(f"host text build {time.perf_counter() - t0:.1f} s, {len(block) / 1e6:.1f} MB per 1e6 rows", flush=True)
 text = torch.from_numpy(np.frombuffer(block, dtype=np.uint8).copy()).to(dev).repeat(reps)
 n = text.numel()
@@ -39,6 +35,28 @@ assert len(nm) == len(names) and i2.size == rows
 ref_ids = torch.from_numpy(ids).to(dev).repeat(reps)
 ref_t = torch.from_numpy(tenths / 10.0).to(dev).repeat(reps)
 assert nm == sorted(names, key=lambda s: s.encode()) and torch.equal(i2.tensor, ref_ids) and torch.equal(t2.tensor, ref_t)
+del i2, t2, ref_ids, ref_t
+# the two C-ABI calls on their own (device time of everything they enqueue; each ends with a synchronising read)
+import ctypes
+from klongpy_b200 import _lib
+lib, stream = ops._lib_for(dev)
+wsb = ctypes.c_size_t()
+lib.kgb_brc_workspace_bytes(n, ctypes.byref(wsb))
+ws = torch.empty(wsb.value, dtype=torch.uint8, device=dev)
+r = ctypes.c_int64()
+o_ids = torch.empty(rows, dtype=torch.int64, device=dev)
+o_t = torch.empty(rows, dtype=torch.float64, device=dev)
+dn = torch.zeros(ingest.DICT_CAPACITY * 256, dtype=torch.uint8, device=dev)
+dl = torch.empty(ingest.DICT_CAPACITY, dtype=torch.int32, device=dev)
+nn = ctypes.c_int64()
+scan = lambda: _lib.check(lib.kgb_brc_scan(text.data_ptr(), n, ctypes.byref(r), ws.data_ptr(), wsb.value, stream), "scan")
+prs = lambda: _lib.check(lib.kgb_brc_parse(text.data_ptr(), n, rows, o_ids.data_ptr(), o_t.data_ptr(), dn.data_ptr(), dl.data_ptr(),
+                                           ingest.DICT_CAPACITY, ctypes.byref(nn), ws.data_ptr(), wsb.value, stream), "parse")
+ms_s = timeit(scan, 5)
+ms_p = timeit(prs, 5)
+alg = n + 16 * rows
+print(f"kgb_brc_scan  {ms_s:.3f} ms ({n / ms_s / 1e6:.0f} GB/s of text)   kgb_brc_parse {ms_p:.3f} ms   "
+      f"both {ms_s + ms_p:.3f} ms = {alg / (ms_s + ms_p) / 1e6:.0f} GB/s algorithmic ({alg / rows:.1f} B/row: text + 16 B out)", flush=True)
 ms = timeit(lambda: ingest.parse(text))
 print(f"parse     rows={rows} bytes={n}: {ms:.2f} ms  {rows / ms / 1e6:.2f} Grows/s  {n / ms / 1e6:.0f} GB/s of text", flush=True)
 ms = timeit(lambda: ingest.aggregate(text))

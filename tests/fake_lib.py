@@ -396,11 +396,11 @@ class FakeLib:
         rows_out._obj.value = int(np.count_nonzero(t == 10))
         return 0
 
-    def kgb_brc_parse(self, text, n, rows, ids, temps, doff, dlen, cap, n_names_out, ws, wsb, stream):
+    def kgb_brc_parse(self, text, n, rows, ids, temps, dnames, dlen, cap, n_names_out, ws, wsb, stream):
         raw = bytes(view_bytes(text, n)) if n else b""
         seen, pos, r = {}, 0, 0
         ido, tmo = view(ids, rows, I64), view(temps, rows, F64)
-        dof, dln = view(doff, cap, I64), view(dlen, cap, I32)
+        dnm, dln = view_bytes(dnames, cap * 256).reshape(cap, 256), view(dlen, cap, I32)
         for line in raw.split(b"\n")[:-1]:
             name, _, meas = line.rpartition(b";")
             ok = len(name) > 0 and len(meas) in (3, 4, 5) and meas[-2:-1] == b"." and meas.lstrip(b"-").replace(b".", b"").isdigit()
@@ -411,7 +411,7 @@ class FakeLib:
                 if len(seen) >= cap:
                     self.err = b"kgb_brc_parse: more than %d distinct names" % cap
                     return 1
-                dof[len(seen)], dln[len(seen)] = pos, len(name)
+                dnm[len(seen), :len(name)], dln[len(seen)] = np.frombuffer(name, np.uint8), len(name)
                 seen[name] = len(seen)
             ido[r], tmo[r] = seen[name], float(meas)
             pos += len(line) + 1

@@ -105,3 +105,28 @@ def test_gpu_ingest_fixture_and_errors(golden):
         with pytest.raises(_lib.KgbError):
             ingest.parse(b"ok;1.0\n" + bad, device="cuda:0")
     assert ingest.parse(b"", device="cuda:0")[2] == []
+
+
+@pytest.mark.gpu
+def test_gpu_ingest_alignment_long_names_tile_edges():
+    """Names of every length 1..255 (rows of the dictionary are compared a word at a time), a text buffer that starts
+    at each of the four byte alignments, lines straddling the 65536-byte tile edges, and a 256-byte name rejected."""
+    import torch
+    from klongpy_b200 import _lib, ingest
+    rng = np.random.default_rng(11)
+    names = ["".join(rng.choice(list("abcdefghijklmnopqrstuvwxyz"), k)) for k in range(1, 256)]
+    names += [names[40][:-1] + "#", names[40][:-2] + "##", names[200][:-1] + "#"]  # same length, differ in the last bytes
+    rows = 40_000                                                                   # ~5 MB: ~80 tiles
+    ids = rng.integers(0, len(names), rows)
+    tenths = rng.integers(-999, 1000, rows)
+    text = "".join(f"{names[i]};{'-' if t < 0 else ''}{abs(int(t)) // 10}.{abs(int(t)) % 10}\n" for i, t in zip(ids, tenths)).encode()
+    rn, ri, rt = O.parse_1brc(text)
+    buf = torch.zeros(len(text) + 8, dtype=torch.uint8, device="cuda:0")
+    for shift in range(4):
+        view = buf[shift:shift + len(text)]
+        view.copy_(torch.from_numpy(np.frombuffer(text, dtype=np.uint8).copy()))
+        gi, gt, gn = ingest.parse(view, device="cuda:0")
+        assert gn == rn and np.array_equal(gi.to_numpy(), ri) and np.array_equal(gt.to_numpy(), rt), shift
+    with pytest.raises(_lib.KgbError):
+        ingest.parse(("x" * 256 + ";1.0\n").encode(), device="cuda:0")
+    assert ingest.parse(("x" * 255 + ";1.0\n").encode(), device="cuda:0")[2] == ["x" * 255]
