@@ -23,12 +23,11 @@
 
 namespace kgb {
 
-constexpr int BRC_LOG2_SLOTS = 18;
+constexpr int BRC_LOG2_SLOTS = 20;  // 32 MB; only the sectors of live names are ever hot (10k names: 320 KB)
 constexpr u64 BRC_SLOTS = 1ull << BRC_LOG2_SLOTS;
 constexpr u64 BRC_UNSET = ~0ull;
 constexpr int BRC_NAME_BYTES = 256;                 // dictionary row: a name of <= 255 bytes as zero-extended 32-bit words
 constexpr int BRC_NAME_WORDS = BRC_NAME_BYTES / 4;
-constexpr int BRC_THREADS = 512;
 constexpr int BRC_MAX_LINES = (int)(SEL_TILE / 6) + 1;  // the shortest valid line, "a;0.0\n", is 6 bytes
 struct __align__(32) BrcSlot {  // one 32-byte sector: a lookup is ONE 256-bit load
     u64 hash;   // 0 = free; set once by the claimant's CAS
@@ -75,14 +74,22 @@ static BrcWs carve_brc(void* ws, i64 n) {
     return w;
 }
 
-// 4 bytes -> 4 mask bits (bit i = byte i == '\n')
-__device__ __forceinline__ u32 nl4(u32 x) {
-    const u32 m = __vcmpeq4(x, 0x0a0a0a0au) & 0x80808080u;  // 0x80 per matching byte
-    return ((m >> 7) | (m >> 14) | (m >> 21) | (m >> 28)) & 0xfu;
+// 4 bytes -> their newline flags as the TOP nibble of the result (bit 28 + i = byte i is '\n'); five instructions.
+// Exact zero-byte test of x ^ 0x0a0a0a0a (no borrow between bytes), then one multiply gathers the four 0x80 flags:
+// flag i sits at bit 8i + 7 and the multiplier's term 2^(21 - 7i) moves it to bit 28 + i; every other partial product
+// lands on a distinct bit below 28 or overflows, so nothing carries into the nibble.
+__device__ __forceinline__ u32 nl4_top(u32 x) {
+    const u32 t = x ^ 0x0a0a0a0au;
+    const u32 m = ~(((t & 0x7f7f7f7fu) + 0x7f7f7f7fu) | t | 0x7f7f7f7fu);
+    return m * 0x00204081u;
 }
-
 // 16 bytes -> 16 mask bits
-__device__ __forceinline__ u32 nl16(uint4 q) { return nl4(q.x) | (nl4(q.y) << 4) | (nl4(q.z) << 8) | (nl4(q.w) << 12); }
+__device__ __forceinline__ u32 nl16(uint4 q) {
+    u32 r = nl4_top(q.w) >> 28;
+    r = __funnelshift_l(nl4_top(q.z), r, 4);
+    r = __funnelshift_l(nl4_top(q.y), r, 4);
+    return __funnelshift_l(nl4_top(q.x), r, 4);
+}
 
 constexpr int BRC_MASK_ROWS = 8;                         // 512-byte rows per warp step: 8 x 128-bit loads in flight per lane
 constexpr int BRC_MASK_STEP = BRC_MASK_ROWS * 512;       // bytes per warp step (divides the 65536-byte tile)
@@ -134,44 +141,26 @@ __global__ void __launch_bounds__(256) brc_mask_kernel(const unsigned char* __re
     }
 }
 
-// position of the newest '\n' strictly before byte position p (or -1): the line containing p starts right after it
-__device__ __forceinline__ i64 prev_newline(const u32* __restrict__ masks, i64 p) {
-    i64 w = p >> 5;
-    const int b = (int)(p & 31);
-    u32 m = b ? (masks[w] & ((1u << b) - 1u)) : 0u;
-    while (m == 0) {
-        if (w == 0) return -1;
-        m = masks[--w];
-    }
-    return w * 32 + (31 - __clz(m));
-}
+// ---- parse kernel: shared-memory layout (dynamic, ~94 KB: two CTAs per SM)
+constexpr int BRC_HALO = 512;                                   // bytes before the tile kept with it: a line may start there
+constexpr int BRC_TEXT_SMEM = BRC_HALO + (int)SEL_TILE + 64;    // + misalignment of the tile (< 16) + 20 bytes of over-read
+constexpr int BRC_POS_SLOTS = (BRC_MAX_LINES + 7) & ~7;
+constexpr size_t BRC_SMEM_BYTES = (size_t)BRC_TEXT_SMEM + 1000 * 8 + (size_t)BRC_POS_SLOTS * 2 + 32 * 4 + 16;
+constexpr int BRC_NO_START = -(1 << 30);
+constexpr u64 BRC_MIX = 0xd6e8feb86659fd93ull;
 
-// Bytes [0, 16) at `p` (any alignment) as two little-endian 64-bit words, zero from byte `len` on.  The text is read
-// through ALIGNED 32-bit loads — five words cover 16 bytes at any alignment, neighbours are funnel-shifted — and never
-// past the word that holds the buffer's last byte.
-__device__ __forceinline__ void load16(const unsigned char* p, int len, const unsigned char* text_end, u64& lo, u64& hi) {
-    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-    const u32* aw = reinterpret_cast<const u32*>(a & ~(uintptr_t)3);
-    const u32 sh = (u32)(a & 3) * 8;
-    u32 a0, a1, a2, a3, a4;
-    if (p + 24 <= text_end) {  // one bounds test for all five
-        a0 = __ldg(aw), a1 = __ldg(aw + 1), a2 = __ldg(aw + 2), a3 = __ldg(aw + 3), a4 = __ldg(aw + 4);
-    } else {
-        const u32* we = reinterpret_cast<const u32*>((reinterpret_cast<uintptr_t>(text_end) + 3) & ~(uintptr_t)3);
-        a0 = __ldg(aw);
-        a1 = aw + 1 < we ? __ldg(aw + 1) : 0u, a2 = aw + 2 < we ? __ldg(aw + 2) : 0u;
-        a3 = aw + 3 < we ? __ldg(aw + 3) : 0u, a4 = aw + 4 < we ? __ldg(aw + 4) : 0u;
-    }
+// Bytes [bo, bo + 16) of the staged text (any alignment) as two little-endian 64-bit words, zero from byte `len` on:
+// five aligned 32-bit shared-memory loads, neighbours funnel-shifted.
+__device__ __forceinline__ void load16(const u32* __restrict__ s_w, int bo, int len, u64& lo, u64& hi) {
+    const int wi = bo >> 2;
+    const u32 sh = (u32)(bo & 3) * 8;
+    const u32 a0 = s_w[wi], a1 = s_w[wi + 1], a2 = s_w[wi + 2], a3 = s_w[wi + 3], a4 = s_w[wi + 4];
     lo = (u64)__funnelshift_r(a0, a1, sh) | ((u64)__funnelshift_r(a1, a2, sh) << 32);
     hi = (u64)__funnelshift_r(a2, a3, sh) | ((u64)__funnelshift_r(a3, a4, sh) << 32);
     if (len < 8) lo &= (1ull << (8 * len)) - 1ull;
     if (len < 16) hi = len <= 8 ? 0ull : hi & ((1ull << (8 * (len - 8))) - 1ull);
 }
-constexpr u64 BRC_MIX = 0xd6e8feb86659fd93ull;
 
-// One CTA per 65536-byte tile.  The tile's newline positions are expanded from the mask words into shared memory, then
-// LINE i of the tile goes to thread i mod 512: neighbouring lanes parse neighbouring lines, so a warp's text loads fall
-// in ~5 consecutive 128-byte lines (L1 serves the re-reads) and its 16 bytes of output per row are coalesced stores.
 __global__ void __launch_bounds__(256) brc_init_kernel(BrcSlot* __restrict__ tab, BrcCtl* __restrict__ ctl) {
     const u64 i = (u64)blockIdx.x * 256 + threadIdx.x;
     if (i < BRC_SLOTS) *reinterpret_cast<uint4*>(&tab[i]) = make_uint4(0u, 0u, 0xffffffffu, 0xffffffffu);  // {hash 0, idlen UNSET}
@@ -181,19 +170,27 @@ __global__ void __launch_bounds__(256) brc_init_kernel(BrcSlot* __restrict__ tab
     }
 }
 
-// 3 CTAs/SM (40 registers); a 4-CTA build (32 registers, small spills) measured slower: 1.94 vs 1.83 ms at 1e8 rows
-__global__ void __launch_bounds__(BRC_THREADS, 3) brc_parse_kernel(const unsigned char* __restrict__ text, i64 n,
-                                                                    const u32* __restrict__ masks, i64 nwords,
-                                                                    const unsigned long long* __restrict__ offs,
-                                                                    BrcSlot* __restrict__ tab, BrcCtl* __restrict__ ctl,
-                                                                    i64* __restrict__ id_out, double* __restrict__ temp_out,
-                                                                    u32* __restrict__ dict_names, int* __restrict__ dict_len,
-                                                                    i64 dict_capacity) {
-    __shared__ unsigned short s_pos[BRC_MAX_LINES];
-    __shared__ u32 s_wcnt[BRC_THREADS / 32];
-    __shared__ i64 s_start0;
-    __shared__ double s_tenth[1000];  // tenths -> tenths / 10.0, correctly rounded (one LDS instead of a division per row)
-    constexpr int WPT = SEL_TILE_WORDS / BRC_THREADS;
+// One CTA per 65536-byte tile.  The tile (plus a 512-byte halo in front, for the line that straddles the tile edge) is
+// staged in shared memory with coalesced 128-bit loads, the tile's newline positions are expanded from the mask words
+// into a second shared array, then LINE i of the tile goes to thread i mod T: all byte work is 32-bit-addressed shared
+// memory traffic (neighbouring lanes parse neighbouring lines: few bank conflicts) and the 16 bytes of output per row
+// are coalesced stores.
+template <int T, int MIN_CTAS>
+__global__ void __launch_bounds__(T, MIN_CTAS) brc_parse_kernel(const unsigned char* __restrict__ text, i64 n,
+                                                                const u32* __restrict__ masks, i64 nwords,
+                                                                const unsigned long long* __restrict__ offs,
+                                                                BrcSlot* __restrict__ tab, BrcCtl* __restrict__ ctl,
+                                                                i64* __restrict__ id_out, double* __restrict__ temp_out,
+                                                                u32* __restrict__ dict_names, int* __restrict__ dict_len,
+                                                                i64 dict_capacity) {
+    extern __shared__ uint4 brc_smem[];
+    unsigned char* s_text = reinterpret_cast<unsigned char*>(brc_smem);
+    const u32* s_w = reinterpret_cast<const u32*>(brc_smem);
+    double* s_tenth = reinterpret_cast<double*>(s_text + BRC_TEXT_SMEM);  // tenths -> tenths / 10.0, correctly rounded
+    unsigned short* s_pos = reinterpret_cast<unsigned short*>(s_tenth + 1000);
+    u32* s_wcnt = reinterpret_cast<u32*>(s_pos + BRC_POS_SLOTS);
+    int* s_start0 = reinterpret_cast<int*>(s_wcnt + 32);
+    constexpr int WPT = (SEL_TILE_WORDS + T - 1) / T;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const i64 tile = blockIdx.x;
     const unsigned long long base = offs[tile];
@@ -204,12 +201,45 @@ __global__ void __launch_bounds__(BRC_THREADS, 3) brc_parse_kernel(const unsigne
         return;
     }
     const i64 byte0 = tile * SEL_TILE;
-    if (tid == 0) s_start0 = prev_newline(masks, byte0) + 1;  // start of the line that ends first in this tile
-    for (int t = tid; t < 1000; t += BRC_THREADS) s_tenth[t] = (double)t / 10.0;
-    const i64 w0 = tile * SEL_TILE_WORDS + (i64)tid * WPT;
+    // ---- stage the text: shared byte j <- the byte at address g0 + j, g0 = (tile start - halo) rounded down to 16
+    const uintptr_t tile_addr = reinterpret_cast<uintptr_t>(text) + (uintptr_t)byte0;
+    const uintptr_t g0 = (tile_addr - BRC_HALO) & ~(uintptr_t)15;
+    const int so = (int)(tile_addr - g0);  // shared offset of the tile's byte 0: halo + misalignment
+    {
+        const uintptr_t lo_b = reinterpret_cast<uintptr_t>(text) & ~(uintptr_t)15;
+        const uintptr_t hi_b = (reinterpret_cast<uintptr_t>(text) + (uintptr_t)n + 15) & ~(uintptr_t)15;
+#pragma unroll 4
+        for (int c = tid; c < BRC_TEXT_SMEM / 16; c += T) {
+            const uintptr_t ga = g0 + (uintptr_t)c * 16;
+            if (ga >= lo_b && ga < hi_b) brc_smem[c] = __ldcs(reinterpret_cast<const uint4*>(ga));
+        }
+    }
+    if (tid == 0) {  // start of the line that ends first in this tile, relative to the tile: walk the mask words back
+        int rel = BRC_NO_START;
+        i64 w = byte0 >> 5;
+        for (int back = 0; back <= BRC_HALO / 32; back++) {
+            if (w == 0) {
+                rel = (int)(0 - byte0);
+                break;
+            }
+            const u32 m = masks[--w];
+            if (m) {
+                rel = (int)(w * 32 + (31 - __clz(m)) + 1 - byte0);
+                break;
+            }
+        }
+        if (rel < -BRC_HALO) rel = BRC_NO_START;
+        *s_start0 = rel;
+    }
+    for (int t = tid; t < 1000; t += T) s_tenth[t] = (double)t / 10.0;
+    // ---- newline positions of the tile, ascending
+    const int lw0 = tid * WPT;
     u32 m[WPT];
 #pragma unroll
-    for (int j = 0; j < WPT; j++) m[j] = (w0 + j < nwords) ? masks[w0 + j] : 0u;
+    for (int j = 0; j < WPT; j++) {
+        const i64 gw = tile * SEL_TILE_WORDS + lw0 + j;
+        m[j] = (lw0 + j < SEL_TILE_WORDS && gw < nwords) ? masks[gw] : 0u;
+    }
     u32 cnt = 0;
 #pragma unroll
     for (int j = 0; j < WPT; j++) cnt += __popc(m[j]);
@@ -223,7 +253,7 @@ __global__ void __launch_bounds__(BRC_THREADS, 3) brc_parse_kernel(const unsigne
     __syncthreads();
     u32 k = inc - cnt;
 #pragma unroll
-    for (int w = 0; w < BRC_THREADS / 32; w++)
+    for (int w = 0; w < T / 32; w++)
         if (w < warp) k += s_wcnt[w];
 #pragma unroll
     for (int j = 0; j < WPT; j++) {
@@ -231,22 +261,30 @@ __global__ void __launch_bounds__(BRC_THREADS, 3) brc_parse_kernel(const unsigne
         while (mm) {
             const int b = __ffs(mm) - 1;
             mm &= mm - 1;
-            s_pos[k++] = (unsigned short)((tid * WPT + j) * 32 + b);
+            s_pos[k++] = (unsigned short)((lw0 + j) * 32 + b);
         }
     }
     __syncthreads();
-    const unsigned char* text_end = text + n;
 #pragma unroll 1
-    for (u32 i = tid; i < nlines; i += BRC_THREADS) {
-        const i64 p = byte0 + s_pos[i];                              // this line's '\n'
-        const i64 start = i ? byte0 + s_pos[i - 1] + 1 : s_start0;
+    for (u32 i = tid; i < nlines; i += T) {
+        const int pe = s_pos[i];  // this line's '\n'
+        const int st = i ? (int)s_pos[i - 1] + 1 : *s_start0;
+        if (st == BRC_NO_START) {  // longer than the halo: no name of <= 255 bytes fits
+            ctl->err = 2;
+            continue;
+        }
         // ---- measurement, backwards from the newline: [-]d[d].d
-        if (p - start < 5) {  // shortest line: "a;0.0"
+        if (pe - st < 5) {  // shortest line: "a;0.0"
             ctl->err = 1;
             continue;
         }
-        const int f = __ldg(text + p - 1) - '0', dot = __ldg(text + p - 2), d1 = __ldg(text + p - 3) - '0';
-        const int c4 = __ldg(text + p - 4), c5 = __ldg(text + p - 5), c6 = p - 6 >= start ? __ldg(text + p - 6) : 0;
+        // the eight bytes before the newline from three aligned words (every shared load of a warp costs ~4 wavefronts:
+        // 32 lines span ~550 bytes, four words per bank)
+        const int qb = so + pe - 8;  // >= 0: the halo precedes the tile
+        const u32 q0 = s_w[qb >> 2], q1 = s_w[(qb >> 2) + 1], q2 = s_w[(qb >> 2) + 2];
+        const u32 tail_lo = __funnelshift_r(q0, q1, (u32)(qb & 3) * 8), tail_hi = __funnelshift_r(q1, q2, (u32)(qb & 3) * 8);
+        const int f = (int)(tail_hi >> 24) - '0', dot = (int)((tail_hi >> 16) & 255u), d1 = (int)((tail_hi >> 8) & 255u) - '0';
+        const int c4 = (int)(tail_hi & 255u), c5 = (int)(tail_lo >> 24), c6 = pe - 6 >= st ? (int)((tail_lo >> 16) & 255u) : 0;
         int d2 = 0, back = 4;  // `back`: distance from the newline to the ';'
         int c = c4;
         if (c >= '0' && c <= '9') {
@@ -260,28 +298,27 @@ __global__ void __launch_bounds__(BRC_THREADS, 3) brc_parse_kernel(const unsigne
             back++;
             c = back == 5 ? c5 : c6;
         }
-        const int len = (int)(p - back - start);
+        const int len = pe - back - st;
         if ((unsigned)f > 9u || (unsigned)d1 > 9u || dot != '.' || c != ';' || len <= 0) {
             ctl->err = 1;
             continue;
         }
-        const int tenths = (d2 * 10 + d1) * 10 + f;
-        const double v = s_tenth[tenths];  // correctly rounded quotient of two exact integers == float("d.d")
+        const double v = s_tenth[(d2 * 10 + d1) * 10 + f];  // correctly rounded quotient of two exact integers == float("d.d")
         temp_out[base + i] = neg ? -v : v;
         if (len > BRC_NAME_BYTES - 1) {
             ctl->err = 2;
             continue;
         }
-        // ---- station: the first 16 bytes travel in two registers, the hash takes four bytes at a time beyond them
-        const unsigned char* name = text + start;
+        // ---- station: the first 16 bytes travel in two registers, the hash takes 16 bytes at a time beyond them
+        const int nb = so + st;  // shared byte offset of the name
         u64 n0, n1;
-        load16(name, len, text_end, n0, n1);
+        load16(s_w, nb, len, n0, n1);
         u64 h = 0x9e3779b97f4a7c15ull ^ (u64)len;
         h = (h ^ n0) * BRC_MIX;
         h = (h ^ (h >> 32) ^ n1) * BRC_MIX;
-        for (int c = 16; c < len; c += 16) {  // rare for station names
+        for (int cb = 16; cb < len; cb += 16) {  // rare for station names
             u64 lo, hi;
-            load16(name + c, len - c, text_end, lo, hi);
+            load16(s_w, nb + cb, len - cb, lo, hi);
             h = (h ^ (h >> 32) ^ lo) * BRC_MIX;
             h = (h ^ (h >> 32) ^ hi) * BRC_MIX;
         }
@@ -289,9 +326,9 @@ __global__ void __launch_bounds__(BRC_THREADS, 3) brc_parse_kernel(const unsigne
         h *= BRC_MIX;
         h ^= h >> 29;
         if (h == 0) h = 1;  // 0 marks a free slot
-        u64 slot = h >> (64 - BRC_LOG2_SLOTS);
+        u32 slot = (u32)(h >> (64 - BRC_LOG2_SLOTS));
         u64 id = BRC_UNSET;
-        for (u64 probe = 0; probe < BRC_SLOTS && id == BRC_UNSET; probe++) {
+        for (u32 probe = 0; probe < (u32)BRC_SLOTS && id == BRC_UNSET; probe++) {
             Slot4 sv = ld_slot(&tab[slot]);
             if (sv.hash == 0) {
                 sv.hash = atomicCAS((unsigned long long*)&tab[slot].hash, 0ull, (unsigned long long)h);
@@ -301,10 +338,10 @@ __global__ void __launch_bounds__(BRC_THREADS, 3) brc_parse_kernel(const unsigne
                     st_relaxed_u64(&tab[slot].n1, n1);
                     if ((i64)nid < dict_capacity) {
                         uint4* row = reinterpret_cast<uint4*>(dict_names + nid * BRC_NAME_WORDS);
-                        for (int c = 0; c < len; c += 16) {  // zero-filled to the next multiple of 16 bytes
+                        for (int cb = 0; cb < len; cb += 16) {  // zero-filled to the next multiple of 16 bytes
                             u64 lo, hi;
-                            load16(name + c, len - c, text_end, lo, hi);
-                            __stcg(row + (c >> 4), make_uint4((u32)lo, (u32)(lo >> 32), (u32)hi, (u32)(hi >> 32)));
+                            load16(s_w, nb + cb, len - cb, lo, hi);
+                            __stcg(row + (cb >> 4), make_uint4((u32)lo, (u32)(lo >> 32), (u32)hi, (u32)(hi >> 32)));
                         }
                         dict_len[nid] = len;
                     } else {
@@ -334,21 +371,38 @@ __global__ void __launch_bounds__(BRC_THREADS, 3) brc_parse_kernel(const unsigne
                         // no fence on this side: the row's address is computed from the id just read, the loads go to
                         // L2 (the point of coherence) and the writer fenced between the row and the id
                         const uint4* row = reinterpret_cast<const uint4*>(dict_names + (sv.idlen >> 8) * BRC_NAME_WORDS);
-                        for (int c = 16; c < len; c += 16) {
-                            const uint4 r = __ldcg(row + (c >> 4));
+                        for (int cb = 16; cb < len; cb += 16) {
+                            const uint4 r = __ldcg(row + (cb >> 4));
                             u64 lo, hi;
-                            load16(name + c, len - c, text_end, lo, hi);
+                            load16(s_w, nb + cb, len - cb, lo, hi);
                             diff |= (lo ^ ((u64)r.x | ((u64)r.y << 32))) | (hi ^ ((u64)r.z | ((u64)r.w << 32)));
                         }
                     }
                     if (diff == 0) id = sv.idlen >> 8;
                 }
             }
-            slot = (slot + 1) & (BRC_SLOTS - 1);
+            slot = (slot + 1) & (u32)(BRC_SLOTS - 1);
         }
         if (id == BRC_UNSET && ctl->err == 0) ctl->err = 2;
         id_out[base + i] = (i64)id;
     }
+}
+
+template <int T, int MIN_CTAS>
+static cudaError_t launch_parse(i64 ntiles, cudaStream_t st, const unsigned char* text, i64 n, const u32* masks, i64 nwords,
+                                const unsigned long long* offs, BrcSlot* tab, BrcCtl* ctl, i64* id_out, double* temp_out,
+                                u32* dict_names, int* dict_len, i64 dict_capacity) {
+    static bool opted[64] = {};
+    const int dev = current_device();
+    if (dev >= 0 && dev < 64 && !opted[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(brc_parse_kernel<T, MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)BRC_SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        opted[dev] = true;
+    }
+    brc_parse_kernel<T, MIN_CTAS><<<(unsigned)ntiles, T, BRC_SMEM_BYTES, st>>>(text, n, masks, nwords, offs, tab, ctl, id_out,
+                                                                                temp_out, dict_names, dict_len, dict_capacity);
+    return cudaGetLastError();
 }
 
 }  // namespace kgb
@@ -406,10 +460,18 @@ extern "C" int kgb_brc_parse(const uint8_t* text, int64_t n_bytes, int64_t rows,
     BrcWs w = carve_brc(workspace, n_bytes);
     brc_init_kernel<<<(unsigned)(BRC_SLOTS / 256), 256, 0, st>>>(w.tab, w.ctl);
     const i64 ntiles = (i64)select_tiles(n_bytes);
-    brc_parse_kernel<<<(unsigned)ntiles, BRC_THREADS, 0, st>>>(text, n_bytes, w.masks, (i64)select_mask_words(n_bytes),
-                                                             w.tilecnt, w.tab, w.ctl, (i64*)id_out, temp_out,
-                                                             (u32*)dict_names_out, dict_len_out, dict_capacity);
-    KGB_CUDA_CHECK(cudaGetLastError());
+    // CTA size, two CTAs per SM: 512 -> 1.70 ms, 768 -> 1.63 ms, 1024 (32 registers, spills) -> 1.80 ms at 1e8 rows
+    static const int threads = getenv("KGB200_BRC_THREADS") ? atoi(getenv("KGB200_BRC_THREADS")) : 768;
+    const i64 nwords = (i64)select_mask_words(n_bytes);
+    if (threads == 768)
+        KGB_CUDA_CHECK((launch_parse<768, 2>(ntiles, st, text, n_bytes, w.masks, nwords, w.tilecnt, w.tab, w.ctl, (i64*)id_out,
+                                             temp_out, (u32*)dict_names_out, dict_len_out, dict_capacity)));
+    else if (threads == 1024)
+        KGB_CUDA_CHECK((launch_parse<1024, 2>(ntiles, st, text, n_bytes, w.masks, nwords, w.tilecnt, w.tab, w.ctl, (i64*)id_out,
+                                              temp_out, (u32*)dict_names_out, dict_len_out, dict_capacity)));
+    else
+        KGB_CUDA_CHECK((launch_parse<512, 2>(ntiles, st, text, n_bytes, w.masks, nwords, w.tilecnt, w.tab, w.ctl, (i64*)id_out,
+                                             temp_out, (u32*)dict_names_out, dict_len_out, dict_capacity)));
     BrcCtl h;
     KGB_CUDA_CHECK(cudaMemcpyAsync(&h, w.ctl, sizeof(BrcCtl), cudaMemcpyDeviceToHost, st));
     KGB_CUDA_CHECK(cudaStreamSynchronize(st));
