@@ -117,6 +117,68 @@ def aggregate(text, device=None):
             mx.to_numpy()[order], ctn)
 
 
+def chunk_bounds(data, parts):
+    """Line-aligned byte ranges of `data` (bytes-like), one per part: the chunking of examples/1brc/par.py:14-49
+    (`get_file_chunks`: a chunk end falls back to the previous line start; an empty chunk grows to the next line end)
+    restated for a buffer.  -> [(start, end)] covering the buffer; parts with nothing left are (n, n)."""
+    mv = memoryview(data).cast("B") if not isinstance(data, (bytes, bytearray)) else data
+    n = len(mv)
+    size = max(1, n // max(int(parts), 1))
+    out, start = [], 0
+    for r in range(int(parts)):
+        if start >= n:
+            out.append((n, n))
+            continue
+        end = n if r == parts - 1 else min(n, start + size)
+        while end > start and end < n and mv[end - 1] != 10:
+            end -= 1
+        if end == start:  # one line longer than the chunk: take it whole
+            nl = bytes(mv[start:]).find(b"\n")
+            end = n if nl < 0 else start + nl + 1
+        out.append((start, end))
+        start = end
+    return out
+
+
+def sharded_aggregate(text_chunk, device=None):
+    """`aggregate` over a file split across the ranks of torch.distributed (one line-aligned chunk per rank, as
+    par.py's worker processes get theirs): every rank parses and aggregates its own chunk on its GPU, then the
+    D-entry per-station tables — not the rows — are exchanged and merged by station NAME in rank order with the
+    worker's rule (worker.kg:4 `merge`: min&, max|, sum+, count+).  Every rank returns the full result."""
+    import torch.distributed as td
+    device = torch.device(device) if device is not None else ops.default_device()
+    ids, temps, names = _parse_arrival(text_chunk, device)
+    raw = names[0]
+    if raw:
+        mn, mx, sm, ct = ops.groupagg(DeviceArray(ids), DeviceArray(temps), len(raw))
+        mine = (raw, mn.to_numpy(), mx.to_numpy(), sm.to_numpy(), ct.to_numpy())
+    else:
+        mine = ([], np.zeros(0), np.zeros(0), np.zeros(0), np.zeros(0, dtype=np.int64))
+    if td.is_available() and td.is_initialized() and td.get_world_size() > 1:
+        parts = [None] * td.get_world_size()
+        td.all_gather_object(parts, mine)
+    else:
+        parts = [mine]
+    index, cols = {}, ([], [], [], [])
+    for rnames, rmn, rmx, rsm, rct in parts:  # fixed rank order: identical sums on every rank and every run
+        for j, s in enumerate(rnames):
+            k = index.get(s)
+            if k is None:
+                index[s] = len(cols[0])
+                for c, v in zip(cols, (rmn[j], rmx[j], rsm[j], rct[j])):
+                    c.append(v)
+            else:
+                cols[0][k] = min(cols[0][k], rmn[j])
+                cols[1][k] = max(cols[1][k], rmx[j])
+                cols[2][k] = cols[2][k] + rsm[j]
+                cols[3][k] = cols[3][k] + rct[j]
+    order = sorted(index, key=lambda b: b)
+    sel = np.asarray([index[s] for s in order], dtype=np.int64)
+    mn, mx, sm = (np.asarray(c, dtype=np.float64)[sel] if len(sel) else np.zeros(0) for c in cols[:3])
+    ct = np.asarray(cols[3], dtype=np.int64)[sel] if len(sel) else np.zeros(0, dtype=np.int64)
+    return [s.decode("utf-8") for s in order], mn, sm / np.maximum(ct, 1), mx, ct
+
+
 def report(text, device=None):
     """{name: 'min/mean/max'} with one decimal each (par.kg:5 `result`)."""
     names, mn, mean, mx, _ = aggregate(text, device)

@@ -54,6 +54,20 @@ for n in (1000, 1_000_003, 40_000_001):
             np.allclose(sm, rsm, rtol=1e-12, atol=1e-9))
     print(f"rank {rank}/{world} n={n}: {'ok' if good else 'MISMATCH'}", flush=True)
     ok &= good
+# 1brc ingest: the text split into line-aligned chunks, one per rank; per-station tables merged by name
+from klongpy_b200 import ingest  # noqa: E402
+srng = np.random.default_rng(77)
+snames = sorted({"".join(srng.choice(list("abcdefghijklmnopqrstuvwxyz éü'"), int(srng.integers(1, 30)))).strip() or "q" for _ in range(3000)})
+rows = [f"{snames[j]};{t / 10:.1f}" for j, t in zip(srng.integers(0, len(snames), 400_000), srng.integers(-999, 1000, 400_000))]
+text = ("\n".join(rows) + "\n").encode("utf-8")
+s0, e0 = ingest.chunk_bounds(text, world)[rank]
+gn, gmn, gmean, gmx, gct = ingest.sharded_aggregate(text[s0:e0], device=f"cuda:{local}")
+rn, ri, rt = O.parse_1brc(text)
+rmn, rmx, rsm, rct = O.grouped_stats(ri, rt, len(rn))
+good = gn == rn and np.array_equal(gmn, rmn) and np.array_equal(gmx, rmx) and np.array_equal(gct, rct) and \
+    np.allclose(gmean, rsm / rct, rtol=1e-12, atol=1e-12)
+print(f"rank {rank}/{world} ingest 400k rows / {len(rn)} stations: {'ok' if good else 'MISMATCH'}", flush=True)
+ok &= good
 flag = torch.tensor([1 if ok else 0], device=f"cuda:{local}")
 td.all_reduce(flag, op=td.ReduceOp.MIN)
 td.barrier()

@@ -80,6 +80,22 @@ def _worker(rank, world, port, q):
         assert np.allclose(gu, 2 * y[lo:hi] * x[lo:hi] ** 2, rtol=1e-12), rank   # a sharded vector's gradient stays sharded
         lv = dist.sharded_loss_sum([ops.OP_ARG, 0, ops.OPC["square"]], [X]).item()
         assert lv == np.add.reduce(x * x) or abs(lv - np.sum(x * x)) <= 1e-12 * np.sum(x * x)
+        # 1brc ingest over a file split into line-aligned chunks, one per rank; per-station tables merged by name
+        from klongpy_b200 import ingest
+        srng = np.random.default_rng(77)
+        snames = ["Abha", "Zürich", "St. John's", "a", "Ab", "x" * 40, "Ürümqi"] + [f"s{j}" for j in range(50)]
+        rows = [f"{snames[j]};{t / 10:.1f}" for j, t in zip(srng.integers(0, len(snames), 4000), srng.integers(-999, 1000, 4000))]
+        rows[:3] = ["only-in-first-chunk;1.0"] * 3
+        text = ("\n".join(rows) + "\n").encode("utf-8")
+        bounds = ingest.chunk_bounds(text, world)
+        assert bounds[0][0] == 0 and bounds[-1][1] == len(text) and all(a[1] == b[0] for a, b in zip(bounds, bounds[1:]))
+        assert all(e == s_ or text[e - 1:e] == b"\n" for s_, e in bounds)
+        s0, e0 = bounds[rank]
+        gn, gmn, gmean, gmx, gct = ingest.sharded_aggregate(text[s0:e0], device=dev)
+        rn, ri, rt = O.parse_1brc(text)
+        rmn, rmx, rsm, rct = O.grouped_stats(ri, rt, len(rn))
+        assert gn == rn and np.array_equal(gmn, rmn) and np.array_equal(gmx, rmx) and np.array_equal(gct, rct), rank
+        assert np.allclose(gmean, rsm / rct, rtol=1e-12, atol=1e-12), rank
         td.barrier()
         td.destroy_process_group()
         q.put((rank, "ok"))
