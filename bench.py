@@ -538,6 +538,16 @@ def primitive_table(be, ops, dist, time_kernel, dev, peak, world, rank):
         out["ingest_1brc_aggregate_1e8"] = prim_row(rows, time_kernel(lambda: ingest.aggregate(text), 3), bpr, peak,
                                                     note="text -> min/mean/max per station, names ascending (examples/1brc end to end)")
         del text
+        # the same file shape at config 4's row count: 1e9 rows, 17 GB of text (the dictionary work on the host is per
+        # station, not per row, so the API-level number converges to the device number)
+        reps = 1000
+        text = torch.from_numpy(np.frombuffer(block, dtype=np.uint8).copy()).to(dev).repeat(reps)
+        rows = 1_000_000 * reps
+        ms_kernels = time_kernel(lambda: ingest._parse_arrival(text, dev, fetch_names=False), 3)
+        out["ingest_1brc_parse_1e9"] = prim_row(rows, time_kernel(lambda: ingest.parse(text), 2), bpr, peak,
+                                                device_ms=ms_kernels, device_roofline_frac=bpr * rows / (ms_kernels * 1e-3) / 1e9 / peak)
+        out["ingest_1brc_aggregate_1e9"] = prim_row(rows, time_kernel(lambda: ingest.aggregate(text), 2), bpr, peak)
+        del text
     return out
 
 

@@ -65,3 +65,33 @@ def test_group_and_grouped_aggregation_1e9_properties(cuda_backend):
     assert bool((sk[1:] >= sk[:-1]).all())
     ties = sk[1:] == sk[:-1]
     assert bool((order.tensor[1:][ties] > order.tensor[:-1][ties]).all())
+
+
+@pytest.mark.gpu
+def test_ingest_1e9_rows_properties(cuda_backend):
+    """1e9 text rows (17 GB): a 1e6-row block whose parse is checked against the oracle, tiled 1000x on the device —
+    the parse of the whole buffer must be the block's parse repeated (ids index the same ascending name list), and the
+    aggregation must be the block's count x 1000, same min / max, sum x 1000 within 1e-12."""
+    import sys
+    import os
+    import numpy as np
+    import torch
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from bench import synthetic_1brc_block
+    from klongpy_b200 import ingest
+    from oracle import kg_oracle as O
+    dev = torch.device("cuda:0")
+    block, names, _, _ = synthetic_1brc_block(rows=1_000_000, n_names=10_000, seed=9)
+    rn, ri, rt = O.parse_1brc(block)
+    reps = 1000
+    text = torch.from_numpy(np.frombuffer(block, dtype=np.uint8).copy()).to(dev).repeat(reps)
+    ids, temps, got_names = ingest.parse(text)
+    assert got_names == rn and ids.size == reps * len(ri)
+    ref_i, ref_t = torch.from_numpy(ri).to(dev), torch.from_numpy(rt).to(dev)
+    assert bool((ids.tensor.view(reps, -1) == ref_i[None, :]).all())
+    assert bool((temps.tensor.view(reps, -1).view(torch.int64) == ref_t.view(torch.int64)[None, :]).all())   # bit-exact, signed zeros too
+    del ids, temps
+    an, mn, mean, mx, ct = ingest.aggregate(text)
+    rmn, rmx, rsm, rct = O.grouped_stats(ri, rt, len(rn))
+    assert an == rn and np.array_equal(ct, rct * reps) and np.array_equal(mn, rmn) and np.array_equal(mx, rmx)
+    assert np.allclose(mean, rsm / rct, rtol=1e-12, atol=1e-12)
