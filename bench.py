@@ -531,8 +531,14 @@ def primitive_table(be, ops, dist, time_kernel, dev, peak, world, rank):
         assert got[0].size == rows and got[2] == sorted(names, key=lambda s: s.encode())
         del got
         ms_kernels = time_kernel(lambda: ingest._parse_arrival(text, dev, fetch_names=False), 5)
+        # the reference's line loop (oracle.parse_1brc = par.py:57-88 restated) on this box's CPU, 200k-row sample
+        sample = block[:block.index(b"\n", len(block) // 5) + 1]
+        t0 = _time.perf_counter()
+        O.parse_1brc(sample)
+        cpu_rows_per_sec = sample.count(b"\n") / (_time.perf_counter() - t0)
         out["ingest_1brc_parse_1e8"] = prim_row(rows, time_kernel(lambda: ingest.parse(text), 3), bpr, peak,
                                                 device_ms=ms_kernels, device_roofline_frac=bpr * rows / (ms_kernels * 1e-3) / 1e9 / peak,
+                                                cpu_port_rows_per_sec=cpu_rows_per_sec,
                                                 note="ms: ingest.parse() incl. the host-side dictionary (10k names fetched, sorted, decoded) "
                                                      "and the id remap gather; device_ms: kgb_brc_scan + kgb_brc_parse only")
         out["ingest_1brc_aggregate_1e8"] = prim_row(rows, time_kernel(lambda: ingest.aggregate(text), 3), bpr, peak,

@@ -8,6 +8,7 @@ min / mean / max kernel and returns the report of par.kg:4-6 (stations in ascend
 ever touches the dictionary (one name per station), never the rows.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -147,18 +148,28 @@ def sharded_aggregate(text_chunk, device=None):
     worker's rule (worker.kg:4 `merge`: min&, max|, sum+, count+).  Every rank returns the full result."""
     import torch.distributed as td
     device = torch.device(device) if device is not None else ops.default_device()
-    ids, temps, names = _parse_arrival(text_chunk, device)
-    raw = names[0]
-    if raw:
-        mn, mx, sm, ct = ops.groupagg(DeviceArray(ids), DeviceArray(temps), len(raw))
-        mine = (raw, mn.to_numpy(), mx.to_numpy(), sm.to_numpy(), ct.to_numpy())
-    else:
-        mine = ([], np.zeros(0), np.zeros(0), np.zeros(0), np.zeros(0, dtype=np.int64))
+    mine = _local_tables(text_chunk, device)
     if td.is_available() and td.is_initialized() and td.get_world_size() > 1:
         parts = [None] * td.get_world_size()
         td.all_gather_object(parts, mine)
     else:
         parts = [mine]
+    return _merge_tables(parts)
+
+
+def _local_tables(text_chunk, device):
+    """One chunk of complete lines -> (names by arrival id (bytes), min, max, sum, count) as host arrays."""
+    ids, temps, names = _parse_arrival(text_chunk, device)
+    raw = names[0]
+    if not raw:
+        return ([], np.zeros(0), np.zeros(0), np.zeros(0), np.zeros(0, dtype=np.int64))
+    mn, mx, sm, ct = ops.groupagg(DeviceArray(ids), DeviceArray(temps), len(raw))
+    return (raw, mn.to_numpy(), mx.to_numpy(), sm.to_numpy(), ct.to_numpy())
+
+
+def _merge_tables(parts):
+    """Per-chunk station tables -> one, by station NAME, in the order given (worker.kg:4 `merge`: min&, max|, sum+,
+    count+).  -> (names ascending, min, mean, max, count)"""
     index, cols = {}, ([], [], [], [])
     for rnames, rmn, rmx, rsm, rct in parts:  # fixed rank order: identical sums on every rank and every run
         for j, s in enumerate(rnames):
@@ -177,6 +188,115 @@ def sharded_aggregate(text_chunk, device=None):
     mn, mx, sm = (np.asarray(c, dtype=np.float64)[sel] if len(sel) else np.zeros(0) for c in cols[:3])
     ct = np.asarray(cols[3], dtype=np.int64)[sel] if len(sel) else np.zeros(0, dtype=np.int64)
     return [s.decode("utf-8") for s in order], mn, sm / np.maximum(ct, 1), mx, ct
+
+
+_file_buffers = {}
+_readers = None
+
+
+def _read_parallel(fd, offset, mv, block=16 << 20, threads=16):
+    """Fill `mv` from the file at `offset` with positional reads issued from several threads (a single read() copies
+    out of the page cache at a few GB/s; pread releases the GIL, so the copies run side by side).  -> bytes read; short
+    only at the end of the file."""
+    global _readers
+    n = len(mv)
+    if n <= block:
+        return os.preadv(fd, [mv], offset)
+    if _readers is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _readers = ThreadPoolExecutor(max_workers=threads)
+
+    def one(lo):
+        done, want = 0, min(block, n - lo)
+        while done < want:
+            r = os.preadv(fd, [mv[lo + done:lo + want]], offset + lo + done)
+            if r <= 0:
+                break
+            done += r
+        return done
+    total = 0
+    for lo, got in zip(range(0, n, block), _readers.map(one, range(0, n, block))):
+        total += got
+        if got < min(block, n - lo):
+            break                                          # end of file inside this block: later blocks read nothing
+    return total
+
+
+def aggregate_file(path, device=None, chunk_bytes=256 << 20):
+    """examples/1brc end to end from a FILE: the measurements file is read in line-aligned chunks of about
+    `chunk_bytes` straight into pinned host memory, each chunk's host->device copy runs on its own stream while the
+    previous chunk is parsed and aggregated, and the per-chunk station tables are merged by name (the reference
+    splits the file the same way across worker processes, par.py:14-49, 92-104).  -> like `aggregate`."""
+    device = torch.device(device) if device is not None else ops.default_device()
+    cuda = device.type == "cuda"
+    chunk_bytes = max(int(chunk_bytes), 1 << 16)
+    cap = chunk_bytes + (1 << 16)                          # room for the carried partial line
+    key = (str(device), cap)
+    if key not in _file_buffers:                           # pinning 2 x 256 MB costs tens of milliseconds: keep them
+        _file_buffers.clear()
+        _file_buffers[key] = ([torch.empty(cap, dtype=torch.uint8, pin_memory=cuda) for _ in range(2)],
+                              [torch.empty(cap, dtype=torch.uint8, device=device) for _ in range(2)] if cuda else None)
+    host, devb = _file_buffers[key]
+    copy_stream = torch.cuda.Stream(device) if cuda else None
+    parts, pending, carry, k, pos = [], None, b"", 0, 0
+
+    def finish(p):
+        slot, m, ev = p
+        if cuda:
+            torch.cuda.current_stream(device).wait_event(ev)
+            parts.append(_local_tables(devb[slot][:m], device))
+        else:
+            parts.append(_local_tables(host[slot][:m].clone(), device))
+
+    with open(path, "rb", buffering=0) as f:
+        while True:
+            slot = k & 1
+            hv = host[slot].numpy()
+            c = len(carry)
+            if c > cap - chunk_bytes:
+                raise _lib.KgbError("aggregate_file: a line longer than 65536 bytes")
+            hv[:c] = np.frombuffer(carry, dtype=np.uint8)
+            got = _read_parallel(f.fileno(), pos, memoryview(hv)[c:c + chunk_bytes])
+            pos += got
+            m = c + (got or 0)
+            if m == 0:
+                break
+            eof = not got
+            if eof:                                        # the last line may lack its newline
+                if hv[m - 1] != 10:
+                    hv[m] = 10
+                    m += 1
+                cut = m
+            else:
+                lo = max(0, m - (1 << 16))
+                nl = np.flatnonzero(hv[lo:m] == 10)
+                if nl.size:
+                    cut = lo + int(nl[-1]) + 1
+                elif got < chunk_bytes:
+                    cut = 0                                # a short read without a newline: keep it all for the next round
+                else:
+                    raise _lib.KgbError("aggregate_file: a line longer than 65536 bytes")
+            carry = bytes(hv[cut:m])
+            ev = None
+            if cuda:
+                with torch.cuda.stream(copy_stream):
+                    devb[slot][:cut].copy_(host[slot][:cut], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(copy_stream)
+            if pending is not None:
+                finish(pending)                            # parse chunk k-1 while chunk k is on the wire
+                if cuda:
+                    copy_stream.wait_stream(torch.cuda.current_stream(device))   # its buffers are free for chunk k+1
+            pending = (slot, cut, ev) if cut else None
+            k += 1
+            if eof:
+                break
+    if pending is not None:
+        finish(pending)
+    if not parts:
+        z = np.zeros(0)
+        return [], z, z, z, np.zeros(0, dtype=np.int64)
+    return _merge_tables(parts)
 
 
 def report(text, device=None):

@@ -1,4 +1,5 @@
 """Throughput of the 1brc ingest: a 1e6-row synthetic file tiled to ~1.4 GB on the device."""
+import os
 import sys
 import time
 import numpy as np
@@ -61,3 +62,20 @@ ms = timeit(lambda: ingest.parse(text))
 print(f"parse     rows={rows} bytes={n}: {ms:.2f} ms  {rows / ms / 1e6:.2f} Grows/s  {n / ms / 1e6:.0f} GB/s of text", flush=True)
 ms = timeit(lambda: ingest.aggregate(text))
 print(f"aggregate rows={rows}: {ms:.2f} ms  {rows / ms / 1e6:.2f} Grows/s", flush=True)
+# from a FILE: line-aligned chunks through pinned memory, H2D of chunk k+1 under the parse of chunk k
+import tempfile
+path = os.path.join(tempfile.gettempdir(), "kgb200_probe_measurements.txt")
+with open(path, "wb") as f:
+    for _ in range(reps):
+        f.write(block)
+fsize = os.path.getsize(path)
+for cb in (64 << 20, 256 << 20):
+    res = ingest.aggregate_file(path, chunk_bytes=cb)   # warm: page cache, pinned buffers
+    assert len(res[0]) == len(names) and int(res[4].sum()) == rows
+    t0 = time.perf_counter()
+    k = 3
+    for _ in range(k):
+        ingest.aggregate_file(path, chunk_bytes=cb)
+    s = (time.perf_counter() - t0) / k
+    print(f"aggregate_file {fsize / 1e9:.2f} GB, {cb >> 20} MB chunks: {s * 1e3:.0f} ms  {rows / s / 1e9:.2f} Grows/s  {fsize / s / 1e9:.1f} GB/s of file", flush=True)
+os.remove(path)

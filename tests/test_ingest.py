@@ -130,3 +130,46 @@ def test_gpu_ingest_alignment_long_names_tile_edges():
     with pytest.raises(_lib.KgbError):
         ingest.parse(("x" * 256 + ";1.0\n").encode(), device="cuda:0")
     assert ingest.parse(("x" * 255 + ";1.0\n").encode(), device="cuda:0")[2] == ["x" * 255]
+
+
+def _file_case(tmp_path, rows, n_names, tail_newline=True, seed=3):
+    rng = np.random.default_rng(seed)
+    text = _synthetic(rng, rows, n_names)
+    if not tail_newline:
+        text = text[:-1]
+    path = tmp_path / "measurements.txt"
+    path.write_bytes(text)
+    rn, ri, rt = O.parse_1brc(text)
+    return str(path), rn, O.grouped_stats(ri, rt, len(rn))
+
+
+def _check_file_result(res, rn, stats):
+    names, mn, mean, mx, ct = res
+    rmn, rmx, rsm, rct = stats
+    assert names == rn and np.array_equal(mn, rmn) and np.array_equal(mx, rmx) and np.array_equal(ct, rct)
+    assert np.allclose(mean, rsm / rct, rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("tail_newline", [True, False])
+def test_aggregate_file_on_cpu_double(tmp_path, tail_newline):
+    """File -> line-aligned chunks -> per-chunk tables merged by name: host logic on the CPU test double, chunks of
+    64 KB so the 25 k-row file takes several rounds and partial lines are carried across them."""
+    import fake_lib
+    dev = fake_lib.install()
+    from klongpy_b200 import ingest
+    path, rn, stats = _file_case(tmp_path, 25_000, 300, tail_newline)
+    _check_file_result(ingest.aggregate_file(path, device=dev, chunk_bytes=1 << 16), rn, stats)
+    empty = tmp_path / "empty.txt"
+    empty.write_bytes(b"")
+    assert ingest.aggregate_file(str(empty), device=dev)[0] == []
+    one = tmp_path / "one.txt"
+    one.write_bytes(b"a;1.0")
+    assert ingest.aggregate_file(str(one), device=dev)[0] == ["a"]
+
+
+@pytest.mark.gpu
+def test_gpu_aggregate_file(tmp_path):
+    from klongpy_b200 import ingest
+    path, rn, stats = _file_case(tmp_path, 400_000, 5_000, tail_newline=False, seed=8)
+    _check_file_result(ingest.aggregate_file(path, device="cuda:0", chunk_bytes=1 << 20), rn, stats)   # ~6 chunks
+    _check_file_result(ingest.aggregate_file(path, device="cuda:0"), rn, stats)                          # one chunk
