@@ -318,3 +318,50 @@ def report_1brc(mn, mx, sm, ct):
         if ct[s]:
             out[s] = f"{mn[s]:.1f}/{sm[s] / ct[s]:.1f}/{mx[s]:.1f}"
     return out
+
+
+# --------------------------------------------------------------------------------------------- tables
+# Restatement of the reference's columnar Table (klongpy/db/sys_fn_db.py:18-127; pandas underneath) as plain
+# NumPy row-matrix operations.  Pinned by tests/golden/golden_table.json, which tests/golden/make_table_golden.py
+# records from the reference's own Table class (the reference's tests/kgtests/db/*.kg scenarios + seeded tables).
+def table_index(rows, idx):
+    """`Table.set_index` (sys_fn_db.py:55-69): sort by the index columns (first is the major key; rows with equal
+    keys keep their order) and drop rows that repeat an earlier row in every column."""
+    rows = np.asarray(rows)
+    if rows.shape[0] == 0:
+        return rows
+    order = np.lexsort([rows[:, j] for j in reversed(list(idx))])
+    rows = rows[order]
+    _, first = np.unique(rows, axis=0, return_index=True)
+    return rows[np.sort(first)]
+
+
+def table_append(rows, buf):
+    """`Table.commit` without an index (sys_fn_db.py:107-109): buffered rows are appended in order."""
+    return np.concatenate([np.asarray(rows)] + [np.asarray(b).reshape(1, -1) for b in buf])
+
+
+def table_upsert(rows, buf, idx):
+    """`Table.commit` with an index (sys_fn_db.py:97-106): every existing row whose key appears in the buffer takes
+    the buffered row's values, buffered rows with new keys are appended, then everything is sorted by key again.
+    Several different buffered rows with the SAME existing key inside one commit are not pinned by the reference
+    (its `.loc` assignment needs unique labels); the restatement lets the last one win."""
+    rows = np.asarray(rows)
+    idx = list(idx)
+    buf = table_index(np.asarray(buf).reshape(-1, rows.shape[1]), idx)
+    last = {tuple(r[idx]): r for r in buf}
+    have = {tuple(r[idx]) for r in rows}
+    upd = np.array([last.get(tuple(r[idx]), r) for r in rows]).reshape(-1, rows.shape[1])
+    new = np.array([r for r in buf if tuple(r[idx]) not in have]).reshape(-1, rows.shape[1])
+    out = np.concatenate([upd, new.astype(upd.dtype)]) if len(new) else upd
+    return out[np.lexsort([out[:, j] for j in reversed(idx)])]
+
+
+def table_group_stats(k, v):
+    """`select k, min(v), avg(v), max(v), count(*) from T group by k order by k` — the grouped statistics of the db /
+    1brc examples (examples/1brc/worker.kg:3-5 computes the same per chunk): -> (keys, min, mean, max, count)."""
+    k = np.asarray(k)
+    v = np.asarray(v, dtype=np.float64)
+    keys, inv = np.unique(k, return_inverse=True)
+    mn, mx, sm, ct = grouped_stats(inv.astype(np.int64), v, len(keys))
+    return keys, mn, sm / ct, mx, ct

@@ -172,3 +172,50 @@ def test_bench_compiler_example_runs(interp):
     for e in exprs:
         got, ref = np.asarray(norm(kb(e), mod)), np.asarray(kn(e))
         assert got.shape == ref.shape and np.allclose(got, ref, rtol=1e-12, atol=0), e
+
+
+TABLE_PROGRAM = r'''
+.py("klongpy_b200.table")
+e::[]
+e::e,,"a",,[1 2 3]
+e::e,,"b",,[2 3 4]
+e::e,,"c",,[3 4 5]
+T::.table(e)
+'''
+
+
+def table_program_checks(klong, mod):
+    """The reference's tests/kgtests/db scenarios (test_create_multi_col_table, test_multi_col_insert_with_single_index,
+    test_rindex, test_table_via_dict_behavior) with `.py("klongpy_b200.table")` in place of `.py("klongpy.db")`; the rows
+    the reference reads back through `db("select * from T")` are read with `T.rows()` here (no SQL engine)."""
+    klong(TABLE_PROGRAM)
+    T = klong["T"]
+    assert list(klong(".schema(T)")) == ["a", "b", "c"]
+    assert T.rows().tolist() == [[1, 2, 3], [2, 3, 4], [3, 4, 5]]
+    klong(".insert(T;[4 5 6])")
+    klong(".insert(T;[4 5 6])")
+    assert T.rows().tolist() == [[1, 2, 3], [2, 3, 4], [3, 4, 5], [4, 5, 6], [4, 5, 6]]
+    assert list(klong('.index(T;["a"])')) == ["a"]
+    klong(".insert(T;[4 5 6])")
+    assert T.rows().tolist() == [[1, 2, 3], [2, 3, 4], [3, 4, 5], [4, 5, 6]]
+    klong(".insert(T;[4 6 7])")
+    assert T.rows().tolist() == [[1, 2, 3], [2, 3, 4], [3, 4, 5], [4, 6, 7]]
+    assert klong(".rindex(T)") == 1 and klong(".rindex(T)") == 0
+    klong(".insert(T;[[4 6 7] [9 9 9]])")
+    assert T.rows().tolist() == [[1, 2, 3], [2, 3, 4], [3, 4, 5], [4, 6, 7], [4, 6, 7], [9, 9, 9]]
+    klong('T,"d",,[1.5 2.5 3.5 4.5 5.5 6.5]')
+    assert list(klong(".schema(T)")) == ["a", "b", "c", "d"]
+    col = klong('T?"a"')                                    # a column is a device array: the verbs take it as is
+    assert isinstance(col, mod.DeviceArray) and col.to_numpy().tolist() == [1, 2, 3, 4, 4, 9]
+    assert klong('+/T?"d"') == 24.0
+    g = klong('=T?"a"')
+    assert [np.asarray(x.to_numpy() if isinstance(x, mod.DeviceArray) else x).tolist() for x in g] == [[0], [1], [2], [3, 4], [5]]
+    keys, mn, mean, mx, ct = klong('.gstats(T;"a";"d")')
+    assert keys.to_numpy().tolist() == [1, 2, 3, 4, 9] and ct.to_numpy().tolist() == [1, 1, 1, 2, 1]
+    assert mn.to_numpy().tolist() == [1.5, 2.5, 3.5, 4.5, 6.5] and mx.to_numpy().tolist() == [1.5, 2.5, 3.5, 5.5, 6.5]
+    assert mean.to_numpy().tolist() == [1.5, 2.5, 3.5, 5.0, 6.5]
+
+
+def test_table_program_through_interpreter(interp):
+    klong, _, mod = interp
+    table_program_checks(klong, mod)

@@ -95,3 +95,9 @@ def test_autograd_through_the_interpreter(interps):
     got = np.array([float(norm(v, mod)) for v in g])
     assert np.allclose(got, ref, rtol=1e-10), (got, ref)
     assert np.allclose(norm(gpu("{+/x^2}:>[1.0 2.0 3.0]"), mod), [2.0, 4.0, 6.0])
+
+
+def test_table_program_through_the_interpreter(interps):
+    from test_host_logic import table_program_checks
+    gpu, _, mod = interps
+    table_program_checks(gpu, mod)
