@@ -119,6 +119,26 @@ def run_reference(args):
         O.eval_ir(ir, {"_v0": x})
         O.eval_ir(sc, {"_v0": x})
 
+    kind, how = "port", "oracle/kg_oracle.eval_ir = numpy_backend.py:116-178"
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if os.path.isdir(os.path.join(ref_dir, "klongpy")):
+        # the UNMODIFIED reference, when its install (git-ignored baseline/_ref) travelled to this box:
+        # the same two expressions through its own interpreter, compiler and NumPy backend
+        try:
+            sys.path.insert(0, ref_dir)
+            from klongpy import KlongInterpreter
+            klong = KlongInterpreter(backend="numpy")
+            klong["x"] = x
+            assert float(klong("+/((x*2)+1)^2")) == float(O.eval_ir(ir, {"_v0": x}))
+
+            def step():  # noqa: F811
+                klong("+/((x*2)+1)^2")
+                klong("+\\x")
+
+            kind, how = "reference", "klongpy 0.7.0 from baseline/_ref: KlongInterpreter(backend='numpy') on '+/((x*2)+1)^2' and '+\\x'"
+        except Exception as ex:  # fall back to the port, say why
+            how += f"; baseline/_ref not usable: {type(ex).__name__}: {ex}"
+
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
@@ -132,8 +152,8 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "n_per_step": n, "note": "bounded sample of the 1e9-element workload; "
                    "NumPy executes these primitives single-threaded"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
-                         "sample": f"{n} float64 elements per step (oracle/kg_oracle.eval_ir = numpy_backend.py:116-178)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind,
+                         "sample": f"{n} float64 elements per step ({how})"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "host_cpus": os.cpu_count(),
     }
@@ -427,6 +447,14 @@ def primitive_table(be, ops, dist, time_kernel, dev, peak, world, rank):
     out["grouped_min_mean_max_10k_1e8"] = prim_row(
         n * world, over_ranks(time_kernel(lambda: dist.sharded_groupagg(keys_10k, temp, 10_000), 3)), 16, peak * world,
         n_gpus=world, rows_per_gpu=n)
+    if world == 1:
+        # the same rows as two columns of a DeviceTable; `.gstats` = key range in one two-output
+        # reduce (+8 B/row), the aggregation kernel, compaction of the live stations, mean = sum / count
+        from klongpy_b200.table import DeviceTable
+        tbl = DeviceTable({"station": keys_10k, "temp": temp})
+        out["table_gstats_10k_1e8"] = prim_row(n, time_kernel(lambda: tbl.group_stats("station", "temp"), 3), 24, peak,
+                                               note="DeviceTable.group_stats: select station, min, avg, max, count group by station")
+        del tbl
     del temp, a, b
     # config 4 at its full size: 1e9 synthetic rows PER GPU, 10k stations (16 GB of input per GPU)
     nb = 1_000_000_000

@@ -99,6 +99,17 @@ __device__ __forceinline__ u64 uniq_hash(u64 k) {
     return k;
 }
 
+// index into the per-CTA key cache.  The low word is only XOR-folded, so small dense integer keys (station ids, the
+// usual input of `?a`) map to DISTINCT entries — a mixing hash makes 10 k keys collide in 16 k entries for 46 % of
+// them and every collision is a miss that goes to the L2 table; the high word (all of the information of a float64
+// with a short mantissa) goes through one multiply.  The 64-bit finaliser above is now paid only by rows that miss.
+// A weak spot here costs hit rate, never correctness.
+__device__ __forceinline__ u32 uniq_cache_index(u64 k, int log2_entries) {
+    const u32 lo = (u32)k, hi = (u32)(k >> 32);
+    const u32 h = lo ^ (lo >> log2_entries) ^ (lo >> (2 * log2_entries)) ^ ((hi * 0x9E3779B1u) >> (32 - log2_entries));
+    return h & ((1u << log2_entries) - 1u);
+}
+
 template <typename T> __device__ __forceinline__ u64 uniq_bits(T v);
 template <> __device__ __forceinline__ u64 uniq_bits<u64>(u64 v) { return v; }
 template <> __device__ __forceinline__ u64 uniq_bits<u32>(u32 v) { return (u64)v; }
@@ -186,8 +197,20 @@ __global__ void __launch_bounds__(256) uniq_insert_kernel(const T* __restrict__ 
 // keys that share a cache line evict each other); with more keys than entries the pass degrades to the plain one.
 constexpr int UNIQ_CACHE_LOG2 = 14;
 constexpr int UNIQ_CACHE = 1 << UNIQ_CACHE_LOG2;
-constexpr int UNIQ_CT = 1024;
-constexpr int UNIQ_CU = 4;
+#ifndef KGB_UNIQ_BAR2
+#define KGB_UNIQ_BAR2 0   // 1 = keep the (redundant) barrier after the cache writes: measured 0.51 vs ... ms
+#endif
+#ifndef KGB_UNIQ_PF
+#define KGB_UNIQ_PF 1     // tiles prefetched into registers ahead of the one being looked up (1 or 2)
+#endif
+#ifndef KGB_UNIQ_CT
+#define KGB_UNIQ_CT 1024  // threads of the persistent CTA (tuning knob; 1024 caps a thread at 64 registers)
+#endif
+constexpr int UNIQ_CT = KGB_UNIQ_CT;
+#ifndef KGB_UNIQ_CU
+#define KGB_UNIQ_CU 4   // rows per thread and iteration (tuning knob)
+#endif
+constexpr int UNIQ_CU = KGB_UNIQ_CU;
 
 // the table protocol for one row (key k at position i), starting at `slot`: shared by both passes' slow paths
 __device__ __forceinline__ void uniq_probe(UniqSlot* __restrict__ tab, UniqCtl* __restrict__ ctl, u64 k, i64 i, u64 slot, u32& fresh,
@@ -231,26 +254,40 @@ constexpr size_t uniq_cached_smem() { return (size_t)UNIQ_CACHE * 8; }
 // not latency-bound, so the ring's extra shared-memory traffic only added work.
 template <typename T>
 __global__ void __launch_bounds__(UNIQ_CT, 1) uniq_insert_cached_kernel(const T* __restrict__ a, i64 n, UniqSlot* __restrict__ tab,
-                                                                        UniqCtl* __restrict__ ctl) {
+                                                                        UniqCtl* __restrict__ ctl, unsigned long long probe_limit) {
     extern __shared__ __align__(16) u64 s_cache[];
     __shared__ int s_special;  // this CTA has already reported the all-ones key at a smaller position
     constexpr int U = UNIQ_CU;
     const int tid = threadIdx.x;
     for (int c = tid; c < UNIQ_CACHE; c += UNIQ_CT) s_cache[c] = UNIQ_EMPTY;
     if (tid == 0) s_special = 0;
-    __syncthreads();
+    // the verdict on the cardinality probe (which ran just before, on the same stream) is taken here, not on the host:
+    // too many distinct keys among the probe's rows -> flag, every CTA leaves at once, the host runs the sort path
+    bool give_up = false;
+    if (tid == 0) {
+        give_up = *(volatile int*)&ctl->overflow != 0 || *(volatile unsigned long long*)&ctl->distinct > probe_limit;
+        if (give_up) ctl->overflow = 1;
+    }
+    if (__syncthreads_or(give_up)) return;
     const i64 tile = (i64)UNIQ_CT * U;
     const i64 stride = (i64)gridDim.x * tile;
     i64 base = (i64)blockIdx.x * tile;
     T cur[U], nxt[U];
+#if KGB_UNIQ_PF == 2
+    T nx1[U];  // two tiles in flight: one tile of 32 KB per SM does not cover HBM latency at full bandwidth
+#endif
 #pragma unroll
     for (int u = 0; u < U; u++) {
         const i64 j = base + u * UNIQ_CT + tid;
         cur[u] = a[j < n ? j : n - 1];
+#if KGB_UNIQ_PF == 2
+        const i64 j1 = j + stride;
+        nx1[u] = a[j1 < n ? j1 : n - 1];
+#endif
     }
     u32 fresh = 0;
     for (; base < n; base += stride) {
-        const i64 nb = base + stride;  // next tile's loads fly while this one is looked up
+        const i64 nb = base + KGB_UNIQ_PF * stride;  // later tiles' loads fly while this one is looked up
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const i64 j = nb + u * UNIQ_CT + tid;
@@ -261,13 +298,13 @@ __global__ void __launch_bounds__(UNIQ_CT, 1) uniq_insert_cached_kernel(const T*
         bool bail = tid == 0 ? *(volatile int*)&ctl->overflow != 0 : false;
         bool special = false;
         u32 miss = 0;
-        u64 hs[U];
+        u32 ci[U];
         // 1. the cache: shared memory only
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const i64 i = base + u * UNIQ_CT + tid;
             const u64 k = uniq_bits<T>(cur[u]);
-            hs[u] = uniq_hash(k);
+            ci[u] = uniq_cache_index(k, UNIQ_CACHE_LOG2);
             if (i >= n) continue;
             if (k == UNIQ_EMPTY) {
                 if (!s_special) {
@@ -276,26 +313,29 @@ __global__ void __launch_bounds__(UNIQ_CT, 1) uniq_insert_cached_kernel(const T*
                 }
                 continue;
             }
-            if (s_cache[(hs[u] >> 40) & (UNIQ_CACHE - 1)] != k) miss |= 1u << u;
+            if (s_cache[ci[u]] != k) miss |= 1u << u;
         }
         // 2. the misses: all table reads are issued before the first one is looked at
         ulonglong2 e[U];
+        u32 hs[U];
 #pragma unroll
         for (int u = 0; u < U; u++)
-            if (miss & (1u << u))
+            if (miss & (1u << u)) {
+                hs[u] = (u32)(uniq_hash(uniq_bits<T>(cur[u])) & (UNIQ_SLOTS - 1));
                 asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];"
                              : "=l"(e[u].x), "=l"(e[u].y)
-                             : "l"(&tab[hs[u] & (UNIQ_SLOTS - 1)])
+                             : "l"(&tab[hs[u]])
                              : "memory");
+            }
 #pragma unroll
         for (int u = 0; u < U; u++)
             if (miss & (1u << u)) {
                 const i64 i = base + u * UNIQ_CT + tid;
                 const u64 k = uniq_bits<T>(cur[u]);
                 if (e[u].x == k) {  // the common case: present; touch it only if this row comes earlier
-                    if ((u64)i < e[u].y) atomicMin((unsigned long long*)&tab[hs[u] & (UNIQ_SLOTS - 1)].first, (unsigned long long)i);
+                    if ((u64)i < e[u].y) atomicMin((unsigned long long*)&tab[hs[u]].first, (unsigned long long)i);
                 } else {
-                    uniq_probe(tab, ctl, k, i, hs[u] & (UNIQ_SLOTS - 1), fresh, bail);
+                    uniq_probe(tab, ctl, k, i, (u64)hs[u], fresh, bail);
                 }
             }
         fresh = __reduce_add_sync(0xffffffffu, fresh);
@@ -307,11 +347,23 @@ __global__ void __launch_bounds__(UNIQ_CT, 1) uniq_insert_cached_kernel(const T*
         // 3. remember what went to the table (visible to the NEXT iteration's lookups only)
 #pragma unroll
         for (int u = 0; u < U; u++)
-            if (miss & (1u << u)) s_cache[(hs[u] >> 40) & (UNIQ_CACHE - 1)] = uniq_bits<T>(cur[u]);
+            if (miss & (1u << u)) s_cache[ci[u]] = uniq_bits<T>(cur[u]);
         if (special) s_special = 1;
+        // no second barrier: a warp that runs ahead into the next iteration's lookups either sees one of these writes
+        // (made for an earlier tile, i.e. smaller positions: a valid hit) or misses and asks the table; its own writes
+        // wait behind the next barrier, which every warp reaches only after its lookups
+#if KGB_UNIQ_BAR2
         __syncthreads();
+#endif
 #pragma unroll
-        for (int u = 0; u < U; u++) cur[u] = nxt[u];
+        for (int u = 0; u < U; u++) {
+#if KGB_UNIQ_PF == 2
+            cur[u] = nx1[u];
+            nx1[u] = nxt[u];
+#else
+            cur[u] = nxt[u];
+#endif
+        }
     }
 }
 
@@ -338,6 +390,47 @@ __global__ void __launch_bounds__(256) uniq_collect_kernel(const UniqSlot* __res
         if (occ) first[b + __popc(m & ((1u << lane) - 1u))] = (i64)f;
     }
     (void)count_out;
+}
+
+// Up to UNIQ_SMALL first positions (the usual outcome of the hash path: 10 k stations) are put in order by RANKING
+// instead of the general radix sort (histogram + plan + eight pass launches + gather: ≈ 75 µs of dependent tiny
+// kernels for 10 k keys): the positions are distinct, so the rank of one is the number of smaller ones.  c x c
+// comparisons spread over the whole GPU (element i x a chunk of the others per thread, tiles broadcast from shared
+// memory) take a few µs; a second small kernel places position and value.  A one-CTA bitonic sort in shared memory
+// was tried first: 105 dependent stages for 16 k slots cost more than the radix sort (0.58 vs 0.50 ms end to end).
+constexpr int UNIQ_SMALL = 16384;
+constexpr int UNIQ_RT = 256;
+__global__ void __launch_bounds__(UNIQ_RT) uniq_rank_kernel(const i64* __restrict__ first, int c, int chunk, u32* __restrict__ rank) {
+    __shared__ __align__(16) u64 s_tile[UNIQ_RT];
+    const int i = blockIdx.x * UNIQ_RT + threadIdx.x;
+    const u64 mine = i < c ? (u64)first[i] : 0ull;
+    const int jb = blockIdx.y * chunk;
+    const int je = jb + chunk < c ? jb + chunk : c;
+    u32 cnt = 0;
+    for (int t = jb; t < je; t += UNIQ_RT) {
+        const int j = t + threadIdx.x;
+        s_tile[threadIdx.x] = j < je ? (u64)first[j] : ~0ull;  // padding is never smaller than a real position
+        __syncthreads();
+#pragma unroll 8
+        for (int q = 0; q < UNIQ_RT; q += 2) {
+            const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(&s_tile[q]);
+            cnt += (v.x < mine) + (v.y < mine);
+        }
+        __syncthreads();
+    }
+    if (i < c && cnt) atomicAdd(&rank[i], cnt);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) uniq_place_kernel(const T* __restrict__ a, const i64* __restrict__ first, const u32* __restrict__ rank,
+                                                          int c, i64* __restrict__ first_sorted_out, T* __restrict__ out) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < c) {
+        const i64 p = first[i];
+        const u32 r = rank[i];
+        first_sorted_out[r] = p;
+        out[r] = a[p];
+    }
 }
 
 }  // namespace kgb
@@ -455,11 +548,17 @@ extern "C" int kgb_unique_first(const void* a, int32_t dtype, int64_t n, void* o
         // if they alone bring in more than 300k distinct keys the table would overflow — go straight to the sort
         const i64 sample = n < (1ll << 19) ? n : (1ll << 19);
         insert(sample, n / sample);
-        KGB_CUDA_CHECK(cudaMemcpyAsync(&h, ctl, sizeof(UniqCtl), cudaMemcpyDeviceToHost, st));
-        KGB_CUDA_CHECK(cudaStreamSynchronize(st));
-        if (!h.overflow && h.distinct <= 300000ull) {
-            // the full pass: persistent CTAs with the shared-memory key cache in front of the table
-            static const bool cache_on = !(getenv("KGB200_UNIQUE_CACHE") && atoi(getenv("KGB200_UNIQUE_CACHE")) == 0);
+        static const bool cache_on = !(getenv("KGB200_UNIQUE_CACHE") && atoi(getenv("KGB200_UNIQUE_CACHE")) == 0);
+        constexpr unsigned long long PROBE_LIMIT = 300000ull;
+        h.overflow = 0;
+        h.distinct = 0;
+        if (!cache_on) {  // (debugging path: the plain pass has no device-side verdict, so the host reads the probe's)
+            KGB_CUDA_CHECK(cudaMemcpyAsync(&h, ctl, sizeof(UniqCtl), cudaMemcpyDeviceToHost, st));
+            KGB_CUDA_CHECK(cudaStreamSynchronize(st));
+        }
+        if (!h.overflow && h.distinct <= PROBE_LIMIT) {
+            // the full pass: persistent CTAs with the shared-memory key cache in front of the table; it reads the probe's
+            // verdict itself, so the host synchronises ONCE per call (after the collect kernel)
             if (cache_on) {
                 static bool opted[64] = {};
                 const int dv = current_device();
@@ -472,9 +571,9 @@ extern "C" int kgb_unique_first(const void* a, int32_t dtype, int64_t n, void* o
                 long long cb = (n + UNIQ_CT * UNIQ_CU - 1) / (UNIQ_CT * UNIQ_CU);
                 if (cb > sm_count()) cb = sm_count();
                 if (dtype_size(dtype) == 8)
-                    uniq_insert_cached_kernel<u64><<<(unsigned)cb, UNIQ_CT, smem8, st>>>((const u64*)a, n, tab, ctl);
+                    uniq_insert_cached_kernel<u64><<<(unsigned)cb, UNIQ_CT, smem8, st>>>((const u64*)a, n, tab, ctl, PROBE_LIMIT);
                 else
-                    uniq_insert_cached_kernel<u32><<<(unsigned)cb, UNIQ_CT, smem4, st>>>((const u32*)a, n, tab, ctl);
+                    uniq_insert_cached_kernel<u32><<<(unsigned)cb, UNIQ_CT, smem4, st>>>((const u32*)a, n, tab, ctl, PROBE_LIMIT);
             } else {
                 insert(n, 1);
             }
@@ -503,7 +602,24 @@ extern "C" int kgb_unique_first(const void* a, int32_t dtype, int64_t n, void* o
         KGB_CUDA_CHECK(cudaMemcpyAsync(&c, count_out, 8, cudaMemcpyDeviceToHost, st));
         KGB_CUDA_CHECK(cudaStreamSynchronize(st));
     }
-    // 4. order of first appearance = ascending first positions
+    // 4. order of first appearance = ascending first positions (+ 5. the values, when one CTA can do both)
+    static const bool small_on = !(getenv("KGB200_UNIQUE_SMALL") && atoi(getenv("KGB200_UNIQUE_SMALL")) == 0);
+    if (small_on && c >= 1 && c <= UNIQ_SMALL) {
+        u32* rank = (u32*)tmpidx;
+        KGB_CUDA_CHECK(cudaMemsetAsync(rank, 0, (size_t)c * 4, st));
+        const int xb = ((int)c + UNIQ_RT - 1) / UNIQ_RT;
+        int yb = (4 * sm_count() + xb - 1) / xb;          // enough CTAs for a few waves ...
+        if (yb > xb) yb = xb;                             // ... but a chunk is at least one tile
+        int chunk = (((int)c + yb - 1) / yb + UNIQ_RT - 1) / UNIQ_RT * UNIQ_RT;
+        yb = ((int)c + chunk - 1) / chunk;
+        uniq_rank_kernel<<<dim3((unsigned)xb, (unsigned)yb), UNIQ_RT, 0, st>>>(first, (int)c, chunk, rank);
+        if (dtype_size(dtype) == 8)
+            uniq_place_kernel<u64><<<(unsigned)xb, 256, 0, st>>>((const u64*)a, first, rank, (int)c, (i64*)first_idx_out, (u64*)out);
+        else
+            uniq_place_kernel<u32><<<(unsigned)xb, 256, 0, st>>>((const u32*)a, first, rank, (int)c, (i64*)first_idx_out, (u32*)out);
+        KGB_CUDA_CHECK(cudaGetLastError());
+        return KGB_OK;
+    }
     rc = sort_pairs(first, KGB_I64, c, 0, tmpidx, first_idx_out, nullptr, g.sort, g.sort_bytes, st);
     if (rc != KGB_OK) return rc;
     // 5. the values
