@@ -197,12 +197,6 @@ __global__ void __launch_bounds__(256) uniq_insert_kernel(const T* __restrict__ 
 // keys that share a cache line evict each other); with more keys than entries the pass degrades to the plain one.
 constexpr int UNIQ_CACHE_LOG2 = 14;
 constexpr int UNIQ_CACHE = 1 << UNIQ_CACHE_LOG2;
-#ifndef KGB_UNIQ_BAR2
-#define KGB_UNIQ_BAR2 0   // 1 = keep the (redundant) barrier after the cache writes: measured 0.51 vs ... ms
-#endif
-#ifndef KGB_UNIQ_PF
-#define KGB_UNIQ_PF 1     // tiles prefetched into registers ahead of the one being looked up (1 or 2)
-#endif
 #ifndef KGB_UNIQ_CT
 #define KGB_UNIQ_CT 1024  // threads of the persistent CTA (tuning knob; 1024 caps a thread at 64 registers)
 #endif
@@ -256,11 +250,11 @@ template <typename T>
 __global__ void __launch_bounds__(UNIQ_CT, 1) uniq_insert_cached_kernel(const T* __restrict__ a, i64 n, UniqSlot* __restrict__ tab,
                                                                         UniqCtl* __restrict__ ctl, unsigned long long probe_limit) {
     extern __shared__ __align__(16) u64 s_cache[];
-    __shared__ int s_special;  // this CTA has already reported the all-ones key at a smaller position
     constexpr int U = UNIQ_CU;
     const int tid = threadIdx.x;
-    for (int c = tid; c < UNIQ_CACHE; c += UNIQ_CT) s_cache[c] = UNIQ_EMPTY;
-    if (tid == 0) s_special = 0;
+    // "empty" entry c holds the key c ^ 1, whose own entry is c ^ 1: no lookup of entry c can ever match it, so the hit
+    // path needs no emptiness test — and the all-ones key (the TABLE's empty pattern) can be cached like any other
+    for (int c = tid; c < UNIQ_CACHE; c += UNIQ_CT) s_cache[c] = (u64)(c ^ 1);
     // the verdict on the cardinality probe (which ran just before, on the same stream) is taken here, not on the host:
     // too many distinct keys among the probe's rows -> flag, every CTA leaves at once, the host runs the sort path
     bool give_up = false;
@@ -271,99 +265,102 @@ __global__ void __launch_bounds__(UNIQ_CT, 1) uniq_insert_cached_kernel(const T*
     if (__syncthreads_or(give_up)) return;
     const i64 tile = (i64)UNIQ_CT * U;
     const i64 stride = (i64)gridDim.x * tile;
-    i64 base = (i64)blockIdx.x * tile;
-    T cur[U], nxt[U];
-#if KGB_UNIQ_PF == 2
-    T nx1[U];  // two tiles in flight: one tile of 32 KB per SM does not cover HBM latency at full bandwidth
-#endif
+    const T* __restrict__ at = a + tid;
+
+    // one tile: `cur` holds its rows (loaded one call earlier), the next tile's rows are fetched into `nxt` meanwhile.
+    // Returns true when the CTA has to leave (table overflow).  Interior tiles take a path without bounds tests; in the
+    // steady state every row hits the cache and a row costs its load, the index fold, one LDS and one compare.
+    auto step = [&](const T (&cur)[U], T (&nxt)[U], i64 base) -> bool {
+        const i64 nb = base + stride;
+        if (nb + tile <= n) {
 #pragma unroll
-    for (int u = 0; u < U; u++) {
-        const i64 j = base + u * UNIQ_CT + tid;
-        cur[u] = a[j < n ? j : n - 1];
-#if KGB_UNIQ_PF == 2
-        const i64 j1 = j + stride;
-        nx1[u] = a[j1 < n ? j1 : n - 1];
-#endif
-    }
-    u32 fresh = 0;
-    for (; base < n; base += stride) {
-        const i64 nb = base + KGB_UNIQ_PF * stride;  // later tiles' loads fly while this one is looked up
+            for (int u = 0; u < U; u++) nxt[u] = at[nb + u * UNIQ_CT];
+        } else {
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            const i64 j = nb + u * UNIQ_CT + tid;
-            nxt[u] = a[j < n ? j : n - 1];
+            for (int u = 0; u < U; u++) {
+                const i64 j = nb + u * UNIQ_CT + tid;
+                nxt[u] = a[j < n ? j : n - 1];
+            }
         }
         // the abort flag is read by one thread and only consumed at the barrier below: a global load every thread
         // waits for would put an L2 round trip on the critical path of every iteration
         bool bail = tid == 0 ? *(volatile int*)&ctl->overflow != 0 : false;
-        bool special = false;
         u32 miss = 0;
         u32 ci[U];
         // 1. the cache: shared memory only
+        if (base + tile <= n) {
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            const i64 i = base + u * UNIQ_CT + tid;
-            const u64 k = uniq_bits<T>(cur[u]);
-            ci[u] = uniq_cache_index(k, UNIQ_CACHE_LOG2);
-            if (i >= n) continue;
-            if (k == UNIQ_EMPTY) {
-                if (!s_special) {
-                    atomicMin(&ctl->special_first, (unsigned long long)i);
-                    special = true;
-                }
-                continue;
-            }
-            if (s_cache[ci[u]] != k) miss |= 1u << u;
-        }
-        // 2. the misses: all table reads are issued before the first one is looked at
-        ulonglong2 e[U];
-        u32 hs[U];
-#pragma unroll
-        for (int u = 0; u < U; u++)
-            if (miss & (1u << u)) {
-                hs[u] = (u32)(uniq_hash(uniq_bits<T>(cur[u])) & (UNIQ_SLOTS - 1));
-                asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];"
-                             : "=l"(e[u].x), "=l"(e[u].y)
-                             : "l"(&tab[hs[u]])
-                             : "memory");
-            }
-#pragma unroll
-        for (int u = 0; u < U; u++)
-            if (miss & (1u << u)) {
-                const i64 i = base + u * UNIQ_CT + tid;
+            for (int u = 0; u < U; u++) {
                 const u64 k = uniq_bits<T>(cur[u]);
-                if (e[u].x == k) {  // the common case: present; touch it only if this row comes earlier
-                    if ((u64)i < e[u].y) atomicMin((unsigned long long*)&tab[hs[u]].first, (unsigned long long)i);
-                } else {
-                    uniq_probe(tab, ctl, k, i, (u64)hs[u], fresh, bail);
-                }
+                ci[u] = uniq_cache_index(k, UNIQ_CACHE_LOG2);
+                miss |= (s_cache[ci[u]] != k ? 1u : 0u) << u;
             }
-        fresh = __reduce_add_sync(0xffffffffu, fresh);
-        if ((tid & 31) == 0 && fresh) {
-            if (atomicAdd(&ctl->distinct, (unsigned long long)fresh) + fresh > UNIQ_LIMIT) ctl->overflow = 1;
-        }
-        fresh = 0;
-        if (__syncthreads_or(bail)) return;  // every lookup of this iteration is done; leave together on overflow
-        // 3. remember what went to the table (visible to the NEXT iteration's lookups only)
+        } else {
 #pragma unroll
-        for (int u = 0; u < U; u++)
-            if (miss & (1u << u)) s_cache[ci[u]] = uniq_bits<T>(cur[u]);
-        if (special) s_special = 1;
-        // no second barrier: a warp that runs ahead into the next iteration's lookups either sees one of these writes
-        // (made for an earlier tile, i.e. smaller positions: a valid hit) or misses and asks the table; its own writes
-        // wait behind the next barrier, which every warp reaches only after its lookups
-#if KGB_UNIQ_BAR2
-        __syncthreads();
-#endif
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-#if KGB_UNIQ_PF == 2
-            cur[u] = nx1[u];
-            nx1[u] = nxt[u];
-#else
-            cur[u] = nxt[u];
-#endif
+            for (int u = 0; u < U; u++) {
+                const u64 k = uniq_bits<T>(cur[u]);
+                ci[u] = uniq_cache_index(k, UNIQ_CACHE_LOG2);
+                if (base + u * UNIQ_CT + tid < n && s_cache[ci[u]] != k) miss |= 1u << u;
+            }
         }
+        if (__any_sync(0xffffffffu, miss != 0)) {  // warp-uniform: a warp whose rows all hit skips the table protocol
+            // 2. the misses: all table reads are issued before the first one is looked at
+            u32 fresh = 0;
+            ulonglong2 e[U];
+            u32 hs[U];
+#pragma unroll
+            for (int u = 0; u < U; u++)
+                if ((miss & (1u << u)) && uniq_bits<T>(cur[u]) != UNIQ_EMPTY) {
+                    hs[u] = (u32)(uniq_hash(uniq_bits<T>(cur[u])) & (UNIQ_SLOTS - 1));
+                    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];"
+                                 : "=l"(e[u].x), "=l"(e[u].y)
+                                 : "l"(&tab[hs[u]])
+                                 : "memory");
+                }
+#pragma unroll
+            for (int u = 0; u < U; u++)
+                if (miss & (1u << u)) {
+                    const i64 i = base + u * UNIQ_CT + tid;
+                    const u64 k = uniq_bits<T>(cur[u]);
+                    if (k == UNIQ_EMPTY) {  // the table's own "empty" pattern: tracked beside the table, cached like any key
+                        atomicMin(&ctl->special_first, (unsigned long long)i);
+                    } else if (e[u].x == k) {  // the common case: present; touch it only if this row comes earlier
+                        if ((u64)i < e[u].y) atomicMin((unsigned long long*)&tab[hs[u]].first, (unsigned long long)i);
+                    } else {
+                        uniq_probe(tab, ctl, k, i, (u64)hs[u], fresh, bail);
+                    }
+                }
+            fresh = __reduce_add_sync(0xffffffffu, fresh);
+            if ((tid & 31) == 0 && fresh) {
+                if (atomicAdd(&ctl->distinct, (unsigned long long)fresh) + fresh > UNIQ_LIMIT) ctl->overflow = 1;
+            }
+        }
+        if (__syncthreads_or(bail)) return true;  // every lookup of this iteration is done; leave together on overflow
+        // 3. remember what went to the table (visible to LATER iterations' lookups only).  No second barrier: a warp that
+        // runs ahead into the next iteration's lookups either sees one of these writes (made for an earlier tile, i.e.
+        // smaller positions: a valid hit) or misses and asks the table; its own writes wait behind the next barrier,
+        // which every warp reaches only after its lookups
+        if (miss) {
+#pragma unroll
+            for (int u = 0; u < U; u++)
+                if (miss & (1u << u)) s_cache[ci[u]] = uniq_bits<T>(cur[u]);
+        }
+        return false;
+    };
+
+    i64 base = (i64)blockIdx.x * tile;
+    T r0[U], r1[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        const i64 j = base + u * UNIQ_CT + tid;
+        r0[u] = a[j < n ? j : n - 1];
+    }
+    while (base < n) {  // two tiles per trip, the register sets trading places (no copies)
+        if (step(r0, r1, base)) return;
+        base += stride;
+        if (base >= n) break;
+        if (step(r1, r0, base)) return;
+        base += stride;
     }
 }
 
