@@ -166,11 +166,11 @@ class DeviceTable(dict):
 
     # ---------------------------------------------------------------- inserts
     def insert(self, y):
-        self.buffer.append(np.asarray(y.to_numpy() if isinstance(y, DeviceArray) else y).reshape(-1))
+        self.buffer.append(np.asarray(y.to_numpy() if isinstance(y, DeviceArray) else y).reshape(1, -1))
 
     def insertb(self, y):
         y = np.asarray(y.to_numpy() if isinstance(y, DeviceArray) else y)
-        self.buffer.extend(y.reshape(-1, len(self.columns)))
+        self.buffer.append(y.reshape(-1, len(self.columns)))   # one block, not one Python object per row
 
     def commit(self):
         """sys_fn_db.py:93-110.  Without an index: append.  With one: existing rows whose key is buffered take the
@@ -178,7 +178,7 @@ class DeviceTable(dict):
         (existing ++ buffered) keys and elementwise kernels over the sorted order; the rows never leave the device."""
         if not self.buffer:
             return
-        buf = np.stack(self.buffer)
+        buf = np.concatenate(self.buffer)
         self.buffer = []
         n_old = next(iter(self._cols.values())).size
         if self.has_index():
