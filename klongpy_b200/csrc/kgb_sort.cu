@@ -17,6 +17,7 @@
 // Replaces np.argsort (klongpy/backends/numpy_backend.py:75-80) behind kg_argsort (klongpy/writer.py:97-122).
 // Stability is the language contract (ties by position; grade-down = reversed stable ascending).
 #include <cstdlib>
+#include <type_traits>
 
 #include "kgb_sort.cuh"
 
@@ -34,6 +35,9 @@ constexpr int STILE = ST * SI;     // 4096 keys per tile
 #define KGB_SORT_PT 512   // compute threads
 #define KGB_SORT_PSI 8    // keys per compute thread (even)
 #define KGB_SORT_PD 2     // tiles parked while their look-back runs
+#endif
+#ifndef KGB_SORT_FULLTILE
+#define KGB_SORT_FULLTILE 0  // 1: interior tiles take instantiations without per-key bounds tests (see write_tile)
 #endif
 #ifndef KGB_SORT_OCC
 #define KGB_SORT_OCC 1    // persistent CTAs per SM
@@ -537,6 +541,60 @@ __global__ void __launch_bounds__(PT + PLT, KGB_SORT_OCC) onesweep_pass_p(const 
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
+#if KGB_SORT_FULLTILE
+    // (interior tiles — all but the last — take instantiations without the per-key bounds test, and the role of the pass
+    // is tested once per tile, not once per key: ncu showed 22 % of the executed instructions of this kernel to be
+    // BSSY/BSYNC/BRA bookkeeping around such guards)
+    auto write_tile = [&](auto full_c, u32 st, int tile_n) {
+        constexpr bool FULL = decltype(full_c)::value;
+        if (!last) {
+#pragma unroll
+            for (int j = 0; j < PSI; j++) {
+                const int p = j * PT + tid;
+                if (FULL || p < tile_n) {
+                    const u64 kk = sm.keys[st][p];
+                    const i64 gp = sm.gbase[st][(u32)(kk >> shift) & 255u] + p;
+                    dst_keys[gp] = kk;
+                    dst_idx[gp] = sm.idx[st][p];
+                }
+            }
+        } else if (!descending && !keys_sorted_out && !enc_sorted_out) {  // plain grade-up
+#pragma unroll
+            for (int j = 0; j < PSI; j++) {
+                const int p = j * PT + tid;
+                if (FULL || p < tile_n) {
+                    const u64 kk = sm.keys[st][p];
+                    idx_out[sm.gbase[st][(u32)(kk >> shift) & 255u] + p] = (i64)sm.idx[st][p];
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < PSI; j++) {
+                const int p = j * PT + tid;
+                if (FULL || p < tile_n) {
+                    const u64 kk = sm.keys[st][p];
+                    const i64 gp = sm.gbase[st][(u32)(kk >> shift) & 255u] + p;
+                    const i64 op = descending ? (n - 1 - gp) : gp;
+                    idx_out[op] = (i64)sm.idx[st][p];
+                    if (keys_sorted_out) keys_sorted_out[op] = KeyCodec<DT>::dec(kk);
+                    if (enc_sorted_out) enc_sorted_out[op] = kk;
+                }
+            }
+        }
+    };
+    // tile parked in stage `st` -> global, as digit-contiguous runs
+    auto write_out = [&](u32 li, u32 t) {
+        const u32 st = li % PNS;
+        mbar_wait(&sm.gb_bar[st], (li / PNS) & 1u);
+        const i64 base = (i64)t * PTILE;
+        const int tile_n = (int)((n - base) < (i64)PTILE ? (n - base) : (i64)PTILE);
+        if (tile_n == PTILE)
+            write_tile(std::true_type{}, st, tile_n);
+        else
+            write_tile(std::false_type{}, st, tile_n);
+    };
+
+#else
     // tile parked in stage `st` -> global, as digit-contiguous runs
     auto write_out = [&](u32 li, u32 t) {
         const u32 st = li % PNS;
@@ -563,6 +621,7 @@ __global__ void __launch_bounds__(PT + PLT, KGB_SORT_OCC) onesweep_pass_p(const 
         }
     };
 
+#endif
 #pragma unroll
     for (int j = 0; j < PP; j++) issue_load((u32)j);
     u32 tq[PD];
@@ -583,87 +642,94 @@ __global__ void __launch_bounds__(PT + PLT, KGB_SORT_OCC) onesweep_pass_p(const 
         const i64 base = (i64)tile * PTILE;
         const int tile_n = (int)((n - base) < (i64)PTILE ? (n - base) : (i64)PTILE);
 
-        // ---- rank: warp w owns slots [w*256, (w+1)*256), item k of lane l is slot w*256 + k*32 + l
-        u64 key[PSI];
-        u32 idx[PSI], rank[PSI];
-        const int wslot = warp * (PSI * 32);
-#pragma unroll
-        for (int k = 0; k < PSI; k++) {
-            const int slot = wslot + k * 32 + lane;
-            if (slot < tile_n) {
-                const u64 raw = sm.keys[st][slot];
-                key[k] = first ? KeyCodec<DT>::enc(*reinterpret_cast<const T*>(&raw)) : raw;
-                idx[k] = first ? (u32)(base + slot) : sm.idx[st][slot];
-            } else {
-                key[k] = ~0ull;
-                idx[k] = 0;
-            }
-        }
-        {
-            const u32 lt = (1u << lane) - 1u;
-            u32 peers[PSI];
-#pragma unroll
+        auto rank_and_park = [&](auto full_c) {
+            constexpr bool FULL = decltype(full_c)::value;
+            // ---- rank: warp w owns slots [w*256, (w+1)*256), item k of lane l is slot w*256 + k*32 + l
+            u64 key[PSI];
+            u32 idx[PSI], rank[PSI];
+            const int wslot = warp * (PSI * 32);
+    #pragma unroll
             for (int k = 0; k < PSI; k++) {
-                const bool valid = (wslot + k * 32 + lane) < tile_n;
-                const u32 d = (u32)(key[k] >> shift) & 255u;
-                peers[k] = digit_peers(d, valid);
+                const int slot = wslot + k * 32 + lane;
+                if (FULL || slot < tile_n) {
+                    const u64 raw = sm.keys[st][slot];
+                    key[k] = first ? KeyCodec<DT>::enc(*reinterpret_cast<const T*>(&raw)) : raw;
+                    idx[k] = first ? (u32)(base + slot) : sm.idx[st][slot];
+                } else {
+                    key[k] = ~0ull;
+                    idx[k] = 0;
+                }
             }
-#pragma unroll
+            {
+                const u32 lt = (1u << lane) - 1u;
+                u32 peers[PSI];
+    #pragma unroll
+                for (int k = 0; k < PSI; k++) {
+                    const bool valid = FULL || (wslot + k * 32 + lane) < tile_n;
+                    const u32 d = (u32)(key[k] >> shift) & 255u;
+                    peers[k] = digit_peers(d, valid);
+                }
+    #pragma unroll
+                for (int k = 0; k < PSI; k++) {
+                    const bool valid = FULL || (wslot + k * 32 + lane) < tile_n;
+                    const u32 d = (u32)(key[k] >> shift) & 255u;
+                    rank[k] = 0;
+                    if (valid && lane == __ffs(peers[k]) - 1) rank[k] = atomicAdd(&sm.whist[warp][d], (u32)__popc(peers[k]));
+                }
+    #pragma unroll
+                for (int k = 0; k < PSI; k++)
+                    rank[k] = __shfl_sync(0xffffffffu, rank[k], __ffs(peers[k]) - 1) + __popc(peers[k] & lt);
+            }
+            bar_compute();              // B: warp histograms complete; every raw key of the stage has been read
+            // ---- per digit (threads 0..255): exclusive offsets across warps, tile count, publish
+            u32 cnt = 0, inc = 0;
+            if (tid < RADIX) {
+                const int d = tid;
+                u32 run = 0;
+    #pragma unroll
+                for (int w = 0; w < PT / 32; w++) {
+                    const u32 c = sm.whist[w][d];
+                    sm.whist[w][d] = run;
+                    run += c;
+                }
+                cnt = run;
+                st_relaxed_u64(&states[(size_t)tile * RADIX + d], lb_pack(tile == 0 ? KGB_LB_PREFIX : KGB_LB_AGG, epoch, cnt));
+                inc = cnt;
+    #pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const u32 v = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += v;
+                }
+                if (lane == 31) sm.wsum[warp] = inc;
+            }
+            bar_compute();              // C'
+            if (tid < RADIX) {
+                u32 wpre = 0;
+    #pragma unroll
+                for (int w = 0; w < RADIX / 32; w++)
+                    if (w < warp) wpre += sm.wsum[w];
+                sm.cntd[st][tid] = make_uint2(cnt, wpre + inc - cnt);
+            }
+            bar_compute();              // C: counts + digit offsets of the tile are in the ring
+            if (tid == 0) {
+                sm.tile_of[st] = tile;
+                mbar_arrive(&sm.cnt_bar[st]);  // hand the tile to the look-back group
+            }
+            // ---- scatter into tile-sorted order, into the stage the raw keys came from
+    #pragma unroll
             for (int k = 0; k < PSI; k++) {
-                const bool valid = (wslot + k * 32 + lane) < tile_n;
-                const u32 d = (u32)(key[k] >> shift) & 255u;
-                rank[k] = 0;
-                if (valid && lane == __ffs(peers[k]) - 1) rank[k] = atomicAdd(&sm.whist[warp][d], (u32)__popc(peers[k]));
+                if (FULL || (wslot + k * 32 + lane) < tile_n) {
+                    const u32 d = (u32)(key[k] >> shift) & 255u;
+                    const u32 p = sm.cntd[st][d].y + sm.whist[warp][d] + rank[k];
+                    sm.keys[st][p] = key[k];
+                    sm.idx[st][p] = idx[k];
+                }
             }
-#pragma unroll
-            for (int k = 0; k < PSI; k++)
-                rank[k] = __shfl_sync(0xffffffffu, rank[k], __ffs(peers[k]) - 1) + __popc(peers[k] & lt);
-        }
-        bar_compute();              // B: warp histograms complete; every raw key of the stage has been read
-        // ---- per digit (threads 0..255): exclusive offsets across warps, tile count, publish
-        u32 cnt = 0, inc = 0;
-        if (tid < RADIX) {
-            const int d = tid;
-            u32 run = 0;
-#pragma unroll
-            for (int w = 0; w < PT / 32; w++) {
-                const u32 c = sm.whist[w][d];
-                sm.whist[w][d] = run;
-                run += c;
-            }
-            cnt = run;
-            st_relaxed_u64(&states[(size_t)tile * RADIX + d], lb_pack(tile == 0 ? KGB_LB_PREFIX : KGB_LB_AGG, epoch, cnt));
-            inc = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const u32 v = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += v;
-            }
-            if (lane == 31) sm.wsum[warp] = inc;
-        }
-        bar_compute();              // C'
-        if (tid < RADIX) {
-            u32 wpre = 0;
-#pragma unroll
-            for (int w = 0; w < RADIX / 32; w++)
-                if (w < warp) wpre += sm.wsum[w];
-            sm.cntd[st][tid] = make_uint2(cnt, wpre + inc - cnt);
-        }
-        bar_compute();              // C: counts + digit offsets of the tile are in the ring
-        if (tid == 0) {
-            sm.tile_of[st] = tile;
-            mbar_arrive(&sm.cnt_bar[st]);  // hand the tile to the look-back group
-        }
-        // ---- scatter into tile-sorted order, into the stage the raw keys came from
-#pragma unroll
-        for (int k = 0; k < PSI; k++) {
-            if ((wslot + k * 32 + lane) < tile_n) {
-                const u32 d = (u32)(key[k] >> shift) & 255u;
-                const u32 p = sm.cntd[st][d].y + sm.whist[warp][d] + rank[k];
-                sm.keys[st][p] = key[k];
-                sm.idx[st][p] = idx[k];
-            }
-        }
+        };
+        if (KGB_SORT_FULLTILE && tile_n == PTILE)
+            rank_and_park(std::true_type{});
+        else
+            rank_and_park(std::false_type{});
         bar_compute();              // D: the sorted tile is parked; whist is free again
         for (int q = tid; q < (PT / 32) * RADIX; q += PT) (&sm.whist[0][0])[q] = 0;
         // ---- write out the tile parked PD iterations ago
