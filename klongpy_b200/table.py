@@ -238,9 +238,13 @@ class DeviceTable(dict):
             lo, hi = -1, 0
         if 0 <= lo and hi < dense_limit:
             mn, mx, sm, ct = ops.groupagg(k, v, hi + 1)
-            live = ops.nonzero(ops.binary("gt_b", ct, 0))
-            keys = live if live.dtype == k.dtype else ops.astype(live, k.dtype)
-            mn, mx, sm, ct = (ops.gather(t, live) for t in (mn, mx, sm, ct))
+            if bool(ops.all_(ct)):                                              # every id in [0, hi] occurs: nothing to drop
+                keys = ops.iota(hi + 1, self.device)
+            else:
+                keys = ops.nonzero(ct)
+                mn, mx, sm, ct = (ops.gather(t, keys) for t in (mn, mx, sm, ct))
+            if keys.dtype != k.dtype:
+                keys = ops.astype(keys, k.dtype)
         else:
             order, starts, g = ops.group(k)
             sizes = ops.binary("sub", DeviceArray(starts._t[1:]), DeviceArray(starts._t[:-1]))

@@ -222,3 +222,46 @@ def test_device_table_large_gpu(cuda_backend):
     v = np.round(rng.normal(10, 15, n), 1)
     check_group_stats(be, a, v)
     check_group_stats(be, a * 1_000_003 - 17, v)
+
+
+def edge_cases(be):
+    """Empty and one-row tables, float index keys, NaN-free ties, appends that change a column's dtype."""
+    from klongpy_b200.table import DeviceTable
+    t = DeviceTable({"a": np.zeros(0)}, columns=["a"], device=be.device)          # tests/kgtests/db/test_create_empty_table.kg
+    assert len(t) == 0 and list(t.schema()) == ["a"] and t.rows().size == 0
+    t.set_index(["a"])
+    t.insert(np.array([3.5]))
+    t.insert(np.array([1.5]))
+    t.insert(np.array([3.5]))
+    assert t.rows().tolist() == [1.5, 3.5] and len(t) == 2                          # one column: rows() squeezes like the reference
+    t.reset_index()
+    keys, mn, mean, mx, ct = t.group_stats("a", "a")
+    assert keys.to_numpy().tolist() == [1.5, 3.5] and ct.to_numpy().tolist() == [1, 1]
+    one = DeviceTable({"k": be.kg_asarray(np.array([7])), "v": be.kg_asarray(np.array([2.0]))})
+    one.set_index(["k"])
+    assert one.rows().tolist() == [7.0, 2.0]
+    one.insert(np.array([7, 9.25]))
+    one.insert(np.array([-2, 0.5]))
+    assert one.rows().tolist() == [[-2.0, 0.5], [7.0, 9.25]]
+    assert one.get("k").dtype == np.float64                                          # the buffered block is one float matrix
+    # float keys incl. -0.0 / 0.0 (equal as keys) and repeated full rows
+    f = DeviceTable({"k": be.kg_asarray(np.array([0.5, -0.0, 0.0, 0.5, 2.0, 0.5])),
+                     "v": be.kg_asarray(np.array([1, 2, 2, 1, 5, 3]))})
+    f.set_index(["k"])
+    m = np.stack([np.array([0.5, -0.0, 0.0, 0.5, 2.0, 0.5]), np.array([1, 2, 2, 1, 5, 3.0])], 1)
+    assert np.array_equal(f.rows(), O.table_index(m, [0]))
+    e = DeviceTable({"k": be.kg_asarray(np.zeros(0, dtype=np.int64)), "v": be.kg_asarray(np.zeros(0))})
+    assert all(x.size == 0 for x in e.group_stats("k", "v"))
+    with pytest.raises(ValueError):
+        DeviceTable({"a": np.arange(3), "b": np.arange(4)}, device=be.device)
+    with pytest.raises(ValueError):
+        one.set("z", np.arange(5))
+
+
+def test_device_table_edge_cases(fake_backend):
+    edge_cases(fake_backend)
+
+
+@pytest.mark.gpu
+def test_device_table_edge_cases_gpu(cuda_backend):
+    edge_cases(cuda_backend)
