@@ -157,11 +157,27 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "host_cpus": os.cpu_count(),
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=_claim_stdout(), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------ our arm
+_RESULT_OUT = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version line to stdout when
+    the box sets NCCL_DEBUG), so everything else this process and its libraries print is sent to stderr and only the
+    result line goes to the real stdout."""
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+    return _RESULT_OUT
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -360,7 +376,7 @@ def main():
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": per_step_launches * args.steps, "clocks": clocks,
             "primitives": prims,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), file=_claim_stdout(), flush=True)
     if world > 1:
         td.barrier()
         td.destroy_process_group()
