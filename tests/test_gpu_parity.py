@@ -460,6 +460,41 @@ def test_range_hash_path_and_fallback(be, K, case):
     assert np.array_equal(gb, wb), case
 
 
+@pytest.mark.parametrize("c", [1, 2, 255, 256, 257, 4097, 16_383, 16_384, 16_385, 40_000])
+@pytest.mark.parametrize("n", [50_000, 2_500_003])
+def test_range_distinct_count_boundaries(be, K, c, n):
+    """The number of distinct keys around the edges of the first-position ranking kernel (tiles of 256, at most 16 384
+    keys; above that the radix sort orders the first positions), on the sort path (small n) and the hash path."""
+    if c > n:
+        pytest.skip("more distinct keys than rows")
+    rng = np.random.default_rng(c + n)
+    vals = rng.permutation(10 * c)[:c] - 3 * c               # distinct, scattered, negative and positive
+    a = vals[rng.integers(0, c, n)]
+    a[rng.permutation(n)[:c]] = vals                         # every key occurs
+    got = host(K.unique_first(dev(be, a)))
+    assert np.array_equal(got, _first_appearance(a))
+    f = a / 4.0                                              # the same as float64 keys (information in the high word)
+    assert np.array_equal(host(K.unique_first(dev(be, f))), _first_appearance(f))
+
+
+def test_range_cache_adversaries(be, K):
+    """Keys built to fight the per-CTA key cache: all of them folding onto ONE cache entry (multiples of 2^28 xor-fold
+    to the same index), small keys next to the patterns 'empty' entries are initialised with (c ^ 1), the all-ones key
+    as the majority key, and a key that first appears in the very last row."""
+    rng = np.random.default_rng(77)
+    n = 2_600_000
+    same_entry = (rng.integers(0, 300, n) << 28) | 5
+    assert np.array_equal(host(K.unique_first(dev(be, same_entry))), _first_appearance(same_entry))
+    small = rng.integers(0, 16_384, n) ^ 1
+    assert np.array_equal(host(K.unique_first(dev(be, small))), _first_appearance(small))
+    ones = np.where(rng.random(n) < 0.9, -1, rng.integers(0, 50, n))
+    ones[-1] = 123_456_789
+    assert np.array_equal(host(K.unique_first(dev(be, ones))), _first_appearance(ones))
+    late = np.zeros(n, dtype=np.int64)
+    late[-1] = -1
+    assert np.array_equal(host(K.unique_first(dev(be, late))), np.array([0, -1]))
+
+
 def test_support_verbs(be, K):
     rng = np.random.default_rng(5)
     assert np.array_equal(host(K.iota(0)), O.enumerate_(0)) and np.array_equal(host(K.iota(100_001)), O.enumerate_(100_001))
