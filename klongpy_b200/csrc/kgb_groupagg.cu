@@ -117,16 +117,25 @@ __global__ void __launch_bounds__(1024, 1) groupagg_kernel_v2(const i64* __restr
                                                               i64 n, i64 G, AggWs a, int l2_every) {
     extern __shared__ __align__(16) unsigned char agg_smem[];
     const bool sum_to_l2 = l2_every > 0 && ((threadIdx.x >> 5) % l2_every) == l2_every - 1;
-    constexpr bool COUNT_IN_SMEM = VARIANT == 1 || VARIANT == 3;
-    constexpr bool SUM_IN_SMEM = VARIANT == 3;
-    double* s_sum = reinterpret_cast<double*>(agg_smem);  // VARIANT 3 only (G doubles first, keeps 8-byte alignment)
+    constexpr bool COUNT_IN_SMEM = VARIANT == 1 || VARIANT == 3 || VARIANT == 5;
+    constexpr bool SUM_IN_SMEM = VARIANT == 3 || VARIANT == 5;
+    // VARIANT 5: both filters in ONE 32-bit word per station — [31:16] top 16 bits of the running max's order encoding,
+    // [15:0] of the running min's (sign, exponent, 4 mantissa bits: a row passes only if it lands in the extreme's
+    // 1/16-binade bucket or beyond) — so a row that cannot beat either extreme costs one LDS instead of two; the word
+    // changes O(log rows) times per station and CTA, by CAS
+    constexpr bool PACKED = VARIANT == 5;
+    double* s_sum = reinterpret_cast<double*>(agg_smem);  // VARIANT 3/5 only (G doubles first, keeps 8-byte alignment)
     u32* s_cnt = reinterpret_cast<u32*>(agg_smem + (SUM_IN_SMEM ? (size_t)G * 8 : 0));
-    u32* s_minhi = s_cnt + G;
-    u32* s_maxhi = s_minhi + G;
+    u32* s_minhi = s_cnt + G;       // PACKED: the packed filter word
+    u32* s_maxhi = s_minhi + G;     // (unused when PACKED)
     for (i64 i = threadIdx.x; i < G; i += blockDim.x) {
         s_cnt[i] = 0u;
-        s_minhi[i] = (u32)(a.tmin[i] >> 32);  // seeded extremes (0xffffffff / 0 where the sample had no row)
-        s_maxhi[i] = (u32)(a.tmax[i] >> 32);
+        if (PACKED) {
+            s_minhi[i] = ((u32)(a.tmax[i] >> 48) << 16) | (u32)(a.tmin[i] >> 48);
+        } else {
+            s_minhi[i] = (u32)(a.tmin[i] >> 32);  // seeded extremes (0xffffffff / 0 where the sample had no row)
+            s_maxhi[i] = (u32)(a.tmax[i] >> 32);
+        }
         if (SUM_IN_SMEM) s_sum[i] = 0.0;
     }
     __syncthreads();
@@ -136,14 +145,35 @@ __global__ void __launch_bounds__(1024, 1) groupagg_kernel_v2(const i64* __restr
             return;
         }
         const u64 emin = enc_for_min(v), emax = enc_for_max(v);
-        const u32 lo = (u32)(emin >> 32), hi = (u32)(emax >> 32);
-        if (lo <= s_minhi[k]) {
-            if (lo < s_minhi[k]) atomicMin(&s_minhi[k], lo);
-            if (emin < ld_relaxed_u64(&a.tmin[k])) atomicMin(&a.tmin[k], emin);
-        }
-        if (hi >= s_maxhi[k]) {
-            if (hi > s_maxhi[k]) atomicMax(&s_maxhi[k], hi);
-            if (emax > ld_relaxed_u64(&a.tmax[k])) atomicMax(&a.tmax[k], emax);
+        if (PACKED) {
+            const u32 lo = (u32)(emin >> 48), hi = (u32)(emax >> 48);
+            const u32 f = s_minhi[k];
+            if (lo <= (f & 0xffffu)) {
+                for (u32 cur = f; lo < (cur & 0xffffu);) {
+                    const u32 got = atomicCAS(&s_minhi[k], cur, (cur & 0xffff0000u) | lo);
+                    if (got == cur) break;
+                    cur = got;
+                }
+                if (emin < ld_relaxed_u64(&a.tmin[k])) atomicMin(&a.tmin[k], emin);
+            }
+            if (hi >= (f >> 16)) {
+                for (u32 cur = f; hi > (cur >> 16);) {
+                    const u32 got = atomicCAS(&s_minhi[k], cur, (cur & 0xffffu) | (hi << 16));
+                    if (got == cur) break;
+                    cur = got;
+                }
+                if (emax > ld_relaxed_u64(&a.tmax[k])) atomicMax(&a.tmax[k], emax);
+            }
+        } else {
+            const u32 lo = (u32)(emin >> 32), hi = (u32)(emax >> 32);
+            if (lo <= s_minhi[k]) {
+                if (lo < s_minhi[k]) atomicMin(&s_minhi[k], lo);
+                if (emin < ld_relaxed_u64(&a.tmin[k])) atomicMin(&a.tmin[k], emin);
+            }
+            if (hi >= s_maxhi[k]) {
+                if (hi > s_maxhi[k]) atomicMax(&s_maxhi[k], hi);
+                if (emax > ld_relaxed_u64(&a.tmax[k])) atomicMax(&a.tmax[k], emax);
+            }
         }
         // the float64 add is the expensive step: a CAS loop (ATOMS.CAST.SPIN.64) on the SM's own atomic unit, or a
         // RED.ADD.F64 on the L2 atomic units.  Both units work at the same time when one warp in `l2_every` sends
@@ -378,11 +408,13 @@ extern "C" int kgb_groupagg_f64(const int64_t* keys, const double* vals, int64_t
         // 4 = one 128-bit CAS per row on a 16-byte record (ATOMS.CAS.128 turned out slower than CAS.64 + POPC.INC), 1 = filters + count in shared
         // memory and RED.ADD.F64 sums on the global table, 2 = filters only, 0 = v1 (all four updates on the
         // global table).  KGB200_AGG_VARIANT overrides for measurements.
-        int variant = 3;  // measured at 1e9 rows / 10k stations: v3 4.2 ms (0.58 of roofline), v4 7.1 ms, v1 ~14 ms, v0 ~23 ms
+        // 5 = variant 3 with both filters packed into one 32-bit word (one LDS per row instead of two; default).
+        int variant = 5;  // measured at 1e9 rows / 10k stations: v5 3.72 ms (0.66 of roofline), v3 4.09 ms (0.60), v4 7.1 ms, v1 ~14 ms, v0 ~23 ms
         if (const char* e = getenv("KGB200_AGG_VARIANT")) variant = atoi(e);
-        if (variant < 0 || variant > 4) variant = 3;
+        if (variant < 0 || variant > 5) variant = 5;
         const size_t limit = 200 * 1024;
         if (variant == 4 && (size_t)n_groups * 16 > limit) variant = 1;
+        if (variant == 5 && (size_t)n_groups * 16 > limit) variant = 1;  // (12 800 stations per CTA; 10 240 for variant 3)
         if (variant == 3 && (size_t)n_groups * 20 > limit) variant = 1;
         if (variant != 0 && (size_t)n_groups * 12 > limit) variant = 0;
         if (variant == 0) {
@@ -401,13 +433,14 @@ extern "C" int kgb_groupagg_f64(const int64_t* keys, const double* vals, int64_t
             groupagg_kernel_v4<<<(unsigned)pb, 1024, (size_t)n_groups * 16, st>>>((const i64*)keys, vals, n, n_groups, a);
             nparts = (int)pb;
         } else {
-            const size_t smem = (size_t)n_groups * (variant == 3 ? 20 : 12);
+            const size_t smem = (size_t)n_groups * (variant == 3 ? 20 : variant == 5 ? 16 : 12);
             static bool attr_set[64] = {false};
             const int dev = current_device();
             if (!attr_set[dev]) {
                 KGB_CUDA_CHECK(cudaFuncSetAttribute(groupagg_kernel_v2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
                 KGB_CUDA_CHECK(cudaFuncSetAttribute(groupagg_kernel_v2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
                 KGB_CUDA_CHECK(cudaFuncSetAttribute(groupagg_kernel_v2<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
+                KGB_CUDA_CHECK(cudaFuncSetAttribute(groupagg_kernel_v2<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
                 attr_set[dev] = true;
             }
             int l2_every = 0;
@@ -427,7 +460,10 @@ extern "C" int kgb_groupagg_f64(const int64_t* keys, const double* vals, int64_t
                 groupagg_kernel_v2<1><<<(unsigned)pb, 1024, smem, st>>>((const i64*)keys, vals, n, n_groups, a, l2_every);
             else if (variant == 2)
                 groupagg_kernel_v2<2><<<(unsigned)pb, 1024, smem, st>>>((const i64*)keys, vals, n, n_groups, a, l2_every);
-            else {
+            else if (variant == 5) {
+                groupagg_kernel_v2<5><<<(unsigned)pb, 1024, smem, st>>>((const i64*)keys, vals, n, n_groups, a, l2_every);
+                nparts = (int)pb;
+            } else {
                 groupagg_kernel_v2<3><<<(unsigned)pb, 1024, smem, st>>>((const i64*)keys, vals, n, n_groups, a, l2_every);
                 nparts = (int)pb;
             }

@@ -541,6 +541,43 @@ def test_grouped_min_mean_max(be, K, n, G):
         K.groupagg(dev(be, [0, G]), dev(be, [1.0, 2.0]), G)
 
 
+@pytest.mark.parametrize("case", ["narrow", "wide", "rising", "falling", "G12800", "G12801", "G40000"])
+def test_grouped_extremes_filter_stress(be, K, case):
+    """The per-CTA filters hold only the top 16 bits of each running extreme: values crowded into one filter bucket,
+    exponents from denormal to 1e300 with infinities and signed zeros, strictly rising / falling streams (every row is
+    a new extreme) and station counts at and beyond what fits the shared-memory tables — min/max bit-exact, counts
+    exact, sums in tolerance."""
+    rng = np.random.default_rng(len(case))
+    n, G = 2_000_003, 1000
+    if case == "narrow":
+        v = 64.0 + rng.integers(0, 1 << 20, n) * 2.0 ** -40
+    elif case == "wide":
+        v = rng.standard_normal(n) * 10.0 ** rng.integers(-300, 300, n)
+        v[::1013] = 0.0
+        v[1::1013] = -0.0
+        v[2::5003] = np.inf
+        v[3::5003] = -np.inf
+        v[4::7001] = 5e-324
+    elif case == "rising":
+        v = np.arange(n, dtype=np.float64) * 0.25 - 1000.0
+    elif case == "falling":
+        v = -np.arange(n, dtype=np.float64) * 0.25 + 1000.0
+    else:
+        G = int(case[1:])
+        v = np.round(rng.normal(10, 15, n), 1)
+    k = rng.integers(0, G, n)
+    mn, mx, sm, ct = (host(t) for t in K.groupagg(dev(be, k), dev(be, v), G))
+    rmn, rmx, rsm, rct = O.grouped_stats_fast(k, v, G)
+    assert np.array_equal(ct, rct)
+    assert np.array_equal(mn.view(np.int64), rmn.view(np.int64)) or np.array_equal(mn, rmn)
+    assert np.array_equal(mx.view(np.int64), rmx.view(np.int64)) or np.array_equal(mx, rmx)
+    if case != "wide":
+        assert np.allclose(sm, rsm, rtol=RTOL, atol=1e-9)
+    else:  # +inf and -inf in one station sum to NaN in both; compare where finite
+        fin = np.isfinite(rsm)
+        assert np.array_equal(np.isnan(sm), np.isnan(rsm)) and np.allclose(sm[fin], rsm[fin], rtol=1e-9, atol=0)
+
+
 def test_grouped_agg_merge_and_nan(be, K):
     k = np.array([0, 1, 0, 2, 1])
     v = np.array([1.0, np.nan, -3.0, 4.0, 2.0])
