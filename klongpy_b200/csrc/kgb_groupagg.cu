@@ -124,11 +124,25 @@ __global__ void __launch_bounds__(1024, 1) groupagg_kernel_v2(const i64* __restr
     // 1/16-binade bucket or beyond) — so a row that cannot beat either extreme costs one LDS instead of two; the word
     // changes O(log rows) times per station and CTA, by CAS
     constexpr bool PACKED = VARIANT == 5;
+    // VARIANT 6 (kept for the record, NOT the default: 6.86 vs 3.73 ms at 1e9 rows): the same state as one 16-byte
+    // RECORD per station {sum f64 | packed filters u32 | count u32}: one LDS.128 brings the filter word AND the current
+    // sum (the seed of a hand-written CAS loop), instead of an LDS.32 + an LDS.64.  The software loop around
+    // ATOMS.CAS.64 is far slower than the ATOMS.CAST.SPIN.64 the compiler emits for atomicAdd(double) on shared memory
+    constexpr bool AOS = VARIANT == 6;
+    struct __align__(16) Rec { u64 sum_bits; u32 filt; u32 cnt; };
+    Rec* s_rec = reinterpret_cast<Rec*>(agg_smem);
     double* s_sum = reinterpret_cast<double*>(agg_smem);  // VARIANT 3/5 only (G doubles first, keeps 8-byte alignment)
     u32* s_cnt = reinterpret_cast<u32*>(agg_smem + (SUM_IN_SMEM ? (size_t)G * 8 : 0));
     u32* s_minhi = s_cnt + G;       // PACKED: the packed filter word
     u32* s_maxhi = s_minhi + G;     // (unused when PACKED)
-    for (i64 i = threadIdx.x; i < G; i += blockDim.x) {
+    if (AOS) {
+        for (i64 i = threadIdx.x; i < G; i += blockDim.x) {
+            s_rec[i].sum_bits = 0ull;
+            s_rec[i].filt = ((u32)(a.tmax[i] >> 48) << 16) | (u32)(a.tmin[i] >> 48);
+            s_rec[i].cnt = 0u;
+        }
+    }
+    for (i64 i = threadIdx.x; !AOS && i < G; i += blockDim.x) {
         s_cnt[i] = 0u;
         if (PACKED) {
             s_minhi[i] = ((u32)(a.tmax[i] >> 48) << 16) | (u32)(a.tmin[i] >> 48);
@@ -145,6 +159,37 @@ __global__ void __launch_bounds__(1024, 1) groupagg_kernel_v2(const i64* __restr
             return;
         }
         const u64 emin = enc_for_min(v), emax = enc_for_max(v);
+        if (AOS) {
+            Rec* p = &s_rec[k];
+            const uint4 r = *reinterpret_cast<const uint4*>(p);  // {sum lo, sum hi, filters, count}
+            const u32 lo = (u32)(emin >> 48), hi = (u32)(emax >> 48);
+            const u32 f = r.z;
+            if (lo <= (f & 0xffffu)) {
+                for (u32 cur = f; lo < (cur & 0xffffu);) {
+                    const u32 got = atomicCAS(&p->filt, cur, (cur & 0xffff0000u) | lo);
+                    if (got == cur) break;
+                    cur = got;
+                }
+                if (emin < ld_relaxed_u64(&a.tmin[k])) atomicMin(&a.tmin[k], emin);
+            }
+            if (hi >= (f >> 16)) {
+                for (u32 cur = f; hi > (cur >> 16);) {
+                    const u32 got = atomicCAS(&p->filt, cur, (cur & 0xffffu) | (hi << 16));
+                    if (got == cur) break;
+                    cur = got;
+                }
+                if (emax > ld_relaxed_u64(&a.tmax[k])) atomicMax(&a.tmax[k], emax);
+            }
+            unsigned long long old = (unsigned long long)r.x | ((unsigned long long)r.y << 32);
+            while (true) {
+                const unsigned long long nw = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)old) + v);
+                const unsigned long long got = atomicCAS(reinterpret_cast<unsigned long long*>(&p->sum_bits), old, nw);
+                if (got == old) break;
+                old = got;
+            }
+            atomicAdd(&p->cnt, 1u);
+            return;
+        }
         if (PACKED) {
             const u32 lo = (u32)(emin >> 48), hi = (u32)(emax >> 48);
             const u32 f = s_minhi[k];
@@ -217,7 +262,15 @@ __global__ void __launch_bounds__(1024, 1) groupagg_kernel_v2(const i64* __restr
     } else {
         for (i64 i = tid; i < n; i += stride) row(keys[i], vals[i]);
     }
-    if (SUM_IN_SMEM) {
+    if (AOS) {
+        __syncthreads();
+        double* ps = a.psum + (size_t)blockIdx.x * G;
+        u32* pc = a.pcnt + (size_t)blockIdx.x * G;
+        for (i64 i = threadIdx.x; i < G; i += blockDim.x) {
+            ps[i] = __longlong_as_double((long long)s_rec[i].sum_bits);
+            pc[i] = s_rec[i].cnt;
+        }
+    } else if (SUM_IN_SMEM) {
         // per-CTA partial tables leave as plain coalesced stores; groupagg_finalize folds them in CTA order
         // (3 M global atomics for the flush cost ~0.1 ms at 1e8 rows)
         __syncthreads();
@@ -411,9 +464,10 @@ extern "C" int kgb_groupagg_f64(const int64_t* keys, const double* vals, int64_t
         // 5 = variant 3 with both filters packed into one 32-bit word (one LDS per row instead of two; default).
         int variant = 5;  // measured at 1e9 rows / 10k stations: v5 3.72 ms (0.66 of roofline), v3 4.09 ms (0.60), v4 7.1 ms, v1 ~14 ms, v0 ~23 ms
         if (const char* e = getenv("KGB200_AGG_VARIANT")) variant = atoi(e);
-        if (variant < 0 || variant > 5) variant = 5;
+        if (variant < 0 || variant > 6) variant = 5;
         const size_t limit = 200 * 1024;
         if (variant == 4 && (size_t)n_groups * 16 > limit) variant = 1;
+        if (variant == 6 && (size_t)n_groups * 16 > limit) variant = 1;
         if (variant == 5 && (size_t)n_groups * 16 > limit) variant = 1;  // (12 800 stations per CTA; 10 240 for variant 3)
         if (variant == 3 && (size_t)n_groups * 20 > limit) variant = 1;
         if (variant != 0 && (size_t)n_groups * 12 > limit) variant = 0;
@@ -433,7 +487,7 @@ extern "C" int kgb_groupagg_f64(const int64_t* keys, const double* vals, int64_t
             groupagg_kernel_v4<<<(unsigned)pb, 1024, (size_t)n_groups * 16, st>>>((const i64*)keys, vals, n, n_groups, a);
             nparts = (int)pb;
         } else {
-            const size_t smem = (size_t)n_groups * (variant == 3 ? 20 : variant == 5 ? 16 : 12);
+            const size_t smem = (size_t)n_groups * (variant == 3 ? 20 : variant >= 5 ? 16 : 12);
             static bool attr_set[64] = {false};
             const int dev = current_device();
             if (!attr_set[dev]) {
@@ -441,6 +495,7 @@ extern "C" int kgb_groupagg_f64(const int64_t* keys, const double* vals, int64_t
                 KGB_CUDA_CHECK(cudaFuncSetAttribute(groupagg_kernel_v2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
                 KGB_CUDA_CHECK(cudaFuncSetAttribute(groupagg_kernel_v2<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
                 KGB_CUDA_CHECK(cudaFuncSetAttribute(groupagg_kernel_v2<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
+                KGB_CUDA_CHECK(cudaFuncSetAttribute(groupagg_kernel_v2<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
                 attr_set[dev] = true;
             }
             int l2_every = 0;
@@ -460,7 +515,10 @@ extern "C" int kgb_groupagg_f64(const int64_t* keys, const double* vals, int64_t
                 groupagg_kernel_v2<1><<<(unsigned)pb, 1024, smem, st>>>((const i64*)keys, vals, n, n_groups, a, l2_every);
             else if (variant == 2)
                 groupagg_kernel_v2<2><<<(unsigned)pb, 1024, smem, st>>>((const i64*)keys, vals, n, n_groups, a, l2_every);
-            else if (variant == 5) {
+            else if (variant == 6) {
+                groupagg_kernel_v2<6><<<(unsigned)pb, 1024, smem, st>>>((const i64*)keys, vals, n, n_groups, a, l2_every);
+                nparts = (int)pb;
+            } else if (variant == 5) {
                 groupagg_kernel_v2<5><<<(unsigned)pb, 1024, smem, st>>>((const i64*)keys, vals, n, n_groups, a, l2_every);
                 nparts = (int)pb;
             } else {
