@@ -103,41 +103,49 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
-def run_reference(args):
-    """The reference's own CPU implementation of the path = its NumPy backend calls, restated in oracle/."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+def reference_step(x):
+    """(step, kind, how): one pass of the workload on the host array `x` through the reference's CPU implementation —
+    the UNMODIFIED reference (klongpy from the git-ignored baseline/_ref install) when it travelled to
+    this box, else the oracle port of its NumPy-backend calls."""
     from oracle import kg_oracle as O
-    n = int(args.ref_n)
-    rng = np.random.default_rng(0)
-    x = rng.integers(0, 256, n) / 256.0
     ir = ("reduce", "+", ("binop", "^", ("binop", "+", ("binop", "*", ("var", "_v0"), ("literal", 2)), ("literal", 1)), ("literal", 2)))
     sc = ("scan", "+", ("var", "_v0"))
 
-    def step():
+    def port_step():
         O.eval_ir(ir, {"_v0": x})
         O.eval_ir(sc, {"_v0": x})
 
-    kind, how = "port", "oracle/kg_oracle.eval_ir = numpy_backend.py:116-178"
+    how = "oracle/kg_oracle.eval_ir = numpy_backend.py:116-178"
     ref_dir = os.path.join(ROOT, "baseline", "_ref")
     if os.path.isdir(os.path.join(ref_dir, "klongpy")):
-        # the UNMODIFIED reference, when its install (git-ignored baseline/_ref, see DESIGN.md) travelled to this box:
-        # the same two expressions through its own interpreter, compiler and NumPy backend
         try:
-            sys.path.insert(0, ref_dir)
+            if ref_dir not in sys.path:
+                sys.path.insert(0, ref_dir)
             from klongpy import KlongInterpreter
             klong = KlongInterpreter(backend="numpy")
             klong["x"] = x
             assert float(klong("+/((x*2)+1)^2")) == float(O.eval_ir(ir, {"_v0": x}))
 
-            def step():  # noqa: F811
+            def ref_step():
                 klong("+/((x*2)+1)^2")
                 klong("+\\x")
 
-            kind, how = "reference", "klongpy 0.7.0 from baseline/_ref: KlongInterpreter(backend='numpy') on '+/((x*2)+1)^2' and '+\\x'"
+            return ref_step, "reference", ("klongpy 0.7.0 from baseline/_ref: KlongInterpreter(backend='numpy') on "
+                                          "'+/((x*2)+1)^2' and '+\\x'")
         except Exception as ex:  # fall back to the port, say why
             how += f"; baseline/_ref not usable: {type(ex).__name__}: {ex}"
+    return port_step, "port", how
+
+
+def run_reference(args):
+    """The reference's own CPU implementation of the path = its NumPy backend calls, restated in oracle/."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = int(args.ref_n)
+    rng = np.random.default_rng(0)
+    x = rng.integers(0, 256, n) / 256.0
+    step, kind, how = reference_step(x)
 
     for _ in range(args.warmup):
         step()
@@ -349,18 +357,16 @@ def main():
     # ---- CPU baseline (oracle port), rank 0, bounded sample
     cpu = None
     if rank == 0:
-        from oracle import kg_oracle as O
         m = int(args.cpu_n)
         hxs = np.random.default_rng(0).integers(0, 256, m) / 256.0
-        ir = ("reduce", "+", ("binop", "^", ("binop", "+", ("binop", "*", ("var", "_v0"), ("literal", 2)), ("literal", 1)), ("literal", 2)))
+        cpu_step, cpu_kind, cpu_how = reference_step(hxs)
         best = 1e30
         for _ in range(3):
             t0 = time.perf_counter()
-            O.eval_ir(ir, {"_v0": hxs})
-            O.eval_ir(("scan", "+", ("var", "_v0")), {"_v0": hxs})
+            cpu_step()
             best = min(best, time.perf_counter() - t0)
-        cpu = {"value": 2 * m / best, "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": f"{m} float64 elements, best of 3 (NumPy runs these ops on one core; host has {os.cpu_count()} cpus)"}
+        cpu = {"value": 2 * m / best, "unit": UNIT, "cores": 1, "kind": cpu_kind,
+               "sample": f"{m} float64 elements, best of 3 ({cpu_how}; NumPy runs these ops on one core; host has {os.cpu_count()} cpus)"}
 
     if rank == 0:
         line = {
