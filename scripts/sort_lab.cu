@@ -1,0 +1,222 @@
+// Development harness for the packed radix pass (klongpy_b200/csrc/kgb_sort_packed.cuh): runs the whole packed sort on
+// the three key sets of BASELINE config 3 at n keys, checks the permutation against cub::DeviceRadixSort (stable) and
+// prints per-kernel times.  Geometry comes from -DKGB_PK_CT/-DKGB_PK_KPT/-DKGB_PK_LBT/-DKGB_PK_OCC, so one binary per
+// variant (scripts/build_sort_lab.sh builds them in parallel; scripts/run_sort_lab.sh runs them on the GPU box).
+//   sort_lab [n=100000000] [reps=5]
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <numeric>
+#include <random>
+#include <vector>
+
+#include "kgb_sort_packed.cuh"
+
+namespace kgb {  // the library's error plumbing is not linked into the lab
+void set_error(const char*, ...) {}
+int current_device() { return 0; }
+int sm_count() { return 148; }
+}  // namespace kgb
+
+using namespace kgb;
+using namespace kgb::pk;
+
+#define CK(x)                                                                                   \
+    do {                                                                                        \
+        cudaError_t e_ = (x);                                                                   \
+        if (e_ != cudaSuccess) {                                                                \
+            printf("CUDA error %s at %s:%d: %s\n", #x, __FILE__, __LINE__, cudaGetErrorString(e_)); \
+            exit(2);                                                                            \
+        }                                                                                       \
+    } while (0)
+
+constexpr int CT = KGB_PK_CT, KPT = KGB_PK_KPT, LBT = KGB_PK_LBT, OCC = KGB_PK_OCC, T = CT * KPT;
+
+__global__ void enc_iota(const i64* k, u64* enc, u32* pos, u64 n) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        enc[i] = key_from_i64(k[i]);
+        pos[i] = (u32)i;
+    }
+}
+__global__ void compare(const i64* got, const u32* ref, u64 n, unsigned long long* bad, unsigned long long* first_bad) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        if (got[i] != (i64)ref[i]) {
+            atomicAdd(bad, 1ull);
+            atomicMin(first_bad, (unsigned long long)i);
+        }
+    }
+}
+
+__host__ __device__ inline u64 mix64(u64 x) {
+    x += 0x9e3779b97f4a7c15ull;
+    x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
+    x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+    return x ^ (x >> 31);
+}
+// pseudo-random permutation of [0, n): 4-round Feistel network on 2*hb bits, cycle-walked into range
+__device__ inline u64 feistel(u64 x, int hb, u64 seed) {
+    const u64 m = (1ull << hb) - 1;
+    u64 l = x >> hb, r = x & m;
+    for (int k = 0; k < 4; k++) {
+        const u64 t = l ^ (mix64(r + seed * 977 + k) & m);
+        l = r;
+        r = t;
+    }
+    return (l << hb) | r;
+}
+__global__ void gen_keys(i64* k, u64 n, int ds, int hb) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        i64 v;
+        if (ds == 0) {
+            u64 x = i;
+            do x = feistel(x, hb, 7); while (x >= n);
+            v = (i64)x;
+        } else if (ds == 1) {
+            v = (i64)(mix64(i) % 10000);
+        } else if (ds == 2) {
+            v = (i64)mix64(i);
+        } else if (ds == 3) {
+            v = (i64)(mix64(i) >> 24) - (1ll << 39);
+        } else {
+            v = (i64)(mix64(i) % 3) * 1000003ll - 7;
+        }
+        k[i] = v;
+    }
+}
+
+struct Times {
+    float total, analyze, hist, passes, pass[MAXP], fix;
+};
+
+static int run_sort(const i64* d_keys, u64 n, i64* d_idx, void* ws, u64* buf0, u64* buf1, int sms, Times* tm, Plan* plan_out,
+                    bool per_kernel) {
+    cudaStream_t st = 0;
+    Ws w = carve_ws<T>(ws, n);
+    cudaEvent_t ev[16];
+    for (auto& e : ev) CK(cudaEventCreate(&e));
+    int ne = 0;
+    CK(cudaEventRecord(ev[ne++], st));
+    CK(packed_analyze<T>(d_keys, KGB_I64, n, w, sms, st));
+    u64 h[2];
+    CK(cudaMemcpyAsync(h, w.ctl, 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaEventRecord(ev[ne++], st));
+    Plan p = make_plan(h[0], h[1], n);
+    *plan_out = p;
+    u64* fin = nullptr;
+    (void)per_kernel;
+    cudaEvent_t pe[MAXP + 1];
+    for (auto& e : pe) CK(cudaEventCreate(&e));
+    CK((packed_passes<CT, KPT, LBT, OCC>(d_keys, KGB_I64, n, p, 0, d_idx, nullptr, nullptr, w, buf0, buf1, p.prefix ? &fin : nullptr, sms, st, pe)));
+    CK(cudaEventRecord(ev[ne++], st));
+    int over = 0;
+    if (p.prefix) {
+        FixArgs f{};
+        f.sorted = fin;
+        f.keys = d_keys;
+        f.idx_out = d_idx;
+        f.flags = w.ctl + 2;
+        f.n = (u32)n;
+        f.pb = p.pb;
+        f.dtype = KGB_I64;
+        fixup_kernel<8><<<sms * 8, 256, 0, st>>>(f);
+        CK(cudaGetLastError());
+        u64 fl = 0;
+        CK(cudaMemcpyAsync(&fl, w.ctl + 2, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        over = (int)fl;
+    }
+    CK(cudaEventRecord(ev[ne++], st));
+    CK(cudaEventSynchronize(ev[ne - 1]));
+    CK(cudaEventElapsedTime(&tm->total, ev[0], ev[ne - 1]));
+    CK(cudaEventElapsedTime(&tm->analyze, ev[0], ev[1]));
+    CK(cudaEventElapsedTime(&tm->passes, ev[1], ev[2]));
+    if (p.npass > 0) {
+        CK(cudaEventElapsedTime(&tm->hist, ev[1], pe[0]));
+        for (int i = 0; i < p.npass; i++) CK(cudaEventElapsedTime(&tm->pass[i], pe[i], pe[i + 1]));
+    }
+    for (auto& e : pe) CK(cudaEventDestroy(e));
+    CK(cudaEventElapsedTime(&tm->fix, ev[2], ev[3]));
+    for (auto& e : ev) CK(cudaEventDestroy(e));
+    return over;
+}
+
+int main(int argc, char** argv) {
+    const u64 n = argc > 1 ? strtoull(argv[1], 0, 10) : 100000000ull;
+    const int reps = argc > 2 ? atoi(argv[2]) : 5;
+    int sms = 0;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
+    printf("sort_lab CT=%d KPT=%d LBT=%d OCC=%d ATOM=%d LB=%d  T=%d  n=%llu sms=%d\n", CT, KPT, LBT, OCC, KGB_PK_ATOM, KGB_PK_LB, T,
+           (unsigned long long)n, sms);
+    {
+        cudaFuncAttributes fa;
+        CK(cudaFuncGetAttributes(&fa, pass_kernel<9, CT, KPT, LBT, 0, 8, OCC>));
+        printf("pass<9,mid>: %d regs, %zu B local, smem %zu B\n", fa.numRegs, fa.localSizeBytes, sizeof(PassSmem<9, CT, KPT, LBT>));
+    }
+    i64 *d_keys, *d_idx;
+    u64 *d_enc, *d_enc2, *buf0, *buf1;
+    u32 *d_pos, *d_ref;
+    void *ws, *cub_ws = nullptr;
+    unsigned long long* d_bad;
+    CK(cudaMalloc(&d_keys, n * 8));
+    CK(cudaMalloc(&d_idx, n * 8));
+    CK(cudaMalloc(&d_enc, n * 8));
+    CK(cudaMalloc(&d_enc2, n * 8));
+    CK(cudaMalloc(&buf0, n * 8));
+    CK(cudaMalloc(&buf1, n * 8));
+    CK(cudaMalloc(&d_pos, n * 4));
+    CK(cudaMalloc(&d_ref, n * 4));
+    CK(cudaMalloc(&d_bad, 16));
+    const size_t wsb = carve_ws<T>(nullptr, n).total;
+    CK(cudaMalloc(&ws, wsb));
+    size_t cub_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, d_enc, d_enc2, d_pos, d_ref, (long long)n);
+    CK(cudaMalloc(&cub_ws, cub_bytes));
+    const char* names[] = {"perm", "10k", "rand64", "rand40", "dup3"};
+    for (int ds = 0; ds < 5; ds++) {
+        {
+            int hb = 1;
+            while ((1ull << (2 * hb)) < n) hb++;
+            gen_keys<<<1184, 256>>>(d_keys, n, ds, hb);
+            CK(cudaGetLastError());
+        }
+        enc_iota<<<1184, 256>>>(d_keys, d_enc, d_pos, n);
+        cudaEvent_t e0, e1;
+        CK(cudaEventCreate(&e0));
+        CK(cudaEventCreate(&e1));
+        float cub_ms = 1e9f;
+        for (int r = 0; r < 2; r++) {
+            CK(cudaEventRecord(e0));
+            cub::DeviceRadixSort::SortPairs(cub_ws, cub_bytes, d_enc, d_enc2, d_pos, d_ref, (long long)n);
+            CK(cudaEventRecord(e1));
+            CK(cudaEventSynchronize(e1));
+            float ms;
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            cub_ms = std::min(cub_ms, ms);
+        }
+        Times best{};
+        best.total = 1e9f;
+        Plan p{};
+        int over = 0;
+        for (int r = 0; r < reps + 1; r++) {
+            Times tm{};
+            over = run_sort(d_keys, n, d_idx, ws, buf0, buf1, sms, &tm, &p, false);
+            if (r > 0 && tm.total < best.total) best = tm;
+        }
+        unsigned long long bad[2] = {0, ~0ull};
+        CK(cudaMemcpy(d_bad, bad, 16, cudaMemcpyHostToDevice));
+        compare<<<1184, 256>>>(d_idx, d_ref, n, d_bad, d_bad + 1);
+        CK(cudaMemcpy(bad, d_bad, 16, cudaMemcpyDeviceToHost));
+        printf("%-7s npass=%d bits=[", names[ds], p.npass);
+        for (int i = 0; i < p.npass; i++) printf("%d%s", p.bits[i], i + 1 < p.npass ? "," : "");
+        printf("] lo=%d live=%d pb=%d prefix=%d | total %.3f ms (analyze+sync %.3f, hist %.3f, passes", p.lo, p.live, p.pb, p.prefix,
+               best.total, best.analyze, best.hist);
+        for (int i = 0; i < p.npass; i++) printf(" %.3f", best.pass[i]);
+        printf(", fixup %.3f) cub %.3f ms | mismatches %llu first %lld over=%d\n", best.fix, cub_ms, bad[0],
+               bad[0] ? (long long)bad[1] : -1ll, over);
+        fflush(stdout);
+    }
+    return 0;
+}
