@@ -7,7 +7,7 @@
  * replaces (paths relative to the reference root).  All pointers are raw device addresses unless a
  * parameter is documented as host memory.  Outputs and workspaces are allocated by the caller (two-phase
  * `*_workspace_bytes` query); the library never owns result memory and never synchronises the stream
- * unless a function is documented as doing so.  Every function returns 0 on success and a negative
+ * unless a function is documented as doing so (kgb_argsort / kgb_group / kgb_unique_first / kgb_groupagg_f64 do).  Every function returns 0 on success and a negative
  * KGB_E* code on failure; kgb_last_error() returns a thread-local message.
  *
  * No torch types appear here.  `stream` is a CUstream / cudaStream_t passed as void*.
@@ -173,7 +173,11 @@ const char* kgb_expr_kernel_name(const kgb_expr* h);
 /* Replaces backend.argsort -> np.argsort (numpy_backend.py:75-80) behind kg_argsort's numeric fast
    path (writer.py:114-117).  Stable ascending LSD radix sort of (key, position); `descending` returns
    the stable ascending permutation reversed, which is the language contract (writer.py:97-108,
-   tests/test_suite.py:82).  idx_out: int64[n].  keys_sorted_out: optional (NULL) dtype-typed [n]. */
+   tests/test_suite.py:82).  idx_out: int64[n].  keys_sorted_out: optional (NULL) dtype-typed [n].
+   SYNCHRONISES `stream` for n >= 2^18: the varying key bits are read back once to pick the digit plan
+   (live key bits and position packed into one 64-bit word, 7..10-bit digits; csrc/kgb_sort_packed.cuh),
+   and keys wider than the packed word are read back once more after the prefix fix-up.  kgb_group,
+   kgb_unique_first and everything else built on the sort inherit this. */
 int kgb_argsort_workspace_bytes(int32_t dtype, int64_t n, size_t* out_bytes);
 int kgb_argsort(const void* keys, int32_t dtype, int64_t n, int32_t descending, int64_t* idx_out,
                 void* keys_sorted_out, void* workspace, size_t workspace_bytes, void* stream);

@@ -20,6 +20,7 @@
 #include <type_traits>
 
 #include "kgb_sort.cuh"
+#include "kgb_sort_packed.cuh"
 
 namespace kgb {
 
@@ -60,6 +61,7 @@ struct SortWs {
     u64* keys[2];
     u32* idx[2];
     size_t zero_bytes;  // hist + tickets + states are contiguous from `hist`
+    void* packed;       // control block, histograms and look-back words of the packed path (kgb_sort_packed.cuh)
     size_t total;
 };
 
@@ -86,6 +88,8 @@ static SortWs carve(void* ws, i64 n) {
         w.idx[b] = (u32*)(p + o);
         o += align_up((size_t)n * 4, 256);
     }
+    w.packed = p + o;
+    o += pk::carve_ws<KGB_PK_CT * KGB_PK_KPT>(nullptr, (u64)n).total;
     w.total = o;
     return w;
 }
@@ -833,12 +837,65 @@ static int sort_impl(const void* keys, i64 n, int descending, i64* idx_out, void
     return KGB_OK;
 }
 
+// Packed path (kgb_sort_packed.cuh): one analysis read of the keys, ONE host synchronisation to read the key range back
+// and choose the digit plan, then 16-byte-per-key passes.  Returns 1 when the sort was done, 0 when the caller must
+// run the general pass (keys too wide for this n, or a prefix tie too long for the fix-up), < 0 on error.
+static int sort_packed(const void* keys, int dtype, i64 n, int descending, i64* idx_out, void* keys_sorted_out,
+                       u64* enc_sorted_out, const SortWs& gw, cudaStream_t st) {
+    constexpr int T = KGB_PK_CT * KGB_PK_KPT;
+    const int sms = sm_count();
+    pk::Ws w = pk::carve_ws<T>(gw.packed, (u64)n);
+    KGB_CUDA_CHECK(pk::packed_analyze<T>(keys, dtype, (u64)n, w, sms, st));
+    u64 h[3];
+    KGB_CUDA_CHECK(cudaMemcpyAsync(h, w.ctl, sizeof h, cudaMemcpyDeviceToHost, st));
+    KGB_CUDA_CHECK(cudaStreamSynchronize(st));
+    const pk::Plan p = pk::make_plan(h[0], ~h[1], h[2], (u64)n);
+    if (p.npass < 0) return 0;
+    u64* fin = nullptr;
+    KGB_CUDA_CHECK((pk::packed_passes<KGB_PK_CT, KGB_PK_KPT, KGB_PK_LBT, KGB_PK_OCC>(
+        keys, dtype, (u64)n, p, descending, idx_out, keys_sorted_out, enc_sorted_out, w, gw.keys[0], gw.keys[1],
+        p.prefix ? &fin : nullptr, sms, st)));
+    if (!p.prefix) return 1;
+    pk::FixArgs f{};
+    f.sorted = fin;
+    f.keys = keys;
+    f.idx_out = idx_out;
+    f.keys_sorted_out = keys_sorted_out;
+    f.enc_sorted_out = enc_sorted_out;
+    f.flags = w.ctl + 3;
+    f.n = (u32)n;
+    f.pb = p.pb;
+    f.dtype = dtype;
+    f.descending = descending;
+    if (pk::key_width(dtype) == 8)
+        pk::fixup_kernel<8><<<sms * 8, 256, 0, st>>>(f);
+    else
+        pk::fixup_kernel<4><<<sms * 8, 256, 0, st>>>(f);
+    KGB_CUDA_CHECK(cudaGetLastError());
+    u64 over = 0;
+    KGB_CUDA_CHECK(cudaMemcpyAsync(&over, w.ctl + 3, 8, cudaMemcpyDeviceToHost, st));
+    KGB_CUDA_CHECK(cudaStreamSynchronize(st));
+    return over ? 0 : 1;
+}
+
 int sort_pairs(const void* keys, int dtype, i64 n, int descending, i64* idx_out, void* keys_sorted_out,
                u64* enc_sorted_out, void* ws, size_t ws_bytes, cudaStream_t st) {
     KGB_REQUIRE(current_device() >= 0, "kgb_init() has not been called on this thread");
     KGB_REQUIRE(n >= 0 && n < 0xffffffffll, "argsort: n must be below 2^32");
     if (n == 0) return KGB_OK;
     KGB_REQUIRE(keys && idx_out && ws && ws_bytes >= sort_ws_bytes(n), "argsort: null pointer or workspace too small");
+    {
+        // KGB200_SORT_PACKED=0 forces the general pass, KGB200_SORT_PACKED_MIN moves the size threshold (the tests run both)
+        const char* e = getenv("KGB200_SORT_PACKED");
+        const int packed_env = e ? (atoi(e) != 0) : 1;
+        const char* m = getenv("KGB200_SORT_PACKED_MIN");
+        const long long packed_min = m ? atoll(m) : (1ll << 18);
+        if (packed_env && n >= packed_min && n < (1ll << 30)) {
+            const SortWs gw = carve(ws, n);
+            const int rc = sort_packed(keys, dtype, n, descending, idx_out, keys_sorted_out, enc_sorted_out, gw, st);
+            if (rc != 0) return rc < 0 ? rc : KGB_OK;
+        }
+    }
     switch (dtype) {
         case KGB_F64: return sort_impl<KGB_F64>(keys, n, descending, idx_out, keys_sorted_out, enc_sorted_out, ws, st);
         case KGB_I64: return sort_impl<KGB_I64>(keys, n, descending, idx_out, keys_sorted_out, enc_sorted_out, ws, st);

@@ -25,6 +25,8 @@
 // Replaces np.argsort behind kg_argsort (klongpy/writer.py:97-122, klongpy/backends/numpy_backend.py:75-80).
 #pragma once
 #include "kgb_device.cuh"
+#include <cstdlib>
+
 #include "kgb_internal.h"
 
 namespace kgb {
@@ -32,15 +34,23 @@ namespace pk {
 
 constexpr int MAXP = 6;  // passes of one packed sort (<= 54 key bits at 9 bits per pass; the planner never needs more)
 constexpr int MINBITS = 7, MAXBITS = 10;
+constexpr int PLAN_MAXP = 5;  // passes a plan may use (n >= 2^14 leaves <= 50 key bits)
 constexpr int MAXBINS = 1 << MAXBITS;
 constexpr int ROLE_FIRST = 1, ROLE_LAST = 2;
 constexpr u32 NO_TILE = 0xffffffffu;
+constexpr int LB_PAD = 32;  // readable rows in front of tile 0's look-back words (the walk loads without bounds tests)
 
 #ifndef KGB_PK_ATOM
 #define KGB_PK_ATOM 0  // 1: warp digit counters are u32 updated with ATOMS.ADD; 0: u16 counters, leader LDS + STS
 #endif
+#ifndef KGB_PK_STATS
+#define KGB_PK_STATS 0  // 1 (lab only): count look-back rounds / steps and the compute threads' waits into PassArgs::stats
+#endif
+#ifndef KGB_PK_NOLB
+#define KGB_PK_NOLB 0
+#endif
 #ifndef KGB_PK_LB
-#define KGB_PK_LB 4    // look-back states fetched per chain and round
+#define KGB_PK_LB 16   // look-back states fetched per chain and round (capped so that a thread keeps <= 32 loads in flight)
 #endif
 
 struct PassArgs {
@@ -51,17 +61,18 @@ struct PassArgs {
     void* keys_sorted_out;  // LAST, optional: typed sorted keys
     u64* enc_sorted_out;    // LAST, optional: order-encoded sorted keys
     const u32* digit_base;  // [1 << BITS] exclusive global digit offsets of this pass
-    u64* states;            // [tiles][1 << BITS] look-back words
+    u32* states;            // [tiles][1 << BITS] look-back words of THIS pass (zeroed): [31:30] flag, [29:0] count
     u32* ticket;
     u32 n;
     int shift;              // bit position of this pass's digit inside the packed word
     int lo;                 // lowest live bit of the encoded key
     int pb;                 // position bits
     u64 kmask;              // mask of the live key field (after >> lo)
-    u64 enc_const;          // the bits all keys agree on (reconstructs encoded keys in the LAST pass)
-    u32 epoch;
+    u64 enc_base;           // smallest encoded key: the key field is (enc - enc_base) >> lo
+    u32 stagger_ns;         // CTA b starts b * stagger_ns late (keeps the CTAs out of lockstep, see the look-back group)
     int dtype;              // KGB_* (+ _RAW) code of the caller's keys
     int descending;
+    u64* stats;             // lab builds only (KGB_PK_STATS)
 };
 
 // ------------------------------------------------------------------------------------------- small device helpers
@@ -87,6 +98,35 @@ __device__ __forceinline__ void mbar_wait(u64* bar, u32 parity, bool sleep) {
             if (now - t0 > 4000000000ull) __trap();
         }
     }
+}
+// look-back word of one (tile, digit): n < 2^30, so flag and count share 32 bits and a thread can keep 32 of them in flight
+constexpr u32 LB_AGG = 1u << 30, LB_PREFIX = 2u << 30, LB_COUNT = (1u << 30) - 1u;
+__device__ __forceinline__ u32 ld_relaxed_u32(const u32* p) {
+    u32 v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(u32* p, u32 v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+template <int N> __device__ __forceinline__ void ld_relaxed_vec(const u32* p, u32 (&w)[N]) {
+    static_assert(N == 1 || N == 2 || N == 4, "vector width");
+    if (N == 1)
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(w[0]) : "l"(p) : "memory");
+    else if (N == 2)
+        asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(w[0]), "=r"(w[N > 1 ? 1 : 0]) : "l"(p) : "memory");
+    else
+        asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(w[0]), "=r"(w[N > 1 ? 1 : 0]), "=r"(w[N > 2 ? 2 : 0]), "=r"(w[N > 3 ? 3 : 0]) : "l"(p) : "memory");
+}
+template <int N> __device__ __forceinline__ void st_relaxed_vec(u32* p, const u32* w) {
+    if (N == 1)
+        asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(w[0]) : "memory");
+    else if (N == 2)
+        asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(w[0]), "r"(w[N > 1 ? 1 : 0]) : "memory");
+    else
+        asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(w[0]), "r"(w[N > 1 ? 1 : 0]),
+                     "r"(w[N > 2 ? 2 : 0]), "r"(w[N > 3 ? 3 : 0]) : "memory");
 }
 template <int N> __device__ __forceinline__ void bar_named(int id) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(N) : "memory");
@@ -134,8 +174,11 @@ template <int BITS, int CT, int KPT, int LBT> struct PassCfg {
     static constexpr int NA = BINS / E;                     // threads that own digits in the totals step
     static constexpr int NAW = (NA + 31) / 32;
     static constexpr int ELB = BINS > LBT ? BINS / LBT : 1; // chains per look-back thread
-    static constexpr int LBN = ELB >= 8 ? (KGB_PK_LB < 2 ? KGB_PK_LB : 2) : KGB_PK_LB;  // states per chain and round
+    static constexpr int GS = ELB < 4 ? ELB : 4;            // digits whose look-back words travel in one vector access
+    static constexpr int NG = ELB / GS;
+    static constexpr int LBN = (32 / ELB) < KGB_PK_LB ? (32 / ELB > 0 ? 32 / ELB : 1) : KGB_PK_LB;  // tiles per group and round
     static_assert(T <= 32768, "tile offsets are 16-bit");
+    static_assert(ELB == 1 || ELB == 2 || ELB == 4 || ELB == 8, "look-back digits per thread");
     static_assert(BINS % E == 0 && (BINS <= CT || BINS % CT == 0) && (BINS <= LBT || BINS % LBT == 0), "digit ownership");
 };
 
@@ -169,9 +212,20 @@ __global__ void __launch_bounds__(CT + LBT, OCC) pass_kernel(const PassArgs a) {
     const u32 n = a.n;
     const u32 ntiles = (n + T - 1) / T;
     const int shift = a.shift;
-    const u32 epoch = a.epoch;
 
     if (tid == 0) {
+        // Out of lockstep: if all CTAs publish their tile counts at the same moment, tile t must walk back over ~grid/2
+        // aggregates to find an inclusive prefix.  Staggered by tile_period / grid, predecessor t-k published k * stagger
+        // earlier and a walk ends within a round or two.
+        if (a.stagger_ns && blockIdx.x) {
+            unsigned long long t0, now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            const unsigned long long wait = (unsigned long long)blockIdx.x * a.stagger_ns;
+            do {
+                __nanosleep(200);
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            } while (now - t0 < wait);
+        }
         mbar_init(&sm.cnt_bar[0], 1);
         mbar_init(&sm.cnt_bar[1], 1);
         mbar_init(&sm.gb_bar[0], LBT);
@@ -187,77 +241,134 @@ __global__ void __launch_bounds__(CT + LBT, OCC) pass_kernel(const PassArgs a) {
 
     if (tid >= CT) {
         // ============================================================ look-back group
+        // Thread lt owns ELB ADJACENT digits, in groups of GS <= 4 whose words travel in one vector load / store.  A round
+        // fetches the LBN nearest unvisited predecessor tiles of every unfinished group (independent loads: one L2 round
+        // trip) and folds them front to back: a tile whose words are not all there yet ends the round (poll again), a
+        // tile carrying inclusive prefixes ends the walk.  A look-back word is never 0 once written (flag 01 or 10 on
+        // top), an aggregate is >= 2^30 and a prefix >= 2^31, so "all present" / "all prefixes" are one unsigned min / max
+        // each; the words of a group are written together, and a reader that catches them half-way (some prefixes, some
+        // aggregates) simply polls again.  The raw words are summed, flags included, and the flags' contribution
+        // ((tiles folded + 1) << 30) comes off at the end — everything is arithmetic modulo 2^32 and every true count is
+        // below 2^30.  The rows in FRONT of tile 0 are readable padding (never interpreted: tile 0 always carries
+        // prefixes), so the loads need no bounds test.
+        constexpr int GS = C::GS, NG = C::NG;
         const int lt = tid - CT;
+        const int d0 = lt * ELB;             // first digit of this thread
+        const bool owner = d0 < BINS;
         u32 dbase[ELB];
 #pragma unroll
-        for (int e = 0; e < ELB; e++) {
-            const int d = lt + e * LBT;
-            dbase[e] = d < BINS ? a.digit_base[d] : 0u;
-        }
+        for (int e = 0; e < ELB; e++) dbase[e] = owner ? a.digit_base[d0 + e] : 0u;
+#if KGB_PK_STATS
+        unsigned long long st_rounds = 0, st_steps = 0, st_tiles = 0;
+#endif
         for (u32 i = 0;; i++) {
             const u32 s = i & 1u;
             mbar_wait(&sm.cnt_bar[s], (i >> 1) & 1u, true);
             const u32 tile = sm.tile_of[s];
             if (tile == NO_TILE) break;
-            u32 excl[ELB], back[ELB];  // running exclusive prefix; number of predecessors already folded in
-            bool done[ELB];
+            u32 excl[ELB];
 #pragma unroll
-            for (int e = 0; e < ELB; e++) {
-                excl[e] = 0;
-                back[e] = 0;
-                done[e] = (tile == 0) || (lt + e * LBT >= BINS);
-            }
-            u32 spins = 0;
-            for (;;) {
-                bool all = true;
+            for (int e = 0; e < ELB; e++) excl[e] = 0;
+            if (owner && tile > 0) {
+                const u32* sp[NG];   // group g's words of the nearest unvisited predecessor
+                u32 adv[NG];
+                bool go[NG];
 #pragma unroll
-                for (int e = 0; e < ELB; e++) all = all && done[e];
-                if (all) break;
-                u64 w[ELB][LBN];
-#pragma unroll
-                for (int e = 0; e < ELB; e++) {
-                    const int d = lt + e * LBT;
-#pragma unroll
-                    for (int j = 0; j < LBN; j++) {
-                        const u32 bk = back[e] + (u32)j;  // predecessor tile - 1 - bk
-                        w[e][j] = (!done[e] && bk < tile) ? ld_relaxed_u64(&a.states[(size_t)(tile - 1u - bk) * BINS + d])
-                                                          : lb_pack(KGB_LB_PREFIX, epoch, 0);
-                    }
+                for (int g = 0; g < NG; g++) {
+                    sp[g] = a.states + (size_t)tile * BINS + d0 + g * GS - BINS;
+                    adv[g] = 0;
+                    go[g] = !KGB_PK_NOLB;
                 }
-                bool progress = false;
+                u32 spins = 0;
+                for (;;) {
+                    bool any = false;
 #pragma unroll
-                for (int e = 0; e < ELB; e++) {
-                    if (!done[e]) {
-                        bool stop = false;
+                    for (int g = 0; g < NG; g++) any = any || go[g];
+                    if (!any) break;
+                    u32 w[NG][LBN][GS];
 #pragma unroll
-                        for (int j = 0; j < LBN; j++) {
-                            if (!stop && !done[e]) {
-                                const u64 f = lb_flag(w[e][j], epoch);
-                                if (f == 0) {
-                                    stop = true;  // not published yet: retry from here next round
-                                } else {
-                                    excl[e] += (u32)lb_count(w[e][j]);
-                                    back[e] += 1u;
-                                    progress = true;
-                                    if (f == KGB_LB_PREFIX || back[e] >= tile) done[e] = true;
-                                }
-                            }
+                    for (int g = 0; g < NG; g++) {
+                        if (go[g]) {
+#pragma unroll
+                            for (int j = 0; j < LBN; j++) ld_relaxed_vec<GS>(sp[g] - (size_t)j * BINS, w[g][j]);
                         }
                     }
-                }
-                if (!progress && ++spins > (1u << 24)) __trap();  // a predecessor never published: fail, do not hang
-            }
+                    u32 progress = 0;
 #pragma unroll
-            for (int e = 0; e < ELB; e++) {
-                const int d = lt + e * LBT;
-                if (d < BINS) {
-                    const u32 cd = sm.cntd[s][d];
-                    if (tile > 0) st_relaxed_u64(&a.states[(size_t)tile * BINS + d], lb_pack(KGB_LB_PREFIX, epoch, (u64)excl[e] + (cd >> 16)));
-                    sm.gbase[s][d] = dbase[e] + excl[e] - (cd & 0xffffu);
+                    for (int g = 0; g < NG; g++) {
+                        if (go[g]) {
+                            bool walk = true;
+                            u32 a_g = 0;
+#pragma unroll
+                            for (int j = 0; j < LBN; j++) {
+                                u32 mn = w[g][j][0], mx = w[g][j][0];
+#pragma unroll
+                                for (int e = 1; e < GS; e++) {
+                                    mn = min(mn, w[g][j][e]);
+                                    mx = max(mx, w[g][j][e]);
+                                }
+                                const bool all_pf = mn >= LB_PREFIX;
+                                const bool ready = mn >= LB_AGG && (all_pf || mx < LB_PREFIX);
+                                const bool take = walk && ready;
+#pragma unroll
+                                for (int e = 0; e < GS; e++) excl[g * GS + e] += take ? w[g][j][e] : 0u;
+                                a_g += take ? 1u : 0u;
+                                if (take && all_pf) go[g] = false;
+                                walk = take && !all_pf;
+                            }
+                            sp[g] -= (size_t)a_g * BINS;
+                            adv[g] += a_g;
+                            progress |= a_g;
+                        }
+                    }
+#if KGB_PK_STATS
+                    if (lt == 0) {
+                        st_rounds++;
+                    }
+#endif
+                    if (!progress) {
+                        __nanosleep(100);
+                        if (++spins > (1u << 24)) __trap();  // a predecessor never published: fail, do not hang
+                    }
+                }
+#pragma unroll
+                for (int g = 0; g < NG; g++) {
+#pragma unroll
+                    for (int e = 0; e < GS; e++) excl[g * GS + e] -= (adv[g] + 1u) << 30;
+                }
+#if KGB_PK_STATS
+                if (lt == 0) st_steps += adv[0];
+#endif
+#if KGB_PK_NOLB
+#pragma unroll
+                for (int e = 0; e < ELB; e++) excl[e] = 0;
+#endif
+            }
+#if KGB_PK_STATS
+            if (lt == 0) st_tiles++;
+#endif
+            if (owner) {
+                u32 pf[ELB];
+#pragma unroll
+                for (int e = 0; e < ELB; e++) {
+                    const u32 cd = sm.cntd[s][d0 + e];
+                    pf[e] = LB_PREFIX | ((excl[e] + (cd >> 16)) & LB_COUNT);
+                    sm.gbase[s][d0 + e] = dbase[e] + excl[e] - (cd & 0xffffu);
+                }
+                if (tile > 0) {
+#pragma unroll
+                    for (int g = 0; g < NG; g++) st_relaxed_vec<GS>(&a.states[(size_t)tile * BINS + d0 + g * GS], &pf[g * GS]);
                 }
             }
             mbar_arrive(&sm.gb_bar[s]);
         }
+#if KGB_PK_STATS
+        if (lt == 0 && a.stats) {
+            atomicAdd((unsigned long long*)&a.stats[0], st_rounds);
+            atomicAdd((unsigned long long*)&a.stats[1], st_steps);
+            atomicAdd((unsigned long long*)&a.stats[2], st_tiles);
+        }
+#endif
         return;
     }
 
@@ -265,6 +376,10 @@ __global__ void __launch_bounds__(CT + LBT, OCC) pass_kernel(const PassArgs a) {
     const u64 posmask = (a.pb >= 64) ? ~0ull : ((1ull << a.pb) - 1ull);
     u64 key[KPT];
     const int wslot = warp * (KPT * 32);
+    const u32 lt_mask = (1u << lane) - 1u;
+#if KGB_PK_STATS
+    unsigned long long st_wait = 0;
+#endif
 
     // request tile t's keys from HBM into `key` (raw for the FIRST pass; finished by `finish_load`)
     auto load_tile = [&](u32 t) {
@@ -274,8 +389,13 @@ __global__ void __launch_bounds__(CT + LBT, OCC) pass_kernel(const PassArgs a) {
         if (FIRST) {
             if (KW == 8) {
                 const u64* p = reinterpret_cast<const u64*>(a.in_keys) + base + wslot + lane;
+                if (full) {
 #pragma unroll
-                for (int k = 0; k < KPT; k++) key[k] = (full || base + wslot + k * 32 + lane < n) ? __ldcs(p + k * 32) : 0ull;
+                    for (int k = 0; k < KPT; k++) key[k] = __ldcs(p + k * 32);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < KPT; k++) key[k] = (base + wslot + k * 32 + lane < n) ? __ldcs(p + k * 32) : 0ull;
+                }
             } else {
                 const u32* p = reinterpret_cast<const u32*>(a.in_keys) + base + wslot + lane;
 #pragma unroll
@@ -283,44 +403,102 @@ __global__ void __launch_bounds__(CT + LBT, OCC) pass_kernel(const PassArgs a) {
             }
         } else {
             const u64* p = a.src + base + wslot + lane;
+            if (full) {
 #pragma unroll
-            for (int k = 0; k < KPT; k++) key[k] = (full || base + wslot + k * 32 + lane < n) ? __ldcs(p + k * 32) : ~0ull;
+                for (int k = 0; k < KPT; k++) key[k] = __ldcs(p + k * 32);
+            } else {
+#pragma unroll
+                for (int k = 0; k < KPT; k++) key[k] = (base + wslot + k * 32 + lane < n) ? __ldcs(p + k * 32) : ~0ull;
+            }
         }
     };
     auto finish_load = [&](u32 t) {
         if (FIRST) {
             const u32 base = t * (u32)T;
+            const u64 ebase = a.enc_base, km = a.kmask;
+            const int lo = a.lo, pb = a.pb;
+            auto pack_all = [&](auto enc) {  // one instantiation per key type: the dtype test runs once per tile, not per key
 #pragma unroll
-            for (int k = 0; k < KPT; k++) {
-                const u32 g = base + wslot + k * 32 + lane;
-                const u64 e = enc_rt(a.dtype, key[k]);
-                key[k] = (g < n) ? ((((e >> a.lo) & a.kmask) << a.pb) | (u64)g) : ~0ull;
+                for (int k = 0; k < KPT; k++) {
+                    const u32 g = base + wslot + k * 32 + lane;
+                    const u64 e = enc(key[k]) - ebase;
+                    key[k] = (g < n) ? ((((e >> lo) & km) << pb) | (u64)g) : ~0ull;
+                }
+            };
+            switch (a.dtype) {
+                case KGB_I64: pack_all([](u64 r) { return r ^ 0x8000000000000000ull; }); break;
+                case KGB_F64: pack_all([](u64 r) { return KeyCodec<KGB_F64>::enc(__longlong_as_double((i64)r)); }); break;
+                case KGB_F64_RAW: pack_all([](u64 r) { return KeyCodec<KGB_F64_RAW>::enc(__longlong_as_double((i64)r)); }); break;
+                case KGB_I32: pack_all([](u64 r) { return (u64)((u32)r ^ 0x80000000u); }); break;
+                case KGB_F32: pack_all([](u64 r) { return KeyCodec<KGB_F32>::enc(__int_as_float((int)(u32)r)); }); break;
+                default: pack_all([](u64 r) { return KeyCodec<KGB_F32_RAW>::enc(__int_as_float((int)(u32)r)); }); break;
             }
         }
     };
-    // tile parked in stage st -> global, as digit-contiguous runs
+    // tile parked in stage st -> global, as digit-contiguous runs.  Interior tiles and the plain roles (middle pass;
+    // ascending permutation without key outputs) take loops without per-key tests.
     auto write_out = [&](u32 li, u32 t) {
         const u32 st = li & 1u;
-        mbar_wait(&sm.gb_bar[st], (li >> 1) & 1u, false);
+        {
+            const u32 bar = smem_u32(&sm.gb_bar[st]), parity = (li >> 1) & 1u;
+            u32 done = 0, spins = 0;
+            while (!done) {
+                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+#if KGB_PK_STATS
+                if (!done) st_wait++;
+#endif
+                if (!done && ++spins > (1u << 26)) __trap();  // the look-back group never answered: fail, do not hang
+            }
+        }
         const u32 base = t * (u32)T;
         const u32 tile_n = (n - base) < (u32)T ? (n - base) : (u32)T;
+        const u64* stg = sm.stage[st];
+        const u32* gb = sm.gbase[st];
+        const bool plain = !LAST || (!a.descending && !a.keys_sorted_out && !a.enc_sorted_out);
+        if (tile_n == (u32)T && plain) {
 #pragma unroll
-        for (int j = 0; j < KPT; j++) {
-            const u32 p = j * CT + tid;
-            if (p < tile_n) {
-                const u64 v = sm.stage[st][p];
-                const u32 d = (u32)(v >> shift) & (BINS - 1);
-                const u32 g = sm.gbase[st][d] + p;
-                if (LAST) {
-                    const u32 op = a.descending ? (n - 1u - g) : g;
-                    a.idx_out[op] = (i64)(v & posmask);
-                    if (a.keys_sorted_out || a.enc_sorted_out) {
-                        const u64 enc = (((v >> a.pb) & a.kmask) << a.lo) | a.enc_const;
-                        if (a.enc_sorted_out) a.enc_sorted_out[op] = enc;
-                        if (a.keys_sorted_out) dec_store_rt(a.dtype, a.keys_sorted_out, op, enc);
-                    }
-                } else {
+            for (int j = 0; j < KPT; j++) {
+                const u32 p = j * CT + tid;
+                const u64 v = stg[p];
+                const u32 g = gb[(u32)(v >> shift) & (BINS - 1)] + p;
+                if (LAST)
+                    a.idx_out[g] = (i64)(v & posmask);
+                else
                     a.dst[g] = v;
+            }
+        } else if (LAST && tile_n == (u32)T) {  // grade-down and/or sorted keys wanted
+#pragma unroll
+            for (int j = 0; j < KPT; j++) {
+                const u32 p = j * CT + tid;
+                const u64 v = stg[p];
+                const u32 g = gb[(u32)(v >> shift) & (BINS - 1)] + p;
+                const u32 op = a.descending ? (n - 1u - g) : g;
+                a.idx_out[op] = (i64)(v & posmask);
+                if (a.keys_sorted_out || a.enc_sorted_out) {
+                    const u64 enc = (((v >> a.pb) & a.kmask) << a.lo) + a.enc_base;
+                    if (a.enc_sorted_out) a.enc_sorted_out[op] = enc;
+                    if (a.keys_sorted_out) dec_store_rt(a.dtype, a.keys_sorted_out, op, enc);
+                }
+            }
+        } else {  // the ragged last tile
+#pragma unroll 1
+            for (int j = 0; j < KPT; j++) {
+                const u32 p = j * CT + tid;
+                if (p < tile_n) {
+                    const u64 v = stg[p];
+                    const u32 g = gb[(u32)(v >> shift) & (BINS - 1)] + p;
+                    if (LAST) {
+                        const u32 op = a.descending ? (n - 1u - g) : g;
+                        a.idx_out[op] = (i64)(v & posmask);
+                        if (a.keys_sorted_out || a.enc_sorted_out) {
+                            const u64 enc = (((v >> a.pb) & a.kmask) << a.lo) + a.enc_base;
+                            if (a.enc_sorted_out) a.enc_sorted_out[op] = enc;
+                            if (a.keys_sorted_out) dec_store_rt(a.dtype, a.keys_sorted_out, op, enc);
+                        }
+                    } else {
+                        a.dst[g] = v;
+                    }
                 }
             }
         }
@@ -336,32 +514,32 @@ __global__ void __launch_bounds__(CT + LBT, OCC) pass_kernel(const PassArgs a) {
         if (tid == 0) sm.tile_slot[(i + 1) & 1u] = atomicAdd(a.ticket, 1u);
         finish_load(tile);
         // ---- rank: warp w owns slots [w*32*KPT, (w+1)*32*KPT), key k of lane l is slot w*32*KPT + k*32 + l.
-        // Three sweeps so that the ballots, the counter updates and the shuffles of a thread are each issued back to back.
+        // Row k: BITS ballots find the lanes with the same digit; EVERY lane then reads the warp's running count of its
+        // digit and writes back count + (number of peers) — peers read and write the same values, so no leader election,
+        // no branch and no shuffle is needed; the rank inside the tile's digit group follows after the totals step.
         u32 rank[KPT];
         {
-            const u32 lt = (1u << lane) - 1u;
-            u32 peers[KPT];
-#pragma unroll
-            for (int k = 0; k < KPT; k++) peers[k] = digit_peers<BITS>((u32)(key[k] >> shift) & (BINS - 1));
+            wcount_t* wh = &sm.whist[warp][0];
 #pragma unroll
             for (int k = 0; k < KPT; k++) {
                 const u32 d = (u32)(key[k] >> shift) & (BINS - 1);
-                const bool leader = (peers[k] & lt) == 0u;
-                rank[k] = 0;
-#if KGB_PK_ATOM
-                if (leader) rank[k] = atomicAdd(&sm.whist[warp][d], (u32)__popc(peers[k]));
-#else
-                if (leader) {
-                    const u32 c = sm.whist[warp][d];
-                    rank[k] = c;
-                    sm.whist[warp][d] = (wcount_t)(c + (u32)__popc(peers[k]));
-                }
-                __syncwarp();  // the next row's leader of the same digit may be another lane
-#endif
-            }
+                u32 peers = 0xffffffffu;
 #pragma unroll
-            for (int k = 0; k < KPT; k++)
-                rank[k] = __shfl_sync(0xffffffffu, rank[k], __ffs(peers[k]) - 1) + __popc(peers[k] & lt);
+                for (int b = 0; b < BITS; b++) {
+                    // test bit b, vote, keep the lanes that agree with this lane: peers &= ballot ^ (bit ? 0 : ~0)
+                    asm("{\n\t.reg .pred p;\n\t.reg .b32 t, m, nb;\n\t"
+                        "and.b32 t, %1, %2;\n\t"
+                        "setp.ne.u32 p, t, 0;\n\t"
+                        "vote.sync.ballot.b32 m, p, 0xffffffff;\n\t"
+                        "selp.b32 nb, 0, -1, p;\n\t"
+                        "lop3.b32 %0, %0, m, nb, 0x60;\n\t}"
+                        : "+r"(peers) : "r"(d), "r"(1u << b));
+                }
+                const u32 c = wh[d];
+                rank[k] = c + (u32)__popc(peers & lt_mask);
+                wh[d] = (wcount_t)(c + (u32)__popc(peers));
+                __syncwarp();  // the next row reads what this row wrote (other lanes may hold the digit then)
+            }
         }
         bar_named<CT>(1);  // B: warp histograms complete
         // ---- digit totals: exclusive offsets across warps, tile count, publish, exclusive digit offsets in the tile
@@ -379,7 +557,7 @@ __global__ void __launch_bounds__(CT + LBT, OCC) pass_kernel(const PassArgs a) {
                 }
                 cnt[e] = run;
                 tsum += run;
-                st_relaxed_u64(&a.states[(size_t)tile * BINS + d], lb_pack(tile == 0 ? KGB_LB_PREFIX : KGB_LB_AGG, epoch, run));
+                st_relaxed_u32(&a.states[(size_t)tile * BINS + d], (tile == 0 ? LB_PREFIX : LB_AGG) | run);
             }
             inc = tsum;
 #pragma unroll
@@ -407,11 +585,15 @@ __global__ void __launch_bounds__(CT + LBT, OCC) pass_kernel(const PassArgs a) {
             mbar_arrive(&sm.cnt_bar[st]);  // hand the tile to the look-back group
         }
         // ---- scatter into tile-sorted order
+        {
+            const wcount_t* wh = &sm.whist[warp][0];
+            const u32* cd = sm.cntd[st];
+            u64* stg = sm.stage[st];
 #pragma unroll
-        for (int k = 0; k < KPT; k++) {
-            const u32 d = (u32)(key[k] >> shift) & (BINS - 1);
-            const u32 p = (sm.cntd[st][d] & 0xffffu) + sm.whist[warp][d] + rank[k];
-            sm.stage[st][p] = key[k];
+            for (int k = 0; k < KPT; k++) {
+                const u32 d = (u32)(key[k] >> shift) & (BINS - 1);
+                stg[(cd[d] & 0xffffu) + wh[d] + rank[k]] = key[k];
+            }
         }
         bar_named<CT>(1);  // D: the sorted tile is parked; whist is free again
 #pragma unroll
@@ -427,15 +609,19 @@ __global__ void __launch_bounds__(CT + LBT, OCC) pass_kernel(const PassArgs a) {
     if (tid == 0) {
         sm.tile_of[i & 1u] = NO_TILE;  // release the look-back group
         mbar_arrive(&sm.cnt_bar[i & 1u]);
+#if KGB_PK_STATS
+        if (a.stats) atomicAdd((unsigned long long*)&a.stats[3], st_wait);
+#endif
     }
 }
 
 // ------------------------------------------------------------------------------------------- analysis + histograms
-// OR of enc(key) ^ enc(key[0]) over all keys: the bits that vary at all.  out[0] = diff mask, out[1] = enc(key[0]).
+// One read of the keys: out[0] = OR of enc(key) ^ enc(key[0]) (bits below its lowest set bit are shared by all keys),
+// out[1] = ~min(enc), out[2] = max(enc) (zero-initialised by the caller, hence the complement).
 template <int KW>
 __global__ void __launch_bounds__(256) analyze_kernel(const void* __restrict__ keys, u32 n, int dtype, u64* __restrict__ out) {
     const u64 first = enc_rt(dtype, KW == 8 ? reinterpret_cast<const u64*>(keys)[0] : (u64)reinterpret_cast<const u32*>(keys)[0]);
-    u64 diff = 0;
+    u64 diff = 0, mn = first, mx = first;
     constexpr int U = 8;
     for (u64 base = (u64)blockIdx.x * (256 * U); base < n; base += (u64)gridDim.x * (256 * U)) {
         u64 r[U];
@@ -446,12 +632,25 @@ __global__ void __launch_bounds__(256) analyze_kernel(const void* __restrict__ k
             r[u] = KW == 8 ? __ldg(reinterpret_cast<const u64*>(keys) + ii) : (u64)__ldg(reinterpret_cast<const u32*>(keys) + ii);
         }
 #pragma unroll
-        for (int u = 0; u < U; u++) diff |= enc_rt(dtype, r[u]) ^ first;
+        for (int u = 0; u < U; u++) {
+            const u64 e = enc_rt(dtype, r[u]);
+            diff |= e ^ first;
+            mn = e < mn ? e : mn;
+            mx = e > mx ? e : mx;
+        }
     }
 #pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) diff |= __shfl_xor_sync(0xffffffffu, diff, o);
-    if ((threadIdx.x & 31) == 0 && diff) atomicOr((unsigned long long*)&out[0], diff);
-    if (blockIdx.x == 0 && threadIdx.x == 0) out[1] = first;
+    for (int o = 16; o >= 1; o >>= 1) {
+        diff |= __shfl_xor_sync(0xffffffffu, diff, o);
+        const u64 a = __shfl_xor_sync(0xffffffffu, mn, o), b = __shfl_xor_sync(0xffffffffu, mx, o);
+        mn = a < mn ? a : mn;
+        mx = b > mx ? b : mx;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (diff) atomicOr((unsigned long long*)&out[0], diff);
+        atomicMax((unsigned long long*)&out[1], ~mn);
+        atomicMax((unsigned long long*)&out[2], mx);
+    }
 }
 
 struct HistArgs {
@@ -459,7 +658,7 @@ struct HistArgs {
     int shift[MAXP];  // digit position inside the KEY FIELD (packed shift minus pb)
     int bits[MAXP];
     int lo;
-    u64 kmask;
+    u64 kmask, enc_base;
     int dtype;
 };
 
@@ -484,7 +683,7 @@ __global__ void __launch_bounds__(256) hist_kernel(const void* __restrict__ keys
 #pragma unroll
         for (int u = 0; u < U; u++) {
             if (valid[u]) {
-                const u64 f = (enc_rt(h.dtype, r[u]) >> h.lo) & h.kmask;
+                const u64 f = ((enc_rt(h.dtype, r[u]) - h.enc_base) >> h.lo) & h.kmask;
                 // atomicAdd(.., 1) compiles to ATOMS.POPC.INC, which folds lanes that hit the same bin in hardware
                 for (int p = 0; p < h.npass; p++) atomicAdd(&sh[p * MAXBINS + ((u32)(f >> h.shift[p]) & ((1u << h.bits[p]) - 1u))], 1u);
             }
@@ -522,8 +721,8 @@ __global__ void __launch_bounds__(256) identity_kernel(const PassArgs a) {
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
         const u64 op = a.descending ? (a.n - 1 - i) : i;
         a.idx_out[op] = (i64)i;
-        if (a.enc_sorted_out) a.enc_sorted_out[op] = a.enc_const;
-        if (a.keys_sorted_out) dec_store_rt(a.dtype, a.keys_sorted_out, op, a.enc_const);
+        if (a.enc_sorted_out) a.enc_sorted_out[op] = a.enc_base;
+        if (a.keys_sorted_out) dec_store_rt(a.dtype, a.keys_sorted_out, op, a.enc_base);
     }
 }
 
@@ -611,7 +810,7 @@ struct Plan {
     int shift[MAXP];      // inside the packed word
     int lo, pb, live;     // live = number of key bits carried
     int prefix;           // 1: the keys have more live bits than fit; bits below `lo` are ignored (fix-up needed)
-    u64 kmask, enc_const;
+    u64 kmask, enc_base;
 };
 
 inline int ceil_log2_u64(u64 x) {  // smallest b with 2^b >= x
@@ -620,18 +819,19 @@ inline int ceil_log2_u64(u64 x) {  // smallest b with 2^b >= x
     return b;
 }
 
-// diff: OR of enc ^ enc0.  Chooses the key field [lo, lo+live) and the digit widths.
-inline Plan make_plan(u64 diff, u64 enc0, u64 n) {
+// diff: OR of enc ^ enc0; mn/mx: extreme encoded keys.  Chooses the key field (enc - mn) >> lo, `live` bits wide, and
+// the digit widths: as few passes as 10-bit digits allow, widths evened out (27 live bits -> 9+9+9, 14 -> 7+7).
+inline Plan make_plan(u64 diff, u64 mn, u64 mx, u64 n) {
     Plan p{};
     p.pb = ceil_log2_u64(n);
     if (p.pb < 1) p.pb = 1;
-    p.enc_const = enc0;
-    if (diff == 0) {
+    p.enc_base = mn;
+    if (diff == 0 || mx == mn) {
         p.npass = 0;
         return p;
     }
-    const int hi = 63 - __builtin_clzll(diff);
-    int lo = __builtin_ctzll(diff);
+    const int hi = 63 - __builtin_clzll(mx - mn);
+    int lo = __builtin_ctzll(diff);  // every key shares the bits below: (enc - mn) has zeros there
     int live = hi - lo + 1;
     const int room = 64 - p.pb;
     if (live > room) {
@@ -642,9 +842,12 @@ inline Plan make_plan(u64 diff, u64 enc0, u64 n) {
     p.lo = lo;
     p.live = live;
     p.kmask = live >= 64 ? ~0ull : ((1ull << live) - 1ull);
-    p.enc_const = enc0 & ~(p.kmask << lo);
     int np = (live + MAXBITS - 1) / MAXBITS;
     if (np < 1) np = 1;
+    if (np > PLAN_MAXP) {  // only tiny n (few position bits) with wide keys: the caller uses the general pass
+        p.npass = -1;
+        return p;
+    }
     p.npass = np;
     int left = live, pos = 0;
     for (int i = 0; i < np; i++) {
@@ -659,7 +862,6 @@ inline Plan make_plan(u64 diff, u64 enc0, u64 n) {
     return p;
 }
 
-
 // ------------------------------------------------------------------------------------------- host-side driver
 // geometry of the pass (tuned on a B200, profiles/r02_sort_lab_*.log)
 #ifndef KGB_PK_CT
@@ -670,10 +872,10 @@ inline Plan make_plan(u64 diff, u64 enc0, u64 n) {
 #endif
 
 struct Ws {
-    u64* ctl;      // [0] diff, [1] enc0, [2] fix-up flags
+    u64* ctl;      // [0] diff, [1] ~min, [2] max, [3] fix-up flags
     u32* hist;     // [MAXP][MAXBINS]
     u32* tickets;  // [MAXP] (+ pad)
-    u64* states;   // [tiles][MAXBINS]
+    u32* states;   // look-back words, one [tiles][1 << bits] block per pass
     size_t zero_bytes;  // ctl .. tickets are contiguous (zeroed before the analysis)
     size_t total;
 };
@@ -688,8 +890,8 @@ template <int T> inline Ws carve_ws(void* ws, u64 n) {
     w.tickets = (u32*)(p + o);
     o += 256;
     w.zero_bytes = o;
-    w.states = (u64*)(p + o);
-    o += align_up((size_t)((n + T - 1) / T) * MAXBINS * 8, 256);
+    w.states = (u32*)(p + o);
+    o += align_up(((size_t)((n + T - 1) / T) + LB_PAD) * 4 * (PLAN_MAXP * MAXBINS), 256);
     w.total = o;
     return w;
 }
@@ -750,18 +952,19 @@ template <int T> inline cudaError_t packed_analyze(const void* keys, int dtype, 
 template <int CT, int KPT, int LBT, int OCC>
 inline cudaError_t packed_passes(const void* keys, int dtype, u64 n, const Plan& p, int descending, i64* idx_out,
                                  void* keys_sorted_out, u64* enc_sorted_out, const Ws& w, u64* buf0, u64* buf1,
-                                 u64** final_packed, int sms, cudaStream_t st, cudaEvent_t* lab_events = nullptr) {
+                                 u64** final_packed, int sms, cudaStream_t st, cudaEvent_t* lab_events = nullptr,
+                                 u64* lab_stats = nullptr) {
     PassArgs a{};
+    a.stats = lab_stats;
     a.in_keys = keys;
     a.idx_out = idx_out;
     a.keys_sorted_out = keys_sorted_out;
     a.enc_sorted_out = enc_sorted_out;
-    a.states = w.states;
     a.n = (u32)n;
     a.lo = p.lo;
     a.pb = p.pb;
     a.kmask = p.kmask;
-    a.enc_const = p.enc_const;
+    a.enc_base = p.enc_base;
     a.dtype = dtype;
     a.descending = descending;
     if (p.npass == 0) {
@@ -778,6 +981,7 @@ inline cudaError_t packed_passes(const void* keys, int dtype, u64 n, const Plan&
     }
     h.lo = p.lo;
     h.kmask = p.kmask;
+    h.enc_base = p.enc_base;
     h.dtype = dtype;
     long long hb = (long long)((n + 1023) / 1024);
     if (hb > (long long)sms * 8) hb = (long long)sms * 8;
@@ -788,15 +992,24 @@ inline cudaError_t packed_passes(const void* keys, int dtype, u64 n, const Plan&
     base_kernel<<<p.npass, MAXBINS, 0, st>>>(w.hist);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    {   // look-back words: one zeroing serves every pass (the epoch in each word tells the passes apart)
-        int maxbits = 0;
-        for (int i = 0; i < p.npass; i++) maxbits = p.bits[i] > maxbits ? p.bits[i] : maxbits;
-        const size_t tiles = (size_t)((n + (u64)(CT * KPT) - 1) / (u64)(CT * KPT));
-        e = cudaMemsetAsync(w.states, 0, tiles * ((size_t)8 << maxbits), st);
+    const size_t tiles = (size_t)((n + (u64)(CT * KPT) - 1) / (u64)(CT * KPT));
+    {   // look-back words of all passes: one memset
+        size_t words = 0;
+        for (int i = 0; i < p.npass; i++) words += (tiles + LB_PAD) << p.bits[i];
+        e = cudaMemsetAsync(w.states, 0, words * 4, st);
         if (e != cudaSuccess) return e;
     }
     if (lab_events) cudaEventRecord(lab_events[0], st);
     u64* bufs[2] = {buf0, buf1};
+    u32* states = w.states;
+    {
+        static int stagger_env = -1;  // KGB200_SORT_STAGGER_NS: tuning override (0 disables)
+        if (stagger_env == -1) {
+            const char* ev = getenv("KGB200_SORT_STAGGER_NS");
+            stagger_env = ev ? atoi(ev) : -2;
+        }
+        a.stagger_ns = stagger_env >= 0 ? (u32)stagger_env : 30u;
+    }
     for (int i = 0; i < p.npass; i++) {
         int role = 0;
         if (i == 0) role |= ROLE_FIRST;
@@ -806,10 +1019,12 @@ inline cudaError_t packed_passes(const void* keys, int dtype, u64 n, const Plan&
         a.digit_base = w.hist + (size_t)i * MAXBINS;
         a.ticket = w.tickets + i;
         a.shift = p.shift[i];
-        a.epoch = (u32)i + 1;
+        a.states = states + ((size_t)LB_PAD << p.bits[i]);
+        states += (tiles + LB_PAD) << p.bits[i];
         e = Launcher<CT, KPT, LBT, OCC>::go(p.bits[i], role, key_width(dtype), a, sms, st);
         if (e != cudaSuccess) return e;
         if (lab_events) cudaEventRecord(lab_events[i + 1], st);
+        if (a.stats) a.stats += 4;
     }
     if (final_packed) *final_packed = bufs[(p.npass - 1) & 1];
     return cudaSuccess;

@@ -90,6 +90,7 @@ struct Times {
     float total, analyze, hist, passes, pass[MAXP], fix;
 };
 
+static u64* g_stats = nullptr;  // device, MAXP * 4 words
 static int run_sort(const i64* d_keys, u64 n, i64* d_idx, void* ws, u64* buf0, u64* buf1, int sms, Times* tm, Plan* plan_out,
                     bool per_kernel) {
     cudaStream_t st = 0;
@@ -99,17 +100,17 @@ static int run_sort(const i64* d_keys, u64 n, i64* d_idx, void* ws, u64* buf0, u
     int ne = 0;
     CK(cudaEventRecord(ev[ne++], st));
     CK(packed_analyze<T>(d_keys, KGB_I64, n, w, sms, st));
-    u64 h[2];
-    CK(cudaMemcpyAsync(h, w.ctl, 16, cudaMemcpyDeviceToHost, st));
+    u64 h[3];
+    CK(cudaMemcpyAsync(h, w.ctl, 24, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaEventRecord(ev[ne++], st));
-    Plan p = make_plan(h[0], h[1], n);
+    Plan p = make_plan(h[0], ~h[1], h[2], n);
     *plan_out = p;
     u64* fin = nullptr;
     (void)per_kernel;
     cudaEvent_t pe[MAXP + 1];
     for (auto& e : pe) CK(cudaEventCreate(&e));
-    CK((packed_passes<CT, KPT, LBT, OCC>(d_keys, KGB_I64, n, p, 0, d_idx, nullptr, nullptr, w, buf0, buf1, p.prefix ? &fin : nullptr, sms, st, pe)));
+    CK((packed_passes<CT, KPT, LBT, OCC>(d_keys, KGB_I64, n, p, 0, d_idx, nullptr, nullptr, w, buf0, buf1, p.prefix ? &fin : nullptr, sms, st, pe, KGB_PK_STATS ? g_stats : nullptr)));
     CK(cudaEventRecord(ev[ne++], st));
     int over = 0;
     if (p.prefix) {
@@ -117,14 +118,14 @@ static int run_sort(const i64* d_keys, u64 n, i64* d_idx, void* ws, u64* buf0, u
         f.sorted = fin;
         f.keys = d_keys;
         f.idx_out = d_idx;
-        f.flags = w.ctl + 2;
+        f.flags = w.ctl + 3;
         f.n = (u32)n;
         f.pb = p.pb;
         f.dtype = KGB_I64;
         fixup_kernel<8><<<sms * 8, 256, 0, st>>>(f);
         CK(cudaGetLastError());
         u64 fl = 0;
-        CK(cudaMemcpyAsync(&fl, w.ctl + 2, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&fl, w.ctl + 3, 8, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         over = (int)fl;
     }
@@ -148,7 +149,7 @@ int main(int argc, char** argv) {
     const int reps = argc > 2 ? atoi(argv[2]) : 5;
     int sms = 0;
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
-    printf("sort_lab CT=%d KPT=%d LBT=%d OCC=%d ATOM=%d LB=%d  T=%d  n=%llu sms=%d\n", CT, KPT, LBT, OCC, KGB_PK_ATOM, KGB_PK_LB, T,
+    printf("sort_lab CT=%d KPT=%d LBT=%d OCC=%d ATOM=%d LB=%d STATS=%d NOLB=%d  T=%d  n=%llu sms=%d\n", CT, KPT, LBT, OCC, KGB_PK_ATOM, KGB_PK_LB, KGB_PK_STATS, KGB_PK_NOLB, T,
            (unsigned long long)n, sms);
     {
         cudaFuncAttributes fa;
@@ -169,6 +170,7 @@ int main(int argc, char** argv) {
     CK(cudaMalloc(&d_pos, n * 4));
     CK(cudaMalloc(&d_ref, n * 4));
     CK(cudaMalloc(&d_bad, 16));
+    CK(cudaMalloc(&g_stats, MAXP * 4 * 8));
     const size_t wsb = carve_ws<T>(nullptr, n).total;
     CK(cudaMalloc(&ws, wsb));
     size_t cub_bytes = 0;
@@ -202,6 +204,7 @@ int main(int argc, char** argv) {
         int over = 0;
         for (int r = 0; r < reps + 1; r++) {
             Times tm{};
+            CK(cudaMemset(g_stats, 0, MAXP * 4 * 8));
             over = run_sort(d_keys, n, d_idx, ws, buf0, buf1, sms, &tm, &p, false);
             if (r > 0 && tm.total < best.total) best = tm;
         }
@@ -216,6 +219,16 @@ int main(int argc, char** argv) {
         for (int i = 0; i < p.npass; i++) printf(" %.3f", best.pass[i]);
         printf(", fixup %.3f) cub %.3f ms | mismatches %llu first %lld over=%d\n", best.fix, cub_ms, bad[0],
                bad[0] ? (long long)bad[1] : -1ll, over);
+#if KGB_PK_STATS
+        {
+            u64 hs[MAXP * 4];
+            CK(cudaMemcpy(hs, g_stats, sizeof hs, cudaMemcpyDeviceToHost));
+            for (int i = 0; i < p.npass; i++)
+                printf("   pass %d: look-back rounds/tile %.2f, steps/tile %.2f (chain 0 of thread 0), write-out wait polls/tile %.1f\n", i,
+                       (double)hs[i * 4] / (double)(hs[i * 4 + 2] ? hs[i * 4 + 2] : 1), (double)hs[i * 4 + 1] / (double)(hs[i * 4 + 2] ? hs[i * 4 + 2] : 1),
+                       (double)hs[i * 4 + 3] / (double)(hs[i * 4 + 2] ? hs[i * 4 + 2] : 1));
+        }
+#endif
         fflush(stdout);
     }
     return 0;

@@ -719,3 +719,55 @@ def test_grade_large_float_keys_with_nan_inf_and_signed_zero(be, K):
     want = np.array(want)
     assert len(u) == len(want) and np.array_equal(np.isnan(u), np.isnan(want))
     assert np.array_equal(u[~np.isnan(u)], want[~np.isnan(want)]) and np.array_equal(np.signbit(u), np.signbit(want))
+
+
+# ------------------------------------------------------------------------------------------ packed radix pass
+def _packed_key_sets(rng, n):
+    """Key sets aimed at the packed sort's planner (csrc/kgb_sort_packed.cuh): key ranges that cross zero, trailing
+    constant bits, keys too wide for the packed word (prefix mode) with short and with long prefix ties."""
+    sets = dict(_key_sets(rng, n))
+    sets["cross0"] = rng.integers(-5, 6, n)
+    sets["stride1024"] = rng.integers(0, max(2, n), n) * 1024 + 7
+    sets["two"] = rng.integers(0, 2, n) * (2**62) - 2**61
+    hi = rng.integers(0, 3, n).astype(np.int64) << 45
+    sets["prefix_long_ties"] = hi | rng.integers(0, 2**20, n)          # few prefixes, many low parts: fix-up overflows
+    sets["prefix_short_ties"] = (rng.integers(-2**62, 2**62, n) >> 9) << 9 | rng.integers(0, 4, n)
+    f = rng.standard_normal(n)
+    f[rng.integers(0, n, max(1, n // 50))] = np.nan
+    f[rng.integers(0, n, max(1, n // 50))] = -0.0
+    f[rng.integers(0, n, max(1, n // 50))] = 0.0
+    f[rng.integers(0, n, max(1, n // 100))] = np.inf
+    sets["f64special"] = f
+    sets["f64temps"] = np.round(rng.normal(10, 15, n), 1)               # wide live range, few distinct values
+    sets["i32"] = rng.integers(-1000, 1000, n).astype(np.int32)
+    sets["f32"] = rng.standard_normal(n).astype(np.float32)
+    return sets
+
+
+@pytest.mark.parametrize("n", [2, 100, 8191, 8192, 8193, 24577, 300_001, 1_000_003])
+def test_grade_packed_path_bit_exact(be, K, n, monkeypatch):
+    """Every size through the packed pass (threshold forced down), every planner branch, both directions, sorted keys."""
+    monkeypatch.setenv("KGB200_SORT_PACKED_MIN", "2")
+    rng = np.random.default_rng(n + 11)
+    for name, keys in _packed_key_sets(rng, n).items():
+        D = K.asarray(keys)
+        ref = np.argsort(keys, kind="stable")
+        up, ks = K.argsort(D, return_sorted=True)
+        assert np.array_equal(host(up), ref), (name, n)
+        assert np.array_equal(host(ks), keys[ref], equal_nan=True), (name, n)
+        assert np.array_equal(host(K.argsort(D, descending=True)), ref[::-1]), (name, n)
+        if keys.dtype == np.int64 or name in ("f64ties", "f64temps"):
+            order, starts, g = K.group(D)
+            ro, rs = O.group_csr(keys)
+            assert np.array_equal(host(order), ro) and np.array_equal(host(starts), rs), (name, n)
+
+
+@pytest.mark.parametrize("n", [300_001, 1_000_003])
+def test_grade_general_pass_still_bit_exact(be, K, n, monkeypatch):
+    """The 12-byte general pass is the fallback of the packed one: keep it covered at sizes the packed path now takes."""
+    monkeypatch.setenv("KGB200_SORT_PACKED", "0")
+    rng = np.random.default_rng(n + 12)
+    for name, keys in _key_sets(rng, n).items():
+        D = dev(be, keys)
+        assert np.array_equal(host(be.argsort(D)), O.grade_up(keys)), (name, n)
+        assert np.array_equal(host(be.argsort(D, descending=True)), O.grade_down(keys)), (name, n)
