@@ -81,6 +81,9 @@ enum kgb_opcode {
     KGB_OP_GE_B = 31,
     KGB_OP_LE_B = 32,
     KGB_OP_ISCLOSE = 33, /* |a-b| <= atol + rtol*|b| with numpy defaults (adverbs.py:33)      */
+    KGB_OP_FLOORDIV = 34, /* np.floor_divide: integers stay integers, exact (x//0 -> 0); floats follow
+                             numpy's divmod (the array type's `//`)                              */
+    KGB_OP_MOD = 35,     /* np.remainder: floored, sign of the divisor (the array type's `%`)    */
     /* monads */
     KGB_OP_NEG = 48,      /* monads.py:224-237                                                */
     KGB_OP_ABS = 49,      /* monads.py:408-427                                                */

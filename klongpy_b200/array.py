@@ -207,7 +207,10 @@ class DeviceArray:
     def __rtruediv__(self, o): return self._bin(o, "div", True)
     def __pow__(self, o): return self._bin(o, "pow")
     def __rpow__(self, o): return self._bin(o, "pow", True)
-    def __mod__(self, o): return self._bin(o, "fmod")
+    def __mod__(self, o): return self._bin(o, "mod")          # numpy's floored remainder (np.fmod is backend.np.fmod)
+    def __rmod__(self, o): return self._bin(o, "mod", True)
+    def __floordiv__(self, o): return self._bin(o, "floordiv")  # integer arrays stay exact integers
+    def __rfloordiv__(self, o): return self._bin(o, "floordiv", True)
     def __lt__(self, o): return self._bin(o, "lt_b")
     def __gt__(self, o): return self._bin(o, "gt_b")
     def __le__(self, o): return self._bin(o, "le_b")
@@ -243,8 +246,8 @@ class DeviceArray:
         return ops.any_(self)
 
     # numpy ufuncs applied to device arrays (np.float64(2) * a, np.equal(a, b), np.add.reduce(a) ...) run on the device
-    # when the ufunc has a kernel opcode, and on host copies otherwise — global-NumPy call sites of the reference
-    # (SURVEY.md §8b "leaks") and user code keep working instead of raising
+    # when the ufunc has a kernel opcode.  Anything else RAISES: there is no CPU fallback on this path (north_star); a
+    # caller who wants host arithmetic says so with `.to_numpy()`.
     _UFUNC = {"add": "add", "subtract": "sub", "multiply": "mul", "divide": "div", "true_divide": "div", "power": "pow",
               "maximum": "max", "minimum": "min", "fmod": "fmod", "equal": "eq_b", "not_equal": "ne_b", "less": "lt_b",
               "greater": "gt_b", "less_equal": "le_b", "greater_equal": "ge_b", "negative": "neg", "absolute": "abs",
@@ -252,7 +255,7 @@ class DeviceArray:
               "sqrt": "sqrt", "exp": "exp", "log": "log", "sin": "sin", "cos": "cos", "tan": "tan", "tanh": "tanh",
               "sign": "sign", "isnan": "isnan_b", "isinf": "isinf_b", "log2": "log2", "log10": "log10", "square": "square",
               "expm1": "expm1", "log1p": "log1p", "sinh": "sinh", "cosh": "cosh", "arcsin": "asin", "arccos": "acos",
-              "arctan": "atan"}
+              "arctan": "atan", "floor_divide": "floordiv", "remainder": "mod", "mod": "mod"}
 
     def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
         from . import ops
@@ -265,8 +268,9 @@ class DeviceArray:
                     return ops.unary(name, inputs[0])
             if method in ("reduce", "accumulate") and name in ("add", "mul", "max", "min") and len(inputs) == 1:
                 return ops.reduce(name, inputs[0]) if method == "reduce" else ops.scan(name, inputs[0])
-        host = [x.to_numpy() if isinstance(x, DeviceArray) else x for x in inputs]
-        return getattr(ufunc, method)(*host, **kwargs)
+        raise TypeError(f"numpy.{ufunc.__name__}.{method} has no device kernel for these operands"
+                        f"{' / keyword arguments ' + repr(sorted(kwargs)) if kwargs else ''}; "
+                        "call .to_numpy() explicitly to compute on the host")
 
     def __hash__(self):
         # 0-d device values appear as dictionary keys (`:{[k v]}` builds `a[b[0]] = b[1]`, dyads dictionary code):
@@ -275,31 +279,23 @@ class DeviceArray:
             return hash(self.item())
         raise TypeError("unhashable type: 'DeviceArray'")
 
-    def __floordiv__(self, other):
+    def _fold(self, name, axis):
+        # ndarray.sum/max/min: axis=None folds EVERY element, axis=0 the leading axis; other axes are not on the path
         from . import ops
-        if self.ndim == 0 and ops.is_host_scalar(other):
-            return self.item() // other
-        return ops.unary("floor_i64", ops.binary("div", self, other)) if self.dtype.kind in "iub" else \
-            ops.unary("floor", ops.binary("div", self, other))
-
-    def __rfloordiv__(self, other):
-        from . import ops
-        if self.ndim == 0 and ops.is_host_scalar(other):
-            return other // self.item()
-        return ops.unary("floor_i64", ops.binary("div", other, self)) if self.dtype.kind in "iub" else \
-            ops.unary("floor", ops.binary("div", other, self))
+        if axis is None:
+            return ops.reduce(name, self.flatten() if self.ndim > 1 else self)
+        if axis in (0, -self.ndim) and self.ndim >= 1:
+            return ops.reduce(name, self)
+        raise NotImplementedError(f"DeviceArray.{name}: axis={axis!r} (only None and 0 have kernels)")
 
     def sum(self, axis=None, out=None, **_kw):
-        from . import ops
-        return ops.reduce("add", self)
+        return self._fold("add", axis)
 
     def max(self, axis=None, out=None, **_kw):
-        from . import ops
-        return ops.reduce("max", self)
+        return self._fold("max", axis)
 
     def min(self, axis=None, out=None, **_kw):
-        from . import ops
-        return ops.reduce("min", self)
+        return self._fold("min", axis)
 
     def argsort(self, kind=None):
         from . import ops

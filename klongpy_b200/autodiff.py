@@ -16,7 +16,7 @@ from . import ops
 _NAME = {v: k for k, v in ops.OPC.items()}
 _ARITY = {}
 for _n in ("add", "sub", "mul", "div", "pow", "eq", "gt", "lt", "max", "min", "fmod", "eq_b", "gt_b", "lt_b", "ne_b", "ge_b",
-           "le_b", "isclose"):
+           "le_b", "isclose", "floordiv", "mod"):
     _ARITY[_n] = 2
 for _n in ("neg", "abs", "floor", "floor_i64", "trunc", "recip", "not_b", "to_f64", "to_i64", "to_f32", "to_b8", "to_i32",
            "sqrt", "exp", "log", "sin", "cos", "tan", "tanh", "ceil", "sign", "isnan_b", "isinf_b", "log2", "log10", "sinh",
@@ -220,10 +220,13 @@ def tangent(tree, i):
     if name == "fmod":
         a, b = kids
         return op("sub", d[0], op("mul", op("trunc", op("div", a, b)), d[1]))
+    if name == "mod":  # a - floor(a / b) * b
+        a, b = kids
+        return op("sub", d[0], op("mul", op("floor", op("div", a, b)), d[1]))
     if name in ("to_f64", "to_f32"):
         return d[0]
     if name in ("eq", "gt", "lt", "eq_b", "gt_b", "lt_b", "ne_b", "ge_b", "le_b", "isclose", "floor", "floor_i64", "trunc",
-                "ceil", "sign", "not_b", "to_i64", "to_i32", "to_b8", "isnan_b", "isinf_b"):
+                "ceil", "sign", "not_b", "to_i64", "to_i32", "to_b8", "isnan_b", "isinf_b", "floordiv"):
         return ZERO  # piecewise constant
     raise NotDifferentiable(f"no derivative rule for {name}")
 

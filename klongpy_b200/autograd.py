@@ -90,6 +90,11 @@ def _sum_to(x, shape):
     """gradient of a broadcast scalar operand: fold the elementwise gradient"""
     if x.ndim == 0:
         return x._t.reshape(shape)
+    size = 1
+    for d in shape:
+        size *= int(d)
+    if size != 1:  # (1, n) against (m, n) and the like: no kernel folds a subset of the axes
+        raise autodiff.NotDifferentiable(f"gradient of an operand of shape {tuple(shape)} broadcast to {tuple(x.shape)}")
     return ops.reduce("add", x.flatten())._t.reshape(shape)
 
 

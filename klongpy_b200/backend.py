@@ -6,9 +6,9 @@ overridable defaults that matter: `compile_expr_ir`, `power`, `floor_to_int`, `t
 `klongpy.backends.register_backend('b200', B200BackendProvider)` (`registry.py:23-25`), after which
 `KlongInterpreter(backend='b200', device='cuda:0')` constructs it (`interpreter.py:249`).
 
-When klongpy is importable the class derives from the reference's own ABC; on a box without klongpy (the GPU
-test box) it derives from a local mirror with the same method set, so parity tests can drive the provider
-with IR tuples captured from the real compiler (tests/golden/).
+The class derives from the reference's own ABC (klongpy must be importable: installed, or the offline install under
+baseline/_ref that travels to the GPU box); the parity tests drive it with IR tuples captured from the real compiler
+(tests/golden/).
 """
 import numpy as np
 import torch
@@ -17,90 +17,36 @@ from . import _lib, lowering, ops
 from .array import DeviceArray
 from .npshim import B200Numpy
 
-try:  # the reference's own ABC when it is installed
-    from klongpy.backends.base import BackendProvider as _Base, UnsupportedDtypeError, is_jagged_array
-    HAVE_KLONGPY = True
-except Exception:  # pragma: no cover - exercised on the GPU box
-    HAVE_KLONGPY = False
-
-    class UnsupportedDtypeError(Exception):
-        """Raised when an operation requires a dtype the backend cannot hold (base.py:509-511)."""
-
-    def is_jagged_array(x):
-        if isinstance(x, list) and len(x) > 0:
-            if all(isinstance(item, (list, tuple)) for item in x):
-                return len(set(map(len, x))) > 1
-        return False
-
-    class _Base:
-        """Mirror of the non-abstract defaults of klongpy.backends.base.BackendProvider the hot path uses."""
-
-        def to_display(self, x):
-            if self.is_backend_array(x):
-                x = self.to_numpy(x)
-            if hasattr(x, "item") and hasattr(x, "ndim") and x.ndim == 0:
-                return x.item()
-            return x
-
-        def scalar_to_python(self, x):
-            return x.item() if hasattr(x, "item") else x
-
-        def is_integer(self, x):
-            if issubclass(type(x), (int, np.integer)):
-                return True
-            return self.is_scalar_integer(x)
-
-        def is_float(self, x):
-            if issubclass(type(x), (float, np.floating, int)):
-                return True
-            return self.is_scalar_float(x) or self.is_scalar_integer(x)
-
-        def is_number(self, a):
-            return self.is_float(a) or self.is_integer(a)
-
-        def str_to_chr_arr(self, s):
-            return self.str_to_char_array(s)
-
-        def vec_fn(self, a, f):
-            if self.np.isarray(a) and a.dtype == "O":
-                result = [self.vec_fn(x, f) if self._is_list(x) else f(x) for x in a]
-                return np.asarray(result, dtype=object)
-            return f(a)
-
-        def vec_fn2(self, a, b, f):
-            if self.np.isarray(a):
-                if a.dtype == "O":
-                    if self.np.isarray(b):
-                        assert len(a) == len(b)
-                        return self.kg_asarray([self.vec_fn2(x, y, f) for x, y in zip(a, b)])
-                    return self.kg_asarray([self.vec_fn2(x, b, f) for x in a])
-                elif self.np.isarray(b) and b.dtype == "O":
-                    assert len(a) == len(b)
-                    return self.kg_asarray([self.vec_fn2(x, y, f) for x, y in zip(a, b)])
-            elif self.np.isarray(b) and b.dtype == "O":
-                return self.kg_asarray([self.vec_fn2(a, x, f) for x in b])
-            return f(a, b)
-
-        def rec_fn(self, a, f):
-            return self.kg_asarray([self.rec_fn(x, f) for x in a]) if self._is_list(a) else f(a)
-
-        def get_info(self):
-            return {
-                "name": self.name, "device": self.device, "devices": self.list_devices(),
-                "supports_float64": self.supports_float64(), "supports_strings": self.supports_strings(),
-                "supports_object_dtype": self.supports_object_dtype(),
-                "supports_autograd": self.supports_autograd(),
-            }
+def _import_reference_abc():
+    """klongpy's own BackendProvider ABC: the provider is a plugin for that interface and derives from it — there is
+    no local copy of its defaults to drift.  Looked for as an installed package first, then in the documented offline
+    install `baseline/_ref` (it travels to the GPU box with the snapshot), then in the read-only
+    reference checkout of the build container."""
+    import importlib
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    tried = []
+    for extra in (None, os.path.join(root, "baseline", "_ref"), "/root/reference"):
+        if extra is not None:
+            if not os.path.isdir(os.path.join(extra, "klongpy")):
+                continue
+            if extra not in sys.path:
+                sys.path.append(extra)
+        try:
+            return importlib.import_module("klongpy.backends.base")
+        except Exception as ex:  # noqa: BLE001 - report every attempt
+            tried.append(f"{extra or 'sys.path'}: {type(ex).__name__}: {ex}")
+    raise ImportError("klongpy_b200 is a backend plugin for klongpy and needs it importable "
+                      "(pip install klongpy, or the offline install under baseline/_ref): " + "; ".join(tried))
 
 
-class KGChar(str):
-    """Character type (numpy_backend.py:16-18); the reference's class is used when available."""
+_base = _import_reference_abc()
+_Base, UnsupportedDtypeError, is_jagged_array = _base.BackendProvider, _base.UnsupportedDtypeError, _base.is_jagged_array
+HAVE_KLONGPY = True
 
 
-try:
-    from klongpy.backends.numpy_backend import KGChar  # noqa: F811
-except Exception:  # pragma: no cover
-    pass
+from klongpy.backends.numpy_backend import KGChar  # noqa: E402 - the reference's character type (numpy_backend.py:16-18)
 
 
 class B200BackendProvider(_Base):
@@ -272,9 +218,7 @@ class B200BackendProvider(_Base):
             a = a.to_numpy()
         if isinstance(b, DeviceArray):
             b = b.to_numpy()
-        if HAVE_KLONGPY:
-            return super().kg_equal(a, b)
-        return _np_kg_equal(self, a, b)
+        return super().kg_equal(a, b)
 
     def detach_if_needed(self, x):
         if isinstance(x, DeviceArray) and x.requires_grad:
@@ -331,23 +275,3 @@ class B200BackendProvider(_Base):
     def compute_jacobian(self, func, x):
         from . import autograd
         return autograd.compute_jacobian(self, func, x)
-
-
-def _np_kg_equal(backend, a, b):
-    """Restatement of base.py:367-433 for host values (used only when klongpy is not importable)."""
-    if isinstance(a, np.ndarray) and isinstance(b, np.ndarray) and a.dtype != object and b.dtype != object:
-        return bool(np.array_equal(a, b))
-    if isinstance(a, np.ndarray) and a.ndim == 0:
-        a = a.item()
-    if isinstance(b, np.ndarray) and b.ndim == 0:
-        b = b.item()
-    a_seq = isinstance(a, (list, tuple)) or (isinstance(a, np.ndarray) and a.ndim > 0)
-    b_seq = isinstance(b, (list, tuple)) or (isinstance(b, np.ndarray) and b.ndim > 0)
-    if a_seq or b_seq:
-        if not (a_seq and b_seq) or len(a) != len(b):
-            return False
-        return all(backend.kg_equal(x, y) for x, y in zip(a, b))
-    if backend.is_number(a) and backend.is_number(b):
-        return bool(np.isclose(a, b))
-    r = a == b
-    return bool(r.all()) if hasattr(r, "all") else bool(r)

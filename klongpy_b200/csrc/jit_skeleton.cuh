@@ -127,6 +127,54 @@ __device__ __forceinline__ double kgb_fmod(double a, double b) { return fmod(a, 
 __device__ __forceinline__ float kgb_fmod(float a, float b) { return fmodf(a, b); }
 __device__ __forceinline__ i64 kgb_fmod(i64 a, i64 b) { return b == 0 ? 0 : (b == -1 ? 0 : a % b); }
 __device__ __forceinline__ int kgb_fmod(int a, int b) { return b == 0 ? 0 : (b == -1 ? 0 : a % b); }
+// np.floor_divide / np.remainder.  Integers: exact, x // 0 == x % 0 == 0, INT_MIN // -1 wraps (numpy's loops).
+// Floats: numpy's npy_divmod (fmod, then the Python sign convention, then the quotient snapped to an integer).
+template <typename I> __device__ __forceinline__ I kgb_ifloordiv(I a, I b) {
+    if (b == 0) return 0;
+    if (b == -1) return (I)(0 - (unsigned long long)a);
+    I q = a / b;
+    if (((a > 0) != (b > 0)) && q * b != a) q--;
+    return q;
+}
+template <typename I> __device__ __forceinline__ I kgb_imod(I a, I b) {
+    if (b == 0 || b == -1) return 0;
+    I r = a % b;
+    if (r != 0 && ((r < 0) != (b < 0))) r += b;
+    return r;
+}
+template <typename F> __device__ __forceinline__ F kgb_fdivmod(F a, F b, F* modulus) {
+    F mod = (sizeof(F) == 8) ? (F)fmod((double)a, (double)b) : (F)fmodf((float)a, (float)b);
+    if (b == (F)0) {
+        *modulus = mod;
+        return a / b;
+    }
+    F div = (a - mod) / b;
+    if (mod != (F)0) {
+        if ((b < (F)0) != (mod < (F)0)) {
+            mod += b;
+            div -= (F)1;
+        }
+    } else {
+        mod = (sizeof(F) == 8) ? (F)copysign(0.0, (double)b) : (F)copysignf(0.0f, (float)b);
+    }
+    F fd;
+    if (div != (F)0) {
+        fd = (sizeof(F) == 8) ? (F)floor((double)div) : (F)floorf((float)div);
+        if (div - fd > (F)0.5) fd += (F)1;
+    } else {
+        fd = (sizeof(F) == 8) ? (F)copysign(0.0, (double)(a / b)) : (F)copysignf(0.0f, (float)(a / b));
+    }
+    *modulus = mod;
+    return fd;
+}
+__device__ __forceinline__ i64 kgb_floordiv(i64 a, i64 b) { return kgb_ifloordiv<i64>(a, b); }
+__device__ __forceinline__ int kgb_floordiv(int a, int b) { return kgb_ifloordiv<int>(a, b); }
+__device__ __forceinline__ double kgb_floordiv(double a, double b) { double m; return kgb_fdivmod<double>(a, b, &m); }
+__device__ __forceinline__ float kgb_floordiv(float a, float b) { float m; return kgb_fdivmod<float>(a, b, &m); }
+__device__ __forceinline__ i64 kgb_mod(i64 a, i64 b) { return kgb_imod<i64>(a, b); }
+__device__ __forceinline__ int kgb_mod(int a, int b) { return kgb_imod<int>(a, b); }
+__device__ __forceinline__ double kgb_mod(double a, double b) { double m; kgb_fdivmod<double>(a, b, &m); return m; }
+__device__ __forceinline__ float kgb_mod(float a, float b) { float m; kgb_fdivmod<float>(a, b, &m); return m; }
 
 __device__ __forceinline__ double kgb_abs(double a) { return fabs(a); }
 __device__ __forceinline__ float kgb_abs(float a) { return fabsf(a); }

@@ -236,7 +236,9 @@ static bool gen_expr(const int32_t* code, int n_code, const std::vector<ArgInfo>
             case KGB_OP_POW:
             case KGB_OP_MAX:
             case KGB_OP_MIN:
-            case KGB_OP_FMOD: {
+            case KGB_OP_FMOD:
+            case KGB_OP_FLOORDIV:
+            case KGB_OP_MOD: {
                 if (!need(2)) return false;
                 Val b = st.back();
                 st.pop_back();
@@ -256,6 +258,8 @@ static bool gen_expr(const int32_t* code, int n_code, const std::vector<ArgInfo>
                     case KGB_OP_MAX: s = "kgb_max(" + ca + ", " + cb + ")"; break;
                     case KGB_OP_MIN: s = "kgb_min(" + ca + ", " + cb + ")"; break;
                     case KGB_OP_FMOD: s = "kgb_fmod(" + ca + ", " + cb + ")"; break;
+                    case KGB_OP_FLOORDIV: s = "kgb_floordiv(" + ca + ", " + cb + ")"; break;
+                    case KGB_OP_MOD: s = "kgb_mod(" + ca + ", " + cb + ")"; break;
                 }
                 st.push_back(Val{s, rt});
                 break;

@@ -23,18 +23,23 @@ struct AggWs {
     size_t total;
 };
 constexpr int AGG_MAX_PARTS = 160;  // >= SM count: one persistent CTA per SM
+constexpr size_t AGG_SMEM_LIMIT = 200 * 1024;
+// The per-CTA partial tables exist only for the variants that keep sums and counts in shared memory (16 B per group):
+// ONE predicate for the workspace query and the launcher, so G = 4e6 sparse keys cost 32*G bytes, not 1920*G.
+static inline bool agg_has_parts(i64 G) { return (size_t)G * 16 <= AGG_SMEM_LIMIT; }
 static AggWs carve_agg(void* ws, i64 G) {
     AggWs a;
     char* p = (char*)ws;
     const size_t gb = align_up((size_t)G * 8, 256);
+    const size_t parts = agg_has_parts(G) ? (size_t)AGG_MAX_PARTS : 0;
     a.tmin = (u64*)p;
     a.tmax = (u64*)(p + gb);
     a.tsum = (double*)(p + 2 * gb);
     a.tcnt = (u64*)(p + 3 * gb);
     a.err = (int*)(p + 4 * gb);
     a.psum = (double*)(p + 4 * gb + 256);
-    a.pcnt = (u32*)(p + 4 * gb + 256 + (size_t)AGG_MAX_PARTS * gb);
-    a.total = 4 * gb + 256 + (size_t)AGG_MAX_PARTS * gb + (size_t)AGG_MAX_PARTS * align_up((size_t)G * 4, 256);
+    a.pcnt = (u32*)(p + 4 * gb + 256 + parts * gb);
+    a.total = 4 * gb + 256 + parts * gb + parts * align_up((size_t)G * 4, 256);
     return a;
 }
 
@@ -465,10 +470,8 @@ extern "C" int kgb_groupagg_f64(const int64_t* keys, const double* vals, int64_t
         int variant = 5;  // measured at 1e9 rows / 10k stations: v5 3.72 ms (0.66 of roofline), v3 4.09 ms (0.60), v4 7.1 ms, v1 ~14 ms, v0 ~23 ms
         if (const char* e = getenv("KGB200_AGG_VARIANT")) variant = atoi(e);
         if (variant < 0 || variant > 6) variant = 5;
-        const size_t limit = 200 * 1024;
-        if (variant == 4 && (size_t)n_groups * 16 > limit) variant = 1;
-        if (variant == 6 && (size_t)n_groups * 16 > limit) variant = 1;
-        if (variant == 5 && (size_t)n_groups * 16 > limit) variant = 1;  // (12 800 stations per CTA; 10 240 for variant 3)
+        const size_t limit = AGG_SMEM_LIMIT;
+        if (variant >= 3 && !agg_has_parts(n_groups)) variant = 1;  // (12 800 stations per CTA; 10 240 for variant 3)
         if (variant == 3 && (size_t)n_groups * 20 > limit) variant = 1;
         if (variant != 0 && (size_t)n_groups * 12 > limit) variant = 0;
         if (variant == 0) {

@@ -333,8 +333,17 @@ class B200Numpy:
         return np.transpose(a, axes)
 
     # ------------------------------------------------------------------ folds
+    def _fold(self, name, a, axis):
+        # numpy semantics: axis=None folds every element, axis=0 the leading axis (what `ufunc.reduce` does by default)
+        a = self.asarray(a)
+        if axis is None:
+            return ops.reduce(name, a.flatten() if a.ndim > 1 else a)
+        if axis in (0, -a.ndim) and a.ndim >= 1:
+            return ops.reduce(name, a)
+        raise NotImplementedError(f"np.{name}: axis={axis!r} on a device array (only None and 0 have kernels)")
+
     def sum(self, a, axis=None):
-        return ops.reduce("add", self.asarray(a)) if not _is_obj(a) else np.sum(a, axis=axis)
+        return self._fold("add", a, axis) if not _is_obj(a) else np.sum(a, axis=axis)
 
     def prod(self, a, axis=None):
         if _is_obj(a):
@@ -344,10 +353,10 @@ class B200Numpy:
         return ops.reduce("mul", self.asarray(a))
 
     def max(self, a, axis=None):
-        return ops.reduce("max", self.asarray(a)) if not _is_obj(a) else np.max(a, axis=axis)
+        return self._fold("max", a, axis) if not _is_obj(a) else np.max(a, axis=axis)
 
     def min(self, a, axis=None):
-        return ops.reduce("min", self.asarray(a)) if not _is_obj(a) else np.min(a, axis=axis)
+        return self._fold("min", a, axis) if not _is_obj(a) else np.min(a, axis=axis)
 
     def cumsum(self, a, axis=0):
         return ops.scan("add", self.asarray(a))

@@ -20,7 +20,7 @@ OP_ARG, OP_LIT_I64, OP_LIT_F64, OP_SCANVAL = 1, 2, 3, 4
 OPC = {
     "add": 16, "sub": 17, "mul": 18, "div": 19, "pow": 20, "eq": 21, "gt": 22, "lt": 23,
     "max": 24, "min": 25, "fmod": 26, "eq_b": 27, "gt_b": 28, "lt_b": 29, "ne_b": 30, "ge_b": 31, "le_b": 32,
-    "isclose": 33,
+    "isclose": 33, "floordiv": 34, "mod": 35,
     "neg": 48, "abs": 49, "floor": 50, "floor_i64": 51, "trunc": 52, "recip": 53, "not_b": 54,
     "to_f64": 55, "to_i64": 56, "to_f32": 57, "to_b8": 58, "to_i32": 59,
     "sqrt": 64, "exp": 65, "log": 66, "sin": 67, "cos": 68, "tan": 69, "tanh": 70, "ceil": 71, "sign": 72,
@@ -36,7 +36,7 @@ _HOST = {
     "add": np.add, "sub": np.subtract, "mul": np.multiply, "div": np.divide, "pow": np.power,
     "max": np.maximum, "min": np.minimum, "fmod": np.fmod, "eq_b": np.equal, "gt_b": np.greater,
     "lt_b": np.less, "ne_b": np.not_equal, "ge_b": np.greater_equal, "le_b": np.less_equal,
-    "isclose": np.isclose,
+    "isclose": np.isclose, "floordiv": np.floor_divide, "mod": np.remainder,
     "neg": np.negative, "abs": np.abs, "floor": np.floor, "trunc": np.trunc, "ceil": np.ceil,
     "recip": lambda x: np.reciprocal(np.asarray(x, dtype=float))[()], "not_b": np.logical_not,
     "sqrt": np.sqrt, "exp": np.exp, "log": np.log, "sin": np.sin, "cos": np.cos, "tan": np.tan,
@@ -586,8 +586,14 @@ def find_equal(a, b):
         else:
             needle = ctypes.c_double(float(b))
     else:
-        if isinstance(b, (float, np.floating)) and float(b) != int(b):
-            return DeviceArray(torch.empty(0, dtype=torch.int64, device=a._t.device))
+        # np.where(a == b)[0] is empty when an integer array cannot hold b: fractional, non-finite or out of range
+        empty = DeviceArray(torch.empty(0, dtype=torch.int64, device=a._t.device))
+        if isinstance(b, (float, np.floating)):
+            if not np.isfinite(b) or float(b) != int(b):
+                return empty
+        info = np.iinfo(np.int64 if a._t.dtype == torch.int64 else np.int32)
+        if not (info.min <= int(b) <= info.max):
+            return empty
         needle = ctypes.c_int64(int(b)) if a._t.dtype == torch.int64 else ctypes.c_int32(int(b))
     return _select("find", a, needle)
 

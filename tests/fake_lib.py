@@ -81,7 +81,7 @@ def run_program(code, args, scanval=None):
                 pc += 1
                 continue
             pc += 1
-            if 16 <= op <= 33:
+            if 16 <= op <= 35:
                 b = st.pop()
                 a = st.pop()
                 if op in (16, 17, 18, 19, 20, 26):
@@ -120,6 +120,12 @@ def run_program(code, args, scanval=None):
                     r = np.greater_equal(a, b)
                 elif op == 32:
                     r = np.less_equal(a, b)
+                elif op == 34:
+                    with np.errstate(all="ignore"):
+                        r = np.floor_divide(_b2i(a), _b2i(b))
+                elif op == 35:
+                    with np.errstate(all="ignore"):
+                        r = np.remainder(_b2i(a), _b2i(b))
                 else:
                     r = np.isclose(a, b)
                 st.append(r)

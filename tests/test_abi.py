@@ -122,4 +122,36 @@ def test_headline_kernels_have_no_spills_and_vectorise(built_lib, tmp_path):
         sass = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True).stdout
         # reduce: 256-bit LDG (sm_100); scan: 128-bit LDG in the tile kernel + 16-byte cp.async in the pipelined one
         assert re.search(r"LDG\.E[.A-Z0-9]*\.(128|256)", sass), "no wide global loads"
-        assert "DFMA" not in sass.split("kgb_")[1] or True  # fmad=false is asserted numerically on the GPU
+        # -fmad=false: `(x*2)+1` must round twice like NumPy, so neither kernel may contain a fused multiply-add
+        assert "DFMA" not in sass, "FMA contraction is on: a*2+1 would round once instead of twice"
+
+
+def test_groupagg_workspace_scales_with_the_tables_only(built_lib):
+    """Sparse key spaces (table.group_stats passes G = max key + 1) must not reserve the per-CTA partial tables the
+    shared-memory variants use: ~32 B per group beyond 12 800 groups, not ~1920 B."""
+    ws = ctypes.c_size_t()
+    assert built_lib.kgb_groupagg_workspace_bytes(1_000_000, 10_000, ctypes.byref(ws)) == 0
+    small = ws.value
+    assert small >= 160 * 10_000 * 12          # per-CTA partial sums + counts exist for 10 k stations
+    assert built_lib.kgb_groupagg_workspace_bytes(1_000_000, 4_000_000, ctypes.byref(ws)) == 0
+    assert ws.value <= 4_000_000 * 32 + 4096   # four 8-byte tables, nothing per CTA
+    assert built_lib.kgb_groupagg_workspace_bytes(1_000_000, 12_801, ctypes.byref(ws)) == 0
+    assert ws.value <= 12_801 * 32 + 4096
+
+
+def test_floor_divide_and_remainder_programs_type_check(built_lib):
+    """`//` and `%` of the array type have integer kernels (no float64 detour): int op int stays int64."""
+    from klongpy_b200 import _lib, ops
+    for name in ("floordiv", "mod"):
+        code = [ops.OP_ARG, 0, ops.OP_ARG, 1, ops.OPC[name]]
+        c = (ctypes.c_int32 * len(code))(*code)
+        k = (ctypes.c_int32 * 2)(_lib.ARG_ARRAY, _lib.ARG_ARRAY)
+        for dts, want in (((_lib.I64, _lib.I64), _lib.I64), ((_lib.I64, _lib.F64), _lib.F64), ((_lib.F64, _lib.F64), _lib.F64)):
+            d = (ctypes.c_int32 * 2)(*dts)
+            od = ctypes.c_int32()
+            src = ctypes.c_char_p()
+            rc = built_lib.kgb_expr_check(c, len(code), None, 0, k, d, 2, _lib.MODE_MAP, _lib.RED_ADD, 0, ctypes.byref(od),
+                                          ctypes.byref(src))
+            assert rc == 0, built_lib.kgb_last_error()
+            assert od.value == want, (name, dts, od.value)
+            assert (b"kgb_floordiv" if name == "floordiv" else b"kgb_mod") in src.value

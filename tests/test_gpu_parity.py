@@ -771,3 +771,57 @@ def test_grade_general_pass_still_bit_exact(be, K, n, monkeypatch):
         D = dev(be, keys)
         assert np.array_equal(host(be.argsort(D)), O.grade_up(keys)), (name, n)
         assert np.array_equal(host(be.argsort(D, descending=True)), O.grade_down(keys)), (name, n)
+
+
+# ------------------------------------------------------------------------------------------ integer //, %, float32 folds
+def test_floor_divide_and_remainder_match_numpy(be, K):
+    """`//` and `%` of the array type: exact integer kernels (also beyond 2^53, x//0 == x%0 == 0 like NumPy's loops) and
+    NumPy's divmod for floats, bit for bit (signed zeros, infinities and NaN included)."""
+    rng = np.random.default_rng(5)
+    a = np.concatenate([rng.integers(-2**62, 2**62, 50_000), [2**62 + 1, -2**62 - 1, -2**63, 2**63 - 1, 0, -7, 7]])
+    b = np.concatenate([rng.integers(-1000, 1000, 50_000), [1, 1, -1, -1, 5, 3, -3]])
+    A, B = dev(be, a), dev(be, b)
+    with np.errstate(all="ignore"):
+        fd, md = np.floor_divide(a, b), np.remainder(a, b)
+    assert np.array_equal(host(A // B), fd) and host(A // B).dtype == np.int64
+    assert np.array_equal(host(A % B), md) and host(A % B).dtype == np.int64
+    assert np.array_equal(host(A // 7), a // 7) and np.array_equal(host(A % -7), a % -7)
+    with np.errstate(all="ignore"):
+        assert np.array_equal(host(10**18 // B), np.floor_divide(10**18, b))
+    x = np.concatenate([rng.standard_normal(50_000) * 1e3, [0.0, -0.0, 7.5, -7.5, np.inf, -np.inf, np.nan, 1e308, 5.0]])
+    y = np.concatenate([rng.standard_normal(50_000), [3.0, 3.0, 2.5, 2.5, 2.0, 2.0, 2.0, 1e-308, 0.0]])
+    X, Y = dev(be, x), dev(be, y)
+    with np.errstate(all="ignore"):
+        fd, md = np.floor_divide(x, y), np.remainder(x, y)
+    assert np.array_equal(host(X // Y), fd, equal_nan=True) and np.array_equal(np.signbit(host(X // Y)), np.signbit(fd))
+    assert np.array_equal(host(X % Y), md, equal_nan=True) and np.array_equal(np.signbit(host(X % Y)), np.signbit(md))
+    with pytest.raises(TypeError):
+        np.hypot(X, Y)  # no kernel: raises, never a silent host copy
+
+
+@pytest.mark.parametrize("n", [1000, 1_000_003, 20_000_001])
+def test_float32_reduce_and_scan_within_1e6(be, K, n):
+    """north_star tolerance for float32 folds: 1e-6 relative against a float64 evaluation of the same float32 data."""
+    rng = np.random.default_rng(n + 32)
+    x = rng.random(n, dtype=np.float32)
+    X = K.asarray(x)
+    assert X.dtype == np.float32
+    ref = np.add.reduce(x.astype(np.float64))
+    s = K.reduce("add", X)
+    assert host(s).dtype == np.float32
+    assert abs(float(s.item()) - ref) <= 1e-6 * abs(ref)
+    assert float(K.reduce("max", X).item()) == float(x.max()) and float(K.reduce("min", X).item()) == float(x.min())
+    c = host(K.scan("add", X))
+    assert c.dtype == np.float32
+    cref = np.cumsum(x.astype(np.float64))
+    assert np.max(np.abs(c - cref) / cref) <= 1e-6
+    assert np.array_equal(host(K.scan("max", X)), np.maximum.accumulate(x))
+    # a fused float32 tree: +/((x*2)+1)^2 keeps float32 with a python-scalar (weak) literal, like NumPy 2
+    ir = ("reduce", "+", ("binop", "^", ("binop", "+", ("binop", "*", ("var", "_v0"), ("literal", 2)), ("literal", 1)), ("literal", 2)))
+    fn, _ = be.compile_expr_ir(ir, ["x"])
+    got = fn(X)
+    want = np.add.reduce(((x.astype(np.float64) * 2) + 1) ** 2)
+    assert host(got).dtype == np.float32 and abs(float(got.item()) - want) <= 1e-6 * want
+    p = host(K.scan("mul", K.asarray((1 + x[:2000] * 1e-3).astype(np.float32))))
+    pref = np.cumprod((1 + x[:2000] * 1e-3).astype(np.float32).astype(np.float64))
+    assert np.max(np.abs(p - pref) / pref) <= 1e-6

@@ -219,3 +219,31 @@ def table_program_checks(klong, mod):
 def test_table_program_through_interpreter(interp):
     klong, _, mod = interp
     table_program_checks(klong, mod)
+
+
+def test_array_type_has_no_silent_host_fallback(fake_backend):
+    """NumPy ufuncs without a kernel RAISE on device arrays instead of copying them to the host (north_star: no CPU
+    fallback); `//` and `%` follow NumPy's floored semantics exactly, also beyond 2^53; sum/max/min honour `axis`."""
+    be = fake_backend
+    a = be.kg_asarray(np.array([-7, 7, 2**62 + 1], dtype=np.int64))
+    with pytest.raises(TypeError):
+        np.hypot(a, a)
+    with pytest.raises(TypeError):
+        np.add(a, a, dtype=np.float32)
+    h = a.to_numpy()
+    assert np.array_equal((a // 1).to_numpy(), h // 1) and (a // 1).to_numpy()[2] == 2**62 + 1
+    assert np.array_equal((a // 3).to_numpy(), h // 3) and np.array_equal((a % 3).to_numpy(), h % 3)
+    assert np.array_equal((7 % be.kg_asarray(np.array([3, -3, 5]))).to_numpy(), 7 % np.array([3, -3, 5]))
+    assert np.array_equal((a % -3).to_numpy(), h % -3)
+    f = be.kg_asarray(np.array([-7.5, 7.5, 0.0, -0.0]))
+    assert np.array_equal((f % 2.0).to_numpy(), f.to_numpy() % 2.0) and np.array_equal((f // 2.0).to_numpy(), f.to_numpy() // 2.0)
+    m = be.kg_asarray(np.arange(6.0).reshape(2, 3))
+    assert m.sum().item() == 15.0 and np.array_equal(m.sum(axis=0).to_numpy(), [3.0, 5.0, 7.0])
+    assert be.np.sum(m).item() == 15.0 and be.np.max(m).item() == 5.0 and be.np.min(m, axis=0).to_numpy().tolist() == [0.0, 1.0, 2.0]
+    with pytest.raises(NotImplementedError):
+        m.sum(axis=1)
+    from klongpy_b200 import ops
+    ints = be.kg_asarray(np.array([1, 2, 3], dtype=np.int64))
+    for needle in (float("inf"), float("nan"), 2.5, 2**70):
+        assert ops.find_equal(ints, needle).to_numpy().tolist() == []
+    assert ops.find_equal(ints, 2.0).to_numpy().tolist() == [1]
