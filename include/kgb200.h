@@ -238,6 +238,20 @@ int kgb_groupagg_merge(double* min_io, double* max_io, double* sum_io, int64_t* 
                        const double* min_in, const double* max_in, const double* sum_in,
                        const int64_t* count_in, int64_t n_groups, void* stream);
 
+/* The exchange of the sharded aggregation (north_star: "hash-partitioned NCCL all-to-all").  A rank's
+   tables travel as one block of 8-byte lanes [4][G] = {min, max, sum as float64 bits, count as int64}.
+   kgb_groupagg_fold: `n_blocks` blocks (block r at blocks + r*block_stride lanes), folded in block order -> tables;
+     after one all_gather of the ranks' blocks this is the whole merge (small G), after the all-to-all it merges the
+     owner's slices.
+   kgb_groupagg_to_owners: local block -> send buffer [world][4][B], B = ceil(G/world); station s goes to its owner
+     hash(s) = s mod world, slot s / world (empty slots carry +inf / -inf / 0 / 0).
+   kgb_groupagg_from_owners: the all-gathered owner slices [world][4][B] -> the four tables in station order. */
+int kgb_groupagg_fold(const void* blocks, int64_t n_blocks, int64_t n_groups, int64_t block_stride,
+                      double* min_out, double* max_out, double* sum_out, int64_t* count_out, void* stream);
+int kgb_groupagg_to_owners(const void* block, int64_t n_groups, int64_t world, void* send, void* stream);
+int kgb_groupagg_from_owners(const void* full, int64_t n_groups, int64_t world, double* min_out, double* max_out,
+                             double* sum_out, int64_t* count_out, void* stream);
+
 /* ---------------------------------------------------------------- 1brc text ingest --------------- */
 /* Replaces the per-line Python loop of examples/1brc/par.py:57-88 (`location, measurement = line.split(";")`,
    `np.asarray(temps, dtype=float)`) and the string grouping `=s` of worker.kg:5: a device buffer of complete lines

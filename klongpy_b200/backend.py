@@ -189,7 +189,8 @@ class B200BackendProvider(_Base):
         """Stable grade (writer.py:114-117 fast path)."""
         if not isinstance(a, DeviceArray):
             a = ops.asarray(a, device=self._device)
-        return ops.argsort(a, descending=descending)
+        # deferred: `a@<a` never builds the permutation (verbs.at_index); every other consumer materialises it
+        return ops.grade_deferred(a, descending=descending)
 
     def safe_equal(self, x, y):
         if isinstance(x, DeviceArray) or isinstance(y, DeviceArray):

@@ -431,9 +431,100 @@ __global__ void __launch_bounds__(256) groupagg_merge_kernel(double* mn, double*
     ct[g] = ct[g] + ct2[g];
 }
 
+// ---- multi-GPU exchange (dist.sharded_groupagg).  A rank's four tables travel as ONE block of 8-byte lanes
+// [4][G] = {min, max, sum (float64 bit patterns), count (int64)}.
+// fold: `w` such blocks, in rank order (bit-identical on every rank and every run) -> the four result tables.
+__global__ void __launch_bounds__(256) groupagg_fold_kernel(const u64* __restrict__ blocks, i64 w, i64 G, i64 stride, double* mn,
+                                                             double* mx, double* sm, i64* ct) {
+    const i64 g = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    double a = __longlong_as_double((i64)blocks[g]), b = __longlong_as_double((i64)blocks[G + g]);
+    double s = __longlong_as_double((i64)blocks[2 * G + g]);
+    i64 c = (i64)blocks[3 * G + g];
+    for (i64 r = 1; r < w; r++) {
+        const u64* t = blocks + r * stride;
+        a = nanpropagating_min(a, __longlong_as_double((i64)t[g]));
+        b = nanpropagating_max(b, __longlong_as_double((i64)t[G + g]));
+        s = s + __longlong_as_double((i64)t[2 * G + g]);
+        c += (i64)t[3 * G + g];
+    }
+    mn[g] = a;
+    mx[g] = b;
+    sm[g] = s;
+    ct[g] = c;
+}
+// hash partition: station s is owned by rank s mod w (the hash of a dense station id), slot s / w of the owner's slice.
+// to_owners: local [4][G] block -> send buffer [w][4][B] (B = ceil(G / w); missing slots carry the fold's identities).
+__global__ void __launch_bounds__(256) groupagg_to_owners_kernel(const u64* __restrict__ block, i64 G, i64 w, i64 B, u64* __restrict__ send) {
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;  // index into [w][B]
+    if (i >= w * B) return;
+    const i64 r = i / B, slot = i - r * B, st = slot * w + r;
+    u64* dst = send + r * 4 * B + slot;
+    if (st < G) {
+        dst[0] = block[st];
+        dst[B] = block[G + st];
+        dst[2 * B] = block[2 * G + st];
+        dst[3 * B] = block[3 * G + st];
+    } else {
+        dst[0] = 0x7ff0000000000000ull;      // +inf
+        dst[B] = 0xfff0000000000000ull;      // -inf
+        dst[2 * B] = 0;
+        dst[3 * B] = 0;
+    }
+}
+// from_owners: all-gathered owner slices [w][4][B] -> the four full tables in station order
+__global__ void __launch_bounds__(256) groupagg_from_owners_kernel(const u64* __restrict__ full, i64 G, i64 w, i64 B, double* mn,
+                                                                    double* mx, double* sm, i64* ct) {
+    const i64 st = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (st >= G) return;
+    const i64 r = st % w, slot = st / w;
+    const u64* src = full + r * 4 * B + slot;
+    mn[st] = __longlong_as_double((i64)src[0]);
+    mx[st] = __longlong_as_double((i64)src[B]);
+    sm[st] = __longlong_as_double((i64)src[2 * B]);
+    ct[st] = (i64)src[3 * B];
+}
+
 }  // namespace kgb
 
 using namespace kgb;
+
+extern "C" int kgb_groupagg_fold(const void* blocks, int64_t n_blocks, int64_t n_groups, int64_t block_stride, double* min_out,
+                                 double* max_out, double* sum_out, int64_t* count_out, void* stream) {
+    KGB_REQUIRE(current_device() >= 0, "kgb_init() has not been called on this thread");
+    KGB_REQUIRE(n_blocks >= 1 && n_groups >= 0 && block_stride >= 4 * n_groups, "kgb_groupagg_fold: bad sizes");
+    if (n_groups == 0) return KGB_OK;
+    KGB_REQUIRE(blocks && min_out && max_out && sum_out && count_out, "kgb_groupagg_fold: null pointer");
+    groupagg_fold_kernel<<<(unsigned)((n_groups + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (const u64*)blocks, n_blocks, n_groups, block_stride, min_out, max_out, sum_out, (i64*)count_out);
+    KGB_CUDA_CHECK(cudaGetLastError());
+    return KGB_OK;
+}
+
+extern "C" int kgb_groupagg_to_owners(const void* block, int64_t n_groups, int64_t world, void* send, void* stream) {
+    KGB_REQUIRE(current_device() >= 0, "kgb_init() has not been called on this thread");
+    KGB_REQUIRE(n_groups >= 0 && world >= 1, "kgb_groupagg_to_owners: bad sizes");
+    if (n_groups == 0) return KGB_OK;
+    KGB_REQUIRE(block && send, "kgb_groupagg_to_owners: null pointer");
+    const i64 B = (n_groups + world - 1) / world;
+    groupagg_to_owners_kernel<<<(unsigned)((world * B + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (const u64*)block, n_groups, world, B, (u64*)send);
+    KGB_CUDA_CHECK(cudaGetLastError());
+    return KGB_OK;
+}
+
+extern "C" int kgb_groupagg_from_owners(const void* full, int64_t n_groups, int64_t world, double* min_out, double* max_out,
+                                        double* sum_out, int64_t* count_out, void* stream) {
+    KGB_REQUIRE(current_device() >= 0, "kgb_init() has not been called on this thread");
+    KGB_REQUIRE(n_groups >= 0 && world >= 1, "kgb_groupagg_from_owners: bad sizes");
+    if (n_groups == 0) return KGB_OK;
+    KGB_REQUIRE(full && min_out && max_out && sum_out && count_out, "kgb_groupagg_from_owners: null pointer");
+    const i64 B = (n_groups + world - 1) / world;
+    groupagg_from_owners_kernel<<<(unsigned)((n_groups + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (const u64*)full, n_groups, world, B, min_out, max_out, sum_out, (i64*)count_out);
+    KGB_CUDA_CHECK(cudaGetLastError());
+    return KGB_OK;
+}
 
 extern "C" int kgb_groupagg_workspace_bytes(int64_t n, int64_t n_groups, size_t* out_bytes) {
     (void)n;

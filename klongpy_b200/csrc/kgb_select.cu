@@ -110,11 +110,18 @@ __device__ __forceinline__ u32 uniq_cache_index(u64 k, int log2_entries) {
     return h & ((1u << log2_entries) - 1u);
 }
 
-template <typename T> __device__ __forceinline__ u64 uniq_bits(T v);
-template <> __device__ __forceinline__ u64 uniq_bits<u64>(u64 v) { return v; }
-template <> __device__ __forceinline__ u64 uniq_bits<u32>(u32 v) { return (u64)v; }
+// table key of a row.  Float rows (FLT) collapse every NaN — any sign, any payload — to ONE key, like the sort path's
+// KeyCodec<*_RAW> and like the reference, which keys its set on str(x) ('nan'); -0.0 and +0.0 stay distinct.
+template <typename T, bool FLT> __device__ __forceinline__ u64 uniq_bits(T v) {
+    if (sizeof(T) == 8) {
+        const u64 b = (u64)v;
+        return (FLT && (b & 0x7fffffffffffffffull) > 0x7ff0000000000000ull) ? 0x7ff8000000000000ull : b;
+    }
+    const u32 b = (u32)v;
+    return (u64)((FLT && (b & 0x7fffffffu) > 0x7f800000u) ? 0x7fc00000u : b);
+}
 
-template <typename T>
+template <typename T, bool FLT>
 __global__ void __launch_bounds__(256) uniq_insert_kernel(const T* __restrict__ a, i64 m, i64 step, UniqSlot* __restrict__ tab,
                                                            UniqCtl* __restrict__ ctl) {
     // visits rows j * step for j < m: step 1 is the full pass, a larger step the cardinality probe on a strided sample
@@ -135,7 +142,7 @@ __global__ void __launch_bounds__(256) uniq_insert_kernel(const T* __restrict__ 
             const i64 j = base + u * 256 + threadIdx.x;
             if (j >= m || bail) continue;
             const i64 i = j * step;
-            const u64 k = uniq_bits<T>(v[u]);
+            const u64 k = uniq_bits<T, FLT>(v[u]);
             if (k == UNIQ_EMPTY) {
                 if ((u64)i < *(volatile unsigned long long*)&ctl->special_first) atomicMin(&ctl->special_first, (unsigned long long)i);
                 continue;
@@ -246,7 +253,7 @@ constexpr size_t uniq_cached_smem() { return (size_t)UNIQ_CACHE * 8; }
 // three-stage cp.async ring (64 KB in flight per SM) was slower (0.86 / 0.55 / 0.65 ms): ncu r01y_uniq_cached_raw.csv
 // shows the pass issue-bound (126 warp-instructions per 32 rows, most of them the 64-bit hash and index arithmetic),
 // not latency-bound, so the ring's extra shared-memory traffic only added work.
-template <typename T>
+template <typename T, bool FLT>
 __global__ void __launch_bounds__(UNIQ_CT, 1) uniq_insert_cached_kernel(const T* __restrict__ a, i64 n, UniqSlot* __restrict__ tab,
                                                                         UniqCtl* __restrict__ ctl, unsigned long long probe_limit) {
     extern __shared__ __align__(16) u64 s_cache[];
@@ -291,14 +298,14 @@ __global__ void __launch_bounds__(UNIQ_CT, 1) uniq_insert_cached_kernel(const T*
         if (base + tile <= n) {
 #pragma unroll
             for (int u = 0; u < U; u++) {
-                const u64 k = uniq_bits<T>(cur[u]);
+                const u64 k = uniq_bits<T, FLT>(cur[u]);
                 ci[u] = uniq_cache_index(k, UNIQ_CACHE_LOG2);
                 miss |= (s_cache[ci[u]] != k ? 1u : 0u) << u;
             }
         } else {
 #pragma unroll
             for (int u = 0; u < U; u++) {
-                const u64 k = uniq_bits<T>(cur[u]);
+                const u64 k = uniq_bits<T, FLT>(cur[u]);
                 ci[u] = uniq_cache_index(k, UNIQ_CACHE_LOG2);
                 if (base + u * UNIQ_CT + tid < n && s_cache[ci[u]] != k) miss |= 1u << u;
             }
@@ -310,8 +317,8 @@ __global__ void __launch_bounds__(UNIQ_CT, 1) uniq_insert_cached_kernel(const T*
             u32 hs[U];
 #pragma unroll
             for (int u = 0; u < U; u++)
-                if ((miss & (1u << u)) && uniq_bits<T>(cur[u]) != UNIQ_EMPTY) {
-                    hs[u] = (u32)(uniq_hash(uniq_bits<T>(cur[u])) & (UNIQ_SLOTS - 1));
+                if ((miss & (1u << u)) && uniq_bits<T, FLT>(cur[u]) != UNIQ_EMPTY) {
+                    hs[u] = (u32)(uniq_hash(uniq_bits<T, FLT>(cur[u])) & (UNIQ_SLOTS - 1));
                     asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];"
                                  : "=l"(e[u].x), "=l"(e[u].y)
                                  : "l"(&tab[hs[u]])
@@ -321,7 +328,7 @@ __global__ void __launch_bounds__(UNIQ_CT, 1) uniq_insert_cached_kernel(const T*
             for (int u = 0; u < U; u++)
                 if (miss & (1u << u)) {
                     const i64 i = base + u * UNIQ_CT + tid;
-                    const u64 k = uniq_bits<T>(cur[u]);
+                    const u64 k = uniq_bits<T, FLT>(cur[u]);
                     if (k == UNIQ_EMPTY) {  // the table's own "empty" pattern: tracked beside the table, cached like any key
                         atomicMin(&ctl->special_first, (unsigned long long)i);
                     } else if (e[u].x == k) {  // the common case: present; touch it only if this row comes earlier
@@ -343,7 +350,7 @@ __global__ void __launch_bounds__(UNIQ_CT, 1) uniq_insert_cached_kernel(const T*
         if (miss) {
 #pragma unroll
             for (int u = 0; u < U; u++)
-                if (miss & (1u << u)) s_cache[ci[u]] = uniq_bits<T>(cur[u]);
+                if (miss & (1u << u)) s_cache[ci[u]] = uniq_bits<T, FLT>(cur[u]);
         }
         return false;
     };
@@ -535,10 +542,14 @@ extern "C" int kgb_unique_first(const void* a, int32_t dtype, int64_t n, void* o
             long long ib = (m + 1023) / 1024;
             const long long icap = (long long)sm_count() * 8;
             if (ib > icap) ib = icap;
-            if (dtype_size(dtype) == 8)
-                uniq_insert_kernel<u64><<<(unsigned)ib, 256, 0, st>>>((const u64*)a, m, step, tab, ctl);
+            if (dtype == KGB_F64)
+                uniq_insert_kernel<u64, true><<<(unsigned)ib, 256, 0, st>>>((const u64*)a, m, step, tab, ctl);
+            else if (dtype == KGB_F32)
+                uniq_insert_kernel<u32, true><<<(unsigned)ib, 256, 0, st>>>((const u32*)a, m, step, tab, ctl);
+            else if (dtype_size(dtype) == 8)
+                uniq_insert_kernel<u64, false><<<(unsigned)ib, 256, 0, st>>>((const u64*)a, m, step, tab, ctl);
             else
-                uniq_insert_kernel<u32><<<(unsigned)ib, 256, 0, st>>>((const u32*)a, m, step, tab, ctl);
+                uniq_insert_kernel<u32, false><<<(unsigned)ib, 256, 0, st>>>((const u32*)a, m, step, tab, ctl);
         };
         UniqCtl h;
         // cardinality probe: 512k rows spread over the whole input go in first (they are real rows, nothing is wasted);
@@ -561,16 +572,22 @@ extern "C" int kgb_unique_first(const void* a, int32_t dtype, int64_t n, void* o
                 const int dv = current_device();
                 const size_t smem8 = uniq_cached_smem(), smem4 = uniq_cached_smem();
                 if (dv >= 0 && dv < 64 && !opted[dv]) {
-                    KGB_CUDA_CHECK(cudaFuncSetAttribute(uniq_insert_cached_kernel<u64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
-                    KGB_CUDA_CHECK(cudaFuncSetAttribute(uniq_insert_cached_kernel<u32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+                    KGB_CUDA_CHECK(cudaFuncSetAttribute(uniq_insert_cached_kernel<u64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+                    KGB_CUDA_CHECK(cudaFuncSetAttribute(uniq_insert_cached_kernel<u32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+                    KGB_CUDA_CHECK(cudaFuncSetAttribute(uniq_insert_cached_kernel<u64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+                    KGB_CUDA_CHECK(cudaFuncSetAttribute(uniq_insert_cached_kernel<u32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
                     opted[dv] = true;
                 }
                 long long cb = (n + UNIQ_CT * UNIQ_CU - 1) / (UNIQ_CT * UNIQ_CU);
                 if (cb > sm_count()) cb = sm_count();
-                if (dtype_size(dtype) == 8)
-                    uniq_insert_cached_kernel<u64><<<(unsigned)cb, UNIQ_CT, smem8, st>>>((const u64*)a, n, tab, ctl, PROBE_LIMIT);
+                if (dtype == KGB_F64)
+                    uniq_insert_cached_kernel<u64, true><<<(unsigned)cb, UNIQ_CT, smem8, st>>>((const u64*)a, n, tab, ctl, PROBE_LIMIT);
+                else if (dtype == KGB_F32)
+                    uniq_insert_cached_kernel<u32, true><<<(unsigned)cb, UNIQ_CT, smem4, st>>>((const u32*)a, n, tab, ctl, PROBE_LIMIT);
+                else if (dtype_size(dtype) == 8)
+                    uniq_insert_cached_kernel<u64, false><<<(unsigned)cb, UNIQ_CT, smem8, st>>>((const u64*)a, n, tab, ctl, PROBE_LIMIT);
                 else
-                    uniq_insert_cached_kernel<u32><<<(unsigned)cb, UNIQ_CT, smem4, st>>>((const u32*)a, n, tab, ctl, PROBE_LIMIT);
+                    uniq_insert_cached_kernel<u32, false><<<(unsigned)cb, UNIQ_CT, smem4, st>>>((const u32*)a, n, tab, ctl, PROBE_LIMIT);
             } else {
                 insert(n, 1);
             }

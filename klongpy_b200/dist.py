@@ -9,8 +9,9 @@ expressions need no exchange.  The primitives with a real exchange step:
     NCCL's choice, so it is not used for float sums).
   * scan    `+\\ *\\ |\\ &\\` : per-rank fold -> all_gather of totals -> exclusive prefix over lower ranks = the
     shard's carried offset -> ONE local decoupled-look-back scan seeded with that offset (24 B/elem/rank).
-  * grouped min/mean/max : per-rank partial G x 4 tables -> all_to_all of the per-owner table slices
-    (station block s // B owned by rank s // B) -> merge -> all_gather of the final slices.
+  * grouped min/mean/max : per-rank partial G x 4 tables -> hash-partitioned all_to_all (station s owned by rank
+    s mod w) -> one rank-ordered fold kernel -> all_gather of the owners' results; small tables (10 k stations) take
+    ONE all_gather + one fold kernel instead (sharded_groupagg).
 
   * find `a?b` : local compaction -> all_gather of (shard length, hit count) -> global positions (sharded_find).
   * autograd : the loss `+/` is a sharded reduce whose tape holds only the local fused node (sharded_loss_sum);
@@ -72,10 +73,18 @@ def sharded_reduce_with_total(code, red, args, scan_code, scan_red):
     red = ops.RED[red] if not isinstance(red, int) else red
     scan_red = ops.RED[scan_red] if not isinstance(scan_red, int) else scan_red
     part, total = ops.reduce2(code, red, scan_code, scan_red, args)
+    return exchange_fold_and_offset(part, total, red, scan_red)
+
+
+def exchange_fold_and_offset(part, total, red, scan_red):
+    """This rank's {partial fold, shard total} (0-d device values) -> (global fold, exclusive scan offset of this rank or
+    None on rank 0) with ONE all_gather of 16 bytes per rank and the same fixed-order combine on every rank."""
+    red = ops.RED[red] if not isinstance(red, int) else red
+    scan_red = ops.RED[scan_red] if not isinstance(scan_red, int) else scan_red
     if world() == 1:
         return part, None
     w = world()
-    # one all_gather of the 16-byte pair {partial fold, shard total} (raw bytes: the two may differ in dtype)
+    # raw bytes: the two values may differ in dtype
     pair = torch.cat([part._t.reshape(1).view(torch.uint8), total._t.reshape(1).view(torch.uint8)])
     allp = torch.empty(16 * w, dtype=torch.uint8, device=pair.device)
     td.all_gather_into_tensor(allp, pair)
@@ -120,41 +129,57 @@ def sharded_scan(code, args, red):
     return ops.run(code, list(args) + [off], mode=_lib.MODE_SCAN, red=red, code2=seed)
 
 
-def sharded_groupagg(keys, vals, n_groups):
-    """Grouped (min, max, sum, count) over block-sharded rows.  Every rank returns the full G-entry tables."""
+ALLGATHER_LIMIT_BYTES = 64 << 20  # total bytes of all ranks' table blocks up to which one all_gather is the exchange
+
+
+def sharded_groupagg(keys, vals, n_groups, exchange="auto"):
+    """Grouped (min, max, sum, count) over block-sharded rows.  Every rank returns the full G-entry tables.
+
+    The per-rank partial tables are one block of 8-byte lanes [4][G] (written by the aggregation kernel in place).
+      * "alltoall" — the hash-partitioned exchange north_star names: station s is owned by rank hash(s) = s mod w;
+        kgb_groupagg_to_owners packs the block per owner, ONE all_to_all moves the slices, ONE kgb_groupagg_fold merges
+        the w slices of an owner in rank order, ONE all_gather returns the owners' results and
+        kgb_groupagg_from_owners puts them back in station order.  Per rank it moves 2 blocks whatever w is.
+      * "allgather" — for small tables (10 k stations: 320 KB per rank) the exchange is latency-, not bandwidth-bound:
+        ONE all_gather of the blocks + ONE kgb_groupagg_fold over the w blocks in rank order (w blocks per rank moved,
+        one collective instead of two).
+      * "auto" — allgather while w * block stays under ALLGATHER_LIMIT_BYTES, else alltoall.
+    Both fold in rank order, so results are bit-identical on every rank and every run."""
     w = world()
-    mn, mx, sm, ct = ops.groupagg(keys, vals, n_groups)
-    if w == 1:
-        return mn, mx, sm, ct
     G = int(n_groups)
-    B = (G + w - 1) // w  # stations [r*B, (r+1)*B) are owned by rank r
-    dev = mn._t.device
+    dev = keys._t.device
+    i64, f64 = torch.int64, torch.float64
+    block = torch.empty((4, G), dtype=i64, device=dev)
+    tabs = (block[0].view(f64), block[1].view(f64), block[2].view(f64), block[3])
+    ops.groupagg(keys, vals, G, tables=tabs, accumulate=False)
+    if w == 1:
+        return tuple(DeviceArray(t) for t in tabs)
     lib, stream = ops._lib_for(dev)
-    # One exchange buffer for the four tables (all 8-byte lanes; float64 travels as its bit pattern):
-    # send[r, j, :] = table j of this rank's partials for the stations rank r owns.
-    i64 = torch.int64
-    pad = torch.empty((4, w * B), dtype=i64, device=dev)
-    if w * B > G:
-        pad[0, G:] = torch.tensor(float("inf"), dtype=torch.float64).view(i64).item()
-        pad[1, G:] = torch.tensor(float("-inf"), dtype=torch.float64).view(i64).item()
-        pad[2:, G:] = 0
-    for j, t in enumerate((mn._t, mx._t, sm._t, ct._t)):
-        pad[j, :G].copy_(t.view(i64) if t.dtype != i64 else t)
-    send = pad.view(4, w, B).permute(1, 0, 2).contiguous()
-    recv = torch.empty_like(send)
-    td.all_to_all_single(recv, send)  # recv[k] = rank k's partial tables for MY stations
-    acc = recv[0]
-    f64 = torch.float64
-    for k in range(1, w):  # fixed rank order: identical results on every run
-        sl = recv[k]
-        _lib.check(lib.kgb_groupagg_merge(acc[0].data_ptr(), acc[1].data_ptr(), acc[2].data_ptr(), acc[3].data_ptr(),
-                                          sl[0].data_ptr(), sl[1].data_ptr(), sl[2].data_ptr(), sl[3].data_ptr(), B,
-                                          stream), "kgb_groupagg_merge")
-    full = torch.empty(w * 4 * B, dtype=i64, device=dev)
-    td.all_gather_into_tensor(full, acc.contiguous().view(-1))
-    tabs = full.view(w, 4, B).permute(1, 0, 2).reshape(4, w * B)[:, :G].contiguous()
-    return (DeviceArray(tabs[0].view(f64)), DeviceArray(tabs[1].view(f64)), DeviceArray(tabs[2].view(f64)),
-            DeviceArray(tabs[3] if ct._t.dtype == i64 else tabs[3].view(ct._t.dtype)))
+    if exchange == "auto":
+        exchange = "allgather" if w * 32 * G <= ALLGATHER_LIMIT_BYTES else "alltoall"
+    out = torch.empty((4, G), dtype=i64, device=dev)
+    o = (out[0].view(f64), out[1].view(f64), out[2].view(f64), out[3])
+    if exchange == "allgather":
+        allb = torch.empty((w, 4, G), dtype=i64, device=dev)
+        td.all_gather_into_tensor(allb.view(-1), block.view(-1))
+        _lib.check(lib.kgb_groupagg_fold(allb.data_ptr(), w, G, 4 * G, o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(),
+                                         o[3].data_ptr(), stream), "kgb_groupagg_fold")
+    elif exchange == "alltoall":
+        B = (G + w - 1) // w
+        send = torch.empty((w, 4, B), dtype=i64, device=dev)
+        _lib.check(lib.kgb_groupagg_to_owners(block.data_ptr(), G, w, send.data_ptr(), stream), "kgb_groupagg_to_owners")
+        recv = torch.empty_like(send)
+        td.all_to_all_single(recv.view(-1), send.view(-1))  # recv[k] = rank k's partials for the stations I own
+        mine = torch.empty((4, B), dtype=i64, device=dev)
+        _lib.check(lib.kgb_groupagg_fold(recv.data_ptr(), w, B, 4 * B, mine[0].data_ptr(), mine[1].data_ptr(),
+                                         mine[2].data_ptr(), mine[3].data_ptr(), stream), "kgb_groupagg_fold")
+        full = torch.empty((w, 4, B), dtype=i64, device=dev)
+        td.all_gather_into_tensor(full.view(-1), mine.view(-1))
+        _lib.check(lib.kgb_groupagg_from_owners(full.data_ptr(), G, w, o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(),
+                                                o[3].data_ptr(), stream), "kgb_groupagg_from_owners")
+    else:
+        raise ValueError(f"sharded_groupagg: unknown exchange {exchange!r}")
+    return tuple(DeviceArray(t) for t in o)
 
 
 def sharded_find(a, needle, n_global=None):

@@ -41,6 +41,20 @@ class Node:
         self.uses = 0
 
 
+class GradeNode:
+    """`<a` / `>a` that has not been launched yet (always on, independent of ENABLED).  Klong sorts with `a@<a`
+    (monads.py:143-179: "To sort a list a, use a@<a"): when the permutation's only consumer is that `@` on the same
+    array, the sorted keys come straight out of the last radix pass (kgb_argsort's keys_sorted_out) and the 24 B/elem
+    random gather never runs.  Any other use materialises the permutation with the ordinary grade."""
+    __slots__ = ("source", "descending", "shape", "kdt", "device", "uses", "args", "code")
+
+    def __init__(self, source, descending):
+        self.source, self.descending = source, bool(descending)
+        self.shape, self.kdt, self.device = tuple(source.shape), _lib.I64, source.device
+        self.uses = 1   # never inlined into an elementwise program: consumers materialise it
+        self.args, self.code = [], ()
+
+
 def _is_lazy(a):
     from .array import DeviceArray
     return isinstance(a, DeviceArray) and a._tensor is None
@@ -149,4 +163,6 @@ def defer(code, args):
 def materialize(node):
     """Launch the deferred program: one fused kernel (and one autograd node when an operand is on the tape)."""
     from . import ops
+    if isinstance(node, GradeNode):
+        return ops.argsort(node.source, descending=node.descending)._t
     return ops.run(node.code, node.args, _no_defer=True)._t

@@ -508,6 +508,27 @@ def argsort(a, descending=False, return_sorted=False):
     return DeviceArray(idx)
 
 
+def sort_values(a, descending=False):
+    """`a@<a` / `a@>a`: the sorted keys, written by the last radix pass itself (no gather through the permutation)."""
+    return argsort(a, descending=descending, return_sorted=True)[1]
+
+
+def grade_deferred(a, descending=False):
+    """`<a` / `>a` as a deferred permutation (lazy.GradeNode): materialised by any use except `a@<a`."""
+    from . import lazy
+    if a._t.dim() != 1 or a._t.numel() == 0 or a._t.dtype == torch.bool:
+        return argsort(a, descending=descending)
+    return DeviceArray._deferred(lazy.GradeNode(a, descending))
+
+
+def grade_source(b):
+    """(source array, descending) when `b` is a still-deferred grade, else None."""
+    from . import lazy
+    if isinstance(b, DeviceArray) and b._tensor is None and isinstance(b._node, lazy.GradeNode):
+        return b._node.source, b._node.descending
+    return None
+
+
 def group(a):
     """`=a` (monads.py:182-204): -> (order int64[n], starts int64[G+1]) with one D2H read of G."""
     a = contiguous(a)
@@ -717,8 +738,9 @@ def array_equal(a, b):
     return bool(flag.item())
 
 
-def groupagg(keys, vals, n_groups, tables=None):
-    """1brc-style grouped (min, max, sum, count) (examples/1brc/worker.kg:3-5)."""
+def groupagg(keys, vals, n_groups, tables=None, accumulate=None):
+    """1brc-style grouped (min, max, sum, count) (examples/1brc/worker.kg:3-5).  `tables`: four preallocated result
+    arrays; they are merged into (the `merge` step) unless accumulate=False."""
     keys, vals = contiguous(keys), contiguous(vals)
     dev = keys._t.device
     lib, stream = _lib_for(dev)
@@ -730,8 +752,8 @@ def groupagg(keys, vals, n_groups, tables=None):
     if vals._t.numel() != n:
         raise ValueError("groupagg: keys and values differ in length")
     G = int(n_groups)
-    acc = tables is not None
-    if not acc:
+    acc = (tables is not None) if accumulate is None else bool(accumulate)
+    if tables is None:
         tables = (torch.empty(G, dtype=torch.float64, device=dev), torch.empty(G, dtype=torch.float64, device=dev),
                   torch.empty(G, dtype=torch.float64, device=dev), torch.empty(G, dtype=torch.int64, device=dev))
     else:

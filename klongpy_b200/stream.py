@@ -71,3 +71,55 @@ class HostStream:
         for s in (self.s_in, self.s_cmp, self.s_out):
             cur.wait_stream(s)
         return acc
+
+    def sharded_reduce_and_scan(self, host_x, reduce_code, reduce_red, scan_code, scan_red, host_scan_out):
+        """The same step for one rank's shard of a vector block-sharded over `torch.distributed` ranks (pinned host in,
+        pinned host out).  The scan of a shard needs every lower rank's total first, so the step has two phases:
+          1. chunks go host -> device into a RESIDENT copy of the shard; each chunk is folded as it lands by ONE
+             two-output reduce (partial of `reduce_code` + total of `scan_code`), partials combine on the device in
+             chunk order; then ONE all_gather of 16 bytes per rank (dist.exchange_fold_and_offset);
+          2. the resident shard is scanned chunk by chunk, seeded with the rank's exclusive offset and then with each
+             chunk's last element, while the previous chunk's scan goes device -> host.
+        Returns the global fold (0-d device value, identical on every rank)."""
+        from . import dist
+        n = host_x.numel()
+        red = ops.RED[reduce_red] if not isinstance(reduce_red, int) else reduce_red
+        sred = ops.RED[scan_red] if not isinstance(scan_red, int) else scan_red
+        if getattr(self, "resident", None) is None or self.resident.numel() < n or self.resident.dtype != host_x.dtype:
+            self.resident = torch.empty(n, dtype=host_x.dtype, device=self.device)
+        cur = torch.cuda.current_stream(self.device)
+        for s in (self.s_in, self.s_cmp, self.s_out):
+            s.wait_stream(cur)
+        nchunks = (n + self.chunk - 1) // self.chunk
+        acc = tot = None
+        for k in range(nchunks):
+            lo, hi = k * self.chunk, min(n, (k + 1) * self.chunk)
+            with torch.cuda.stream(self.s_in):
+                xin = self.resident[lo:hi]
+                xin.copy_(host_x[lo:hi], non_blocking=True)
+                ev_in = torch.cuda.Event()
+                ev_in.record(self.s_in)
+            with torch.cuda.stream(self.s_cmp):
+                self.s_cmp.wait_event(ev_in)
+                part, total = ops.reduce2(reduce_code, red, scan_code, sred, [DeviceArray(xin)])
+                acc = part if acc is None else ops.binary(_RED_NAME[red], acc, part)
+                tot = total if tot is None else ops.binary(_RED_NAME[sred], tot, total)
+        with torch.cuda.stream(self.s_cmp):
+            fold, carry = dist.exchange_fold_and_offset(acc, tot, red, sred)  # NCCL runs on the compute stream
+            for k in range(nchunks):
+                lo, hi = k * self.chunk, min(n, (k + 1) * self.chunk)
+                X = DeviceArray(self.resident[lo:hi])
+                if carry is None:
+                    sc = ops.run(scan_code, [X], mode=_lib.MODE_SCAN, red=sred)
+                else:
+                    sc = ops.run(scan_code, [X, carry], mode=_lib.MODE_SCAN, red=sred, code2=[ops.OP_ARG, 1])
+                carry = DeviceArray(sc._t[-1])
+                ev_c = torch.cuda.Event()
+                ev_c.record(self.s_cmp)
+                with torch.cuda.stream(self.s_out):
+                    self.s_out.wait_event(ev_c)
+                    host_scan_out[lo:hi].copy_(sc._t, non_blocking=True)
+                    sc._t.record_stream(self.s_out)
+        for s in (self.s_in, self.s_cmp, self.s_out):
+            cur.wait_stream(s)
+        return fold

@@ -7,10 +7,17 @@ on the b200 backend `install(klong)` replaces the affected entries of `klong._vm
 built at interpreter.py:252-253) with device-aware versions.  Every override handles ONLY device arrays and
 defers to the reference implementation for everything else (strings, dicts, host object arrays).
 """
+import os
+import warnings
+
 import numpy as np
 
 from . import ops
 from .array import DeviceArray
+
+
+class HostRoundTripWarning(UserWarning):
+    """A structural verb (`:= :- :_ :^ :# $ :$`) moved device operands to the host and back (see install())."""
 
 
 def _is_dev(x):
@@ -113,6 +120,11 @@ def install(klong):
     def at_index(a, b):  # a@b  (dyads.py:140-191)
         if _is_dev(a):
             if _is_dev(b):
+                g = ops.grade_source(b)
+                if g is not None and (g[0] is a or (g[0]._tensor is not None and a._tensor is not None and
+                                                    g[0]._tensor.data_ptr() == a._tensor.data_ptr() and g[0].shape == a.shape
+                                                    and g[0].dtype == a.dtype)):
+                    return ops.sort_values(a, descending=g[1])  # a@<a: sorted keys from the last radix pass, no gather
                 return a[b] if b.ndim == 0 else (ops.gather(a, b) if b.size else DeviceArray(a._t[:0]))
             if isinstance(b, (int, np.integer)) and not isinstance(b, bool):
                 return a[int(b)]
@@ -178,10 +190,15 @@ def install(klong):
             return [_to_host(y) for y in x]
         return x
 
-    def _via_host(fn):
+    def _via_host(fn, sym):
         def wrapped(a, b):
             if not (_has_dev(a) or _has_dev(b)):
                 return fn(a, b)
+            # explicit, never silent: a HostRoundTripWarning names the verb (once per verb), KGB200_STRICT=1 raises
+            if os.environ.get("KGB200_STRICT", "0") not in ("", "0"):
+                raise NotImplementedError(f"Klong verb `{sym}` has no device kernel (KGB200_STRICT=1 forbids the host round trip)")
+            warnings.warn(f"Klong verb `{sym}` restructures its operands on the host: device operands make one round trip "
+                          "(structural verb, not on the data-parallel path)", HostRoundTripWarning, stacklevel=2)
             r = fn(_to_host(a), _to_host(b))
             return backend.kg_asarray(r) if isinstance(r, (np.ndarray, list)) else r
         return wrapped
@@ -198,7 +215,7 @@ def install(klong):
     host_vd = _host_twin()._vd
     for sym in (":=", ":-", ":_", ":^", ":#", "$", ":$"):  # `$` / `:$` format to / from strings: host data either way
         if sym in host_vd:
-            vd[sym] = _via_host(host_vd[sym])
+            vd[sym] = _via_host(host_vd[sym], sym)
 
     vd.update({"?": find, "@": at_index, ",": join, ":+": rotate})
     klong._b200_installed = True

@@ -425,6 +425,44 @@ class FakeLib:
         n_names_out._obj.value = len(seen)
         return 0
 
+    def kgb_groupagg_fold(self, blocks, w, G, stride, mn, mx, sm, ct, stream):
+        lanes = view(blocks, (w - 1) * stride + 4 * G, I64)
+        outs = (view(mn, G, F64), view(mx, G, F64), view(sm, G, F64), view(ct, G, I64))
+        for r in range(w):
+            b = lanes[r * stride:r * stride + 4 * G].reshape(4, G)
+            f = b[:3].view(np.float64)
+            if r == 0:
+                outs[0][:], outs[1][:], outs[2][:], outs[3][:] = f[0], f[1], f[2], b[3]
+            else:
+                outs[0][:] = np.minimum(outs[0], f[0])
+                outs[1][:] = np.maximum(outs[1], f[1])
+                outs[2][:] = outs[2] + f[2]
+                outs[3][:] += b[3]
+        return 0
+
+    def kgb_groupagg_to_owners(self, block, G, w, send, stream):
+        B = (G + w - 1) // w
+        src = view(block, 4 * G, I64).reshape(4, G)
+        dst = view(send, w * 4 * B, I64).reshape(w, 4, B)
+        ident = np.array([np.inf, -np.inf, 0.0]).view(np.int64)
+        for r in range(w):
+            st = np.arange(B) * w + r
+            ok = st < G
+            for j in range(4):
+                dst[r, j, :] = ident[j] if j < 3 else 0
+                dst[r, j, ok] = src[j, st[ok]]
+        return 0
+
+    def kgb_groupagg_from_owners(self, full, G, w, mn, mx, sm, ct, stream):
+        B = (G + w - 1) // w
+        src = view(full, w * 4 * B, I64).reshape(w, 4, B)
+        st = np.arange(G)
+        outs = (view(mn, G, F64), view(mx, G, F64), view(sm, G, F64), view(ct, G, I64))
+        for j in range(3):
+            outs[j][:] = src[st % w, j, st // w].view(np.float64)
+        outs[3][:] = src[st % w, 3, st // w]
+        return 0
+
     def kgb_groupagg_merge(self, mn, mx, sm, ct, mn2, mx2, sm2, ct2, G, stream):
         a = (view(mn, G, F64), view(mx, G, F64), view(sm, G, F64), view(ct, G, I64))
         b = (view(mn2, G, F64), view(mx2, G, F64), view(sm2, G, F64), view(ct2, G, I64))

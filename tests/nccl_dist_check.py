@@ -39,6 +39,9 @@ for n in (1000, 1_000_003, 40_000_001):
     v = np.round(rng.normal(10, 15, n), 1)
     mn, mxg, sm, ct = (t.to_numpy() for t in dist.sharded_groupagg(be.kg_asarray(k[lo:hi]), be.kg_asarray(v[lo:hi]), G))
     rmn, rmx, rsm, rct = O.grouped_stats(k, v, G)
+    for exchange in ("allgather", "alltoall"):  # both exchanges: same tables, partial sums folded in rank order
+        t2 = [t.to_numpy() for t in dist.sharded_groupagg(be.kg_asarray(k[lo:hi]), be.kg_asarray(v[lo:hi]), G, exchange=exchange)]
+        assert np.array_equal(t2[0], mn) and np.array_equal(t2[1], mxg) and np.array_equal(t2[2], sm) and np.array_equal(t2[3], ct), exchange
     pos, counts = dist.sharded_find(be.kg_asarray(k[lo:hi]), 7)
     want = np.nonzero(k == 7)[0]
     find_ok = counts.sum() == len(want) and np.array_equal(pos.to_numpy(), want[(want >= lo) & (want < hi)])
@@ -52,6 +55,17 @@ for n in (1000, 1_000_003, 40_000_001):
     good = (find_ok and grad_ok and r == ref and np.array_equal(s, sref) and np.array_equal(mx, np.maximum.accumulate(x)[lo:hi]) and
             np.array_equal(mn, rmn) and np.array_equal(mxg, rmx) and np.array_equal(ct, rct) and
             np.allclose(sm, rsm, rtol=1e-12, atol=1e-9))
+    # host-resident shard streamed through the same step (stream.HostStream.sharded_reduce_and_scan): chunked H2D +
+    # two-output reduce on arrival, one all_gather, seeded scan chunks overlapped with D2H
+    from klongpy_b200 import stream  # noqa: E402
+    hx = torch.from_numpy(x[lo:hi].copy()).pin_memory()
+    hs = torch.empty(hi - lo, dtype=torch.float64).pin_memory()
+    hstream = stream.HostStream(f"cuda:{local}", chunk=1 << 16)
+    for _ in range(2):
+        f2 = hstream.sharded_reduce_and_scan(hx, red, "+", [ops.OP_ARG, 0], "+", hs)
+        torch.cuda.synchronize()
+        good = good and f2.item() == ref and np.array_equal(hs.numpy(), sref)
+        hs.zero_()
     print(f"rank {rank}/{world} n={n}: {'ok' if good else 'MISMATCH'}", flush=True)
     ok &= good
 # 1brc ingest: the text split into line-aligned chunks, one per rank; per-station tables merged by name

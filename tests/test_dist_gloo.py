@@ -55,11 +55,24 @@ def _worker(rank, world, port, q):
         G = 37
         k = rng.integers(0, G, n)
         v = np.round(rng.normal(10, 15, n), 1)
-        mn, mx, sm, ct = (t.to_numpy() for t in dist.sharded_groupagg(be.kg_asarray(k[lo:hi]), be.kg_asarray(v[lo:hi]), G))
         from oracle import kg_oracle as O
         rmn, rmx, rsm, rct = O.grouped_stats(k, v, G)
-        assert np.array_equal(mn, rmn) and np.array_equal(mx, rmx) and np.array_equal(ct, rct)
-        assert np.allclose(sm, rsm, rtol=1e-12, atol=1e-9)
+        ref_sum = None
+        for exchange in ("auto", "allgather", "alltoall"):  # one all_gather + fold | hash-partitioned all_to_all
+            mn, mx, sm, ct = (t.to_numpy() for t in dist.sharded_groupagg(be.kg_asarray(k[lo:hi]), be.kg_asarray(v[lo:hi]), G,
+                                                                          exchange=exchange))
+            assert np.array_equal(mn, rmn) and np.array_equal(mx, rmx) and np.array_equal(ct, rct), (exchange, rank)
+            assert np.allclose(sm, rsm, rtol=1e-12, atol=1e-9), (exchange, rank)
+            # both exchanges fold the ranks' partial sums in rank order: bit-identical to one another and on every rank
+            assert ref_sum is None or np.array_equal(sm, ref_sum), (exchange, rank)
+            ref_sum = sm
+        # a station count that is not a multiple of the world size, and one smaller than it (empty owner slices)
+        for G2 in (world * 5 + 1, 1):
+            k2 = rng.integers(0, G2, n)
+            got = [t.to_numpy() for t in dist.sharded_groupagg(be.kg_asarray(k2[lo:hi]), be.kg_asarray(v[lo:hi]), G2, exchange="alltoall")]
+            want = O.grouped_stats(k2, v, G2)
+            assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and np.array_equal(got[3], want[3]), (G2, rank)
+            assert np.allclose(got[2], want[2], rtol=1e-12, atol=1e-9), (G2, rank)
         # find: global positions of this rank's hits + every rank's count
         pos, counts = dist.sharded_find(I, 7)
         want = np.nonzero(i == 7)[0]

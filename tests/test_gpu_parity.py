@@ -825,3 +825,23 @@ def test_float32_reduce_and_scan_within_1e6(be, K, n):
     p = host(K.scan("mul", K.asarray((1 + x[:2000] * 1e-3).astype(np.float32))))
     pref = np.cumprod((1 + x[:2000] * 1e-3).astype(np.float32).astype(np.float64))
     assert np.max(np.abs(p - pref) / pref) <= 1e-6
+
+
+def test_range_hash_path_collapses_nans_like_the_sort_path(be, K):
+    """`?a` must not depend on which path ran: NaNs of either sign / any payload are ONE value on the hash path (n >= 2M,
+    low cardinality) as on the sort path and in the reference (a set of str(x)); -0.0 and +0.0 stay distinct."""
+    rng = np.random.default_rng(17)
+    n = 3_000_000
+    x = np.round(rng.standard_normal(n), 1)
+    nan_neg = np.frombuffer(np.uint64(0xfff8000000000000).tobytes(), dtype=np.float64)[0]
+    nan_pay = np.frombuffer(np.uint64(0x7ff8000000000123).tobytes(), dtype=np.float64)[0]
+    x[rng.integers(0, n, 5000)] = np.nan
+    x[rng.integers(0, n, 5000)] = nan_neg
+    x[rng.integers(0, n, 5000)] = nan_pay
+    x[rng.integers(0, n, 5000)] = -0.0
+    u = host(K.unique_first(dev(be, x)))
+    small = host(K.unique_first(dev(be, x[:100_000])))  # sort path
+    assert np.isnan(u).sum() == 1 and np.isnan(small).sum() == 1
+    want = O.range_unique(x)
+    assert len(u) == len(want)
+    assert np.array_equal(u[~np.isnan(u)], want[~np.isnan(want)]) and np.array_equal(np.signbit(u[~np.isnan(u)]), np.signbit(want[~np.isnan(want)]))

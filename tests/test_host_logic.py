@@ -247,3 +247,28 @@ def test_array_type_has_no_silent_host_fallback(fake_backend):
     for needle in (float("inf"), float("nan"), 2.5, 2**70):
         assert ops.find_equal(ints, needle).to_numpy().tolist() == []
     assert ops.find_equal(ints, 2.0).to_numpy().tolist() == [1]
+
+
+def test_sort_by_grade_takes_sorted_keys_from_the_sort(interp, monkeypatch):
+    """`a@<a` / `a@>a` (monads.py: "To sort a list a, use a@<a"): the grade is deferred and the `@` on the same array
+    asks the sort for its sorted keys — no permutation is built and no gather runs; every other use of `<a`
+    materialises the permutation."""
+    b200, ref, mod = interp
+    from klongpy_b200 import ops
+    calls = {"gather": 0}
+    real_gather = ops.gather
+    monkeypatch.setattr(ops, "gather", lambda *a, **k: (calls.__setitem__("gather", calls["gather"] + 1), real_gather(*a, **k))[1])
+    rng = np.random.default_rng(3)
+    keys = rng.integers(-50, 50, 2000)
+    for kl in (b200, ref):
+        kl["a"] = kl._backend.kg_asarray(keys) if kl is b200 else keys
+    for src in ("a@<a", "a@>a"):
+        got = b200(src)
+        assert isinstance(got, mod.DeviceArray)
+        assert np.array_equal(got.to_numpy(), np.asarray(ref(src))), src
+    assert calls["gather"] == 0
+    p = b200("<a")
+    assert ops.grade_source(p) is not None            # still deferred
+    assert np.array_equal(p.to_numpy(), np.argsort(keys, kind="stable")) and ops.grade_source(p) is None
+    assert np.array_equal(b200("(<a)+1").to_numpy(), np.argsort(keys, kind="stable") + 1)
+    assert np.array_equal(b200("a@<a+0").to_numpy(), np.sort(keys, kind="stable")) and calls["gather"] == 1  # another array: gather
