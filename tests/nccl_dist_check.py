@@ -39,9 +39,11 @@ for n in (1000, 1_000_003, 40_000_001):
     v = np.round(rng.normal(10, 15, n), 1)
     mn, mxg, sm, ct = (t.to_numpy() for t in dist.sharded_groupagg(be.kg_asarray(k[lo:hi]), be.kg_asarray(v[lo:hi]), G))
     rmn, rmx, rsm, rct = O.grouped_stats(k, v, G)
-    for exchange in ("allgather", "alltoall"):  # both exchanges: same tables, partial sums folded in rank order
+    for exchange in ("allgather", "alltoall"):  # both exchanges: same tables (each call re-aggregates the shard, and the
+        # kernel's shared-memory float adds associate differently from run to run, so sums are compared to 1e-12)
         t2 = [t.to_numpy() for t in dist.sharded_groupagg(be.kg_asarray(k[lo:hi]), be.kg_asarray(v[lo:hi]), G, exchange=exchange)]
-        assert np.array_equal(t2[0], mn) and np.array_equal(t2[1], mxg) and np.array_equal(t2[2], sm) and np.array_equal(t2[3], ct), exchange
+        assert np.array_equal(t2[0], mn) and np.array_equal(t2[1], mxg) and np.array_equal(t2[3], ct), exchange
+        assert np.allclose(t2[2], sm, rtol=1e-12, atol=1e-9), exchange
     pos, counts = dist.sharded_find(be.kg_asarray(k[lo:hi]), 7)
     want = np.nonzero(k == 7)[0]
     find_ok = counts.sum() == len(want) and np.array_equal(pos.to_numpy(), want[(want >= lo) & (want < hi)])
