@@ -638,15 +638,17 @@ def primitive_table(be, ops, dist, time_kernel, dev, peak, world, rank):
         s = 1 / (1 + ops.unary("exp", 0 - ((w * X) + b)))
         return ops.reduce("add", (s - Y) ** 2)
 
-    out["autograd_sigmoid_nn_1e7"] = prim_row(m, time_kernel(lambda: be.compute_multi_autograd(nn_loss, [0.1, 0.1]), 3), 32, peak,
-                                              note="operator-by-operator tape, as the interpreter evaluates the Klong source")
     from klongpy_b200 import lazy
-    lazy.enable(True)   # opt-in deferred elementwise expressions: the same Python, fused forward + fused backward
+    # default path: eager operators are deferred and fused (klongpy_b200/lazy.py, on by default) and the backend's own tape
+    # records the launches — fused forward reduce + ONE two-output backward reduce for dL/dw1 and dL/db1
+    out["autograd_sigmoid_nn_1e7"] = prim_row(m, time_kernel(lambda: be.compute_multi_autograd(nn_loss, [0.1, 0.1]), 5), 32, peak,
+                                              note="operators deferred + fused (default); float64")
+    lazy.enable(False)
     try:
-        out["autograd_sigmoid_nn_1e7_lazy"] = prim_row(m, time_kernel(lambda: be.compute_multi_autograd(nn_loss, [0.1, 0.1]), 3), 32, peak,
-                                                       note="KGB200_LAZY: eager operators deferred and fused (klongpy_b200/lazy.py)")
+        out["autograd_sigmoid_nn_1e7_eager"] = prim_row(m, time_kernel(lambda: be.compute_multi_autograd(nn_loss, [0.1, 0.1]), 3), 32, peak,
+                                                        note="KGB200_LAZY=0: operator-by-operator tape, one kernel per Klong operator")
     finally:
-        lazy.enable(False)
+        lazy.enable(True)
     R = DeviceArray(torch.rand(m, dtype=torch.float64, device=dev, generator=g) * 0.14 + 0.01)
     V = DeviceArray(torch.rand(m, dtype=torch.float64, device=dev, generator=g) * 0.35 + 0.05)
     W = DeviceArray(torch.full((m,), 1.0 / m, dtype=torch.float64, device=dev))
@@ -654,7 +656,7 @@ def primitive_table(be, ops, dist, time_kernel, dev, peak, world, rank):
                  ("binop", "^", ("reduce", "+", ("binop", "*", ("binop", "^", ("var", "_v0"), ("literal", 2)),
                                                  ("binop", "^", ("var", "_v2"), ("literal", 2)))), ("literal", 0.5)))
     sharpe, _ = be.compile_expr_ir(sharpe_ir, ["x", "returns", "vols"])
-    out["autograd_sharpe_grad_1e7"] = prim_row(m, time_kernel(lambda: be.compute_autograd(lambda x: sharpe(x, R, V), W), 3), 56, peak,
+    out["autograd_sharpe_grad_1e7"] = prim_row(m, time_kernel(lambda: be.compute_autograd(lambda x: sharpe(x, R, V), W), 5), 56, peak,
                                                note="compiled IR tree: fused forward and fused backward kernels")
     del X, Y, R, V, W
     keys_full = DeviceArray(torch.randint(-2**62, 2**62, (n,), dtype=torch.int64, device=dev, generator=g))

@@ -36,6 +36,20 @@ except Exception:  # pragma: no cover - GPU box without klongpy
 NotDifferentiable = autodiff.NotDifferentiable
 
 
+import threading  # noqa: E402
+
+_tls = threading.local()
+_parsed_ok = set()
+
+
+def _parse_checked(code):
+    """autodiff.parse as a validity check, once per program"""
+    key = tuple(code)
+    if key not in _parsed_ok:
+        autodiff.parse(code)
+        _parsed_ok.add(key)
+
+
 def wants_grad(args):
     return torch.is_grad_enabled() and any(isinstance(a, DeviceArray) and a._t.requires_grad for a in args)
 
@@ -65,10 +79,27 @@ def run_differentiable(code, args, mode, red, code2, red2, out_shape, device):
         raise NotDifferentiable("*/ has no gradient rule here")
     if mode == _lib.MODE_SCAN and red != _lib.RED_ADD:
         raise NotDifferentiable("only +\\ is differentiable")
-    autodiff.parse(code)  # unknown operators fail before anything runs
+    _parse_checked(code)  # unknown operators fail before anything runs
     tensors = [a._t for a in args if isinstance(a, DeviceArray)]
     template = [_TENSOR if isinstance(a, DeviceArray) else a for a in args]
-    out = _Launch.apply(_Spec(code, mode, red, template, out_shape, device), *tensors)
+    spec = _Spec(code, mode, red, template, out_shape, device)
+    tape = getattr(_tls, "tape", None)
+    if tape is not None:
+        # inside compute_autograd / compute_multi_autograd: our own tape — the launch itself plus a list append, instead of a
+        # torch.autograd.Function node (~40 us of engine bookkeeping per launch; a fused forward kernel at 1e7 elements
+        # takes 25 us).  The result is a fresh leaf that requires grad, so later launches see it as differentiable.
+        prev = torch.is_grad_enabled()
+        torch._C._set_grad_enabled(False)
+        try:
+            out = ops.run(spec.code, args, mode=mode, red=red, out_shape=out_shape, device=device, _no_defer=True)
+        finally:
+            torch._C._set_grad_enabled(prev)
+        t = out._t
+        if t.dtype.is_floating_point:
+            t.requires_grad_(True)
+            tape.append((1, spec, tensors, (t,), None))
+        return out
+    out = _Launch.apply(spec, *tensors)
     return DeviceArray(out)
 
 
@@ -77,11 +108,26 @@ def run_differentiable2(code, red, code2, red2, args, device):
     backward is one fused kernel per differentiated operand for BOTH incoming gradients."""
     if red != _lib.RED_ADD or red2 != _lib.RED_ADD:
         raise NotDifferentiable("paired reductions are differentiated for +/ only")
-    autodiff.parse(code)
-    autodiff.parse(code2)
+    _parse_checked(code)
+    _parse_checked(code2)
     tensors = [a._t for a in args if isinstance(a, DeviceArray)]
     template = [_TENSOR if isinstance(a, DeviceArray) else a for a in args]
     spec = _Spec(code, _lib.MODE_REDUCE, red, template, None, device)
+    tape = getattr(_tls, "tape", None)
+    if tape is not None:
+        prev = torch.is_grad_enabled()
+        torch._C._set_grad_enabled(False)
+        try:
+            o1, o2 = ops.reduce2(spec.code, spec.red, code2, _lib.RED_ADD, args)
+        finally:
+            torch._C._set_grad_enabled(prev)
+        outs = []
+        for o in (o1, o2):
+            if o._t.dtype.is_floating_point:
+                o._t.requires_grad_(True)
+            outs.append(o._t)
+        tape.append((2, spec, tensors, tuple(outs), tuple(code2)))
+        return o1, o2
     o1, o2 = _Launch2.apply(spec, tuple(code2), *tensors)
     return DeviceArray(o1), DeviceArray(o2)
 
@@ -173,40 +219,44 @@ class _Launch2(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g1, g2):
-        spec = ctx.spec
-        tensors = ctx.saved_tensors
-        with torch.no_grad():
-            args = spec.rebuild(tensors)
-            n_args = len(args)
-            dev = tensors[0].device
-            z = None
+        return (None, None) + tuple(_backward2(ctx.spec, ctx.code2, ctx.saved_tensors, g1, g2, ctx.needs_input_grad[2:]))
 
-            def scalar(g):
-                nonlocal z
-                if g is None:
-                    if z is None:
-                        z = torch.zeros((), dtype=torch.float64, device=dev)
-                    return DeviceArray(z)
-                return DeviceArray(g.contiguous().to(torch.float64))
 
-            full = args + [scalar(g1), scalar(g2)]
-            grads = [None, None] + [None] * len(tensors)
-            pending = []
-            slots = [k for k, s in enumerate(spec.template) if s is _TENSOR]
-            for j, pos in enumerate(slots):
-                t = tensors[j]
-                if not ctx.needs_input_grad[j + 2] or not t.dtype.is_floating_point:
-                    continue
-                prog = _grad_prog2(spec.code, ctx.code2, pos, n_args)
-                if prog is None:
-                    grads[j + 2] = torch.zeros_like(t)
-                elif t.dim() > 0:
-                    r = ops.run(prog, full)
-                    grads[j + 2] = r._t.to(t.dtype) if r._t.shape == t.shape else _sum_to(r, t.shape).to(t.dtype)
-                else:
-                    pending.append((j + 2, prog, full, t))
-            _fold_scalars(pending, grads)
-        return tuple(grads)
+def _backward2(spec, code2, tensors, g1, g2, needs):
+    """Gradients of a two-output fold node w.r.t. its tensor operands: one fused kernel per differentiated operand for
+    BOTH incoming gradients (shared by the torch.autograd.Function node and the backend's own tape)."""
+    with torch.no_grad():
+        args = spec.rebuild(tensors)
+        n_args = len(args)
+        dev = tensors[0].device
+        z = None
+
+        def scalar(g):
+            nonlocal z
+            if g is None:
+                if z is None:
+                    z = torch.zeros((), dtype=torch.float64, device=dev)
+                return DeviceArray(z)
+            return DeviceArray(g.contiguous().to(torch.float64))
+
+        full = args + [scalar(g1), scalar(g2)]
+        grads = [None] * len(tensors)
+        pending = []
+        slots = [k for k, s in enumerate(spec.template) if s is _TENSOR]
+        for j, pos in enumerate(slots):
+            t = tensors[j]
+            if not needs[j] or not t.dtype.is_floating_point:
+                continue
+            prog = _grad_prog2(spec.code, code2, pos, n_args)
+            if prog is None:
+                grads[j] = torch.zeros_like(t)
+            elif t.dim() > 0:
+                r = ops.run(prog, full)
+                grads[j] = r._t.to(t.dtype) if r._t.shape == t.shape else _sum_to(r, t.shape).to(t.dtype)
+            else:
+                pending.append((j, prog, full, t))
+        _fold_scalars(pending, grads)
+    return grads
 
 
 class _Launch(torch.autograd.Function):
@@ -223,52 +273,100 @@ class _Launch(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        spec = ctx.spec
         *tensors, out = ctx.saved_tensors
-        with torch.no_grad():
-            args = spec.rebuild(tensors)
-            n_args = len(args)
-            G = DeviceArray(g.contiguous())
-            extra = [G]
-            gate = None  # tree multiplied into the tangent (max/min folds route the gradient to the arg-extremes)
-            if spec.mode == _lib.MODE_SCAN:
-                # out_j = sum_{k<=j} f_k  =>  dL/df_k = sum_{j>=k} g_j : a reversed running sum
-                extra = [ops.reverse(ops.scan("add", ops.reverse(G)))]
-            elif spec.mode == _lib.MODE_REDUCE and spec.red in (_lib.RED_MAX, _lib.RED_MIN):
-                f = autodiff.parse(spec.code)
-                hit = autodiff.op("eq_b", f, ("arg", n_args + 1))
-                cnt = ops.run(autodiff.emit(("op", "to_f64", hit)), args + [G, DeviceArray(out)], mode=_lib.MODE_REDUCE,
-                              red=_lib.RED_ADD)
-                extra = [G, DeviceArray(out), cnt]  # ties share the gradient evenly, like torch.amax
-                gate = True
-            grads = [None]
-            pending = []
-            full = args + extra
-            slots = [k for k, s in enumerate(spec.template) if s is _TENSOR]
-            for j, pos in enumerate(slots):
-                t = tensors[j]
-                if not ctx.needs_input_grad[j + 1] or not t.dtype.is_floating_point:
+        return (None,) + tuple(_backward1(ctx.spec, tensors, out, g, ctx.needs_input_grad[1:]))
+
+
+def _backward1(spec, tensors, out, g, needs):
+    """Gradients of one launch w.r.t. its tensor operands (shared by the torch.autograd.Function node and the backend's
+    own tape): one fused kernel per differentiated array operand, one fused fold per (pair of) 0-d operand(s)."""
+    with torch.no_grad():
+        args = spec.rebuild(tensors)
+        n_args = len(args)
+        G = DeviceArray(g.contiguous())
+        extra = [G]
+        gate = None  # tree multiplied into the tangent (max/min folds route the gradient to the arg-extremes)
+        if spec.mode == _lib.MODE_SCAN:
+            # out_j = sum_{k<=j} f_k  =>  dL/df_k = sum_{j>=k} g_j : a reversed running sum
+            extra = [ops.reverse(ops.scan("add", ops.reverse(G)))]
+        elif spec.mode == _lib.MODE_REDUCE and spec.red in (_lib.RED_MAX, _lib.RED_MIN):
+            f = autodiff.parse(spec.code)
+            hit = autodiff.op("eq_b", f, ("arg", n_args + 1))
+            cnt = ops.run(autodiff.emit(("op", "to_f64", hit)), args + [G, DeviceArray(out)], mode=_lib.MODE_REDUCE,
+                          red=_lib.RED_ADD)
+            extra = [G, DeviceArray(out), cnt]  # ties share the gradient evenly, like torch.amax
+            gate = True
+        grads = []
+        pending = []
+        full = args + extra
+        slots = [k for k, s in enumerate(spec.template) if s is _TENSOR]
+        for j, pos in enumerate(slots):
+            t = tensors[j]
+            if not needs[j] or not t.dtype.is_floating_point:
+                grads.append(None)
+                continue
+            prog = _grad_prog(spec.code, pos, n_args, gate is not None)
+            if prog is None:
+                grads.append(torch.zeros_like(t))
+                continue
+            elementwise = t.dim() > 0
+            if elementwise:
+                r = ops.run(prog, full, out_shape=tuple(t.shape) if t.numel() == 0 else None)
+                grads.append(r._t.to(t.dtype) if r._t.shape == t.shape else _sum_to(r, t.shape).to(t.dtype))
+            else:
+                # a 0-d operand broadcast against arrays: its gradient is the FOLD of the elementwise gradient —
+                # one fused reduce kernel, nothing materialised (two such operands share one pass)
+                if any(isinstance(a, DeviceArray) and a.ndim > 0 for a in full):
                     grads.append(None)
-                    continue
-                prog = _grad_prog(spec.code, pos, n_args, gate is not None)
-                if prog is None:
-                    grads.append(torch.zeros_like(t))
-                    continue
-                elementwise = t.dim() > 0
-                if elementwise:
-                    r = ops.run(prog, full, out_shape=tuple(t.shape) if t.numel() == 0 else None)
-                    grads.append(r._t.to(t.dtype) if r._t.shape == t.shape else _sum_to(r, t.shape).to(t.dtype))
+                    pending.append((len(grads) - 1, prog, full, t))
                 else:
-                    # a 0-d operand broadcast against arrays: its gradient is the FOLD of the elementwise gradient —
-                    # one fused reduce kernel, nothing materialised (two such operands share one pass)
-                    if any(isinstance(a, DeviceArray) and a.ndim > 0 for a in full):
-                        grads.append(None)
-                        pending.append((len(grads) - 1, prog, full, t))
-                    else:
-                        r = ops.run(prog, full, out_shape=())
-                        grads.append(r._t.reshape(t.shape).to(t.dtype))
-            _fold_scalars(pending, grads)
-        return tuple(grads)
+                    r = ops.run(prog, full, out_shape=())
+                    grads.append(r._t.reshape(t.shape).to(t.dtype))
+        _fold_scalars(pending, grads)
+    return grads
+
+
+def _tape_gradients(tape, y, leaves):
+    """Reverse walk of the backend's own tape: d y / d leaf for every leaf tensor, or None where y does not depend on it.
+
+    Tensors that torch arithmetic produced between two launches (views such as flatten / reshape / indexing, the tail of
+    dist.sharded_loss_sum) carry a torch grad_fn: their gradient is pushed through torch's graph down to the tape
+    results and leaves recorded before them, and the tape takes over again from there."""
+    grads = {}
+
+    def add(t, g):
+        have = grads.get(id(t))
+        grads[id(t)] = g if have is None else have + g
+
+    def through_torch(t, g, upto):
+        cand = [o for node in tape[:upto] for o in node[3] if o.requires_grad] + list(leaves)
+        for c, gc in zip(cand, torch.autograd.grad(t, cand, grad_outputs=g, allow_unused=True, retain_graph=True)):
+            if gc is not None:
+                add(c, gc)
+
+    yt = y._t
+    if yt.grad_fn is not None:
+        through_torch(yt, torch.ones_like(yt), len(tape))
+    else:
+        grads[id(yt)] = torch.ones_like(yt)
+    for k in range(len(tape) - 1, -1, -1):
+        kind, spec, tensors, outs, code2 = tape[k]
+        gs_out = [grads.pop(id(o), None) for o in outs]
+        if all(g is None for g in gs_out):
+            continue
+        needs = [t.requires_grad for t in tensors]
+        if kind == 1:
+            gin = _backward1(spec, tensors, outs[0], gs_out[0], needs)
+        else:
+            gin = _backward2(spec, code2, tensors, gs_out[0], gs_out[1], needs)
+        for t, g in zip(tensors, gin):
+            if g is None:
+                continue
+            if t.grad_fn is not None:
+                through_torch(t, g, k)
+            else:
+                add(t, g)
+    return [grads.get(id(t)) for t in leaves]
 
 
 # ------------------------------------------------------------------------------------------- provider hooks
@@ -297,19 +395,32 @@ def _check_loss(y, what):
                                        "Output lost gradient tracking (integer result, .item(), or a host round trip).")
 
 
+def _with_tape(func, arg):
+    """Run the loss function with the backend's own tape recording every differentiable launch."""
+    outer = getattr(_tls, "tape", None)
+    _tls.tape = tape = []
+    try:
+        return func(arg), tape
+    finally:
+        _tls.tape = outer
+
+
 def compute_autograd(backend, func, x):
     xt = create_grad_tensor(backend, x)
-    y = func(xt)
+    y, tape = _with_tape(func, xt)
     _check_loss(y, "function output")
-    y._t.backward()
-    return DeviceArray(xt._t.grad)
+    (g,) = _tape_gradients(tape, y, [xt._t])
+    return DeviceArray(g if g is not None else torch.zeros_like(xt._t))
 
 
 def compute_multi_autograd(backend, func, params):
     leaves = [create_grad_tensor(backend, p) for p in params]
-    y = func(leaves)
+    y, tape = _with_tape(func, leaves)
     _check_loss(y, "loss computation")
-    grads = torch.autograd.grad(y._t, [p._t for p in leaves], create_graph=False)
+    grads = _tape_gradients(tape, y, [p._t for p in leaves])
+    if any(g is None for g in grads):
+        # torch.autograd.grad's contract (and the reference's behaviour): a parameter the loss does not depend on is an error
+        raise RuntimeError("One of the differentiated Tensors appears to not have been used in the graph.")
     return [DeviceArray(g) for g in grads]
 
 

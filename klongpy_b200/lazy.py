@@ -1,5 +1,5 @@
-"""Deferred elementwise expressions — SURVEY.md §8f rank 2 ("compiler coverage"), OPT-IN (KGB200_LAZY=1 or
-`lazy.enable()`).
+"""Deferred elementwise expressions — SURVEY.md §8f rank 2 ("compiler coverage").  ON by default (KGB200_LAZY=0 or
+`lazy.enable(False)` switch it off).
 
 The reference's compiler IR covers `+ - * % ^ = < > -x +/ +\\` only (`compiler.py:77-90`); everything else — `& | !
 _`, `%x`, and the `.bkf` unary math the autograd examples live on (`exp tanh sqrt ...`, `sys_fn.py:715-723`) — reaches
@@ -11,7 +11,8 @@ sort, an operand used a second time) materialises it with ONE fused kernel.  Und
 single tape node whose backward is derived symbolically (autodiff.py), so the backward fuses too.
 
 Rules that keep it safe:
-  * shapes are checked and dtypes inferred when the node is built — errors are raised at the operator, not later;
+  * shapes are checked and dtypes inferred when the node is built — errors are raised at the operator, not later
+    (elementwise kernels have no data-dependent errors: x%0 is inf/nan like NumPy, never an exception);
   * a node inlines into at most ONE consumer; a second consumer materialises it first (no exponential recompute);
   * programs are capped (arguments <= KGB_MAX_ARGS, code <= 96 words); beyond that operands are materialised.
 """
@@ -22,7 +23,7 @@ import torch
 
 from . import _lib
 
-ENABLED = os.environ.get("KGB200_LAZY", "0") == "1"
+ENABLED = os.environ.get("KGB200_LAZY", "1") != "0"   # on by default since round 2 (KGB200_LAZY=0 switches it off)
 MAX_ARGS = 12
 MAX_CODE = 96
 _infer_cache = {}

@@ -76,6 +76,9 @@ def default_device():
     return _default_device
 
 
+_RAW_STREAM = getattr(torch._C, "_cuda_getCurrentRawStream", None)  # torch's own fast accessor of the current stream
+
+
 def _lib_for(device):
     """Library bound to `device` on this thread (and the raw stream to launch on)."""
     if device.type != "cuda":
@@ -83,6 +86,8 @@ def _lib_for(device):
         return lib, None
     idx = device.index if device.index is not None else torch.cuda.current_device()
     lib = _lib.bind_device(idx)
+    if _RAW_STREAM is not None:
+        return lib, ctypes.c_void_p(_RAW_STREAM(idx))
     return lib, ctypes.c_void_p(torch.cuda.current_stream(idx).cuda_stream)
 
 
@@ -186,21 +191,48 @@ def run(code, args, mode=_lib.MODE_MAP, red=0, code2=None, red2=0, out_shape=Non
             r = _lazy.defer(code, args)
             if r is not None:
                 return r
+    # ---- one pass over the operands: shape agreement, autograd, and the launch description (kind, dtype, pointer)
     shape = None
     mixed = False
     grad = False
     dev_param = device
+    kinds, dts, ptrs, keep = [], [], [], []
     for a in args:
         if isinstance(a, DeviceArray):
             t = a._t
             device = t.device
             if t.requires_grad:
                 grad = True
-            if t.dim() > 0:
+            nd = t.dim()
+            if nd > 0:
                 if shape is None:
                     shape = tuple(t.shape)
                 elif tuple(t.shape) != shape:
                     mixed = True
+                if not t.is_contiguous():
+                    t = t.contiguous()
+                    keep.append(t)
+                kinds.append(_lib.ARG_ARRAY)
+            else:
+                kinds.append(_lib.ARG_DEVSCALAR)
+            dts.append(kgb_dtype(t))
+            ptrs.append(t.data_ptr())
+        else:
+            if isinstance(a, (bool, np.bool_)):
+                a = int(a)
+            elif isinstance(a, np.ndarray) and a.ndim == 0:
+                a = a[()]
+            if isinstance(a, (int, np.integer)):
+                c = ctypes.c_int64(int(a))
+                dts.append(_lib.I64)
+            elif isinstance(a, (float, np.floating)):
+                c = ctypes.c_double(float(a))
+                dts.append(_lib.F64)
+            else:
+                raise TypeError(f"unsupported operand type {type(a).__name__}")
+            keep.append(c)
+            kinds.append(_lib.ARG_SCALAR)
+            ptrs.append(ctypes.addressof(c))
     if grad and torch.is_grad_enabled():
         from . import autograd  # operands on the autograd tape: same launch, recorded as one node
         return autograd.run_differentiable(code, args, mode, red, code2, red2, out_shape, dev_param)
@@ -214,14 +246,17 @@ def run(code, args, mode=_lib.MODE_MAP, red=0, code2=None, red2=0, out_shape=Non
             raise ValueError("operands could not be broadcast together with shapes " + " ".join(map(str, shapes))) from None
         args = [DeviceArray(a._t.expand(shape).contiguous()) if isinstance(a, DeviceArray) and a._t.dim() > 0 and
                 tuple(a._t.shape) != shape else a for a in args]
+        return run(code, args, mode=mode, red=red, code2=code2, red2=red2, out_shape=out_shape, device=dev_param, _no_defer=True)
     if device is None:
         raise TypeError("run() needs at least one device operand")
+    for a in args:
+        if isinstance(a, DeviceArray) and a._t.device != device:
+            raise ValueError(f"operand on {a._t.device}, expected {device}")
     if shape is None and out_shape is not None:
         shape = tuple(out_shape)
     lib, stream = _lib_for(device)
-    cls = [_classify(a, device) for a in args]
-    kinds = tuple(c[0] for c in cls)
-    dts = tuple(c[1] for c in cls)
+    kinds = tuple(kinds)
+    dts = tuple(dts)
     code_t = tuple(code)
     code2_t = tuple(code2) if code2 else ()
     key = (device.index, code_t, code2_t, kinds, dts, mode, red, red2)
@@ -236,9 +271,9 @@ def run(code, args, mode=_lib.MODE_MAP, red=0, code2=None, red2=0, out_shape=Non
         od = ctypes.c_int32()
         _lib.check(lib.kgb_expr_compile(c_code, len(code_t), c_code2, len(code2_t), c_k, c_d, n_args, mode, red,
                                         red2, ctypes.byref(h), ctypes.byref(od)), "kgb_expr_compile")
-        ent = (h, od.value)
+        ent = (h, od.value, _K2T[od.value])
         _handles[key] = ent
-    h, od = ent
+    h, od, out_td = ent
     n = 1
     if shape is not None:
         for s in shape:
@@ -251,21 +286,37 @@ def run(code, args, mode=_lib.MODE_MAP, red=0, code2=None, red2=0, out_shape=Non
         oshape = shape if shape is not None else ()
     if out_shape is not None:
         oshape = out_shape
-    out = empty(oshape, od, device)
-    wsb = ctypes.c_size_t()
-    ws = None
+    out = torch.empty(oshape, dtype=out_td, device=device)
     ws_ptr = None
+    ws_bytes = 0
     if mode != _lib.MODE_MAP:
+        wsb = ctypes.c_size_t()
         _lib.check(lib.kgb_expr_workspace_bytes(h, n, ctypes.byref(wsb)), "kgb_expr_workspace_bytes")
-        ws = torch.empty(max(wsb.value, 64), dtype=torch.uint8, device=device)
-        ws_ptr = ws.data_ptr()
+        ws_bytes = wsb.value
+        ws_ptr = _scratch(device, stream, ws_bytes)
     if n == 0:
-        return out  # empty MAP / SCAN: nothing to launch
-    argv = _ARGV[len(cls)](*[c[3] for c in cls]) if len(cls) < len(_ARGV) else (ctypes.c_void_p * len(cls))(*[c[3] for c in cls])
-    rc = lib.kgb_expr_launch(h, argv, n, out._t.data_ptr(), ws_ptr, wsb.value, stream)
+        return DeviceArray(out)  # empty MAP / SCAN: nothing to launch
+    na = len(ptrs)
+    argv = _ARGV[na](*ptrs) if na < len(_ARGV) else (ctypes.c_void_p * na)(*ptrs)
+    rc = lib.kgb_expr_launch(h, argv, n, out.data_ptr(), ws_ptr, ws_bytes, stream)
     if rc:
         _lib.check(rc, "kgb_expr_launch")
-    return out
+    return DeviceArray(out)
+
+
+_scratch_cache = {}
+
+
+def _scratch(device, stream, nbytes):
+    """Fold / scan scratch (partials, tile states) for one launch: ONE growing buffer per (device, stream), reused by
+    every launch on that stream — the library zeroes what it needs inside the launch and launches on a stream are
+    ordered, so consecutive kernels can share it (a torch.empty per call was a third of the host time of a small fold)."""
+    key = (device.index, stream.value if stream is not None else None)
+    buf = _scratch_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 16), dtype=torch.uint8, device=device)
+        _scratch_cache[key] = buf
+    return buf.data_ptr()
 
 
 def reduce2(code, red, code2, red2, args):
@@ -312,9 +363,9 @@ def reduce2(code, red, code2, red2, args):
     buf = torch.empty(16, dtype=torch.uint8, device=device)
     wsb = ctypes.c_size_t()
     _lib.check(lib.kgb_expr_workspace_bytes(h, n, ctypes.byref(wsb)), "kgb_expr_workspace_bytes")
-    ws = torch.empty(max(wsb.value, 64), dtype=torch.uint8, device=device)
     argv = (ctypes.c_void_p * max(len(args), 1))(*[c[3] for c in cls])
-    _lib.check(lib.kgb_expr_launch(h, argv, n, buf.data_ptr(), ws.data_ptr(), wsb.value, stream), "kgb_expr_launch")
+    _lib.check(lib.kgb_expr_launch(h, argv, n, buf.data_ptr(), _scratch(device, stream, wsb.value), wsb.value, stream),
+               "kgb_expr_launch")
     return DeviceArray(buf[:8].view(_K2T[od]).reshape(())), DeviceArray(buf[8:].view(_K2T[od2]).reshape(()))
 
 
