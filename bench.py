@@ -612,12 +612,13 @@ def primitive_table(be, ops, dist, time_kernel, dev, peak, world, rank):
     for name, (ir, params) in exprs.items():
         fnc, _ = be.compile_expr_ir(ir, params)
         dargs = [dc[k] for k in params]
+        # (`.tensor` launches a deferred elementwise result: with lazy evaluation on, a discarded `a+b` would never run)
         for _ in range(20):
-            fnc(*dargs)
+            fnc(*dargs).tensor
         torch.cuda.synchronize()
         t0 = _time.perf_counter()
         for _ in range(1000):
-            fnc(*dargs)
+            fnc(*dargs).tensor
         torch.cuda.synchronize()
         us = (_time.perf_counter() - t0) * 1e3
         env = {f"_v{i}": hc[k] for i, k in enumerate(params)}

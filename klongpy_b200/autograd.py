@@ -379,6 +379,10 @@ def create_grad_tensor(backend, x):
         t = t.to(torch.float64) if t.dtype != torch.float64 else t
     elif isinstance(x, torch.Tensor):
         t = x.detach().clone().to(device=backend._device, dtype=torch.float64)
+    elif isinstance(x, (int, float, np.integer, np.floating)) or (isinstance(x, np.ndarray) and x.ndim == 0):
+        # a fill kernel, not a host->device copy: a pageable copy blocks the host until everything queued before it has
+        # run, which serialises the CPU with the GPU once per parameter and step
+        t = torch.full((), float(x), dtype=torch.float64, device=backend._device)
     else:
         t = torch.as_tensor(np.asarray(x, dtype=np.float64)).to(backend._device)
     return DeviceArray(t.requires_grad_(True))
@@ -400,7 +404,10 @@ def _with_tape(func, arg):
     outer = getattr(_tls, "tape", None)
     _tls.tape = tape = []
     try:
-        return func(arg), tape
+        y = func(arg)
+        if isinstance(y, DeviceArray):
+            y._t  # noqa: B018 - a deferred result is launched HERE, while the tape is still recording
+        return y, tape
     finally:
         _tls.tape = outer
 

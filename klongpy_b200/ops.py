@@ -162,8 +162,11 @@ def _classify(x, device):
 def _classify_meta(x):
     """(kind, kgb dtype) of an operand from metadata only (never materialises a deferred array)."""
     if isinstance(x, DeviceArray):
-        kind = _lib.ARG_DEVSCALAR if x.ndim == 0 else _lib.ARG_ARRAY
-        return kind, {"float64": _lib.F64, "int64": _lib.I64, "float32": _lib.F32, "int32": _lib.I32, "bool": _lib.B8}[x.dtype.name]
+        t = x._tensor
+        if t is None:
+            nd = x._node
+            return (_lib.ARG_DEVSCALAR if len(nd.shape) == 0 else _lib.ARG_ARRAY), nd.kdt
+        return (_lib.ARG_DEVSCALAR if t.dim() == 0 else _lib.ARG_ARRAY), kgb_dtype(t)
     if isinstance(x, (bool, np.bool_, int, np.integer)):
         return _lib.ARG_SCALAR, _lib.I64
     if isinstance(x, np.ndarray) and x.ndim == 0:

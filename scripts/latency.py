@@ -43,6 +43,6 @@ for n in (1000, 100_000):
     fred, _ = be.compile_expr_ir(red_ir, ["a", "b"])
     scan_ir = ("scan", "+", ("var", "_v0"))
     fscan, _ = be.compile_expr_ir(scan_ir, ["a"])
-    print(f"n={n}: a+b eager {per_call(lambda: ops.binary('add', A, B)):.1f} us | compiled {per_call(lambda: fadd(A, B)):.1f} us "
+    print(f"n={n}: a+b eager {per_call(lambda: ops.binary('add', A, B).tensor):.1f} us | compiled {per_call(lambda: fadd(A, B).tensor):.1f} us "
           f"(numpy {per_call_np(lambda: a + b):.1f}) | +/a*b {per_call(lambda: fred(A, B)):.1f} us (numpy {per_call_np(lambda: np.add.reduce(a * b)):.1f}) | "
           f"+\\a {per_call(lambda: fscan(A)):.1f} us (numpy {per_call_np(lambda: np.cumsum(a)):.1f})", flush=True)
