@@ -26,6 +26,11 @@ from . import _lib
 ENABLED = os.environ.get("KGB200_LAZY", "1") != "0"   # on by default since round 2 (KGB200_LAZY=0 switches it off)
 MAX_ARGS = 12
 MAX_CODE = 96
+# Deferring costs ~8 us of host bookkeeping per operator; an extra elementwise pass over n float64 elements costs the GPU
+# 24 n bytes / 6.5 TB/s, i.e. the same 8 us at n ~ 2 M.  Below that an immediate launch is cheaper than the chance to fuse
+# (bench_compiler.kg's 100 K-element rows: `a+b` 11 us launched at once, 19 us deferred and then materialised), so small
+# vectors launch eagerly; 0-d results stay deferred (a chain of scalar operators becomes one launch instead of one each).
+MIN_SIZE = int(os.environ.get("KGB200_LAZY_MIN", str(1 << 21)))
 _infer_cache = {}
 
 
@@ -157,6 +162,12 @@ def defer(code, args):
                     return None  # NumPy broadcasting between different shapes: the eager path expands (or raises)
     if device is None or len(args) > MAX_ARGS or len(code) > MAX_CODE:
         return None
+    if shape is not None:
+        size = 1
+        for d in shape:
+            size *= d
+        if 1 < size < MIN_SIZE or size == 0:
+            return None
     kdt = _infer(code, args, device)
     return DeviceArray._deferred(Node(code, args, shape if shape is not None else (), kdt, device))
 

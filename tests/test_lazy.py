@@ -18,12 +18,14 @@ def lazy_env(fake_backend):
         return orig(*a, **k)
 
     lib.kgb_expr_launch = counting
-    was = lazy.ENABLED
+    was, was_min = lazy.ENABLED, lazy.MIN_SIZE
     lazy.enable(True)
+    lazy.MIN_SIZE = 0   # (the size threshold below which operators launch at once is a tuning knob, not semantics)
     try:
         yield fake_backend, ops, launches
     finally:
         lazy.enable(was)
+        lazy.MIN_SIZE = was_min
         lib.kgb_expr_launch = orig
 
 
@@ -105,7 +107,7 @@ def test_lazy_is_the_default_and_matches_eager_bit_for_bit(cuda_backend):
     assert lazy.ENABLED
     be = cuda_backend
     rng = np.random.default_rng(21)
-    n = 1_000_003
+    n = 3_000_003   # above lazy.MIN_SIZE: elementwise results are deferred
     x, y = rng.standard_normal(n), rng.random(n) + 0.5
     i = rng.integers(-50, 50, n)
     X, Y, I = be.kg_asarray(x), be.kg_asarray(y), be.kg_asarray(i)
@@ -157,7 +159,7 @@ def test_lazy_autograd_on_the_device_matches_torch_float64(cuda_backend):
     import torch
     from klongpy_b200 import lazy, ops
     be = cuda_backend
-    n = 2_000_003
+    n = 3_000_003
     g = torch.Generator(device="cuda").manual_seed(3)
     Xt = torch.rand(n, dtype=torch.float64, device="cuda", generator=g) * 2
     Yt = torch.rand(n, dtype=torch.float64, device="cuda", generator=g)
