@@ -491,8 +491,12 @@ extern "C" int kgb_group(const void* keys, int32_t dtype, int64_t n, int64_t* or
     KGB_REQUIRE(keys && order_out && workspace && workspace_bytes >= carve_group(nullptr, n).total,
                 "kgb_group: null pointer or workspace too small");
     GroupWs g = carve_group(workspace, n);
-    int rc = sort_pairs(keys, dtype, n, 0, (i64*)order_out, nullptr, g.enc, g.sort, g.sort_bytes, st);
+    // small key ranges (10 k stations): the packed sort's full key histogram IS the group table — starts and count come out
+    // of it and neither the sorted keys nor the boundary pass are needed
+    SortGroupOut go{(i64*)starts_out, (i64*)ngroups_out, 0};
+    int rc = sort_pairs(keys, dtype, n, 0, (i64*)order_out, nullptr, g.enc, g.sort, g.sort_bytes, st, &go);
     if (rc != KGB_OK) return rc;
+    if (go.done) return KGB_OK;
     rc = launch_select(BoundaryPred{g.enc}, n, (i64*)starts_out, (i64*)ngroups_out, g.sel, g.sel_bytes, st);
     if (rc != KGB_OK) return rc;
     close_starts<<<1, 1, 0, st>>>((i64*)starts_out, (const i64*)ngroups_out, n);

@@ -837,49 +837,32 @@ static int sort_impl(const void* keys, i64 n, int descending, i64* idx_out, void
     return KGB_OK;
 }
 
-// Packed path (kgb_sort_packed.cuh): one analysis read of the keys, ONE host synchronisation to read the key range back
-// and choose the digit plan, then 16-byte-per-key passes.  Returns 1 when the sort was done, 0 when the caller must
-// run the general pass (keys too wide for this n, or a prefix tie too long for the fix-up), < 0 on error.
+// Packed path (kgb_sort_packed.cuh): a 64 K-key sample guesses the key range, one read of the keys verifies the guess and
+// builds the histograms, then 16-byte-per-key passes.  Returns 1 when the sort was done, 0 when the caller must run the
+// general pass (keys too wide for this n, or a prefix tie too long for the fix-up), < 0 on error.
 static int sort_packed(const void* keys, int dtype, i64 n, int descending, i64* idx_out, void* keys_sorted_out,
-                       u64* enc_sorted_out, const SortWs& gw, cudaStream_t st) {
+                       u64* enc_sorted_out, const SortWs& gw, cudaStream_t st, SortGroupOut* grp) {
     constexpr int T = KGB_PK_CT * KGB_PK_KPT;
-    const int sms = sm_count();
     pk::Ws w = pk::carve_ws<T>(gw.packed, (u64)n);
-    KGB_CUDA_CHECK(pk::packed_analyze<T>(keys, dtype, (u64)n, w, sms, st));
-    u64 h[3];
-    KGB_CUDA_CHECK(cudaMemcpyAsync(h, w.ctl, sizeof h, cudaMemcpyDeviceToHost, st));
-    KGB_CUDA_CHECK(cudaStreamSynchronize(st));
-    const pk::Plan p = pk::make_plan(h[0], ~h[1], h[2], (u64)n);
-    if (p.npass < 0) return 0;
-    u64* fin = nullptr;
-    KGB_CUDA_CHECK((pk::packed_passes<KGB_PK_CT, KGB_PK_KPT, KGB_PK_LBT, KGB_PK_OCC>(
-        keys, dtype, (u64)n, p, descending, idx_out, keys_sorted_out, enc_sorted_out, w, gw.keys[0], gw.keys[1],
-        p.prefix ? &fin : nullptr, sms, st)));
-    if (!p.prefix) return 1;
-    pk::FixArgs f{};
-    f.sorted = fin;
-    f.keys = keys;
-    f.idx_out = idx_out;
-    f.keys_sorted_out = keys_sorted_out;
-    f.enc_sorted_out = enc_sorted_out;
-    f.flags = w.ctl + 3;
-    f.n = (u32)n;
-    f.pb = p.pb;
-    f.dtype = dtype;
-    f.descending = descending;
-    if (pk::key_width(dtype) == 8)
-        pk::fixup_kernel<8><<<sms * 8, 256, 0, st>>>(f);
-    else
-        pk::fixup_kernel<4><<<sms * 8, 256, 0, st>>>(f);
-    KGB_CUDA_CHECK(cudaGetLastError());
-    u64 over = 0;
-    KGB_CUDA_CHECK(cudaMemcpyAsync(&over, w.ctl + 3, 8, cudaMemcpyDeviceToHost, st));
-    KGB_CUDA_CHECK(cudaStreamSynchronize(st));
-    return over ? 0 : 1;
+    pk::GroupOut g{};
+    if (grp) {
+        g.starts_out = grp->starts_out;
+        g.ngroups_out = grp->ngroups_out;
+    }
+    const int rc = pk::packed_sort_run<KGB_PK_CT, KGB_PK_KPT, KGB_PK_LBT, KGB_PK_OCC>(
+        keys, dtype, (u64)n, descending, idx_out, keys_sorted_out, enc_sorted_out, w, gw.keys[0], gw.keys[1], sm_count(), st,
+        grp ? &g : nullptr);
+    if (grp) grp->done = rc == 1 ? g.done : 0;
+    if (rc < 0) {
+        set_error("packed sort: %s", cudaGetErrorString((cudaError_t)(-rc)));
+        return KGB_ECUDA;
+    }
+    return rc;
 }
 
 int sort_pairs(const void* keys, int dtype, i64 n, int descending, i64* idx_out, void* keys_sorted_out,
-               u64* enc_sorted_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+               u64* enc_sorted_out, void* ws, size_t ws_bytes, cudaStream_t st, SortGroupOut* grp) {
+    if (grp) grp->done = 0;
     KGB_REQUIRE(current_device() >= 0, "kgb_init() has not been called on this thread");
     KGB_REQUIRE(n >= 0 && n < 0xffffffffll, "argsort: n must be below 2^32");
     if (n == 0) return KGB_OK;
@@ -892,7 +875,7 @@ int sort_pairs(const void* keys, int dtype, i64 n, int descending, i64* idx_out,
         const long long packed_min = m ? atoll(m) : (1ll << 18);
         if (packed_env && n >= packed_min && n < (1ll << 30)) {
             const SortWs gw = carve(ws, n);
-            const int rc = sort_packed(keys, dtype, n, descending, idx_out, keys_sorted_out, enc_sorted_out, gw, st);
+            const int rc = sort_packed(keys, dtype, n, descending, idx_out, keys_sorted_out, enc_sorted_out, gw, st, grp);
             if (rc != 0) return rc < 0 ? rc : KGB_OK;
         }
     }

@@ -60,7 +60,11 @@ struct PassArgs {
     i64* idx_out;           // LAST: the permutation
     void* keys_sorted_out;  // LAST, optional: typed sorted keys
     u64* enc_sorted_out;    // LAST, optional: order-encoded sorted keys
-    const u32* digit_base;  // [1 << BITS] exclusive global digit offsets of this pass
+    const u32* hist;        // [1 << BITS] digit counts of this pass (the look-back group scans them into digit bases)
+    u32* next_hist;         // next pass's digit counts, accumulated by THIS pass while the keys are in registers
+    int next_shift;         //   (digit position of the next pass inside the packed word)
+    u32 next_mask;          //   (1 << next bits) - 1, or 0: nothing to count (last pass, or the histograms came up front)
+    const u64* invalid;     // device flag: non-zero = the guessed key range was wrong, every pass returns at once
     u32* states;            // [tiles][1 << BITS] look-back words of THIS pass (zeroed): [31:30] flag, [29:0] count
     u32* ticket;
     u32 n;
@@ -195,6 +199,8 @@ template <int BITS, int CT, int KPT, int LBT> struct PassSmem {
     u32 cntd[2][C::BINS];   // (tile count of the digit) << 16 | exclusive digit offset inside the tile
     u32 gbase[2][C::BINS];  // global position of tile-sorted slot p with digit d is gbase[d] + p   (mod 2^32)
     u32 wsum[32];
+    u32 lbw[32];            // look-back group: warp totals of the digit-count scan
+    u32 nhist[MAXBINS];     // next pass's digit counts of this CTA
     u64 cnt_bar[2], gb_bar[2];
     u32 tile_of[2];
     u32 tile_slot[2];
@@ -212,7 +218,9 @@ __global__ void __launch_bounds__(CT + LBT, OCC) pass_kernel(const PassArgs a) {
     const u32 n = a.n;
     const u32 ntiles = (n + T - 1) / T;
     const int shift = a.shift;
+    if (a.invalid && *a.invalid) return;  // (uniform: every thread reads the same word before any barrier)
 
+    for (int q = tid; q < MAXBINS; q += CT + LBT) sm.nhist[q] = 0;
     if (tid == 0) {
         // Out of lockstep: if all CTAs publish their tile counts at the same moment, tile t must walk back over ~grid/2
         // aggregates to find an inclusive prefix.  Staggered by tile_period / grid, predecessor t-k published k * stagger
@@ -255,9 +263,30 @@ __global__ void __launch_bounds__(CT + LBT, OCC) pass_kernel(const PassArgs a) {
         const int lt = tid - CT;
         const int d0 = lt * ELB;             // first digit of this thread
         const bool owner = d0 < BINS;
+        // exclusive scan of the pass's digit counts -> global digit bases (was a separate launch per sort)
         u32 dbase[ELB];
+        {
+            u32 tot = 0;
 #pragma unroll
-        for (int e = 0; e < ELB; e++) dbase[e] = owner ? a.digit_base[d0 + e] : 0u;
+            for (int e = 0; e < ELB; e++) {
+                const u32 c = owner ? a.hist[d0 + e] : 0u;
+                dbase[e] = tot;
+                tot += c;
+            }
+            u32 inc = tot;
+            const int ll = lt & 31;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const u32 v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (ll >= o) inc += v;
+            }
+            if (ll == 31) sm.lbw[lt >> 5] = inc;
+            asm volatile("bar.sync 2, %0;" ::"n"(LBT) : "memory");
+            u32 pre = inc - tot;
+            for (int w = 0; w < (lt >> 5); w++) pre += sm.lbw[w];
+#pragma unroll
+            for (int e = 0; e < ELB; e++) dbase[e] += pre;
+        }
 #if KGB_PK_STATS
         unsigned long long st_rounds = 0, st_steps = 0, st_tiles = 0;
 #endif
@@ -518,6 +547,19 @@ __global__ void __launch_bounds__(CT + LBT, OCC) pass_kernel(const PassArgs a) {
         // digit and writes back count + (number of peers) — peers read and write the same values, so no leader election,
         // no branch and no shuffle is needed; the rank inside the tile's digit group follows after the totals step.
         u32 rank[KPT];
+        if (a.next_mask) {
+            // the NEXT pass's digit histogram, taken here while the keys sit in registers (one ATOMS.POPC.INC per key: lanes
+            // that hit the same bin fold in hardware) instead of another read of all keys before the sort
+            const u32 base = tile * (u32)T;
+            if ((n - base) >= (u32)T) {
+#pragma unroll
+                for (int k = 0; k < KPT; k++) atomicAdd(&sm.nhist[(u32)(key[k] >> a.next_shift) & a.next_mask], 1u);
+            } else {
+#pragma unroll
+                for (int k = 0; k < KPT; k++)
+                    if (base + wslot + k * 32 + lane < n) atomicAdd(&sm.nhist[(u32)(key[k] >> a.next_shift) & a.next_mask], 1u);
+            }
+        }
         {
             wcount_t* wh = &sm.whist[warp][0];
 #pragma unroll
@@ -606,6 +648,12 @@ __global__ void __launch_bounds__(CT + LBT, OCC) pass_kernel(const PassArgs a) {
     }
     if (prev != NO_TILE) write_out(i - 1, prev);
     bar_named<CT>(1);
+    if (a.next_mask) {
+        for (u32 q = tid; q <= a.next_mask; q += CT) {
+            const u32 c = sm.nhist[q];
+            if (c) atomicAdd(&a.next_hist[q], c);
+        }
+    }
     if (tid == 0) {
         sm.tile_of[i & 1u] = NO_TILE;  // release the look-back group
         mbar_arrive(&sm.cnt_bar[i & 1u]);
@@ -616,11 +664,121 @@ __global__ void __launch_bounds__(CT + LBT, OCC) pass_kernel(const PassArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------- analysis + histograms
-// One read of the keys: out[0] = OR of enc(key) ^ enc(key[0]) (bits below its lowest set bit are shared by all keys),
-// out[1] = ~min(enc), out[2] = max(enc) (zero-initialised by the caller, hence the complement).
+// Control block (u64 words, zeroed before each attempt):
+//   [0] OR of enc ^ enc(key[0])   [1] ~min(enc)   [2] max(enc)  (exact, analyze_kernel)   [3] prefix fix-up overflow
+//   [4] guessed plan invalid
+//   [8..10] the same three statistics of the SAMPLE
+constexpr int CTL_DIFF = 0, CTL_NMIN = 1, CTL_MAX = 2, CTL_FIXOVER = 3, CTL_INVALID = 4, CTL_SAMPLE = 8, CTL_WORDS = 16;
+constexpr int FULL_MAX_BITS = 15;   // key fields up to 2^15 values get a full histogram in shared memory (128 KB)
+constexpr u32 SAMPLE_KEYS = 1u << 16;
+
+template <int KW> __device__ __forceinline__ u64 load_key(const void* keys, u64 i) {
+    return KW == 8 ? __ldg(reinterpret_cast<const u64*>(keys) + i) : (u64)__ldg(reinterpret_cast<const u32*>(keys) + i);
+}
+
+// min / max / varying bits of a strided sample of the keys: enough to GUESS the key field (verified by hist_verify_kernel)
 template <int KW>
-__global__ void __launch_bounds__(256) analyze_kernel(const void* __restrict__ keys, u32 n, int dtype, u64* __restrict__ out) {
-    const u64 first = enc_rt(dtype, KW == 8 ? reinterpret_cast<const u64*>(keys)[0] : (u64)reinterpret_cast<const u32*>(keys)[0]);
+__global__ void __launch_bounds__(1024) sample_kernel(const void* __restrict__ keys, u32 n, int dtype, u64* __restrict__ ctl) {
+    const u64 first = enc_rt(dtype, load_key<KW>(keys, 0));
+    const u32 m = n < SAMPLE_KEYS ? n : SAMPLE_KEYS;
+    const u64 step = n / m;
+    u64 diff = 0, mn = first, mx = first;
+    for (u32 j = blockIdx.x * 1024 + threadIdx.x; j < m; j += gridDim.x * 1024) {
+        const u64 e = enc_rt(dtype, load_key<KW>(keys, (u64)j * step));
+        diff |= e ^ first;
+        mn = e < mn ? e : mn;
+        mx = e > mx ? e : mx;
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        diff |= __shfl_xor_sync(0xffffffffu, diff, o);
+        const u64 a = __shfl_xor_sync(0xffffffffu, mn, o), b = __shfl_xor_sync(0xffffffffu, mx, o);
+        mn = a < mn ? a : mn;
+        mx = b > mx ? b : mx;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (diff) atomicOr((unsigned long long*)&ctl[CTL_SAMPLE + CTL_DIFF], diff);
+        atomicMax((unsigned long long*)&ctl[CTL_SAMPLE + CTL_NMIN], ~mn);
+        atomicMax((unsigned long long*)&ctl[CTL_SAMPLE + CTL_MAX], mx);
+    }
+}
+
+struct HvArgs {
+    const void* keys;
+    u32 n;
+    int dtype;
+    u64 enc_base;   // key field = (enc - enc_base) >> lo, `live` bits wide
+    int lo, live, prefix;
+    int shift0;     // first pass's digit inside the key field (digit mode)
+    u32 mask0;
+    u64* ctl;
+    u32* hist;      // digit mode: first pass's digit counts; full mode: the whole field's histogram [1 << live]
+};
+
+// ONE read of the keys: the check that every key fits the guessed field, and a histogram — of the first pass's digit, or
+// (FULL, fields up to 2^15 values) of the whole key field, from which every pass's digit counts AND the group boundaries
+// of `=a` follow without touching the keys again.  Shared-memory atomicAdd(.., 1) compiles to ATOMS.POPC.INC (lanes on
+// one bin fold in hardware).  A key outside the field raises ctl[CTL_INVALID]; the caller then takes the exact
+// statistics (analyze_kernel) and plans again.
+template <int KW, bool FULL>
+__global__ void __launch_bounds__(1024) hist_verify_kernel(const HvArgs h) {
+    extern __shared__ u32 sh_hist[];
+    const u32 bins = FULL ? (1u << h.live) : (h.mask0 + 1u);
+    for (u32 q = threadIdx.x; q < bins; q += 1024) sh_hist[q] = 0;
+    __syncthreads();
+    const u64 lowmask = (h.prefix || h.lo == 0) ? 0ull : ((1ull << h.lo) - 1ull);
+    // fits <=> enc >= base, field < 2^live, shared low bits equal the base's: one unsigned compare on rel = enc - base
+    // (enc < base wraps to a huge rel) plus the low-bit test
+    const u64 limit = (h.live + h.lo >= 64) ? ~0ull : ((1ull << (h.live + h.lo)) - 1ull);
+    bool bad = false;
+    constexpr int U = 8;
+    auto sweep = [&](auto enc) {  // one instantiation per key type: the dtype is tested once per kernel, not per key
+        for (u64 base = (u64)blockIdx.x * (1024 * U); base < h.n; base += (u64)gridDim.x * (1024 * U)) {
+            u64 r[U];
+            bool valid[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const u64 i = base + u * 1024 + threadIdx.x;
+                valid[u] = i < h.n;
+                r[u] = valid[u] ? (KW == 8 ? __ldcs(reinterpret_cast<const u64*>(h.keys) + i) : (u64)__ldcs(reinterpret_cast<const u32*>(h.keys) + i)) : 0ull;
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const u64 e = enc(r[u]);
+                const u64 rel = e - h.enc_base;
+                const bool fits = e >= h.enc_base && rel <= limit && (rel & lowmask) == 0;
+                const u64 f = rel >> h.lo;
+                if (valid[u]) {
+                    if (fits)
+                        atomicAdd(&sh_hist[FULL ? (u32)f : ((u32)(f >> h.shift0) & h.mask0)], 1u);
+                    else
+                        bad = true;
+                }
+            }
+        }
+    };
+    switch (h.dtype) {
+        case KGB_I64: sweep([](u64 r) { return r ^ 0x8000000000000000ull; }); break;
+        case KGB_F64: sweep([](u64 r) { return KeyCodec<KGB_F64>::enc(__longlong_as_double((i64)r)); }); break;
+        case KGB_F64_RAW: sweep([](u64 r) { return KeyCodec<KGB_F64_RAW>::enc(__longlong_as_double((i64)r)); }); break;
+        case KGB_I32: sweep([](u64 r) { return (u64)((u32)r ^ 0x80000000u); }); break;
+        case KGB_F32: sweep([](u64 r) { return KeyCodec<KGB_F32>::enc(__int_as_float((int)(u32)r)); }); break;
+        default: sweep([](u64 r) { return KeyCodec<KGB_F32_RAW>::enc(__int_as_float((int)(u32)r)); }); break;
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0 && bad) atomicOr((unsigned long long*)&h.ctl[CTL_INVALID], 1ull);
+    __syncthreads();
+    for (u32 q = threadIdx.x; q < bins; q += 1024) {
+        const u32 c = sh_hist[q];
+        if (c) atomicAdd(&h.hist[q], c);
+    }
+}
+
+// exact statistics of ALL keys (only after a wrong guess): ctl[CTL_DIFF] = OR of enc ^ enc(key[0]), ctl[CTL_NMIN] = ~min,
+// ctl[CTL_MAX] = max (zero-initialised by the caller, hence the complement)
+template <int KW>
+__global__ void __launch_bounds__(256) analyze_kernel(const void* __restrict__ keys, u32 n, int dtype, u64* __restrict__ ctl) {
+    const u64 first = enc_rt(dtype, load_key<KW>(keys, 0));
     u64 diff = 0, mn = first, mx = first;
     constexpr int U = 8;
     for (u64 base = (u64)blockIdx.x * (256 * U); base < n; base += (u64)gridDim.x * (256 * U)) {
@@ -628,8 +786,7 @@ __global__ void __launch_bounds__(256) analyze_kernel(const void* __restrict__ k
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const u64 i = base + u * 256 + threadIdx.x;
-            const u64 ii = i < n ? i : 0;
-            r[u] = KW == 8 ? __ldg(reinterpret_cast<const u64*>(keys) + ii) : (u64)__ldg(reinterpret_cast<const u32*>(keys) + ii);
+            r[u] = load_key<KW>(keys, i < n ? i : 0);
         }
 #pragma unroll
         for (int u = 0; u < U; u++) {
@@ -647,72 +804,78 @@ __global__ void __launch_bounds__(256) analyze_kernel(const void* __restrict__ k
         mx = b > mx ? b : mx;
     }
     if ((threadIdx.x & 31) == 0) {
-        if (diff) atomicOr((unsigned long long*)&out[0], diff);
-        atomicMax((unsigned long long*)&out[1], ~mn);
-        atomicMax((unsigned long long*)&out[2], mx);
+        if (diff) atomicOr((unsigned long long*)&ctl[CTL_DIFF], diff);
+        atomicMax((unsigned long long*)&ctl[CTL_NMIN], ~mn);
+        atomicMax((unsigned long long*)&ctl[CTL_MAX], mx);
     }
 }
 
-struct HistArgs {
-    int npass;
-    int shift[MAXP];  // digit position inside the KEY FIELD (packed shift minus pb)
+struct DeriveArgs {
+    const u32* full;   // [1 << live]
+    int live, npass;
+    int shift[MAXP];   // digit positions inside the key field
     int bits[MAXP];
-    int lo;
-    u64 kmask, enc_base;
-    int dtype;
+    u32* hist;         // [npass][MAXBINS] out
+    // group boundaries (optional): starts of the runs of equal keys in the sorted order, ascending key
+    i64* starts_out;
+    i64* ngroups_out;
+    u32 n;
 };
 
-// digit histograms of all passes in one read of the keys: hist[p][1 << bits[p]] at hist + p * MAXBINS
-template <int KW>
-__global__ void __launch_bounds__(256) hist_kernel(const void* __restrict__ keys, u32 n, const HistArgs h, u32* __restrict__ ghist) {
+// From the full key-field histogram: every pass's digit counts, and — for `=a` — the group start offsets (exclusive
+// prefix sums of the non-empty bins) and their number.  One CTA; at most 2^15 bins.
+__global__ void __launch_bounds__(1024) derive_kernel(const DeriveArgs d) {
     __shared__ u32 sh[MAXP * MAXBINS];
-    const int tot = h.npass * MAXBINS;
-    for (int i = threadIdx.x; i < tot; i += 256) sh[i] = 0;
+    __shared__ u32 wtot[32], wcnt[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int q = tid; q < d.npass * MAXBINS; q += 1024) sh[q] = 0;
     __syncthreads();
-    constexpr int U = 4;
-    for (u64 base = (u64)blockIdx.x * (256 * U); base < n; base += (u64)gridDim.x * (256 * U)) {
-        u64 r[U];
-        bool valid[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const u64 i = base + u * 256 + threadIdx.x;
-            valid[u] = i < n;
-            const u64 ii = valid[u] ? i : 0;
-            r[u] = KW == 8 ? __ldcs(reinterpret_cast<const u64*>(keys) + ii) : (u64)__ldcs(reinterpret_cast<const u32*>(keys) + ii);
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            if (valid[u]) {
-                const u64 f = ((enc_rt(h.dtype, r[u]) - h.enc_base) >> h.lo) & h.kmask;
-                // atomicAdd(.., 1) compiles to ATOMS.POPC.INC, which folds lanes that hit the same bin in hardware
-                for (int p = 0; p < h.npass; p++) atomicAdd(&sh[p * MAXBINS + ((u32)(f >> h.shift[p]) & ((1u << h.bits[p]) - 1u))], 1u);
-            }
+    const u32 bins = 1u << d.live;
+    const u32 per = (bins + 1023) / 1024;          // consecutive bins per thread (<= 32)
+    const u32 b0 = tid * per;
+    u32 sum = 0, cnt = 0;
+    for (u32 q = b0; q < b0 + per && q < bins; q++) {
+        const u32 c = d.full[q];
+        if (c) {
+            for (int p = 0; p < d.npass; p++) atomicAdd(&sh[p * MAXBINS + ((q >> d.shift[p]) & ((1u << d.bits[p]) - 1u))], c);
+            sum += c;
+            cnt++;
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < tot; i += 256) {
-        const u32 c = sh[i];
-        if (c) atomicAdd(&ghist[i], c);
-    }
-}
-
-// exclusive scan of every pass's histogram (in place): one CTA per pass, MAXBINS threads
-__global__ void __launch_bounds__(MAXBINS) base_kernel(u32* __restrict__ ghist) {
-    __shared__ u32 ws[32];
-    u32* h = ghist + (size_t)blockIdx.x * MAXBINS;
-    const int d = threadIdx.x, lane = d & 31, warp = d >> 5;
-    const u32 c = h[d];
-    u32 inc = c;
+    for (int q = tid; q < d.npass * MAXBINS; q += 1024) d.hist[q] = sh[q];
+    if (!d.starts_out) return;
+    // block-wide exclusive scan of (sum, cnt) over the threads, then each thread walks its bins again
+    u32 isum = sum, icnt = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const u32 v = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += v;
+        const u32 a = __shfl_up_sync(0xffffffffu, isum, o), b = __shfl_up_sync(0xffffffffu, icnt, o);
+        if (lane >= o) {
+            isum += a;
+            icnt += b;
+        }
     }
-    if (lane == 31) ws[warp] = inc;
+    if (lane == 31) {
+        wtot[warp] = isum;
+        wcnt[warp] = icnt;
+    }
     __syncthreads();
-    u32 pre = 0;
-    for (int w = 0; w < warp; w++) pre += ws[w];
-    h[d] = pre + inc - c;
+    u32 ps = isum - sum, pc = icnt - cnt;
+    for (int w = 0; w < warp; w++) {
+        ps += wtot[w];
+        pc += wcnt[w];
+    }
+    for (u32 q = b0; q < b0 + per && q < bins; q++) {
+        const u32 c = d.full[q];
+        if (c) {
+            d.starts_out[pc++] = (i64)ps;
+            ps += c;
+        }
+    }
+    if (tid == 1023) {
+        d.starts_out[pc] = (i64)d.n;
+        *d.ngroups_out = (i64)pc;
+    }
 }
 
 // no live bit at all (or n == 1): the stable permutation is the identity
@@ -739,11 +902,13 @@ struct FixArgs {
     void* keys_sorted_out;
     u64* enc_sorted_out;
     u64* flags;
+    const u64* invalid;   // the guessed plan was wrong: nothing to fix up
     u32 n;
     int pb, dtype, descending;
 };
 template <int KW>
 __global__ void __launch_bounds__(256) fixup_kernel(const FixArgs a) {
+    if (a.invalid && *a.invalid) return;
     const u64 posmask = (1ull << a.pb) - 1ull;
     const bool want_keys = a.keys_sorted_out || a.enc_sorted_out;
     auto fetch = [&](u64 pos) -> u64 {
@@ -805,7 +970,7 @@ __global__ void __launch_bounds__(256) fixup_kernel(const FixArgs a) {
 
 // ------------------------------------------------------------------------------------------- host-side planning
 struct Plan {
-    int npass;            // 0: identity
+    int npass;            // 0: identity; < 0: not sortable by the packed pass (the caller uses the general one)
     int bits[MAXP];
     int shift[MAXP];      // inside the packed word
     int lo, pb, live;     // live = number of key bits carried
@@ -819,19 +984,16 @@ inline int ceil_log2_u64(u64 x) {  // smallest b with 2^b >= x
     return b;
 }
 
-// diff: OR of enc ^ enc0; mn/mx: extreme encoded keys.  Chooses the key field (enc - mn) >> lo, `live` bits wide, and
-// the digit widths: as few passes as 10-bit digits allow, widths evened out (27 live bits -> 9+9+9, 14 -> 7+7).
-inline Plan make_plan(u64 diff, u64 mn, u64 mx, u64 n) {
+// Key field (enc - mn) >> lo for keys in [mn, mx] whose bits below `lo` all equal mn's; digit widths: as few passes as
+// 10-bit digits allow, widths evened out (27 live bits -> 9+9+9, 14 -> 7+7).
+inline Plan plan_from_range(u64 mn, u64 mx, int lo, u64 n) {
     Plan p{};
     p.pb = ceil_log2_u64(n);
     if (p.pb < 1) p.pb = 1;
     p.enc_base = mn;
-    if (diff == 0 || mx == mn) {
-        p.npass = 0;
-        return p;
-    }
-    const int hi = 63 - __builtin_clzll(mx - mn);
-    int lo = __builtin_ctzll(diff);  // every key shares the bits below: (enc - mn) has zeros there
+    const u64 range = mx - mn;
+    const int hi = range ? 63 - __builtin_clzll(range) : 0;
+    if (lo > hi) lo = hi;
     int live = hi - lo + 1;
     const int room = 64 - p.pb;
     if (live > room) {
@@ -844,7 +1006,7 @@ inline Plan make_plan(u64 diff, u64 mn, u64 mx, u64 n) {
     p.kmask = live >= 64 ? ~0ull : ((1ull << live) - 1ull);
     int np = (live + MAXBITS - 1) / MAXBITS;
     if (np < 1) np = 1;
-    if (np > PLAN_MAXP) {  // only tiny n (few position bits) with wide keys: the caller uses the general pass
+    if (np > PLAN_MAXP) {  // only tiny n (few position bits) with wide keys
         p.npass = -1;
         return p;
     }
@@ -862,8 +1024,34 @@ inline Plan make_plan(u64 diff, u64 mn, u64 mx, u64 n) {
     return p;
 }
 
+// exact statistics (diff = OR of enc ^ enc(key 0), extremes) -> plan; all keys equal -> identity
+inline Plan make_plan(u64 diff, u64 mn, u64 mx, u64 n) {
+    if (diff == 0 || mx == mn) {
+        Plan p{};
+        p.pb = ceil_log2_u64(n);
+        if (p.pb < 1) p.pb = 1;
+        p.enc_base = mn;
+        return p;
+    }
+    return plan_from_range(mn, mx, __builtin_ctzll(diff), n);
+}
+
+// statistics of a 64 K-key SAMPLE -> a guess: the sampled range widened by 1/1024 of itself on either side (the
+// extremes of uniform data lie range/65536 outside the sample's), aligned to the low bits the sampled keys share.
+// hist_verify_kernel checks every key against it; a wrong guess is re-planned from the exact statistics.
+inline Plan guess_plan(u64 sdiff, u64 smn, u64 smx, u64 n) {
+    const int lo = sdiff ? __builtin_ctzll(sdiff) : 0;
+    const u64 unit = 1ull << lo;
+    const u64 r = smx - smn;
+    u64 margin = r / 1024 + 1;
+    margin = (margin + unit - 1) / unit * unit;   // a multiple of 2^lo: the base keeps the keys' shared low bits
+    const u64 mn = smn >= margin ? smn - margin : (smn & (unit - 1));
+    const u64 mx = smx <= ~0ull - margin ? smx + margin : smx + ((~0ull - smx) / unit * unit);
+    return plan_from_range(mn, mx, lo, n);
+}
+
 // ------------------------------------------------------------------------------------------- host-side driver
-// geometry of the pass (tuned on a B200, profiles/r02_sort_lab_*.log)
+// geometry of the pass (tuned on a B200, profiles/r02*_sort_lab_*.log)
 #ifndef KGB_PK_CT
 #define KGB_PK_CT 512
 #define KGB_PK_KPT 16
@@ -872,11 +1060,12 @@ inline Plan make_plan(u64 diff, u64 mn, u64 mx, u64 n) {
 #endif
 
 struct Ws {
-    u64* ctl;      // [0] diff, [1] ~min, [2] max, [3] fix-up flags
-    u32* hist;     // [MAXP][MAXBINS]
+    u64* ctl;      // CTL_WORDS control words (see above)
+    u32* hist;     // [MAXP][MAXBINS] digit counts per pass
     u32* tickets;  // [MAXP] (+ pad)
-    u32* states;   // look-back words, one [tiles][1 << bits] block per pass
-    size_t zero_bytes;  // ctl .. tickets are contiguous (zeroed before the analysis)
+    u32* full;     // [1 << FULL_MAX_BITS] full key-field histogram
+    size_t zero_bytes;  // ctl .. full are contiguous (zeroed before every attempt)
+    u32* states;   // look-back words, one [LB_PAD + tiles][1 << bits] block per pass
     size_t total;
 };
 template <int T> inline Ws carve_ws(void* ws, u64 n) {
@@ -889,6 +1078,8 @@ template <int T> inline Ws carve_ws(void* ws, u64 n) {
     o += (size_t)MAXP * MAXBINS * 4;
     w.tickets = (u32*)(p + o);
     o += 256;
+    w.full = (u32*)(p + o);
+    o += (size_t)4 << FULL_MAX_BITS;
     w.zero_bytes = o;
     w.states = (u32*)(p + o);
     o += align_up(((size_t)((n + T - 1) / T) + LB_PAD) * 4 * (PLAN_MAXP * MAXBINS), 256);
@@ -934,32 +1125,99 @@ template <int CT, int KPT, int LBT, int OCC> struct Launcher {
 
 inline int key_width(int dtype) { return (dtype == KGB_F32 || dtype == KGB_I32 || dtype == KGB_F32_RAW) ? 4 : 8; }
 
-// Step 1: zero the control block and find the varying bits (the caller synchronises and reads ctl[0..1] back).
-template <int T> inline cudaError_t packed_analyze(const void* keys, int dtype, u64 n, const Ws& w, int sms, cudaStream_t st) {
-    cudaError_t e = cudaMemsetAsync(w.ctl, 0, w.zero_bytes, st);
-    if (e != cudaSuccess) return e;
-    long long blocks = (long long)((n + 2047) / 2048);
-    if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
-    if (key_width(dtype) == 8)
-        analyze_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(keys, (u32)n, dtype, w.ctl);
-    else
-        analyze_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(keys, (u32)n, dtype, w.ctl);
-    return cudaGetLastError();
-}
+struct GroupOut {      // `=a`: filled when the key field is small enough for the full histogram (done = 1)
+    i64* starts_out;   // [G + 1]
+    i64* ngroups_out;
+    int done;
+};
+struct LabInfo {       // development harness only
+    cudaEvent_t ev[MAXP + 4];   // [0] start, [1] sample read back, [2] histograms done, [3 + i] pass i done, last: fix-up done
+    Plan plan;
+    int attempts;
+    u64* stats;
+};
 
-// Step 2: histograms, digit bases and the passes of plan `p`.  buf0/buf1: 8n bytes each.  When `final_packed` is set the
-// last pass is run as a middle pass and leaves the sorted packed words in *final_packed (the prefix fix-up reads them).
+#define KGB_PK_TRY(expr)                 \
+    do {                                 \
+        cudaError_t e_ = (expr);         \
+        if (e_ != cudaSuccess) return e_; \
+    } while (0)
+
+// One attempt with plan `p`: histograms (+ verification of the plan), passes, prefix fix-up.  No synchronisation.
 template <int CT, int KPT, int LBT, int OCC>
-inline cudaError_t packed_passes(const void* keys, int dtype, u64 n, const Plan& p, int descending, i64* idx_out,
-                                 void* keys_sorted_out, u64* enc_sorted_out, const Ws& w, u64* buf0, u64* buf1,
-                                 u64** final_packed, int sms, cudaStream_t st, cudaEvent_t* lab_events = nullptr,
-                                 u64* lab_stats = nullptr) {
+inline cudaError_t packed_attempt(const void* keys, int dtype, u64 n, const Plan& p, int descending, i64* idx_out,
+                                  void* keys_sorted_out, u64* enc_sorted_out, const Ws& w, u64* buf0, u64* buf1, int sms,
+                                  cudaStream_t st, GroupOut* grp, LabInfo* lab) {
+    const int kw = key_width(dtype);
+    const bool full = !p.prefix && p.live <= FULL_MAX_BITS;
+    KGB_PK_TRY(cudaMemsetAsync(w.ctl, 0, CTL_SAMPLE * 8, st));                         // keep the sample's words
+    KGB_PK_TRY(cudaMemsetAsync(w.hist, 0, w.zero_bytes - ((char*)w.hist - (char*)w.ctl), st));
+    const size_t tiles = (size_t)((n + (u64)(CT * KPT) - 1) / (u64)(CT * KPT));
+    {   // look-back words of all passes: one memset
+        size_t words = 0;
+        for (int i = 0; i < p.npass; i++) words += (tiles + LB_PAD) << p.bits[i];
+        KGB_PK_TRY(cudaMemsetAsync(w.states, 0, words * 4, st));
+    }
+    HvArgs h{};
+    h.keys = keys;
+    h.n = (u32)n;
+    h.dtype = dtype;
+    h.enc_base = p.enc_base;
+    h.lo = p.lo;
+    h.live = p.live;
+    h.prefix = p.prefix;
+    h.shift0 = p.shift[0] - p.pb;
+    h.mask0 = (1u << p.bits[0]) - 1u;
+    h.ctl = w.ctl;
+    h.hist = full ? w.full : w.hist;
+    {
+        static bool attr_set[64] = {false};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+            KGB_PK_TRY(cudaFuncSetAttribute(hist_verify_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << FULL_MAX_BITS));
+            KGB_PK_TRY(cudaFuncSetAttribute(hist_verify_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << FULL_MAX_BITS));
+            attr_set[dev] = true;
+        }
+        long long blocks = (long long)((n + 8191) / 8192);
+        const long long cap = (long long)sms * (full ? 1 : 2);
+        if (blocks > cap) blocks = cap;
+        const size_t smem = full ? ((size_t)4 << p.live) : ((size_t)4 << p.bits[0]);
+        if (full) {
+            if (kw == 8) hist_verify_kernel<8, true><<<(unsigned)blocks, 1024, smem, st>>>(h);
+            else hist_verify_kernel<4, true><<<(unsigned)blocks, 1024, smem, st>>>(h);
+        } else {
+            if (kw == 8) hist_verify_kernel<8, false><<<(unsigned)blocks, 1024, smem, st>>>(h);
+            else hist_verify_kernel<4, false><<<(unsigned)blocks, 1024, smem, st>>>(h);
+        }
+        KGB_PK_TRY(cudaGetLastError());
+    }
+    if (grp) grp->done = 0;
+    if (full) {
+        DeriveArgs d{};
+        d.full = w.full;
+        d.live = p.live;
+        d.npass = p.npass;
+        for (int i = 0; i < p.npass; i++) {
+            d.shift[i] = p.shift[i] - p.pb;
+            d.bits[i] = p.bits[i];
+        }
+        d.hist = w.hist;
+        d.n = (u32)n;
+        if (grp) {
+            d.starts_out = grp->starts_out;
+            d.ngroups_out = grp->ngroups_out;
+            grp->done = 1;
+        }
+        derive_kernel<<<1, 1024, 0, st>>>(d);
+        KGB_PK_TRY(cudaGetLastError());
+    }
+    if (lab) cudaEventRecord(lab->ev[2], st);
     PassArgs a{};
-    a.stats = lab_stats;
     a.in_keys = keys;
     a.idx_out = idx_out;
     a.keys_sorted_out = keys_sorted_out;
-    a.enc_sorted_out = enc_sorted_out;
+    a.enc_sorted_out = (grp && full) ? nullptr : enc_sorted_out;  // `=a` wanted the sorted keys only to find the boundaries
     a.n = (u32)n;
     a.lo = p.lo;
     a.pb = p.pb;
@@ -967,67 +1225,128 @@ inline cudaError_t packed_passes(const void* keys, int dtype, u64 n, const Plan&
     a.enc_base = p.enc_base;
     a.dtype = dtype;
     a.descending = descending;
-    if (p.npass == 0) {
-        long long ib = (long long)((n + 255) / 256);
-        if (ib > (long long)sms * 8) ib = (long long)sms * 8;
-        identity_kernel<<<(unsigned)ib, 256, 0, st>>>(a);
-        return cudaGetLastError();
+    a.invalid = w.ctl + CTL_INVALID;
+    a.stats = lab ? lab->stats : nullptr;
+    {
+        const char* ev = getenv("KGB200_SORT_STAGGER_NS");  // tuning override (0 disables)
+        a.stagger_ns = ev ? (u32)atoi(ev) : 30u;
     }
-    HistArgs h{};
-    h.npass = p.npass;
-    for (int i = 0; i < p.npass; i++) {
-        h.shift[i] = p.shift[i] - p.pb;
-        h.bits[i] = p.bits[i];
-    }
-    h.lo = p.lo;
-    h.kmask = p.kmask;
-    h.enc_base = p.enc_base;
-    h.dtype = dtype;
-    long long hb = (long long)((n + 1023) / 1024);
-    if (hb > (long long)sms * 8) hb = (long long)sms * 8;
-    if (key_width(dtype) == 8)
-        hist_kernel<8><<<(unsigned)hb, 256, 0, st>>>(keys, (u32)n, h, w.hist);
-    else
-        hist_kernel<4><<<(unsigned)hb, 256, 0, st>>>(keys, (u32)n, h, w.hist);
-    base_kernel<<<p.npass, MAXBINS, 0, st>>>(w.hist);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    const size_t tiles = (size_t)((n + (u64)(CT * KPT) - 1) / (u64)(CT * KPT));
-    {   // look-back words of all passes: one memset
-        size_t words = 0;
-        for (int i = 0; i < p.npass; i++) words += (tiles + LB_PAD) << p.bits[i];
-        e = cudaMemsetAsync(w.states, 0, words * 4, st);
-        if (e != cudaSuccess) return e;
-    }
-    if (lab_events) cudaEventRecord(lab_events[0], st);
     u64* bufs[2] = {buf0, buf1};
     u32* states = w.states;
-    {
-        static int stagger_env = -1;  // KGB200_SORT_STAGGER_NS: tuning override (0 disables)
-        if (stagger_env == -1) {
-            const char* ev = getenv("KGB200_SORT_STAGGER_NS");
-            stagger_env = ev ? atoi(ev) : -2;
-        }
-        a.stagger_ns = stagger_env >= 0 ? (u32)stagger_env : 30u;
-    }
     for (int i = 0; i < p.npass; i++) {
         int role = 0;
         if (i == 0) role |= ROLE_FIRST;
-        if (i == p.npass - 1 && !final_packed) role |= ROLE_LAST;
+        if (i == p.npass - 1 && !p.prefix) role |= ROLE_LAST;
         a.src = bufs[(i + 1) & 1];
         a.dst = bufs[i & 1];
-        a.digit_base = w.hist + (size_t)i * MAXBINS;
+        a.hist = w.hist + (size_t)i * MAXBINS;
         a.ticket = w.tickets + i;
         a.shift = p.shift[i];
         a.states = states + ((size_t)LB_PAD << p.bits[i]);
         states += (tiles + LB_PAD) << p.bits[i];
-        e = Launcher<CT, KPT, LBT, OCC>::go(p.bits[i], role, key_width(dtype), a, sms, st);
-        if (e != cudaSuccess) return e;
-        if (lab_events) cudaEventRecord(lab_events[i + 1], st);
-        if (a.stats) a.stats += 4;
+        if (!full && i + 1 < p.npass) {
+            a.next_hist = w.hist + (size_t)(i + 1) * MAXBINS;
+            a.next_shift = p.shift[i + 1];
+            a.next_mask = (1u << p.bits[i + 1]) - 1u;
+        } else {
+            a.next_hist = nullptr;
+            a.next_mask = 0;
+        }
+        KGB_PK_TRY((Launcher<CT, KPT, LBT, OCC>::go(p.bits[i], role, kw, a, sms, st)));
+        if (lab) {
+            cudaEventRecord(lab->ev[3 + i], st);
+            if (a.stats) a.stats += 4;
+        }
     }
-    if (final_packed) *final_packed = bufs[(p.npass - 1) & 1];
+    if (p.prefix) {
+        FixArgs f{};
+        f.sorted = bufs[(p.npass - 1) & 1];
+        f.keys = keys;
+        f.idx_out = idx_out;
+        f.keys_sorted_out = keys_sorted_out;
+        f.enc_sorted_out = enc_sorted_out;
+        f.flags = w.ctl + CTL_FIXOVER;
+        f.invalid = w.ctl + CTL_INVALID;
+        f.n = (u32)n;
+        f.pb = p.pb;
+        f.dtype = dtype;
+        f.descending = descending;
+        if (kw == 8) fixup_kernel<8><<<sms * 8, 256, 0, st>>>(f);
+        else fixup_kernel<4><<<sms * 8, 256, 0, st>>>(f);
+        KGB_PK_TRY(cudaGetLastError());
+    }
     return cudaSuccess;
+}
+
+// The whole packed sort.  Returns 1 when idx_out (and the optional outputs) are complete, 0 when the caller must run
+// the general pass (keys too wide for this n, or a prefix tie too long for the fix-up), a negative cudaError otherwise.
+// Synchronises `st` twice: after the 64 K-key sample (to guess the key field) and at the end (was the guess right?).
+template <int CT, int KPT, int LBT, int OCC>
+inline int packed_sort_run(const void* keys, int dtype, u64 n, int descending, i64* idx_out, void* keys_sorted_out,
+                           u64* enc_sorted_out, const Ws& w, u64* buf0, u64* buf1, int sms, cudaStream_t st,
+                           GroupOut* grp = nullptr, LabInfo* lab = nullptr) {
+#define KGB_PK_RUN(expr)                        \
+    do {                                        \
+        cudaError_t e_ = (expr);                \
+        if (e_ != cudaSuccess) return -(int)e_; \
+    } while (0)
+    const int kw = key_width(dtype);
+    if (lab) cudaEventRecord(lab->ev[0], st);
+    KGB_PK_RUN(cudaMemsetAsync(w.ctl, 0, CTL_WORDS * 8, st));
+    {
+        const unsigned sb = n >= SAMPLE_KEYS ? 16u : 1u;
+        if (kw == 8) sample_kernel<8><<<sb, 1024, 0, st>>>(keys, (u32)n, dtype, w.ctl);
+        else sample_kernel<4><<<sb, 1024, 0, st>>>(keys, (u32)n, dtype, w.ctl);
+        KGB_PK_RUN(cudaGetLastError());
+    }
+    u64 hs[3];
+    KGB_PK_RUN(cudaMemcpyAsync(hs, w.ctl + CTL_SAMPLE, sizeof hs, cudaMemcpyDeviceToHost, st));
+    KGB_PK_RUN(cudaStreamSynchronize(st));
+    if (lab) cudaEventRecord(lab->ev[1], st);
+    Plan p = guess_plan(hs[CTL_DIFF], ~hs[CTL_NMIN], hs[CTL_MAX], n);
+    if (grp) grp->done = 0;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        if (lab) {
+            lab->plan = p;
+            lab->attempts = attempt + 1;
+        }
+        if (p.npass < 0) return 0;
+        if (p.npass == 0) {  // (second attempt only: the exact statistics say every key is equal)
+            PassArgs a{};
+            a.idx_out = idx_out;
+            a.keys_sorted_out = keys_sorted_out;
+            a.enc_sorted_out = enc_sorted_out;
+            a.n = (u32)n;
+            a.enc_base = p.enc_base;
+            a.dtype = dtype;
+            a.descending = descending;
+            long long ib = (long long)((n + 255) / 256);
+            if (ib > (long long)sms * 8) ib = (long long)sms * 8;
+            identity_kernel<<<(unsigned)ib, 256, 0, st>>>(a);
+            KGB_PK_RUN(cudaGetLastError());
+            if (grp) grp->done = 0;
+            return 1;
+        }
+        KGB_PK_RUN((packed_attempt<CT, KPT, LBT, OCC>(keys, dtype, n, p, descending, idx_out, keys_sorted_out, enc_sorted_out, w,
+                                                     buf0, buf1, sms, st, grp, lab)));
+        if (lab) cudaEventRecord(lab->ev[3 + p.npass], st);
+        u64 hc[5];
+        KGB_PK_RUN(cudaMemcpyAsync(hc, w.ctl, sizeof hc, cudaMemcpyDeviceToHost, st));
+        KGB_PK_RUN(cudaStreamSynchronize(st));
+        if (!hc[CTL_INVALID]) return hc[CTL_FIXOVER] ? 0 : 1;
+        // the sample misled (an outlier, a rare low bit): exact statistics from one more read of the keys, then once more
+        KGB_PK_RUN(cudaMemsetAsync(w.ctl, 0, CTL_SAMPLE * 8, st));
+        long long blocks = (long long)((n + 2047) / 2048);
+        if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
+        if (kw == 8) analyze_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(keys, (u32)n, dtype, w.ctl);
+        else analyze_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(keys, (u32)n, dtype, w.ctl);
+        KGB_PK_RUN(cudaGetLastError());
+        KGB_PK_RUN(cudaMemcpyAsync(hc, w.ctl, sizeof hc, cudaMemcpyDeviceToHost, st));
+        KGB_PK_RUN(cudaStreamSynchronize(st));
+        p = make_plan(hc[CTL_DIFF], ~hc[CTL_NMIN], hc[CTL_MAX], n);
+    }
+    return -(int)cudaErrorUnknown;  // unreachable: a plan made from the exact statistics cannot be invalid
+#undef KGB_PK_RUN
 }
 
 }  // namespace pk

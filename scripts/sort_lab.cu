@@ -87,61 +87,39 @@ __global__ void gen_keys(i64* k, u64 n, int ds, int hb) {
 }
 
 struct Times {
-    float total, analyze, hist, passes, pass[MAXP], fix;
+    float total, sample, hist, pass[MAXP], fix;
 };
 
 static u64* g_stats = nullptr;  // device, MAXP * 4 words
 static int run_sort(const i64* d_keys, u64 n, i64* d_idx, void* ws, u64* buf0, u64* buf1, int sms, Times* tm, Plan* plan_out,
-                    bool per_kernel) {
+                    int* attempts, GroupOut* grp) {
     cudaStream_t st = 0;
     Ws w = carve_ws<T>(ws, n);
-    cudaEvent_t ev[16];
-    for (auto& e : ev) CK(cudaEventCreate(&e));
-    int ne = 0;
-    CK(cudaEventRecord(ev[ne++], st));
-    CK(packed_analyze<T>(d_keys, KGB_I64, n, w, sms, st));
-    u64 h[3];
-    CK(cudaMemcpyAsync(h, w.ctl, 24, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    CK(cudaEventRecord(ev[ne++], st));
-    Plan p = make_plan(h[0], ~h[1], h[2], n);
+    LabInfo lab{};
+    for (auto& e : lab.ev) CK(cudaEventCreate(&e));
+    lab.stats = KGB_PK_STATS ? g_stats : nullptr;
+    const int rc = packed_sort_run<CT, KPT, LBT, OCC>(d_keys, KGB_I64, n, 0, d_idx, nullptr, nullptr, w, buf0, buf1, sms, st, grp, &lab);
+    if (rc < 0) {
+        printf("packed_sort_run: %s\n", cudaGetErrorString((cudaError_t)(-rc)));
+        exit(2);
+    }
+    cudaEvent_t end;
+    CK(cudaEventCreate(&end));
+    CK(cudaEventRecord(end, st));
+    CK(cudaEventSynchronize(end));
+    const Plan& p = lab.plan;
     *plan_out = p;
-    u64* fin = nullptr;
-    (void)per_kernel;
-    cudaEvent_t pe[MAXP + 1];
-    for (auto& e : pe) CK(cudaEventCreate(&e));
-    CK((packed_passes<CT, KPT, LBT, OCC>(d_keys, KGB_I64, n, p, 0, d_idx, nullptr, nullptr, w, buf0, buf1, p.prefix ? &fin : nullptr, sms, st, pe, KGB_PK_STATS ? g_stats : nullptr)));
-    CK(cudaEventRecord(ev[ne++], st));
-    int over = 0;
-    if (p.prefix) {
-        FixArgs f{};
-        f.sorted = fin;
-        f.keys = d_keys;
-        f.idx_out = d_idx;
-        f.flags = w.ctl + 3;
-        f.n = (u32)n;
-        f.pb = p.pb;
-        f.dtype = KGB_I64;
-        fixup_kernel<8><<<sms * 8, 256, 0, st>>>(f);
-        CK(cudaGetLastError());
-        u64 fl = 0;
-        CK(cudaMemcpyAsync(&fl, w.ctl + 3, 8, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        over = (int)fl;
+    *attempts = lab.attempts;
+    CK(cudaEventElapsedTime(&tm->total, lab.ev[0], end));
+    if (lab.attempts == 1 && p.npass > 0) {
+        CK(cudaEventElapsedTime(&tm->sample, lab.ev[0], lab.ev[1]));
+        CK(cudaEventElapsedTime(&tm->hist, lab.ev[1], lab.ev[2]));
+        for (int i = 0; i < p.npass; i++) CK(cudaEventElapsedTime(&tm->pass[i], lab.ev[2 + i], lab.ev[3 + i]));
+        CK(cudaEventElapsedTime(&tm->fix, lab.ev[2 + p.npass], lab.ev[3 + p.npass]));
     }
-    CK(cudaEventRecord(ev[ne++], st));
-    CK(cudaEventSynchronize(ev[ne - 1]));
-    CK(cudaEventElapsedTime(&tm->total, ev[0], ev[ne - 1]));
-    CK(cudaEventElapsedTime(&tm->analyze, ev[0], ev[1]));
-    CK(cudaEventElapsedTime(&tm->passes, ev[1], ev[2]));
-    if (p.npass > 0) {
-        CK(cudaEventElapsedTime(&tm->hist, ev[1], pe[0]));
-        for (int i = 0; i < p.npass; i++) CK(cudaEventElapsedTime(&tm->pass[i], pe[i], pe[i + 1]));
-    }
-    for (auto& e : pe) CK(cudaEventDestroy(e));
-    CK(cudaEventElapsedTime(&tm->fix, ev[2], ev[3]));
-    for (auto& e : ev) CK(cudaEventDestroy(e));
-    return over;
+    for (auto& e : lab.ev) CK(cudaEventDestroy(e));
+    CK(cudaEventDestroy(end));
+    return rc == 1 ? 0 : 1;
 }
 
 int main(int argc, char** argv) {
@@ -201,11 +179,15 @@ int main(int argc, char** argv) {
         Times best{};
         best.total = 1e9f;
         Plan p{};
-        int over = 0;
+        int over = 0, attempts = 0;
+        i64 *d_starts, *d_ng;
+        CK(cudaMalloc(&d_starts, (n + 1) * 8));
+        CK(cudaMalloc(&d_ng, 8));
+        GroupOut grp{d_starts, d_ng, 0};
         for (int r = 0; r < reps + 1; r++) {
             Times tm{};
             CK(cudaMemset(g_stats, 0, MAXP * 4 * 8));
-            over = run_sort(d_keys, n, d_idx, ws, buf0, buf1, sms, &tm, &p, false);
+            over = run_sort(d_keys, n, d_idx, ws, buf0, buf1, sms, &tm, &p, &attempts, ds == 1 ? &grp : nullptr);
             if (r > 0 && tm.total < best.total) best = tm;
         }
         unsigned long long bad[2] = {0, ~0ull};
@@ -214,11 +196,24 @@ int main(int argc, char** argv) {
         CK(cudaMemcpy(bad, d_bad, 16, cudaMemcpyDeviceToHost));
         printf("%-7s npass=%d bits=[", names[ds], p.npass);
         for (int i = 0; i < p.npass; i++) printf("%d%s", p.bits[i], i + 1 < p.npass ? "," : "");
-        printf("] lo=%d live=%d pb=%d prefix=%d | total %.3f ms (analyze+sync %.3f, hist %.3f, passes", p.lo, p.live, p.pb, p.prefix,
-               best.total, best.analyze, best.hist);
+        printf("] lo=%d live=%d pb=%d prefix=%d attempts=%d | total %.3f ms (sample+sync %.3f, hist %.3f, passes", p.lo, p.live, p.pb,
+               p.prefix, attempts, best.total, best.sample, best.hist);
         for (int i = 0; i < p.npass; i++) printf(" %.3f", best.pass[i]);
-        printf(", fixup %.3f) cub %.3f ms | mismatches %llu first %lld over=%d\n", best.fix, cub_ms, bad[0],
+        printf(", fixup+sync %.3f) cub %.3f ms | mismatches %llu first %lld fallback=%d", best.fix, cub_ms, bad[0],
                bad[0] ? (long long)bad[1] : -1ll, over);
+        if (ds == 1) {
+            i64 ng = -1, first3[3] = {-1, -1, -1}, lastv = -1;
+            CK(cudaMemcpy(&ng, d_ng, 8, cudaMemcpyDeviceToHost));
+            if (grp.done && ng > 2) {
+                CK(cudaMemcpy(first3, d_starts, 24, cudaMemcpyDeviceToHost));
+                CK(cudaMemcpy(&lastv, d_starts + ng, 8, cudaMemcpyDeviceToHost));
+            }
+            printf(" | group done=%d G=%lld starts[0..2]=%lld,%lld,%lld starts[G]=%lld", grp.done, (long long)ng, (long long)first3[0],
+                   (long long)first3[1], (long long)first3[2], (long long)lastv);
+        }
+        printf("\n");
+        CK(cudaFree(d_starts));
+        CK(cudaFree(d_ng));
 #if KGB_PK_STATS
         {
             u64 hs[MAXP * 4];
