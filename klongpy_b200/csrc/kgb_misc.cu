@@ -1,5 +1,7 @@
 // Support verbs: iota (!n), gather (a@b), expand (&a), reverse (|a), array_equal.  All HBM-bound streaming
 // kernels: coalesced accesses, grid sized to the data with a cap of a few waves over the 148 SMs.
+#include <cstdlib>
+
 #include "kgb_device.cuh"
 #include "kgb_internal.h"
 
@@ -109,40 +111,65 @@ __global__ void __launch_bounds__(256) array_equal_kernel(const T* __restrict__ 
 // gather of single elements (`x@<x`, the common case): four independent index loads, then four independent
 // random loads in flight per thread — a random 8-byte read costs a whole 32-byte sector, so the only lever is
 // memory-level parallelism
-template <typename W>
-__global__ void __launch_bounds__(256) gather1_kernel(const W* __restrict__ a, i64 n_a, const i64* __restrict__ idx,
+template <typename W, int U, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) gather1_kernel(const W* __restrict__ a, i64 n_a, const i64* __restrict__ idx,
                                                        i64 n_idx, W* __restrict__ out, int* err) {
-    constexpr int U = 4;
-    const i64 stride = (i64)gridDim.x * blockDim.x;
-    for (i64 g0 = (i64)blockIdx.x * blockDim.x + threadIdx.x; g0 < n_idx; g0 += stride * U) {
+    // 32-bit arithmetic inside a CTA's contiguous chunk of U*256 indices: thread t owns chunk slots t, t+BLOCK, ... so the
+    // index loads and the result stores of a warp are coalesced and U independent random loads are in flight per thread
+    const u64 n_chunks = ((u64)n_idx + (U * BLOCK) - 1) / (U * BLOCK);
+    bool bad = false;
+    for (u64 c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+        const i64 base = (i64)(c * (U * BLOCK)) + threadIdx.x;
         i64 j[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            const i64 g = g0 + u * stride;
+            const i64 g = base + u * BLOCK;
             j[u] = g < n_idx ? __ldcs(&idx[g]) : 0;
             if (j[u] < 0) j[u] += n_a;
         }
         W v[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            const bool ok = j[u] >= 0 && j[u] < n_a;
+            const bool ok = (u64)j[u] < (u64)n_a;
             v[u] = ok ? __ldg(&a[j[u]]) : W(0);
-            if (!ok && g0 + u * stride < n_idx) *err = 1;
+            bad = bad || (!ok && base + u * BLOCK < n_idx);
         }
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            const i64 g = g0 + u * stride;
+            const i64 g = base + u * BLOCK;
             if (g < n_idx) __stcs(&out[g], v[u]);
         }
     }
+    if (bad) *err = 1;
 }
 
 template <typename W>
 static int launch_gather(const void* a, i64 n_a, const i64* idx, i64 n_idx, i64 units, void* out, int* err,
                          cudaStream_t st) {
-    if (units == 1)
-        gather1_kernel<W><<<grid_for((n_idx + 3) / 4, 256, 8), 256, 0, st>>>((const W*)a, n_a, idx, n_idx, (W*)out, err);
-    else
+    if (units == 1) {
+        // One small CTA per chunk of 4 x 256 indices, all chunks launched (no persistent loop): measured at 1e8 random
+        // 8-byte reads (profiles/r02e_gather_probe.log) the many-small-CTA shape beats every persistent geometry — the block
+        // scheduler keeps the SMs' load queues evenly full (2.16 ms = torch's index kernel = the DRAM random-sector rate).  KGB200_GATHER_U / _BLOCK / _CTAS are tuning overrides.
+        int U = 4, block = 256, per_sm = 0;
+        if (const char* e = getenv("KGB200_GATHER_U")) U = atoi(e);
+        if (const char* e = getenv("KGB200_GATHER_BLOCK")) block = atoi(e);
+        if (const char* e = getenv("KGB200_GATHER_CTAS")) per_sm = atoi(e);
+        const long long chunks = (n_idx + (long long)U * block - 1) / ((long long)U * block);
+        long long grid = per_sm > 0 ? (long long)sm_count() * per_sm : chunks;
+        if (grid > chunks) grid = chunks;
+        if (grid < 1) grid = 1;
+#define KGB_GATHER1(UU, BB) gather1_kernel<W, UU, BB><<<(unsigned)grid, BB, 0, st>>>((const W*)a, n_a, idx, n_idx, (W*)out, err)
+        if (block == 256) {
+            if (U == 8) KGB_GATHER1(8, 256);
+            else if (U == 16) KGB_GATHER1(16, 256);
+            else KGB_GATHER1(4, 256);
+        } else {
+            if (U == 8) KGB_GATHER1(8, 128);
+            else if (U == 2) KGB_GATHER1(2, 128);
+            else KGB_GATHER1(4, 128);
+        }
+#undef KGB_GATHER1
+    } else
         gather_kernel<W><<<grid_for(n_idx * units, 256, 2), 256, 0, st>>>((const W*)a, n_a, idx, n_idx, units, (W*)out, err);
     KGB_CUDA_CHECK(cudaGetLastError());
     return KGB_OK;
