@@ -115,15 +115,19 @@ class DeviceArray:
         return DeviceArray(self._t.T)
 
     def __len__(self):
-        if self._t.dim() == 0:
+        shape = self.shape   # metadata only: never launches a deferred expression or gathers a sharded vector
+        if len(shape) == 0:
             raise TypeError("len() of unsized object")
-        return self._t.shape[0]
+        return shape[0]
 
     def __repr__(self):
         return f"DeviceArray({self.to_numpy()!r}, device='{self._t.device}')"
 
     # ------------------------------------------------------------------ host transfer (explicit syncs)
     def to_numpy(self):
+        if self._tensor is None and type(self._node).__name__ == "ShardNode":
+            from . import sharded
+            return sharded.to_numpy(self)   # block by block, no gather on a device
         return self._t.detach().cpu().numpy()
 
     def __array__(self, dtype=None, copy=None):

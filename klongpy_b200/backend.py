@@ -13,7 +13,7 @@ baseline/_ref that travels to the GPU box); the parity tests drive it with IR tu
 import numpy as np
 import torch
 
-from . import _lib, lowering, ops
+from . import _lib, lowering, ops, sharded
 from .array import DeviceArray
 from .npshim import B200Numpy
 
@@ -53,6 +53,16 @@ class B200BackendProvider(_Base):
     """Array backend whose arrays live in B200 HBM and whose primitives are libkgb200 kernels."""
 
     def __init__(self, device=None):
+        # "cuda:*" (every visible GPU) or "cuda:0,1,2,3": ONE interpreter drives several devices — long 1-d vectors are
+        # block-sharded over them by kg_asarray (klongpy_b200/sharded.py); the first device holds everything else
+        devices = None
+        if isinstance(device, str) and device.startswith("cuda:") and ("*" in device or "," in device):
+            spec = device.split(":", 1)[1]
+            idx = range(torch.cuda.device_count()) if spec.strip() == "*" else [int(x) for x in spec.split(",") if x.strip() != ""]
+            devices = [torch.device("cuda", int(i)) for i in idx]
+            if not devices:
+                raise ValueError(f"Backend 'b200': no CUDA device matches '{device}'")
+            device = devices[0]
         if device is None:
             device = ops.default_device()
         device = torch.device(device)
@@ -61,6 +71,10 @@ class B200BackendProvider(_Base):
         if device.type != "cuda" and _lib._host_double is None:
             raise ValueError(f"Backend 'b200' needs a CUDA device, got '{device}' (there is no CPU fallback)")
         self._device = device
+        self._devices = devices if devices and len(devices) > 1 else None
+        if self._devices:
+            for d in reversed(self._devices):
+                _lib.bind_device(d.index)  # every device must be an sm_100 GPU the library can bind (ends on the first)
         if device.type == "cuda":
             _lib.bind_device(device.index)  # fails loudly if the .so is missing or the GPU is not sm_100
         ops.set_default_device(device)
@@ -82,6 +96,13 @@ class B200BackendProvider(_Base):
 
     def list_devices(self):
         return [f"cuda:{i}" for i in range(torch.cuda.device_count())]
+
+    def _maybe_shard(self, x):
+        """Long 1-d numeric vectors live block-sharded over the provider's devices (only with device="cuda:*" / a list)."""
+        if self._devices and isinstance(x, DeviceArray) and x.ndim == 1 and x.size >= sharded.SHARD_MIN and \
+                x.dtype.kind in "if" and not sharded.is_sharded(x):
+            return sharded.shard(x, self._devices)
+        return x
 
     def supports_object_dtype(self):
         return False
@@ -157,6 +178,8 @@ class B200BackendProvider(_Base):
             return self.str_to_char_array(a)
         if isinstance(a, np.ndarray):
             if a.dtype.kind in "ifb":
+                if self._devices and a.ndim == 1 and a.size >= sharded.SHARD_MIN and a.dtype.kind in "if":
+                    return sharded.shard(a, self._devices)   # host blocks go straight to their devices
                 return ops.asarray(a, device=self._device)
             if a.dtype != object:
                 return a

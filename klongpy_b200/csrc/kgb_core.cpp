@@ -8,6 +8,7 @@ namespace kgb {
 static thread_local std::string t_error;
 static thread_local int t_device = -1;
 static int g_sm_count[64];
+static bool g_ready[64];
 
 void set_error(const char* fmt, ...) {
     char buf[8192];
@@ -26,6 +27,13 @@ extern "C" int kgb_abi_version(void) { return KGB_ABI_VERSION; }
 extern "C" const char* kgb_last_error(void) { return kgb::t_error.c_str(); }
 
 extern "C" int kgb_init(int device) {
+    // re-binding a thread to a device that was already initialised (one interpreter driving several GPUs switches per
+    // launch, klongpy_b200/sharded.py): cudaSetDevice only
+    if (device >= 0 && device < 64 && kgb::g_sm_count[device] > 0 && kgb::g_ready[device]) {
+        KGB_CUDA_CHECK(cudaSetDevice(device));
+        kgb::t_device = device;
+        return KGB_OK;
+    }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {
@@ -42,6 +50,7 @@ extern "C" int kgb_init(int device) {
         return KGB_ENOGPU;
     }
     kgb::g_sm_count[device] = prop.multiProcessorCount;
+    kgb::g_ready[device] = true;
     kgb::t_device = device;
     return KGB_OK;
 }

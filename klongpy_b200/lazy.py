@@ -177,4 +177,7 @@ def materialize(node):
     from . import ops
     if isinstance(node, GradeNode):
         return ops.argsort(node.source, descending=node.descending)._t
+    from . import sharded
+    if isinstance(node, sharded.ShardNode):
+        return sharded.gather(node)   # no sharded kernel for this consumer: all blocks onto the first device
     return ops.run(node.code, node.args, _no_defer=True)._t

@@ -176,6 +176,8 @@ def _classify_meta(x):
     raise TypeError(f"unsupported operand type {type(x).__name__}")
 
 
+from . import sharded as _sharded  # noqa: E402 - imports only array.py; ops is imported lazily inside its functions
+
 _ARGV = [ctypes.c_void_p * max(k, 1) for k in range(17)]  # argument-pointer array types, by argument count
 _lazy = None  # klongpy_b200.lazy, imported on first use (it imports this module)
 
@@ -186,6 +188,11 @@ def run(code, args, mode=_lib.MODE_MAP, red=0, code2=None, red2=0, out_shape=Non
     if _lazy is None:
         from . import lazy as _lazy_mod
         _lazy = _lazy_mod
+    if _sharded.ACTIVE and any(_sharded.is_sharded(a) for a in args):
+        # a vector block-sharded over several devices of this process (klongpy_b200.sharded): same program per shard
+        r = _sharded.run(code, args, mode, red, code2, red2)
+        if r is not NotImplemented:
+            return r
     if _lazy.ENABLED and not _no_defer:
         # deferred operands are inlined into this program (elementwise chains, reduce / scan prologues fuse);
         # a MAP result is itself deferred until something needs the data
@@ -329,16 +336,20 @@ def reduce2(code, red, code2, red2, args):
     n = None
     for a in args:
         if isinstance(a, DeviceArray):
-            device = a._t.device
-            if a._t.dim() > 0:
-                m = a._t.numel()
-                if a._t.dim() != 1 or (n is not None and m != n):
+            device = a.device
+            if a.ndim > 0:
+                m = a.size
+                if a.ndim != 1 or (n is not None and m != n):
                     raise ValueError("reduce2: operands must be 1-d arrays of one length")
                 n = m
     if device is None or n is None or n == 0:
         raise ValueError("reduce2 needs a non-empty device array operand")
     red = RED[red] if not isinstance(red, int) else red
     red2 = RED[red2] if not isinstance(red2, int) else red2
+    if _sharded.ACTIVE and any(_sharded.is_sharded(a) for a in args):
+        r = _sharded.reduce2(code, red, code2, red2, args)
+        if r is not NotImplemented:
+            return r
     if torch.is_grad_enabled() and any(isinstance(a, DeviceArray) and a._t.requires_grad for a in args):
         from . import autograd  # one two-output node on the tape (raises NotDifferentiable for folds other than +/)
         return autograd.run_differentiable2(code, red, code2, red2, args, device)
@@ -795,6 +806,10 @@ def array_equal(a, b):
 def groupagg(keys, vals, n_groups, tables=None, accumulate=None):
     """1brc-style grouped (min, max, sum, count) (examples/1brc/worker.kg:3-5).  `tables`: four preallocated result
     arrays; they are merged into (the `merge` step) unless accumulate=False."""
+    if _sharded.ACTIVE and (_sharded.is_sharded(keys) or _sharded.is_sharded(vals)) and tables is None:
+        r = _sharded.groupagg(keys, vals, n_groups)
+        if r is not NotImplemented:
+            return r
     keys, vals = contiguous(keys), contiguous(vals)
     dev = keys._t.device
     lib, stream = _lib_for(dev)
