@@ -231,11 +231,16 @@ def make_callable(ir):
             raise TypeError(f"compiled expression takes {n_params} arguments ({len(args)} given)")
         vals = list(args) + [None] * (plan.n_slots - n_params)
         any_dev = False
+        nd_shape = None
         for v in args:
             if isinstance(v, DeviceArray):
                 any_dev = True
                 if v.ndim > 1:
-                    raise NotImplementedError("compiled kernels take 1-d arrays; N-d goes through the eager verbs")
+                    # N-d operands (numpy_backend.py:163-173): elementwise trees keep the shape, `np.add.reduce` & co fold
+                    # axis 0, `np.cumsum` / `np.cumprod` scan the FLATTENED array (the reference's compiled semantics)
+                    if nd_shape is not None and v.shape != nd_shape:
+                        raise NotImplementedError("compiled kernels take N-d operands of one shape")
+                    nd_shape = v.shape
             elif type(v) in (int, float) or isinstance(v, (np.integer, np.floating)):
                 pass
             else:
@@ -245,7 +250,7 @@ def make_callable(ir):
         for st in plan.stages:
             if vals[st.out_slot] is not None:
                 continue  # second half of a pair, already produced by the two-output kernel
-            if st.pair is not None:
+            if st.pair is not None and nd_shape is None:
                 other, code_b, slots = st.pair
                 pargs = [vals[s] for s in slots]
                 lens = {a.size for a in pargs if _is_arraylike(a)}
@@ -256,6 +261,18 @@ def make_callable(ir):
                     except (_lib.KgbError, autodiff.NotDifferentiable):
                         pass  # a narrow accumulator, or a fold without a gradient rule: two separate reductions
             sargs = [vals[s] for s in st.slots]
+            if nd_shape is not None and any(isinstance(a, DeviceArray) and a.ndim > 1 for a in sargs):
+                if any(isinstance(a, DeviceArray) and a.ndim == 1 for a in sargs):
+                    raise NotImplementedError("compiled kernels do not broadcast 1-d against N-d operands")
+                if st.mode == _lib.MODE_REDUCE:
+                    vals[st.out_slot] = ops.reduce_axis0(st.code, sargs, st.red)
+                    continue
+                if st.mode == _lib.MODE_SCAN:
+                    if st.red not in (_lib.RED_ADD, _lib.RED_MUL):
+                        raise NotImplementedError("|\\ and &\\ on N-d operands: interpreter semantics (row by row)")
+                    sargs = [a.flatten() if isinstance(a, DeviceArray) and a.ndim > 1 else a for a in sargs]
+                elif st.mode == _lib.MODE_SCANRED:
+                    raise NotImplementedError("fused scan+reduce takes 1-d operands")
             has_array = any(_is_arraylike(a) for a in sargs)
             if st.mode != _lib.MODE_MAP and not has_array:
                 raise NotImplementedError("fold over a scalar: interpreter semantics apply")

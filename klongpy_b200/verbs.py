@@ -11,6 +11,7 @@ import os
 import warnings
 
 import numpy as np
+import torch as _torch
 
 from . import ops
 from .array import DeviceArray
@@ -115,6 +116,17 @@ def install(klong):
     def find(a, b):  # a?b  (dyads.py:307-342)
         if _is_dev(a) and (_is_num(b) or (_is_dev(b) and b.ndim == 0)):
             return ops.find_equal(a, b)
+        if _is_dev(a) and _is_dev(b) and b.ndim >= 1 and a.ndim >= 1:
+            # list b (dyads.py:340-341): positions i with kg_equal(a[i], b) — for two device arrays kg_equal is exact
+            # array equality (base.py:372-374).  The reference walks `a` in Python; here one compare + row fold + compaction.
+            if a.ndim != b.ndim + 1 or a.shape[1:] != b.shape or a.shape[0] == 0:
+                return DeviceArray(a._t.new_empty(0, dtype=_torch.int64))   # no element of `a` has b's shape: no match
+            rows = a.shape[0]
+            eq = ops.binary("eq_b", a.reshape(rows, -1), b.reshape(1, -1))  # [rows, cols] bool
+            if eq.shape[1] == 0:
+                return ops.iota(rows, dev)
+            flags = ops.reduce_axis0([ops.OP_ARG, 0], [DeviceArray(eq._t.T.contiguous())], ops.RED["&"])
+            return ops.nonzero(flags)
         return ref_d["?"](a, b)
 
     def at_index(a, b):  # a@b  (dyads.py:140-191)

@@ -272,3 +272,40 @@ def test_sort_by_grade_takes_sorted_keys_from_the_sort(interp, monkeypatch):
     assert np.array_equal(p.to_numpy(), np.argsort(keys, kind="stable")) and ops.grade_source(p) is None
     assert np.array_equal(b200("(<a)+1").to_numpy(), np.argsort(keys, kind="stable") + 1)
     assert np.array_equal(b200("a@<a+0").to_numpy(), np.sort(keys, kind="stable")) and calls["gather"] == 1  # another array: gather
+
+
+def test_compiled_expressions_take_nd_operands(interp):
+    """N-d operands through the COMPILED path with the reference's own semantics (numpy_backend.py:163-173): elementwise
+    trees keep the shape, `+/ */ |/ &/` fold axis 0 (np.<ufunc>.reduce), `+\\` / `*\\` scan the flattened array (np.cumsum)."""
+    b200, ref, mod = interp
+    rng = np.random.default_rng(12)
+    for shape in ((2, 3), (30, 7), (5, 4, 3)):
+        m = rng.integers(1, 9, shape).astype(np.float64)
+        w = rng.integers(1, 5, shape)
+        b200["m"], b200["w"] = b200._backend.kg_asarray(m), b200._backend.kg_asarray(w)
+        ref["m"], ref["w"] = m, w
+        for src in ("+/m", "*/w", "|/m", "&/m", "+/(m*2)+w", "+\\m", "*\\w", "+\\m*w", "(m*2)+w", "+/m=w", "(+/m)%+/w"):
+            got, want = b200(src), np.asarray(ref(src))
+            assert isinstance(got, mod.DeviceArray), src
+            g = got.to_numpy()
+            assert g.shape == want.shape and g.dtype == want.dtype and np.array_equal(g, want), (src, shape)
+        # the compiled callable itself (not the interpreter's eager fallback) takes them
+        fn, _ = b200._backend.compile_expr_ir(("reduce", "+", ("binop", "*", ("var", "_v0"), ("var", "_v1"))), ["m", "w"])
+        assert np.array_equal(fn(b200["m"], b200["w"]).to_numpy(), np.add.reduce(m * w))
+
+
+def test_find_with_a_list_needle(interp):
+    """`a?b` with a list b (dyads.py:340-341): positions of the elements of `a` that equal the whole list."""
+    b200, ref, mod = interp
+    for src in ("[[1 2] [3 4] [1 2] [5 6]]?[1 2]", "[[1 2] [3 4]]?[9 9]", "[1 2 3 1]?[1 2]", "[[1.5 2.0] [1.5 2.0] [0.0 1.0]]?[1.5 2.0]",
+                "[[1 2 3] [4 5 6]]?[4 5 6]", "[[[1 2] [3 4]] [[5 6] [7 8]] [[1 2] [3 4]]]?[[1 2] [3 4]]"):
+        got, want = b200(src), np.asarray(ref(src))
+        g = got.to_numpy() if isinstance(got, mod.DeviceArray) else np.asarray(got)
+        assert list(g) == list(want), src
+    rng = np.random.default_rng(2)
+    m = rng.integers(0, 3, (5000, 4))
+    b200["m"], ref["m"] = b200._backend.kg_asarray(m), m
+    b200["b"], ref["b"] = b200._backend.kg_asarray(m[17]), m[17]
+    got = b200("m?b")
+    assert isinstance(got, mod.DeviceArray)
+    assert np.array_equal(got.to_numpy(), np.flatnonzero((m == m[17]).all(axis=1)))
