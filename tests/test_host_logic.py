@@ -101,8 +101,10 @@ def test_compiled_callable_raises_on_unsupported(interp):
         fn(np.arange(3))
     with pytest.raises(Exception):
         fn(3)
+    # (N-d operands are compiled since round 2: test_compiled_expressions_take_nd_operands)
+    two = lowering.make_callable(("binop", "+", ("var", "_v0"), ("var", "_v1")))
     with pytest.raises(Exception):
-        fn(kb("[[1 2] [3 4]]"))
+        two(kb("[[1 2] [3 4]]"), kb("[[1 2 3] [4 5 6]]"))   # N-d operands of different shapes
 
 
 def test_host_numpy_symbols_are_not_compiled(interp):
