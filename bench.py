@@ -487,13 +487,14 @@ def primitive_table(be, ops, dist, time_kernel, dev, peak, world, rank):
     b = DeviceArray(torch.rand(n, dtype=torch.float64, device=dev, generator=g))
     # `torch_eager_ms`: the same primitive through the ATen calls the reference's torch backend issues
     # (torch_backend.py:413-459, 612-616, 1058-1082) on the same GPU in the same run — the prior-art GPU path.
-    out["a+b"] = prim_row(n, time_kernel(lambda: ops.binary("add", a, b), 5), 24, peak,
+    # (`.tensor` launches a deferred elementwise result: with lazy evaluation on, a discarded `a+b` would never run)
+    out["a+b"] = prim_row(n, time_kernel(lambda: ops.binary("add", a, b).tensor, 5), 24, peak,
                           torch_eager_ms=time_kernel(lambda: torch.add(a.tensor, b.tensor), 5))
     c = DeviceArray(torch.rand(n, dtype=torch.float64, device=dev, generator=g))
     fn, _ = be.compile_expr_ir(("binop", "%", ("binop", "*", ("var", "_v0"), ("binop", "+", ("literal", 2), ("binop", "*", ("var", "_v1"), ("literal", 3)))),
                                 ("binop", "-", ("binop", "+", ("var", "_v0"), ("literal", 1)), ("binop", "*", ("var", "_v1"), ("var", "_v2")))), ["a", "b", "c"])
     ta, tb, tc = a.tensor, b.tensor, c.tensor
-    out["(a*2+b*3)%(a+1)-(b*c)"] = prim_row(n, time_kernel(lambda: fn(a, b, c), 5), 32, peak,
+    out["(a*2+b*3)%(a+1)-(b*c)"] = prim_row(n, time_kernel(lambda: fn(a, b, c).tensor, 5), 32, peak,
                                             torch_eager_ms=time_kernel(lambda: (ta * (2 + (tb * 3))) / ((ta + 1) - (tb * tc)), 5))
     fn2, _ = be.compile_expr_ir(("reduce", "|", ("binop", "-", ("scan", "|", ("var", "_v0")), ("var", "_v0"))), ["a"])
     out["|/(|\\ts)-ts"] = prim_row(n, time_kernel(lambda: fn2(a), 5), 8, peak,

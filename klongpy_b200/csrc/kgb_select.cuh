@@ -118,6 +118,7 @@ static __global__ void __launch_bounds__(1024) select_offsets_kernel(unsigned lo
     if (tid == 0) {
         cnt[ntiles] = s_carry;
         *count_out = (i64)s_carry;
+        __threadfence_system();  // count_out may be mapped host memory that the caller polls while the emit kernel runs
     }
 }
 

@@ -195,12 +195,23 @@ def run(code, args, mode=_lib.MODE_MAP, red=0, code2=None, red2=0, out_shape=Non
             return r
     if _lazy.ENABLED and not _no_defer:
         # deferred operands are inlined into this program (elementwise chains, reduce / scan prologues fuse);
-        # a MAP result is itself deferred until something needs the data
-        code, args = _lazy.inline(code, args)
-        if mode == _lib.MODE_MAP and out_shape is None and not code2:
-            r = _lazy.defer(code, args)
-            if r is not None:
-                return r
+        # a MAP result is itself deferred until something needs the data.  Small vectors launch at once (lazy.MIN_SIZE):
+        # a cheap look at the operands keeps the deferral machinery off their path entirely.
+        has_lazy, n_el = False, 0
+        for a in args:
+            if isinstance(a, DeviceArray):
+                t = a._tensor
+                if t is None:
+                    has_lazy = True
+                    break
+                if t.dim() > 0:
+                    n_el = t.numel()
+        if has_lazy or n_el == 0 or n_el >= _lazy.MIN_SIZE:
+            code, args = _lazy.inline(code, args)
+            if mode == _lib.MODE_MAP and out_shape is None and not code2:
+                r = _lazy.defer(code, args)
+                if r is not None:
+                    return r
     # ---- one pass over the operands: shape agreement, autograd, and the launch description (kind, dtype, pointer)
     shape = None
     mixed = False
@@ -699,22 +710,31 @@ def _select(fn_name, a, needle=None):
     if not n:
         return DeviceArray(torch.empty(0, dtype=torch.int64, device=dev))
     pos = torch.empty(n, dtype=torch.int64, device=dev)
-    # the match count is the one value the host needs: the kernel writes it straight into pinned (device-visible) host
-    # memory, so the read-back is a stream synchronise and no copy
+    # the match count is the one value the host needs: the offsets kernel writes it straight into pinned (device-visible)
+    # host memory and the host POLLS that word — it does not wait for the emit kernel that follows on the stream (the
+    # positions are consumed in stream order anyway), and no D2H copy is involved
     cnt = _count_slot(dev)
-    if n:
-        wsb = ctypes.c_size_t()
-        _lib.check(lib.kgb_select_workspace_bytes(n, ctypes.byref(wsb)))
-        ws = _ws(wsb.value, dev)
-        if fn_name == "find":
-            _lib.check(lib.kgb_find_equal(a._t.data_ptr(), kdt, n, ctypes.addressof(needle), pos.data_ptr(),
-                                          cnt.data_ptr(), ws.data_ptr(), wsb.value, stream), "kgb_find_equal")
-        else:
-            _lib.check(lib.kgb_nonzero(a._t.data_ptr(), kdt, n, pos.data_ptr(), cnt.data_ptr(), ws.data_ptr(),
-                                       wsb.value, stream), "kgb_nonzero")
+    cnt_np = cnt.numpy()
+    cnt_np[0] = -1
+    wsb = ctypes.c_size_t()
+    _lib.check(lib.kgb_select_workspace_bytes(n, ctypes.byref(wsb)))
+    ws_ptr = _scratch(dev, stream, wsb.value)
+    if fn_name == "find":
+        _lib.check(lib.kgb_find_equal(a._t.data_ptr(), kdt, n, ctypes.addressof(needle), pos.data_ptr(),
+                                      cnt.data_ptr(), ws_ptr, wsb.value, stream), "kgb_find_equal")
+    else:
+        _lib.check(lib.kgb_nonzero(a._t.data_ptr(), kdt, n, pos.data_ptr(), cnt.data_ptr(), ws_ptr, wsb.value, stream),
+                   "kgb_nonzero")
     if dev.type == "cuda":
-        torch.cuda.current_stream(dev).synchronize()
-    c = int(cnt[0])
+        spins = 0
+        while cnt_np[0] < 0:
+            spins += 1
+            if spins > 2_000_000:  # (seconds) the kernel must have failed: let the synchronise raise the CUDA error
+                torch.cuda.current_stream(dev).synchronize()
+                break
+    c = int(cnt_np[0])
+    if c < 0:
+        raise _lib.KgbError("select: the match count never arrived")
     res = pos[:c]
     return DeviceArray(res.clone() if 2 * c < n else res)  # do not pin n words of storage under a short result
 
