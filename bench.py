@@ -584,6 +584,7 @@ def primitive_table(be, ops, dist, time_kernel, dev, peak, world, rank):
         # config 3 at its upper size: 1e9 int64 keys
         out["group_10k_1e9"] = prim_row(nb, time_kernel(lambda: ops.group(st_b), 2), 16, peak)
         out["find_1e9"] = prim_row(nb, time_kernel(lambda: ops.find_equal(st_b, 77), 3), 8, peak)
+        out["range_10k_1e9"] = prim_row(nb, time_kernel(lambda: ops.unique_first(st_b), 2), 8, peak)
         del st_b
         kp = DeviceArray(torch.randperm(nb, device=dev, generator=g))
         out["grade_up_perm_1e9"] = prim_row(nb, time_kernel(lambda: ops.argsort(kp), 2), 16, peak,

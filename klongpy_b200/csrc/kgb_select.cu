@@ -3,6 +3,7 @@
 
 #include "kgb_select.cuh"
 #include "kgb_sort.cuh"
+#include "kgb_sort_packed.cuh"
 
 namespace kgb {
 
@@ -437,6 +438,77 @@ __global__ void __launch_bounds__(256) uniq_place_kernel(const T* __restrict__ a
     }
 }
 
+// ------------------------------------------------------------------------------------------- range (?a), small key ranges
+// Integer keys that span at most 2^15 values (station ids: the usual argument of `?a`) need neither a hash nor a sort: the
+// first position of key k lives in entry (k - base) of a DIRECT-ADDRESS table in shared memory.  A row whose key already
+// has a smaller position costs one LDS and no atomic — every row but the first few of each key per CTA — so the pass
+// streams at the HBM rate.  The key range is GUESSED from the grade's 64 K-key sample (pk::sample_kernel / guess_plan)
+// and verified here: a key outside it raises a flag and the hash / sort paths run instead.
+constexpr int UNIQ_DIRECT_BITS = pk::FULL_MAX_BITS;   // 2^15 entries x 4 B = 128 KB of shared memory
+struct UniqDirectCtl {
+    unsigned long long count;    // distinct keys collected
+    unsigned long long invalid;  // a key fell outside the guessed range
+};
+template <int KW>
+__global__ void __launch_bounds__(1024, 1) uniq_direct_kernel(const void* __restrict__ a, u32 n, int dtype, u64 enc_base, int lo, u32 range,
+                                                              u32* __restrict__ gfirst, UniqDirectCtl* __restrict__ ctl) {
+    extern __shared__ u32 s_first[];
+    for (u32 q = threadIdx.x; q < range; q += 1024) s_first[q] = 0xffffffffu;
+    __syncthreads();
+    const u64 lowmask = lo ? ((1ull << lo) - 1ull) : 0ull;
+    bool bad = false;
+    constexpr int U = 8;
+    // a CTA walks its tiles in ascending position order, so after the first rows of a key the test `pos < first` fails
+    auto sweep = [&](auto enc) {  // (integer keys only: the dtype is tested once per kernel, not per key)
+        for (u64 base = (u64)blockIdx.x * (1024 * U); base < n; base += (u64)gridDim.x * (1024 * U)) {
+            u64 r[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const u64 i = base + u * 1024 + threadIdx.x;
+                r[u] = i < n ? pk::load_key<KW>(a, i) : 0ull;
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const u64 i = base + u * 1024 + threadIdx.x;
+                if (i < n) {
+                    const u64 rel = enc(r[u]) - enc_base;
+                    const u64 f = rel >> lo;
+                    if (f < range && (rel & lowmask) == 0) {
+                        if ((u32)i < s_first[f]) atomicMin(&s_first[f], (u32)i);
+                    } else {
+                        bad = true;
+                    }
+                }
+            }
+        }
+    };
+    if (dtype == KGB_I64)
+        sweep([](u64 r) { return r ^ 0x8000000000000000ull; });
+    else
+        sweep([](u64 r) { return (u64)((u32)r ^ 0x80000000u); });
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(&ctl->invalid, 1ull);
+    __syncthreads();
+    for (u32 q = threadIdx.x; q < range; q += 1024) {
+        const u32 p = s_first[q];
+        if (p != 0xffffffffu && p < gfirst[q]) atomicMin(&gfirst[q], p);
+    }
+}
+// the occupied entries -> first[] (any order: they are ranked by position afterwards) and their count
+__global__ void __launch_bounds__(256) uniq_direct_collect_kernel(const u32* __restrict__ gfirst, u32 range, UniqDirectCtl* __restrict__ ctl,
+                                                                   i64* __restrict__ first) {
+    const u32 q = blockIdx.x * 256 + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const u32 p = q < range ? gfirst[q] : 0xffffffffu;
+    const bool occ = p != 0xffffffffu;
+    const u32 m = __ballot_sync(0xffffffffu, occ);
+    if (m) {
+        unsigned long long b = 0;
+        if (lane == __ffs(m) - 1) b = atomicAdd(&ctl->count, (unsigned long long)__popc(m));
+        b = __shfl_sync(0xffffffffu, b, __ffs(m) - 1);
+        if (occ) first[b + __popc(m & ((1u << lane) - 1u))] = (i64)p;
+    }
+}
+
 }  // namespace kgb
 
 using namespace kgb;
@@ -533,10 +605,53 @@ extern "C" int kgb_unique_first(const void* a, int32_t dtype, int64_t n, void* o
     GroupWs g = carve_group(p + 4 * nb, n);
     int rc;
     i64 c = -1;
+    // 00. small key RANGES (integer keys spanning <= 2^15 values): direct-address first-position table in shared memory
+    static const bool direct_on = !(getenv("KGB200_UNIQUE_DIRECT") && atoi(getenv("KGB200_UNIQUE_DIRECT")) == 0);
+    if (direct_on && n >= (1ll << 18) && n < 0xffffffffll && (dtype == KGB_I64 || dtype == KGB_I32) &&
+        nb >= 256 + ((size_t)4 << UNIQ_DIRECT_BITS) + pk::CTL_WORDS * 8) {
+        const int kw = dtype == KGB_I64 ? 8 : 4;
+        u64* sctl = (u64*)idx1;                                   // the sample's statistics (pk::CTL_* layout)
+        UniqDirectCtl* dctl = (UniqDirectCtl*)(sctl + pk::CTL_WORDS);
+        u32* gfirst = (u32*)((char*)idx1 + 256 + pk::CTL_WORDS * 8);
+        KGB_CUDA_CHECK(cudaMemsetAsync(sctl, 0, 256 + pk::CTL_WORDS * 8, st));
+        if (kw == 8) pk::sample_kernel<8><<<16, 1024, 0, st>>>(a, (u32)n, dtype, sctl);
+        else pk::sample_kernel<4><<<16, 1024, 0, st>>>(a, (u32)n, dtype, sctl);
+        KGB_CUDA_CHECK(cudaGetLastError());
+        u64 hs[3];
+        KGB_CUDA_CHECK(cudaMemcpyAsync(hs, sctl + pk::CTL_SAMPLE, sizeof hs, cudaMemcpyDeviceToHost, st));
+        KGB_CUDA_CHECK(cudaStreamSynchronize(st));
+        const pk::Plan gp = pk::guess_plan(hs[pk::CTL_DIFF], ~hs[pk::CTL_NMIN], hs[pk::CTL_MAX], (u64)n);
+        if (gp.npass > 0 && !gp.prefix && gp.live <= UNIQ_DIRECT_BITS) {
+            const u32 range = 1u << gp.live;
+            KGB_CUDA_CHECK(cudaMemsetAsync(gfirst, 0xff, (size_t)range * 4, st));
+            static bool opted[64] = {};
+            const int dv = current_device();
+            if (dv >= 0 && dv < 64 && !opted[dv]) {
+                KGB_CUDA_CHECK(cudaFuncSetAttribute(uniq_direct_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << UNIQ_DIRECT_BITS));
+                KGB_CUDA_CHECK(cudaFuncSetAttribute(uniq_direct_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << UNIQ_DIRECT_BITS));
+                opted[dv] = true;
+            }
+            long long cb = (n + 8191) / 8192;
+            if (cb > sm_count()) cb = sm_count();
+            if (kw == 8)
+                uniq_direct_kernel<8><<<(unsigned)cb, 1024, (size_t)range * 4, st>>>(a, (u32)n, dtype, gp.enc_base, gp.lo, range, gfirst, dctl);
+            else
+                uniq_direct_kernel<4><<<(unsigned)cb, 1024, (size_t)range * 4, st>>>(a, (u32)n, dtype, gp.enc_base, gp.lo, range, gfirst, dctl);
+            uniq_direct_collect_kernel<<<(range + 255) / 256, 256, 0, st>>>(gfirst, range, dctl, first);
+            KGB_CUDA_CHECK(cudaGetLastError());
+            UniqDirectCtl hd;
+            KGB_CUDA_CHECK(cudaMemcpyAsync(&hd, dctl, sizeof hd, cudaMemcpyDeviceToHost, st));
+            KGB_CUDA_CHECK(cudaStreamSynchronize(st));
+            if (!hd.invalid) {
+                c = (i64)hd.count;
+                KGB_CUDA_CHECK(cudaMemcpyAsync(count_out, &dctl->count, 8, cudaMemcpyDeviceToDevice, st));
+            }
+        }
+    }
     // 0. low-cardinality fast path: first positions through an L2-resident hash table (no sort of the n rows)
     static const bool hash_on = !(getenv("KGB200_UNIQUE_HASH") && atoi(getenv("KGB200_UNIQUE_HASH")) == 0);
     const size_t tab_bytes = (size_t)UNIQ_SLOTS * sizeof(UniqSlot);
-    if (hash_on && nb >= tab_bytes && nb >= 256 + sizeof(UniqCtl)) {
+    if (c < 0 && hash_on && nb >= tab_bytes && nb >= 256 + sizeof(UniqCtl)) {
         UniqSlot* tab = (UniqSlot*)idx1;          // the table borrows the sort path's index buffer
         UniqCtl* ctl = (UniqCtl*)heads;
         KGB_CUDA_CHECK(cudaMemsetAsync(tab, 0xff, tab_bytes, st));

@@ -824,7 +824,7 @@ struct DeriveArgs {
 
 // From the full key-field histogram: every pass's digit counts, and — for `=a` — the group start offsets (exclusive
 // prefix sums of the non-empty bins) and their number.  One CTA; at most 2^15 bins.
-__global__ void __launch_bounds__(1024) derive_kernel(const DeriveArgs d) {
+static __global__ void __launch_bounds__(1024) derive_kernel(const DeriveArgs d) {
     __shared__ u32 sh[MAXP * MAXBINS];
     __shared__ u32 wtot[32], wcnt[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -879,7 +879,7 @@ __global__ void __launch_bounds__(1024) derive_kernel(const DeriveArgs d) {
 }
 
 // no live bit at all (or n == 1): the stable permutation is the identity
-__global__ void __launch_bounds__(256) identity_kernel(const PassArgs a) {
+static __global__ void __launch_bounds__(256) identity_kernel(const PassArgs a) {
     const u64 stride = (u64)gridDim.x * blockDim.x;
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
         const u64 op = a.descending ? (a.n - 1 - i) : i;

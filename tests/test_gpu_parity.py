@@ -846,3 +846,30 @@ def test_range_hash_path_collapses_nans_like_the_sort_path(be, K):
     want = O.range_unique(x)
     assert len(u) == len(want)
     assert np.array_equal(u[~np.isnan(u)], want[~np.isnan(want)]) and np.array_equal(np.signbit(u[~np.isnan(u)]), np.signbit(want[~np.isnan(want)]))
+
+
+@pytest.mark.parametrize("case", ["dense", "negative", "stride", "int32", "outlier", "edge_2p15", "too_wide"])
+def test_range_direct_address_path(be, K, case):
+    """`?a` on integer keys spanning <= 2^15 values: first positions from a direct-address table in shared memory, the key
+    range guessed from a sample and verified — an outlier the sample missed must fall back, never mis-answer."""
+    rng = np.random.default_rng(hash(case) % 1000)
+    n = 1_500_007
+    if case == "dense":
+        k = rng.integers(0, 10_000, n)
+    elif case == "negative":
+        k = rng.integers(-3000, 3000, n)
+    elif case == "stride":
+        k = rng.integers(0, 500, n) * 4096 + 17
+    elif case == "int32":
+        k = rng.integers(-100, 30_000, n).astype(np.int32)
+    elif case == "outlier":
+        k = rng.integers(0, 1000, n)
+        k[n // 3] = 10**15          # one key far outside what a 64 K sample sees
+        k[n // 2] = -5
+    elif case == "edge_2p15":
+        k = rng.integers(0, 2**15, n)
+    else:
+        k = rng.integers(0, 2**20, n)
+    got = host(K.unique_first(K.asarray(k)))
+    want = O.range_unique(k)
+    assert got.dtype == k.dtype and np.array_equal(got, want), case
