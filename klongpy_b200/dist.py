@@ -14,6 +14,9 @@ expressions need no exchange.  The primitives with a real exchange step:
     ONE all_gather + one fold kernel instead (sharded_groupagg).
 
   * find `a?b` : local compaction -> all_gather of (shard length, hit count) -> global positions (sharded_find).
+  * grade `<a >a` : sample sort — composite (key, position) splitters, one variable-size all_to_all of (key, position)
+    pairs, a local stable sort, one all_to_all of positions back to the block partition (sharded_argsort).
+  * range `?a` : the ranks' own answers concatenated in rank order, then `?` of that (sharded_range).
   * autograd : the loss `+/` is a sharded reduce whose tape holds only the local fused node (sharded_loss_sum);
     vector gradients stay sharded, scalar-parameter gradients are summed rank-ordered (combine_param_grads).
 
@@ -180,6 +183,145 @@ def sharded_groupagg(keys, vals, n_groups, exchange="auto"):
     else:
         raise ValueError(f"sharded_groupagg: unknown exchange {exchange!r}")
     return tuple(DeviceArray(t) for t in o)
+
+
+def _all_counts(counts_row):
+    """all_gather of one row of `world` int64 counts per rank -> [world, world] host matrix (row r = rank r's row)."""
+    w = world()
+    mat = torch.empty(w * w, dtype=torch.int64, device=counts_row.device)
+    td.all_gather_into_tensor(mat, counts_row.contiguous())
+    return mat.reshape(w, w).cpu().numpy()
+
+
+def _exchange(send, send_counts, recv_counts):
+    """Variable-size all_to_all of a 1-d tensor (segments in destination-rank order)."""
+    recv = torch.empty(int(sum(recv_counts)), dtype=send.dtype, device=send.device)
+    td.all_to_all_single(recv, send.contiguous(), [int(c) for c in recv_counts], [int(c) for c in send_counts])
+    return recv
+
+
+def sharded_argsort(a, descending=False, samples_per_rank=1024):
+    """Grade of a block-sharded vector: this rank's block of the GLOBAL stable permutation (global
+    positions; the blocks are partitioned like the input).  Sample sort:
+
+      1. every rank contributes `samples_per_rank` (key, global position) pairs; the w-1 splitters are quantiles of the
+         sorted samples — COMPOSITE (key, position) splitters, so heavy ties (10 k distinct keys) still balance and the
+         stable order is respected across ranks;
+      2. elements are bucketed by one fused compare program per splitter group, partitioned stably by bucket (a one-pass
+         packed radix sort of the bucket ids) and exchanged with ONE variable-size all_to_all of keys and one of positions
+         (16 B per element over NVLink);
+      3. the received segments arrive in source-rank order = ascending position among equal keys, so ONE local stable sort by
+         key finishes the job; a second all_to_all of positions only (8 B per element) restores the block partition.
+
+    `descending` follows the language contract: the reversed stable ascending permutation (writer.py:97-108)."""
+    w, r = world(), rank()
+    if w == 1:
+        return ops.argsort(a, descending=descending)
+    dev = a._t.device
+    n_local = a.size
+    sizes = torch.empty(w, dtype=torch.int64, device=dev)
+    td.all_gather_into_tensor(sizes, torch.tensor([n_local], dtype=torch.int64, device=dev))
+    sizes = sizes.cpu().numpy()
+    lo, n_global = int(sizes[:r].sum()), int(sizes.sum())
+    gidx = ops.iota(n_local, dev, start=lo)
+    keys = a if a._t.dtype != torch.bool else ops.astype(a, np.int64)
+    # ---- 1. splitters
+    s = samples_per_rank
+    if n_local:
+        pick = ops.astype(ops.binary("div", ops.binary("mul", ops.iota(s, dev), n_local), s), np.int64)   # floor(j * n / s)
+        sk, sp = ops.gather(keys, pick)._t, ops.gather(gidx, pick)._t
+    else:
+        sk = torch.empty(0, dtype=keys._t.dtype, device=dev)
+        sp = torch.empty(0, dtype=torch.int64, device=dev)
+    cnt = _all_counts(torch.tensor([sk.numel()] * w, dtype=torch.int64, device=dev))[:, 0]
+    pad_k = torch.zeros(s, dtype=keys._t.dtype, device=dev)
+    pad_p = torch.zeros(s, dtype=torch.int64, device=dev)
+    pad_k[: sk.numel()], pad_p[: sp.numel()] = sk, sp
+    all_k = torch.empty(w * s, dtype=keys._t.dtype, device=dev)
+    all_p = torch.empty(w * s, dtype=torch.int64, device=dev)
+    td.all_gather_into_tensor(all_k, pad_k)
+    td.all_gather_into_tensor(all_p, pad_p)
+    valid = torch.cat([torch.arange(s, device=dev) < int(c) for c in cnt])
+    all_k, all_p = DeviceArray(all_k[valid]), DeviceArray(all_p[valid])
+    order = ops.argsort(all_k)                       # samples are in ascending position order per rank: stable = composite
+    m = all_k.size
+    if m == 0:
+        return DeviceArray(torch.empty(0, dtype=torch.int64, device=dev))
+    qs = ops.asarray(np.minimum((np.arange(1, w) * m) // w, m - 1).astype(np.int64), device=dev)
+    at = ops.gather(order, qs)
+    split_k, split_p = ops.gather(all_k, at).to_numpy(), ops.gather(all_p, at).to_numpy()
+    # ---- 2. bucket = number of splitters (k_s, p_s) <= (key, position), lexicographically
+    bucket = None
+    for j in range(w - 1):
+        ks = split_k[j].item()
+        ps = int(split_p[j])
+        # (key > ks) | ((key == ks) & (pos >= ps))  as 0/1 int64:  gt + eq * ge
+        code = [ops.OP_ARG, 0, ops.OP_ARG, 2, ops.OPC["gt"], ops.OP_ARG, 0, ops.OP_ARG, 2, ops.OPC["eq"],
+                ops.OP_ARG, 1, ops.OP_ARG, 3, ops.OPC["lt"]] + ops.lit(1) + [ops.OPC["sub"], ops.OPC["neg"], ops.OPC["mul"], ops.OPC["add"]]
+        term = ops.run(code, [keys, gidx, ks, ps], _no_defer=True) if n_local else ops.iota(0, dev)
+        bucket = term if bucket is None else ops.binary("add", bucket, term)
+    if n_local:
+        if np.issubdtype(np.asarray(split_k).dtype, np.floating):
+            # NaN keys sort last (np.argsort): comparisons with NaN are false, so they would land in bucket 0
+            isn = ops.astype(ops.unary("isnan_b", keys), np.int64)
+            bucket = ops.binary("add", ops.binary("mul", bucket, ops.binary("sub", 1, isn)), ops.binary("mul", isn, w - 1))
+        part = ops.argsort(bucket)                   # stable partition by bucket
+        send_k, send_p = ops.gather(keys, part)._t, ops.gather(gidx, part)._t
+        counts = torch.stack([ops.reduce("add", ops.astype(ops.binary("eq_b", bucket, b), np.int64))._t for b in range(w)])
+    else:
+        send_k, send_p = keys._t, gidx._t
+        counts = torch.zeros(w, dtype=torch.int64, device=dev)
+    mat = _all_counts(counts)                        # mat[src, dst]
+    recv_k = _exchange(send_k, mat[r, :], mat[:, r])
+    recv_p = _exchange(send_p, mat[r, :], mat[:, r])
+    # ---- 3. local stable sort by key, then back to the block partition
+    if recv_k.numel():
+        local = ops.argsort(DeviceArray(recv_k))
+        chunk = ops.gather(DeviceArray(recv_p), local)._t
+    else:
+        chunk = recv_p
+    held = mat.sum(axis=0)                           # elements each rank holds after the exchange
+    my_off = int(held[:r].sum())
+    if descending:
+        chunk = ops.reverse(DeviceArray(chunk))._t if chunk.numel() else chunk
+        my_off = n_global - my_off - int(held[r])    # reversed global order: this rank's chunk sits mirrored
+    blocks = np.concatenate([[0], np.cumsum(sizes)])
+    send_counts = [max(0, min(my_off + int(held[r]), int(blocks[d + 1])) - max(my_off, int(blocks[d]))) for d in range(w)]
+    if descending:
+        # destination blocks are visited from the last rank down in the mirrored order; segments must still be laid out
+        # in destination-rank order for the collective, which they are (offsets ascend with the destination)
+        pass
+    mat2 = _all_counts(torch.tensor(send_counts, dtype=torch.int64, device=dev))
+    out = _exchange(chunk, mat2[r, :], mat2[:, r])
+    if descending:
+        # source ranks contribute in ascending rank order, but in the mirrored order higher ranks come first
+        segs, o = [], 0
+        for src in range(w):
+            c = int(mat2[src, r])
+            segs.append(out[o:o + c])
+            o += c
+        out = torch.cat(segs[::-1]) if segs else out
+    return DeviceArray(out)
+
+
+def sharded_range(a):
+    """`?a` of a block-sharded vector: the distinct values in order of first appearance, replicated on
+    every rank.  The ranks' own answers, concatenated in rank order, list every candidate in ascending position of its first
+    LOCAL appearance — so the global answer is simply `?` of that concatenation: one all_gather of the candidate counts, one
+    of the (padded) candidates, one small local `?a`."""
+    w = world()
+    local = ops.unique_first(a)
+    if w == 1:
+        return local
+    dev = a._t.device
+    cnt = _all_counts(torch.tensor([local.size] * w, dtype=torch.int64, device=dev))[:, 0]
+    cap = int(cnt.max())
+    pad = torch.zeros(cap, dtype=local._t.dtype, device=dev)
+    pad[: local.size] = local._t
+    allc = torch.empty(w * cap, dtype=local._t.dtype, device=dev)
+    td.all_gather_into_tensor(allc, pad)
+    valid = torch.cat([torch.arange(cap, device=dev) < int(c) for c in cnt])
+    return ops.unique_first(DeviceArray(allc[valid]))
 
 
 def sharded_find(a, needle, n_global=None):

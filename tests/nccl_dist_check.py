@@ -44,6 +44,13 @@ for n in (1000, 1_000_003, 40_000_001):
         t2 = [t.to_numpy() for t in dist.sharded_groupagg(be.kg_asarray(k[lo:hi]), be.kg_asarray(v[lo:hi]), G, exchange=exchange)]
         assert np.array_equal(t2[0], mn) and np.array_equal(t2[1], mxg) and np.array_equal(t2[3], ct), exchange
         assert np.allclose(t2[2], sm, rtol=1e-12, atol=1e-9), exchange
+    # multi-GPU grade (sample sort, composite splitters, two all_to_alls) and range — SURVEY.md §8e rows 5-6
+    for kk in (rng.permutation(n), k, np.round(v, 0)):
+        gref = np.argsort(kk, kind="stable")
+        up = dist.sharded_argsort(be.kg_asarray(kk[lo:hi])).to_numpy()
+        down = dist.sharded_argsort(be.kg_asarray(kk[lo:hi]), descending=True).to_numpy()
+        assert np.array_equal(up, gref[lo:hi]) and np.array_equal(down, gref[::-1][lo:hi]), "sharded_argsort"
+    assert np.array_equal(dist.sharded_range(be.kg_asarray(k[lo:hi])).to_numpy(), O.range_unique(k)), "sharded_range"
     pos, counts = dist.sharded_find(be.kg_asarray(k[lo:hi]), 7)
     want = np.nonzero(k == 7)[0]
     find_ok = counts.sum() == len(want) and np.array_equal(pos.to_numpy(), want[(want >= lo) & (want < hi)])

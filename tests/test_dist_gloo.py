@@ -73,6 +73,21 @@ def _worker(rank, world, port, q):
             want = O.grouped_stats(k2, v, G2)
             assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and np.array_equal(got[3], want[3]), (G2, rank)
             assert np.allclose(got[2], want[2], rtol=1e-12, atol=1e-9), (G2, rank)
+        # grade of a sharded vector (sample sort with composite splitters) and range (?a): exact against the global oracle
+        for name, kk in (("perm", rng.permutation(n)), ("ties", rng.integers(0, 7, n)), ("neg", rng.integers(-50, 50, n)),
+                         ("f64", np.round(rng.standard_normal(n), 1)), ("const", np.full(n, 3))):
+            if name == "f64":
+                kk = kk.copy()
+                kk[rng.integers(0, n, 50)] = np.nan
+                kk[rng.integers(0, n, 50)] = -0.0
+            ref = np.argsort(kk, kind="stable")
+            up = dist.sharded_argsort(be.kg_asarray(kk[lo:hi])).to_numpy()
+            assert np.array_equal(up, ref[lo:hi]), (name, rank)
+            down = dist.sharded_argsort(be.kg_asarray(kk[lo:hi]), descending=True).to_numpy()
+            assert np.array_equal(down, ref[::-1][lo:hi]), (name, rank)
+            u = dist.sharded_range(be.kg_asarray(kk[lo:hi])).to_numpy()
+            want_u = O.range_unique(kk)
+            assert len(u) == len(want_u) and np.array_equal(u, want_u, equal_nan=True), (name, rank)
         # find: global positions of this rank's hits + every rank's count
         pos, counts = dist.sharded_find(I, 7)
         want = np.nonzero(i == 7)[0]
