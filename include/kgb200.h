@@ -177,7 +177,7 @@ const char* kgb_expr_kernel_name(const kgb_expr* h);
    path (writer.py:114-117).  Stable ascending LSD radix sort of (key, position); `descending` returns
    the stable ascending permutation reversed, which is the language contract (writer.py:97-108,
    tests/test_suite.py:82).  idx_out: int64[n].  keys_sorted_out: optional (NULL) dtype-typed [n].
-   SYNCHRONISES `stream` for n >= 2^18: the varying key bits are read back once to pick the digit plan
+   SYNCHRONISES `stream` for n >= 2^21: a 64 K-key sample is read back once to pick the digit plan
    (live key bits and position packed into one 64-bit word, 7..10-bit digits; csrc/kgb_sort_packed.cuh),
    and keys wider than the packed word are read back once more after the prefix fix-up.  kgb_group,
    kgb_unique_first and everything else built on the sort inherit this. */

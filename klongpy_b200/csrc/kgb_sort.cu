@@ -872,7 +872,7 @@ int sort_pairs(const void* keys, int dtype, i64 n, int descending, i64* idx_out,
         const char* e = getenv("KGB200_SORT_PACKED");
         const int packed_env = e ? (atoi(e) != 0) : 1;
         const char* m = getenv("KGB200_SORT_PACKED_MIN");
-        const long long packed_min = m ? atoll(m) : (1ll << 18);
+        const long long packed_min = m ? atoll(m) : (1ll << 21);  // crossover measured at 2^20..2^21 (profiles/r02g_sort_small.log)
         if (packed_env && n >= packed_min && n < (1ll << 30)) {
             const SortWs gw = carve(ws, n);
             const int rc = sort_packed(keys, dtype, n, descending, idx_out, keys_sorted_out, enc_sorted_out, gw, st, grp);

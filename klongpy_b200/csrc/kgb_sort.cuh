@@ -9,7 +9,7 @@ size_t sort_ws_bytes(i64 n);
 
 // Stable ascending LSD radix sort of (order-encoded key, position).  idx_out: int64[n] permutation
 // (written reversed when `descending`).  keys_sorted_out: optional typed sorted keys.  enc_sorted_out:
-// optional order-encoded (u64) sorted keys.  Synchronises the stream for n >= 2^18 (packed path, kgb_sort_packed.cuh).
+// optional order-encoded (u64) sorted keys.  Synchronises the stream for n >= 2^21 (packed path, kgb_sort_packed.cuh).
 // `grp` (optional, for `=a`): when the keys' value range is small enough for the packed path's full histogram, the group
 // start offsets and their count are written as well and grp->done is set — the caller skips its boundary pass (and
 // enc_sorted_out, wanted only for that pass, is then NOT written).
