@@ -287,7 +287,11 @@ def make_callable(ir):
                     raise ValueError("zero-size array to reduction operation which has no identity")
             if not any(isinstance(a, DeviceArray) for a in sargs):
                 raise NotImplementedError("stage without device operands")
-            vals[st.out_slot] = ops.run(st.code, sargs, mode=st.mode, red=st.red, code2=st.code2, red2=st.red2)
+            # the plan's final scalar epilogue (`(+/p*s)%+/s`: a divide of two 0-d results) launches at once: deferring a
+            # 0-d result that the caller reads next only adds bookkeeping
+            final_scalar = st.out_slot == plan.result_slot and st.mode == _lib.MODE_MAP and not has_array
+            vals[st.out_slot] = ops.run(st.code, sargs, mode=st.mode, red=st.red, code2=st.code2, red2=st.red2,
+                                        _no_defer=final_scalar)
         return vals[plan.result_slot]
 
     fn.plan = plan
