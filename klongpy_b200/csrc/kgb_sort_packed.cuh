@@ -34,6 +34,7 @@ namespace pk {
 
 constexpr int MAXP = 6;  // passes of one packed sort (<= 54 key bits at 9 bits per pass; the planner never needs more)
 constexpr int MINBITS = 7, MAXBITS = 10;
+constexpr int PLAN_MAXBITS = 10;  // widest digit the planner uses (KGB200_SORT_MAXBITS overrides; see make_plan)
 constexpr int PLAN_MAXP = 5;  // passes a plan may use (n >= 2^14 leaves <= 50 key bits)
 constexpr int MAXBINS = 1 << MAXBITS;
 constexpr int ROLE_FIRST = 1, ROLE_LAST = 2;
@@ -1021,22 +1022,46 @@ inline Plan plan_from_range(u64 mn, u64 mx, int lo, u64 n) {
     p.lo = lo;
     p.live = live;
     p.kmask = live >= 64 ? ~0ull : ((1ull << live) - 1ull);
-    int np = (live + MAXBITS - 1) / MAXBITS;
-    if (np < 1) np = 1;
-    if (np > PLAN_MAXP) {  // only tiny n (few position bits) with wide keys
+    // Digit widths by measured cost (ms per pass and 1e8 keys on a B200, profiles/r02h_sort_widths.log: 7 bits 0.52,
+    // 8 bits 0.63, 9 bits 0.66, 10 bits 0.88 — the 1024-bin pass pays for two digits per totals thread, twice the
+    // look-back words and 32 KB of warp counters): the cheapest multiset of widths covering `live` bits, e.g. 27 -> 9+9+9,
+    // 30 -> 9+7+7+7 (not 10+10+10), 14 -> 7+7, 37 -> 9+7+7+7+7.  KGB200_SORT_MAXBITS caps the widest digit (tuning).
+    int maxbits = PLAN_MAXBITS;
+    if (const char* ev = getenv("KGB200_SORT_MAXBITS")) maxbits = atoi(ev) < MINBITS ? MINBITS : (atoi(ev) > MAXBITS ? MAXBITS : atoi(ev));
+    static const int cost[MAXBITS + 1] = {0, 0, 0, 0, 0, 0, 0, 52, 63, 66, 88};
+    int best_cost = 1 << 30, best_np = -1, best_w[PLAN_MAXP] = {0};
+    int w[PLAN_MAXP];
+    for (int np = 1; np <= PLAN_MAXP; np++) {
+        // non-increasing width sequences of length np (odometer)
+        for (int i = 0; i < np; i++) w[i] = MINBITS;
+        for (;;) {
+            int sum = 0, c = 0;
+            for (int i = 0; i < np; i++) {
+                sum += w[i];
+                c += cost[w[i]];
+            }
+            if (sum >= live && c < best_cost) {
+                best_cost = c;
+                best_np = np;
+                for (int i = 0; i < np; i++) best_w[i] = w[i];
+            }
+            int i = np - 1;   // next non-increasing sequence
+            while (i >= 0 && w[i] == (i == 0 ? maxbits : w[i - 1])) i--;
+            if (i < 0) break;
+            w[i]++;
+            for (int j = i + 1; j < np; j++) w[j] = MINBITS;
+        }
+    }
+    if (best_np < 0) {  // only tiny n (few position bits) with wide keys
         p.npass = -1;
         return p;
     }
-    p.npass = np;
-    int left = live, pos = 0;
-    for (int i = 0; i < np; i++) {
-        int w = (left + (np - i) - 1) / (np - i);
-        if (w < MINBITS) w = MINBITS;
-        p.bits[i] = w;
+    p.npass = best_np;
+    int pos = 0;
+    for (int i = 0; i < best_np; i++) {
+        p.bits[i] = best_w[i];
         p.shift[i] = p.pb + pos;
-        pos += w;
-        left -= w;
-        if (left < 0) left = 0;
+        pos += best_w[i];
     }
     return p;
 }
