@@ -256,22 +256,31 @@ int kgb_groupagg_from_owners(const void* full, int64_t n_groups, int64_t world, 
 /* Replaces the per-line Python loop of examples/1brc/par.py:57-88 (`location, measurement = line.split(";")`,
    `np.asarray(temps, dtype=float)`) and the string grouping `=s` of worker.kg:5: a device buffer of complete lines
    `name;[-]d[d].d\n` becomes a dense station id and a float64 temperature per row plus the station dictionary.
-   Two phases, because the row count sizes the outputs:
-     kgb_brc_scan   newline bitmask + per-tile counts; writes the number of rows to *rows_out_host (one
-                    synchronising 8-byte read).  The text must end with '\n'.
-     kgb_brc_parse  per row: name span, 64-bit hash, insert / look up in an open-addressing table (names are
-                    compared byte for byte on a hash match), fixed-point parse of the measurement (exactly
-                    float("[-]d[d].d")).  id_out[r] in [0, *n_names) in first-arrival order; row i of
-                    dict_names_out (dict_capacity rows of 256 bytes, 4-byte aligned) holds the dict_len_out[i] <= 255
-                    bytes of name i, zero-filled up to the next multiple of 16.  *n_names_out_host receives the
-                    dictionary size (synchronising read).  Returns KGB_EINVAL for a malformed row, a name longer
-                    than 255 bytes or more than dict_capacity distinct names.
-   `workspace` must be the one kgb_brc_scan filled (same text, same n_bytes). */
+   ONE pass over the text (round 2; round 1 read it twice):
+     kgb_brc_parse  per 65536-byte tile: newline positions in shared memory, the tile's first row number from a
+                    decoupled look-back over the tiles' line counts; per row: name span, multilinear hash, insert /
+                    look up in an open-addressing table (names are compared byte for byte on a tag match),
+                    fixed-point parse of the measurement (exactly float("[-]d[d].d")).  The text must end with
+                    '\n'.  Rows r < rows_capacity are written: id_out[r] in [0, *n_names) in first-arrival order,
+                    temp_out[r]; *rows_out_host receives the number of rows FOUND — when it exceeds rows_capacity
+                    the outputs are incomplete and the call is repeated with larger arrays (rows_capacity 0 with
+                    null outputs just counts and builds the dictionary).  Row i of dict_names_out (dict_capacity
+                    rows of 256 bytes, 4-byte aligned) holds the dict_len_out[i] <= 255 bytes of name i,
+                    zero-filled up to the next multiple of 16.  *n_names_out_host receives the dictionary size.
+                    Synchronises the stream once (40-byte read-back).  Returns KGB_EINVAL for a malformed row, a
+                    name longer than 255 bytes or more than dict_capacity distinct names.
+   Because the row count sizes the outputs, two ways to get it first:
+     kgb_brc_estimate  newline count of three 4 MB windows scaled to the text, + 2 % + 4096 rows (exact for texts up
+                    to 12 MB): an upper estimate that is almost always enough, for the price of a 12 MB read;
+     kgb_brc_scan   the exact count (one more read of the text).
+   Both synchronise the stream once (8-byte read-back). */
 int kgb_brc_workspace_bytes(int64_t n_bytes, size_t* out_bytes);
 int kgb_brc_scan(const uint8_t* text, int64_t n_bytes, int64_t* rows_out_host, void* workspace,
                  size_t workspace_bytes, void* stream);
-int kgb_brc_parse(const uint8_t* text, int64_t n_bytes, int64_t rows, int64_t* id_out, double* temp_out,
-                  uint8_t* dict_names_out, int32_t* dict_len_out, int64_t dict_capacity,
+int kgb_brc_estimate(const uint8_t* text, int64_t n_bytes, int64_t* rows_estimate_out_host, void* workspace,
+                     size_t workspace_bytes, void* stream);
+int kgb_brc_parse(const uint8_t* text, int64_t n_bytes, int64_t rows_capacity, int64_t* id_out, double* temp_out,
+                  uint8_t* dict_names_out, int32_t* dict_len_out, int64_t dict_capacity, int64_t* rows_out_host,
                   int64_t* n_names_out_host, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus

@@ -63,7 +63,8 @@ SIGNATURES = {
     "kgb_groupagg_from_owners": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "kgb_brc_workspace_bytes": (_i32, [_i64, _psz]),
     "kgb_brc_scan": (_i32, [_vp, _i64, _pi64, _vp, _sz, _vp]),
-    "kgb_brc_parse": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _pi64, _vp, _sz, _vp]),
+    "kgb_brc_estimate": (_i32, [_vp, _i64, _pi64, _vp, _sz, _vp]),
+    "kgb_brc_parse": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _pi64, _pi64, _vp, _sz, _vp]),
 }
 
 _lib = None

@@ -402,10 +402,16 @@ class FakeLib:
         rows_out._obj.value = int(np.count_nonzero(t == 10))
         return 0
 
-    def kgb_brc_parse(self, text, n, rows, ids, temps, dnames, dlen, cap, n_names_out, ws, wsb, stream):
+    def kgb_brc_estimate(self, text, n, rows_out, ws, wsb, stream):
+        return self.kgb_brc_scan(text, n, rows_out, ws, wsb, stream)
+
+    def kgb_brc_parse(self, text, n, rows, ids, temps, dnames, dlen, cap, rows_out, n_names_out, ws, wsb, stream):
         raw = bytes(view_bytes(text, n)) if n else b""
+        if raw and raw[-1:] != b"\n":
+            self.err = b"kgb_brc_parse: the text must end with a newline"
+            return 1
         seen, pos, r = {}, 0, 0
-        ido, tmo = view(ids, rows, I64), view(temps, rows, F64)
+        ido, tmo = (view(ids, rows, I64), view(temps, rows, F64)) if rows else (None, None)
         dnm, dln = view_bytes(dnames, cap * 256).reshape(cap, 256), view(dlen, cap, I32)
         for line in raw.split(b"\n")[:-1]:
             name, _, meas = line.rpartition(b";")
@@ -419,9 +425,11 @@ class FakeLib:
                     return 1
                 dnm[len(seen), :len(name)], dln[len(seen)] = np.frombuffer(name, np.uint8), len(name)
                 seen[name] = len(seen)
-            ido[r], tmo[r] = seen[name], float(meas)
+            if r < rows:
+                ido[r], tmo[r] = seen[name], float(meas)
             pos += len(line) + 1
             r += 1
+        rows_out._obj.value = r
         n_names_out._obj.value = len(seen)
         return 0
 

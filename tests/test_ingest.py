@@ -132,6 +132,66 @@ def test_gpu_ingest_alignment_long_names_tile_edges():
     assert ingest.parse(("x" * 255 + ";1.0\n").encode(), device="cuda:0")[2] == ["x" * 255]
 
 
+@pytest.mark.gpu
+def test_gpu_ingest_every_measurement_value_and_row_estimate_miss():
+    """(1) Every measurement -99.9 .. 99.9 in every spelling the format allows (d.d, dd.d, -d.d, -dd.d, 0d.d) equals
+    Python's float() bit for bit — the kernel computes tenths * 0.1 corrected by its exact residual instead of a table.
+    (2) A text whose three sample windows hold long lines while the rest holds short ones: kgb_brc_estimate comes out
+    too low, kgb_brc_parse reports the real row count and ingest.parse repeats the pass — same result as the oracle.
+    (3) rows_capacity 0 with null outputs counts the rows and builds the dictionary."""
+    import ctypes
+    import torch
+    from klongpy_b200 import _lib, ingest, ops
+    vals = [f"{s}{a}.{b}" for s in ("", "-") for a in list(range(100)) + ["00", "01", "05", "09"] for b in range(10)]
+    text = "".join(f"st{k % 7};{v}\n" for k, v in enumerate(vals)).encode()
+    ids, temps, names = ingest.parse(text, device="cuda:0")
+    want = np.array([float(v) for v in vals])
+    got = temps.to_numpy()
+    assert got.shape == want.shape and np.array_equal(got.view(np.int64), want.view(np.int64))   # incl. the sign of -0.0
+    rn, ri, rt = O.parse_1brc(text)
+    assert names == rn and np.array_equal(ids.to_numpy(), ri)
+    # (2)
+    rng = np.random.default_rng(4)
+    long_names = ["L" + "".join(rng.choice(list("abcdefghij"), 40)) for _ in range(50)]
+    short_names = ["s%d" % k for k in range(90)]
+    win = 4 << 20
+
+    def block(names_, nbytes):
+        out, size = [], 0
+        while size < nbytes:
+            line = f"{names_[int(rng.integers(0, len(names_)))]};{int(rng.integers(-99, 100))}.{int(rng.integers(0, 10))}\n"
+            out.append(line)
+            size += len(line)
+        return "".join(out)
+    text = (block(long_names, win + 4096) + block(short_names, 3 * win) + block(long_names, win + 4096) +
+            block(short_names, 3 * win) + block(long_names, win + 4096)).encode()
+    dev = torch.device("cuda:0")
+    t = torch.from_numpy(np.frombuffer(text, dtype=np.uint8).copy()).to(dev)
+    lib, stream = ops._lib_for(dev)
+    wsb = ctypes.c_size_t()
+    _lib.check(lib.kgb_brc_workspace_bytes(t.numel(), ctypes.byref(wsb)), "ws")
+    ws = torch.empty(wsb.value, dtype=torch.uint8, device=dev)
+    est, exact = ctypes.c_int64(), ctypes.c_int64()
+    _lib.check(lib.kgb_brc_estimate(t.data_ptr(), t.numel(), ctypes.byref(est), ws.data_ptr(), wsb.value, stream), "estimate")
+    _lib.check(lib.kgb_brc_scan(t.data_ptr(), t.numel(), ctypes.byref(exact), ws.data_ptr(), wsb.value, stream), "scan")
+    rows = text.count(b"\n")
+    assert exact.value == rows and est.value < rows          # the windows were not representative
+    gi, gt, gn = ingest.parse(t, device=dev)
+    rn, ri, rt = O.parse_1brc(text)
+    assert gn == rn and np.array_equal(gi.to_numpy(), ri) and np.array_equal(gt.to_numpy(), rt)
+    # (3)
+    dn = torch.zeros(ingest.DICT_CAPACITY * 256, dtype=torch.uint8, device=dev)
+    dl = torch.empty(ingest.DICT_CAPACITY, dtype=torch.int32, device=dev)
+    r, nn = ctypes.c_int64(), ctypes.c_int64()
+    _lib.check(lib.kgb_brc_parse(t.data_ptr(), t.numel(), 0, None, None, dn.data_ptr(), dl.data_ptr(), ingest.DICT_CAPACITY,
+                                 ctypes.byref(r), ctypes.byref(nn), ws.data_ptr(), wsb.value, stream), "count only")
+    assert r.value == rows and nn.value == len(rn)
+    with pytest.raises(_lib.KgbError):                       # no final newline
+        lib_text = t[:-1].contiguous()
+        _lib.check(lib.kgb_brc_parse(lib_text.data_ptr(), lib_text.numel(), 0, None, None, dn.data_ptr(), dl.data_ptr(),
+                                     ingest.DICT_CAPACITY, ctypes.byref(r), ctypes.byref(nn), ws.data_ptr(), wsb.value, stream), "parse")
+
+
 def _file_case(tmp_path, rows, n_names, tail_newline=True, seed=3):
     rng = np.random.default_rng(seed)
     text = _synthetic(rng, rows, n_names)
