@@ -558,6 +558,11 @@ extern "C" int kgb_groupagg_f64(const int64_t* keys, const double* vals, int64_t
         // memory and RED.ADD.F64 sums on the global table, 2 = filters only, 0 = v1 (all four updates on the
         // global table).  KGB200_AGG_VARIANT overrides for measurements.
         // 5 = variant 3 with both filters packed into one 32-bit word (one LDS per row instead of two; default).
+        // Round 2, measured and NOT kept: count and filters in ONE 32-bit word {count:8 | max filter:12 | min filter:12}
+        // updated by a native RETURNING ATOMS.ADD (the filters arrive with the increment: 3 shared-memory operations
+        // per row instead of 4; the one thread that sees the 8-bit count wrap adds 256 to the global table) — 5.30 ms
+        // at 1e9 rows against 3.73 ms: a returning shared atomic stalls its warp far longer than LDS + ATOMS.POPC.INC.
+        // (64-bit shared integer adds are not native at all: ATOMS.CAST.SPIN.64, a CAS loop.)
         int variant = 5;  // measured at 1e9 rows / 10k stations: v5 3.72 ms (0.66 of roofline), v3 4.09 ms (0.60), v4 7.1 ms, v1 ~14 ms, v0 ~23 ms
         if (const char* e = getenv("KGB200_AGG_VARIANT")) variant = atoi(e);
         if (variant < 0 || variant > 6) variant = 5;
