@@ -3,8 +3,8 @@
 // worker.kg:5.  Byte work, HBM-bound by design; round 2 reads the text ONCE:
 //
 //   brc_onepass_kernel  one CTA per 65536-byte tile, tiles handed out by an atomic ticket.  The tile (plus a 512-byte
-//                     halo in front, for the line that straddles the tile edge) is staged in shared memory with
-//                     coalesced 128-bit loads; while a 16-byte granule sits in registers its newline flags are taken
+//                     halo in front, for the line that straddles the tile edge) is staged in shared memory by one
+//                     cp.async.bulk (TMA engine, mbarrier completion); of every 16-byte granule the newline flags are taken
 //                     (exact zero-byte test of x ^ 0x0a0a0a0a, one multiply gathers four flags: 24 instructions per
 //                     granule) and paired into 32-byte mask words in shared memory — no mask array in HBM.  A block
 //                     scan of the popcounts numbers the tile's lines and expands the masks into a list of newline
@@ -36,6 +36,9 @@ constexpr int BRC_LOG2_SLOTS = 20;  // 32 MB; only the sectors of live names are
 constexpr u64 BRC_SLOTS = 1ull << BRC_LOG2_SLOTS;
 constexpr int BRC_NAME_BYTES = 256;                 // dictionary row: a name of <= 255 bytes as zero-extended 32-bit words
 constexpr int BRC_NAME_WORDS = BRC_NAME_BYTES / 4;
+#ifndef KGB_BRC_BULK
+#define KGB_BRC_BULK 1  // 0: stage interior tiles through registers (LDG + STS) instead of cp.async.bulk
+#endif
 constexpr int BRC_HALO = 512;                       // bytes before the tile kept with it: a line may start there
 constexpr int BRC_MIN_TILE = 16384;                 // the look-back states are sized for the smallest tile
 template <int TILE>
@@ -193,12 +196,36 @@ __global__ void __launch_bounds__(T, CTAS) brc_onepass_kernel(const unsigned cha
     u32* s_mask = reinterpret_cast<u32*>(s_text + G::OFF_MASK);
     unsigned short* s_pos = reinterpret_cast<unsigned short*>(s_text + G::OFF_POS + 16);
     u32* s_wcnt = reinterpret_cast<u32*>(s_text + G::OFF_WCNT);
-    int* s_misc = reinterpret_cast<int*>(s_text + G::OFF_MISC);  // [0] tile  [1] start of the first line  [2..3] first row
+    int* s_misc = reinterpret_cast<int*>(s_text + G::OFF_MISC);
     constexpr int WPT = (G::WORDS + T - 1) / T;
     constexpr int NW = T / 32;
     static_assert(WPT * (T - 32) >= G::WORDS, "the last warp owns no mask words: it runs the look-back");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_misc[0] = (int)atomicAdd(&ctl->ticket, 1u);
+    // [0] tile  [1] start of the first line  [2..3] first row  [4..5] mbarrier of the bulk copy  [6] bulk copy issued
+    const u32 bar = (u32)__cvta_generic_to_shared(s_misc + 4);
+    if (tid == 0) {
+        // interior tiles (every staged granule inside the text's granules) arrive by ONE bulk copy of the TMA engine
+        // (cp.async.bulk, SASS UBLKCP), issued by this thread as soon as it holds the ticket — before the CTA's first
+        // barrier; the tiles at the two ends of the text take the per-granule path below (bytes outside the text read
+        // as zero there)
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const i64 tk = (i64)atomicAdd(&ctl->ticket, 1u);
+        const uintptr_t ta = reinterpret_cast<uintptr_t>(text) + (uintptr_t)(tk * TILE);
+        const uintptr_t gg = (ta - BRC_HALO) & ~(uintptr_t)15;
+        const uintptr_t lo_b = reinterpret_cast<uintptr_t>(text) & ~(uintptr_t)15;
+        const uintptr_t hi_b = (reinterpret_cast<uintptr_t>(text) + (uintptr_t)n + 15) & ~(uintptr_t)15;
+        const bool bulk = KGB_BRC_BULK && gg >= lo_b && gg + G::STAGE <= hi_b;
+        if (bulk) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((u32)G::STAGE) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             (u32)__cvta_generic_to_shared(brc_smem)),
+                         "l"(gg), "r"((u32)G::STAGE), "r"(bar)
+                         : "memory");
+        }
+        s_misc[0] = (int)tk;
+        s_misc[6] = bulk ? 1 : 0;
+    }
     if (tid < (BRC_INSLOT + 1) * 8) {
         const int rem = (tid >> 3) - 4 * (tid & 7);
         s_mlut[tid] = rem >= 4 ? 0xffffffffu : rem <= 0 ? 0u : (1u << (8 * rem)) - 1u;
@@ -216,7 +243,23 @@ __global__ void __launch_bounds__(T, CTAS) brc_onepass_kernel(const unsigned cha
         const uintptr_t lo_b = reinterpret_cast<uintptr_t>(text) & ~(uintptr_t)15;
         const uintptr_t hi_b = (reinterpret_cast<uintptr_t>(text) + (uintptr_t)n + 15) & ~(uintptr_t)15;
         const uint4* gsrc = reinterpret_cast<const uint4*>(g0);
-        if (g0 >= lo_b && g0 + G::STAGE <= hi_b) {  // every staged granule lies inside the text's granules
+        if (s_misc[6]) {  // the bulk copy is on its way: wait for its bytes, then take the newline flags from shared memory
+            u32 done = 0;
+            while (!done)
+                asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}"
+                             : "=r"(done)
+                             : "r"(bar)
+                             : "memory");
+#pragma unroll 3
+            for (int c0 = 0; c0 < G::GRAN; c0 += T) {
+                const int c = c0 + tid;
+                uint4 q = make_uint4(0u, 0u, 0u, 0u);
+                if (c < G::GRAN) q = brc_smem[c];
+                const u32 h = nl16(q);
+                const u32 other = __shfl_xor_sync(0xffffffffu, h, 1);
+                if (!(tid & 1) && c < G::GRAN) s_mask[c >> 1] = h | (other << 16);
+            }
+        } else if (g0 >= lo_b && g0 + G::STAGE <= hi_b) {  // (KGB_BRC_BULK=0: the same tiles through registers)
 #pragma unroll 3
             for (int c0 = 0; c0 < G::GRAN; c0 += T) {
                 const int c = c0 + tid;
