@@ -1224,7 +1224,10 @@ inline cudaError_t packed_attempt(const void* keys, int dtype, u64 n, const Plan
             attr_set[dev] = true;
         }
         long long blocks = (long long)((n + 8191) / 8192);
-        const long long cap = (long long)sms * (full ? 1 : 2);
+        // two resident CTAs per SM wherever their histograms fit (the whole-field one takes 4 << live bytes: 128 KB at
+        // 15 bits): 0.274 -> 0.191 ms for 10 k keys in 1e8 rows; three are slower again (KGB200_HV_CTAS: measurements)
+        static const int hv_ctas = getenv("KGB200_HV_CTAS") ? atoi(getenv("KGB200_HV_CTAS")) : 0;
+        const long long cap = (long long)sms * (hv_ctas > 0 ? hv_ctas : ((full && p.live > 14) ? 1 : 2));
         if (blocks > cap) blocks = cap;
         const size_t smem = full ? ((size_t)4 << p.live) : ((size_t)4 << p.bits[0]);
         if (full) {
