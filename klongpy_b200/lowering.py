@@ -225,10 +225,30 @@ def make_callable(ir):
     """Return fn(*args) executing the plan on device arrays.  Raises on unsupported argument kinds."""
     plan = Plan(ir)
     n_params = len(plan.params)
+    # a plan of ONE kernel whose operands are exactly the call arguments (a+b, a*2+b, +/a*b, +\a ... — five of the six
+    # rows of examples/bench_compiler.kg): the pre-resolved launcher takes the call when every argument is a plain 1-d
+    # device vector or a Python number; everything else (and every other plan) goes through the general loop below
+    fast = None
+    if len(plan.stages) == 1:
+        st0 = plan.stages[0]
+        if st0.pair is None and st0.code2 is None and list(st0.slots) == list(range(n_params)) and \
+                st0.mode in (_lib.MODE_MAP, _lib.MODE_REDUCE, _lib.MODE_SCAN):
+            fast = ops.FastStage(st0.code, st0.mode, st0.red)
+    # inside the general loop every plain stage (and every paired fold) tries its own pre-resolved launcher first
+    stage_fast = {}
+    for st in plan.stages:
+        if st.pair is not None:
+            stage_fast[id(st)] = ops.FastStage(st.code, _lib.MODE_REDUCE, st.red, st.pair[1], st.pair[0].red)
+        elif st.code2 is None and st.mode in (_lib.MODE_MAP, _lib.MODE_REDUCE, _lib.MODE_SCAN):
+            stage_fast[id(st)] = ops.FastStage(st.code, st.mode, st.red)
 
     def fn(*args):
         if len(args) != n_params:
             raise TypeError(f"compiled expression takes {n_params} arguments ({len(args)} given)")
+        if fast is not None:
+            r = fast(args)
+            if r is not NotImplemented:
+                return r
         vals = list(args) + [None] * (plan.n_slots - n_params)
         any_dev = False
         nd_shape = None
@@ -253,6 +273,13 @@ def make_callable(ir):
             if st.pair is not None and nd_shape is None:
                 other, code_b, slots = st.pair
                 pargs = [vals[s] for s in slots]
+                try:
+                    r = stage_fast[id(st)](pargs)
+                except _lib.KgbError:
+                    r = NotImplemented   # a narrow accumulator: the general path below sorts it out
+                if r is not NotImplemented:
+                    vals[st.out_slot], vals[other.out_slot] = r
+                    continue
                 lens = {a.size for a in pargs if _is_arraylike(a)}
                 if len(lens) == 1 and 0 not in lens:
                     try:
@@ -261,6 +288,13 @@ def make_callable(ir):
                     except (_lib.KgbError, autodiff.NotDifferentiable):
                         pass  # a narrow accumulator, or a fold without a gradient rule: two separate reductions
             sargs = [vals[s] for s in st.slots]
+            if nd_shape is None:
+                fs = stage_fast.get(id(st))
+                if fs is not None:
+                    r = fs(sargs)
+                    if r is not NotImplemented:
+                        vals[st.out_slot] = r
+                        continue
             if nd_shape is not None and any(isinstance(a, DeviceArray) and a.ndim > 1 for a in sargs):
                 if any(isinstance(a, DeviceArray) and a.ndim == 1 for a in sargs):
                     raise NotImplementedError("compiled kernels do not broadcast 1-d against N-d operands")

@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .array import DeviceArray, _K2T, kgb_dtype, torch_dtype_of
+from .array import DeviceArray, _K2T, _T2K as _T2K_FAST, kgb_dtype, torch_dtype_of
 
 # ---------------------------------------------------------------------------------------- opcodes
 OP_ARG, OP_LIT_I64, OP_LIT_F64, OP_SCANVAL = 1, 2, 3, 4
@@ -182,6 +182,26 @@ _ARGV = [ctypes.c_void_p * max(k, 1) for k in range(17)]  # argument-pointer arr
 _lazy = None  # klongpy_b200.lazy, imported on first use (it imports this module)
 
 
+def _compile_handle(lib, device, code_t, code2_t, kinds, dts, mode, red, red2):
+    """(handle, kgb output dtype, torch output dtype) of one specialised program: NVRTC on the first use, a dictionary
+    hit afterwards."""
+    key = (device.index, code_t, code2_t, kinds, dts, mode, red, red2)
+    ent = _handles.get(key)
+    if ent is None:
+        n_args = len(kinds)
+        c_code = (ctypes.c_int32 * len(code_t))(*code_t)
+        c_code2 = (ctypes.c_int32 * len(code2_t))(*code2_t) if code2_t else None
+        c_k = (ctypes.c_int32 * max(n_args, 1))(*kinds)
+        c_d = (ctypes.c_int32 * max(n_args, 1))(*dts)
+        h = ctypes.c_void_p()
+        od = ctypes.c_int32()
+        _lib.check(lib.kgb_expr_compile(c_code, len(code_t), c_code2, len(code2_t), c_k, c_d, n_args, mode, red,
+                                        red2, ctypes.byref(h), ctypes.byref(od)), "kgb_expr_compile")
+        ent = (h, od.value, _K2T[od.value])
+        _handles[key] = ent
+    return ent
+
+
 def run(code, args, mode=_lib.MODE_MAP, red=0, code2=None, red2=0, out_shape=None, device=None, _no_defer=False):
     """Compile (cached) and launch one expression program.  Returns a DeviceArray."""
     global _lazy
@@ -280,21 +300,7 @@ def run(code, args, mode=_lib.MODE_MAP, red=0, code2=None, red2=0, out_shape=Non
     dts = tuple(dts)
     code_t = tuple(code)
     code2_t = tuple(code2) if code2 else ()
-    key = (device.index, code_t, code2_t, kinds, dts, mode, red, red2)
-    ent = _handles.get(key)
-    if ent is None:
-        n_args = len(args)
-        c_code = (ctypes.c_int32 * len(code_t))(*code_t)
-        c_code2 = (ctypes.c_int32 * len(code2_t))(*code2_t) if code2_t else None
-        c_k = (ctypes.c_int32 * max(n_args, 1))(*kinds)
-        c_d = (ctypes.c_int32 * max(n_args, 1))(*dts)
-        h = ctypes.c_void_p()
-        od = ctypes.c_int32()
-        _lib.check(lib.kgb_expr_compile(c_code, len(code_t), c_code2, len(code2_t), c_k, c_d, n_args, mode, red,
-                                        red2, ctypes.byref(h), ctypes.byref(od)), "kgb_expr_compile")
-        ent = (h, od.value, _K2T[od.value])
-        _handles[key] = ent
-    h, od, out_td = ent
+    h, od, out_td = _compile_handle(lib, device, code_t, code2_t, kinds, dts, mode, red, red2)
     n = 1
     if shape is not None:
         for s in shape:
@@ -323,6 +329,149 @@ def run(code, args, mode=_lib.MODE_MAP, red=0, code2=None, red2=0, out_shape=Non
     if rc:
         _lib.check(rc, "kgb_expr_launch")
     return DeviceArray(out)
+
+
+class FastStage:
+    """Pre-resolved launch state of ONE compiled stage for the common call shape of small-vector programs
+    (`examples/bench_compiler.kg`): every operand a materialised, contiguous 1-d device array of one length on one device,
+    a 0-d device value (an earlier stage's result) or a Python int / float, nothing on the autograd tape, nothing to
+    defer.  Then a call is: one signature tuple, one dictionary hit, one output allocation, one C-ABI launch.  Anything
+    else returns NotImplemented and the caller goes through `run` / `reduce2` (same kernels, same handle cache: this is
+    a shortcut through the host bookkeeping, not another path).  With `code2` the stage is the two-output fold
+    (`(+/p*s)%+/s`: both sums in one pass) and the call returns two 0-d values."""
+    __slots__ = ("code", "code2", "mode", "red", "red2", "cache", "ws_bytes")
+
+    def __init__(self, code, mode, red, code2=None, red2=0):
+        self.code, self.code2 = tuple(code), tuple(code2) if code2 else ()
+        self.mode, self.red, self.red2 = mode, red, red2
+        self.cache = {}      # (device index, operand signature) -> (handle, output torch dtype[, second output's])
+        self.ws_bytes = {}   # (handle value, n) -> scratch bytes of a fold / scan launch
+
+    def __call__(self, args):
+        global _lazy
+        dev = None
+        n = -1
+        sig, ptrs, keep = [], [], None
+        for a in args:
+            ta = type(a)
+            if ta is DeviceArray:
+                t = a._tensor
+                if t is None or t.requires_grad:
+                    return NotImplemented
+                if t.dim() == 1:
+                    if not t.is_contiguous():
+                        return NotImplemented
+                    m = t.numel()
+                    if n < 0:
+                        n = m
+                    elif m != n:
+                        return NotImplemented
+                    sig.append(t.dtype)
+                elif t.dim() == 0:
+                    sig.append((t.dtype,))   # 0-d device value
+                else:
+                    return NotImplemented
+                if dev is None:
+                    dev = t.device
+                elif t.device != dev:
+                    return NotImplemented
+                ptrs.append(t.data_ptr())
+            elif ta is float:
+                c = ctypes.c_double(a)
+                keep = (keep, c)
+                sig.append(float)
+                ptrs.append(ctypes.addressof(c))
+            elif ta is int:
+                c = ctypes.c_int64(a)
+                keep = (keep, c)
+                sig.append(int)
+                ptrs.append(ctypes.addressof(c))
+            else:
+                return NotImplemented
+        mode = self.mode
+        if dev is None or n == 0:
+            return NotImplemented
+        if n < 0:
+            if mode != _lib.MODE_MAP:
+                return NotImplemented   # a fold over scalars: interpreter semantics (the caller raises)
+            scalar_out, n = True, 1
+        else:
+            scalar_out = mode == _lib.MODE_REDUCE
+            if mode == _lib.MODE_MAP:
+                if _lazy is None:
+                    from . import lazy as _lazy_mod
+                    _lazy = _lazy_mod
+                if _lazy.ENABLED and n >= _lazy.MIN_SIZE:
+                    return NotImplemented   # long vectors: the result is deferred (run)
+        lib, stream = _lib_for(dev)
+        key = (dev.index, tuple(sig))
+        ent = self.cache.get(key)
+        if ent is None:
+            kinds, dts = [], []
+            for x in sig:
+                if isinstance(x, torch.dtype) or isinstance(x, tuple):
+                    td = x[0] if isinstance(x, tuple) else x
+                    if td not in _T2K_FAST:
+                        return NotImplemented   # (run raises the TypeError)
+                    kinds.append(_lib.ARG_DEVSCALAR if isinstance(x, tuple) else _lib.ARG_ARRAY)
+                    dts.append(_T2K_FAST[td])
+                else:
+                    kinds.append(_lib.ARG_SCALAR)
+                    dts.append(_lib.F64 if x is float else _lib.I64)
+            if self.code2:
+                ent = _compile_pair(lib, dev, self.code, self.code2, tuple(kinds), tuple(dts), self.red, self.red2)
+            else:
+                h, od, out_td = _compile_handle(lib, dev, self.code, (), tuple(kinds), tuple(dts), mode, self.red, self.red2)
+                ent = (h, out_td)
+            self.cache[key] = ent
+        h, out_td = ent[0], ent[1]
+        if self.code2:
+            out = torch.empty(2, dtype=torch.int64, device=dev)   # two 8-byte results side by side
+        else:
+            out = torch.empty(() if scalar_out else (n,), dtype=out_td, device=dev)
+        if mode == _lib.MODE_MAP:
+            ws_ptr, wsb = None, 0
+        else:
+            wkey = (h.value, n)
+            wsb = self.ws_bytes.get(wkey)
+            if wsb is None:
+                q = ctypes.c_size_t()
+                _lib.check(lib.kgb_expr_workspace_bytes(h, n, ctypes.byref(q)), "kgb_expr_workspace_bytes")
+                if len(self.ws_bytes) > 64:
+                    self.ws_bytes.clear()
+                wsb = self.ws_bytes[wkey] = q.value
+            ws_ptr = _scratch(dev, stream, wsb)
+        na = len(ptrs)
+        argv = _ARGV[na](*ptrs) if na < len(_ARGV) else (ctypes.c_void_p * na)(*ptrs)
+        rc = lib.kgb_expr_launch(h, argv, n, out.data_ptr(), ws_ptr, wsb, stream)
+        if rc:
+            _lib.check(rc, "kgb_expr_launch")
+        if self.code2:
+            a0, a1 = out.unbind(0)
+            return (DeviceArray(a0 if out_td is torch.int64 else a0.view(out_td)),
+                    DeviceArray(a1 if ent[2] is torch.int64 else a1.view(ent[2])))
+        return DeviceArray(out)
+
+
+def _compile_pair(lib, device, code_t, code2_t, kinds, dts, red, red2):
+    """(handle, torch dtype of output 1, of output 2) of a two-output fold (both accumulators 8 bytes wide)."""
+    key = (device.index, code_t, code2_t, kinds, dts, _lib.MODE_REDUCE, red, red2, "reduce2")
+    ent = _handles.get(key)
+    if ent is None:
+        n_args = len(kinds)
+        h = ctypes.c_void_p()
+        od = ctypes.c_int32()
+        _lib.check(lib.kgb_expr_compile((ctypes.c_int32 * len(code_t))(*code_t), len(code_t),
+                                        (ctypes.c_int32 * len(code2_t))(*code2_t), len(code2_t),
+                                        (ctypes.c_int32 * max(n_args, 1))(*kinds), (ctypes.c_int32 * max(n_args, 1))(*dts),
+                                        n_args, _lib.MODE_REDUCE, red, red2, ctypes.byref(h), ctypes.byref(od)),
+                   "kgb_expr_compile")
+        od2 = lib.kgb_expr_out_dtype2(h)
+        if od2 < 0:
+            raise _lib.KgbError("kgb_expr_compile did not produce a two-output reduce")
+        ent = (h, od.value, od2)
+        _handles[key] = ent
+    return ent[0], _K2T[ent[1]], _K2T[ent[2]]
 
 
 _scratch_cache = {}
