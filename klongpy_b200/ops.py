@@ -569,8 +569,18 @@ def _lift(x, device):
     return x
 
 
+_fast_dyads, _fast_monads, _fast_folds, _fast_scans = {}, {}, {}, {}
+
+
 def binary(op, a, b):
     """Eager dyad: one-node program (dyads.py:6-21, 214-232, 588-803 call sites)."""
+    if op != "pow":   # (an integer power may need its operands converted first)
+        fs = _fast_dyads.get(op)
+        if fs is None:
+            fs = _fast_dyads[op] = FastStage((OP_ARG, 0, OP_ARG, 1, OPC[op]), _lib.MODE_MAP, 0)
+        r = fs((a, b))   # short 1-d device vectors / Python numbers: the pre-resolved launcher
+        if r is not NotImplemented:
+            return r
     dev = _device_of(a, b)
     if dev is None:
         if is_host_scalar(a) and is_host_scalar(b):
@@ -595,6 +605,12 @@ def _pow_operands(a, b):
 
 
 def unary(op, a):
+    fs = _fast_monads.get(op)
+    if fs is None:
+        fs = _fast_monads[op] = FastStage((OP_ARG, 0, OPC[op]), _lib.MODE_MAP, 0)
+    r = fs((a,))
+    if r is not NotImplemented:
+        return r
     dev = _device_of(a)
     if dev is None:
         if is_host_scalar(a):
@@ -654,6 +670,12 @@ def copy(a):
 
 def reduce(op, a, code=None, args=None):
     """op-fold over a 1-d device array (adverbs.py:232-243); N-d folds along axis 0 like numpy ufunc.reduce."""
+    fs = _fast_folds.get(op)
+    if fs is None:
+        fs = _fast_folds[op] = FastStage((OP_ARG, 0), _lib.MODE_REDUCE, RED[op])
+    r = fs((a,))
+    if r is not NotImplemented:
+        return r
     if a.ndim == 0:
         return a
     if a.ndim > 1:
@@ -735,6 +757,12 @@ def reduce_axis0(code, args, red):
 
 def scan(op, a):
     """inclusive op-scan (adverbs.py:325-332); N-d scans along axis 0."""
+    fs = _fast_scans.get(op)
+    if fs is None:
+        fs = _fast_scans[op] = FastStage((OP_ARG, 0), _lib.MODE_SCAN, RED[op])
+    r = fs((a,))
+    if r is not NotImplemented:
+        return r
     if a.ndim == 0:
         return a
     if a.ndim > 1:
