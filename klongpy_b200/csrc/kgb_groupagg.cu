@@ -198,21 +198,28 @@ __global__ void __launch_bounds__(1024, 1) groupagg_kernel_v2(const i64* __restr
         if (PACKED) {
             const u32 lo = (u32)(emin >> 48), hi = (u32)(emax >> 48);
             const u32 f = s_minhi[k];
+            // a row that passes this CTA's filter visits the global table anyway: the filter is then tightened to what
+            // ALL CTAs have seen so far (the global extreme's bucket), not just to this row's — the private filters
+            // converge after one or two visits per station instead of ~ln(rows per station per CTA)
             if (lo <= (f & 0xffffu)) {
-                for (u32 cur = f; lo < (cur & 0xffffu);) {
-                    const u32 got = atomicCAS(&s_minhi[k], cur, (cur & 0xffff0000u) | lo);
+                const u64 gmin = ld_relaxed_u64(&a.tmin[k]);
+                if (emin < gmin) atomicMin(&a.tmin[k], emin);
+                const u32 glo = (u32)(gmin >> 48), nlo = lo < glo ? lo : glo;
+                for (u32 cur = f; nlo < (cur & 0xffffu);) {
+                    const u32 got = atomicCAS(&s_minhi[k], cur, (cur & 0xffff0000u) | nlo);
                     if (got == cur) break;
                     cur = got;
                 }
-                if (emin < ld_relaxed_u64(&a.tmin[k])) atomicMin(&a.tmin[k], emin);
             }
             if (hi >= (f >> 16)) {
-                for (u32 cur = f; hi > (cur >> 16);) {
-                    const u32 got = atomicCAS(&s_minhi[k], cur, (cur & 0xffffu) | (hi << 16));
+                const u64 gmax = ld_relaxed_u64(&a.tmax[k]);
+                if (emax > gmax) atomicMax(&a.tmax[k], emax);
+                const u32 ghi = (u32)(gmax >> 48), nhi = hi > ghi ? hi : ghi;
+                for (u32 cur = f; nhi > (cur >> 16);) {
+                    const u32 got = atomicCAS(&s_minhi[k], cur, (cur & 0xffffu) | (nhi << 16));
                     if (got == cur) break;
                     cur = got;
                 }
-                if (emax > ld_relaxed_u64(&a.tmax[k])) atomicMax(&a.tmax[k], emax);
             }
         } else {
             const u32 lo = (u32)(emin >> 32), hi = (u32)(emax >> 32);
