@@ -160,6 +160,13 @@ int kgb_expr_workspace_bytes(const kgb_expr* h, int64_t n, size_t* out_bytes);
    REDUCE over n == 0 is rejected (the host mirrors numpy's identity / ValueError rules). */
 int kgb_expr_launch(kgb_expr* h, const void* const* args, int64_t n, void* out, void* workspace,
                     size_t workspace_bytes, void* stream);
+/* kgb_expr_launch with flags.  KGB_LAUNCH_WS_CLEAN: the caller zero-filled `workspace` when it allocated it and has
+   since passed it only to kgb_expr_launch* calls on this stream — then a REDUCE launch needs no memset in front of it
+   (the fold's last CTA returns its ticket word to zero; SCAN launches zero what they use themselves either way).
+   Saves one driver call per fold: ~2 us of the ~10 us a small-vector `+/a` costs end to end. */
+#define KGB_LAUNCH_WS_CLEAN 1
+int kgb_expr_launch_ex(kgb_expr* h, const void* const* args, int64_t n, void* out, void* workspace,
+                       size_t workspace_bytes, void* stream, int32_t flags);
 /* Host-only type inference: the element type a MAP program would produce for these argument kinds / dtypes (the
    NumPy promotion rules of numpy_backend.py's generated source).  No NVRTC, no GPU: lets the host answer `.dtype`
    for a deferred (not yet launched) elementwise expression. */

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libkgb200.so")
 F64, I64, F32, I32, B8 = 0, 1, 2, 3, 4
 ARG_ARRAY, ARG_SCALAR, ARG_DEVSCALAR = 0, 1, 2
 MODE_MAP, MODE_REDUCE, MODE_SCAN, MODE_SCANRED = 0, 1, 2, 3
+LAUNCH_WS_CLEAN = 1  # kgb_expr_launch_ex: the workspace was zero-filled once and is only ever used by this library
 RED_ADD, RED_MUL, RED_MAX, RED_MIN = 0, 1, 2, 3
 
 
@@ -37,6 +38,7 @@ SIGNATURES = {
                               _c.POINTER(_c.c_char_p)]),
     "kgb_expr_workspace_bytes": (_i32, [_vp, _i64, _psz]),
     "kgb_expr_launch": (_i32, [_vp, _c.POINTER(_vp), _i64, _vp, _vp, _sz, _vp]),
+    "kgb_expr_launch_ex": (_i32, [_vp, _c.POINTER(_vp), _i64, _vp, _vp, _sz, _vp, _i32]),
     "kgb_expr_infer": (_i32, [_pi32, _i32, _pi32, _pi32, _i32, _pi32]),
     "kgb_expr_out_dtype2": (_i32, [_vp]),
     "kgb_expr_source": (_c.c_char_p, [_vp]),

@@ -305,7 +305,7 @@ extern "C" __global__ void __launch_bounds__(KGB_BLOCK) KGB_KERNEL_NAME_S(const 
 // Per-thread V*UNROLL independent accumulators -> fixed tree -> warp shuffle -> block smem -> one
 // partial per block in ws -> the last block to finish folds the partials in index order.  The shape of
 // the tree depends only on (n, grid), so results are bit-reproducible run to run.
-// ws layout: [0,4) ticket (zeroed by the host wrapper), [64, 64+grid*sizeof(ACC)) partials.
+// ws layout: [32,36) ticket (zero on entry, zero again on exit), [64, 64+grid*sizeof(ACC)) partials.
 __device__ __forceinline__ KGB_ACC_T kgb_block_fold(KGB_ACC_T v, KGB_ACC_T* sh) {
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) {
@@ -413,7 +413,10 @@ template <int V> __device__ __forceinline__ void kgb_reduce_body(const KgbParams
     }
     KGB_ACC_T v = kgb_block_fold(acc[0], sh);
 
-    u32* ticket = (u32*)p.ws;
+    // the fold's ticket has its own word (ws + 32): the scan kernels keep their ticket at ws + 0 and leave it dirty, this
+    // one is returned to zero by the last CTA — a workspace that was zero-filled once stays valid for every later fold
+    // without a memset in front of the launch (kgb_expr_launch_ex, KGB_LAUNCH_WS_CLEAN)
+    u32* ticket = (u32*)((char*)p.ws + 32);
     volatile KGB_ACC_T* partial = (volatile KGB_ACC_T*)((char*)p.ws + 64);
 #ifdef KGB_HAS_RED2
     KGB_ACC2_T v2 = kgb_block_fold2(acc2[0], sh2);

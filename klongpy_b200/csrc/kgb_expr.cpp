@@ -824,6 +824,11 @@ extern "C" int kgb_expr_workspace_bytes(const kgb_expr* h, int64_t n, size_t* ou
 
 extern "C" int kgb_expr_launch(kgb_expr* h, const void* const* args, int64_t n, void* out, void* workspace,
                                size_t workspace_bytes, void* stream) {
+    return kgb_expr_launch_ex(h, args, n, out, workspace, workspace_bytes, stream, 0);
+}
+
+extern "C" int kgb_expr_launch_ex(kgb_expr* h, const void* const* args, int64_t n, void* out, void* workspace,
+                                  size_t workspace_bytes, void* stream, int32_t flags) {
     KGB_REQUIRE(h && (out || n == 0), "kgb_expr_launch: null handle / output");
     KGB_REQUIRE(h->device == current_device(), "kgb_expr_launch: handle compiled for device %d, thread bound to %d",
                 h->device, current_device());
@@ -863,7 +868,9 @@ extern "C" int kgb_expr_launch(kgb_expr* h, const void* const* args, int64_t n, 
         grid = fold_grid(h, n, aligned);
     } else if (h->mode == KGB_MODE_REDUCE) {
         grid = fold_grid(h, n, aligned);
-        KGB_CUDA_CHECK(cudaMemsetAsync(workspace, 0, 64, st));
+        // the fold's ticket (ws + 32) must be zero on entry; the kernel's last CTA zeroes it again, so a caller that
+        // zero-filled the workspace once and only ever hands it to this library can skip the memset (one driver call)
+        if (!(flags & KGB_LAUNCH_WS_CLEAN)) KGB_CUDA_CHECK(cudaMemsetAsync(workspace, 0, 64, st));
     } else {
         const size_t tiles = (size_t)((n + scan_tile(h) - 1) / scan_tile(h));
         KGB_REQUIRE(tiles < 0xffffffffull, "kgb_expr_launch: too many scan tiles");

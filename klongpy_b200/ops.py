@@ -325,7 +325,7 @@ def run(code, args, mode=_lib.MODE_MAP, red=0, code2=None, red2=0, out_shape=Non
         return DeviceArray(out)  # empty MAP / SCAN: nothing to launch
     na = len(ptrs)
     argv = _ARGV[na](*ptrs) if na < len(_ARGV) else (ctypes.c_void_p * na)(*ptrs)
-    rc = lib.kgb_expr_launch(h, argv, n, out.data_ptr(), ws_ptr, ws_bytes, stream)
+    rc = lib.kgb_expr_launch_ex(h, argv, n, out.data_ptr(), ws_ptr, ws_bytes, stream, _lib.LAUNCH_WS_CLEAN)
     if rc:
         _lib.check(rc, "kgb_expr_launch")
     return DeviceArray(out)
@@ -443,7 +443,7 @@ class FastStage:
             ws_ptr = _scratch(dev, stream, wsb)
         na = len(ptrs)
         argv = _ARGV[na](*ptrs) if na < len(_ARGV) else (ctypes.c_void_p * na)(*ptrs)
-        rc = lib.kgb_expr_launch(h, argv, n, out.data_ptr(), ws_ptr, wsb, stream)
+        rc = lib.kgb_expr_launch_ex(h, argv, n, out.data_ptr(), ws_ptr, wsb, stream, _lib.LAUNCH_WS_CLEAN)
         if rc:
             _lib.check(rc, "kgb_expr_launch")
         if self.code2:
@@ -477,14 +477,16 @@ def _compile_pair(lib, device, code_t, code2_t, kinds, dts, red, red2):
 _scratch_cache = {}
 
 
-def _scratch(device, stream, nbytes):
-    """Fold / scan scratch (partials, tile states) for one launch: ONE growing buffer per (device, stream), reused by
-    every launch on that stream — the library zeroes what it needs inside the launch and launches on a stream are
-    ordered, so consecutive kernels can share it (a torch.empty per call was a third of the host time of a small fold)."""
-    key = (device.index, stream.value if stream is not None else None)
+def _scratch(device, stream, nbytes, owner="expr"):
+    """Fold / scan scratch (partials, tile states) for one launch: ONE growing buffer per (device, stream, owner), reused
+    by every launch on that stream — launches on a stream are ordered, so consecutive kernels can share it (a torch.empty
+    per call was a third of the host time of a small fold).  The expression kernels' buffer is zero-filled ONCE and never
+    lent to anything else: folds keep their ticket word zero between launches (KGB_LAUNCH_WS_CLEAN), scans zero what
+    they use themselves.  Other kernels (stream compaction) get their own buffer."""
+    key = (device.index, stream.value if stream is not None else None, owner)
     buf = _scratch_cache.get(key)
     if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(int(nbytes), 1 << 16), dtype=torch.uint8, device=device)
+        buf = torch.zeros(max(int(nbytes), 1 << 16), dtype=torch.uint8, device=device)
         _scratch_cache[key] = buf
     return buf.data_ptr()
 
@@ -538,8 +540,8 @@ def reduce2(code, red, code2, red2, args):
     wsb = ctypes.c_size_t()
     _lib.check(lib.kgb_expr_workspace_bytes(h, n, ctypes.byref(wsb)), "kgb_expr_workspace_bytes")
     argv = (ctypes.c_void_p * max(len(args), 1))(*[c[3] for c in cls])
-    _lib.check(lib.kgb_expr_launch(h, argv, n, buf.data_ptr(), _scratch(device, stream, wsb.value), wsb.value, stream),
-               "kgb_expr_launch")
+    _lib.check(lib.kgb_expr_launch_ex(h, argv, n, buf.data_ptr(), _scratch(device, stream, wsb.value), wsb.value, stream,
+                                      _lib.LAUNCH_WS_CLEAN), "kgb_expr_launch")
     return DeviceArray(buf[:8].view(_K2T[od]).reshape(())), DeviceArray(buf[8:].view(_K2T[od2]).reshape(()))
 
 
@@ -895,7 +897,7 @@ def _select(fn_name, a, needle=None):
     cnt_np[0] = -1
     wsb = ctypes.c_size_t()
     _lib.check(lib.kgb_select_workspace_bytes(n, ctypes.byref(wsb)))
-    ws_ptr = _scratch(dev, stream, wsb.value)
+    ws_ptr = _scratch(dev, stream, wsb.value, "select")
     if fn_name == "find":
         _lib.check(lib.kgb_find_equal(a._t.data_ptr(), kdt, n, ctypes.addressof(needle), pos.data_ptr(),
                                       cnt.data_ptr(), ws_ptr, wsb.value, stream), "kgb_find_equal")

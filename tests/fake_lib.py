@@ -251,6 +251,9 @@ class FakeLib:
         out._obj.value = 64
         return 0
 
+    def kgb_expr_launch_ex(self, h, argv, n, out, ws, wsb, stream, flags):
+        return self.kgb_expr_launch(h, argv, n, out, ws, wsb, stream)
+
     def kgb_expr_launch(self, h, argv, n, out, ws, wsb, stream):
         e = self.exprs[_addr(h) - 1]
         args = []
