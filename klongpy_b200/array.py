@@ -44,6 +44,26 @@ def kgb_dtype(t):
         raise TypeError(f"tensor dtype {t.dtype} is not supported by libkgb200") from None
 
 
+# ops / lazy import this module, so they are bound on first use — ONCE: an `from . import ops` statement inside every
+# operator method costs ~1 us of import machinery per call, a tenth of a small-vector launch
+_ops = None
+_lazy = None
+
+
+def _bind_ops():
+    global _ops
+    from . import ops
+    _ops = ops
+    return ops
+
+
+def _bind_lazy():
+    global _lazy
+    from . import lazy
+    _lazy = lazy
+    return lazy
+
+
 class DeviceArray:
     """N-d array living in B200 HBM.  Immutable from the verbs' point of view (results are fresh arrays)."""
 
@@ -68,8 +88,7 @@ class DeviceArray:
     def _t(self):
         """The backing tensor.  Touching it materialises a deferred expression (one fused kernel)."""
         if self._tensor is None:
-            from . import lazy
-            self._tensor = lazy.materialize(self._node)
+            self._tensor = (_lazy or _bind_lazy()).materialize(self._node)
             self._node = None
         return self._tensor
 
@@ -171,30 +190,30 @@ class DeviceArray:
     def reshape(self, *shape):
         if len(shape) == 1 and isinstance(shape[0], (tuple, list)):
             shape = tuple(shape[0])
-        from . import ops
+        ops = _ops or _bind_ops()
         return DeviceArray(ops.contiguous(self)._t.reshape(*shape))
 
     def flatten(self):
-        from . import ops
+        ops = _ops or _bind_ops()
         return DeviceArray(ops.contiguous(self)._t.reshape(-1))
 
     ravel = flatten
 
     def copy(self):
-        from . import ops
+        ops = _ops or _bind_ops()
         return ops.copy(self)
 
     def astype(self, dtype, copy=True):
-        from . import ops
+        ops = _ops or _bind_ops()
         return ops.astype(self, dtype)
 
     def __getitem__(self, key):
-        from . import ops
+        ops = _ops or _bind_ops()
         return ops.getitem(self, key)
 
     # ------------------------------------------------------------------ arithmetic -> fused kernels
     def _bin(self, other, op, reflected=False):
-        from . import ops
+        ops = _ops or _bind_ops()
         if isinstance(other, (list, tuple)):
             other = ops.asarray(other, device=self.device)
         if not ops.is_operand(other):
@@ -223,30 +242,30 @@ class DeviceArray:
     def __ne__(self, o): return self._bin(o, "ne_b")
 
     def __neg__(self):
-        from . import ops
+        ops = _ops or _bind_ops()
         return ops.unary("neg", self)
 
     def __pos__(self):
         return self
 
     def __abs__(self):
-        from . import ops
+        ops = _ops or _bind_ops()
         return ops.unary("abs", self)
 
     def __invert__(self):
-        from . import ops
+        ops = _ops or _bind_ops()
         return ops.unary("not_b", self)
 
     def trunc(self):
-        from . import ops
+        ops = _ops or _bind_ops()
         return ops.unary("trunc", self)
 
     def all(self):
-        from . import ops
+        ops = _ops or _bind_ops()
         return ops.all_(self)
 
     def any(self):
-        from . import ops
+        ops = _ops or _bind_ops()
         return ops.any_(self)
 
     # numpy ufuncs applied to device arrays (np.float64(2) * a, np.equal(a, b), np.add.reduce(a) ...) run on the device
@@ -262,7 +281,7 @@ class DeviceArray:
               "arctan": "atan", "floor_divide": "floordiv", "remainder": "mod", "mod": "mod"}
 
     def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
-        from . import ops
+        ops = _ops or _bind_ops()
         name = self._UFUNC.get(ufunc.__name__)
         if name is not None and not kwargs:
             if method == "__call__" and all(ops.is_operand(x) for x in inputs):
@@ -285,7 +304,7 @@ class DeviceArray:
 
     def _fold(self, name, axis):
         # ndarray.sum/max/min: axis=None folds EVERY element, axis=0 the leading axis; other axes are not on the path
-        from . import ops
+        ops = _ops or _bind_ops()
         if axis is None:
             return ops.reduce(name, self.flatten() if self.ndim > 1 else self)
         if axis in (0, -self.ndim) and self.ndim >= 1:
@@ -302,5 +321,5 @@ class DeviceArray:
         return self._fold("min", axis)
 
     def argsort(self, kind=None):
-        from . import ops
+        ops = _ops or _bind_ops()
         return ops.argsort(self)

@@ -61,31 +61,50 @@ class GradeNode:
         self.args, self.code = [], ()
 
 
-def _is_lazy(a):
+_DA = None   # klongpy_b200.array.DeviceArray / klongpy_b200.ops, bound on first use (they import this module's users)
+_OPS = None
+
+
+def _bind():
+    global _DA, _OPS
+    from . import ops
     from .array import DeviceArray
-    return isinstance(a, DeviceArray) and a._tensor is None
+    _DA, _OPS = DeviceArray, ops
+    return ops
+
+
+def _is_lazy(a):
+    if _DA is None:
+        _bind()
+    return isinstance(a, _DA) and a._tensor is None
 
 
 def inline(code, args):
     """Expand deferred operands into `code` (postfix over `args`).  Returns (code, args) over leaf operands only."""
-    if not any(_is_lazy(a) for a in args):
+    if _DA is None:
+        _bind()
+    DA = _DA
+    lz = [isinstance(a, DA) and a._tensor is None for a in args]   # which operands are deferred (looked at once)
+    if True not in lz:
         return list(code), list(args)
-    from . import ops
+    ops = _OPS
+    OP_ARG, LIT_I, LIT_F = ops.OP_ARG, ops.OP_LIT_I64, ops.OP_LIT_F64
     new_args, index_of = [], {}
 
     def leaf(a):
         k = id(a)
-        if k not in index_of:
-            index_of[k] = len(new_args)
+        i = index_of.get(k)
+        if i is None:
+            i = index_of[k] = len(new_args)
             new_args.append(a)
-        return index_of[k]
+        return i
 
     # decide which deferred operands can be inlined (first consumer, and the result must stay within the caps)
-    budget_args = MAX_ARGS - sum(1 for a in args if not _is_lazy(a))
+    budget_args = MAX_ARGS - lz.count(False)
     budget_code = MAX_CODE - len(code)
     plan = []
-    for a in args:
-        if _is_lazy(a):
+    for a, z in zip(args, lz):
+        if z:
             nd = a._node
             ok = nd.uses == 0 and len(nd.args) <= budget_args and len(nd.code) <= budget_code
             if ok:
@@ -96,31 +115,37 @@ def inline(code, args):
             plan.append(False)
     out, i = [], 0
     code = list(code)
-    while i < len(code):
+    ncode = len(code)
+    while i < ncode:
         w = code[i]
-        if w == ops.OP_ARG:
-            a = args[code[i + 1]]
-            if _is_lazy(a) and plan[code[i + 1]]:
+        if w == OP_ARG:
+            ai = code[i + 1]
+            a = args[ai]
+            if plan[ai]:
                 nd = a._node
                 nd.uses += 1
-                sub, j = list(nd.code), 0
-                while j < len(sub):
+                sub, j = nd.code, 0
+                nsub = len(sub)
+                nargs = nd.args
+                while j < nsub:
                     v = sub[j]
-                    if v == ops.OP_ARG:
-                        out += [ops.OP_ARG, leaf(nd.args[sub[j + 1]])]
+                    if v == OP_ARG:
+                        out.append(OP_ARG)
+                        out.append(leaf(nargs[sub[j + 1]]))
                         j += 2
-                    elif v in (ops.OP_LIT_I64, ops.OP_LIT_F64):
+                    elif v == LIT_I or v == LIT_F:
                         out += sub[j:j + 3]
                         j += 3
                     else:
                         out.append(v)
                         j += 1
             else:
-                if _is_lazy(a):
+                if lz[ai]:
                     a._t  # noqa: B018 - materialise: used twice, or the fused program would get too large
-                out += [ops.OP_ARG, leaf(a)]
+                out.append(OP_ARG)
+                out.append(leaf(a))
             i += 2
-        elif w in (ops.OP_LIT_I64, ops.OP_LIT_F64):
+        elif w == LIT_I or w == LIT_F:
             out += code[i:i + 3]
             i += 3
         else:
@@ -130,7 +155,7 @@ def inline(code, args):
 
 
 def _infer(code, args, device):
-    from . import ops
+    ops = _OPS or _bind()
     lib, _ = ops._lib_for(device)
     cls = [ops._classify_meta(a) for a in args]
     key = (tuple(code), tuple(cls))
@@ -150,7 +175,9 @@ def _infer(code, args, device):
 def defer(code, args):
     """A deferred DeviceArray for the MAP program `code` over leaf operands `args`, or None when it cannot be
     deferred (no device operand, too many arguments)."""
-    from .array import DeviceArray
+    if _DA is None:
+        _bind()
+    DeviceArray = _DA
     device, shape = None, None
     for a in args:
         if isinstance(a, DeviceArray):

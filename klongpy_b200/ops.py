@@ -178,6 +178,16 @@ def _classify_meta(x):
 
 from . import sharded as _sharded  # noqa: E402 - imports only array.py; ops is imported lazily inside its functions
 
+_autograd_mod = None
+
+
+def _bind_autograd():
+    global _autograd_mod
+    from . import autograd
+    _autograd_mod = autograd
+    return autograd
+
+
 _ARGV = [ctypes.c_void_p * max(k, 1) for k in range(17)]  # argument-pointer array types, by argument count
 _lazy = None  # klongpy_b200.lazy, imported on first use (it imports this module)
 
@@ -275,7 +285,7 @@ def run(code, args, mode=_lib.MODE_MAP, red=0, code2=None, red2=0, out_shape=Non
             kinds.append(_lib.ARG_SCALAR)
             ptrs.append(ctypes.addressof(c))
     if grad and torch.is_grad_enabled():
-        from . import autograd  # operands on the autograd tape: same launch, recorded as one node
+        autograd = _autograd_mod or _bind_autograd()  # operands on the autograd tape: same launch, recorded as one node
         return autograd.run_differentiable(code, args, mode, red, code2, red2, out_shape, dev_param)
     if mixed:
         # NumPy broadcasting between arrays of different shapes (`[[1]]&[2]`, tests/kgtests/language/test_broadcasting.kg):
@@ -513,7 +523,7 @@ def reduce2(code, red, code2, red2, args):
         if r is not NotImplemented:
             return r
     if torch.is_grad_enabled() and any(isinstance(a, DeviceArray) and a._t.requires_grad for a in args):
-        from . import autograd  # one two-output node on the tape (raises NotDifferentiable for folds other than +/)
+        autograd = _autograd_mod or _bind_autograd()  # one two-output node on the tape (raises NotDifferentiable for folds other than +/)
         return autograd.run_differentiable2(code, red, code2, red2, args, device)
     lib, stream = _lib_for(device)
     cls = [_classify(a, device) for a in args]
