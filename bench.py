@@ -579,6 +579,12 @@ def primitive_table(be, ops, dist, time_kernel, dev, peak, world, rank):
     out["grouped_min_mean_max_10k_1e9"] = prim_row(
         nb * world, over_ranks(time_kernel(lambda: dist.sharded_groupagg(st_b, tp_b, 10_000), 3)), 16, peak * world,
         n_gpus=world, rows_per_gpu=nb, check=check_groupagg(st_b, tp_b, 10_000))
+    if world > 1:
+        # config 4 in BASELINE.json's own words: the hash-partitioned all_to_all exchange across the GPUs
+        out["grouped_min_mean_max_10k_1e9_alltoall"] = prim_row(
+            nb * world, over_ranks(time_kernel(lambda: dist.sharded_groupagg(st_b, tp_b, 10_000, exchange="alltoall"), 3)),
+            16, peak * world, n_gpus=world, rows_per_gpu=nb,
+            note="station s owned by rank s mod w: to_owners, ONE all_to_all, fold in rank order, ONE all_gather, from_owners")
     del tp_b
     if world == 1:
         # config 3 at its upper size: 1e9 int64 keys
@@ -588,7 +594,7 @@ def primitive_table(be, ops, dist, time_kernel, dev, peak, world, rank):
         del st_b
         kp = DeviceArray(torch.randperm(nb, device=dev, generator=g))
         out["grade_up_perm_1e9"] = prim_row(nb, time_kernel(lambda: ops.argsort(kp), 2), 16, peak,
-                                            model_bytes_per_elem=16 + 16 * 3, passes=3)
+                                            model_bytes_per_elem=16 + 16 * 4, passes=4)  # 30 live bits: 9+7+7+7
         del kp
     else:
         del st_b

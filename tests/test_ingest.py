@@ -192,6 +192,33 @@ def test_gpu_ingest_every_measurement_value_and_row_estimate_miss():
                                      ingest.DICT_CAPACITY, ctypes.byref(r), ctypes.byref(nn), ws.data_ptr(), wsb.value, stream), "parse")
 
 
+@pytest.mark.gpu
+def test_gpu_ingest_text_lengths_around_tile_edges():
+    """Texts whose LAST newline falls exactly on, one before and one after a 65536-byte tile edge (the one-pass kernel's
+    tiles, look-back chain and the final-newline check all key on that position), for one to three tiles, with short
+    and near-maximal names around the edge."""
+    from klongpy_b200 import ingest
+    rng = np.random.default_rng(17)
+    names = ["n%d" % k for k in range(50)] + ["".join(rng.choice(list("abcdefgh"), int(k))) for k in rng.integers(100, 250, 20)]
+    for target in (65535, 65536, 65537, 131071, 131072, 131073, 196607, 196608, 196609):
+        out, size = [], 0
+        while size < target - 300:
+            line = f"{names[int(rng.integers(0, len(names)))]};{int(rng.integers(-99, 100))}.{int(rng.integers(0, 10))}\n"
+            out.append(line)
+            size += len(line)
+        while target - size > 260:                       # leave a last line of 6 .. 260 bytes
+            line = f"pad;{int(rng.integers(0, 10))}.{int(rng.integers(0, 10))}\n"
+            out.append(line)
+            size += len(line)
+        rest = target - size                             # the last line: name of rest - 5 bytes + ";1.5\n"
+        out.append("z" * (rest - 5) + ";1.5\n")
+        text = "".join(out).encode()
+        assert len(text) == target
+        gi, gt, gn = ingest.parse(text, device="cuda:0")
+        rn, ri, rt = O.parse_1brc(text)
+        assert gn == rn and np.array_equal(gi.to_numpy(), ri) and np.array_equal(gt.to_numpy(), rt), target
+
+
 def _file_case(tmp_path, rows, n_names, tail_newline=True, seed=3):
     rng = np.random.default_rng(seed)
     text = _synthetic(rng, rows, n_names)
