@@ -240,6 +240,15 @@ int kgb_groupagg_workspace_bytes(int64_t n, int64_t n_groups, size_t* out_bytes)
 int kgb_groupagg_f64(const int64_t* keys, const double* vals, int64_t n, int64_t n_groups,
                      double* min_out, double* max_out, double* sum_out, int64_t* count_out,
                      int32_t accumulate, void* workspace, size_t workspace_bytes, void* stream);
+/* The same without the synchronising read-back of the "key outside [0, n_groups)" flag: nothing blocks the host, so a
+   caller that follows the aggregation with an exchange (dist.sharded_groupagg: NCCL collectives + fold) enqueues it
+   while the aggregation kernel is still running.  kgb_groupagg_status(workspace, n_groups, stream) collects the flag
+   later (one 4-byte read, synchronises `stream`; KGB_EINVAL if a key was out of range); `workspace` must stay
+   untouched until then. */
+int kgb_groupagg_f64_async(const int64_t* keys, const double* vals, int64_t n, int64_t n_groups, double* min_out,
+                           double* max_out, double* sum_out, int64_t* count_out, int32_t accumulate, void* workspace,
+                           size_t workspace_bytes, void* stream);
+int kgb_groupagg_status(const void* workspace, int64_t n_groups, void* stream);
 /* merge step of the multi-GPU exchange: dst tables (op)= src tables, elementwise over G entries */
 int kgb_groupagg_merge(double* min_io, double* max_io, double* sum_io, int64_t* count_io,
                        const double* min_in, const double* max_in, const double* sum_in,

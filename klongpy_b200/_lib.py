@@ -59,6 +59,8 @@ SIGNATURES = {
     "kgb_array_equal": (_i32, [_vp, _vp, _i32, _i64, _vp, _vp]),
     "kgb_groupagg_workspace_bytes": (_i32, [_i64, _i64, _psz]),
     "kgb_groupagg_f64": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _sz, _vp]),
+    "kgb_groupagg_f64_async": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _sz, _vp]),
+    "kgb_groupagg_status": (_i32, [_vp, _i64, _vp]),
     "kgb_groupagg_merge": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "kgb_groupagg_fold": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "kgb_groupagg_to_owners": (_i32, [_vp, _i64, _i64, _vp, _vp]),

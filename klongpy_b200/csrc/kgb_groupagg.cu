@@ -540,9 +540,40 @@ extern "C" int kgb_groupagg_workspace_bytes(int64_t n, int64_t n_groups, size_t*
     return KGB_OK;
 }
 
+static int groupagg_run(const int64_t* keys, const double* vals, int64_t n, int64_t n_groups, double* min_out, double* max_out,
+                        double* sum_out, int64_t* count_out, int32_t accumulate, void* workspace, size_t workspace_bytes,
+                        void* stream, bool check_now);
+
 extern "C" int kgb_groupagg_f64(const int64_t* keys, const double* vals, int64_t n, int64_t n_groups, double* min_out,
                                 double* max_out, double* sum_out, int64_t* count_out, int32_t accumulate,
                                 void* workspace, size_t workspace_bytes, void* stream) {
+    return groupagg_run(keys, vals, n, n_groups, min_out, max_out, sum_out, count_out, accumulate, workspace, workspace_bytes,
+                        stream, true);
+}
+
+extern "C" int kgb_groupagg_f64_async(const int64_t* keys, const double* vals, int64_t n, int64_t n_groups, double* min_out,
+                                      double* max_out, double* sum_out, int64_t* count_out, int32_t accumulate,
+                                      void* workspace, size_t workspace_bytes, void* stream) {
+    return groupagg_run(keys, vals, n, n_groups, min_out, max_out, sum_out, count_out, accumulate, workspace, workspace_bytes,
+                        stream, false);
+}
+
+extern "C" int kgb_groupagg_status(const void* workspace, int64_t n_groups, void* stream) {
+    KGB_REQUIRE(current_device() >= 0, "kgb_init() has not been called on this thread");
+    KGB_REQUIRE(n_groups >= 0, "kgb_groupagg_status: negative size");
+    if (n_groups == 0) return KGB_OK;
+    KGB_REQUIRE(workspace, "kgb_groupagg_status: null workspace");
+    AggWs a = carve_agg(const_cast<void*>(workspace), n_groups);
+    int err = 0;
+    KGB_CUDA_CHECK(cudaMemcpyAsync(&err, a.err, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    KGB_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+    KGB_REQUIRE(err == 0, "kgb_groupagg_f64: key outside [0, n_groups)");
+    return KGB_OK;
+}
+
+static int groupagg_run(const int64_t* keys, const double* vals, int64_t n, int64_t n_groups, double* min_out, double* max_out,
+                        double* sum_out, int64_t* count_out, int32_t accumulate, void* workspace, size_t workspace_bytes,
+                        void* stream, bool check_now) {
     KGB_REQUIRE(current_device() >= 0, "kgb_init() has not been called on this thread");
     KGB_REQUIRE(n >= 0 && n_groups >= 0, "kgb_groupagg_f64: negative size");
     if (n_groups == 0) return KGB_OK;
@@ -636,6 +667,7 @@ extern "C" int kgb_groupagg_f64(const int64_t* keys, const double* vals, int64_t
     groupagg_finalize<<<(unsigned)((n_groups + 255) / 256), 256, 0, st>>>(a, n_groups, min_out, max_out, sum_out,
                                                                          (i64*)count_out, accumulate, nparts);
     KGB_CUDA_CHECK(cudaGetLastError());
+    if (!check_now) return KGB_OK;  // kgb_groupagg_f64_async: the caller collects the flag with kgb_groupagg_status
     int err = 0;
     // out-of-range keys are a caller bug: report it (one 4-byte read after the kernels)
     KGB_CUDA_CHECK(cudaMemcpyAsync(&err, a.err, 4, cudaMemcpyDeviceToHost, st));

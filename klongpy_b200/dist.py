@@ -154,9 +154,12 @@ def sharded_groupagg(keys, vals, n_groups, exchange="auto"):
     i64, f64 = torch.int64, torch.float64
     block = torch.empty((4, G), dtype=i64, device=dev)
     tabs = (block[0].view(f64), block[1].view(f64), block[2].view(f64), block[3])
-    ops.groupagg(keys, vals, G, tables=tabs, accumulate=False)
     if w == 1:
+        ops.groupagg(keys, vals, G, tables=tabs, accumulate=False)
         return tuple(DeviceArray(t) for t in tabs)
+    # the aggregation is enqueued WITHOUT waiting for its error flag: the exchange below (host-side NCCL enqueue, two
+    # small kernels) is issued while the aggregation kernel is still running; the flag is collected at the end
+    _, check = ops.groupagg(keys, vals, G, tables=tabs, accumulate=False, defer_check=True)
     lib, stream = ops._lib_for(dev)
     if exchange == "auto":
         exchange = "allgather" if w * 32 * G <= ALLGATHER_LIMIT_BYTES else "alltoall"
@@ -182,6 +185,7 @@ def sharded_groupagg(keys, vals, n_groups, exchange="auto"):
                                                 o[3].data_ptr(), stream), "kgb_groupagg_from_owners")
     else:
         raise ValueError(f"sharded_groupagg: unknown exchange {exchange!r}")
+    check()
     return tuple(DeviceArray(t) for t in o)
 
 

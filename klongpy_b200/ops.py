@@ -1073,9 +1073,11 @@ def array_equal(a, b):
     return bool(flag.item())
 
 
-def groupagg(keys, vals, n_groups, tables=None, accumulate=None):
+def groupagg(keys, vals, n_groups, tables=None, accumulate=None, defer_check=False):
     """1brc-style grouped (min, max, sum, count) (examples/1brc/worker.kg:3-5).  `tables`: four preallocated result
-    arrays; they are merged into (the `merge` step) unless accumulate=False."""
+    arrays; they are merged into (the `merge` step) unless accumulate=False.  defer_check=True does not wait for the
+    "key outside [0, n_groups)" flag: -> (tables, check) where check() collects it later (and raises) — the caller can
+    enqueue more work behind the aggregation first (dist.sharded_groupagg: the exchange)."""
     if _sharded.ACTIVE and (_sharded.is_sharded(keys) or _sharded.is_sharded(vals)) and tables is None:
         r = _sharded.groupagg(keys, vals, n_groups)
         if r is not NotImplemented:
@@ -1100,6 +1102,14 @@ def groupagg(keys, vals, n_groups, tables=None, accumulate=None):
     wsb = ctypes.c_size_t()
     _lib.check(lib.kgb_groupagg_workspace_bytes(n, G, ctypes.byref(wsb)))
     ws = _ws(wsb.value, dev)
+    if defer_check:
+        _lib.check(lib.kgb_groupagg_f64_async(keys._t.data_ptr(), vals._t.data_ptr(), n, G, tables[0].data_ptr(),
+                                              tables[1].data_ptr(), tables[2].data_ptr(), tables[3].data_ptr(),
+                                              1 if acc else 0, ws.data_ptr(), wsb.value, stream), "kgb_groupagg_f64_async")
+
+        def check(ws=ws, keep=(keys, vals)):
+            _lib.check(lib.kgb_groupagg_status(ws.data_ptr(), G, stream), "kgb_groupagg_f64")
+        return tuple(DeviceArray(t) for t in tables), check
     _lib.check(lib.kgb_groupagg_f64(keys._t.data_ptr(), vals._t.data_ptr(), n, G, tables[0].data_ptr(),
                                     tables[1].data_ptr(), tables[2].data_ptr(), tables[3].data_ptr(),
                                     1 if acc else 0, ws.data_ptr(), wsb.value, stream), "kgb_groupagg_f64")

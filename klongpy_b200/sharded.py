@@ -200,16 +200,20 @@ def groupagg(keys, vals, n_groups):
     devs, sizes = lay
     G, k = int(n_groups), len(devs)
     i64, f64 = torch.int64, torch.float64
-    blocks = []
+    blocks, checks = [], []
     for r in range(k):
         block = torch.empty((4, G), dtype=i64, device=devs[r])
         tabs = (block[0].view(f64), block[1].view(f64), block[2].view(f64), block[3])
-        ops.groupagg(shards_of(keys)[r], shards_of(vals)[r], G, tables=tabs, accumulate=False)
+        # no wait for the error flag here: device r's kernel runs while device r + 1's is being enqueued
+        _, chk = ops.groupagg(shards_of(keys)[r], shards_of(vals)[r], G, tables=tabs, accumulate=False, defer_check=True)
         blocks.append(block)
+        checks.append(chk)
     allb = torch.stack([b.to(devs[0]) for b in blocks])   # k x 4 x G lanes on device 0 (320 KB each at 10 k stations)
     out = torch.empty((4, G), dtype=i64, device=devs[0])
     o = (out[0].view(f64), out[1].view(f64), out[2].view(f64), out[3])
     lib, stream = ops._lib_for(devs[0])
     _lib.check(lib.kgb_groupagg_fold(allb.data_ptr(), k, G, 4 * G, o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(),
                                      o[3].data_ptr(), stream), "kgb_groupagg_fold")
+    for chk in checks:
+        chk()
     return tuple(DeviceArray(t) for t in o)

@@ -380,6 +380,13 @@ class FakeLib:
         view(flag, 1, I32)[0] = int(np.array_equal(view(a, n, dt), view(b, n, dt)))
         return 0
 
+    def kgb_groupagg_f64_async(self, keys, vals, n, G, mn, mx, sm, ct, acc, ws, wsb, stream):
+        self._agg_status = self.kgb_groupagg_f64(keys, vals, n, G, mn, mx, sm, ct, acc, ws, wsb, stream)
+        return 0
+
+    def kgb_groupagg_status(self, ws, G, stream):
+        return getattr(self, "_agg_status", 0)
+
     def kgb_groupagg_f64(self, keys, vals, n, G, mn, mx, sm, ct, acc, ws, wsb, stream):
         r = O.grouped_stats(view(keys, n, I64), view(vals, n, F64), G)
         outs = (view(mn, G, F64), view(mx, G, F64), view(sm, G, F64), view(ct, G, I64))
