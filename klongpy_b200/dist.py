@@ -87,13 +87,20 @@ def exchange_fold_and_offset(part, total, red, scan_red):
     if world() == 1:
         return part, None
     w = world()
-    # raw bytes: the two values may differ in dtype
-    pair = torch.cat([part._t.reshape(1).view(torch.uint8), total._t.reshape(1).view(torch.uint8)])
-    allp = torch.empty(16 * w, dtype=torch.uint8, device=pair.device)
+    # raw 8-byte lanes: the two values may differ in dtype.  ops.reduce2 writes both results side by side into one
+    # 16-byte buffer: that buffer IS the message (no concatenation kernel in the dependent chain between the fold and
+    # the scan); one transposing copy then yields both columns contiguous
+    pt, tt = part._t, total._t
+    if (pt.untyped_storage().data_ptr() == tt.untyped_storage().data_ptr() and pt.element_size() == 8 and
+            tt.element_size() == 8 and tt.storage_offset() == pt.storage_offset() + 1):
+        pair = torch.empty(0, dtype=torch.int64, device=pt.device).set_(pt.untyped_storage(), pt.storage_offset(), (2,))
+    else:
+        pair = torch.cat([pt.reshape(1).view(torch.int64), tt.reshape(1).view(torch.int64)])
+    allp = torch.empty(2 * w, dtype=torch.int64, device=pair.device)
     td.all_gather_into_tensor(allp, pair)
-    allp = allp.reshape(w, 16)
-    parts = DeviceArray(allp[:, :8].contiguous().view(part._t.dtype).reshape(w))
-    totals = DeviceArray(allp[:, 8:].contiguous().view(total._t.dtype).reshape(w))
+    cols = allp.reshape(w, 2).t().contiguous()
+    parts = DeviceArray(cols[0].view(pt.dtype))
+    totals = DeviceArray(cols[1].view(tt.dtype))
     fold = ops.run([ops.OP_ARG, 0], [parts], mode=_lib.MODE_REDUCE, red=red)
     r = rank()
     off = None if r == 0 else ops.run([ops.OP_ARG, 0], [DeviceArray(totals._t[:r])], mode=_lib.MODE_REDUCE, red=scan_red)
