@@ -149,6 +149,13 @@ int kgb_device_sm_count(int device, int* out);
 int kgb_expr_compile(const int32_t* code, int32_t n_code, const int32_t* code2, int32_t n_code2,
                      const int32_t* arg_kinds, const int32_t* arg_dtypes, int32_t n_args, int32_t mode,
                      int32_t red_op, int32_t red_op2, kgb_expr** out_handle, int32_t* out_dtype);
+/* kgb_expr_compile for a two-output REDUCE (code + code2) with an EPILOGUE: `code3` is a program over two arguments —
+   argument 0 the finished first fold, argument 1 the second — evaluated once by the kernel's last CTA; the launch then
+   writes ONE value of type *out_dtype to `out` (`(+/p*s)%+/s`, compiler.py's VWAP example: both sums and the divide
+   in one launch instead of a fold kernel plus a one-thread kernel).  kgb_expr_out_dtype2 returns -1 for such handles. */
+int kgb_expr_compile_epi(const int32_t* code, int32_t n_code, const int32_t* code2, int32_t n_code2, const int32_t* code3,
+                         int32_t n_code3, const int32_t* arg_kinds, const int32_t* arg_dtypes, int32_t n_args,
+                         int32_t mode, int32_t red_op, int32_t red_op2, kgb_expr** out_handle, int32_t* out_dtype);
 /* Same code generation + NVRTC compile to an sm_100a cubin, but WITHOUT loading it: works on a box with
    no GPU (build check, host-logic tests).  *source_out stays valid until the next call on the thread. */
 int kgb_expr_check(const int32_t* code, int32_t n_code, const int32_t* code2, int32_t n_code2,

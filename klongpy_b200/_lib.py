@@ -34,6 +34,8 @@ SIGNATURES = {
     "kgb_device_sm_count": (_i32, [_i32, _pi32]),
     "kgb_expr_compile": (_i32, [_pi32, _i32, _pi32, _i32, _pi32, _pi32, _i32, _i32, _i32, _i32,
                                 _c.POINTER(_vp), _pi32]),
+    "kgb_expr_compile_epi": (_i32, [_pi32, _i32, _pi32, _i32, _pi32, _i32, _pi32, _pi32, _i32, _i32, _i32, _i32,
+                                    _c.POINTER(_vp), _pi32]),
     "kgb_expr_check": (_i32, [_pi32, _i32, _pi32, _i32, _pi32, _pi32, _i32, _i32, _i32, _i32, _pi32,
                               _c.POINTER(_c.c_char_p)]),
     "kgb_expr_workspace_bytes": (_i32, [_vp, _i64, _psz]),

@@ -452,9 +452,13 @@ template <int V> __device__ __forceinline__ void kgb_reduce_body(const KgbParams
         a2 = kgb_block_fold2(a2, sh2);
 #endif
         if (threadIdx.x == 0) {
+#ifdef KGB_HAS_EPI
+            *(KGB_EPI_T*)p.out = (KGB_EPI_T)(KGB_EPI(a, a2));  // ONE result: the epilogue of the two finished folds
+#else
             *(KGB_OUT_T*)p.out = (KGB_OUT_T)a;
 #ifdef KGB_HAS_RED2
             *(KGB_ACC2_T*)((char*)p.out + 8) = a2;  // second result in the next 8-byte slot
+#endif
 #endif
             *ticket = 0u;
         }

@@ -464,6 +464,7 @@ struct kgb_expr {
     int pipe_threads = 256, pipe_stages = 7, pipe_load = 2, pipe_park = 4, pipe_lw = 2, pipe_lbw = 1;
     int pipe_ctas_per_sm = 1;
     bool has_red2 = false;          // two-output reduce (second result at out + 8 bytes)
+    bool has_epi = false;           // two-output reduce whose last CTA combines both folds into ONE result (kgb_expr_compile_epi)
 };
 
 namespace kgb {
@@ -522,7 +523,8 @@ static size_t scan_smem_bytes(const kgb_expr* h) {
     return (size_t)h->sblock * ((size_t)h->sitems * sz + 16);
 }
 
-static int build_source(kgb_expr* h, const int32_t* code, int n_code, const int32_t* code2, int n_code2) {
+static int build_source(kgb_expr* h, const int32_t* code, int n_code, const int32_t* code2, int n_code2,
+                        const int32_t* code3 = nullptr, int n_code3 = 0) {
     Val v;
     if (!gen_expr(code, n_code, h->args, false, 0, &v)) return KGB_EINVAL;
     int res_dt = v.t.dt;
@@ -600,6 +602,18 @@ static int build_source(kgb_expr* h, const int32_t* code, int n_code, const int3
         m << "#define KGB_HAS_RED2 1\n#define KGB_ACC2_T " << ctype(h->acc2_dtype) << "\n";
         m << "#define KGB_EVALB(j) (" << cast(vb, h->acc2_dtype) << ")\n";
         m << fold_macro("KGB_RED2", h->red_op2) << fold_ident("KGB_RED2_IDENT", h->red_op2, h->acc2_dtype);
+        if (code3 && n_code3 > 0) {
+            // epilogue over the two finished folds (`(+/p*s)%+/s`: the divide), evaluated once by the last CTA: the
+            // program's argument 0 is the first fold, argument 1 the second; the kernel then has ONE result
+            std::vector<ArgInfo> eargs = {ArgInfo{KGB_ARG_DEVSCALAR, h->acc_dtype}, ArgInfo{KGB_ARG_DEVSCALAR, h->acc2_dtype}};
+            Val ve;
+            if (!gen_expr(code3, n_code3, eargs, false, 0, &ve)) return KGB_EINVAL;
+            h->has_epi = true;
+            h->out_dtype = ve.t.dt;
+            m << "#define KGB_HAS_EPI 1\n#define KGB_EPI_T " << ctype(ve.t.dt) << "\n#define KGB_EPI(s0, s1) (" << ve.s << ")\n";
+        }
+    } else if (code3 && n_code3 > 0) {
+        return set_error("an epilogue program needs a two-output reduce"), KGB_EINVAL;
     }
     if (h->mode == KGB_MODE_SCAN && code2 && n_code2 > 0) {
         // optional seed program over scalar arguments only (multi-GPU scans pass the shard's exclusive offset)
@@ -736,6 +750,14 @@ using namespace kgb;
 extern "C" int kgb_expr_compile(const int32_t* code, int32_t n_code, const int32_t* code2, int32_t n_code2,
                                 const int32_t* arg_kinds, const int32_t* arg_dtypes, int32_t n_args, int32_t mode,
                                 int32_t red_op, int32_t red_op2, kgb_expr** out_handle, int32_t* out_dtype) {
+    return kgb_expr_compile_epi(code, n_code, code2, n_code2, nullptr, 0, arg_kinds, arg_dtypes, n_args, mode, red_op, red_op2,
+                                out_handle, out_dtype);
+}
+
+extern "C" int kgb_expr_compile_epi(const int32_t* code, int32_t n_code, const int32_t* code2, int32_t n_code2,
+                                    const int32_t* code3, int32_t n_code3, const int32_t* arg_kinds,
+                                    const int32_t* arg_dtypes, int32_t n_args, int32_t mode, int32_t red_op,
+                                    int32_t red_op2, kgb_expr** out_handle, int32_t* out_dtype) {
     KGB_REQUIRE(code && n_code > 0 && out_handle, "kgb_expr_compile: null program");
     KGB_REQUIRE(n_args >= 0 && n_args <= KGB_MAX_ARGS, "kgb_expr_compile: %d arguments (max %d)", n_args, KGB_MAX_ARGS);
     KGB_REQUIRE(mode >= KGB_MODE_MAP && mode <= KGB_MODE_SCANRED, "kgb_expr_compile: bad mode %d", mode);
@@ -749,6 +771,7 @@ extern "C" int kgb_expr_compile(const int32_t* code, int32_t n_code, const int32
     if (n_args) key.append((const char*)arg_kinds, 4 * n_args).append((const char*)arg_dtypes, 4 * n_args);
     key.append((const char*)&n_code, 4).append((const char*)code, 4 * (size_t)n_code);
     if (code2 && n_code2 > 0) key.append((const char*)code2, 4 * (size_t)n_code2);
+    if (code3 && n_code3 > 0) key.append("|epi", 4).append((const char*)code3, 4 * (size_t)n_code3);
 
     std::lock_guard<std::mutex> lk(g_cache_mu);
     auto it = g_cache.find(key);
@@ -771,7 +794,7 @@ extern "C" int kgb_expr_compile(const int32_t* code, int32_t n_code, const int32
         }
         h->args.push_back(ArgInfo{k, dt});
     }
-    int rc = build_source(h, code, n_code, code2, n_code2);
+    int rc = build_source(h, code, n_code, code2, n_code2, code3, n_code3);
     if (rc == KGB_OK) rc = jit_compile(h, true);
     if (rc != KGB_OK) {
         delete h;
@@ -911,6 +934,6 @@ extern "C" int kgb_expr_infer(const int32_t* code, int32_t n_code, const int32_t
     return KGB_OK;
 }
 
-extern "C" int kgb_expr_out_dtype2(const kgb_expr* h) { return (h && h->has_red2) ? h->acc2_dtype : -1; }
+extern "C" int kgb_expr_out_dtype2(const kgb_expr* h) { return (h && h->has_red2 && !h->has_epi) ? h->acc2_dtype : -1; }
 extern "C" const char* kgb_expr_source(const kgb_expr* h) { return h ? h->source.c_str() : ""; }
 extern "C" const char* kgb_expr_kernel_name(const kgb_expr* h) { return h ? h->name_v.c_str() : ""; }

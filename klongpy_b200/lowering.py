@@ -234,6 +234,27 @@ def make_callable(ir):
         if st0.pair is None and st0.code2 is None and list(st0.slots) == list(range(n_params)) and \
                 st0.mode in (_lib.MODE_MAP, _lib.MODE_REDUCE, _lib.MODE_SCAN):
             fast = ops.FastStage(st0.code, st0.mode, st0.red)
+    # `(+/p*s)%+/s`: two folds that share one pass + an elementwise tree over exactly those two results -> ONE launch
+    # (kgb_expr_compile_epi: the last CTA of the two-output fold evaluates the epilogue)
+    fast_epi = None
+    if len(plan.stages) == 3:
+        sa, sb, sc = plan.stages
+        if sa.pair is not None and sa.pair[0] is sb and sc.mode == _lib.MODE_MAP and sc.code2 is None and \
+                sc.out_slot == plan.result_slot and sc.slots and set(sc.slots) <= {sa.out_slot, sb.out_slot}:
+            remap = [0 if sl == sa.out_slot else 1 for sl in sc.slots]
+            code3, i, src = [], 0, list(sc.code)
+            while i < len(src):
+                w = src[i]
+                if w == ops.OP_ARG:
+                    code3 += [w, remap[src[i + 1]]]
+                    i += 2
+                elif w in (ops.OP_LIT_I64, ops.OP_LIT_F64):
+                    code3 += src[i:i + 3]
+                    i += 3
+                else:
+                    code3.append(w)
+                    i += 1
+            fast_epi = (ops.FastStage(sa.code, _lib.MODE_REDUCE, sa.red, sa.pair[1], sb.red, code3), sa.pair[2])
     # inside the general loop every plain stage (and every paired fold) tries its own pre-resolved launcher first
     stage_fast = {}
     for st in plan.stages:
@@ -247,6 +268,13 @@ def make_callable(ir):
             raise TypeError(f"compiled expression takes {n_params} arguments ({len(args)} given)")
         if fast is not None:
             r = fast(args)
+            if r is not NotImplemented:
+                return r
+        if fast_epi is not None:
+            try:
+                r = fast_epi[0]([args[sl] for sl in fast_epi[1]])
+            except _lib.KgbError:
+                r = NotImplemented   # a narrow accumulator: the general path below sorts it out
             if r is not NotImplemented:
                 return r
         vals = list(args) + [None] * (plan.n_slots - n_params)

@@ -349,10 +349,11 @@ class FastStage:
     else returns NotImplemented and the caller goes through `run` / `reduce2` (same kernels, same handle cache: this is
     a shortcut through the host bookkeeping, not another path).  With `code2` the stage is the two-output fold
     (`(+/p*s)%+/s`: both sums in one pass) and the call returns two 0-d values."""
-    __slots__ = ("code", "code2", "mode", "red", "red2", "cache", "ws_bytes")
+    __slots__ = ("code", "code2", "code3", "mode", "red", "red2", "cache", "ws_bytes")
 
-    def __init__(self, code, mode, red, code2=None, red2=0):
+    def __init__(self, code, mode, red, code2=None, red2=0, code3=None):
         self.code, self.code2 = tuple(code), tuple(code2) if code2 else ()
+        self.code3 = tuple(code3) if code3 else ()   # epilogue over the two finished folds: ONE result, one launch
         self.mode, self.red, self.red2 = mode, red, red2
         self.cache = {}      # (device index, operand signature) -> (handle, output torch dtype[, second output's])
         self.ws_bytes = {}   # (handle value, n) -> scratch bytes of a fold / scan launch
@@ -428,14 +429,18 @@ class FastStage:
                 else:
                     kinds.append(_lib.ARG_SCALAR)
                     dts.append(_lib.F64 if x is float else _lib.I64)
-            if self.code2:
+            if self.code3:
+                ent = _compile_epi(lib, dev, self.code, self.code2, self.code3, tuple(kinds), tuple(dts), self.red, self.red2)
+            elif self.code2:
                 ent = _compile_pair(lib, dev, self.code, self.code2, tuple(kinds), tuple(dts), self.red, self.red2)
             else:
                 h, od, out_td = _compile_handle(lib, dev, self.code, (), tuple(kinds), tuple(dts), mode, self.red, self.red2)
                 ent = (h, out_td)
             self.cache[key] = ent
         h, out_td = ent[0], ent[1]
-        if self.code2:
+        if self.code3:
+            out = torch.empty((), dtype=out_td, device=dev)
+        elif self.code2:
             out = torch.empty(2, dtype=torch.int64, device=dev)   # two 8-byte results side by side
         else:
             out = torch.empty(() if scalar_out else (n,), dtype=out_td, device=dev)
@@ -456,11 +461,30 @@ class FastStage:
         rc = lib.kgb_expr_launch_ex(h, argv, n, out.data_ptr(), ws_ptr, wsb, stream, _lib.LAUNCH_WS_CLEAN)
         if rc:
             _lib.check(rc, "kgb_expr_launch")
-        if self.code2:
+        if self.code2 and not self.code3:
             a0, a1 = out.unbind(0)
             return (DeviceArray(a0 if out_td is torch.int64 else a0.view(out_td)),
                     DeviceArray(a1 if ent[2] is torch.int64 else a1.view(ent[2])))
         return DeviceArray(out)
+
+
+def _compile_epi(lib, device, code_t, code2_t, code3_t, kinds, dts, red, red2):
+    """(handle, torch dtype of the single result) of a two-output fold with an epilogue over both folds."""
+    key = (device.index, code_t, code2_t, code3_t, kinds, dts, _lib.MODE_REDUCE, red, red2, "epi")
+    ent = _handles.get(key)
+    if ent is None:
+        n_args = len(kinds)
+        h = ctypes.c_void_p()
+        od = ctypes.c_int32()
+        _lib.check(lib.kgb_expr_compile_epi((ctypes.c_int32 * len(code_t))(*code_t), len(code_t),
+                                            (ctypes.c_int32 * len(code2_t))(*code2_t), len(code2_t),
+                                            (ctypes.c_int32 * len(code3_t))(*code3_t), len(code3_t),
+                                            (ctypes.c_int32 * max(n_args, 1))(*kinds), (ctypes.c_int32 * max(n_args, 1))(*dts),
+                                            n_args, _lib.MODE_REDUCE, red, red2, ctypes.byref(h), ctypes.byref(od)),
+                   "kgb_expr_compile_epi")
+        ent = (h, _K2T[od.value])
+        _handles[key] = ent
+    return ent
 
 
 def _compile_pair(lib, device, code_t, code2_t, kinds, dts, red, red2):

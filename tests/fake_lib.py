@@ -234,6 +234,20 @@ class FakeLib:
         od._obj.value = _CODE[e.out]
         return 0
 
+    def kgb_expr_compile_epi(self, code, n_code, code2, n_code2, code3, n_code3, kinds, dtypes, n_args, mode, red, red2, h, od):
+        rc = self.kgb_expr_compile(code, n_code, code2, n_code2, kinds, dtypes, n_args, mode, red, red2, h, od)
+        if rc or code3 is None or not n_code3:
+            return rc
+        e = self.exprs[h._obj.value - 1]
+        if e.out2 is None:
+            self.err = b"fake compile: an epilogue program needs a two-output reduce"
+            return -1
+        e.code3 = list(code3[:n_code3])
+        r = np.asarray(run_program(e.code3, [np.ones((), dtype=e.out)[()], np.ones((), dtype=e.out2)[()]]))
+        e.out3 = r.dtype if r.dtype in _CODE else (np.dtype(np.int64) if r.dtype.kind in "iu" else np.dtype(np.float64))
+        od._obj.value = _CODE[e.out3]
+        return 0
+
     def kgb_expr_infer(self, code, n_code, kinds, dtypes, n_args, od):
         try:
             e = _Expr(list(code[:n_code]), None, list(kinds[:n_args]), list(dtypes[:n_args]), 0, 0, 0)
@@ -245,7 +259,7 @@ class FakeLib:
 
     def kgb_expr_out_dtype2(self, h):
         e = self.exprs[_addr(h) - 1]
-        return -1 if e.out2 is None else _CODE[e.out2]
+        return -1 if e.out2 is None or getattr(e, "code3", None) else _CODE[e.out2]
 
     def kgb_expr_workspace_bytes(self, h, n, out):
         out._obj.value = 64
@@ -274,10 +288,15 @@ class FakeLib:
                     return 0
                 v = np.broadcast_to(np.asarray(v), (n,)).astype(e.acc)
                 if e.mode == 1:
-                    view(out, 1, _CODE[e.out])[0] = _RED[e.red].reduce(v)
+                    r1 = _RED[e.red].reduce(v)
                     if e.out2 is not None:
                         vb = np.broadcast_to(np.asarray(run_program(e.code2, args)), (n,)).astype(e.out2)
-                        view(_addr(out) + 8, 1, _CODE[e.out2])[0] = _RED[e.red2].reduce(vb)
+                        r2 = _RED[e.red2].reduce(vb)
+                        if getattr(e, "code3", None):
+                            view(out, 1, _CODE[e.out3])[0] = np.asarray(run_program(e.code3, [e.out.type(r1), e.out2.type(r2)])).astype(e.out3)
+                            return 0
+                        view(_addr(out) + 8, 1, _CODE[e.out2])[0] = r2
+                    view(out, 1, _CODE[e.out])[0] = r1
                 elif e.mode == 2:
                     if e.code2:
                         v = v.copy()

@@ -873,3 +873,29 @@ def test_range_direct_address_path(be, K, case):
     got = host(K.unique_first(K.asarray(k)))
     want = O.range_unique(k)
     assert got.dtype == k.dtype and np.array_equal(got, want), case
+
+
+@pytest.mark.gpu
+def test_two_folds_with_epilogue_single_kernel(cuda_backend):
+    """`(+/p*s)%+/s` and relatives through kgb_expr_compile_epi (both folds + the epilogue in ONE kernel) against NumPy:
+    float64 to 1e-12, integer folds exact, min / max folds bit-exact, at a size with many CTAs and at a tiny one."""
+    be = cuda_backend
+    rng = np.random.default_rng(31)
+    vwap = ("binop", "%", ("reduce", "+", ("binop", "*", ("var", "_v0"), ("var", "_v1"))), ("reduce", "+", ("var", "_v1")))
+    spread = ("binop", "-", ("reduce", "|", ("var", "_v0")), ("reduce", "&", ("var", "_v1")))
+    scaled = ("binop", "+", ("binop", "*", ("reduce", "+", ("var", "_v0")), ("literal", 3)), ("reduce", "+", ("var", "_v1")))
+    f_vwap, _ = be.compile_expr_ir(vwap, ["p", "s"])
+    f_spread, _ = be.compile_expr_ir(spread, ["a", "b"])
+    f_scaled, _ = be.compile_expr_ir(scaled, ["a", "b"])
+    for n in (7, 100_000, 1_500_001):
+        p, s = rng.random(n) * 100, rng.random(n) + 0.5
+        P, S = be.kg_asarray(p), be.kg_asarray(s)
+        ref = np.add.reduce(p * s) / np.add.reduce(s)
+        got = f_vwap(P, S)
+        assert got.dtype == np.float64 and abs(got.item() - ref) <= 1e-12 * abs(ref), n
+        assert f_spread(P, S).item() == np.max(p) - np.min(s), n
+        pi, si = rng.integers(-1000, 1000, n), rng.integers(1, 9, n)
+        PI, SI = be.kg_asarray(pi), be.kg_asarray(si)
+        assert f_scaled(PI, SI).item() == int(np.add.reduce(pi)) * 3 + int(np.add.reduce(si)), n
+        gi = f_vwap(PI, SI)
+        assert gi.dtype == np.float64 and gi.item() == np.add.reduce(pi * si) / np.add.reduce(si), n

@@ -311,3 +311,39 @@ def test_find_with_a_list_needle(interp):
     got = b200("m?b")
     assert isinstance(got, mod.DeviceArray)
     assert np.array_equal(got.to_numpy(), np.flatnonzero((m == m[17]).all(axis=1)))
+
+
+def test_two_folds_and_their_epilogue_are_one_launch(fake_backend):
+    """`(+/p*s)%+/s` (compiler.py's VWAP example): both sums share one pass AND the divide runs in the fold kernel's last
+    CTA (kgb_expr_compile_epi) — one launch for small vectors; operands the pre-resolved launcher does not take (a float32
+    vector: narrow accumulator) still give the right answer through the general stages."""
+    import klongpy_b200
+    be = fake_backend
+    lib = klongpy_b200._lib._host_double
+    ir = ("binop", "%", ("reduce", "+", ("binop", "*", ("var", "_v0"), ("var", "_v1"))), ("reduce", "+", ("var", "_v1")))
+    fn, _ = be.compile_expr_ir(ir, ["p", "s"])
+    rng = np.random.default_rng(2)
+    p, s = rng.random(1000), rng.random(1000) + 0.5
+    P, S = be.kg_asarray(p), be.kg_asarray(s)
+    calls = {"n": 0}
+    orig = lib.kgb_expr_launch
+
+    def counting(*a, **k):
+        calls["n"] += 1
+        return orig(*a, **k)
+
+    lib.kgb_expr_launch = counting
+    try:
+        r = fn(P, S)
+    finally:
+        lib.kgb_expr_launch = orig
+    assert calls["n"] == 1
+    assert abs(r.item() - np.add.reduce(p * s) / np.add.reduce(s)) <= 1e-12 * abs(r.item())
+    # integer operands: the epilogue divides in float64 like NumPy
+    pi, si = rng.integers(1, 50, 777), rng.integers(1, 9, 777)
+    ri = fn(be.kg_asarray(pi), be.kg_asarray(si))
+    assert ri.dtype == np.float64 and ri.item() == np.add.reduce(pi * si) / np.add.reduce(si)
+    # (+/a) - (+/a)*2 style trees that use a fold twice, and literals in the epilogue
+    ir2 = ("binop", "-", ("binop", "*", ("reduce", "+", ("var", "_v0")), ("literal", 2)), ("reduce", "|", ("var", "_v1")))
+    fn2, _ = be.compile_expr_ir(ir2, ["a", "b"])
+    assert abs(fn2(P, S).item() - (np.add.reduce(p) * 2 - np.max(s))) <= 1e-12 * np.add.reduce(p)
