@@ -16,6 +16,7 @@ expressions need no exchange.  The primitives with a real exchange step:
   * find `a?b` : local compaction -> all_gather of (shard length, hit count) -> global positions (sharded_find).
   * grade `<a >a` : sample sort — composite (key, position) splitters, one variable-size all_to_all of (key, position)
     pairs, a local stable sort, one all_to_all of positions back to the block partition (sharded_argsort).
+  * group `=a` : the same sample sort + boundaries of each rank's sorted piece, merged across pieces (sharded_group).
   * range `?a` : the ranks' own answers concatenated in rank order, then `?` of that (sharded_range).
   * autograd : the loss `+/` is a sharded reduce whose tape holds only the local fused node (sharded_loss_sum);
     vector gradients stay sharded, scalar-parameter gradients are summed rank-ordered (combine_param_grads).
@@ -211,7 +212,20 @@ def _exchange(send, send_counts, recv_counts):
     return recv
 
 
-def sharded_argsort(a, descending=False, samples_per_rank=1024):
+def sharded_group(a, samples_per_rank=1024):
+    """`=a` of a block-sharded vector (monads.py:182-204) in CSR form: (this rank's block of the
+    GLOBAL order — global positions, grouped by ascending key, ascending within a group; partitioned like the input —,
+    the group start offsets into the global order, replicated on every rank (G + 1 entries), G).
+
+    The sample sort of `sharded_argsort` leaves every rank with a contiguous piece of the globally sorted sequence; the
+    group boundaries inside a piece come from the local `=` of its keys, a piece's first group is merged with the
+    previous piece's last one when they carry the same key (one all_gather of each piece's first / last key), and the
+    boundary lists meet in one (padded) all_gather."""
+    order, info = sharded_argsort(a, samples_per_rank=samples_per_rank, _group=True)
+    return order, info[0], info[1]
+
+
+def sharded_argsort(a, descending=False, samples_per_rank=1024, _group=False):
     """Grade of a block-sharded vector: this rank's block of the GLOBAL stable permutation (global
     positions; the blocks are partitioned like the input).  Sample sort:
 
@@ -227,6 +241,9 @@ def sharded_argsort(a, descending=False, samples_per_rank=1024):
     `descending` follows the language contract: the reversed stable ascending permutation (writer.py:97-108)."""
     w, r = world(), rank()
     if w == 1:
+        if _group:
+            o, st, g = ops.group(a)
+            return o, (st, g)
         return ops.argsort(a, descending=descending)
     dev = a._t.device
     n_local = a.size
@@ -257,7 +274,8 @@ def sharded_argsort(a, descending=False, samples_per_rank=1024):
     order = ops.argsort(all_k)                       # samples are in ascending position order per rank: stable = composite
     m = all_k.size
     if m == 0:
-        return DeviceArray(torch.empty(0, dtype=torch.int64, device=dev))
+        empty = DeviceArray(torch.empty(0, dtype=torch.int64, device=dev))
+        return (empty, (DeviceArray(torch.zeros(1, dtype=torch.int64, device=dev)), 0)) if _group else empty
     qs = ops.asarray(np.minimum((np.arange(1, w) * m) // w, m - 1).astype(np.int64), device=dev)
     at = ops.gather(order, qs)
     split_k, split_p = ops.gather(all_k, at).to_numpy(), ops.gather(all_p, at).to_numpy()
@@ -286,13 +304,43 @@ def sharded_argsort(a, descending=False, samples_per_rank=1024):
     recv_k = _exchange(send_k, mat[r, :], mat[:, r])
     recv_p = _exchange(send_p, mat[r, :], mat[:, r])
     # ---- 3. local stable sort by key, then back to the block partition
-    if recv_k.numel():
+    held = mat.sum(axis=0)                           # elements each rank holds after the exchange
+    my_off = int(held[:r].sum())
+    group_info = None
+    if _group:
+        # boundaries of this piece (local `=`), shifted to global offsets; the piece's first group continues the previous
+        # non-empty piece's last one when the keys agree (NaN keys all fall into one group, like the local kernel)
+        if recv_k.numel():
+            local, lstarts, lg = ops.group(DeviceArray(recv_k))
+            chunk = ops.gather(DeviceArray(recv_p), local)._t
+            first_k, last_k = recv_k[local._t[0]].reshape(1), recv_k[local._t[-1]].reshape(1)
+            bounds = lstarts._t[:lg] + my_off
+        else:
+            chunk = recv_p
+            first_k = last_k = torch.zeros(1, dtype=recv_k.dtype, device=dev)
+            bounds = torch.empty(0, dtype=torch.int64, device=dev)
+        ends = torch.empty(2 * w, dtype=recv_k.dtype, device=dev)
+        td.all_gather_into_tensor(ends, torch.cat([first_k, last_k]))
+        ends = ends.reshape(w, 2).cpu().numpy()
+        prev = [q for q in range(r) if held[q] > 0]
+        if bounds.numel() and prev:
+            pk, fk = ends[prev[-1], 1], ends[r, 0]
+            if pk == fk or (pk != pk and fk != fk):
+                bounds = bounds[1:]
+        bc = _all_counts(torch.tensor([bounds.numel()] * w, dtype=torch.int64, device=dev))[:, 0]
+        cap = max(int(bc.max()), 1)
+        padb = torch.zeros(cap, dtype=torch.int64, device=dev)
+        padb[: bounds.numel()] = bounds
+        allb = torch.empty(w * cap, dtype=torch.int64, device=dev)
+        td.all_gather_into_tensor(allb, padb)
+        validb = torch.cat([torch.arange(cap, device=dev) < int(c) for c in bc])
+        starts = torch.cat([allb[validb], torch.tensor([n_global], dtype=torch.int64, device=dev)])
+        group_info = (DeviceArray(starts), int(starts.numel()) - 1)
+    elif recv_k.numel():
         local = ops.argsort(DeviceArray(recv_k))
         chunk = ops.gather(DeviceArray(recv_p), local)._t
     else:
         chunk = recv_p
-    held = mat.sum(axis=0)                           # elements each rank holds after the exchange
-    my_off = int(held[:r].sum())
     if descending:
         chunk = ops.reverse(DeviceArray(chunk))._t if chunk.numel() else chunk
         my_off = n_global - my_off - int(held[r])    # reversed global order: this rank's chunk sits mirrored
@@ -312,6 +360,8 @@ def sharded_argsort(a, descending=False, samples_per_rank=1024):
             segs.append(out[o:o + c])
             o += c
         out = torch.cat(segs[::-1]) if segs else out
+    if _group:
+        return DeviceArray(out), group_info
     return DeviceArray(out)
 
 

@@ -51,6 +51,11 @@ for n in (1000, 1_000_003, 40_000_001):
         down = dist.sharded_argsort(be.kg_asarray(kk[lo:hi]), descending=True).to_numpy()
         assert np.array_equal(up, gref[lo:hi]) and np.array_equal(down, gref[::-1][lo:hi]), "sharded_argsort"
     assert np.array_equal(dist.sharded_range(be.kg_asarray(k[lo:hi])).to_numpy(), O.range_unique(k)), "sharded_range"
+    go, gs, gg = dist.sharded_group(be.kg_asarray(k[lo:hi]))       # `=a`: block of the global order + replicated starts
+    ginv = np.argsort(k, kind="stable")
+    gstarts = np.concatenate([[0], np.cumsum(np.bincount(k, minlength=G))])
+    gstarts = gstarts[np.concatenate([[True], np.diff(gstarts) > 0])] if n else gstarts[:1]
+    assert gg == len(gstarts) - 1 and np.array_equal(gs.to_numpy(), gstarts) and np.array_equal(go.to_numpy(), ginv[lo:hi]), "sharded_group"
     pos, counts = dist.sharded_find(be.kg_asarray(k[lo:hi]), 7)
     want = np.nonzero(k == 7)[0]
     find_ok = counts.sum() == len(want) and np.array_equal(pos.to_numpy(), want[(want >= lo) & (want < hi)])

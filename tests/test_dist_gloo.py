@@ -88,6 +88,11 @@ def _worker(rank, world, port, q):
             u = dist.sharded_range(be.kg_asarray(kk[lo:hi])).to_numpy()
             want_u = O.range_unique(kk)
             assert len(u) == len(want_u) and np.array_equal(u, want_u, equal_nan=True), (name, rank)
+            # group `=a` in CSR form: this rank's block of the global order + the replicated group starts
+            go, gs, gg = dist.sharded_group(be.kg_asarray(kk[lo:hi]))
+            want_o, want_s = O.group_csr(kk)
+            assert gg == len(want_s) - 1 and np.array_equal(gs.to_numpy(), want_s), (name, rank)
+            assert np.array_equal(go.to_numpy(), want_o[lo:hi]), (name, rank)
         # find: global positions of this rank's hits + every rank's count
         pos, counts = dist.sharded_find(I, 7)
         want = np.nonzero(i == 7)[0]
