@@ -36,6 +36,9 @@ constexpr int BRC_LOG2_SLOTS = 20;  // 32 MB; only the sectors of live names are
 constexpr u64 BRC_SLOTS = 1ull << BRC_LOG2_SLOTS;
 constexpr int BRC_NAME_BYTES = 256;                 // dictionary row: a name of <= 255 bytes as zero-extended 32-bit words
 constexpr int BRC_NAME_WORDS = BRC_NAME_BYTES / 4;
+#ifndef KGB_BRC_MASK_LUT
+#define KGB_BRC_MASK_LUT 0  // 1: name byte masks from a 25-row shared table (two LDS per line) instead of clamped shifts
+#endif
 #ifndef KGB_BRC_BULK
 #define KGB_BRC_BULK 1  // 0: stage interior tiles through registers (LDG + STS) instead of cp.async.bulk
 #endif
@@ -226,10 +229,14 @@ __global__ void __launch_bounds__(T, CTAS) brc_onepass_kernel(const unsigned cha
         s_misc[0] = (int)tk;
         s_misc[6] = bulk ? 1 : 0;
     }
+#if KGB_BRC_MASK_LUT
     if (tid < (BRC_INSLOT + 1) * 8) {
         const int rem = (tid >> 3) - 4 * (tid & 7);
         s_mlut[tid] = rem >= 4 ? 0xffffffffu : rem <= 0 ? 0u : (1u << (8 * rem)) - 1u;
     }
+#else
+    (void)s_mlut;
+#endif
     __syncthreads();
     const i64 tile = s_misc[0];
     const i64 byte0 = tile * TILE;
@@ -423,12 +430,23 @@ __global__ void __launch_bounds__(T, CTAS) brc_onepass_kernel(const unsigned cha
         const u32 a0 = up ? p0.y : p0.x, a1 = up ? p1.x : p0.y, a2 = up ? p1.y : p1.x, a3 = up ? p2.x : p1.y;
         const u32 a4 = up ? p2.y : p2.x, a5 = up ? p3.x : p2.y, a6 = up ? p3.y : p3.x;
         const u32 sh = (u32)(nb & 3) * 8;
+#if KGB_BRC_MASK_LUT
         const int lc = len < BRC_INSLOT ? len : BRC_INSLOT;
         const uint4 ma = *reinterpret_cast<const uint4*>(s_mlut + lc * 8);
         const uint2 mb = *reinterpret_cast<const uint2*>(s_mlut + lc * 8 + 4);
         const u32 x0 = __funnelshift_r(a0, a1, sh) & ma.x, x1 = __funnelshift_r(a1, a2, sh) & ma.y;
         const u32 x2 = __funnelshift_r(a2, a3, sh) & ma.z, x3 = __funnelshift_r(a3, a4, sh) & ma.w;
         const u32 x4 = __funnelshift_r(a4, a5, sh) & mb.x, x5 = __funnelshift_r(a5, a6, sh) & mb.y;
+#else
+        // byte masks of a name of `len` bytes without a table: word k keeps its low min(max(len - 4k, 0), 4) bytes =
+        // all-ones shifted right by max(32 (k + 1) - 8 len, 0) bits, the clamped funnel shift giving 0 from 32 bits on
+        const int t8 = -8 * len;
+#define KGB_BRC_M(k) __funnelshift_rc(0xffffffffu, 0u, (u32)max(t8 + 32 * ((k) + 1), 0))
+        const u32 x0 = __funnelshift_r(a0, a1, sh) & KGB_BRC_M(0), x1 = __funnelshift_r(a1, a2, sh) & KGB_BRC_M(1);
+        const u32 x2 = __funnelshift_r(a2, a3, sh) & KGB_BRC_M(2), x3 = __funnelshift_r(a3, a4, sh) & KGB_BRC_M(3);
+        const u32 x4 = __funnelshift_r(a4, a5, sh) & KGB_BRC_M(4), x5 = __funnelshift_r(a5, a6, sh) & KGB_BRC_M(5);
+#undef KGB_BRC_M
+#endif
         u64 h = (u64)(u32)len * 0x9e3779b1ull + 0x7f4a7c15f39cc060ull;
         h += (u64)x0 * 0x85ebca6bull;
         h += (u64)x1 * 0xc2b2ae35ull;
