@@ -657,6 +657,8 @@ extern "C" int kgb_brc_parse(const uint8_t* text, int64_t n_bytes, int64_t rows_
         case 3: KGB_BRC_GO(32768, 512, 3); break;
         case 4: KGB_BRC_GO(16384, 256, 6); break;
         case 5: KGB_BRC_GO(24576, 384, 4); break;
+        case 6: KGB_BRC_GO(65536, 512, 2); break;
+        case 7: KGB_BRC_GO(65536, 1024, 1); break;
         default: KGB_BRC_GO(65536, 768, 2); break;
     }
 #undef KGB_BRC_GO
