@@ -13,7 +13,7 @@
 //                     while the other warps expand.  Then line i goes to thread i mod T, so a warp reads ~5
 //                     consecutive 128-byte lines of text and writes its 16 bytes per row coalesced.  Per line: the
 //                     measurement is parsed backwards from the newline in fixed point; the name's first 24 bytes are
-//                     loaded unconditionally (seven aligned words, funnel-shifted, masked from a shared table),
+//                     loaded unconditionally (four 64-bit shared loads, funnel-shifted, masked by clamped shifts),
 //                     hashed multilinearly (one IMAD.WIDE per word) and resolved in an L2-resident open-addressing
 //                     table of 32-byte slots {tag | published | id | len, 24 name bytes}: a known name of <= 24
 //                     bytes costs ONE 256-bit load and six compares.  Longer names continue against the dictionary
